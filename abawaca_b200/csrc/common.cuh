@@ -1,0 +1,86 @@
+// Shared host/device helpers of libabawaca_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include "../../include/abawaca_b200.h"
+
+struct abw_ctx {
+	int          device = 0;
+	cudaStream_t stream = nullptr;
+	int          sm_count = 148;
+	uint64_t     launches = 0;
+	std::string  err;
+};
+
+inline int abw_fail(abw_ctx* ctx, int code, const std::string& msg)
+{
+	if(ctx)
+		ctx->err = msg;
+	return code;
+}
+
+#define ABW_CUDA(ctx, call)                                                                                          \
+	do {                                                                                                             \
+		cudaError_t e__ = (call);                                                                                    \
+		if(e__ != cudaSuccess) {                                                                                     \
+			char b__[512];                                                                                           \
+			snprintf(b__, sizeof(b__), "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));   \
+			return abw_fail((ctx), ABW_ERR_CUDA, b__);                                                               \
+		}                                                                                                            \
+	} while(0)
+
+#define ABW_CHECK(expr)                                                                                              \
+	do {                                                                                                             \
+		int r__ = (expr);                                                                                            \
+		if(r__ != ABW_OK)                                                                                            \
+			return r__;                                                                                              \
+	} while(0)
+
+// every launch goes through this so that abw_kernel_launches() is an honest count
+#define ABW_LAUNCH(ctx, kernel, grid, block, smem, ...)                                                              \
+	do {                                                                                                             \
+		kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                                             \
+		(ctx)->launches++;                                                                                           \
+		ABW_CUDA((ctx), cudaGetLastError());                                                                         \
+	} while(0)
+
+template <typename T>
+struct DevBuf {
+	T*     p = nullptr;
+	size_t n = 0;
+	DevBuf() {}
+	DevBuf(const DevBuf&) = delete;
+	DevBuf& operator=(const DevBuf&) = delete;
+	~DevBuf() { release(); }
+	void release()
+	{
+		if(p)
+			cudaFree(p);
+		p = nullptr;
+		n = 0;
+	}
+	cudaError_t alloc(size_t count)
+	{
+		release();
+		n = count;
+		return cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+	}
+};
+
+static inline unsigned int abw_div_up(uint64_t a, uint64_t b) { return (unsigned int)((a + b - 1) / b); }
+
+// ---- device-wide primitives implemented in scan_sort.cu -------------------------------------------
+// exclusive prefix sum of n uint64 values (in place allowed); d_total (may be null) receives the sum
+int abw_exclusive_scan_u64(abw_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n, uint64_t* d_total);
+// exclusive prefix sum of uint32 inputs into uint64 outputs
+int abw_exclusive_scan_u32_to_u64(abw_ctx* ctx, const uint32_t* d_in, uint64_t* d_out, uint64_t n, uint64_t* d_total);
+
+// Stable LSD radix sort of `batch` independent arrays of n (key, value) pairs each (array b at offset b*stride).
+// Only key bits [0, nbits) are examined.  Result is left in (keys, vals); (keys_tmp, vals_tmp) are scratch of the same size.
+// Passes in which every key of every array shares the same digit are skipped.
+int abw_radix_sort_pairs_u64(abw_ctx* ctx, uint64_t* d_keys, uint64_t* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, uint32_t batch,
+                             uint64_t stride, int nbits);
+int abw_radix_sort_pairs_u32(abw_ctx* ctx, uint32_t* d_keys, uint32_t* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, int nbits);

@@ -1,0 +1,118 @@
+// Context, error text and raw device-memory helpers of the C ABI.
+#include "common.cuh"
+
+extern "C" {
+
+const char* abw_version(void) { return "abawaca_b200 0.1 (sm_100a)"; }
+
+void abw_default_params(abw_params* p)
+{
+	if(!p)
+		return;
+	p->cluster_ndps_threshold = 100;
+	p->sensitivity_threshold = 0.8;
+	p->specificity_threshold = 0.8;
+	p->product_threshold = 0.8;
+	p->sum_threshold = 1.6;
+	p->scg_overlap_threshold = 0.2;
+	p->scg_min_size = 500000;
+	p->fraction_dps_in = 0.8;
+	p->split_scaf_ratio_threshold = 0.1;
+	p->max_snps = 15;
+	p->window_size = 2000;
+	p->min_reported_score = 0.8;
+}
+
+int abw_ctx_create(int device, abw_ctx** out)
+{
+	if(!out)
+		return ABW_ERR_ARG;
+	*out = nullptr;
+	int ndev = 0;
+	if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return ABW_ERR_CUDA;        // no CPU fallback: without a device there is no context
+	if(device < 0 || device >= ndev)
+		return ABW_ERR_ARG;
+	if(cudaSetDevice(device) != cudaSuccess)
+		return ABW_ERR_CUDA;
+	abw_ctx* c = new abw_ctx();
+	c->device = device;
+	if(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+		delete c;
+		return ABW_ERR_CUDA;
+	}
+	cudaDeviceProp prop;
+	if(cudaGetDeviceProperties(&prop, device) == cudaSuccess)
+		c->sm_count = prop.multiProcessorCount;
+	*out = c;
+	return ABW_OK;
+}
+
+void abw_ctx_destroy(abw_ctx* ctx)
+{
+	if(!ctx)
+		return;
+	cudaSetDevice(ctx->device);
+	if(ctx->stream)
+		cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+const char* abw_last_error(const abw_ctx* ctx) { return ctx? ctx->err.c_str() : "no context (is a CUDA device present?)"; }
+
+uint64_t abw_kernel_launches(const abw_ctx* ctx) { return ctx? ctx->launches : 0; }
+
+void* abw_ctx_stream(const abw_ctx* ctx) { return ctx? (void*)ctx->stream : nullptr; }
+
+int abw_ctx_synchronize(abw_ctx* ctx)
+{
+	if(!ctx)
+		return ABW_ERR_ARG;
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return ABW_OK;
+}
+
+int abw_device_alloc(abw_ctx* ctx, size_t bytes, void** d_out)
+{
+	if(!ctx || !d_out)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_device_alloc: null argument");
+	ABW_CUDA(ctx, cudaSetDevice(ctx->device));
+	ABW_CUDA(ctx, cudaMalloc(d_out, bytes? bytes : 1));
+	return ABW_OK;
+}
+
+int abw_device_free(abw_ctx* ctx, void* d_ptr)
+{
+	if(!ctx)
+		return ABW_ERR_ARG;
+	ABW_CUDA(ctx, cudaFree(d_ptr));
+	return ABW_OK;
+}
+
+int abw_copy_to_device(abw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes)
+{
+	if(!ctx)
+		return ABW_ERR_ARG;
+	ABW_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return ABW_OK;
+}
+
+int abw_copy_to_host(abw_ctx* ctx, void* h_dst, const void* d_src, size_t bytes)
+{
+	if(!ctx)
+		return ABW_ERR_ARG;
+	ABW_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return ABW_OK;
+}
+
+int abw_memset_device(abw_ctx* ctx, void* d_ptr, int byte, size_t bytes)
+{
+	if(!ctx)
+		return ABW_ERR_ARG;
+	ABW_CUDA(ctx, cudaMemsetAsync(d_ptr, byte, bytes, ctx->stream));
+	return ABW_OK;
+}
+
+}  // extern "C"

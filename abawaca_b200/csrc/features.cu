@@ -1,0 +1,780 @@
+// Feature stage of abawaca-build on the device: 2-bit packing, windowing, k-mer signatures, coverage.
+//
+// Data layout in HBM (abw_seqset): every scaffold starts at a base offset that is a multiple of 128, so that
+//   packed : 2 bits/base, 16 bases per u32, base i of the scaffold at bits [2*(i%16), +2) of word base/16+i/16
+//            (A=0 C=1 G=2 T=3; non-ACGT positions hold 0),
+//   valid  : 1 bit/base, set for A/C/G/T (after upper-casing),
+//   nmask  : 1 bit/base, set for the literal 'N' only (quirk Q2: IUPAC codes are bases for windowing, but break k-mers)
+// are all 16-byte aligned per scaffold and can be fetched with 128-bit loads.
+#include "common.cuh"
+#include <algorithm>
+
+struct abw_seqset {
+	uint32_t nscaf = 0;
+	uint64_t total_padded = 0;            // bases
+	DevBuf<uint64_t> len, base;           // [nscaf], [nscaf+1]
+	DevBuf<uint32_t> packed, valid, nmask;
+	DevBuf<unsigned long long> countN, countGC;
+	std::vector<uint64_t> h_len, h_base;
+};
+
+struct abw_segments {
+	uint32_t nscaf = 0;
+	uint64_t nseg = 0;
+	DevBuf<uint64_t> seg_first;           // [nscaf+1]
+	DevBuf<uint32_t> seg_scaf;            // [nseg]
+	DevBuf<uint64_t> seg_start, seg_end, seg_nonN;   // 1-based inclusive, abawaca-build.cpp:216
+	DevBuf<uint64_t> seg_gbase;           // absolute (padded) base index of the first base of the segment
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// pack
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gather_bits_0_8_16_24(uint32_t v)   // bit0 of each byte -> 4 bits
+{
+	uint32_t t = (v | (v >> 7)) & 0x00030003u;
+	return (t | (t >> 14)) & 0xFu;
+}
+
+// 4 ASCII characters -> 8 bits of 2-bit codes + 4 valid bits + 4 N bits (+ GC count, + lower-case-n flag)
+__device__ __forceinline__ void classify4(uint32_t w, uint32_t& code8, uint32_t& valid4, uint32_t& n4, uint32_t& gc, uint32_t& bad)
+{
+	bad |= __vcmpeq4(w, 0x6E6E6E6Eu);                       // 'n' throws in the reference (String.cpp:47-49)
+	// toupper() for letters only (String.cpp:44); bytes outside a-z are left alone
+	uint32_t is_lower = __vcmpgeu4(w, 0x61616161u) & __vcmpleu4(w, 0x7A7A7A7Au);
+	uint32_t u = w & ~(is_lower & 0x20202020u);
+	uint32_t eA = __vcmpeq4(u, 0x41414141u), eC = __vcmpeq4(u, 0x43434343u), eG = __vcmpeq4(u, 0x47474747u), eT = __vcmpeq4(u, 0x54545454u);
+	uint32_t eN = __vcmpeq4(u, 0x4E4E4E4Eu);
+	uint32_t lo = (eC | eT) & 0x01010101u, hi = (eG | eT) & 0x01010101u;
+	uint32_t x = lo | (hi << 1);                            // one 2-bit code per byte
+	uint32_t y = (x | (x >> 6)) & 0x000F000Fu;
+	code8 = (y | (y >> 12)) & 0xFFu;
+	valid4 = gather_bits_0_8_16_24((eA | eC | eG | eT) & 0x01010101u);
+	n4 = gather_bits_0_8_16_24(eN & 0x01010101u);
+	gc += __popc((eC | eG) & 0x01010101u);
+}
+
+// one warp per scaffold, one lane per 32-base unit
+__global__ void __launch_bounds__(256) k_pack(const unsigned char* __restrict__ ascii, uint64_t ascii_bytes, const uint64_t* __restrict__ offsets,
+                                              const uint64_t* __restrict__ base, uint32_t nscaf, uint32_t* __restrict__ packed, uint32_t* __restrict__ valid,
+                                              uint32_t* __restrict__ nmask, unsigned long long* __restrict__ countN, unsigned long long* __restrict__ countGC,
+                                              int* __restrict__ err)
+{
+	const int lane = threadIdx.x & 31;
+	const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	for(uint64_t s = warp0; s < nscaf; s += nwarps) {
+		const uint64_t off = offsets[s], len = offsets[s + 1] - off, b0 = base[s], units = (base[s + 1] - b0) >> 5;
+		uint32_t nN = 0, nGC = 0, bad = 0;
+		for(uint64_t u = lane; u < units; u += 32) {
+			uint64_t p = u << 5;                            // first base of the unit within the scaffold
+			uint32_t code_lo = 0, code_hi = 0, v = 0, nm = 0;
+			if(p < len) {
+				uint64_t a = off + p;
+				uint32_t cnt = (uint32_t)min((uint64_t)32, len - p);
+				uint32_t w[8];
+				if(cnt == 32 && ((a & ~3ull) + 36 <= ascii_bytes)) {
+					const uint32_t* src = (const uint32_t*)(ascii + (a & ~3ull));
+					uint32_t sh = (uint32_t)(a & 3) * 8;
+					uint32_t t[9];
+#pragma unroll
+					for(int i = 0; i < 9; i++)
+						t[i] = __ldg(src + i);
+#pragma unroll
+					for(int i = 0; i < 8; i++)
+						w[i] = __funnelshift_r(t[i], t[i + 1], sh);
+				}
+				else {
+#pragma unroll
+					for(int i = 0; i < 8; i++) {
+						uint32_t x = 0;
+#pragma unroll
+						for(int j = 0; j < 4; j++) {
+							uint32_t k = i * 4 + j;
+							uint32_t c = (k < cnt)? (uint32_t)ascii[a + k] : 0u;
+							x |= c << (8 * j);
+						}
+						w[i] = x;
+					}
+				}
+#pragma unroll
+				for(int i = 0; i < 8; i++) {
+					uint32_t c8, v4, n4;
+					classify4(w[i], c8, v4, n4, nGC, bad);
+					if(i < 4) code_lo |= c8 << (8 * i); else code_hi |= c8 << (8 * (i - 4));
+					v |= v4 << (4 * i);
+					nm |= n4 << (4 * i);
+				}
+				nN += __popc(nm);
+			}
+			uint64_t unit = (b0 >> 5) + u;
+			packed[2 * unit] = code_lo;
+			packed[2 * unit + 1] = code_hi;
+			valid[unit] = v;
+			nmask[unit] = nm;
+		}
+#pragma unroll
+		for(int o = 16; o > 0; o >>= 1) {
+			nN += __shfl_xor_sync(0xffffffffu, nN, o);
+			nGC += __shfl_xor_sync(0xffffffffu, nGC, o);
+			bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+		}
+		if(lane == 0) {
+			countN[s] = nN;
+			countGC[s] = nGC;
+			if(bad)
+				atomicExch(err, 1);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// windowing, abawaca-build.cpp:198-228
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void window_plan(uint64_t len, uint64_t nN, uint64_t window, uint64_t& nbps, uint64_t& count)
+{
+	uint64_t nonN = len - nN;
+	uint64_t nsegments = nonN / window;                     // :202
+	if(nsegments == 0)
+		nsegments = 1;                                      // :204-205
+	nbps = nonN / nsegments;                                // :206
+	// a window closes every time nbps non-N characters were seen (:210-224); with no non-N base at all the
+	// test `nbps_segment == nbps` is 0 == 0 at every character, so every character becomes a window
+	count = (nbps > 0)? nonN / nbps : len;
+}
+
+__global__ void k_seg_count(const uint64_t* __restrict__ len, const unsigned long long* __restrict__ countN, uint32_t nscaf, uint64_t window, uint64_t* __restrict__ counts)
+{
+	uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if(s < nscaf) {
+		uint64_t nbps, count;
+		window_plan(len[s], countN[s], window, nbps, count);
+		counts[s] = count;
+	}
+}
+
+// one warp per scaffold walks the N mask; window j ends at the (j*nbps)-th non-N character
+__global__ void __launch_bounds__(256) k_seg_fill(const uint64_t* __restrict__ len, const unsigned long long* __restrict__ countN, const uint64_t* __restrict__ base,
+                                                  const uint32_t* __restrict__ nmask, uint32_t nscaf, uint64_t window, const uint64_t* __restrict__ seg_first,
+                                                  uint32_t* __restrict__ seg_scaf, uint64_t* __restrict__ seg_start, uint64_t* __restrict__ seg_end,
+                                                  uint64_t* __restrict__ seg_nonN, uint64_t* __restrict__ seg_gbase)
+{
+	const int lane = threadIdx.x & 31;
+	const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	for(uint64_t s = warp0; s < nscaf; s += nwarps) {
+		const uint64_t L = len[s], b0 = base[s], first = seg_first[s];
+		uint64_t nbps, count;
+		window_plan(L, countN[s], window, nbps, count);
+		if(count == 0)
+			continue;
+		if(nbps == 0) {
+			for(uint64_t i = lane; i < count; i += 32) {
+				seg_scaf[first + i] = (uint32_t)s;
+				seg_start[first + i] = i + 1;
+				seg_end[first + i] = i + 1;
+				seg_nonN[first + i] = 0;
+				seg_gbase[first + i] = b0 + i;
+			}
+			continue;
+		}
+		if(lane == 0) {
+			seg_start[first] = 1;
+			seg_gbase[first] = b0;
+		}
+		for(uint64_t i = lane; i < count; i += 32) {
+			seg_scaf[first + i] = (uint32_t)s;
+			seg_nonN[first + i] = nbps;
+		}
+		const uint64_t units = (L + 31) >> 5;
+		uint64_t carry = 0;
+		for(uint64_t u0 = 0; u0 < units; u0 += 32) {
+			uint64_t u = u0 + lane;
+			uint32_t bits = 0;
+			if(u < units) {
+				uint32_t in_range = (L - (u << 5) >= 32)? 0xFFFFFFFFu : ((1u << (uint32_t)(L - (u << 5))) - 1u);
+				bits = ~nmask[(b0 >> 5) + u] & in_range;
+			}
+			uint32_t c = __popc(bits), incl = c;
+#pragma unroll
+			for(int o = 1; o < 32; o <<= 1) {
+				uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+				if(lane >= o)
+					incl += t;
+			}
+			uint64_t before = carry + incl - c, after = carry + incl;
+			for(uint64_t j = before / nbps + 1; j * nbps <= after && j <= count; j++) {
+				uint32_t k = (uint32_t)(j * nbps - before);          // the k-th set bit of this word closes window j
+				uint32_t bit = __fns(bits, 0, k);
+				uint64_t pos1 = (u << 5) + bit + 1;                   // 1-based, :216
+				seg_end[first + j - 1] = pos1;
+				if(j < count) {
+					seg_start[first + j] = pos1 + 1;                  // :221-222
+					seg_gbase[first + j] = b0 + pos1;
+				}
+			}
+			carry += __shfl_sync(0xffffffffu, incl, 31);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k-mer signature, abawaca-build.cpp:103-174
+// ---------------------------------------------------------------------------------------------------
+// dimension tables: for each of the 180 canonical dims the k, and the two little-endian codes (mer, reverse complement)
+__constant__ uint8_t  c_dim_k[ABW_NKMER_DIMS];
+__constant__ uint16_t c_dim_code_a[ABW_NKMER_DIMS];
+__constant__ uint16_t c_dim_code_b[ABW_NKMER_DIMS];
+__constant__ double   c_milli[1001];                        // m / 1000.0
+
+constexpr int KM_WARPS = 8;
+constexpr int KM_WORDS_PER_LANE = 7;                        // 16-base words per lane per round: <= 112 increments per byte counter
+constexpr int KM_ROUND_WORDS = 32 * KM_WORDS_PER_LANE;      // 224 words = 3584 bases per round
+constexpr int KM_STAGE_WORDS = KM_ROUND_WORDS + 2;          // + lookahead word + alignment slack
+
+struct __align__(16) KmWarpSmem {
+	uint32_t hist[64 * 32];         // [3-mer row][lane] four byte counters (4th base) : 8 KB, bank = lane
+	uint32_t seq[KM_STAGE_WORDS + 2];
+	uint32_t val[KM_STAGE_WORDS / 2 + 4];
+	uint32_t cnt4[256];
+	uint32_t cnt3[64];
+	uint32_t cnt2[16];
+	uint32_t cnt1[4];
+	uint32_t tot[4];
+	uint32_t pad[2];
+};
+
+__device__ __forceinline__ uint32_t stream_bits(const uint32_t* __restrict__ a, uint64_t bitpos, uint32_t nbits_le32)
+{
+	// nbits (<= 32) bits of the little-endian bit stream `a` starting at bit `bitpos`
+	uint64_t w = bitpos >> 5;
+	uint32_t sh = (uint32_t)(bitpos & 31);
+	uint32_t lo = a[w], hi = a[w + 1];
+	uint32_t r = __funnelshift_r(lo, hi, sh);
+	return (nbits_le32 >= 32)? r : (r & ((1u << nbits_le32) - 1u));
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(KM_WARPS * 32) k_kmer(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid, const uint64_t* __restrict__ seg_gbase,
+                                                        const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end, uint64_t nseg, int skip_A,
+                                                        double* __restrict__ rows, uint64_t ld, uint32_t col0)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	KmWarpSmem* sm = reinterpret_cast<KmWarpSmem*>(smem_raw) + (threadIdx.x >> 5);
+	const int lane = threadIdx.x & 31;
+	for(int i = lane; i < 64 * 32; i += 32)
+		sm->hist[i] = 0;
+	__syncwarp();
+	const uint64_t warp0 = (uint64_t)blockIdx.x * KM_WARPS + (threadIdx.x >> 5), nwarps = (uint64_t)gridDim.x * KM_WARPS;
+	for(uint64_t g = warp0; g < nseg; g += nwarps) {
+		const uint64_t gb = seg_gbase[g];
+		const uint64_t L = seg_end[g] - seg_start[g] + 1;
+		for(int i = lane; i < 256; i += 32)
+			sm->cnt4[i] = 0;
+		for(int i = lane; i < 64 + 16 + 4 + 4; i += 32)
+			sm->cnt3[i] = 0;                                // cnt3, cnt2, cnt1, tot are contiguous
+		__syncwarp();
+		// rounds of at most KM_ROUND_WORDS 16-base words of the packed stream
+		const uint64_t word_first = gb >> 4;
+		const uint64_t nwords = ((gb + L + 15) >> 4) - word_first;
+		for(uint64_t w0 = 0; w0 < nwords; w0 += KM_ROUND_WORDS) {
+			const uint32_t rw = (uint32_t)min((uint64_t)KM_ROUND_WORDS, nwords - w0);
+			// stage packed words (+1 lookahead) and validity bits of [w0, w0+rw] into shared memory
+			for(uint32_t i = lane; i < rw + 1; i += 32)
+				sm->seq[i] = packed[word_first + w0 + i];
+			// validity as a bit stream aligned to the same 16-base words: 16 bits per word -> (rw+1)*16 bits
+			const uint64_t vbit0 = (word_first + w0) << 4;   // absolute base index of the first staged position
+			for(uint32_t i = lane; i < (rw + 1 + 1) / 2 + 1; i += 32) {
+				uint64_t p = vbit0 + ((uint64_t)i << 5);      // 32 positions
+				uint32_t v = valid[p >> 5];                   // vbit0 is a multiple of 16; p>>5 word, possibly half offset
+				uint32_t v2 = valid[(p >> 5) + 1];
+				v = __funnelshift_r(v, v2, (uint32_t)(p & 31));
+				// positions outside [gb, gb+L) never hold a base of this segment
+				uint64_t lo = (gb > p)? gb - p : 0, hi = (gb + L > p)? gb + L - p : 0;
+				uint32_t m_lo = (lo >= 32)? 0u : (0xFFFFFFFFu << (uint32_t)lo);
+				uint32_t m_hi = (hi >= 32)? 0xFFFFFFFFu : ((1u << (uint32_t)hi) - 1u);
+				sm->val[i] = v & m_lo & m_hi;
+			}
+			__syncwarp();
+			const uint32_t wpl = (rw + 31) >> 5;              // words per lane this round (<= KM_WORDS_PER_LANE)
+			uint32_t* myhist = sm->hist + lane;
+			for(uint32_t k = lane * wpl; k < min(rw, (lane + 1) * wpl); k++) {
+				const uint64_t win = (uint64_t)sm->seq[k] | ((uint64_t)sm->seq[k + 1] << 32);
+				const uint32_t v = stream_bits(sm->val, (uint64_t)k << 4, 19);   // 16 positions + 3 lookahead
+				const uint32_t v1 = v & 0xFFFFu, v2 = v & (v >> 1) & 0xFFFFu, v3 = v2 & (v >> 2), v4 = v3 & (v >> 3);
+				if(v4 == 0xFFFFu) {
+#pragma unroll
+					for(int t = 0; t < 16; t++) {
+						uint32_t x = (uint32_t)(win >> (2 * t)) & 0xFFu;
+						unsigned char* b = reinterpret_cast<unsigned char*>(myhist + (x & 63u) * 32) + (x >> 6);
+						*b = (unsigned char)(*b + 1);
+					}
+				}
+				else {
+					// windows broken by a non-ACGT character or by the end of the segment (:131,147 key = 0)
+					const uint32_t e3 = v3 & ~v4, e2 = v2 & ~v3, e1 = v1 & ~v2;
+#pragma unroll
+					for(int t = 0; t < 16; t++) {
+						uint32_t x = (uint32_t)(win >> (2 * t)) & 0xFFu;
+						if((v4 >> t) & 1u) {
+							unsigned char* b = reinterpret_cast<unsigned char*>(myhist + (x & 63u) * 32) + (x >> 6);
+							*b = (unsigned char)(*b + 1);
+						}
+						else if((e3 >> t) & 1u)
+							atomicAdd(&sm->cnt3[x & 63u], 1u);
+						else if((e2 >> t) & 1u)
+							atomicAdd(&sm->cnt2[x & 15u], 1u);
+						else if((e1 >> t) & 1u)
+							atomicAdd(&sm->cnt1[x & 3u], 1u);
+					}
+				}
+			}
+			__syncwarp();
+			// fold the 32 private histograms into cnt4 and clear them; lane handles 3-mer rows lane and lane+32
+#pragma unroll
+			for(int rr = 0; rr < 2; rr++) {
+				const int row = lane + 32 * rr;
+				uint4* rp = reinterpret_cast<uint4*>(sm->hist + row * 32);
+				uint32_t even = 0, odd = 0;
+#pragma unroll
+				for(int q = 0; q < 8; q++) {
+					int qq = (q + lane) & 7;                  // rotate so that a quarter warp touches 8 different 16-byte columns
+					uint4 w = rp[qq];
+					rp[qq] = make_uint4(0, 0, 0, 0);
+					uint32_t a = w.x + w.y, b = w.z + w.w;    // byte counters <= 112 each: no carry between bytes
+					even += (a & 0x00FF00FFu) + (b & 0x00FF00FFu);
+					odd += ((a >> 8) & 0x00FF00FFu) + ((b >> 8) & 0x00FF00FFu);
+				}
+				sm->cnt4[row] += even & 0xFFFFu;              // 4th base A
+				sm->cnt4[row + 64] += odd & 0xFFFFu;          // C
+				sm->cnt4[row + 128] += even >> 16;            // G
+				sm->cnt4[row + 192] += odd >> 16;             // T
+			}
+			__syncwarp();
+		}
+		// lower orders: every valid 4-mer start is a valid 3-mer start, etc.; cnt3/cnt2/cnt1 hold the run-end extras
+		{
+			uint32_t a = sm->cnt4[lane] + sm->cnt4[lane + 64] + sm->cnt4[lane + 128] + sm->cnt4[lane + 192];
+			uint32_t b = sm->cnt4[lane + 32] + sm->cnt4[lane + 96] + sm->cnt4[lane + 160] + sm->cnt4[lane + 224];
+			uint32_t t4 = a + b;
+#pragma unroll
+			for(int o = 16; o > 0; o >>= 1)
+				t4 += __shfl_xor_sync(0xffffffffu, t4, o);
+			sm->cnt3[lane] += a;
+			sm->cnt3[lane + 32] += b;
+			__syncwarp();
+			uint32_t c3a = sm->cnt3[lane], c3b = sm->cnt3[lane + 32];
+			uint32_t t3 = c3a + c3b;
+#pragma unroll
+			for(int o = 16; o > 0; o >>= 1)
+				t3 += __shfl_xor_sync(0xffffffffu, t3, o);
+			if(lane < 16)
+				sm->cnt2[lane] += sm->cnt3[lane] + sm->cnt3[lane + 16] + sm->cnt3[lane + 32] + sm->cnt3[lane + 48];
+			__syncwarp();
+			uint32_t c2 = (lane < 16)? sm->cnt2[lane] : 0u;
+			uint32_t t2 = c2;
+#pragma unroll
+			for(int o = 16; o > 0; o >>= 1)
+				t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+			if(lane < 4)
+				sm->cnt1[lane] += sm->cnt2[lane] + sm->cnt2[lane + 4] + sm->cnt2[lane + 8] + sm->cnt2[lane + 12];
+			__syncwarp();
+			uint32_t t1 = sm->cnt1[0] + sm->cnt1[1] + sm->cnt1[2] + sm->cnt1[3];
+			if(lane == 0) {
+				sm->tot[0] = t1; sm->tot[1] = t2; sm->tot[2] = t3; sm->tot[3] = t4;
+			}
+			__syncwarp();
+		}
+		// 180 canonical dimensions: dims[canon] += count/total for the mer and for its reverse complement (:171)
+		for(int d = lane; d < ABW_NKMER_DIMS; d += 32) {
+			const int k = c_dim_k[d];
+			const uint32_t* cnt = (k == 4)? sm->cnt4 : (k == 3)? sm->cnt3 : (k == 2)? sm->cnt2 : sm->cnt1;
+			const uint32_t ca = c_dim_code_a[d], cb = c_dim_code_b[d];
+			const uint32_t c1 = cnt[ca], c2 = (cb != ca)? cnt[cb] : 0u;
+			const uint32_t t = sm->tot[k - 1];
+			double out = 0.0;
+			if(t != 0 && (c1 + c2) != 0) {
+				if(KIND == ABW_FEAT_TRUNC3) {
+					// int(1000*(c1/t + c2/t)) equals floor(1000*(c1+c2)/t) whenever the quotient is not an integer: the rounding
+					// error of the three fp64 operations (< 1e-12) is far below the distance 1/t (t < 2^24) to the next integer
+					uint64_t num = 1000ull * (c1 + c2), m = num / t;
+					if(num - m * t != 0)
+						out = c_milli[m];
+					else {
+						double x = (c1? __ddiv_rn((double)c1, (double)(int)t) : 0.0);
+						if(c2)
+							x = __dadd_rn(x, __ddiv_rn((double)c2, (double)(int)t));
+						out = __ddiv_rn((double)__double2int_rz(__dmul_rn(1000.0, x)), 1000.0);
+					}
+				}
+				else {
+					double x = (c1? __ddiv_rn((double)c1, (double)(int)t) : 0.0);
+					if(c2)
+						x = __dadd_rn(x, __ddiv_rn((double)c2, (double)(int)t));
+					out = x;
+				}
+			}
+			if(!(skip_A && d == 0))
+				rows[g * ld + col0 + d - (skip_A? 1 : 0)] = out;
+		}
+		__syncwarp();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// coverage, abawaca-build.cpp:177-185, 231-244, 546-551
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool read_accepted(const abw_read& r, uint32_t max_snps, uint32_t nscaf)
+{
+	uint32_t flag = r.flag_nsnps & 0xFFFFu, nsnps = r.flag_nsnps >> 16;
+	return !((flag & 0x4u) || (nsnps > max_snps) || (flag & 0x100u)) && r.scaf < nscaf;   // :546-550
+}
+
+// first window of the scaffold whose end is >= s (windows before it are skipped by `continue`, :235-236)
+__device__ __forceinline__ uint64_t first_window_reaching(const uint64_t* __restrict__ seg_end, uint64_t f0, uint64_t f1, uint64_t s)
+{
+	uint64_t lo = f0, hi = f1;
+	while(lo < hi) {
+		uint64_t mid = (lo + hi) >> 1;
+		if(seg_end[mid] < s) lo = mid + 1; else hi = mid;
+	}
+	return lo;
+}
+
+__global__ void k_cov_count(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf, const uint64_t* __restrict__ seg_first,
+                            const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end, uint32_t* __restrict__ counts,
+                            unsigned long long* __restrict__ scaf_nbps)
+{
+	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(r >= nreads)
+		return;
+	abw_read rd = reads[r];
+	uint32_t c = 0;
+	if(read_accepted(rd, max_snps, nscaf)) {
+		uint64_t s = rd.pos0, e = (uint64_t)rd.pos0 + rd.len - 1;
+		uint64_t f1 = seg_first[rd.scaf + 1];
+		for(uint64_t g = first_window_reaching(seg_end, seg_first[rd.scaf], f1, s); g < f1 && !(e < seg_start[g]); g++)
+			c++;
+		if(scaf_nbps != nullptr)
+			atomicAdd(&scaf_nbps[rd.scaf], (unsigned long long)rd.len);     // integer: order free (:242-243)
+	}
+	counts[r] = c;
+}
+
+__global__ void k_cov_emit(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf, const uint64_t* __restrict__ seg_first,
+                           const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end, const uint64_t* __restrict__ offs,
+                           uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ per_seg)
+{
+	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(r >= nreads)
+		return;
+	abw_read rd = reads[r];
+	if(!read_accepted(rd, max_snps, nscaf))
+		return;
+	uint64_t s = rd.pos0, e = (uint64_t)rd.pos0 + rd.len - 1, o = offs[r];
+	uint64_t f1 = seg_first[rd.scaf + 1];
+	for(uint64_t g = first_window_reaching(seg_end, seg_first[rd.scaf], f1, s); g < f1 && !(e < seg_start[g]); g++) {
+		keys[o] = (uint32_t)g;
+		vals[o] = (uint32_t)r;
+		o++;
+		atomicAdd(&per_seg[g], 1u);
+	}
+}
+
+// one thread per window: the reads that hit it, in SAM order (the pairs were sorted stably by window)
+template <int KIND>
+__global__ void k_cov_accumulate(const abw_read* __restrict__ reads, const uint32_t* __restrict__ vals, const uint64_t* __restrict__ seg_off, uint64_t nseg,
+                                 const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end, double* __restrict__ rows, uint64_t ld, uint32_t col)
+{
+	uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(g >= nseg)
+		return;
+	const uint64_t st = seg_start[g], en = seg_end[g];
+	const double seglen = (double)(en - st + 1);
+	double acc = 0.0;
+	for(uint64_t i = seg_off[g]; i < seg_off[g + 1]; i++) {
+		abw_read rd = reads[vals[i]];
+		uint64_t s = rd.pos0, e = (uint64_t)rd.pos0 + rd.len - 1;
+		uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // 0-based read against 1-based window: quirk Q3, kept
+		acc = __dadd_rn(acc, __ddiv_rn((double)(e2 - s2 + 1), seglen));
+	}
+	if(KIND == ABW_FEAT_TRUNC3)
+		acc = __ddiv_rn((double)__double2int_rz(__dmul_rn(1000.0, acc)), 1000.0);
+	rows[g * ld + col] = acc;
+}
+
+bool g_tables_ready[64] = {};
+
+int upload_tables(abw_ctx* ctx)
+{
+	if(ctx->device >= 0 && ctx->device < 64 && g_tables_ready[ctx->device])
+		return ABW_OK;
+	uint8_t dk[ABW_NKMER_DIMS];
+	uint16_t da[ABW_NKMER_DIMS], db[ABW_NKMER_DIMS];
+	int next = 0;
+	int dim_of[5][256];
+	for(int k = 1; k <= 4; k++) {
+		int n = 1 << (2 * k);
+		for(int code = 0; code < n; code++) {              // big-endian code = lexicographic order, abawaca-build.cpp:90-99
+			int rc = 0, c = code;
+			for(int i = 0; i < k; i++) { rc = (rc << 2) | (3 - (c & 3)); c >>= 2; }
+			auto to_le = [k](int be) { int le = 0; for(int i = 0; i < k; i++) { le |= ((be >> (2 * (k - 1 - i))) & 3) << (2 * i); } return le; };
+			if(rc < code)
+				dim_of[k][code] = dim_of[k][rc];
+			else {
+				dim_of[k][code] = next;
+				dk[next] = (uint8_t)k;
+				da[next] = (uint16_t)to_le(code);
+				db[next] = (uint16_t)to_le(rc);
+				next++;
+			}
+		}
+	}
+	if(next != ABW_NKMER_DIMS)
+		return abw_fail(ctx, ABW_ERR_ARG, "internal: canonical k-mer table size");
+	double milli[1001];
+	for(int m = 0; m <= 1000; m++)
+		milli[m] = (double)m / 1000.0;
+	ABW_CUDA(ctx, cudaMemcpyToSymbol(c_dim_k, dk, sizeof(dk)));
+	ABW_CUDA(ctx, cudaMemcpyToSymbol(c_dim_code_a, da, sizeof(da)));
+	ABW_CUDA(ctx, cudaMemcpyToSymbol(c_dim_code_b, db, sizeof(db)));
+	ABW_CUDA(ctx, cudaMemcpyToSymbol(c_milli, milli, sizeof(milli)));
+	if(ctx->device >= 0 && ctx->device < 64)
+		g_tables_ready[ctx->device] = true;
+	return ABW_OK;
+}
+
+}  // namespace
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+extern "C" {
+
+int abw_pack_sequences(abw_ctx* ctx, const char* ascii, int ascii_on_device, const uint64_t* h_offsets, uint32_t nscaf, abw_seqset** out)
+{
+	if(!ctx || !out || !h_offsets || (!ascii && nscaf && h_offsets[nscaf] > 0))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_pack_sequences: null argument");
+	ABW_CUDA(ctx, cudaSetDevice(ctx->device));
+	abw_seqset* s = new abw_seqset();
+	s->nscaf = nscaf;
+	s->h_len.resize(nscaf);
+	s->h_base.resize((size_t)nscaf + 1);
+	uint64_t b = 0;
+	for(uint32_t i = 0; i < nscaf; i++) {
+		if(h_offsets[i + 1] < h_offsets[i]) {
+			delete s;
+			return abw_fail(ctx, ABW_ERR_ARG, "abw_pack_sequences: offsets must be non-decreasing");
+		}
+		s->h_len[i] = h_offsets[i + 1] - h_offsets[i];
+		s->h_base[i] = b;
+		b += (s->h_len[i] + 127) & ~127ull;
+	}
+	s->h_base[nscaf] = b;
+	s->total_padded = b;
+	const uint64_t bytes = h_offsets[nscaf];
+	DevBuf<unsigned char> d_ascii;
+	DevBuf<uint64_t> d_off;
+	DevBuf<int> d_err;
+	const unsigned char* src = (const unsigned char*)ascii;
+	auto fail = [&](int code) { delete s; return code; };
+#define PK(call) do { cudaError_t e__ = (call); if(e__ != cudaSuccess) { abw_fail(ctx, ABW_ERR_CUDA, std::string("abw_pack_sequences: ") + cudaGetErrorString(e__)); return fail(ABW_ERR_CUDA); } } while(0)
+	uint64_t readable = bytes;
+	if(!ascii_on_device) {
+		PK(d_ascii.alloc(bytes + 64));
+		PK(cudaMemcpyAsync(d_ascii.p, ascii, bytes, cudaMemcpyHostToDevice, ctx->stream));
+		src = d_ascii.p;
+		readable = bytes + 64;
+	}
+	PK(d_off.alloc((size_t)nscaf + 1));
+	PK(cudaMemcpyAsync(d_off.p, h_offsets, sizeof(uint64_t) * ((size_t)nscaf + 1), cudaMemcpyHostToDevice, ctx->stream));
+	PK(s->len.alloc(nscaf));
+	PK(s->base.alloc((size_t)nscaf + 1));
+	PK(cudaMemcpyAsync(s->len.p, s->h_len.data(), sizeof(uint64_t) * nscaf, cudaMemcpyHostToDevice, ctx->stream));
+	PK(cudaMemcpyAsync(s->base.p, s->h_base.data(), sizeof(uint64_t) * ((size_t)nscaf + 1), cudaMemcpyHostToDevice, ctx->stream));
+	// + slack so that the k-mer kernel may read one word past a segment
+	PK(s->packed.alloc(b / 16 + 16));
+	PK(s->valid.alloc(b / 32 + 16));
+	PK(s->nmask.alloc(b / 32 + 16));
+	PK(cudaMemsetAsync(s->packed.p + b / 16, 0, 16 * sizeof(uint32_t), ctx->stream));
+	PK(cudaMemsetAsync(s->valid.p + b / 32, 0, 16 * sizeof(uint32_t), ctx->stream));
+	PK(cudaMemsetAsync(s->nmask.p + b / 32, 0, 16 * sizeof(uint32_t), ctx->stream));
+	PK(s->countN.alloc(nscaf));
+	PK(s->countGC.alloc(nscaf));
+	PK(d_err.alloc(1));
+	PK(cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
+	if(nscaf > 0) {
+		unsigned int blocks = (unsigned int)std::min<uint64_t>(abw_div_up((uint64_t)nscaf * 32, 256), (uint64_t)ctx->sm_count * 16);
+		k_pack<<<blocks, 256, 0, ctx->stream>>>(src, readable, d_off.p, s->base.p, nscaf, s->packed.p, s->valid.p, s->nmask.p, s->countN.p, s->countGC.p, d_err.p);
+		ctx->launches++;
+		PK(cudaGetLastError());
+	}
+	int h_err = 0;
+	PK(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	PK(cudaStreamSynchronize(ctx->stream));
+#undef PK
+	if(h_err) {
+		delete s;
+		return abw_fail(ctx, ABW_ERR_ILLEGAL_DNA, "Illegal_DNAString: lower-case 'n' in a sequence (String.cpp:47-49)");
+	}
+	*out = s;
+	return ABW_OK;
+}
+
+void abw_seqset_destroy(abw_seqset* s) { delete s; }
+
+int abw_seqset_stats(abw_ctx* ctx, const abw_seqset* s, uint64_t* h_count_N, uint64_t* h_count_GC)
+{
+	if(!ctx || !s)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_seqset_stats: null argument");
+	if(h_count_N)
+		ABW_CUDA(ctx, cudaMemcpyAsync(h_count_N, s->countN.p, sizeof(uint64_t) * s->nscaf, cudaMemcpyDeviceToHost, ctx->stream));
+	if(h_count_GC)
+		ABW_CUDA(ctx, cudaMemcpyAsync(h_count_GC, s->countGC.p, sizeof(uint64_t) * s->nscaf, cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return ABW_OK;
+}
+
+int abw_segment(abw_ctx* ctx, const abw_seqset* s, uint32_t window_size, abw_segments** out)
+{
+	if(!ctx || !s || !out || window_size == 0)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_segment: bad argument");
+	ABW_CUDA(ctx, cudaSetDevice(ctx->device));
+	abw_segments* g = new abw_segments();
+	g->nscaf = s->nscaf;
+	int rc = [&]() -> int {
+		ABW_CUDA(ctx, g->seg_first.alloc((size_t)s->nscaf + 1));
+		DevBuf<uint64_t> counts, total;
+		ABW_CUDA(ctx, counts.alloc(s->nscaf));
+		ABW_CUDA(ctx, total.alloc(1));
+		if(s->nscaf > 0)
+			ABW_LAUNCH(ctx, k_seg_count, abw_div_up(s->nscaf, 256), 256, 0, s->len.p, s->countN.p, s->nscaf, (uint64_t)window_size, counts.p);
+		ABW_CHECK(abw_exclusive_scan_u64(ctx, counts.p, g->seg_first.p, s->nscaf, total.p));
+		ABW_CUDA(ctx, cudaMemcpyAsync(&g->nseg, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, cudaMemcpyAsync(g->seg_first.p + s->nscaf, &g->nseg, sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+		ABW_CUDA(ctx, g->seg_scaf.alloc(g->nseg));
+		ABW_CUDA(ctx, g->seg_start.alloc(g->nseg));
+		ABW_CUDA(ctx, g->seg_end.alloc(g->nseg));
+		ABW_CUDA(ctx, g->seg_nonN.alloc(g->nseg));
+		ABW_CUDA(ctx, g->seg_gbase.alloc(g->nseg));
+		if(s->nscaf > 0 && g->nseg > 0) {
+			unsigned int blocks = (unsigned int)std::min<uint64_t>(abw_div_up((uint64_t)s->nscaf * 32, 256), (uint64_t)ctx->sm_count * 16);
+			ABW_LAUNCH(ctx, k_seg_fill, blocks, 256, 0, s->len.p, s->countN.p, s->base.p, s->nmask.p, s->nscaf, (uint64_t)window_size, g->seg_first.p,
+			           g->seg_scaf.p, g->seg_start.p, g->seg_end.p, g->seg_nonN.p, g->seg_gbase.p);
+		}
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		return ABW_OK;
+	}();
+	if(rc != ABW_OK) {
+		delete g;
+		return rc;
+	}
+	*out = g;
+	return ABW_OK;
+}
+
+void abw_segments_destroy(abw_segments* g) { delete g; }
+
+uint64_t abw_segments_count(const abw_segments* g) { return g? g->nseg : 0; }
+
+int abw_segments_get(abw_ctx* ctx, const abw_segments* g, uint64_t* h_seg_first, uint32_t* h_seg_scaf, uint64_t* h_seg_start, uint64_t* h_seg_end, uint64_t* h_seg_nonN)
+{
+	if(!ctx || !g)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_segments_get: null argument");
+	if(h_seg_first)
+		ABW_CUDA(ctx, cudaMemcpyAsync(h_seg_first, g->seg_first.p, sizeof(uint64_t) * ((size_t)g->nscaf + 1), cudaMemcpyDeviceToHost, ctx->stream));
+	if(h_seg_scaf)
+		ABW_CUDA(ctx, cudaMemcpyAsync(h_seg_scaf, g->seg_scaf.p, sizeof(uint32_t) * g->nseg, cudaMemcpyDeviceToHost, ctx->stream));
+	if(h_seg_start)
+		ABW_CUDA(ctx, cudaMemcpyAsync(h_seg_start, g->seg_start.p, sizeof(uint64_t) * g->nseg, cudaMemcpyDeviceToHost, ctx->stream));
+	if(h_seg_end)
+		ABW_CUDA(ctx, cudaMemcpyAsync(h_seg_end, g->seg_end.p, sizeof(uint64_t) * g->nseg, cudaMemcpyDeviceToHost, ctx->stream));
+	if(h_seg_nonN)
+		ABW_CUDA(ctx, cudaMemcpyAsync(h_seg_nonN, g->seg_nonN.p, sizeof(uint64_t) * g->nseg, cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return ABW_OK;
+}
+
+int abw_kmer_features(abw_ctx* ctx, const abw_seqset* s, const abw_segments* g, int kind, int skip_A, double* d_rows, uint64_t ld, uint32_t col0)
+{
+	if(!ctx || !s || !g || !d_rows)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_kmer_features: null argument");
+	if(kind != ABW_FEAT_TRUNC3 && kind != ABW_FEAT_RAW)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_kmer_features: unknown kind");
+	if(ld < (uint64_t)col0 + ABW_NKMER_DIMS - (skip_A? 1 : 0))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_kmer_features: row stride too small");
+	ABW_CUDA(ctx, cudaSetDevice(ctx->device));
+	ABW_CHECK(upload_tables(ctx));
+	if(g->nseg == 0)
+		return ABW_OK;
+	const size_t smem = sizeof(KmWarpSmem) * KM_WARPS;
+	unsigned int blocks = (unsigned int)std::min<uint64_t>(abw_div_up(g->nseg, KM_WARPS), (uint64_t)ctx->sm_count * 2 * 4);
+	if(kind == ABW_FEAT_TRUNC3) {
+		ABW_CUDA(ctx, cudaFuncSetAttribute(k_kmer<ABW_FEAT_TRUNC3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		ABW_LAUNCH(ctx, k_kmer<ABW_FEAT_TRUNC3>, blocks, KM_WARPS * 32, smem, s->packed.p, s->valid.p, g->seg_gbase.p, g->seg_start.p, g->seg_end.p, g->nseg, skip_A, d_rows, ld, col0);
+	}
+	else {
+		ABW_CUDA(ctx, cudaFuncSetAttribute(k_kmer<ABW_FEAT_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		ABW_LAUNCH(ctx, k_kmer<ABW_FEAT_RAW>, blocks, KM_WARPS * 32, smem, s->packed.p, s->valid.p, g->seg_gbase.p, g->seg_start.p, g->seg_end.p, g->nseg, skip_A, d_rows, ld, col0);
+	}
+	return ABW_OK;
+}
+
+int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uint64_t nreads, int reads_on_device, uint32_t max_snps,
+                 int kind, double* d_rows, uint64_t ld, uint32_t col, uint64_t* d_scaf_nbps)
+{
+	if(!ctx || !g || !d_rows || (!reads && nreads))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_coverage: null argument");
+	if(nreads >= (1ull << 32))
+		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_coverage: more than 2^32-1 reads per call; split the sample");
+	if(g->nseg >= (1ull << 32))
+		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_coverage: more than 2^32-1 windows");
+	ABW_CUDA(ctx, cudaSetDevice(ctx->device));
+	DevBuf<abw_read> d_reads;
+	const abw_read* rd = reads;
+	if(!reads_on_device && nreads) {
+		ABW_CUDA(ctx, d_reads.alloc(nreads));
+		ABW_CUDA(ctx, cudaMemcpyAsync(d_reads.p, reads, sizeof(abw_read) * nreads, cudaMemcpyHostToDevice, ctx->stream));
+		rd = d_reads.p;
+	}
+	DevBuf<uint32_t> counts, per_seg, keys, keys_tmp, vals, vals_tmp;
+	DevBuf<uint64_t> offs, seg_off, total;
+	ABW_CUDA(ctx, counts.alloc(nreads));
+	ABW_CUDA(ctx, offs.alloc(nreads));
+	ABW_CUDA(ctx, total.alloc(1));
+	ABW_CUDA(ctx, per_seg.alloc(g->nseg));
+	ABW_CUDA(ctx, seg_off.alloc(g->nseg + 1));
+	ABW_CUDA(ctx, cudaMemsetAsync(per_seg.p, 0, sizeof(uint32_t) * g->nseg, ctx->stream));
+	uint64_t npairs = 0;
+	if(nreads) {
+		ABW_LAUNCH(ctx, k_cov_count, abw_div_up(nreads, 256), 256, 0, rd, nreads, max_snps, g->nscaf, g->seg_first.p, g->seg_start.p, g->seg_end.p, counts.p,
+		           (unsigned long long*)d_scaf_nbps);
+		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, counts.p, offs.p, nreads, total.p));
+		ABW_CUDA(ctx, cudaMemcpyAsync(&npairs, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	ABW_CUDA(ctx, keys.alloc(npairs));
+	ABW_CUDA(ctx, keys_tmp.alloc(npairs));
+	ABW_CUDA(ctx, vals.alloc(npairs));
+	ABW_CUDA(ctx, vals_tmp.alloc(npairs));
+	if(npairs) {
+		ABW_LAUNCH(ctx, k_cov_emit, abw_div_up(nreads, 256), 256, 0, rd, nreads, max_snps, g->nscaf, g->seg_first.p, g->seg_start.p, g->seg_end.p, offs.p, keys.p,
+		           vals.p, per_seg.p);
+		int nbits = 1;
+		while(nbits < 32 && (1ull << nbits) < g->nseg)
+			nbits++;
+		ABW_CHECK(abw_radix_sort_pairs_u32(ctx, keys.p, keys_tmp.p, vals.p, vals_tmp.p, npairs, nbits));
+	}
+	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, per_seg.p, seg_off.p, g->nseg, seg_off.p + g->nseg));
+	if(g->nseg) {
+		if(kind == ABW_FEAT_TRUNC3)
+			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_TRUNC3>, abw_div_up(g->nseg, 128), 128, 0, rd, vals.p, seg_off.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col);
+		else
+			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_RAW>, abw_div_up(g->nseg, 128), 128, 0, rd, vals.p, seg_off.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col);
+	}
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return ABW_OK;
+}
+
+}  // extern "C"

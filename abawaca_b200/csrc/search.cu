@@ -1,0 +1,1464 @@
+// Split search of abawaca on the device (ClusterSeparator*.cpp, ClusterQuality.cpp, SCGdb.cpp).
+//
+// B200-first formulation:
+//   * every Dimension is sorted ONCE (abw_search_create).  A cluster only ever contains whole scaffold groups
+//     (ClusterSeparator.cpp:104-122 re-homes datapoints to their scaffold's cluster), so the rank of a datapoint
+//     inside its scaffold is a per-(datapoint, dimension) constant and the reference's incremental TP/FP counters
+//     (ClusterSeparatorBySensitivitySpecificity.cpp:6-76) become prefix sums of per-element constants.
+//   * per dimension the device keeps one u32 per datapoint, "element" = scaffold id | class | flags, ordered by value
+//     and grouped by live cluster.  A level of the breadth-first search is
+//        sweep      : stream the elements of every live (cluster, dimension) once, block scans, score candidates
+//        reduce     : best candidate per cluster (score, then lowest dimension, then lowest value)
+//        children   : scaffold majority vote + re-homing (ClusterSeparator.cpp:82-134)
+//        partition  : stable 2-way partition of every dimension's element array by the scaffold's new cluster
+//     instead of re-sorting every cluster (std::sort at ...Specificity.cpp:114) and rebuilding std::map/std::set state.
+//   * the SCG acceptance test (ClusterQuality.cpp:96-136) is evaluated for EVERY candidate through a small per
+//     (cluster, dimension) table indexed by the number of SCG-carrying scaffolds already flipped to side 1.
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+constexpr int      SW_THREADS = 256;
+constexpr int      SW_ITEMS = 8;
+constexpr int      SW_TILE = SW_THREADS * SW_ITEMS;
+constexpr uint32_t EL_SCAF_BITS = 27;
+constexpr uint32_t EL_SCAF_MASK = (1u << EL_SCAF_BITS) - 1u;
+constexpr uint32_t EL_CLASS_SHIFT = 27;     // 2 bits: sens/spec: 0 before the flip, 1 the flip element, 2 after
+                                            //         split-scafs: position relative to r1 (0 below, 1 equal, 2 above)
+constexpr uint32_t EL_AUX_SHIFT = 29;       // 2 bits: sens/spec: bit0 = flip element of an SCG-carrying scaffold
+                                            //         split-scafs: position relative to r2
+constexpr uint32_t EL_BOUNDARY = 1u << 31;  // value differs from the previous element of the same cluster
+
+struct __align__(16) ScafRow { uint32_t T, n; uint64_t len; };
+
+struct ClusterDesc {
+	uint64_t off;        // first element of the cluster in every dimension's array
+	uint32_t n;          // datapoints
+	uint32_t kOff, K;    // segment of the per-dimension SCG scaffold list
+	uint32_t tabOff;     // offset of the (K+1)-entry pass table (per dimension)
+	uint32_t sOff, ns;   // segment of the scaffold list
+	uint32_t totT;       // sum of T over the scaffolds of the cluster
+	uint32_t U;          // number of scaffolds
+	uint64_t totLen;     // sum of sequence lengths
+	uint32_t ss_ok;      // split-scafs: every scaffold starts "in" cluster 2 (ClusterSeparatorSplitScafs.cpp:102-106)
+	uint32_t pad;
+};
+
+struct CandRec {
+	double   k1, k2;     // sens/spec: k1 = sens*spec (maximise).  split-scafs: k1 = ratio, k2 = size ratio (minimise)
+	uint32_t p;          // number of datapoints with value <= candidate value
+	uint32_t i0, i1, i2; // sens/spec: TP, total, TP+FP of the small side.  split-scafs: separated, in_small, in_large
+	uint32_t found;
+	uint32_t dim0;       // 0-based dimension (filled by the reduction)
+};
+
+template <int STRATEGY>
+__device__ __forceinline__ bool cand_better(const CandRec& x, const CandRec& y)
+{
+	if(!x.found) return false;
+	if(!y.found) return true;
+	if(STRATEGY == ABW_SENS_SPEC) {
+		if(x.k1 != y.k1) return x.k1 > y.k1;        // ...Specificity.h:28 (scores are never NaN here)
+	}
+	else {
+		if(x.k1 != y.k1) return x.k1 < y.k1;        // ...SplitScafs.h:34-35
+		if(x.k2 != y.k2) return x.k2 < y.k2;
+	}
+	if(x.dim0 != y.dim0) return x.dim0 < y.dim0;    // ClusterSeparator.cpp:13-14
+	return x.p < y.p;                               // lower value <=> fewer datapoints at or below it (:15)
+}
+
+struct Agg {
+	uint32_t a, b, c, d;
+	unsigned long long e;
+};
+__device__ __forceinline__ Agg agg_zero() { Agg r; r.a = r.b = r.c = r.d = 0; r.e = 0; return r; }
+__device__ __forceinline__ Agg agg_add(const Agg& x, const Agg& y)
+{
+	Agg r; r.a = x.a + y.a; r.b = x.b + y.b; r.c = x.c + y.c; r.d = x.d + y.d; r.e = x.e + y.e; return r;
+}
+__device__ __forceinline__ Agg agg_shfl_up(const Agg& x, int o)
+{
+	Agg r;
+	r.a = __shfl_up_sync(0xffffffffu, x.a, o); r.b = __shfl_up_sync(0xffffffffu, x.b, o);
+	r.c = __shfl_up_sync(0xffffffffu, x.c, o); r.d = __shfl_up_sync(0xffffffffu, x.d, o);
+	r.e = __shfl_up_sync(0xffffffffu, x.e, o);
+	return r;
+}
+
+// exclusive block scan of one Agg per thread, plus the block total.  smem: Agg[SW_THREADS/32 + 1]
+__device__ __forceinline__ Agg block_excl_scan_agg(const Agg& v, Agg& total, Agg* sm)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	Agg incl = v;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) {
+		Agg t = agg_shfl_up(incl, o);
+		if(lane >= o)
+			incl = agg_add(incl, t);
+	}
+	if(lane == 31)
+		sm[warp] = incl;
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		Agg run = agg_zero();
+		for(int w = 0; w < SW_THREADS / 32; w++) {
+			Agg t = sm[w];
+			sm[w] = run;
+			run = agg_add(run, t);
+		}
+		sm[SW_THREADS / 32] = run;
+	}
+	__syncthreads();
+	Agg warp_ex = sm[warp];
+	total = sm[SW_THREADS / 32];
+	Agg ex = agg_add(warp_ex, incl);
+	ex.a -= v.a; ex.b -= v.b; ex.c -= v.c; ex.d -= v.d; ex.e -= v.e;
+	__syncthreads();
+	return ex;
+}
+
+struct SweepParams {
+	uint32_t thr;            // cluster_ndps_threshold
+	double   min_score;      // min_reported_score
+	float    prune;          // safe single-precision lower bound of min_score
+	unsigned long long scg_min_size;
+	double   fraction_in;    // split-scafs
+};
+
+// ---------------------------------------------------------------------------------------------------
+// the threshold sweep: one CTA per (live cluster, dimension), tiles of SW_TILE elements in order
+// ---------------------------------------------------------------------------------------------------
+template <int STRATEGY>
+__global__ void __launch_bounds__(SW_THREADS) k_sweep(const uint32_t* __restrict__ E, uint64_t N, const ClusterDesc* __restrict__ clusters, const ScafRow* __restrict__ rows,
+                                                     const uint8_t* __restrict__ pass_tab, uint64_t tab_stride, SweepParams prm, CandRec* __restrict__ out)
+{
+	__shared__ Agg sm_agg[SW_THREADS / 32 + 1];
+	__shared__ CandRec sm_best[SW_THREADS / 32];
+	const uint32_t c = blockIdx.x, d = blockIdx.y, D = gridDim.y;
+	const ClusterDesc cl = clusters[c];
+	const uint32_t* __restrict__ seg = E + (uint64_t)d * N + cl.off;
+	const uint8_t* __restrict__ tab = (STRATEGY == ABW_SENS_SPEC)? pass_tab + (uint64_t)d * tab_stride + cl.tabOff : nullptr;
+	const uint32_t n = cl.n;
+	CandRec best;
+	best.found = 0; best.k1 = 0; best.k2 = 0; best.p = 0; best.i0 = best.i1 = best.i2 = 0; best.dim0 = d;
+	Agg carry = agg_zero();
+	if(STRATEGY == ABW_SPLIT_SCAFS && !cl.ss_ok) {
+		if(threadIdx.x == 0)
+			out[(uint64_t)c * D + d] = best;
+		return;
+	}
+	for(uint32_t t0 = 0; t0 < n; t0 += SW_TILE) {
+		const uint32_t i0 = t0 + threadIdx.x * SW_ITEMS;
+		uint32_t el[SW_ITEMS];
+		if(i0 + SW_ITEMS <= n && ((reinterpret_cast<uintptr_t>(seg + i0) & 15) == 0)) {
+			const uint4* p4 = reinterpret_cast<const uint4*>(seg + i0);
+			uint4 x = __ldg(p4), y = __ldg(p4 + 1);
+			el[0] = x.x; el[1] = x.y; el[2] = x.z; el[3] = x.w; el[4] = y.x; el[5] = y.y; el[6] = y.z; el[7] = y.w;
+		}
+		else {
+#pragma unroll
+			for(int j = 0; j < SW_ITEMS; j++)
+				el[j] = (i0 + j < n)? __ldg(seg + i0 + j) : 0u;   // class 0, no boundary: contributes nothing
+		}
+		// per-element contributions
+		Agg w[SW_ITEMS];
+		Agg tsum = agg_zero();
+#pragma unroll
+		for(int j = 0; j < SW_ITEMS; j++) {
+			const uint32_t cls = (el[j] >> EL_CLASS_SHIFT) & 3u, aux = (el[j] >> EL_AUX_SHIFT) & 3u;
+			Agg x = agg_zero();
+			if(STRATEGY == ABW_SENS_SPEC) {
+				// a: TP1 (dps of side 1 whose scaffold is assigned to side 1), b: total_dps_for_assigned_scafs of side 1,
+				// c: dps in the cluster of the scaffolds assigned to side 1, d: SCG-carrying scaffolds flipped, e: their length
+				if(cls == 2u)
+					x.a = 1;
+				else if(cls == 1u) {
+					const ScafRow r = rows[el[j] & EL_SCAF_MASK];
+					x.a = r.T / 2 + 1;          // the flip element brings itself and the floor(T/2) earlier dps of the scaffold (...Specificity.cpp:41-57)
+					x.b = r.T;
+					x.c = r.n;
+					x.d = aux & 1u;
+					x.e = r.len;
+				}
+			}
+			else {
+				// a: ndps_in_scafs_that_belong of side 1, b: scafs_in of side 1, c: decrease of ndps_in_scafs_that_belong of side 2, d: decrease of scafs_in of side 2
+				if(cls == 2u)
+					x.a = 1;
+				if(aux == 0u && i0 + j < n)
+					x.c = 1;
+				if(cls == 1u || aux == 1u) {
+					const ScafRow r = rows[el[j] & EL_SCAF_MASK];
+					const uint32_t r1 = (uint32_t)ceil(__dmul_rn(prm.fraction_in, (double)r.T));
+					if(cls == 1u) { x.a = r1; x.b = 1; }
+					if(aux == 1u) { x.c = r1; x.d = 1; }
+				}
+			}
+			w[j] = x;
+			tsum = agg_add(tsum, x);
+		}
+		Agg total;
+		Agg ex = agg_add(carry, block_excl_scan_agg(tsum, total, sm_agg));
+		// candidates: a boundary before element i means "all dps with value <= value[i-1]" is a threshold with p = i
+#pragma unroll
+		for(int j = 0; j < SW_ITEMS; j++) {
+			const uint32_t p = i0 + j;
+			if((el[j] & EL_BOUNDARY) && p < n && p >= prm.thr && n - p >= prm.thr) {
+				if(STRATEGY == ABW_SENS_SPEC) {
+					// ...Specificity.cpp:146-161 with TP1/FP1/TP2/FP2 written as prefix sums
+					uint32_t TP, tot, u;
+					if(p < n - p) { TP = ex.a; tot = ex.b; u = p; }
+					else { TP = (n - p) - (ex.c - ex.a); tot = cl.totT - ex.b; u = n - p; }
+					if(tot != 0) {
+						const float fTP = (float)TP;
+						if(fTP >= prm.prune * (float)tot && fTP >= prm.prune * (float)u) {
+							const double sens = __ddiv_rn((double)(int)TP, (double)(int)tot), spec = __ddiv_rn((double)(int)TP, (double)(int)u);
+							const double score = __dmul_rn(sens, spec);
+							if(score >= prm.min_score && (!best.found || score > best.k1)) {
+								const uint8_t pt = tab[ex.d];
+								bool ok = (pt == 1);
+								if(pt == 2)
+									ok = (ex.e >= prm.scg_min_size) && (cl.totLen - ex.e >= prm.scg_min_size);
+								if(ok) {
+									best.found = 1; best.k1 = score; best.p = p; best.i0 = TP; best.i1 = tot; best.i2 = u;
+								}
+							}
+						}
+					}
+				}
+				else {
+					// ...SplitScafs.cpp:131-154
+					const uint32_t belong1 = ex.a, in1 = ex.b, belong2 = n - ex.c, in2 = cl.U - ex.d;
+					if(belong1 >= prm.thr && belong2 >= prm.thr) {
+						const uint32_t separated = cl.U - in1 - in2;
+						const uint32_t in_small = (p < n - p)? in1 : in2, in_large = (p < n - p)? in2 : in1;
+						const double ratio = __ddiv_rn((double)separated, (double)(int)in_small);
+						double csr = __ddiv_rn((double)(int)in_small, (double)(int)in_large);
+						if(csr < 1)
+							csr = __ddiv_rn(1.0, csr);
+						if(!best.found || ratio < best.k1 || (ratio == best.k1 && csr < best.k2)) {
+							best.found = 1; best.k1 = ratio; best.k2 = csr; best.p = p; best.i0 = separated; best.i1 = in_small; best.i2 = in_large;
+						}
+					}
+				}
+			}
+			ex = agg_add(ex, w[j]);
+		}
+		carry = agg_add(carry, total);
+	}
+	// block arg-best: (key, then lowest p); each thread already holds its lowest-p optimum
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for(int o = 16; o > 0; o >>= 1) {
+		CandRec other;
+		other.k1 = __shfl_xor_sync(0xffffffffu, best.k1, o); other.k2 = __shfl_xor_sync(0xffffffffu, best.k2, o);
+		other.p = __shfl_xor_sync(0xffffffffu, best.p, o); other.i0 = __shfl_xor_sync(0xffffffffu, best.i0, o);
+		other.i1 = __shfl_xor_sync(0xffffffffu, best.i1, o); other.i2 = __shfl_xor_sync(0xffffffffu, best.i2, o);
+		other.found = __shfl_xor_sync(0xffffffffu, best.found, o); other.dim0 = d;
+		if(cand_better<STRATEGY>(other, best))
+			best = other;
+	}
+	if(lane == 0)
+		sm_best[warp] = best;
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		CandRec b = sm_best[0];
+		for(int w2 = 1; w2 < SW_THREADS / 32; w2++)
+			if(cand_better<STRATEGY>(sm_best[w2], b))
+				b = sm_best[w2];
+		out[(uint64_t)c * D + d] = b;
+	}
+}
+
+// best candidate of every cluster over its dimensions: ascending dimension, strict improvement only
+// (...Specificity.cpp:137-140 under the mutex; is_better is a total order so thread order never mattered)
+template <int STRATEGY>
+__global__ void k_reduce_best(const CandRec* __restrict__ per_dim, uint32_t D, CandRec* __restrict__ out)
+{
+	__shared__ CandRec sm[32];
+	const uint32_t c = blockIdx.x;
+	CandRec best;
+	best.found = 0; best.k1 = best.k2 = 0; best.p = 0; best.i0 = best.i1 = best.i2 = 0; best.dim0 = 0;
+	for(uint32_t d = threadIdx.x; d < D; d += blockDim.x) {
+		CandRec x = per_dim[(uint64_t)c * D + d];
+		x.dim0 = d;
+		if(cand_better<STRATEGY>(x, best))
+			best = x;
+	}
+	sm[threadIdx.x] = best;
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		for(uint32_t t = 1; t < blockDim.x; t++)
+			if(cand_better<STRATEGY>(sm[t], best))
+				best = sm[t];
+		out[c] = best;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SCG acceptance table, ClusterQuality.cpp:96-136 + SCGdb.cpp:21-38.  One warp per (cluster, dimension).
+// entry k (k SCG-carrying scaffolds already assigned to side 1): 0 reject, 1 accept, 2 decide on the sizes.
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t SCG_WMAX = 8;   // up to 512 distinct SCG names
+
+__global__ void k_pass_table(const uint32_t* __restrict__ scg_list, uint64_t list_stride, const ClusterDesc* __restrict__ clusters, const uint64_t* __restrict__ scgmask,
+                             uint32_t W, const uint64_t* __restrict__ never_mask, double overlap_thr, uint64_t* __restrict__ suffix_tmp, uint8_t* __restrict__ tab,
+                             uint64_t tab_stride, uint32_t D)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t c = blockIdx.x, d = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if(d >= D)
+		return;
+	const ClusterDesc cl = clusters[c];
+	const uint32_t* __restrict__ list = scg_list + (uint64_t)d * list_stride + cl.kOff;
+	uint64_t* __restrict__ suf = suffix_tmp + ((uint64_t)d * list_stride + cl.kOff) * W;     // suf[k] = OR of masks k..K-1
+	uint8_t* __restrict__ t = tab + (uint64_t)d * tab_stride + cl.tabOff;
+	const uint32_t K = cl.K;
+	// pass 1 (backwards): suffix ORs, one mask word at a time
+	for(uint32_t w = 0; w < W; w++) {
+		uint64_t carry = 0;
+		for(int64_t base = (int64_t)((K + 31) / 32) * 32 - 32; base >= 0; base -= 32) {
+			const uint32_t k = (uint32_t)base + lane;
+			uint64_t m = (k < K)? scgmask[(uint64_t)list[k] * W + w] : 0ull;
+#pragma unroll
+			for(int o = 1; o < 32; o <<= 1) {
+				uint64_t x = __shfl_down_sync(0xffffffffu, m, o);
+				if(lane + o < 32)
+					m |= x;
+			}
+			m |= carry;
+			if(k < K)
+				suf[(uint64_t)k * W + w] = m;
+			carry = __shfl_sync(0xffffffffu, m, 0);
+		}
+	}
+	__syncwarp();
+	// pass 2 (forwards): entry k sees side 1 = events [0, k), side 2 = events [k, K) plus the scaffolds that can never flip
+	uint64_t carry[SCG_WMAX];
+#pragma unroll
+	for(uint32_t w = 0; w < SCG_WMAX; w++)
+		carry[w] = 0;
+	for(uint32_t base = 0; base <= K; base += 32) {
+		const uint32_t k = base + lane;
+		uint32_t g1 = 0, g2 = 0, g12 = 0;
+#pragma unroll
+		for(uint32_t w = 0; w < SCG_WMAX; w++) {
+			if(w < W) {
+				uint64_t pre = (k >= 1 && k - 1 < K)? scgmask[(uint64_t)list[k - 1] * W + w] : 0ull;
+#pragma unroll
+				for(int o = 1; o < 32; o <<= 1) {
+					uint64_t x = __shfl_up_sync(0xffffffffu, pre, o);
+					if(lane >= o)
+						pre |= x;
+				}
+				pre |= carry[w];
+				carry[w] = __shfl_sync(0xffffffffu, pre, 31);
+				const uint64_t s2 = ((k < K)? suf[(uint64_t)k * W + w] : 0ull) | never_mask[(uint64_t)c * W + w];
+				g1 += __popcll(pre);
+				g2 += __popcll(s2);
+				g12 += __popcll(pre & s2);
+			}
+		}
+		if(k <= K) {
+			uint8_t r;
+			if(g1 == 0 || g2 == 0)
+				r = 2;                                                  // ClusterQuality.cpp:118-120: decided on the two total sizes
+			else
+				r = (__ddiv_rn((double)g12, (double)min(g1, g2)) < overlap_thr)? 0 : 1;   // :130
+			t[k] = r;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// children, ClusterSeparator.cpp:25-54, 82-134
+// ---------------------------------------------------------------------------------------------------
+struct SplitJob {
+	uint32_t cluster;    // index into the level's cluster array
+	uint32_t dim0;       // winning dimension
+	uint32_t p;          // datapoints with value <= separating value
+	uint32_t swapped;    // cluster1 is the high side (ClusterSeparator.cpp:49-53)
+};
+
+struct ChildStats {      // [job][2]
+	unsigned long long ndps, totLen;
+	uint32_t ns, nassigned, totT, K, viol, pad;
+};
+
+__global__ void k_count_low(const uint32_t* __restrict__ E, uint64_t N, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs, uint32_t* __restrict__ low)
+{
+	const SplitJob jb = jobs[blockIdx.y];
+	const ClusterDesc cl = clusters[jb.cluster];
+	const uint32_t* __restrict__ seg = E + (uint64_t)jb.dim0 * N + cl.off;
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.p; i += gridDim.x * blockDim.x)
+		atomicAdd(&low[seg[i] & EL_SCAF_MASK], 1u);
+}
+
+__device__ __forceinline__ unsigned long long orderable(double v)
+{
+	v = v + 0.0;                                    // -0.0 and +0.0 compare equal in comp_by_value (ClusterSeparator.cpp:8)
+	unsigned long long b = (unsigned long long)__double_as_longlong(v);
+	return (b >> 63)? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double unorderable(unsigned long long k)
+{
+	unsigned long long b = (k >> 63)? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+	return __longlong_as_double((long long)b);
+}
+
+// one thread per scaffold of every split cluster: vote (ClusterSeparator.cpp:94-101), child statistics, separating value
+__global__ void k_scaf_sides(const uint32_t* __restrict__ scaf_list, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs, const ScafRow* __restrict__ rows,
+                             const uint32_t* __restrict__ low, const uint64_t* __restrict__ dp_first, const double* __restrict__ values, uint64_t N,
+                             const uint64_t* __restrict__ scgmask, uint32_t W, int strategy, double fraction_in, uint8_t* __restrict__ side, uint8_t* __restrict__ new_assigned,
+                             ChildStats* __restrict__ stats, uint64_t* __restrict__ child_never, unsigned long long* __restrict__ value_key)
+{
+	const SplitJob jb = jobs[blockIdx.y];
+	const ClusterDesc cl = clusters[jb.cluster];
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cl.ns; i += gridDim.x * blockDim.x) {
+		const uint32_t s = scaf_list[cl.sOff + i];
+		const ScafRow r = rows[s];
+		const uint32_t lo = low[s];
+		const uint32_t c1 = jb.swapped? r.n - lo : lo, c2 = r.n - c1;
+		const bool A1 = c1 > 0 && 2ull * c1 >= r.T;          // :95-97
+		const bool A2 = c2 > 0 && 2ull * c2 > r.T;           // :98-101
+		// dps not in a scaffold assigned to cluster2 end up in cluster1 (:104-122)
+		const uint32_t sd = A2? 2u : 1u;
+		side[s] = (uint8_t)sd;
+		new_assigned[s] = A1? 1 : (A2? 2 : 0);
+		ChildStats* st = stats + (uint64_t)blockIdx.y * 2 + (sd - 1);
+		atomicAdd(&st->ndps, (unsigned long long)r.n);
+		atomicAdd(&st->totLen, (unsigned long long)r.len);
+		atomicAdd(&st->ns, 1u);
+		atomicAdd(&st->totT, r.T);
+		if(A1 || A2)
+			atomicAdd(&st->nassigned, 1u);
+		bool has_scg = false;
+		for(uint32_t w = 0; w < W; w++)
+			has_scg |= scgmask[(uint64_t)s * W + w] != 0;
+		if(has_scg) {
+			if(r.n >= r.T / 2 + 1)
+				atomicAdd(&st->K, 1u);
+			else                                             // can never be assigned to side 1 of a sweep: always counted on side 2
+				for(uint32_t w = 0; w < W; w++)
+					atomicOr((unsigned long long*)&child_never[((uint64_t)blockIdx.y * 2 + (sd - 1)) * W + w], (unsigned long long)scgmask[(uint64_t)s * W + w]);
+		}
+		if(strategy == ABW_SPLIT_SCAFS && !((double)r.n >= __dmul_rn(fraction_in, (double)r.T)))
+			atomicAdd(&st->viol, 1u);
+		// separating value = largest value on the low side = max over scaffolds of their lo-th smallest value
+		if(lo > 0) {
+			const double* __restrict__ col = values + (uint64_t)jb.dim0 * N + dp_first[s];
+			unsigned long long kth = 0;
+			for(uint32_t a = 0; a < r.n; a++) {
+				const unsigned long long ka = orderable(col[a]);
+				uint32_t rank = 0;
+				for(uint32_t b = 0; b < r.n; b++) {
+					const unsigned long long kb = orderable(col[b]);
+					rank += (kb < ka) || (kb == ka && b < a);
+				}
+				if(rank == lo - 1)
+					kth = ka;
+			}
+			atomicMax(&value_key[blockIdx.y], kth);
+		}
+	}
+}
+
+// same as the tail of k_scaf_sides but for clusters that are NOT split: only the value of the best separation (log line parity)
+__global__ void k_value_only(const uint32_t* __restrict__ scaf_list, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs, const ScafRow* __restrict__ rows,
+                             const uint32_t* __restrict__ low, const uint64_t* __restrict__ dp_first, const double* __restrict__ values, uint64_t N,
+                             unsigned long long* __restrict__ value_key)
+{
+	const SplitJob jb = jobs[blockIdx.y];
+	const ClusterDesc cl = clusters[jb.cluster];
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cl.ns; i += gridDim.x * blockDim.x) {
+		const uint32_t s = scaf_list[cl.sOff + i];
+		const ScafRow r = rows[s];
+		const uint32_t lo = low[s];
+		if(lo > 0) {
+			const double* __restrict__ col = values + (uint64_t)jb.dim0 * N + dp_first[s];
+			unsigned long long kth = 0;
+			for(uint32_t a = 0; a < r.n; a++) {
+				const unsigned long long ka = orderable(col[a]);
+				uint32_t rank = 0;
+				for(uint32_t b = 0; b < r.n; b++) {
+					const unsigned long long kb = orderable(col[b]);
+					rank += (kb < ka) || (kb == ka && b < a);
+				}
+				if(rank == lo - 1)
+					kth = ka;
+			}
+			atomicMax(&value_key[blockIdx.y], kth);
+		}
+	}
+}
+
+__global__ void k_clear_low(const uint32_t* __restrict__ scaf_list, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs, uint32_t* __restrict__ low)
+{
+	const SplitJob jb = jobs[blockIdx.y];
+	const ClusterDesc cl = clusters[jb.cluster];
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cl.ns; i += gridDim.x * blockDim.x)
+		low[scaf_list[cl.sOff + i]] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stable partition of every dimension's elements of a split cluster; the boundary flag of an element becomes
+// "value differs from the previous element OF ITS NEW CLUSTER", i.e. the OR of the flags since that element
+// ---------------------------------------------------------------------------------------------------
+struct PartJob {
+	uint64_t off;        // parent segment (child 1 is written at off, child 2 at off + n1)
+	uint32_t n, n1;
+};
+
+// state = (pend1, pend2): a boundary was seen since the last side-1 / side-2 element.  maps on 4 states, 2 bits each
+__device__ __forceinline__ uint32_t map_of(uint32_t sd, uint32_t c)
+{
+	uint32_t m = 0;
+#pragma unroll
+	for(uint32_t s = 0; s < 4; s++) {
+		uint32_t p1 = s & 1u, p2 = s >> 1;
+		uint32_t ns = (sd == 1u)? (0u | ((p2 | c) << 1)) : ((p1 | c) | 0u);
+		m |= ns << (2 * s);
+	}
+	return m;
+}
+__device__ __forceinline__ uint32_t map_apply(uint32_t m, uint32_t s) { return (m >> (2 * s)) & 3u; }
+__device__ __forceinline__ uint32_t map_compose(uint32_t first, uint32_t then)   // then(first(s))
+{
+	uint32_t m = 0;
+#pragma unroll
+	for(uint32_t s = 0; s < 4; s++)
+		m |= map_apply(then, map_apply(first, s)) << (2 * s);
+	return m;
+}
+constexpr uint32_t MAP_IDENTITY = 0xE4u;   // 3,2,1,0
+
+__global__ void __launch_bounds__(SW_THREADS) k_partition(const uint32_t* __restrict__ Ein, uint32_t* __restrict__ Eout, uint64_t N, const PartJob* __restrict__ jobs,
+                                                         const uint8_t* __restrict__ side)
+{
+	__shared__ uint32_t sm_cnt[SW_THREADS / 32 + 1];
+	__shared__ uint32_t sm_map[SW_THREADS / 32 + 1];
+	const PartJob jb = jobs[blockIdx.x];
+	const uint32_t d = blockIdx.y;
+	const uint32_t* __restrict__ src = Ein + (uint64_t)d * N + jb.off;
+	uint32_t* __restrict__ dst1 = Eout + (uint64_t)d * N + jb.off;
+	uint32_t* __restrict__ dst2 = dst1 + jb.n1;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t carry_cnt = 0, carry_state = 3u;          // the first element of each child gets its boundary flag set
+	for(uint32_t t0 = 0; t0 < jb.n; t0 += SW_TILE) {
+		const uint32_t i0 = t0 + threadIdx.x * SW_ITEMS;
+		uint32_t el[SW_ITEMS], sd[SW_ITEMS];
+		uint32_t cnt1 = 0, tmap = MAP_IDENTITY;
+#pragma unroll
+		for(int j = 0; j < SW_ITEMS; j++) {
+			if(i0 + j < jb.n) {
+				el[j] = __ldg(src + i0 + j);
+				sd[j] = side[el[j] & EL_SCAF_MASK];
+				cnt1 += (sd[j] == 1u);
+				tmap = map_compose(tmap, map_of(sd[j], el[j] >> 31));
+			}
+			else {
+				el[j] = 0;
+				sd[j] = 0;
+			}
+		}
+		// inclusive warp scans
+		uint32_t icnt = cnt1, imap = tmap;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) {
+			uint32_t c2 = __shfl_up_sync(0xffffffffu, icnt, o), m2 = __shfl_up_sync(0xffffffffu, imap, o);
+			if(lane >= o) {
+				icnt += c2;
+				imap = map_compose(m2, imap);
+			}
+		}
+		if(lane == 31) {
+			sm_cnt[warp] = icnt;
+			sm_map[warp] = imap;
+		}
+		__syncthreads();
+		if(threadIdx.x == 0) {
+			uint32_t rc = 0, rm = MAP_IDENTITY;
+			for(int w = 0; w < SW_THREADS / 32; w++) {
+				uint32_t tc = sm_cnt[w], tm = sm_map[w];
+				sm_cnt[w] = rc;
+				sm_map[w] = rm;
+				rc += tc;
+				rm = map_compose(rm, tm);
+			}
+			sm_cnt[SW_THREADS / 32] = rc;
+			sm_map[SW_THREADS / 32] = rm;
+		}
+		__syncthreads();
+		// exclusive prefix for this thread
+		uint32_t ecnt = __shfl_up_sync(0xffffffffu, icnt, 1), emap = __shfl_up_sync(0xffffffffu, imap, 1);
+		if(lane == 0) {
+			ecnt = 0;
+			emap = MAP_IDENTITY;
+		}
+		uint32_t before1 = carry_cnt + sm_cnt[warp] + ecnt;
+		uint32_t state = map_apply(emap, map_apply(sm_map[warp], carry_state));
+#pragma unroll
+		for(int j = 0; j < SW_ITEMS; j++) {
+			const uint32_t i = i0 + j;
+			if(i < jb.n) {
+				const uint32_t c = el[j] >> 31;
+				uint32_t e = el[j] & 0x7FFFFFFFu;
+				if(sd[j] == 1u) {
+					e |= (c | (state & 1u)) << 31;
+					dst1[before1] = e;
+					before1++;
+					state = ((state >> 1) | c) << 1;               // pend1 = 0, pend2 |= c
+				}
+				else {
+					e |= (c | (state >> 1)) << 31;
+					dst2[i - before1] = e;
+					state = (state & 1u) | c;                      // pend2 = 0, pend1 |= c
+				}
+			}
+		}
+		const uint32_t tile_cnt = sm_cnt[SW_THREADS / 32], tile_map = sm_map[SW_THREADS / 32];
+		carry_cnt += tile_cnt;
+		carry_state = map_apply(tile_map, carry_state);
+		__syncthreads();
+	}
+}
+
+// stable partition of small u32 lists of scaffold ids (scaffold list: 1 "dimension"; SCG lists: D dimensions); one warp per (job, dimension)
+struct ListJob { uint32_t off, n, n1; };
+__global__ void k_partition_list(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t stride, const ListJob* __restrict__ jobs, const uint8_t* __restrict__ side,
+                                 uint32_t ndims)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t d = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if(d >= ndims)
+		return;
+	const ListJob jb = jobs[blockIdx.x];
+	const uint32_t* __restrict__ src = in + (uint64_t)d * stride + jb.off;
+	uint32_t* __restrict__ dst1 = out + (uint64_t)d * stride + jb.off;
+	uint32_t* __restrict__ dst2 = dst1 + jb.n1;
+	uint32_t c1 = 0;
+	for(uint32_t base = 0; base < jb.n; base += 32) {
+		const uint32_t i = base + lane;
+		uint32_t s = 0, sd = 0;
+		if(i < jb.n) {
+			s = src[i];
+			sd = side[s];
+		}
+		const uint32_t b1 = __ballot_sync(0xffffffffu, sd == 1u);
+		const uint32_t before = __popc(b1 & ((1u << lane) - 1u));
+		if(i < jb.n) {
+			if(sd == 1u) dst1[c1 + before] = s;
+			else dst2[i - (c1 + before)] = s;
+		}
+		c1 += __popc(b1);
+	}
+}
+
+// terminal cluster: bins of its scaffolds and datapoints (abawaca.cpp:135-138), total size and SCG tallies (ClusterQuality.cpp:44-48,78-87)
+struct TermJob { uint32_t sOff, ns, id, slot; };
+struct TermStats { unsigned long long total_size, scg_copies; };
+__global__ void k_finalize_terminal(const uint32_t* __restrict__ scaf_list, const TermJob* __restrict__ jobs, const ScafRow* __restrict__ rows, const uint8_t* __restrict__ assigned,
+                                    const uint64_t* __restrict__ scgmask, uint32_t W, uint32_t* __restrict__ scaf_member, uint32_t* __restrict__ scaf_final,
+                                    TermStats* __restrict__ stats, uint64_t* __restrict__ union_mask)
+{
+	const TermJob jb = jobs[blockIdx.y];
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.ns; i += gridDim.x * blockDim.x) {
+		const uint32_t s = scaf_list[jb.sOff + i];
+		scaf_member[s] = jb.id;
+		if(assigned[s]) {
+			scaf_final[s] = jb.id;
+			atomicAdd(&stats[jb.slot].total_size, (unsigned long long)rows[s].len);
+			uint32_t copies = 0;
+			for(uint32_t w = 0; w < W; w++) {
+				const uint64_t m = scgmask[(uint64_t)s * W + w];
+				if(m) {
+					copies += __popcll(m);
+					atomicOr((unsigned long long*)&union_mask[(uint64_t)jb.slot * W + w], (unsigned long long)m);
+				}
+			}
+			if(copies)
+				atomicAdd(&stats[jb.slot].scg_copies, (unsigned long long)copies);
+		}
+	}
+}
+
+__global__ void k_commit_assigned(const uint32_t* __restrict__ scaf_list, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs,
+                                  const uint8_t* __restrict__ new_assigned, uint8_t* __restrict__ assigned)
+{
+	const SplitJob jb = jobs[blockIdx.y];
+	const ClusterDesc cl = clusters[jb.cluster];
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cl.ns; i += gridDim.x * blockDim.x) {
+		const uint32_t s = scaf_list[cl.sOff + i];
+		assigned[s] = new_assigned[s] != 0;
+	}
+}
+
+__global__ void k_dp_bins(const uint32_t* __restrict__ dp2scaf, const uint32_t* __restrict__ scaf_member, uint64_t N, uint32_t* __restrict__ dp2cluster)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < N)
+		dp2cluster[i] = scaf_member[dp2scaf[i]];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// build: keys, within-scaffold classes, element packing
+// ---------------------------------------------------------------------------------------------------
+// tiled transpose of a row-major [N][ld] matrix (columns [d0, d0+nd)) into column-major [nd][N]
+__global__ void k_transpose_in(const double* __restrict__ rows, uint64_t ld, uint64_t N, uint32_t d0, uint32_t nd, double* __restrict__ cols)
+{
+	__shared__ double tile[32][33];
+	const uint64_t r0 = (uint64_t)blockIdx.x * 32;
+	const uint32_t c0 = blockIdx.y * 32;
+	for(int j = threadIdx.y; j < 32; j += blockDim.y) {
+		uint64_t r = r0 + j;
+		uint32_t c = c0 + threadIdx.x;
+		tile[j][threadIdx.x] = (r < N && c < nd)? rows[r * ld + d0 + c] : 0.0;
+	}
+	__syncthreads();
+	for(int j = threadIdx.y; j < 32; j += blockDim.y) {
+		uint32_t c = c0 + j;
+		uint64_t r = r0 + threadIdx.x;
+		if(r < N && c < nd)
+			cols[(uint64_t)c * N + r] = tile[threadIdx.x][j];
+	}
+}
+
+__global__ void k_make_keys(const double* __restrict__ values, uint64_t N, uint32_t nd, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ nan_flag)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t d = blockIdx.y;
+	if(i < N && d < nd) {
+		const double v = values[(uint64_t)d * N + i];
+		if(v != v)
+			atomicExch(nan_flag, 1);
+		keys[(uint64_t)d * N + i] = orderable(v);
+		vals[(uint64_t)d * N + i] = (uint32_t)i;
+	}
+}
+
+// class of every datapoint in every dimension of the chunk, from its rank inside its scaffold (ties by datapoint index,
+// the order a stable sort produces).  Thread per (datapoint, dimension).
+__global__ void k_rank_class(const double* __restrict__ values, uint64_t N, uint32_t nd, const uint32_t* __restrict__ dp2scaf, const uint64_t* __restrict__ dp_first,
+                             const ScafRow* __restrict__ rows, const uint8_t* __restrict__ has_scg, int strategy, double fraction_in, uint8_t* __restrict__ cls_out)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t d = blockIdx.y;
+	if(i >= N || d >= nd)
+		return;
+	const uint32_t s = dp2scaf[i];
+	const ScafRow r = rows[s];
+	const uint64_t f = dp_first[s];
+	const double* __restrict__ col = values + (uint64_t)d * N;
+	const unsigned long long ki = orderable(col[i]);
+	uint32_t a = 1;                                              // 1-based rank of this dp among the dps of its scaffold
+	for(uint64_t j = f; j < f + r.n; j++) {
+		const unsigned long long kj = orderable(col[j]);
+		a += (kj < ki) || (kj == ki && j < i);
+	}
+	uint32_t cls, aux;
+	if(strategy == ABW_SENS_SPEC) {
+		const uint32_t flip = r.T / 2 + 1;                       // first a with 2*a > T (...Specificity.cpp:125)
+		cls = (a < flip)? 0u : (a == flip)? 1u : 2u;
+		aux = (a == flip && has_scg[s])? 1u : 0u;
+	}
+	else {
+		const uint32_t r1 = (uint32_t)ceil(__dmul_rn(fraction_in, (double)r.T));   // first a with a >= fraction*T (...SplitScafs.h:85-86)
+		const uint32_t r2 = r.n - r1 + 1;                                             // the a whose removal drops side 2 below fraction*T
+		cls = (a < r1)? 0u : (a == r1)? 1u : 2u;
+		aux = (r1 > r.n)? 2u : ((a < r2)? 0u : (a == r2)? 1u : 2u);                   // r1 > n: the scaffold is never "in" either side
+	}
+	cls_out[(uint64_t)d * N + i] = (uint8_t)(cls | (aux << 2));
+}
+
+__global__ void k_pack_elements(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t N, uint32_t nd, const uint32_t* __restrict__ dp2scaf,
+                                const uint8_t* __restrict__ cls, uint32_t* __restrict__ E, const uint32_t* __restrict__ scg_index, uint32_t* __restrict__ flip_pos, uint64_t K)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t d = blockIdx.y;
+	if(i >= N || d >= nd)
+		return;
+	const uint64_t o = (uint64_t)d * N + i;
+	const uint32_t dp = vals[o];
+	const uint32_t s = dp2scaf[dp];
+	const uint32_t c = cls[(uint64_t)d * N + dp];
+	const uint32_t boundary = (i == 0) || (keys[o] != keys[o - 1]);
+	E[o] = s | ((c & 3u) << EL_CLASS_SHIFT) | (((c >> 2) & 3u) << EL_AUX_SHIFT) | (boundary? EL_BOUNDARY : 0u);
+	if(flip_pos != nullptr && (c & 3u) == 1u && ((c >> 2) & 1u))
+		flip_pos[(uint64_t)d * K + scg_index[s]] = (uint32_t)i;
+}
+
+__global__ void k_iota_pairs(unsigned long long* __restrict__ keys, const uint32_t* __restrict__ flip_pos, uint32_t* __restrict__ vals, const uint32_t* __restrict__ scg_scafs,
+                             uint64_t K, uint32_t nd)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t d = blockIdx.y;
+	if(i < K && d < nd) {
+		keys[(uint64_t)d * K + i] = flip_pos[(uint64_t)d * K + i];
+		vals[(uint64_t)d * K + i] = scg_scafs[i];
+	}
+}
+
+}  // namespace
+
+// ===================================================================================================
+// host side
+// ===================================================================================================
+struct HostCluster {
+	uint32_t id = 0, parent = 0;
+	ClusterDesc desc{};
+	uint32_t nassigned = 0;
+	std::vector<uint64_t> never;     // [W]
+};
+
+struct abw_search {
+	abw_ctx* ctx = nullptr;
+	uint64_t N = 0;
+	uint32_t D = 0, S = 0, W = 1, K = 0;
+	int strategy = 0;
+	abw_params prm{};
+	DevBuf<double> values;
+	DevBuf<uint32_t> dp2scaf;
+	DevBuf<uint64_t> dp_first;
+	DevBuf<ScafRow> rows;
+	DevBuf<uint64_t> scgmask;
+	DevBuf<uint8_t> has_scg;
+	DevBuf<uint32_t> E[2];
+	DevBuf<uint32_t> scg_list[2];
+	DevBuf<uint32_t> scaf_list[2];
+	DevBuf<uint8_t> side, assigned, new_assigned;
+	DevBuf<uint32_t> low, scaf_member, scaf_final;
+	std::vector<uint32_t> h_T;
+	std::vector<uint64_t> h_len, h_mask;
+	std::vector<uint32_t> h_n;
+	uint64_t root_totT = 0, root_totLen = 0;
+	uint32_t root_viol = 0;
+	std::vector<uint64_t> root_never;
+	bool consumed = false;
+	abw_search_profile prof{};
+};
+
+namespace {
+
+struct EventTimer {
+	cudaEvent_t a = nullptr, b = nullptr;
+	cudaStream_t st;
+	explicit EventTimer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); }
+	~EventTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+	void start() { cudaEventRecord(a, st); }
+	float stop() { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+};
+
+template <typename T>
+int upload(abw_ctx* ctx, DevBuf<T>& buf, const std::vector<T>& h)
+{
+	ABW_CUDA(ctx, buf.alloc(h.size()));
+	if(!h.empty())
+		ABW_CUDA(ctx, cudaMemcpyAsync(buf.p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+	return ABW_OK;
+}
+
+int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_on_device, int layout, uint64_t ld, const uint32_t* h_dp2scaf)
+{
+	const uint64_t N = s->N;
+	const uint32_t D = s->D, S = s->S, W = s->W;
+	// ---- host-side per-scaffold tables
+	s->h_n.assign(S, 0);
+	std::vector<uint64_t> first((size_t)S + 1, 0);
+	for(uint64_t i = 0; i < N; i++) {
+		if(h_dp2scaf[i] >= S)
+			return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: dp2scaf entry out of range");
+		if(i > 0 && h_dp2scaf[i] < h_dp2scaf[i - 1])
+			return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: datapoints must be grouped by scaffold in scaffold order (ScafDpData.cpp:91-99)");
+		s->h_n[h_dp2scaf[i]]++;
+	}
+	std::vector<ScafRow> rows(S);
+	std::vector<uint8_t> has(S, 0);
+	std::vector<uint32_t> scg_scafs, scg_index(S, 0);
+	s->root_never.assign(W, 0);
+	s->root_totT = s->root_totLen = 0;
+	s->root_viol = 0;
+	for(uint32_t i = 0; i < S; i++) {
+		first[i + 1] = first[i] + s->h_n[i];
+		if(s->h_T[i] < 2)
+			return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: every scaffold needs T >= 2 datapoints (ScafDpData.cpp:92-93 drops the others)");
+		if(s->h_n[i] == 0 || s->h_n[i] > s->h_T[i])
+			return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: every scaffold needs between 1 and T datapoints in the matrix");
+		rows[i].T = s->h_T[i];
+		rows[i].n = s->h_n[i];
+		rows[i].len = s->h_len[i];
+		s->root_totT += s->h_T[i];
+		s->root_totLen += s->h_len[i];
+		bool any = false;
+		for(uint32_t w = 0; w < W; w++)
+			any |= s->h_mask[(size_t)i * W + w] != 0;
+		has[i] = any;
+		if(any) {
+			if(s->h_n[i] >= s->h_T[i] / 2 + 1) {
+				scg_index[i] = (uint32_t)scg_scafs.size();
+				scg_scafs.push_back(i);
+			}
+			else
+				for(uint32_t w = 0; w < W; w++)
+					s->root_never[w] |= s->h_mask[(size_t)i * W + w];
+		}
+		if(!((double)s->h_n[i] >= s->prm.fraction_dps_in * (double)s->h_T[i]))
+			s->root_viol++;
+	}
+	if(s->root_totT >= (1ull << 31))
+		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: sum of T over scaffolds must be below 2^31");
+	s->K = (uint32_t)scg_scafs.size();
+	const uint64_t K = s->K;
+	ABW_CHECK(upload(ctx, s->rows, rows));
+	ABW_CHECK(upload(ctx, s->has_scg, has));
+	ABW_CHECK(upload(ctx, s->dp_first, first));
+	ABW_CHECK(upload(ctx, s->scgmask, s->h_mask));
+	{
+		std::vector<uint32_t> v(h_dp2scaf, h_dp2scaf + N);
+		ABW_CHECK(upload(ctx, s->dp2scaf, v));
+	}
+	DevBuf<uint32_t> d_scg_scafs, d_scg_index;
+	ABW_CHECK(upload(ctx, d_scg_scafs, scg_scafs));
+	ABW_CHECK(upload(ctx, d_scg_index, scg_index));
+	// ---- values, column major on the device
+	ABW_CUDA(ctx, s->values.alloc((size_t)D * N));
+	if(layout == ABW_LAYOUT_COLMAJOR) {
+		ABW_CUDA(ctx, cudaMemcpy2DAsync(s->values.p, N * sizeof(double), values, ld * sizeof(double), N * sizeof(double), D,
+		                                values_on_device? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+	}
+	else {
+		DevBuf<double> tmp;
+		const double* src = values;
+		if(!values_on_device) {
+			ABW_CUDA(ctx, tmp.alloc((size_t)N * ld));
+			ABW_CUDA(ctx, cudaMemcpyAsync(tmp.p, values, sizeof(double) * N * ld, cudaMemcpyHostToDevice, ctx->stream));
+			src = tmp.p;
+		}
+		dim3 grid(abw_div_up(N, 32), abw_div_up(D, 32)), block(32, 8);
+		ABW_LAUNCH(ctx, k_transpose_in, grid, block, 0, src, ld, N, 0u, D, s->values.p);
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	// ---- per-dimension order, classes, elements; dimensions are processed in chunks to bound scratch memory
+	for(int b = 0; b < 2; b++) {
+		ABW_CUDA(ctx, s->E[b].alloc((size_t)D * N));
+		ABW_CUDA(ctx, s->scg_list[b].alloc((size_t)D * K));
+		ABW_CUDA(ctx, s->scaf_list[b].alloc(S));
+	}
+	size_t free_b = 0, total_b = 0;
+	ABW_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+	const uint64_t per_dim = N * (8 + 8 + 4 + 4 + 1) + 4096;
+	uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(D, (free_b / 2) / per_dim));
+	DevBuf<unsigned long long> keys, keys_tmp;
+	DevBuf<uint32_t> vals, vals_tmp, flip_pos;
+	DevBuf<uint8_t> cls;
+	DevBuf<int> nan_flag;
+	ABW_CUDA(ctx, keys.alloc((size_t)chunk * N));
+	ABW_CUDA(ctx, keys_tmp.alloc((size_t)chunk * N));
+	ABW_CUDA(ctx, vals.alloc((size_t)chunk * N));
+	ABW_CUDA(ctx, vals_tmp.alloc((size_t)chunk * N));
+	ABW_CUDA(ctx, cls.alloc((size_t)chunk * N));
+	ABW_CUDA(ctx, flip_pos.alloc((size_t)D * K));
+	ABW_CUDA(ctx, nan_flag.alloc(1));
+	ABW_CUDA(ctx, cudaMemsetAsync(nan_flag.p, 0, sizeof(int), ctx->stream));
+	for(uint32_t d0 = 0; d0 < D; d0 += chunk) {
+		const uint32_t nd = std::min(chunk, D - d0);
+		dim3 grid(abw_div_up(N, 256), nd);
+		const double* vchunk = s->values.p + (uint64_t)d0 * N;
+		ABW_LAUNCH(ctx, k_make_keys, grid, 256, 0, vchunk, N, nd, keys.p, vals.p, nan_flag.p);
+		ABW_LAUNCH(ctx, k_rank_class, grid, 256, 0, vchunk, N, nd, s->dp2scaf.p, s->dp_first.p, s->rows.p, s->has_scg.p, s->strategy, s->prm.fraction_dps_in, cls.p);
+		ABW_CHECK(abw_radix_sort_pairs_u64(ctx, (uint64_t*)keys.p, (uint64_t*)keys_tmp.p, vals.p, vals_tmp.p, N, nd, N, 64));
+		ABW_LAUNCH(ctx, k_pack_elements, grid, 256, 0, keys.p, vals.p, N, nd, s->dp2scaf.p, cls.p, s->E[0].p + (uint64_t)d0 * N, d_scg_index.p,
+		           (s->strategy == ABW_SENS_SPEC && K > 0)? flip_pos.p + (uint64_t)d0 * K : nullptr, K);
+	}
+	int h_nan = 0;
+	ABW_CUDA(ctx, cudaMemcpyAsync(&h_nan, nan_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if(h_nan)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: NaN in the feature matrix (comp_by_value is not a strict weak order on NaN)");
+	keys.release(); keys_tmp.release(); vals.release(); vals_tmp.release(); cls.release();
+	// ---- per-dimension list of SCG-carrying scaffolds in the order their flip element appears
+	if(s->strategy == ABW_SENS_SPEC && K > 0) {
+		DevBuf<unsigned long long> lk, lk_tmp;
+		DevBuf<uint32_t> lv_tmp;
+		ABW_CUDA(ctx, lk.alloc((size_t)D * K));
+		ABW_CUDA(ctx, lk_tmp.alloc((size_t)D * K));
+		ABW_CUDA(ctx, lv_tmp.alloc((size_t)D * K));
+		dim3 grid(abw_div_up(K, 256), D);
+		ABW_LAUNCH(ctx, k_iota_pairs, grid, 256, 0, lk.p, flip_pos.p, s->scg_list[0].p, d_scg_scafs.p, K, D);
+		int nbits = 1;
+		while(nbits < 32 && (1ull << nbits) < N)
+			nbits++;
+		ABW_CHECK(abw_radix_sort_pairs_u64(ctx, (uint64_t*)lk.p, (uint64_t*)lk_tmp.p, s->scg_list[0].p, lv_tmp.p, K, D, K, nbits));
+	}
+	// ---- root cluster
+	{
+		std::vector<uint32_t> iota(S);
+		for(uint32_t i = 0; i < S; i++)
+			iota[i] = i;
+		ABW_CUDA(ctx, cudaMemcpyAsync(s->scaf_list[0].p, iota.data(), sizeof(uint32_t) * S, cudaMemcpyHostToDevice, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	ABW_CUDA(ctx, s->side.alloc(S));
+	ABW_CUDA(ctx, s->assigned.alloc(S));
+	ABW_CUDA(ctx, s->new_assigned.alloc(S));
+	ABW_CUDA(ctx, s->low.alloc(S));
+	ABW_CUDA(ctx, s->scaf_member.alloc(S));
+	ABW_CUDA(ctx, s->scaf_final.alloc(S));
+	ABW_CUDA(ctx, cudaMemsetAsync(s->assigned.p, 1, S, ctx->stream));
+	ABW_CUDA(ctx, cudaMemsetAsync(s->low.p, 0, sizeof(uint32_t) * S, ctx->stream));
+	ABW_CUDA(ctx, cudaMemsetAsync(s->scaf_member.p, 0, sizeof(uint32_t) * S, ctx->stream));
+	ABW_CUDA(ctx, cudaMemsetAsync(s->scaf_final.p, 0, sizeof(uint32_t) * S, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return ABW_OK;
+}
+
+bool is_legal(const abw_params& p, int strategy, const abw_best& b)
+{
+	if(!b.found)
+		return false;
+	if(strategy == ABW_SENS_SPEC)       // ...Specificity.h:31-35
+		return (b.a >= p.sensitivity_threshold) && (b.b >= p.specificity_threshold) && (b.a + b.b >= p.sum_threshold) && (b.a * b.b >= p.product_threshold);
+	return b.a <= p.split_scaf_ratio_threshold;   // ...SplitScafs.h:38
+}
+
+template <typename T>
+int to_device(abw_ctx* ctx, DevBuf<T>& buf, const std::vector<T>& h)
+{
+	if(buf.n < h.size())
+		ABW_CUDA(ctx, buf.alloc(std::max<size_t>(h.size(), 64)));
+	if(!h.empty())
+		ABW_CUDA(ctx, cudaMemcpyAsync(buf.p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+	return ABW_OK;
+}
+
+int search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t cap, uint32_t* nrecs, uint32_t* h_dp2cluster, uint32_t* h_scaf2cluster)
+{
+	const uint64_t N = s->N;
+	const uint32_t D = s->D, S = s->S, W = s->W;
+	const abw_params& prm = s->prm;
+	if(s->consumed)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_run: this search object was already run (element arrays are consumed); create a new one");
+	s->consumed = true;
+	EventTimer tm(ctx->stream);
+	s->prof.sweep_ms = s->prof.partition_ms = s->prof.other_ms = 0;
+	s->prof.sweep_elements = s->prof.partition_elements = 0;
+	s->prof.levels = s->prof.sweep_launches = 0;
+
+	SweepParams sp;
+	sp.thr = prm.cluster_ndps_threshold;
+	sp.min_score = prm.min_reported_score;
+	sp.prune = (float)(prm.min_reported_score * (1.0 - 1e-5)) ;
+	if(!(sp.prune > 0.0f))
+		sp.prune = 0.0f;
+	sp.scg_min_size = prm.scg_min_size;
+	sp.fraction_in = prm.fraction_dps_in;
+
+	std::vector<HostCluster> level(1);
+	level[0].id = 1;
+	level[0].parent = 0;
+	level[0].desc.off = 0;
+	level[0].desc.n = (uint32_t)N;
+	level[0].desc.kOff = 0;
+	level[0].desc.K = s->K;
+	level[0].desc.sOff = 0;
+	level[0].desc.ns = S;
+	level[0].desc.totT = (uint32_t)s->root_totT;
+	level[0].desc.U = S;
+	level[0].desc.totLen = s->root_totLen;
+	level[0].desc.ss_ok = (s->root_viol == 0);
+	level[0].nassigned = S;
+	level[0].never = s->root_never;
+	uint32_t next_id = 2, nrec = 0;
+	int cur = 0;
+
+	DevBuf<ClusterDesc> d_clusters;
+	DevBuf<CandRec> d_cand, d_best;
+	DevBuf<uint8_t> d_tab;
+	DevBuf<uint64_t> d_suffix, d_never, d_child_never, d_union;
+	DevBuf<SplitJob> d_jobs;
+	DevBuf<ChildStats> d_stats;
+	DevBuf<unsigned long long> d_value_key;
+	DevBuf<PartJob> d_pjobs;
+	DevBuf<ListJob> d_ljobs_scaf, d_ljobs_scg;
+	DevBuf<TermJob> d_tjobs;
+	DevBuf<TermStats> d_tstats;
+	if(s->strategy == ABW_SENS_SPEC)
+		ABW_CUDA(ctx, d_suffix.alloc((size_t)D * std::max<uint32_t>(s->K, 1) * W));
+
+	auto emit = [&](const abw_cluster_rec& r) {
+		if(nrec < cap && h_recs)
+			h_recs[nrec] = r;
+		nrec++;
+	};
+
+	while(!level.empty()) {
+		s->prof.levels++;
+		const uint32_t C = (uint32_t)level.size();
+		// pass-table offsets
+		uint32_t tab_total = 0;
+		std::vector<ClusterDesc> descs(C);
+		std::vector<uint64_t> never((size_t)C * W, 0);
+		for(uint32_t c = 0; c < C; c++) {
+			level[c].desc.tabOff = tab_total;
+			tab_total += level[c].desc.K + 1;
+			descs[c] = level[c].desc;
+			for(uint32_t w = 0; w < W; w++)
+				never[(size_t)c * W + w] = level[c].never.empty()? 0 : level[c].never[w];
+		}
+		ABW_CHECK(to_device(ctx, d_clusters, descs));
+		ABW_CHECK(to_device(ctx, d_never, never));
+		if(d_cand.n < (size_t)C * D)
+			ABW_CUDA(ctx, d_cand.alloc((size_t)C * D));
+		if(d_best.n < C)
+			ABW_CUDA(ctx, d_best.alloc(C));
+		const uint64_t tab_stride = tab_total;
+		if(s->strategy == ABW_SENS_SPEC) {
+			if(d_tab.n < (size_t)D * tab_stride)
+				ABW_CUDA(ctx, d_tab.alloc((size_t)D * tab_stride));
+			tm.start();
+			ABW_LAUNCH(ctx, k_pass_table, dim3(C, abw_div_up(D, 4)), 128, 0, s->scg_list[cur].p, (uint64_t)s->K, d_clusters.p, s->scgmask.p, W, d_never.p,
+			           prm.scg_overlap_threshold, d_suffix.p, d_tab.p, tab_stride, D);
+			s->prof.other_ms += tm.stop();
+		}
+		// sweep
+		tm.start();
+		{
+			dim3 grid(C, D);
+			if(s->strategy == ABW_SENS_SPEC)
+				ABW_LAUNCH(ctx, k_sweep<ABW_SENS_SPEC>, grid, SW_THREADS, 0, s->E[cur].p, N, d_clusters.p, s->rows.p, d_tab.p, tab_stride, sp, d_cand.p);
+			else
+				ABW_LAUNCH(ctx, k_sweep<ABW_SPLIT_SCAFS>, grid, SW_THREADS, 0, s->E[cur].p, N, d_clusters.p, s->rows.p, (const uint8_t*)nullptr, tab_stride, sp, d_cand.p);
+		}
+		s->prof.sweep_ms += tm.stop();
+		s->prof.sweep_launches++;
+		for(uint32_t c = 0; c < C; c++)
+			s->prof.sweep_elements += (uint64_t)level[c].desc.n * D;
+		tm.start();
+		if(s->strategy == ABW_SENS_SPEC)
+			ABW_LAUNCH(ctx, k_reduce_best<ABW_SENS_SPEC>, C, 32, 0, d_cand.p, D, d_best.p);
+		else
+			ABW_LAUNCH(ctx, k_reduce_best<ABW_SPLIT_SCAFS>, C, 32, 0, d_cand.p, D, d_best.p);
+		std::vector<CandRec> best(C);
+		ABW_CUDA(ctx, cudaMemcpyAsync(best.data(), d_best.p, sizeof(CandRec) * C, cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		// host: scores, legality (same IEEE operations as ClusterStats::get_sensitivity/get_specificity, .h:74-75)
+		std::vector<abw_best> hb(C);
+		std::vector<SplitJob> jobs;          // every cluster with a best separation: value recovery; legal ones: children
+		std::vector<uint32_t> job_of(C, UINT32_MAX);
+		for(uint32_t c = 0; c < C; c++) {
+			abw_best b;
+			memset(&b, 0, sizeof(b));
+			b.value = -1;
+			if(s->strategy == ABW_SPLIT_SCAFS) { b.a = 1000000; b.b = 1000000; }
+			if(best[c].found) {
+				b.found = 1;
+				b.dim = best[c].dim0 + 1;
+				if(s->strategy == ABW_SENS_SPEC) {
+					b.a = (double)(int)best[c].i0 / (double)(int)best[c].i1;
+					b.b = (double)(int)best[c].i0 / (double)(int)best[c].i2;
+				}
+				else {
+					b.a = best[c].k1;
+					b.b = best[c].k2;
+				}
+				b.legal = is_legal(prm, s->strategy, b);
+				SplitJob jb;
+				jb.cluster = c;
+				jb.dim0 = best[c].dim0;
+				jb.p = best[c].p;
+				jb.swapped = (level[c].desc.n - best[c].p) < best[c].p;      // ClusterSeparator.cpp:49
+				job_of[c] = (uint32_t)jobs.size();
+				jobs.push_back(jb);
+			}
+			hb[c] = b;
+		}
+		const uint32_t J = (uint32_t)jobs.size();
+		std::vector<ChildStats> stats((size_t)J * 2);
+		std::vector<unsigned long long> vkeys(J, 0);
+		std::vector<uint64_t> child_never((size_t)J * 2 * W, 0);
+		if(J > 0) {
+			ABW_CHECK(to_device(ctx, d_jobs, jobs));
+			if(d_stats.n < (size_t)J * 2) ABW_CUDA(ctx, d_stats.alloc((size_t)J * 2));
+			if(d_value_key.n < J) ABW_CUDA(ctx, d_value_key.alloc(J));
+			if(d_child_never.n < (size_t)J * 2 * W) ABW_CUDA(ctx, d_child_never.alloc((size_t)J * 2 * W));
+			ABW_CUDA(ctx, cudaMemsetAsync(d_stats.p, 0, sizeof(ChildStats) * J * 2, ctx->stream));
+			ABW_CUDA(ctx, cudaMemsetAsync(d_value_key.p, 0, sizeof(unsigned long long) * J, ctx->stream));
+			ABW_CUDA(ctx, cudaMemsetAsync(d_child_never.p, 0, sizeof(uint64_t) * J * 2 * W, ctx->stream));
+			dim3 g1(std::min<uint32_t>(abw_div_up(N, 256), 4u * ctx->sm_count), J);
+			ABW_LAUNCH(ctx, k_count_low, g1, 256, 0, s->E[cur].p, N, d_clusters.p, d_jobs.p, s->low.p);
+			dim3 g2(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), J);
+			ABW_LAUNCH(ctx, k_scaf_sides, g2, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs.p, s->rows.p, s->low.p, s->dp_first.p, s->values.p, N, s->scgmask.p, W,
+			           s->strategy, prm.fraction_dps_in, s->side.p, s->new_assigned.p, d_stats.p, d_child_never.p, d_value_key.p);
+			ABW_LAUNCH(ctx, k_clear_low, g2, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs.p, s->low.p);
+			ABW_CUDA(ctx, cudaMemcpyAsync(stats.data(), d_stats.p, sizeof(ChildStats) * J * 2, cudaMemcpyDeviceToHost, ctx->stream));
+			ABW_CUDA(ctx, cudaMemcpyAsync(vkeys.data(), d_value_key.p, sizeof(unsigned long long) * J, cudaMemcpyDeviceToHost, ctx->stream));
+			ABW_CUDA(ctx, cudaMemcpyAsync(child_never.data(), d_child_never.p, sizeof(uint64_t) * J * 2 * W, cudaMemcpyDeviceToHost, ctx->stream));
+			ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		}
+		// decide
+		std::vector<HostCluster> next;
+		std::vector<PartJob> pjobs;
+		std::vector<ListJob> ljobs_scaf, ljobs_scg;
+		std::vector<SplitJob> commit_jobs;
+		std::vector<TermJob> tjobs;
+		std::vector<abw_cluster_rec> recs(C);
+		for(uint32_t c = 0; c < C; c++) {
+			abw_cluster_rec r;
+			memset(&r, 0, sizeof(r));
+			r.id = level[c].id;
+			r.parent = level[c].parent;
+			r.ndps = level[c].desc.n;
+			r.nscafs = level[c].nassigned;
+			r.best = hb[c];
+			bool split = false;
+			if(hb[c].found) {
+				const uint32_t j = job_of[c];
+				unsigned long long k = vkeys[j];
+				unsigned long long bits = (k >> 63)? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+				double v;
+				memcpy(&v, &bits, sizeof(v));
+				r.best.value = v;
+				if(hb[c].legal) {
+					const ChildStats& s1 = stats[(size_t)j * 2], &s2 = stats[(size_t)j * 2 + 1];
+					split = !(s1.ndps < prm.cluster_ndps_threshold || s2.ndps < prm.cluster_ndps_threshold);   // ClusterSeparator.cpp:125
+					if(split) {
+						r.split = 1;
+						r.child1 = next_id++;
+						r.child2 = next_id++;
+						r.child1_ndps = s1.ndps; r.child2_ndps = s2.ndps;
+						r.child1_nscafs = s1.nassigned; r.child2_nscafs = s2.nassigned;
+						r.child1_raw = jobs[j].swapped? level[c].desc.n - jobs[j].p : jobs[j].p;
+						r.child2_raw = level[c].desc.n - r.child1_raw;
+						const ChildStats* st[2] = {&s1, &s2};
+						uint64_t off = level[c].desc.off;
+						uint32_t kOff = level[c].desc.kOff, sOff = level[c].desc.sOff;
+						for(int ch = 0; ch < 2; ch++) {
+							HostCluster hc;
+							hc.id = ch? r.child2 : r.child1;
+							hc.parent = r.id;
+							hc.desc.off = off;
+							hc.desc.n = (uint32_t)st[ch]->ndps;
+							hc.desc.kOff = kOff;
+							hc.desc.K = st[ch]->K;
+							hc.desc.sOff = sOff;
+							hc.desc.ns = st[ch]->ns;
+							hc.desc.totT = st[ch]->totT;
+							hc.desc.U = st[ch]->ns;
+							hc.desc.totLen = st[ch]->totLen;
+							hc.desc.ss_ok = (st[ch]->viol == 0);
+							hc.nassigned = st[ch]->nassigned;
+							hc.never.assign(child_never.begin() + ((size_t)j * 2 + ch) * W, child_never.begin() + ((size_t)j * 2 + ch + 1) * W);
+							off += st[ch]->ndps;
+							kOff += st[ch]->K;
+							sOff += st[ch]->ns;
+							next.push_back(hc);
+						}
+						PartJob pj;
+						pj.off = level[c].desc.off; pj.n = level[c].desc.n; pj.n1 = (uint32_t)s1.ndps;
+						pjobs.push_back(pj);
+						ListJob l1; l1.off = level[c].desc.sOff; l1.n = level[c].desc.ns; l1.n1 = s1.ns;
+						ljobs_scaf.push_back(l1);
+						ListJob l2; l2.off = level[c].desc.kOff; l2.n = level[c].desc.K; l2.n1 = s1.K;
+						ljobs_scg.push_back(l2);
+						commit_jobs.push_back(jobs[j]);
+					}
+					else {
+						// children too small: best_separation->reset() (ClusterSeparator.cpp:125-132)
+						memset(&r.best, 0, sizeof(r.best));
+						r.best.value = -1;
+						if(s->strategy == ABW_SPLIT_SCAFS) { r.best.a = 1000000; r.best.b = 1000000; }
+					}
+				}
+			}
+			if(!split) {
+				TermJob tj;
+				tj.sOff = level[c].desc.sOff; tj.ns = level[c].desc.ns; tj.id = level[c].id; tj.slot = (uint32_t)tjobs.size();
+				tjobs.push_back(tj);
+			}
+			recs[c] = r;
+		}
+		s->prof.other_ms += tm.stop();   // includes the host decisions; kernels here are small
+		// terminal clusters
+		tm.start();
+		if(!tjobs.empty()) {
+			const uint32_t Tn = (uint32_t)tjobs.size();
+			ABW_CHECK(to_device(ctx, d_tjobs, tjobs));
+			if(d_tstats.n < Tn) ABW_CUDA(ctx, d_tstats.alloc(Tn));
+			if(d_union.n < (size_t)Tn * W) ABW_CUDA(ctx, d_union.alloc((size_t)Tn * W));
+			ABW_CUDA(ctx, cudaMemsetAsync(d_tstats.p, 0, sizeof(TermStats) * Tn, ctx->stream));
+			ABW_CUDA(ctx, cudaMemsetAsync(d_union.p, 0, sizeof(uint64_t) * Tn * W, ctx->stream));
+			dim3 g(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), Tn);
+			ABW_LAUNCH(ctx, k_finalize_terminal, g, 128, 0, s->scaf_list[cur].p, d_tjobs.p, s->rows.p, s->assigned.p, s->scgmask.p, W, s->scaf_member.p, s->scaf_final.p,
+			           d_tstats.p, d_union.p);
+			std::vector<TermStats> ts(Tn);
+			std::vector<uint64_t> un((size_t)Tn * W);
+			ABW_CUDA(ctx, cudaMemcpyAsync(ts.data(), d_tstats.p, sizeof(TermStats) * Tn, cudaMemcpyDeviceToHost, ctx->stream));
+			ABW_CUDA(ctx, cudaMemcpyAsync(un.data(), d_union.p, sizeof(uint64_t) * Tn * W, cudaMemcpyDeviceToHost, ctx->stream));
+			ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			uint32_t t = 0;
+			for(uint32_t c = 0; c < C; c++) {
+				if(recs[c].split)
+					continue;
+				uint32_t u = 0;
+				for(uint32_t w = 0; w < W; w++)
+					u += (uint32_t)__builtin_popcountll(un[(size_t)t * W + w]);
+				recs[c].total_size = ts[t].total_size;
+				recs[c].scg_unique = u;
+				recs[c].scg_avg = (ts[t].scg_copies == 0)? 0 : (double)ts[t].scg_copies / (double)u;   // SCGdb.cpp:54
+				t++;
+			}
+		}
+		for(uint32_t c = 0; c < C; c++)
+			emit(recs[c]);
+		s->prof.other_ms += tm.stop();
+		// partition the split clusters
+		if(!pjobs.empty()) {
+			const uint32_t P = (uint32_t)pjobs.size();
+			ABW_CHECK(to_device(ctx, d_pjobs, pjobs));
+			ABW_CHECK(to_device(ctx, d_ljobs_scaf, ljobs_scaf));
+			ABW_CHECK(to_device(ctx, d_ljobs_scg, ljobs_scg));
+			ABW_CHECK(to_device(ctx, d_jobs, commit_jobs));
+			tm.start();
+			{
+				dim3 g(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), P);
+				ABW_LAUNCH(ctx, k_commit_assigned, g, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs.p, s->new_assigned.p, s->assigned.p);
+				ABW_LAUNCH(ctx, k_partition_list, dim3(P, 1), 32, 0, s->scaf_list[cur].p, s->scaf_list[cur ^ 1].p, (uint64_t)S, d_ljobs_scaf.p, s->side.p, 1u);
+				if(s->strategy == ABW_SENS_SPEC && s->K > 0)
+					ABW_LAUNCH(ctx, k_partition_list, dim3(P, abw_div_up(D, 4)), 128, 0, s->scg_list[cur].p, s->scg_list[cur ^ 1].p, (uint64_t)s->K, d_ljobs_scg.p, s->side.p, D);
+			}
+			s->prof.other_ms += tm.stop();
+			tm.start();
+			ABW_LAUNCH(ctx, k_partition, dim3(P, D), SW_THREADS, 0, s->E[cur].p, s->E[cur ^ 1].p, N, d_pjobs.p, s->side.p);
+			s->prof.partition_ms += tm.stop();
+			for(uint32_t i = 0; i < P; i++)
+				s->prof.partition_elements += (uint64_t)pjobs[i].n * D;
+			cur ^= 1;
+		}
+		level.swap(next);
+	}
+	if(nrecs)
+		*nrecs = nrec;
+	if(h_scaf2cluster)
+		ABW_CUDA(ctx, cudaMemcpyAsync(h_scaf2cluster, s->scaf_final.p, sizeof(uint32_t) * S, cudaMemcpyDeviceToHost, ctx->stream));
+	if(h_dp2cluster) {
+		DevBuf<uint32_t> d_dp;
+		ABW_CUDA(ctx, d_dp.alloc(N));
+		ABW_LAUNCH(ctx, k_dp_bins, abw_div_up(N, 256), 256, 0, s->dp2scaf.p, s->scaf_member.p, N, d_dp.p);
+		ABW_CUDA(ctx, cudaMemcpyAsync(h_dp2cluster, d_dp.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return ABW_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, int layout, uint64_t ld, uint64_t N, uint32_t D,
+                      const uint32_t* h_dp2scaf, uint32_t S, const uint32_t* h_T, const uint64_t* h_len, const uint64_t* h_scgmask, uint32_t W,
+                      const abw_params* params, int strategy, abw_search** out)
+{
+	if(!ctx || !out || !values || !h_dp2scaf || !h_T || !h_len || (W > 0 && !h_scgmask))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: null argument");
+	if(strategy != ABW_SENS_SPEC && strategy != ABW_SPLIT_SCAFS)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: unknown strategy");
+	if(N == 0 || D == 0 || S == 0)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: empty problem");
+	if(W > SCG_WMAX)
+		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: at most 512 distinct SCG names (W <= 8)");
+	if(N >= (1ull << 31) || S >= (1u << EL_SCAF_BITS))
+		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: at most 2^31-1 datapoints and 2^27-1 scaffolds per device");
+	if((layout == ABW_LAYOUT_COLMAJOR && ld < N) || (layout == ABW_LAYOUT_ROWMAJOR && ld < D))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: leading dimension too small");
+	ABW_CUDA(ctx, cudaSetDevice(ctx->device));
+	abw_search* s = new abw_search();
+	s->ctx = ctx;
+	s->N = N; s->D = D; s->S = S; s->W = (W == 0)? 1 : W;
+	s->strategy = strategy;
+	if(params)
+		s->prm = *params;
+	else
+		abw_default_params(&s->prm);
+	s->h_T.assign(h_T, h_T + S);
+	s->h_len.assign(h_len, h_len + S);
+	s->h_mask.assign((size_t)S * s->W, 0);
+	if(W > 0)
+		memcpy(s->h_mask.data(), h_scgmask, sizeof(uint64_t) * (size_t)S * W);
+	EventTimer tm(ctx->stream);
+	tm.start();
+	int rc = search_build(ctx, s, values, values_on_device, layout, ld, h_dp2scaf);
+	s->prof.build_ms = tm.stop();
+	if(rc != ABW_OK) {
+		delete s;
+		return rc;
+	}
+	*out = s;
+	return ABW_OK;
+}
+
+void abw_search_destroy(abw_search* s) { delete s; }
+
+int abw_search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t cap, uint32_t* nrecs, uint32_t* h_dp2cluster, uint32_t* h_scaf2cluster)
+{
+	if(!ctx || !s)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_run: null argument");
+	ABW_CUDA(ctx, cudaSetDevice(ctx->device));
+	return search_run(ctx, s, h_recs, cap, nrecs, h_dp2cluster, h_scaf2cluster);
+}
+
+int abw_search_get_profile(const abw_search* s, abw_search_profile* out)
+{
+	if(!s || !out)
+		return ABW_ERR_ARG;
+	*out = s->prof;
+	return ABW_OK;
+}
+
+int abw_cluster_scg(abw_ctx* ctx, const abw_search* s, const uint32_t* h_scafs, uint32_t nscafs, uint32_t* nunique, double* avg)
+{
+	if(!ctx || !s || (!h_scafs && nscafs))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_cluster_scg: null argument");
+	// SCGdb::num_unique_scgs / average_num_copies_for_unique_scgs (SCGdb.cpp:6-18,41-55) through the same terminal-cluster kernel
+	DevBuf<uint32_t> d_list;
+	DevBuf<TermJob> d_job;
+	DevBuf<TermStats> d_st;
+	DevBuf<uint64_t> d_un;
+	DevBuf<uint32_t> d_member, d_final;
+	DevBuf<uint8_t> d_assigned;
+	for(uint32_t i = 0; i < nscafs; i++)
+		if(h_scafs[i] >= s->S)
+			return abw_fail(ctx, ABW_ERR_ARG, "abw_cluster_scg: scaffold index out of range");
+	ABW_CUDA(ctx, d_list.alloc(nscafs));
+	ABW_CUDA(ctx, d_job.alloc(1));
+	ABW_CUDA(ctx, d_st.alloc(1));
+	ABW_CUDA(ctx, d_un.alloc(s->W));
+	ABW_CUDA(ctx, d_member.alloc(s->S));
+	ABW_CUDA(ctx, d_final.alloc(s->S));
+	ABW_CUDA(ctx, d_assigned.alloc(s->S));
+	TermJob tj; tj.sOff = 0; tj.ns = nscafs; tj.id = 1; tj.slot = 0;
+	if(nscafs)
+		ABW_CUDA(ctx, cudaMemcpyAsync(d_list.p, h_scafs, sizeof(uint32_t) * nscafs, cudaMemcpyHostToDevice, ctx->stream));
+	ABW_CUDA(ctx, cudaMemcpyAsync(d_job.p, &tj, sizeof(tj), cudaMemcpyHostToDevice, ctx->stream));
+	ABW_CUDA(ctx, cudaMemsetAsync(d_st.p, 0, sizeof(TermStats), ctx->stream));
+	ABW_CUDA(ctx, cudaMemsetAsync(d_un.p, 0, sizeof(uint64_t) * s->W, ctx->stream));
+	ABW_CUDA(ctx, cudaMemsetAsync(d_assigned.p, 1, s->S, ctx->stream));
+	if(nscafs)
+		ABW_LAUNCH(ctx, k_finalize_terminal, dim3(abw_div_up(nscafs, 128), 1), 128, 0, d_list.p, d_job.p, s->rows.p, d_assigned.p, s->scgmask.p, s->W, d_member.p, d_final.p, d_st.p, d_un.p);
+	TermStats ts;
+	std::vector<uint64_t> un(s->W);
+	ABW_CUDA(ctx, cudaMemcpyAsync(&ts, d_st.p, sizeof(ts), cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaMemcpyAsync(un.data(), d_un.p, sizeof(uint64_t) * s->W, cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	uint32_t u = 0;
+	for(uint32_t w = 0; w < s->W; w++)
+		u += (uint32_t)__builtin_popcountll(un[w]);
+	if(nunique) *nunique = u;
+	if(avg) *avg = (ts.scg_copies == 0)? 0 : (double)ts.scg_copies / (double)u;
+	return ABW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+"""Host-side drivers over the C ABI, mirroring the two reference programs' hot paths.
+
+`build_features`  ~ abawaca-build.cpp main(): FASTA -> windows -> k-mer signature + per-sample coverage rows
+`search`          ~ abawaca.cpp main(): recursive split search from the all-inclusive cluster
+
+Everything that computes goes through libabawaca_b200.so; numpy only carries buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class FeatureBuild:
+    """Device-resident result of the feature stage; `rows_host()` fetches the .lrn matrix."""
+
+    def __init__(self, ctx, seqset, segs, d_rows, nseg, ncols, nscaf, d_nbps):
+        self.ctx, self.seqset, self.segs, self.d_rows, self.nseg, self.ncols, self.nscaf, self.d_nbps = ctx, seqset, segs, d_rows, nseg, ncols, nscaf, d_nbps
+
+    def rows_host(self):
+        out = np.empty((self.nseg, self.ncols), dtype=np.float64)
+        if out.size:
+            self.ctx.to_host(out, self.d_rows)
+        return out
+
+    def segments_host(self):
+        seg_first = np.zeros(self.nscaf + 1, dtype=np.uint64)
+        seg_scaf = np.zeros(self.nseg, dtype=np.uint32)
+        seg_start = np.zeros(self.nseg, dtype=np.uint64)
+        seg_end = np.zeros(self.nseg, dtype=np.uint64)
+        seg_nonN = np.zeros(self.nseg, dtype=np.uint64)
+        L = self.ctx.lib
+        self.ctx.check(L.abw_segments_get(self.ctx.h, self.segs, capi._p(seg_first), capi._p(seg_scaf), capi._p(seg_start), capi._p(seg_end), capi._p(seg_nonN)))
+        return dict(seg_first=seg_first, seg_scaf=seg_scaf, seg_start=seg_start, seg_end=seg_end, seg_nonN=seg_nonN)
+
+    def scaffold_stats_host(self, lengths):
+        """(.info columns) length-normalised coverage of the -c sample, GC and N count -- abawaca-build.cpp:597"""
+        nN = np.zeros(self.nscaf, dtype=np.uint64)
+        nGC = np.zeros(self.nscaf, dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.abw_seqset_stats(self.ctx.h, self.seqset, capi._p(nN), capi._p(nGC)))
+        nbps = np.zeros(self.nscaf, dtype=np.uint64)
+        if self.nscaf:
+            self.ctx.to_host(nbps, self.d_nbps)
+        lengths = np.asarray(lengths, dtype=np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            cvg = nbps.astype(np.float64) / lengths                               # Scaf::cvg, abawaca-build.cpp:57
+            denom = lengths - nN.astype(np.float64)
+            gc = np.where(denom == 0, 0.0, nGC.astype(np.float64) / np.where(denom == 0, 1.0, denom))   # Bio::gc, String.cpp:114-131
+        trunc3 = lambda x: np.trunc(1000.0 * x) / 1000.0                         # noqa: E731  int(1000.0*x)/1000.0
+        return dict(cvg=trunc3(cvg), gc=trunc3(gc), Ns=nN)
+
+    def close(self):
+        L = self.ctx.lib
+        if self.d_rows:
+            self.ctx.free(self.d_rows)
+            self.d_rows = None
+        if self.d_nbps:
+            self.ctx.free(self.d_nbps)
+            self.d_nbps = None
+        if self.segs:
+            L.abw_segments_destroy(self.segs)
+            self.segs = None
+        if self.seqset:
+            L.abw_seqset_destroy(self.seqset)
+            self.seqset = None
+
+
+def build_features(ctx: capi.Context, seq, offsets, reads, this_sample=0, params=None, kind=capi.FEAT_TRUNC3, skip_A=True,
+                   seq_on_device=False, reads_on_device=False, nreads=None) -> FeatureBuild:
+    """seq: uint8 ASCII (numpy array, or a device pointer int when seq_on_device); offsets: uint64 [nscaf+1];
+    reads: one structured array (capi.READ_DTYPE) per sample (or device pointers + nreads)."""
+    L = ctx.lib
+    p = params or capi.default_params()
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    nscaf = offsets.size - 1
+    seqset = C.c_void_p()
+    if seq_on_device:
+        ctx.check(L.abw_pack_sequences(ctx.h, C.c_void_p(seq), 1, capi._p(offsets), nscaf, C.byref(seqset)))
+    else:
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        ctx.check(L.abw_pack_sequences(ctx.h, capi._p(seq), 0, capi._p(offsets), nscaf, C.byref(seqset)))
+    segs = C.c_void_p()
+    ctx.check(L.abw_segment(ctx.h, seqset, p.window_size, C.byref(segs)))
+    nseg = int(L.abw_segments_count(segs))
+    nk = capi.NKMER - (1 if skip_A else 0)
+    ncols = nk + len(reads)
+    d_rows = ctx.alloc(max(nseg * ncols, 1) * 8)
+    d_nbps = ctx.alloc(max(nscaf, 1) * 8)
+    ctx.memset(d_nbps, 0, max(nscaf, 1) * 8)
+    ctx.check(L.abw_kmer_features(ctx.h, seqset, segs, kind, 1 if skip_A else 0, C.c_void_p(d_rows), ncols, 0))
+    for j, r in enumerate(reads):
+        nb = C.c_void_p(d_nbps) if j == this_sample else None
+        if reads_on_device:
+            ctx.check(L.abw_coverage(ctx.h, segs, C.c_void_p(r), nreads[j], 1, p.max_snps, kind, C.c_void_p(d_rows), ncols, nk + j, nb))
+        else:
+            r = np.ascontiguousarray(r)
+            ctx.check(L.abw_coverage(ctx.h, segs, capi._p(r), r.size, 0, p.max_snps, kind, C.c_void_p(d_rows), ncols, nk + j, nb))
+    ctx.synchronize()
+    return FeatureBuild(ctx, seqset, segs, d_rows, nseg, ncols, nscaf, d_nbps)
+
+
+def search_problem_from_features(seg_scaf, nscaf):
+    """ScafDpData.cpp:91-99: drop scaffolds with exactly one datapoint (quirk Q1), renumber the rest in order.
+
+    Returns (keep_rows, dp2scaf, T, kept_scaffolds)."""
+    seg_scaf = np.asarray(seg_scaf)
+    counts = np.bincount(seg_scaf, minlength=nscaf)
+    keep_scaf = counts != 1
+    keep_scaf &= counts > 0
+    new_id = np.cumsum(keep_scaf) - 1
+    keep_rows = keep_scaf[seg_scaf]
+    dp2scaf = new_id[seg_scaf[keep_rows]].astype(np.uint32)
+    T = counts[keep_scaf].astype(np.uint32)
+    return keep_rows, dp2scaf, T, np.nonzero(keep_scaf)[0]
+
+
+class SearchResult:
+    def __init__(self, recs, dp2cluster, scaf2cluster, profile):
+        self.recs, self.dp2cluster, self.scaf2cluster, self.profile = recs, dp2cluster, scaf2cluster, profile
+
+
+def search(ctx: capi.Context, values, dp2scaf, T, length, scgmask, params=None, strategy=capi.SENS_SPEC, layout=capi.LAYOUT_COLMAJOR,
+           values_on_device=False, N=None, D=None, ld=None, want_bins=True) -> SearchResult:
+    """values: numpy [D][N] (column major) or [N][D] (row major), or a device pointer with N, D, ld given."""
+    L = ctx.lib
+    p = params or capi.default_params()
+    if not values_on_device:
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        if layout == capi.LAYOUT_COLMAJOR:
+            D, N = values.shape
+            ld = N
+        else:
+            N, D = values.shape
+            ld = D
+        vptr = capi._p(values)
+    else:
+        vptr = C.c_void_p(values)
+    dp2scaf = np.ascontiguousarray(dp2scaf, dtype=np.uint32)
+    T = np.ascontiguousarray(T, dtype=np.uint32)
+    length = np.ascontiguousarray(length, dtype=np.uint64)
+    scgmask = np.ascontiguousarray(scgmask, dtype=np.uint64)
+    if scgmask.ndim == 1:
+        scgmask = scgmask.reshape(-1, 1)
+    S, W = T.size, scgmask.shape[1]
+    h = C.c_void_p()
+    ctx.check(L.abw_search_create(ctx.h, vptr, 1 if values_on_device else 0, layout, ld, N, D, capi._p(dp2scaf), S, capi._p(T), capi._p(length),
+                                  capi._p(scgmask), W, C.byref(p), strategy, C.byref(h)))
+    try:
+        cap = int(max(64, 2 * (N // max(p.cluster_ndps_threshold, 1)) + 64))
+        recs = (capi.ClusterRec * cap)()
+        n = C.c_uint32()
+        dp2c = np.zeros(N, dtype=np.uint32) if want_bins else None
+        s2c = np.zeros(S, dtype=np.uint32) if want_bins else None
+        ctx.check(L.abw_search_run(ctx.h, h, recs, cap, C.byref(n), capi._p(dp2c), capi._p(s2c)))
+        prof = capi.SearchProfile()
+        L.abw_search_get_profile(h, C.byref(prof))
+        return SearchResult([recs[i] for i in range(min(n.value, cap))], dp2c, s2c, prof)
+    finally:
+        L.abw_search_destroy(h)

@@ -1,0 +1,183 @@
+/* abawaca_b200 -- C ABI of the B200-native abawaca hot path.
+ *
+ * The reference (CK7/abawaca) has no FFI layer; its seams are C++ constructors and virtuals
+ * (SURVEY.md section 8b).  This header is what a maintainer of the reference binds instead of
+ * those seams; INTEGRATION.md shows the C++ adapter for each.  Every entry point
+ *   - is extern "C", takes plain pointers and sizes, returns an int status (0 = ok),
+ *   - never throws and never takes ownership of caller memory,
+ *   - is callable from one host thread per context; abw_last_error(ctx) holds the text.
+ * Pointers named h_* are host memory, d_* device memory; plain names follow the `on_device` flag.
+ *
+ * Index conventions: scaffolds and datapoints (dps) are 0-based here (the reference's are 1-based,
+ * ScafDpData.cpp:90-101); scaffolds must be in byte-wise name order and dps grouped by scaffold in
+ * dp-name order, which is what abawaca-build writes and ScafDpData builds.  Dimension numbers in
+ * result records are 1-based like the reference's (ClusterData.cpp:187).
+ */
+#ifndef ABAWACA_B200_H
+#define ABAWACA_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABW_OK                 0
+#define ABW_ERR_CUDA           1
+#define ABW_ERR_ARG            2
+#define ABW_ERR_ILLEGAL_DNA    3   /* lower-case 'n': the reference throws Illegal_DNAString (String.cpp:47-49) */
+#define ABW_ERR_UNSUPPORTED    4
+#define ABW_ERR_NOMEM          5
+
+#define ABW_NKMER_DIMS 180         /* canonical 1..4-mers, abawaca-build.cpp:75-100 */
+
+typedef struct abw_ctx abw_ctx;
+typedef struct abw_seqset abw_seqset;     /* packed assembly on the device */
+typedef struct abw_segments abw_segments; /* the datapoints (windows) of an assembly */
+typedef struct abw_search abw_search;     /* one split-search problem resident on the device */
+
+/* Constants compiled into the reference's hot path, as a POD. */
+typedef struct {
+	uint32_t cluster_ndps_threshold;     /* 100     ClusterSeparator.h:72 */
+	double   sensitivity_threshold;      /* 0.8     ClusterSeparatorBySensitivitySpecificity.h:42 */
+	double   specificity_threshold;      /* 0.8     :43 */
+	double   product_threshold;          /* 0.8     :44 */
+	double   sum_threshold;              /* 1.6     :45 */
+	double   scg_overlap_threshold;      /* 0.2     ClusterQuality.cpp:130 */
+	uint64_t scg_min_size;               /* 500000  ClusterQuality.cpp:119 */
+	double   fraction_dps_in;            /* 0.8     ClusterSeparatorSplitScafs.h:59 */
+	double   split_scaf_ratio_threshold; /* 0.1     ClusterSeparatorSplitScafs.h:44 */
+	uint32_t max_snps;                   /* 15      abawaca-build.cpp:437 */
+	uint32_t window_size;                /* 2000    abawaca-build.cpp:436 */
+	/* Not in the reference: candidates scoring below this are not examined.  The default, equal to
+	 * product_threshold, cannot change any split (a best separation below it fails is_legal), but the
+	 * best separation reported for a TERMINAL cluster is then only found if it is legal.  Set to 0 to
+	 * also reproduce the reference's log line for terminal clusters. */
+	double   min_reported_score;
+} abw_params;
+
+typedef struct {
+	uint32_t scaf;        /* 0-based scaffold index; >= nscaf: reference name not in the assembly (skipped, abawaca-build.cpp:549-550) */
+	uint32_t pos0;        /* 0-based leftmost reference position = SAM POS - 1 (ReadMapping.cpp:41) */
+	uint32_t len;         /* read length = SEQ.size() (ReadMapping.h:44) */
+	uint32_t flag_nsnps;  /* low 16 bits: SAM FLAG; high 16 bits: num_snps() from MD:Z/CIGAR (ReadMapping.cpp:78-185) */
+} abw_read;
+
+/* ---- context -------------------------------------------------------------------------------- */
+int         abw_ctx_create(int device, abw_ctx** out);
+void        abw_ctx_destroy(abw_ctx* ctx);
+const char* abw_last_error(const abw_ctx* ctx);
+const char* abw_version(void);
+void        abw_default_params(abw_params* p);
+/* number of kernel launches issued through this context so far (bench.py reports it) */
+uint64_t    abw_kernel_launches(const abw_ctx* ctx);
+/* the stream every kernel of this context is launched on (a cudaStream_t), for event timing */
+void*       abw_ctx_stream(const abw_ctx* ctx);
+int         abw_ctx_synchronize(abw_ctx* ctx);
+
+/* ---- feature stage (abawaca-build) ------------------------------------------------------------ */
+
+/* Replaces Bio::DNAString construction for every scaffold read by SeqIORead_fasta<DNASequence>::next_seq
+ * (SeqIORead_fasta.h:51-103, String.cpp:37-51): upper-cases, keeps A/C/G/T as 2-bit codes, marks every
+ * other character in a validity mask and the literal 'N' in a second mask (quirk Q2).
+ * ascii: concatenated scaffold sequences; offsets[nscaf+1] (host) delimit them. */
+int abw_pack_sequences(abw_ctx* ctx, const char* ascii, int ascii_on_device, const uint64_t* h_offsets, uint32_t nscaf, abw_seqset** out);
+void abw_seqset_destroy(abw_seqset* s);
+/* Bio::Ns and the C+G count behind Bio::gc, per scaffold (String.cpp:114-146); host arrays [nscaf] */
+int abw_seqset_stats(abw_ctx* ctx, const abw_seqset* s, uint64_t* h_count_N, uint64_t* h_count_GC);
+
+/* Replaces Scaf::Scaf (abawaca-build.cpp:198-228): cuts every scaffold into windows of equal non-N length. */
+int abw_segment(abw_ctx* ctx, const abw_seqset* s, uint32_t window_size, abw_segments** out);
+void abw_segments_destroy(abw_segments* g);
+uint64_t abw_segments_count(const abw_segments* g);
+/* host copies (any pointer may be NULL): seg_first[nscaf+1], and per segment scaffold, 1-based inclusive start/end, non-N bases */
+int abw_segments_get(abw_ctx* ctx, const abw_segments* g, uint64_t* h_seg_first, uint32_t* h_seg_scaf, uint64_t* h_seg_start, uint64_t* h_seg_end, uint64_t* h_seg_nonN);
+
+#define ABW_FEAT_TRUNC3 0   /* int(1000*x)/1000.0, the value abawaca-build prints with %.3lf (abawaca-build.cpp:603) */
+#define ABW_FEAT_RAW    1   /* the un-truncated double */
+/* Replaces Scaf_segment::Scaf_segment (abawaca-build.cpp:103-174).  Writes, for every segment, the 180 canonical
+ * k-mer frequencies into columns [col0, col0+180) of the row-major matrix `rows` (row stride ld doubles).
+ * With skip_A != 0 the first dimension ("A", which abawaca-build does not write, :585-602) is dropped and 179 columns are written. */
+int abw_kmer_features(abw_ctx* ctx, const abw_seqset* s, const abw_segments* g, int kind, int skip_A, double* d_rows, uint64_t ld, uint32_t col0);
+
+/* Replaces the SAM loop body abawaca-build.cpp:546-551 with Scaf::add_mapped_read (:231-244) and
+ * Scaf_segment::add_mapped_read (:177-185) for ONE sample: reads in SAM order.  Writes column `col` of `rows`.
+ * d_scaf_nbps (may be NULL): per scaffold sum of accepted read lengths (the -c sample, :242-243), uint64 [nscaf]. */
+int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uint64_t nreads, int reads_on_device, uint32_t max_snps,
+                 int kind, double* d_rows, uint64_t ld, uint32_t col, uint64_t* d_scaf_nbps);
+
+/* device memory helpers so that hosts without a CUDA runtime binding can drive the ABI */
+int abw_device_alloc(abw_ctx* ctx, size_t bytes, void** d_out);
+int abw_device_free(abw_ctx* ctx, void* d_ptr);
+int abw_copy_to_device(abw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int abw_copy_to_host(abw_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+int abw_memset_device(abw_ctx* ctx, void* d_ptr, int byte, size_t bytes);
+
+/* ---- split search (abawaca) ----------------------------------------------------------------- */
+
+#define ABW_SENS_SPEC   0   /* ClusterSeparatorBySensitivitySpecificity (live, abawaca.cpp:109) */
+#define ABW_SPLIT_SCAFS 1   /* ClusterSeparatorSplitScafs (compiled, not instantiated, abawaca.cpp:110) */
+
+#define ABW_LAYOUT_COLMAJOR 0  /* values[d * ld + dp] */
+#define ABW_LAYOUT_ROWMAJOR 1  /* values[dp * ld + d] (the .lrn layout written by abw_kmer_features/abw_coverage) */
+
+/* Replaces ClusterData(lrn, scaf_db) + ScafDpData + SCGdb as the split search sees them (ClusterData.cpp:27,
+ * ScafDpData.cpp:91-99, SCGdb.cpp:86-117): N datapoints x D dimensions, dp2scaf[N] (non-decreasing),
+ * T[S] = scaf_db.ndps(scaf) (must be >= 2: ScafDpData drops scaffolds with one dp, quirk Q1),
+ * len[S] = sequence length, scgmask[S][W] = bit set of SCG names per scaffold.
+ * The all-inclusive cluster 1 (init_cluster, abawaca.cpp:242-251) is the root. */
+int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, int layout, uint64_t ld, uint64_t N, uint32_t D,
+                      const uint32_t* h_dp2scaf, uint32_t S, const uint32_t* h_T, const uint64_t* h_len, const uint64_t* h_scgmask, uint32_t W,
+                      const abw_params* params, int strategy, abw_search** out);
+void abw_search_destroy(abw_search* s);
+
+typedef struct {
+	int32_t  found;     /* 0: best_separation untouched (dimension -1, ClusterSeparator.h:21) */
+	uint32_t dim;       /* 1-based */
+	double   value;
+	double   a;         /* sensitivity            | split_scaf_ratio   */
+	double   b;         /* specificity            | cluster_size_ratio */
+	int32_t  legal;     /* ClusteringResult::is_legal */
+} abw_best;
+
+typedef struct {
+	uint32_t id, parent;
+	uint64_t ndps;
+	uint32_t nscafs;            /* assigned scaffolds */
+	int32_t  split;             /* ClusterSeparator::separate() returned true */
+	abw_best best;              /* best_separation after separate() (reset when the children were too small, ClusterSeparator.cpp:125-132) */
+	uint32_t child1, child2;    /* ids handed out at split time, cluster1 first (abawaca.cpp:164-193) */
+	uint64_t child1_ndps, child2_ndps;
+	uint32_t child1_nscafs, child2_nscafs;
+	uint64_t child1_raw, child2_raw;   /* |raw_dps_cluster1/2| before scaffold re-homing */
+	uint64_t total_size;        /* terminal clusters: ClusterQuality::total_size */
+	uint32_t scg_unique;        /* terminal clusters: SCGdb::num_unique_scgs */
+	double   scg_avg;           /* terminal clusters: SCGdb::average_num_copies_for_unique_scgs */
+} abw_cluster_rec;
+
+/* Replaces the work-list loop abawaca.cpp:98-197 with ClusterSeparator::separate() (ClusterSeparator.cpp:57-135) inside:
+ * evaluates clusters breadth first (= ascending id), level by level, until every cluster is terminal.
+ * h_recs[cap] receives one record per evaluated cluster in id order; *nrecs the number evaluated.
+ * h_dp2cluster[N] / h_scaf2cluster[S] (may be NULL): terminal cluster id, 0 if none (abawaca.cpp:199-210). */
+int abw_search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t cap, uint32_t* nrecs, uint32_t* h_dp2cluster, uint32_t* h_scaf2cluster);
+
+/* Timing of the last abw_search_run, in milliseconds of device time per kernel family (CUDA events on the context stream) */
+typedef struct {
+	float build_ms;       /* abw_search_create: key transform, sort, element packing */
+	float sweep_ms;       /* threshold-sweep kernels, all levels */
+	float partition_ms;   /* stable partition kernels, all levels */
+	float other_ms;       /* reductions, children, SCG tables */
+	uint64_t sweep_elements;     /* sum over levels of (dps x dimensions) swept */
+	uint64_t partition_elements;
+	uint32_t levels;
+	uint32_t sweep_launches;
+} abw_search_profile;
+int abw_search_get_profile(const abw_search* s, abw_search_profile* out);
+
+/* ClusterQuality::scg (ClusterQuality.cpp:44-48) for an arbitrary scaffold list */
+int abw_cluster_scg(abw_ctx* ctx, const abw_search* s, const uint32_t* h_scafs, uint32_t nscafs, uint32_t* nunique, double* avg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

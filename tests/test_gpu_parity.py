@@ -1,0 +1,197 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against
+ (a) the committed golden vectors produced by the unmodified reference, and
+ (b) the flat-array oracle on seeded random inputs (edge cases: heavy ties, partial scaffolds, SCG filters)."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import GOLDEN, load_set, parse_lrn_text, parse_ref_search, search_problem, compare_cluster_records
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from abawaca_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _kat_arrays():
+    kat = json.loads(gzip.open(os.path.join(GOLDEN, "kat_features.json.gz"), "rb").read())
+    from abawaca_b200 import capi
+    seqs = sorted(kat["seqs"], key=lambda x: x[0].encode())
+    names = [n for n, _ in seqs]
+    idx = {n: i for i, n in enumerate(names)}
+    offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(s) for _, s in seqs])
+    seq = np.frombuffer("".join(s for _, s in seqs).encode(), dtype=np.uint8)
+    reads = []
+    for rr in kat["reads"]:
+        rec = np.zeros(len(rr), dtype=capi.READ_DTYPE)
+        for i, (rname, pos1, ln, flag, nsnps) in enumerate(rr):
+            rec[i] = (idx.get(rname, 0xFFFFFFFF), (pos1 - 1) & 0xFFFFFFFF, ln, (flag & 0xFFFF) | (nsnps << 16))
+        reads.append(rec)
+    return kat, names, seq, offsets, reads
+
+
+def test_kat_features_bit_exact(ctx):
+    from abawaca_b200 import capi, pipeline
+    kat, names, seq, offsets, reads = _kat_arrays()
+    fb = pipeline.build_features(ctx, seq, offsets, reads, this_sample=0)
+    heads, vals = parse_lrn_text(kat["lrn"])
+    rows = fb.rows_host()
+    assert rows.shape == vals.shape
+    assert np.array_equal(rows, vals)
+    sg = fb.segments_host()
+    recs = [l.split("\t") for l in kat["names"].splitlines()[1:]]
+    per = {}
+    for i, r in enumerate(recs):
+        s = int(sg["seg_scaf"][i]); per[s] = per.get(s, 0) + 1
+        ln = int(sg["seg_end"][i] - sg["seg_start"][i] + 1)
+        assert r[2] == f"{names[s]}:({int(sg['seg_start'][i])}, {int(sg['seg_end'][i])}), {int(sg['seg_nonN'][i])}/{ln} non-Ns bps"
+    st = fb.scaffold_stats_host(np.diff(offsets.astype(np.int64)))
+    for i, l in enumerate(kat["info"].splitlines()):
+        nm, ln, cvg, gc, Ns = l.split("\t")
+        assert ("%.3f" % st["cvg"][i], "%.3f" % st["gc"][i], int(st["Ns"][i])) == (cvg, gc, int(Ns))
+    fb.close()
+    # un-truncated doubles
+    fb = pipeline.build_features(ctx, seq, offsets, reads, this_sample=0, kind=capi.FEAT_RAW, skip_A=False)
+    raw = np.array([[float(x) for x in l.split("\t")[3:]] for l in kat["raw"].splitlines() if l.startswith("SEG")])
+    assert np.array_equal(fb.rows_host(), raw)
+    fb.close()
+
+
+def test_lowercase_n_is_rejected_like_the_reference(ctx):
+    from abawaca_b200 import capi, pipeline
+    seq = np.frombuffer(b"ACGT" * 600 + b"n" + b"ACGT" * 10, dtype=np.uint8)
+    with pytest.raises(capi.AbwError, match="Illegal_DNAString"):
+        pipeline.build_features(ctx, seq, np.array([0, seq.size], dtype=np.uint64), [])
+
+
+@pytest.mark.parametrize("name", ["tiny_clean", "tiny_noisy"])
+def test_features_match_reference_files(ctx, name):
+    from abawaca_b200 import capi, pipeline
+    g = load_set(name)
+    mg = g["mg"]
+    fb = pipeline.build_features(ctx, mg.seq, mg.offsets, mg.reads, this_sample=0)
+    heads, vals = parse_lrn_text(g["lrn_text"])
+    assert np.array_equal(fb.rows_host(), vals)
+    st = fb.scaffold_stats_host(np.diff(mg.offsets.astype(np.int64)))
+    info = [l.split("\t") for l in g["info_text"].splitlines()]
+    assert ["%.3f" % v for v in st["cvg"]] == [x[2] for x in info]
+    assert ["%.3f" % v for v in st["gc"]] == [x[3] for x in info]
+    assert [int(x[4]) for x in info] == st["Ns"].tolist()
+    fb.close()
+    fb = pipeline.build_features(ctx, mg.seq, mg.offsets, mg.reads, this_sample=0, kind=capi.FEAT_RAW, skip_A=False)
+    assert np.array_equal(fb.rows_host()[:, 180:], g["rawcov"])
+    fb.close()
+
+
+@pytest.mark.parametrize("name", ["tiny_clean", "tiny_noisy"])
+@pytest.mark.parametrize("strategy", [0, 1])
+def test_search_matches_reference(ctx, name, strategy):
+    from abawaca_b200 import capi, pipeline
+    g = load_set(name)
+    prob = search_problem(name)
+    ref_clusters, ref_bins = parse_ref_search(g["meta"]["ref_search"]["sensspec" if strategy == 0 else "splitscafs"])
+    # full fidelity: also the best separation the reference logs for terminal clusters
+    p = capi.default_params()
+    p.min_reported_score = 0.0
+    res = pipeline.search(ctx, prob["values"], prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"], params=p, strategy=strategy)
+    assert compare_cluster_records(ref_clusters, res.recs, strategy) == []
+    assert [b for _, b in ref_bins] == res.scaf2cluster.tolist()
+    # default parameters: identical splits and bins
+    res = pipeline.search(ctx, prob["values"], prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"], strategy=strategy)
+    assert compare_cluster_records(ref_clusters, res.recs, strategy, check_illegal_best=(strategy == 1)) == []
+    assert [b for _, b in ref_bins] == res.scaf2cluster.tolist()
+    # row-major input (the .lrn layout) gives the same answer
+    res2 = pipeline.search(ctx, np.ascontiguousarray(prob["values"].T), prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"], strategy=strategy,
+                           layout=capi.LAYOUT_ROWMAJOR)
+    assert res2.scaf2cluster.tolist() == res.scaf2cluster.tolist() and res2.dp2cluster.tolist() == res.dp2cluster.tolist()
+
+
+def _random_problem(rng, S, D, partial=False, ties=True, scg=True, nclus=3):
+    T = rng.integers(2, 9, S).astype(np.uint32)
+    n = T.copy()
+    if partial:
+        drop = rng.random(S) < 0.3
+        n = np.where(drop, np.maximum(1, T - rng.integers(1, 4, S)), T).astype(np.uint32)
+    dp2scaf = np.repeat(np.arange(S, dtype=np.uint32), n)
+    N = dp2scaf.size
+    grp = rng.integers(0, nclus, S)
+    centers = rng.normal(0, 1.0, (nclus, D))
+    vals = centers[grp[dp2scaf]].T + rng.normal(0, 0.35, (D, N))
+    if ties:
+        vals = np.round(vals, 1)             # heavy ties, negative values and +-0.0
+        vals[vals == 0] = np.where(rng.random((vals == 0).sum()) < 0.5, 0.0, -0.0)
+    length = rng.integers(2000, 400000, S).astype(np.uint64)
+    W = 2
+    mask = np.zeros((S, W), dtype=np.uint64)
+    if scg:
+        for g in range(70):
+            for c in range(nclus):
+                if rng.random() < 0.8:
+                    cand = np.nonzero(grp == c)[0]
+                    if cand.size:
+                        s = cand[rng.integers(0, cand.size)]
+                        mask[s, g // 64] |= np.uint64(1) << np.uint64(g % 64)
+    return np.ascontiguousarray(vals), dp2scaf, T, length, mask
+
+
+@pytest.mark.parametrize("seed,partial,scg,strategy", [(1, False, True, 0), (2, True, True, 0), (3, False, False, 0), (4, True, True, 1), (5, False, True, 1),
+                                                     (6, False, True, 0), (7, True, False, 0)])
+def test_search_matches_oracle_on_random_problems(ctx, oracle, seed, partial, scg, strategy):
+    from abawaca_b200 import capi, pipeline
+    rng = np.random.default_rng(seed)
+    S = int(rng.integers(150, 500))
+    D = int(rng.integers(3, 12))
+    vals, dp2scaf, T, length, mask = _random_problem(rng, S, D, partial=partial, scg=scg, nclus=int(rng.integers(2, 5)))
+    O = oracle.Search(vals, dp2scaf, T, length, mask)
+    orecs, odp, osc = O.run(strategy=strategy)
+    p = capi.default_params()
+    p.min_reported_score = 0.0
+    res = pipeline.search(ctx, vals, dp2scaf, T, length, mask, params=p, strategy=strategy)
+    assert len(orecs) == len(res.recs)
+    for o, r in zip(orecs, res.recs):
+        assert (o.id, o.parent, o.ndps, o.nscafs, o.split) == (r.id, r.parent, r.ndps, r.nscafs, r.split)
+        assert (o.best.found, o.best.dim, o.best.value, o.best.a, o.best.legal) == (r.best.found, r.best.dim, r.best.value, r.best.a, r.best.legal), (o.id, o.best.b, r.best.b)
+        assert o.best.b == r.best.b
+        assert (o.child1, o.child2, o.child1_ndps, o.child2_ndps, o.child1_nscafs, o.child2_nscafs, o.child1_raw, o.child2_raw) == \
+               (r.child1, r.child2, r.child1_ndps, r.child2_ndps, r.child1_nscafs, r.child2_nscafs, r.child1_raw, r.child2_raw)
+        assert (o.total_size, o.scg_unique, o.scg_avg) == (r.total_size, r.scg_unique, r.scg_avg)
+    assert odp.tolist() == res.dp2cluster.tolist()
+    assert osc.tolist() == res.scaf2cluster.tolist()
+
+
+def test_small_and_degenerate_searches(ctx, oracle):
+    from abawaca_b200 import pipeline
+    rng = np.random.default_rng(11)
+    # fewer than 2 x 100 datapoints: never splits; constant columns: no boundary at all
+    for S, D, const in ((20, 2, False), (300, 3, True)):
+        vals, dp2scaf, T, length, mask = _random_problem(rng, S, D)
+        if const:
+            vals[:] = 0.25
+        O = oracle.Search(vals, dp2scaf, T, length, mask)
+        orecs, odp, osc = O.run()
+        res = pipeline.search(ctx, vals, dp2scaf, T, length, mask)
+        assert len(res.recs) == len(orecs) == 1 and res.recs[0].split == 0
+        assert res.scaf2cluster.tolist() == osc.tolist() and res.dp2cluster.tolist() == odp.tolist()
+
+
+def test_features_match_oracle_on_a_larger_random_assembly(ctx, oracle):
+    """size-independent check at a size the oracle still finishes quickly: 3000 scaffolds, shuffled reads"""
+    from abawaca_b200 import pipeline, synth
+    mg = synth.make_metagenome(3000, 2, 6, 991, shuffle_reads=True, n_run_frac=0.05)
+    f = oracle.build_features(mg.seq, mg.offsets, mg.reads, this_sample=1)
+    fb = pipeline.build_features(ctx, mg.seq, mg.offsets, mg.reads, this_sample=1)
+    assert np.array_equal(fb.rows_host(), f["rows"])
+    sg = fb.segments_host()
+    assert np.array_equal(sg["seg_start"], f["seg_start"]) and np.array_equal(sg["seg_end"], f["seg_end"]) and np.array_equal(sg["seg_scaf"], f["seg_scaf"])
+    st = fb.scaffold_stats_host(np.diff(mg.offsets.astype(np.int64)))
+    assert np.array_equal(st["cvg"], f["info_cvg"]) and np.array_equal(st["gc"], f["info_gc"]) and np.array_equal(st["Ns"], f["info_Ns"])
+    fb.close()

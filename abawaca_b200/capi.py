@@ -51,7 +51,7 @@ class SearchProfile(C.Structure):
 
 EXPORTS = [
     "abw_ctx_create", "abw_ctx_destroy", "abw_last_error", "abw_version", "abw_default_params", "abw_kernel_launches", "abw_ctx_stream",
-    "abw_ctx_synchronize", "abw_pack_sequences", "abw_seqset_destroy", "abw_seqset_stats", "abw_segment", "abw_segments_destroy",
+    "abw_ctx_synchronize", "abw_profile_enable", "abw_profile_report", "abw_pack_sequences", "abw_seqset_destroy", "abw_seqset_stats", "abw_segment", "abw_segments_destroy",
     "abw_segments_count", "abw_segments_get", "abw_kmer_features", "abw_coverage", "abw_device_alloc", "abw_device_free",
     "abw_copy_to_device", "abw_copy_to_host", "abw_memset_device", "abw_search_create", "abw_search_destroy", "abw_search_run",
     "abw_search_get_profile", "abw_cluster_scg",
@@ -80,6 +80,9 @@ def load():
     L.abw_kernel_launches.argtypes = [C.c_void_p]
     L.abw_ctx_stream.argtypes = [C.c_void_p]
     L.abw_ctx_synchronize.argtypes = [C.c_void_p]
+    L.abw_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.abw_profile_report.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    L.abw_profile_report.restype = C.c_size_t
     L.abw_pack_sequences.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
     L.abw_seqset_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.abw_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
@@ -91,7 +94,7 @@ def load():
     L.abw_copy_to_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.abw_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.abw_memset_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]
-    L.abw_search_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+    L.abw_search_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     L.abw_search_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p]
     L.abw_search_get_profile.argtypes = [C.c_void_p, C.c_void_p]
@@ -143,6 +146,20 @@ class Context:
 
     def synchronize(self):
         self.check(self.lib.abw_ctx_synchronize(self.h))
+
+    def profile(self, on=True):
+        self.check(self.lib.abw_profile_enable(self.h, 1 if on else 0))
+
+    def profile_report(self):
+        """{kernel: (launches, total_ms)} accumulated since profile(True)"""
+        n = self.lib.abw_profile_report(self.h, None, 0)
+        buf = C.create_string_buffer(int(n) + 16)
+        self.lib.abw_profile_report(self.h, buf, len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            k, c, ms = line.split("\t")
+            out[k] = (int(c), float(ms))
+        return out
 
     # raw device memory
     def alloc(self, nbytes):

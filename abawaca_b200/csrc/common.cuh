@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <string>
 #include <vector>
+#include <map>
 #include <cstdio>
 #include "../../include/abawaca_b200.h"
 
@@ -13,6 +14,10 @@ struct abw_ctx {
 	int          sm_count = 148;
 	uint64_t     launches = 0;
 	std::string  err;
+	// optional per-kernel timing (abw_profile_enable): every launch is bracketed by events and waited for
+	bool         profiling = false;
+	cudaEvent_t  ev_a = nullptr, ev_b = nullptr;
+	std::map<std::string, std::pair<uint64_t, double>> prof;   // kernel -> (launches, total ms)
 };
 
 inline int abw_fail(abw_ctx* ctx, int code, const std::string& msg)
@@ -42,15 +47,38 @@ inline int abw_fail(abw_ctx* ctx, int code, const std::string& msg)
 // every launch goes through this so that abw_kernel_launches() is an honest count
 #define ABW_LAUNCH(ctx, kernel, grid, block, smem, ...)                                                              \
 	do {                                                                                                             \
+		if((ctx)->profiling)                                                                                         \
+			cudaEventRecord((ctx)->ev_a, (ctx)->stream);                                                             \
 		kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                                             \
 		(ctx)->launches++;                                                                                           \
 		ABW_CUDA((ctx), cudaGetLastError());                                                                         \
+		if((ctx)->profiling) {                                                                                       \
+			float ms__ = 0;                                                                                          \
+			cudaEventRecord((ctx)->ev_b, (ctx)->stream);                                                             \
+			ABW_CUDA((ctx), cudaEventSynchronize((ctx)->ev_b));                                                      \
+			cudaEventElapsedTime(&ms__, (ctx)->ev_a, (ctx)->ev_b);                                                   \
+			auto& e__ = (ctx)->prof[#kernel];                                                                        \
+			e__.first++;                                                                                             \
+			e__.second += ms__;                                                                                      \
+		}                                                                                                            \
+	} while(0)
+
+// Stream of the context whose entry point is executing on this host thread (set by ABW_ENTER).  Device buffers are
+// allocated and freed in stream order from the device's memory pool (cudaMallocAsync), so that after the first call of
+// a given size no entry point pays for cudaMalloc/cudaFree or for the device-wide synchronisation cudaFree implies.
+extern thread_local cudaStream_t abw_tls_stream;
+
+#define ABW_ENTER(ctx)                                                                                               \
+	do {                                                                                                             \
+		ABW_CUDA((ctx), cudaSetDevice((ctx)->device));                                                               \
+		abw_tls_stream = (ctx)->stream;                                                                              \
 	} while(0)
 
 template <typename T>
 struct DevBuf {
-	T*     p = nullptr;
-	size_t n = 0;
+	T*           p = nullptr;
+	size_t       n = 0;
+	cudaStream_t st = nullptr;
 	DevBuf() {}
 	DevBuf(const DevBuf&) = delete;
 	DevBuf& operator=(const DevBuf&) = delete;
@@ -58,7 +86,7 @@ struct DevBuf {
 	void release()
 	{
 		if(p)
-			cudaFree(p);
+			cudaFreeAsync(p, st);
 		p = nullptr;
 		n = 0;
 	}
@@ -66,7 +94,8 @@ struct DevBuf {
 	{
 		release();
 		n = count;
-		return cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+		st = abw_tls_stream;
+		return cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), st);
 	}
 };
 

@@ -1,5 +1,9 @@
 // Context, error text and raw device-memory helpers of the C ABI.
 #include "common.cuh"
+#include <algorithm>
+#include <cstring>
+
+thread_local cudaStream_t abw_tls_stream = nullptr;
 
 extern "C" {
 
@@ -44,6 +48,12 @@ int abw_ctx_create(int device, abw_ctx** out)
 	cudaDeviceProp prop;
 	if(cudaGetDeviceProperties(&prop, device) == cudaSuccess)
 		c->sm_count = prop.multiProcessorCount;
+	// keep freed blocks in the pool instead of returning them to the driver at every synchronisation
+	cudaMemPool_t pool;
+	if(cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+		uint64_t keep = UINT64_MAX;
+		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+	}
 	*out = c;
 	return ABW_OK;
 }
@@ -55,6 +65,10 @@ void abw_ctx_destroy(abw_ctx* ctx)
 	cudaSetDevice(ctx->device);
 	if(ctx->stream)
 		cudaStreamDestroy(ctx->stream);
+	if(ctx->ev_a) {
+		cudaEventDestroy(ctx->ev_a);
+		cudaEventDestroy(ctx->ev_b);
+	}
 	delete ctx;
 }
 
@@ -72,12 +86,45 @@ int abw_ctx_synchronize(abw_ctx* ctx)
 	return ABW_OK;
 }
 
+int abw_profile_enable(abw_ctx* ctx, int on)
+{
+	if(!ctx)
+		return ABW_ERR_ARG;
+	if(on && !ctx->ev_a) {
+		ABW_CUDA(ctx, cudaEventCreate(&ctx->ev_a));
+		ABW_CUDA(ctx, cudaEventCreate(&ctx->ev_b));
+	}
+	ctx->profiling = on != 0;
+	if(on)
+		ctx->prof.clear();
+	return ABW_OK;
+}
+
+size_t abw_profile_report(abw_ctx* ctx, char* buf, size_t cap)
+{
+	if(!ctx)
+		return 0;
+	std::string out;
+	char line[256];
+	for(auto& kv : ctx->prof) {
+		snprintf(line, sizeof(line), "%s\t%llu\t%.6f\n", kv.first.c_str(), (unsigned long long)kv.second.first, kv.second.second);
+		out += line;
+	}
+	if(buf && cap) {
+		size_t n = std::min(out.size(), cap - 1);
+		memcpy(buf, out.data(), n);
+		buf[n] = 0;
+	}
+	return out.size() + 1;
+}
+
 int abw_device_alloc(abw_ctx* ctx, size_t bytes, void** d_out)
 {
 	if(!ctx || !d_out)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_device_alloc: null argument");
-	ABW_CUDA(ctx, cudaSetDevice(ctx->device));
-	ABW_CUDA(ctx, cudaMalloc(d_out, bytes? bytes : 1));
+	ABW_ENTER(ctx);
+	ABW_CUDA(ctx, cudaMallocAsync(d_out, bytes? bytes : 1, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return ABW_OK;
 }
 
@@ -85,7 +132,7 @@ int abw_device_free(abw_ctx* ctx, void* d_ptr)
 {
 	if(!ctx)
 		return ABW_ERR_ARG;
-	ABW_CUDA(ctx, cudaFree(d_ptr));
+	ABW_CUDA(ctx, cudaFreeAsync(d_ptr, ctx->stream));
 	return ABW_OK;
 }
 

@@ -551,21 +551,15 @@ int upload_tables(abw_ctx* ctx)
 // ===================================================================================================
 extern "C" {
 
-int abw_pack_sequences(abw_ctx* ctx, const char* ascii, int ascii_on_device, const uint64_t* h_offsets, uint32_t nscaf, abw_seqset** out)
+static int pack_impl(abw_ctx* ctx, abw_seqset* s, const char* ascii, int ascii_on_device, const uint64_t* h_offsets, uint32_t nscaf)
 {
-	if(!ctx || !out || !h_offsets || (!ascii && nscaf && h_offsets[nscaf] > 0))
-		return abw_fail(ctx, ABW_ERR_ARG, "abw_pack_sequences: null argument");
-	ABW_CUDA(ctx, cudaSetDevice(ctx->device));
-	abw_seqset* s = new abw_seqset();
 	s->nscaf = nscaf;
 	s->h_len.resize(nscaf);
 	s->h_base.resize((size_t)nscaf + 1);
 	uint64_t b = 0;
 	for(uint32_t i = 0; i < nscaf; i++) {
-		if(h_offsets[i + 1] < h_offsets[i]) {
-			delete s;
+		if(h_offsets[i + 1] < h_offsets[i])
 			return abw_fail(ctx, ABW_ERR_ARG, "abw_pack_sequences: offsets must be non-decreasing");
-		}
 		s->h_len[i] = h_offsets[i + 1] - h_offsets[i];
 		s->h_base[i] = b;
 		b += (s->h_len[i] + 127) & ~127ull;
@@ -577,45 +571,52 @@ int abw_pack_sequences(abw_ctx* ctx, const char* ascii, int ascii_on_device, con
 	DevBuf<uint64_t> d_off;
 	DevBuf<int> d_err;
 	const unsigned char* src = (const unsigned char*)ascii;
-	auto fail = [&](int code) { delete s; return code; };
-#define PK(call) do { cudaError_t e__ = (call); if(e__ != cudaSuccess) { abw_fail(ctx, ABW_ERR_CUDA, std::string("abw_pack_sequences: ") + cudaGetErrorString(e__)); return fail(ABW_ERR_CUDA); } } while(0)
 	uint64_t readable = bytes;
 	if(!ascii_on_device) {
-		PK(d_ascii.alloc(bytes + 64));
-		PK(cudaMemcpyAsync(d_ascii.p, ascii, bytes, cudaMemcpyHostToDevice, ctx->stream));
+		ABW_CUDA(ctx, d_ascii.alloc(bytes + 64));
+		ABW_CUDA(ctx, cudaMemcpyAsync(d_ascii.p, ascii, bytes, cudaMemcpyHostToDevice, ctx->stream));
 		src = d_ascii.p;
 		readable = bytes + 64;
 	}
-	PK(d_off.alloc((size_t)nscaf + 1));
-	PK(cudaMemcpyAsync(d_off.p, h_offsets, sizeof(uint64_t) * ((size_t)nscaf + 1), cudaMemcpyHostToDevice, ctx->stream));
-	PK(s->len.alloc(nscaf));
-	PK(s->base.alloc((size_t)nscaf + 1));
-	PK(cudaMemcpyAsync(s->len.p, s->h_len.data(), sizeof(uint64_t) * nscaf, cudaMemcpyHostToDevice, ctx->stream));
-	PK(cudaMemcpyAsync(s->base.p, s->h_base.data(), sizeof(uint64_t) * ((size_t)nscaf + 1), cudaMemcpyHostToDevice, ctx->stream));
+	ABW_CUDA(ctx, d_off.alloc((size_t)nscaf + 1));
+	ABW_CUDA(ctx, cudaMemcpyAsync(d_off.p, h_offsets, sizeof(uint64_t) * ((size_t)nscaf + 1), cudaMemcpyHostToDevice, ctx->stream));
+	ABW_CUDA(ctx, s->len.alloc(nscaf));
+	ABW_CUDA(ctx, s->base.alloc((size_t)nscaf + 1));
+	ABW_CUDA(ctx, cudaMemcpyAsync(s->len.p, s->h_len.data(), sizeof(uint64_t) * nscaf, cudaMemcpyHostToDevice, ctx->stream));
+	ABW_CUDA(ctx, cudaMemcpyAsync(s->base.p, s->h_base.data(), sizeof(uint64_t) * ((size_t)nscaf + 1), cudaMemcpyHostToDevice, ctx->stream));
 	// + slack so that the k-mer kernel may read one word past a segment
-	PK(s->packed.alloc(b / 16 + 16));
-	PK(s->valid.alloc(b / 32 + 16));
-	PK(s->nmask.alloc(b / 32 + 16));
-	PK(cudaMemsetAsync(s->packed.p + b / 16, 0, 16 * sizeof(uint32_t), ctx->stream));
-	PK(cudaMemsetAsync(s->valid.p + b / 32, 0, 16 * sizeof(uint32_t), ctx->stream));
-	PK(cudaMemsetAsync(s->nmask.p + b / 32, 0, 16 * sizeof(uint32_t), ctx->stream));
-	PK(s->countN.alloc(nscaf));
-	PK(s->countGC.alloc(nscaf));
-	PK(d_err.alloc(1));
-	PK(cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
+	ABW_CUDA(ctx, s->packed.alloc(b / 16 + 16));
+	ABW_CUDA(ctx, s->valid.alloc(b / 32 + 16));
+	ABW_CUDA(ctx, s->nmask.alloc(b / 32 + 16));
+	ABW_CUDA(ctx, cudaMemsetAsync(s->packed.p + b / 16, 0, 16 * sizeof(uint32_t), ctx->stream));
+	ABW_CUDA(ctx, cudaMemsetAsync(s->valid.p + b / 32, 0, 16 * sizeof(uint32_t), ctx->stream));
+	ABW_CUDA(ctx, cudaMemsetAsync(s->nmask.p + b / 32, 0, 16 * sizeof(uint32_t), ctx->stream));
+	ABW_CUDA(ctx, s->countN.alloc(nscaf));
+	ABW_CUDA(ctx, s->countGC.alloc(nscaf));
+	ABW_CUDA(ctx, d_err.alloc(1));
+	ABW_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
 	if(nscaf > 0) {
 		unsigned int blocks = (unsigned int)std::min<uint64_t>(abw_div_up((uint64_t)nscaf * 32, 256), (uint64_t)ctx->sm_count * 16);
-		k_pack<<<blocks, 256, 0, ctx->stream>>>(src, readable, d_off.p, s->base.p, nscaf, s->packed.p, s->valid.p, s->nmask.p, s->countN.p, s->countGC.p, d_err.p);
-		ctx->launches++;
-		PK(cudaGetLastError());
+		ABW_LAUNCH(ctx, k_pack, blocks, 256, 0, src, readable, d_off.p, s->base.p, nscaf, s->packed.p, s->valid.p, s->nmask.p, s->countN.p, s->countGC.p, d_err.p);
 	}
 	int h_err = 0;
-	PK(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-	PK(cudaStreamSynchronize(ctx->stream));
-#undef PK
-	if(h_err) {
-		delete s;
+	ABW_CUDA(ctx, cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if(h_err)
 		return abw_fail(ctx, ABW_ERR_ILLEGAL_DNA, "Illegal_DNAString: lower-case 'n' in a sequence (String.cpp:47-49)");
+	return ABW_OK;
+}
+
+int abw_pack_sequences(abw_ctx* ctx, const char* ascii, int ascii_on_device, const uint64_t* h_offsets, uint32_t nscaf, abw_seqset** out)
+{
+	if(!ctx || !out || !h_offsets || (!ascii && nscaf && h_offsets[nscaf] > 0))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_pack_sequences: null argument");
+	ABW_ENTER(ctx);
+	abw_seqset* s = new abw_seqset();
+	int rc = pack_impl(ctx, s, ascii, ascii_on_device, h_offsets, nscaf);
+	if(rc != ABW_OK) {
+		delete s;
+		return rc;
 	}
 	*out = s;
 	return ABW_OK;
@@ -639,7 +640,7 @@ int abw_segment(abw_ctx* ctx, const abw_seqset* s, uint32_t window_size, abw_seg
 {
 	if(!ctx || !s || !out || window_size == 0)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_segment: bad argument");
-	ABW_CUDA(ctx, cudaSetDevice(ctx->device));
+	ABW_ENTER(ctx);
 	abw_segments* g = new abw_segments();
 	g->nscaf = s->nscaf;
 	int rc = [&]() -> int {
@@ -704,7 +705,7 @@ int abw_kmer_features(abw_ctx* ctx, const abw_seqset* s, const abw_segments* g, 
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_kmer_features: unknown kind");
 	if(ld < (uint64_t)col0 + ABW_NKMER_DIMS - (skip_A? 1 : 0))
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_kmer_features: row stride too small");
-	ABW_CUDA(ctx, cudaSetDevice(ctx->device));
+	ABW_ENTER(ctx);
 	ABW_CHECK(upload_tables(ctx));
 	if(g->nseg == 0)
 		return ABW_OK;
@@ -730,7 +731,7 @@ int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uin
 		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_coverage: more than 2^32-1 reads per call; split the sample");
 	if(g->nseg >= (1ull << 32))
 		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_coverage: more than 2^32-1 windows");
-	ABW_CUDA(ctx, cudaSetDevice(ctx->device));
+	ABW_ENTER(ctx);
 	DevBuf<abw_read> d_reads;
 	const abw_read* rd = reads;
 	if(!reads_on_device && nreads) {

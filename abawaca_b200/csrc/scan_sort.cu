@@ -115,8 +115,7 @@ int scan_impl(abw_ctx* ctx, const Tin* d_in, uint64_t* d_out, uint64_t n, uint64
 	ABW_LAUNCH(ctx, k_scan_reduce<Tin>, nblocks, SCAN_THREADS, 0, d_in, n, sums.p);
 	ABW_LAUNCH(ctx, k_scan_block_sums, 1, 1024, 0, sums.p, (uint64_t)nblocks, d_total);
 	ABW_LAUNCH(ctx, k_scan_apply<Tin>, nblocks, SCAN_THREADS, 0, d_in, d_out, n, sums.p);
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // sums is freed on return
-	return ABW_OK;
+	return ABW_OK;                                       // sums is freed in stream order
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -276,7 +275,6 @@ int radix_sort_impl(abw_ctx* ctx, K* d_keys, K* d_keys_tmp, uint32_t* d_vals, ui
 		ABW_CUDA(ctx, cudaMemcpyAsync(d_keys, src_k, total * sizeof(K), cudaMemcpyDeviceToDevice, ctx->stream));
 		ABW_CUDA(ctx, cudaMemcpyAsync(d_vals, src_v, total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
 	}
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return ABW_OK;
 }
 

@@ -404,12 +404,6 @@ __device__ __forceinline__ unsigned long long orderable(double v)
 	unsigned long long b = (unsigned long long)__double_as_longlong(v);
 	return (b >> 63)? ~b : (b | 0x8000000000000000ull);
 }
-__device__ __forceinline__ double unorderable(unsigned long long k)
-{
-	unsigned long long b = (k >> 63)? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
-	return __longlong_as_double((long long)b);
-}
-
 // one thread per scaffold of every split cluster: vote (ClusterSeparator.cpp:94-101), child statistics, separating value
 __global__ void k_scaf_sides(const uint32_t* __restrict__ scaf_list, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs, const ScafRow* __restrict__ rows,
                              const uint32_t* __restrict__ low, const uint64_t* __restrict__ dp_first, const double* __restrict__ values, uint64_t N,
@@ -449,35 +443,6 @@ __global__ void k_scaf_sides(const uint32_t* __restrict__ scaf_list, const Clust
 		if(strategy == ABW_SPLIT_SCAFS && !((double)r.n >= __dmul_rn(fraction_in, (double)r.T)))
 			atomicAdd(&st->viol, 1u);
 		// separating value = largest value on the low side = max over scaffolds of their lo-th smallest value
-		if(lo > 0) {
-			const double* __restrict__ col = values + (uint64_t)jb.dim0 * N + dp_first[s];
-			unsigned long long kth = 0;
-			for(uint32_t a = 0; a < r.n; a++) {
-				const unsigned long long ka = orderable(col[a]);
-				uint32_t rank = 0;
-				for(uint32_t b = 0; b < r.n; b++) {
-					const unsigned long long kb = orderable(col[b]);
-					rank += (kb < ka) || (kb == ka && b < a);
-				}
-				if(rank == lo - 1)
-					kth = ka;
-			}
-			atomicMax(&value_key[blockIdx.y], kth);
-		}
-	}
-}
-
-// same as the tail of k_scaf_sides but for clusters that are NOT split: only the value of the best separation (log line parity)
-__global__ void k_value_only(const uint32_t* __restrict__ scaf_list, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs, const ScafRow* __restrict__ rows,
-                             const uint32_t* __restrict__ low, const uint64_t* __restrict__ dp_first, const double* __restrict__ values, uint64_t N,
-                             unsigned long long* __restrict__ value_key)
-{
-	const SplitJob jb = jobs[blockIdx.y];
-	const ClusterDesc cl = clusters[jb.cluster];
-	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cl.ns; i += gridDim.x * blockDim.x) {
-		const uint32_t s = scaf_list[cl.sOff + i];
-		const ScafRow r = rows[s];
-		const uint32_t lo = low[s];
 		if(lo > 0) {
 			const double* __restrict__ col = values + (uint64_t)jb.dim0 * N + dp_first[s];
 			unsigned long long kth = 0;
@@ -708,7 +673,8 @@ __global__ void k_dp_bins(const uint32_t* __restrict__ dp2scaf, const uint32_t* 
 // build: keys, within-scaffold classes, element packing
 // ---------------------------------------------------------------------------------------------------
 // tiled transpose of a row-major [N][ld] matrix (columns [d0, d0+nd)) into column-major [nd][N]
-__global__ void k_transpose_in(const double* __restrict__ rows, uint64_t ld, uint64_t N, uint32_t d0, uint32_t nd, double* __restrict__ cols)
+__global__ void k_transpose_in(const double* __restrict__ rows, uint64_t ld, uint64_t N, uint32_t d0, uint32_t nd, const uint64_t* __restrict__ row_of_dp,
+                               double* __restrict__ cols)
 {
 	__shared__ double tile[32][33];
 	const uint64_t r0 = (uint64_t)blockIdx.x * 32;
@@ -716,7 +682,7 @@ __global__ void k_transpose_in(const double* __restrict__ rows, uint64_t ld, uin
 	for(int j = threadIdx.y; j < 32; j += blockDim.y) {
 		uint64_t r = r0 + j;
 		uint32_t c = c0 + threadIdx.x;
-		tile[j][threadIdx.x] = (r < N && c < nd)? rows[r * ld + d0 + c] : 0.0;
+		tile[j][threadIdx.x] = (r < N && c < nd)? rows[(row_of_dp? row_of_dp[r] : r) * ld + d0 + c] : 0.0;
 	}
 	__syncthreads();
 	for(int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -725,6 +691,14 @@ __global__ void k_transpose_in(const double* __restrict__ rows, uint64_t ld, uin
 		if(r < N && c < nd)
 			cols[(uint64_t)c * N + r] = tile[threadIdx.x][j];
 	}
+}
+
+__global__ void k_gather_columns(const double* __restrict__ src, uint64_t ld, uint64_t N, const uint64_t* __restrict__ row_of_dp, double* __restrict__ cols)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t d = blockIdx.y;
+	if(i < N)
+		cols[(uint64_t)d * N + i] = src[(uint64_t)d * ld + row_of_dp[i]];
 }
 
 __global__ void k_make_keys(const double* __restrict__ values, uint64_t N, uint32_t nd, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ nan_flag)
@@ -861,7 +835,8 @@ int upload(abw_ctx* ctx, DevBuf<T>& buf, const std::vector<T>& h)
 	return ABW_OK;
 }
 
-int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_on_device, int layout, uint64_t ld, const uint32_t* h_dp2scaf)
+int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_on_device, int layout, uint64_t ld, uint64_t nrows, const uint64_t* h_row_of_dp,
+                 const uint32_t* h_dp2scaf)
 {
 	const uint64_t N = s->N;
 	const uint32_t D = s->D, S = s->S, W = s->W;
@@ -923,22 +898,39 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	DevBuf<uint32_t> d_scg_scafs, d_scg_index;
 	ABW_CHECK(upload(ctx, d_scg_scafs, scg_scafs));
 	ABW_CHECK(upload(ctx, d_scg_index, scg_index));
-	// ---- values, column major on the device
+	// ---- values, column major on the device (datapoint i lives in row row_of_dp[i] of the caller's matrix)
 	ABW_CUDA(ctx, s->values.alloc((size_t)D * N));
-	if(layout == ABW_LAYOUT_COLMAJOR) {
-		ABW_CUDA(ctx, cudaMemcpy2DAsync(s->values.p, N * sizeof(double), values, ld * sizeof(double), N * sizeof(double), D,
-		                                values_on_device? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-	}
-	else {
+	{
+		DevBuf<uint64_t> d_rowidx;
+		if(h_row_of_dp) {
+			for(uint64_t i = 0; i < N; i++)
+				if(h_row_of_dp[i] >= nrows)
+					return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: row_of_dp entry out of range");
+			std::vector<uint64_t> v(h_row_of_dp, h_row_of_dp + N);
+			ABW_CHECK(upload(ctx, d_rowidx, v));
+		}
 		DevBuf<double> tmp;
 		const double* src = values;
-		if(!values_on_device) {
-			ABW_CUDA(ctx, tmp.alloc((size_t)N * ld));
-			ABW_CUDA(ctx, cudaMemcpyAsync(tmp.p, values, sizeof(double) * N * ld, cudaMemcpyHostToDevice, ctx->stream));
-			src = tmp.p;
+		if(layout == ABW_LAYOUT_COLMAJOR && !h_row_of_dp) {
+			ABW_CUDA(ctx, cudaMemcpy2DAsync(s->values.p, N * sizeof(double), values, ld * sizeof(double), N * sizeof(double), D,
+			                                values_on_device? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
 		}
-		dim3 grid(abw_div_up(N, 32), abw_div_up(D, 32)), block(32, 8);
-		ABW_LAUNCH(ctx, k_transpose_in, grid, block, 0, src, ld, N, 0u, D, s->values.p);
+		else {
+			if(!values_on_device) {
+				const uint64_t count = (layout == ABW_LAYOUT_ROWMAJOR)? nrows * ld : (uint64_t)D * ld;
+				ABW_CUDA(ctx, tmp.alloc(count));
+				ABW_CUDA(ctx, cudaMemcpyAsync(tmp.p, values, sizeof(double) * count, cudaMemcpyHostToDevice, ctx->stream));
+				src = tmp.p;
+			}
+			if(layout == ABW_LAYOUT_ROWMAJOR) {
+				dim3 grid(abw_div_up(N, 32), abw_div_up(D, 32)), block(32, 8);
+				ABW_LAUNCH(ctx, k_transpose_in, grid, block, 0, src, ld, N, 0u, D, (const uint64_t*)(h_row_of_dp? d_rowidx.p : nullptr), s->values.p);
+			}
+			else {
+				dim3 grid(abw_div_up(N, 256), D);
+				ABW_LAUNCH(ctx, k_gather_columns, grid, 256, 0, src, ld, N, (const uint64_t*)d_rowidx.p, s->values.p);
+			}
+		}
 		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	}
 	// ---- per-dimension order, classes, elements; dimensions are processed in chunks to bound scratch memory
@@ -1358,8 +1350,8 @@ int search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t ca
 
 extern "C" {
 
-int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, int layout, uint64_t ld, uint64_t N, uint32_t D,
-                      const uint32_t* h_dp2scaf, uint32_t S, const uint32_t* h_T, const uint64_t* h_len, const uint64_t* h_scgmask, uint32_t W,
+int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, int layout, uint64_t ld, uint64_t nrows, const uint64_t* h_row_of_dp,
+                      uint64_t N, uint32_t D, const uint32_t* h_dp2scaf, uint32_t S, const uint32_t* h_T, const uint64_t* h_len, const uint64_t* h_scgmask, uint32_t W,
                       const abw_params* params, int strategy, abw_search** out)
 {
 	if(!ctx || !out || !values || !h_dp2scaf || !h_T || !h_len || (W > 0 && !h_scgmask))
@@ -1372,9 +1364,11 @@ int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, 
 		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: at most 512 distinct SCG names (W <= 8)");
 	if(N >= (1ull << 31) || S >= (1u << EL_SCAF_BITS))
 		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: at most 2^31-1 datapoints and 2^27-1 scaffolds per device");
-	if((layout == ABW_LAYOUT_COLMAJOR && ld < N) || (layout == ABW_LAYOUT_ROWMAJOR && ld < D))
+	if(!h_row_of_dp)
+		nrows = N;
+	if(nrows < 1 || (layout == ABW_LAYOUT_COLMAJOR && ld < nrows) || (layout == ABW_LAYOUT_ROWMAJOR && ld < D))
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: leading dimension too small");
-	ABW_CUDA(ctx, cudaSetDevice(ctx->device));
+	ABW_ENTER(ctx);
 	abw_search* s = new abw_search();
 	s->ctx = ctx;
 	s->N = N; s->D = D; s->S = S; s->W = (W == 0)? 1 : W;
@@ -1390,7 +1384,7 @@ int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, 
 		memcpy(s->h_mask.data(), h_scgmask, sizeof(uint64_t) * (size_t)S * W);
 	EventTimer tm(ctx->stream);
 	tm.start();
-	int rc = search_build(ctx, s, values, values_on_device, layout, ld, h_dp2scaf);
+	int rc = search_build(ctx, s, values, values_on_device, layout, ld, nrows, h_row_of_dp, h_dp2scaf);
 	s->prof.build_ms = tm.stop();
 	if(rc != ABW_OK) {
 		delete s;
@@ -1406,7 +1400,7 @@ int abw_search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_
 {
 	if(!ctx || !s)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_run: null argument");
-	ABW_CUDA(ctx, cudaSetDevice(ctx->device));
+	ABW_ENTER(ctx);
 	return search_run(ctx, s, h_recs, cap, nrecs, h_dp2cluster, h_scaf2cluster);
 }
 
@@ -1422,6 +1416,7 @@ int abw_cluster_scg(abw_ctx* ctx, const abw_search* s, const uint32_t* h_scafs, 
 {
 	if(!ctx || !s || (!h_scafs && nscafs))
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_cluster_scg: null argument");
+	ABW_ENTER(ctx);
 	// SCGdb::num_unique_scgs / average_num_copies_for_unique_scgs (SCGdb.cpp:6-18,41-55) through the same terminal-cluster kernel
 	DevBuf<uint32_t> d_list;
 	DevBuf<TermJob> d_job;

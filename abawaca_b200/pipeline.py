@@ -8,6 +8,7 @@ Everything that computes goes through libabawaca_b200.so; numpy only carries buf
 from __future__ import annotations
 
 import ctypes as C
+import time
 
 import numpy as np
 
@@ -69,21 +70,31 @@ class FeatureBuild:
 
 
 def build_features(ctx: capi.Context, seq, offsets, reads, this_sample=0, params=None, kind=capi.FEAT_TRUNC3, skip_A=True,
-                   seq_on_device=False, reads_on_device=False, nreads=None) -> FeatureBuild:
+                   seq_on_device=False, reads_on_device=False, nreads=None, timings=None) -> FeatureBuild:
     """seq: uint8 ASCII (numpy array, or a device pointer int when seq_on_device); offsets: uint64 [nscaf+1];
     reads: one structured array (capi.READ_DTYPE) per sample (or device pointers + nreads)."""
     L = ctx.lib
     p = params or capi.default_params()
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
     nscaf = offsets.size - 1
+    t_last = [time.perf_counter()]
+
+    def lap(name):
+        if timings is not None:
+            ctx.synchronize()
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + 1000.0 * (now - t_last[0])
+            t_last[0] = now
     seqset = C.c_void_p()
     if seq_on_device:
         ctx.check(L.abw_pack_sequences(ctx.h, C.c_void_p(seq), 1, capi._p(offsets), nscaf, C.byref(seqset)))
     else:
         seq = np.ascontiguousarray(seq, dtype=np.uint8)
         ctx.check(L.abw_pack_sequences(ctx.h, capi._p(seq), 0, capi._p(offsets), nscaf, C.byref(seqset)))
+    lap("pack_ms")
     segs = C.c_void_p()
     ctx.check(L.abw_segment(ctx.h, seqset, p.window_size, C.byref(segs)))
+    lap("segment_ms")
     nseg = int(L.abw_segments_count(segs))
     nk = capi.NKMER - (1 if skip_A else 0)
     ncols = nk + len(reads)
@@ -91,6 +102,7 @@ def build_features(ctx: capi.Context, seq, offsets, reads, this_sample=0, params
     d_nbps = ctx.alloc(max(nscaf, 1) * 8)
     ctx.memset(d_nbps, 0, max(nscaf, 1) * 8)
     ctx.check(L.abw_kmer_features(ctx.h, seqset, segs, kind, 1 if skip_A else 0, C.c_void_p(d_rows), ncols, 0))
+    lap("kmer_ms")
     for j, r in enumerate(reads):
         nb = C.c_void_p(d_nbps) if j == this_sample else None
         if reads_on_device:
@@ -99,6 +111,7 @@ def build_features(ctx: capi.Context, seq, offsets, reads, this_sample=0, params
             r = np.ascontiguousarray(r)
             ctx.check(L.abw_coverage(ctx.h, segs, capi._p(r), r.size, 0, p.max_snps, kind, C.c_void_p(d_rows), ncols, nk + j, nb))
     ctx.synchronize()
+    lap("coverage_ms")
     return FeatureBuild(ctx, seqset, segs, d_rows, nseg, ncols, nscaf, d_nbps)
 
 
@@ -123,21 +136,29 @@ class SearchResult:
 
 
 def search(ctx: capi.Context, values, dp2scaf, T, length, scgmask, params=None, strategy=capi.SENS_SPEC, layout=capi.LAYOUT_COLMAJOR,
-           values_on_device=False, N=None, D=None, ld=None, want_bins=True) -> SearchResult:
-    """values: numpy [D][N] (column major) or [N][D] (row major), or a device pointer with N, D, ld given."""
+           values_on_device=False, N=None, D=None, ld=None, want_bins=True, row_of_dp=None, nrows=None, timings=None) -> SearchResult:
+    """values: numpy [D][nrows] (column major) or [nrows][D] (row major), or a device pointer with nrows, D, ld given.
+    row_of_dp (uint64 [N], optional): the matrix row of every datapoint; default: N = nrows, datapoint i = row i."""
     L = ctx.lib
     p = params or capi.default_params()
     if not values_on_device:
         values = np.ascontiguousarray(values, dtype=np.float64)
         if layout == capi.LAYOUT_COLMAJOR:
-            D, N = values.shape
-            ld = N
+            D, nrows = values.shape
+            ld = nrows
         else:
-            N, D = values.shape
+            nrows, D = values.shape
             ld = D
         vptr = capi._p(values)
     else:
         vptr = C.c_void_p(values)
+        if nrows is None:
+            nrows = N
+    if row_of_dp is not None:
+        row_of_dp = np.ascontiguousarray(row_of_dp, dtype=np.uint64)
+        N = row_of_dp.size
+    else:
+        N = nrows
     dp2scaf = np.ascontiguousarray(dp2scaf, dtype=np.uint32)
     T = np.ascontiguousarray(T, dtype=np.uint32)
     length = np.ascontiguousarray(length, dtype=np.uint64)
@@ -146,8 +167,10 @@ def search(ctx: capi.Context, values, dp2scaf, T, length, scgmask, params=None, 
         scgmask = scgmask.reshape(-1, 1)
     S, W = T.size, scgmask.shape[1]
     h = C.c_void_p()
-    ctx.check(L.abw_search_create(ctx.h, vptr, 1 if values_on_device else 0, layout, ld, N, D, capi._p(dp2scaf), S, capi._p(T), capi._p(length),
+    t0 = time.perf_counter()
+    ctx.check(L.abw_search_create(ctx.h, vptr, 1 if values_on_device else 0, layout, ld, nrows, capi._p(row_of_dp), N, D, capi._p(dp2scaf), S, capi._p(T), capi._p(length),
                                   capi._p(scgmask), W, C.byref(p), strategy, C.byref(h)))
+    t1 = time.perf_counter()
     try:
         cap = int(max(64, 2 * (N // max(p.cluster_ndps_threshold, 1)) + 64))
         recs = (capi.ClusterRec * cap)()
@@ -155,6 +178,9 @@ def search(ctx: capi.Context, values, dp2scaf, T, length, scgmask, params=None, 
         dp2c = np.zeros(N, dtype=np.uint32) if want_bins else None
         s2c = np.zeros(S, dtype=np.uint32) if want_bins else None
         ctx.check(L.abw_search_run(ctx.h, h, recs, cap, C.byref(n), capi._p(dp2c), capi._p(s2c)))
+        if timings is not None:
+            timings["search_create_ms"] = timings.get("search_create_ms", 0.0) + 1000.0 * (t1 - t0)
+            timings["search_run_ms"] = timings.get("search_run_ms", 0.0) + 1000.0 * (time.perf_counter() - t1)
         prof = capi.SearchProfile()
         L.abw_search_get_profile(h, C.byref(prof))
         return SearchResult([recs[i] for i in range(min(n.value, cap))], dp2c, s2c, prof)

@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- scaffolds/s binned (feature build + split search) on N B200s, with roofline and CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scaffolds S --samples M --genomes G]
+
+One "step" = one pass of the hot path over one synthetic metagenome: pack -> windows -> k-mer signature ->
+per-sample coverage -> split search down to the final bins.  At N=1 the workload is BASELINE.json configs[1]
+(50k scaffolds, 10 samples).  At N>1 every rank bins its own metagenome of that size (independent assemblies,
+no data-path collective; weak scaling) and only bin counts are gathered over NCCL.
+
+  value : whole-job scaffolds/s with the inputs (ASCII assembly, read records) already resident in HBM
+  e2e   : the same through the C ABI with HOST buffers: H2D of assembly + reads and D2H of the .lrn matrix and bins inside the timed region
+  roofline / kernels : per-kernel CUDA-event durations of one extra profiled step (abw_profile_enable), algorithmic bytes from DESIGN.md
+  cpu_baseline : the UNMODIFIED reference binaries (oracle/_ref, -O2 build) on a bounded sample of the same workload, on this box's cores
+
+`--impl reference` times only that reference arm (rank 0; other ranks exit 0).
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from abawaca_b200 import synth  # noqa: E402
+
+FALLBACK_HBM_GBS = 6650.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_args(args):
+    w = dict(synth.CONFIGS["cfg2"])
+    if args.scaffolds:
+        w["n_scaffolds"] = args.scaffolds
+    if args.samples:
+        w["n_samples"] = args.samples
+    if args.genomes:
+        w["n_genomes"] = args.genomes
+    return w
+
+
+def workload_name(w):
+    base = "BASELINE.json configs[1]: 50k scaffolds, 10 samples, feature build + split search" if (w["n_scaffolds"], w["n_samples"]) == (50000, 10) \
+        else "reduced variant of configs[1]"
+    return f"{base} ({w['n_scaffolds']} scaffolds, {w['n_samples']} samples, {w['n_genomes']} synthetic genomes, seed {w['seed']})"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified reference binaries on a bounded sample
+# ------------------------------------------------------------------------------------------------------------------
+def reference_sample(mg, per_genome=400, genomes=2):
+    """The first `per_genome` scaffolds (name order) of each of the first `genomes` genomes, with their reads."""
+    sel = []
+    for g in sorted(set(mg.genome.tolist()))[:genomes]:
+        sel.extend(np.nonzero(mg.genome == g)[0][:per_genome].tolist())
+    sel = np.array(sorted(sel))
+    remap = np.full(mg.nscaf, -1, dtype=np.int64)
+    remap[sel] = np.arange(sel.size)
+    lengths = np.diff(mg.offsets.astype(np.int64))[sel]
+    offsets = np.zeros(sel.size + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lengths)
+    seq = np.concatenate([mg.scaffold(int(i)) for i in sel])
+    reads = []
+    for r in mg.reads:
+        keep = remap[r["scaf"]] >= 0
+        rr = r[keep].copy()
+        rr["scaf"] = remap[rr["scaf"]].astype(np.uint32)
+        reads.append(rr)
+    names = [mg.names[int(i)] for i in sel]
+    nameset = set(names)
+    g2s = [(g, s) for g, s in mg.gene2scg if g[:g.rfind("_")] in nameset]
+    return synth.Metagenome(names, mg.genome[sel], offsets, seq, reads, mg.scg_names, g2s, mg.read_len, mg.seed)
+
+
+def run_reference_once(paths, workdir, ncpu):
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    build = os.path.join(workdir, "build")
+    out = os.path.join(workdir, "out")
+    shutil.rmtree(build, ignore_errors=True)
+    shutil.rmtree(out, ignore_errors=True)
+    os.makedirs(build)
+    t0 = time.perf_counter()
+    subprocess.run([os.path.join(ref, "abawaca-build"), "-f", paths["fasta"], "-o", build, "-s", os.path.join(workdir, "sample*.sam"), "-c", paths["sams"][0]],
+                   check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    t1 = time.perf_counter()
+    env = dict(os.environ, ABW_SCG_LIST=paths["scg_list"])
+    subprocess.run([os.path.join(ref, "abawaca"), "-u", build, "-o", out, "-c", paths["gene2scg"], "-p", str(ncpu)], check=True, env=env,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    t2 = time.perf_counter()
+    bins = [int(l.split("\t")[1]) for l in open(os.path.join(out, "scaf2cluster.txt"))]
+    return t1 - t0, t2 - t1, bins
+
+
+def reference_arm(mg, steps, warmup, want_bins=False):
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref, "abawaca")):
+        raise RuntimeError("oracle/_ref is not built (run __graft_entry__.build() where /root/reference is mounted)")
+    sample = reference_sample(mg)
+    ncpu = max(1, min(40, os.cpu_count() or 1))       # abawaca -p is capped at 40 (abawaca.cpp:326-331)
+    wd = tempfile.mkdtemp(prefix="abw_ref_")
+    try:
+        paths = synth.write_reference_inputs(sample, wd)
+        tb, ts, bins = [], [], None
+        for i in range(warmup + steps):
+            b, s, bins = run_reference_once(paths, wd, ncpu)
+            if i >= warmup:
+                tb.append(b); ts.append(s)
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+    t = float(np.mean(tb) + np.mean(ts))
+    info = dict(value=sample.nscaf / t, unit="scaffolds/s", cores=ncpu, kind="reference",
+                sample=f"{sample.nscaf} scaffolds (first 400 of each of 2 genomes) of the workload, {sum(r.size for r in sample.reads)} reads in {len(sample.reads)} SAM files; "
+                       f"unmodified reference built -O2; abawaca-build (single-threaded by construction) {np.mean(tb):.2f} s + abawaca -p {ncpu} {np.mean(ts):.2f} s",
+                build_s=float(np.mean(tb)), bin_s=float(np.mean(ts)))
+    return info, sample, bins
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------------------------
+def gpu_bins_for(ctx, mg, pipeline, capi):
+    """One full pass from HOST buffers; returns (scaf2cluster over ALL scaffolds incl. dropped ones = 0, FeatureBuild kept open = None)."""
+    fb = pipeline.build_features(ctx, mg.seq, mg.offsets, mg.reads, this_sample=0)
+    sg = fb.segments_host()
+    keep, dp2scaf, T, kept = pipeline.search_problem_from_features(sg["seg_scaf"], mg.nscaf)
+    length = np.diff(mg.offsets.astype(np.int64)).astype(np.uint64)[kept]
+    mask = mg.scg_masks()[kept]
+    rows = fb.rows_host()
+    res = pipeline.search(ctx, rows, dp2scaf, T, length, mask, layout=capi.LAYOUT_ROWMAJOR, row_of_dp=np.nonzero(keep)[0])
+    fb.close()
+    bins = np.zeros(mg.nscaf, dtype=np.int64)
+    bins[kept] = res.scaf2cluster
+    return bins, kept
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaffolds", type=int, default=0)
+    ap.add_argument("--samples", type=int, default=0)
+    ap.add_argument("--genomes", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    w = workload_args(args)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        mg = synth.make_metagenome(**w, q6_reads=True)
+        info, sample, _ = reference_arm(mg, args.steps, max(args.warmup, 0))
+        line = {"impl": "reference", "metric": "scaffolds/sec binned (feature build + split search)", "value": info["value"], "unit": "scaffolds/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sample.nscaf / info["value"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64/f64", "data": "synthetic",
+                "config": {"workload": workload_name(w), "timed": "bounded sample: " + info["sample"]},
+                "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": info["value"], "unit": "scaffolds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    from abawaca_b200 import capi, pipeline
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w_rank = dict(w, seed=w["seed"] + 1000 * rank)
+    mg = synth.make_metagenome(**w_rank, q6_reads=True)
+    ctx = capi.Context(local_rank)
+    L = ctx.lib
+    import ctypes as C
+    nscaf = mg.nscaf
+    lengths = np.diff(mg.offsets.astype(np.int64)).astype(np.uint64)
+    masks = mg.scg_masks()
+    total_bp = int(mg.seq.size)
+    nreads = [int(r.size) for r in mg.reads]
+
+    # pinned host copies (e2e) and device-resident copies (value)
+    h_seq = torch.from_numpy(mg.seq).pin_memory()
+    h_reads = [torch.from_numpy(r.view(np.uint32).reshape(-1, 4)).pin_memory() for r in mg.reads]
+    d_seq = ctx.alloc(total_bp + 64)
+    ctx.to_device(d_seq, mg.seq)
+    d_reads = []
+    for r in mg.reads:
+        p = ctx.alloc(max(r.nbytes, 16))
+        ctx.to_device(p, r)
+        d_reads.append(p)
+
+    state = {}
+    h_reads_np = [t.numpy().view(capi.READ_DTYPE).reshape(-1) for t in h_reads]
+
+    def step(resident, timings=None):
+        if resident:
+            fb = pipeline.build_features(ctx, d_seq, mg.offsets, d_reads, this_sample=0, seq_on_device=True, reads_on_device=True, nreads=nreads, timings=timings)
+        else:
+            fb = pipeline.build_features(ctx, h_seq.numpy(), mg.offsets, h_reads_np, this_sample=0, timings=timings)
+        sg = fb.segments_host()
+        keep, dp2scaf, T, kept = pipeline.search_problem_from_features(sg["seg_scaf"], nscaf)
+        row_of_dp = None if keep.all() else np.nonzero(keep)[0].astype(np.uint64)   # scaffolds with one window are dropped (ScafDpData.cpp:92-93)
+        rows_host = None
+        if not resident:
+            rows_host = fb.rows_host()                 # the .lrn matrix goes back to the host in the end-to-end path
+        res = pipeline.search(ctx, fb.d_rows, dp2scaf, T, lengths[kept], masks[kept], layout=capi.LAYOUT_ROWMAJOR, values_on_device=True,
+                              nrows=fb.nseg, D=fb.ncols, ld=fb.ncols, row_of_dp=row_of_dp, timings=timings)
+        state.update(ndps=int(keep.sum()), nseg=fb.nseg, ncols=fb.ncols, prof=res.profile, nclusters=len(res.recs), nbins=len(set(res.scaf2cluster.tolist()) - {0}),
+                     seg_len=(sg["seg_end"] - sg["seg_start"] + 1), rows_bytes=0 if rows_host is None else rows_host.nbytes, bins=res.scaf2cluster)
+        fb.close()
+        return res
+
+    ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(resident, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches
+        e0.record(ext)
+        for _ in range(steps):
+            step(resident)
+        e1.record(ext)
+        e1.synchronize()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), ctx.launches - l0
+
+    for _ in range(args.warmup):
+        step(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_res, launches = timed(True, args.steps)
+    clocks = sampler.stop()
+    step(False)                                        # warm the host-buffer path once
+    ms_e2e, _ = timed(False, args.steps)
+
+    # one extra profiled step: per-kernel CUDA-event durations (launches serialised while profiling)
+    phase_ms = {}
+    t0 = time.perf_counter()
+    step(True, timings=phase_ms)                       # host wall-clock per ABI phase of one (un-profiled) resident step
+    phase_ms["step_total_ms"] = 1000.0 * (time.perf_counter() - t0)
+    ctx.profile(True)
+    step(True)
+    report = ctx.profile_report()
+    ctx.profile(False)
+    prof = state["prof"]
+    hbm, peak_src = peaks()
+    seg_len = state["seg_len"].astype(np.int64)
+    alg = {
+        # algorithmic bytes per launch
+        "k_kmer<ABW_FEAT_TRUNC3>": float(((seg_len + 3) // 4 + (seg_len + 7) // 8).sum() + state["nseg"] * 179 * 8),
+        "k_sweep<ABW_SENS_SPEC>": 12.0 * prof.sweep_elements,
+    }
+    kernels = {}
+    total_ms = sum(v[1] for v in report.values())
+    for k, (cnt, ms) in sorted(report.items(), key=lambda kv: -kv[1][1]):
+        ent = {"launches": cnt, "ms": round(ms, 4), "share": round(ms / total_ms, 4) if total_ms else None}
+        if k in alg and ms > 0:
+            ent["algorithmic_GBps"] = round(alg[k] / (ms * 1e-3) / 1e9, 2)
+            ent["frac_of_hbm_peak"] = round(alg[k] / (ms * 1e-3) / 1e9 / hbm, 4)
+        kernels[k] = ent
+    # the roofline object: the dominant kernel among those the survey gives algorithmic bytes for
+    dom = max(alg, key=lambda k: report.get(k, (0, 0.0))[1])
+    dcnt, dms = report.get(dom, (1, 0.0))
+    ach = alg[dom] / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 2), "peak": hbm, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / hbm, 4),
+                "traffic": None, "launches_per_step": dcnt, "ms_per_step_in_kernel": round(dms, 4),
+                "algorithmic_bytes_per_step": alg[dom]}
+
+    total_scaf = nscaf * world
+    value = total_scaf * args.steps / (ms_res * 1e-3)
+    e2e_value = total_scaf * args.steps / (ms_e2e * 1e-3)
+    h2d = total_bp + sum(r.nbytes for r in mg.reads) + mg.offsets.nbytes + state["nseg"] * 4 + nscaf * (4 + 8 + 8 * masks.shape[1])
+    # .lrn matrix + window table + per-scaffold bins + per-datapoint bins
+    d2h = state["nseg"] * state["ncols"] * 8 + state["nseg"] * (4 + 3 * 8) + (nscaf + 1) * 8 + nscaf * 4 + state["nseg"] * 4
+
+    bins_total = state["nbins"]
+    if world > 1:
+        t = torch.tensor([bins_total], device="cuda")
+        dist.all_reduce(t)                            # NCCL: gather of per-shard bin counts only
+        bins_total = int(t.item())
+
+    line = {"metric": "scaffolds/sec binned (feature build + split search)", "value": round(value, 2), "unit": "scaffolds/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/int64/f64", "data": "synthetic",
+            "config": {"workload": workload_name(w), "per_gpu": f"{nscaf} scaffolds, {total_bp} bp, {state['nseg']} windows x {state['ncols']} dimensions, {sum(nreads)} read records",
+                       "parallelism": f"{world} independent assemblies, one per GPU" if world > 1 else "1 GPU",
+                       "l2": "inputs (assembly + read records, > 2 GB) are larger than the 126 MB L2; no explicit flush",
+                       "clusters_evaluated": state["nclusters"], "bins": bins_total, "search_levels": prof.levels},
+            "e2e": {"value": round(e2e_value, 2), "unit": "scaffolds/s", "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "phase_wall_ms": {k: round(v, 3) for k, v in phase_ms.items()},
+            "search_profile_ms": {"build": round(prof.build_ms, 3), "sweep": round(prof.sweep_ms, 3), "partition": round(prof.partition_ms, 3), "other": round(prof.other_ms, 3)}}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            info, sample, ref_bins = reference_arm(mg, 1, 0)
+            gbins, kept = gpu_bins_for(ctx, sample, pipeline, capi)
+            # the reference lists only scaffolds with >= 2 windows (ScafDpData.cpp:92-93)
+            info["gpu_bins_identical_on_sample"] = bool(ref_bins == [int(b) for b in gbins[kept]])
+            line["cpu_baseline"] = info
+        except Exception as e:  # the baseline must never take the bench line down
+            line["cpu_baseline"] = {"value": None, "unit": "scaffolds/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e!r}"}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

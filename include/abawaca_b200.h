@@ -74,6 +74,11 @@ uint64_t    abw_kernel_launches(const abw_ctx* ctx);
 /* the stream every kernel of this context is launched on (a cudaStream_t), for event timing */
 void*       abw_ctx_stream(const abw_ctx* ctx);
 int         abw_ctx_synchronize(abw_ctx* ctx);
+/* Per-kernel device timing for profiling runs: while enabled every launch is bracketed by CUDA events on the context
+ * stream and waited for (so launches are serialised; do not enable it in a timed region).  abw_profile_report writes
+ * "kernel<TAB>launches<TAB>total_ms" lines into buf and returns the size needed. */
+int         abw_profile_enable(abw_ctx* ctx, int on);
+size_t      abw_profile_report(abw_ctx* ctx, char* buf, size_t cap);
 
 /* ---- feature stage (abawaca-build) ------------------------------------------------------------ */
 
@@ -125,9 +130,11 @@ int abw_memset_device(abw_ctx* ctx, void* d_ptr, int byte, size_t bytes);
  * ScafDpData.cpp:91-99, SCGdb.cpp:86-117): N datapoints x D dimensions, dp2scaf[N] (non-decreasing),
  * T[S] = scaf_db.ndps(scaf) (must be >= 2: ScafDpData drops scaffolds with one dp, quirk Q1),
  * len[S] = sequence length, scgmask[S][W] = bit set of SCG names per scaffold.
- * The all-inclusive cluster 1 (init_cluster, abawaca.cpp:242-251) is the root. */
-int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, int layout, uint64_t ld, uint64_t N, uint32_t D,
-                      const uint32_t* h_dp2scaf, uint32_t S, const uint32_t* h_T, const uint64_t* h_len, const uint64_t* h_scgmask, uint32_t W,
+ * The value matrix has nrows rows; datapoint i is row h_row_of_dp[i] of it (NULL: nrows = N and datapoint i is row i).
+ * This is how the rows of scaffolds with a single window, which abawaca-build writes but ScafDpData drops, are skipped
+ * without copying the matrix.  The all-inclusive cluster 1 (init_cluster, abawaca.cpp:242-251) is the root. */
+int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, int layout, uint64_t ld, uint64_t nrows, const uint64_t* h_row_of_dp,
+                      uint64_t N, uint32_t D, const uint32_t* h_dp2scaf, uint32_t S, const uint32_t* h_T, const uint64_t* h_len, const uint64_t* h_scgmask, uint32_t W,
                       const abw_params* params, int strategy, abw_search** out);
 void abw_search_destroy(abw_search* s);
 

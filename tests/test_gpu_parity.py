@@ -195,3 +195,21 @@ def test_features_match_oracle_on_a_larger_random_assembly(ctx, oracle):
     st = fb.scaffold_stats_host(np.diff(mg.offsets.astype(np.int64)))
     assert np.array_equal(st["cvg"], f["info_cvg"]) and np.array_equal(st["gc"], f["info_gc"]) and np.array_equal(st["Ns"], f["info_Ns"])
     fb.close()
+
+
+def test_row_index_skips_dropped_rows(ctx):
+    """abawaca-build writes rows for scaffolds with a single window; ScafDpData drops them (quirk Q1): row_of_dp does the same without a copy."""
+    from abawaca_b200 import capi, pipeline
+    prob = search_problem("tiny_clean")
+    vals = prob["values"]                                   # [D][N]
+    D, N = vals.shape
+    rng = np.random.default_rng(3)
+    nrows = N + 37
+    pos = np.sort(rng.choice(nrows, size=N, replace=False)).astype(np.uint64)
+    big = rng.normal(size=(nrows, D))
+    big[pos] = vals.T
+    ref = pipeline.search(ctx, vals, prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"])
+    for layout, mat in ((capi.LAYOUT_ROWMAJOR, big), (capi.LAYOUT_COLMAJOR, np.ascontiguousarray(big.T))):
+        res = pipeline.search(ctx, mat, prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"], layout=layout, row_of_dp=pos)
+        assert res.scaf2cluster.tolist() == ref.scaf2cluster.tolist() and res.dp2cluster.tolist() == ref.dp2cluster.tolist()
+        assert [(r.id, r.split, r.best.dim, r.best.value) for r in res.recs] == [(r.id, r.split, r.best.dim, r.best.value) for r in ref.recs]

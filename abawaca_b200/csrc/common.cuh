@@ -109,7 +109,8 @@ int abw_exclusive_scan_u32_to_u64(abw_ctx* ctx, const uint32_t* d_in, uint64_t* 
 
 // Stable LSD radix sort of `batch` independent arrays of n (key, value) pairs each (array b at offset b*stride).
 // Only key bits [0, nbits) are examined.  Result is left in (keys, vals); (keys_tmp, vals_tmp) are scratch of the same size.
-// Passes in which every key of every array shares the same digit are skipped.
+// Digits are 8 or 9 bits wide, placed only over key bits that actually vary (bits equal in all keys of all arrays are skipped).
 int abw_radix_sort_pairs_u64(abw_ctx* ctx, uint64_t* d_keys, uint64_t* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, uint32_t batch,
                              uint64_t stride, int nbits);
-int abw_radix_sort_pairs_u32(abw_ctx* ctx, uint32_t* d_keys, uint32_t* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, int nbits);
+int abw_radix_sort_pairs_u32(abw_ctx* ctx, uint32_t* d_keys, uint32_t* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, uint32_t batch,
+                             uint64_t stride, int nbits);

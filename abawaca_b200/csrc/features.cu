@@ -222,15 +222,20 @@ __global__ void __launch_bounds__(256) k_seg_fill(const uint64_t* __restrict__ l
 // k-mer signature, abawaca-build.cpp:103-174
 // ---------------------------------------------------------------------------------------------------
 // dimension tables: for each of the 180 canonical dims the k, and the two little-endian codes (mer, reverse complement)
-__constant__ uint8_t  c_dim_k[ABW_NKMER_DIMS];
-__constant__ uint16_t c_dim_code_a[ABW_NKMER_DIMS];
-__constant__ uint16_t c_dim_code_b[ABW_NKMER_DIMS];
-__constant__ double   c_milli[1001];                        // m / 1000.0
+// Kept in GLOBAL memory and copied to shared memory by every CTA: lanes index them with different addresses, which the
+// indexed-constant path serialises (round 1 ncu: ADU pipe 72 % busy with these lookups when they were __constant__).
+__device__ uint32_t g_dim_tab[ABW_NKMER_DIMS];              // k | code_a << 8 | code_b << 16
+__device__ double   g_milli[1001];                          // m / 1000.0
 
 constexpr int KM_WARPS = 8;
 constexpr int KM_WORDS_PER_LANE = 7;                        // 16-base words per lane per round: <= 112 increments per byte counter
 constexpr int KM_ROUND_WORDS = 32 * KM_WORDS_PER_LANE;      // 224 words = 3584 bases per round
 constexpr int KM_STAGE_WORDS = KM_ROUND_WORDS + 2;          // + lookahead word + alignment slack
+
+struct __align__(16) KmBlockSmem {
+	double   milli[1001 + 1];
+	uint32_t dim_tab[ABW_NKMER_DIMS];
+};
 
 struct __align__(16) KmWarpSmem {
 	uint32_t hist[64 * 32];         // [3-mer row][lane] four byte counters (4th base) : 8 KB, bank = lane
@@ -242,6 +247,7 @@ struct __align__(16) KmWarpSmem {
 	uint32_t cnt1[4];
 	uint32_t tot[4];
 	uint32_t pad[2];
+	double   inv_tot[4];            // 1 / total_k, only used to form an integer quotient that is then verified exactly
 };
 
 __device__ __forceinline__ uint32_t stream_bits(const uint32_t* __restrict__ a, uint64_t bitpos, uint32_t nbits_le32)
@@ -260,11 +266,16 @@ __global__ void __launch_bounds__(KM_WARPS * 32) k_kmer(const uint32_t* __restri
                                                         double* __restrict__ rows, uint64_t ld, uint32_t col0)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	KmWarpSmem* sm = reinterpret_cast<KmWarpSmem*>(smem_raw) + (threadIdx.x >> 5);
+	KmBlockSmem* bs = reinterpret_cast<KmBlockSmem*>(smem_raw);
+	KmWarpSmem* sm = reinterpret_cast<KmWarpSmem*>(smem_raw + sizeof(KmBlockSmem)) + (threadIdx.x >> 5);
 	const int lane = threadIdx.x & 31;
+	for(int i = threadIdx.x; i <= 1000; i += blockDim.x)
+		bs->milli[i] = g_milli[i];
+	for(int i = threadIdx.x; i < ABW_NKMER_DIMS; i += blockDim.x)
+		bs->dim_tab[i] = g_dim_tab[i];
 	for(int i = lane; i < 64 * 32; i += 32)
 		sm->hist[i] = 0;
-	__syncwarp();
+	__syncthreads();
 	const uint64_t warp0 = (uint64_t)blockIdx.x * KM_WARPS + (threadIdx.x >> 5), nwarps = (uint64_t)gridDim.x * KM_WARPS;
 	for(uint64_t g = warp0; g < nseg; g += nwarps) {
 		const uint64_t gb = seg_gbase[g];
@@ -383,35 +394,41 @@ __global__ void __launch_bounds__(KM_WARPS * 32) k_kmer(const uint32_t* __restri
 			if(lane == 0) {
 				sm->tot[0] = t1; sm->tot[1] = t2; sm->tot[2] = t3; sm->tot[3] = t4;
 			}
+			if(lane < 4) {
+				const uint32_t tk = (lane == 0)? t1 : (lane == 1)? t2 : (lane == 2)? t3 : t4;
+				sm->inv_tot[lane] = tk? 1.0 / (double)tk : 0.0;
+			}
 			__syncwarp();
 		}
 		// 180 canonical dimensions: dims[canon] += count/total for the mer and for its reverse complement (:171)
 		for(int d = lane; d < ABW_NKMER_DIMS; d += 32) {
-			const int k = c_dim_k[d];
+			const uint32_t ent = bs->dim_tab[d];
+			const int k = ent & 0xFFu;
 			const uint32_t* cnt = (k == 4)? sm->cnt4 : (k == 3)? sm->cnt3 : (k == 2)? sm->cnt2 : sm->cnt1;
-			const uint32_t ca = c_dim_code_a[d], cb = c_dim_code_b[d];
+			const uint32_t ca = (ent >> 8) & 0xFFu, cb = (ent >> 16) & 0xFFu;
 			const uint32_t c1 = cnt[ca], c2 = (cb != ca)? cnt[cb] : 0u;
 			const uint32_t t = sm->tot[k - 1];
 			double out = 0.0;
 			if(t != 0 && (c1 + c2) != 0) {
-				if(KIND == ABW_FEAT_TRUNC3) {
+				bool exact_path = (KIND != ABW_FEAT_TRUNC3) || (c1 + c2) > 4000000u;
+				if(!exact_path) {
 					// int(1000*(c1/t + c2/t)) equals floor(1000*(c1+c2)/t) whenever the quotient is not an integer: the rounding
-					// error of the three fp64 operations (< 1e-12) is far below the distance 1/t (t < 2^24) to the next integer
-					uint64_t num = 1000ull * (c1 + c2), m = num / t;
-					if(num - m * t != 0)
-						out = c_milli[m];
-					else {
-						double x = (c1? __ddiv_rn((double)c1, (double)(int)t) : 0.0);
-						if(c2)
-							x = __dadd_rn(x, __ddiv_rn((double)c2, (double)(int)t));
-						out = __ddiv_rn((double)__double2int_rz(__dmul_rn(1000.0, x)), 1000.0);
-					}
+					// error of the three fp64 operations (< 1e-12) is far below the distance 1/t to the next integer
+					const uint32_t num = 1000u * (c1 + c2);
+					uint32_t m = (uint32_t)__double2uint_rz(__dmul_rn((double)num, sm->inv_tot[k - 1]));
+					int32_t r = (int32_t)(num - m * t);               // the approximate quotient is off by at most one: verify exactly
+					if(r < 0) { m--; r += (int32_t)t; }
+					else if((uint32_t)r >= t) { m++; r -= (int32_t)t; }
+					if(r != 0)
+						out = bs->milli[m];
+					else
+						exact_path = true;
 				}
-				else {
+				if(exact_path) {
 					double x = (c1? __ddiv_rn((double)c1, (double)(int)t) : 0.0);
 					if(c2)
 						x = __dadd_rn(x, __ddiv_rn((double)c2, (double)(int)t));
-					out = x;
+					out = (KIND == ABW_FEAT_TRUNC3)? __ddiv_rn((double)__double2int_rz(__dmul_rn(1000.0, x)), 1000.0) : x;
 				}
 			}
 			if(!(skip_A && d == 0))
@@ -474,8 +491,10 @@ __global__ void k_cov_emit(const abw_read* __restrict__ reads, uint64_t nreads, 
 	uint64_t s = rd.pos0, e = (uint64_t)rd.pos0 + rd.len - 1, o = offs[r];
 	uint64_t f1 = seg_first[rd.scaf + 1];
 	for(uint64_t g = first_window_reaching(seg_end, seg_first[rd.scaf], f1, s); g < f1 && !(e < seg_start[g]); g++) {
+		const uint64_t st = seg_start[g], en = seg_end[g];
+		const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // 0-based read against 1-based window: quirk Q3, kept (:182-183)
 		keys[o] = (uint32_t)g;
-		vals[o] = (uint32_t)r;
+		vals[o] = (uint32_t)(e2 - s2 + 1);                             // the overlap travels with the pair: no gather after the sort
 		o++;
 		atomicAdd(&per_seg[g], 1u);
 	}
@@ -483,20 +502,23 @@ __global__ void k_cov_emit(const abw_read* __restrict__ reads, uint64_t nreads, 
 
 // one thread per window: the reads that hit it, in SAM order (the pairs were sorted stably by window)
 template <int KIND>
-__global__ void k_cov_accumulate(const abw_read* __restrict__ reads, const uint32_t* __restrict__ vals, const uint64_t* __restrict__ seg_off, uint64_t nseg,
+__global__ void k_cov_accumulate(const uint32_t* __restrict__ vals, const uint64_t* __restrict__ seg_off, uint64_t nseg,
                                  const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end, double* __restrict__ rows, uint64_t ld, uint32_t col)
 {
 	uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(g >= nseg)
 		return;
-	const uint64_t st = seg_start[g], en = seg_end[g];
-	const double seglen = (double)(en - st + 1);
-	double acc = 0.0;
-	for(uint64_t i = seg_off[g]; i < seg_off[g + 1]; i++) {
-		abw_read rd = reads[vals[i]];
-		uint64_t s = rd.pos0, e = (uint64_t)rd.pos0 + rd.len - 1;
-		uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // 0-based read against 1-based window: quirk Q3, kept
-		acc = __dadd_rn(acc, __ddiv_rn((double)(e2 - s2 + 1), seglen));
+	const double seglen = (double)(seg_end[g] - seg_start[g] + 1);
+	double acc = 0.0, q = 0.0;
+	uint32_t last = 0xFFFFFFFFu;
+	const uint64_t i1 = seg_off[g + 1];
+	for(uint64_t i = seg_off[g]; i < i1; i++) {
+		const uint32_t ov = __ldg(vals + i);
+		if(ov != last) {                                   // most reads lie entirely inside the window: same quotient, computed once
+			q = __ddiv_rn((double)ov, seglen);             // :184
+			last = ov;
+		}
+		acc = __dadd_rn(acc, q);                           // strictly in SAM order (quirk Q5)
 	}
 	if(KIND == ABW_FEAT_TRUNC3)
 		acc = __ddiv_rn((double)__double2int_rz(__dmul_rn(1000.0, acc)), 1000.0);
@@ -535,10 +557,11 @@ int upload_tables(abw_ctx* ctx)
 	double milli[1001];
 	for(int m = 0; m <= 1000; m++)
 		milli[m] = (double)m / 1000.0;
-	ABW_CUDA(ctx, cudaMemcpyToSymbol(c_dim_k, dk, sizeof(dk)));
-	ABW_CUDA(ctx, cudaMemcpyToSymbol(c_dim_code_a, da, sizeof(da)));
-	ABW_CUDA(ctx, cudaMemcpyToSymbol(c_dim_code_b, db, sizeof(db)));
-	ABW_CUDA(ctx, cudaMemcpyToSymbol(c_milli, milli, sizeof(milli)));
+	uint32_t tab[ABW_NKMER_DIMS];
+	for(int i = 0; i < ABW_NKMER_DIMS; i++)
+		tab[i] = (uint32_t)dk[i] | ((uint32_t)da[i] << 8) | ((uint32_t)db[i] << 16);
+	ABW_CUDA(ctx, cudaMemcpyToSymbol(g_dim_tab, tab, sizeof(tab)));
+	ABW_CUDA(ctx, cudaMemcpyToSymbol(g_milli, milli, sizeof(milli)));
 	if(ctx->device >= 0 && ctx->device < 64)
 		g_tables_ready[ctx->device] = true;
 	return ABW_OK;
@@ -709,7 +732,7 @@ int abw_kmer_features(abw_ctx* ctx, const abw_seqset* s, const abw_segments* g, 
 	ABW_CHECK(upload_tables(ctx));
 	if(g->nseg == 0)
 		return ABW_OK;
-	const size_t smem = sizeof(KmWarpSmem) * KM_WARPS;
+	const size_t smem = sizeof(KmBlockSmem) + sizeof(KmWarpSmem) * KM_WARPS;
 	unsigned int blocks = (unsigned int)std::min<uint64_t>(abw_div_up(g->nseg, KM_WARPS), (uint64_t)ctx->sm_count * 2 * 4);
 	if(kind == ABW_FEAT_TRUNC3) {
 		ABW_CUDA(ctx, cudaFuncSetAttribute(k_kmer<ABW_FEAT_TRUNC3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -765,14 +788,14 @@ int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uin
 		int nbits = 1;
 		while(nbits < 32 && (1ull << nbits) < g->nseg)
 			nbits++;
-		ABW_CHECK(abw_radix_sort_pairs_u32(ctx, keys.p, keys_tmp.p, vals.p, vals_tmp.p, npairs, nbits));
+		ABW_CHECK(abw_radix_sort_pairs_u32(ctx, keys.p, keys_tmp.p, vals.p, vals_tmp.p, npairs, 1, npairs, nbits));
 	}
 	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, per_seg.p, seg_off.p, g->nseg, seg_off.p + g->nseg));
 	if(g->nseg) {
 		if(kind == ABW_FEAT_TRUNC3)
-			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_TRUNC3>, abw_div_up(g->nseg, 128), 128, 0, rd, vals.p, seg_off.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col);
+			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_TRUNC3>, abw_div_up(g->nseg, 64), 64, 0, vals.p, seg_off.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col);
 		else
-			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_RAW>, abw_div_up(g->nseg, 128), 128, 0, rd, vals.p, seg_off.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col);
+			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_RAW>, abw_div_up(g->nseg, 64), 64, 0, vals.p, seg_off.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col);
 	}
 	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return ABW_OK;

@@ -148,50 +148,61 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_or_and(const K* __restrict__ 
 	}
 }
 
-// per-block digit histogram, layout hist[((array * 256) + digit) * nblocks + block]
-template <typename K>
+// per-block digit histogram, layout hist[((array * NB) + digit) * nblocks + block], NB = 2^BITS digits
+template <typename K, int BITS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K* __restrict__ keys, uint64_t n, uint64_t stride, int shift, uint32_t* __restrict__ hist)
 {
-	__shared__ uint32_t sh[256];
+	constexpr int NB = 1 << BITS;
+	__shared__ uint32_t sh[NB];
 	const K* a = keys + (uint64_t)blockIdx.y * stride;
-	sh[threadIdx.x] = 0;
+	for(int d = threadIdx.x; d < NB; d += RS_THREADS)
+		sh[d] = 0;
 	__syncthreads();
 	uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
 #pragma unroll
 	for(int r = 0; r < RS_ITEMS; r++) {
 		uint64_t i = base + (uint64_t)r * RS_THREADS + threadIdx.x;
 		if(i < n)
-			atomicAdd(&sh[(uint32_t)(a[i] >> shift) & 0xFFu], 1u);
+			atomicAdd(&sh[(uint32_t)(a[i] >> shift) & (uint32_t)(NB - 1)], 1u);
 	}
 	__syncthreads();
-	hist[((uint64_t)blockIdx.y * 256 + threadIdx.x) * gridDim.x + blockIdx.x] = sh[threadIdx.x];
+	for(int d = threadIdx.x; d < NB; d += RS_THREADS)
+		hist[((uint64_t)blockIdx.y * NB + d) * gridDim.x + blockIdx.x] = sh[d];
 }
 
-template <typename K>
+template <typename K, int BITS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, K* __restrict__ keys_out,
                                                           uint32_t* __restrict__ vals_out, uint64_t n, uint64_t stride, int shift, const uint64_t* __restrict__ offsets)
 {
-	__shared__ uint32_t cnt[RS_WARPS][257];
+	constexpr int NB = 1 << BITS;
+	__shared__ uint32_t cnt[RS_WARPS][NB + 1];
+	__shared__ uint64_t digit_base[NB];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint64_t arr = blockIdx.y;
 	const K* ki = keys_in + arr * stride;
 	const uint32_t* vi = vals_in + arr * stride;
 	K* ko = keys_out + arr * stride;
 	uint32_t* vo = vals_out + arr * stride;
-	for(int d = lane; d < 257; d += 32)
+	for(int d = lane; d < NB + 1; d += 32)
 		cnt[warp][d] = 0;
 	__syncwarp();
 	K key[RS_ITEMS];
+	uint32_t val[RS_ITEMS];
 	uint32_t lrank[RS_ITEMS];
 	const uint64_t wbase = (uint64_t)blockIdx.x * RS_TILE + (uint64_t)warp * RS_WARP_TILE;
 	const uint32_t lt = (1u << lane) - 1u;
-	// phase A: stable rank of every key among the keys of its warp with the same digit
 #pragma unroll
 	for(int r = 0; r < RS_ITEMS; r++) {
 		uint64_t i = wbase + (uint64_t)r * 32 + lane;
 		bool ok = i < n;
 		key[r] = ok? ki[i] : (K)0;
-		uint32_t d = ok? ((uint32_t)(key[r] >> shift) & 0xFFu) : 256u;
+		val[r] = ok? vi[i] : 0u;
+	}
+	// phase A: stable rank of every key among the keys of its warp with the same digit
+#pragma unroll
+	for(int r = 0; r < RS_ITEMS; r++) {
+		uint64_t i = wbase + (uint64_t)r * 32 + lane;
+		uint32_t d = (i < n)? ((uint32_t)(key[r] >> shift) & (uint32_t)(NB - 1)) : (uint32_t)NB;
 		uint32_t peers = __match_any_sync(0xffffffffu, d);
 		int leader = __ffs(peers) - 1;
 		uint32_t old = 0;
@@ -204,11 +215,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K* __restrict__
 		__syncwarp();
 	}
 	__syncthreads();
-	// phase B: thread t owns digit t: destination base of every (warp, digit)
-	{
-		int d = threadIdx.x;
-		uint64_t run = offsets[(arr * 256 + d) * gridDim.x + blockIdx.x] - arr * n;
-		// destinations of one block span < 2^32 only relative to the block base, so keep the low bits relative to `run`
+	// phase B: every digit gets the destination base of each (warp, digit)
+	for(int d = threadIdx.x; d < NB; d += RS_THREADS) {
+		digit_base[d] = offsets[(arr * NB + d) * gridDim.x + blockIdx.x] - arr * n;
 		uint32_t acc = 0;
 #pragma unroll
 		for(int w = 0; w < RS_WARPS; w++) {
@@ -216,22 +225,31 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K* __restrict__
 			cnt[w][d] = acc;
 			acc += c;
 		}
-		// stash the 64-bit base of the digit in shared memory through two words
-		__shared__ uint64_t digit_base[256];
-		digit_base[d] = run;
-		__syncthreads();
-		// phase C
+	}
+	__syncthreads();
+	// phase C
 #pragma unroll
-		for(int r = 0; r < RS_ITEMS; r++) {
-			uint64_t i = wbase + (uint64_t)r * 32 + lane;
-			if(i < n) {
-				uint32_t dg = (uint32_t)(key[r] >> shift) & 0xFFu;
-				uint64_t dst = digit_base[dg] + cnt[warp][dg] + lrank[r];
-				ko[dst] = key[r];
-				vo[dst] = vi[i];
-			}
+	for(int r = 0; r < RS_ITEMS; r++) {
+		uint64_t i = wbase + (uint64_t)r * 32 + lane;
+		if(i < n) {
+			uint32_t dg = (uint32_t)(key[r] >> shift) & (uint32_t)(NB - 1);
+			uint64_t dst = digit_base[dg] + cnt[warp][dg] + lrank[r];
+			ko[dst] = key[r];
+			vo[dst] = val[r];
 		}
 	}
+}
+
+template <typename K, int BITS>
+int radix_pass(abw_ctx* ctx, const K* src_k, const uint32_t* src_v, K* dst_k, uint32_t* dst_v, uint64_t n, uint32_t batch, uint64_t stride, int shift,
+               unsigned int nblocks, uint32_t* hist, uint64_t* offs)
+{
+	dim3 grid(nblocks, batch);
+	const uint64_t nh = (uint64_t)batch * (1u << BITS) * nblocks;
+	ABW_LAUNCH(ctx, (k_rs_hist<K, BITS>), grid, RS_THREADS, 0, src_k, n, stride, shift, hist);
+	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, hist, offs, nh, nullptr));
+	ABW_LAUNCH(ctx, (k_rs_scatter<K, BITS>), grid, RS_THREADS, 0, src_k, src_v, dst_k, dst_v, n, stride, shift, offs);
+	return ABW_OK;
 }
 
 template <typename K>
@@ -252,21 +270,45 @@ int radix_sort_impl(abw_ctx* ctx, K* d_keys, K* d_keys_tmp, uint32_t* d_vals, ui
 	ABW_CUDA(ctx, cudaMemcpyAsync(oa, or_and.p, sizeof(oa), cudaMemcpyDeviceToHost, ctx->stream));
 	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	unsigned long long varying = oa[0] ^ oa[1];
-
+	if(nbits < 64)
+		varying &= (1ull << nbits) - 1ull;
+	// plan: cover every varying bit with as few 8- or 9-bit digits as possible (bits that are equal in all keys are skipped)
+	struct Pass { int shift, bits; };
+	Pass plan[16];
+	int npass = 0;
+	{
+		int total9 = 0, total8 = 0;
+		for(int width = 9; width >= 8; width--) {
+			int cnt = 0, bit = 0;
+			while(bit < 64) {
+				if(!((varying >> bit) & 1ull)) { bit++; continue; }
+				cnt++;
+				bit += width;
+			}
+			if(width == 9) total9 = cnt; else total8 = cnt;
+		}
+		const int width = (total9 < total8)? 9 : 8;
+		int bit = 0;
+		while(bit < 64) {
+			if(!((varying >> bit) & 1ull)) { bit++; continue; }
+			plan[npass].shift = bit;
+			plan[npass].bits = width;
+			npass++;
+			bit += width;
+		}
+	}
 	DevBuf<uint32_t> hist;
 	DevBuf<uint64_t> offs;
-	uint64_t nh = (uint64_t)batch * 256 * nblocks;
+	uint64_t nh = (uint64_t)batch * 512 * nblocks;
 	ABW_CUDA(ctx, hist.alloc(nh));
 	ABW_CUDA(ctx, offs.alloc(nh));
 	K* src_k = d_keys; K* dst_k = d_keys_tmp;
 	uint32_t* src_v = d_vals; uint32_t* dst_v = d_vals_tmp;
-	dim3 grid(nblocks, batch);
-	for(int shift = 0; shift < nbits; shift += 8) {
-		if(((varying >> shift) & 0xFFull) == 0)
-			continue;                               // every key has the same digit here: the pass is the identity
-		ABW_LAUNCH(ctx, k_rs_hist<K>, grid, RS_THREADS, 0, src_k, n, stride, shift, hist.p);
-		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, hist.p, offs.p, nh, nullptr));
-		ABW_LAUNCH(ctx, k_rs_scatter<K>, grid, RS_THREADS, 0, src_k, src_v, dst_k, dst_v, n, stride, shift, offs.p);
+	for(int ps = 0; ps < npass; ps++) {
+		if(plan[ps].bits == 9)
+			ABW_CHECK((radix_pass<K, 9>(ctx, src_k, src_v, dst_k, dst_v, n, batch, stride, plan[ps].shift, nblocks, hist.p, offs.p)));
+		else
+			ABW_CHECK((radix_pass<K, 8>(ctx, src_k, src_v, dst_k, dst_v, n, batch, stride, plan[ps].shift, nblocks, hist.p, offs.p)));
 		K* tk = src_k; src_k = dst_k; dst_k = tk;
 		uint32_t* tv = src_v; src_v = dst_v; dst_v = tv;
 	}
@@ -296,7 +338,8 @@ int abw_radix_sort_pairs_u64(abw_ctx* ctx, uint64_t* d_keys, uint64_t* d_keys_tm
 	return radix_sort_impl<uint64_t>(ctx, d_keys, d_keys_tmp, d_vals, d_vals_tmp, n, batch, stride, nbits);
 }
 
-int abw_radix_sort_pairs_u32(abw_ctx* ctx, uint32_t* d_keys, uint32_t* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, int nbits)
+int abw_radix_sort_pairs_u32(abw_ctx* ctx, uint32_t* d_keys, uint32_t* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, uint32_t batch,
+                             uint64_t stride, int nbits)
 {
-	return radix_sort_impl<uint32_t>(ctx, d_keys, d_keys_tmp, d_vals, d_vals_tmp, n, 1, n, nbits);
+	return radix_sort_impl<uint32_t>(ctx, d_keys, d_keys_tmp, d_vals, d_vals_tmp, n, batch, stride, nbits);
 }

@@ -22,7 +22,7 @@
 namespace {
 
 constexpr int      SW_THREADS = 256;
-constexpr int      SW_ITEMS = 8;
+constexpr int      SW_ITEMS = 32;     // consecutive elements per thread: one 128-byte line, four 16-byte loads in flight
 constexpr int      SW_TILE = SW_THREADS * SW_ITEMS;
 constexpr uint32_t EL_SCAF_BITS = 27;
 constexpr uint32_t EL_SCAF_MASK = (1u << EL_SCAF_BITS) - 1u;
@@ -44,7 +44,7 @@ struct ClusterDesc {
 	uint32_t U;          // number of scaffolds
 	uint64_t totLen;     // sum of sequence lengths
 	uint32_t ss_ok;      // split-scafs: every scaffold starts "in" cluster 2 (ClusterSeparatorSplitScafs.cpp:102-106)
-	uint32_t pad;
+	uint32_t tile0;      // first entry of the cluster in the level's tile table
 };
 
 struct CandRec {
@@ -130,173 +130,296 @@ struct SweepParams {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// the threshold sweep: one CTA per (live cluster, dimension), tiles of SW_TILE elements in order
+// the threshold sweep: one CTA per tile of SW_TILE consecutive elements of a (cluster, dimension) segment.
+// Work items are (cluster, dimension, tile), tile fastest, handed out through an atomic ticket so that an item only
+// ever waits for items taken earlier (forward progress).  The running sums across the tiles of a segment come from a
+// decoupled look-back: every tile publishes its aggregate, then walks back until it meets a published inclusive prefix.
 // ---------------------------------------------------------------------------------------------------
+struct __align__(16) AggSlot { Agg v; unsigned long long pad; };   // 32 bytes
+
+constexpr uint32_t LB_EMPTY = 0, LB_AGG = 1, LB_PREFIX = 2;
+constexpr uint32_t LB_SPIN_LIMIT = 1u << 28;      // a bug must not hang the GPU: give up, flag the error, produce garbage that the host rejects
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+__device__ __forceinline__ Agg ld_cg_agg(const AggSlot* p)
+{
+	const uint4* q = reinterpret_cast<const uint4*>(p);
+	uint4 x = __ldcg(q), y = __ldcg(q + 1);
+	Agg r; r.a = x.x; r.b = x.y; r.c = x.z; r.d = x.w; r.e = (unsigned long long)y.x | ((unsigned long long)y.y << 32);
+	return r;
+}
+__device__ __forceinline__ void st_cg_agg(AggSlot* p, const Agg& v)
+{
+	uint4* q = reinterpret_cast<uint4*>(p);
+	__stcg(q, make_uint4(v.a, v.b, v.c, v.d));
+	__stcg(q + 1, make_uint4((uint32_t)v.e, (uint32_t)(v.e >> 32), 0u, 0u));
+}
+
+// per-element contribution to the running sums (see the table in DESIGN.md section 3)
 template <int STRATEGY>
-__global__ void __launch_bounds__(SW_THREADS) k_sweep(const uint32_t* __restrict__ E, uint64_t N, const ClusterDesc* __restrict__ clusters, const ScafRow* __restrict__ rows,
-                                                     const uint8_t* __restrict__ pass_tab, uint64_t tab_stride, SweepParams prm, CandRec* __restrict__ out)
+__device__ __forceinline__ Agg contribution(uint32_t el, bool in_range, const ScafRow* __restrict__ rows, double fraction_in)
+{
+	const uint32_t cls = (el >> EL_CLASS_SHIFT) & 3u, aux = (el >> EL_AUX_SHIFT) & 3u;
+	Agg x = agg_zero();
+	if(STRATEGY == ABW_SENS_SPEC) {
+		// a: TP1 (dps of side 1 whose scaffold is assigned to side 1), b: total_dps_for_assigned_scafs of side 1,
+		// c: dps in the cluster of the scaffolds assigned to side 1, d: SCG-carrying scaffolds flipped, e: their length
+		if(cls == 2u)
+			x.a = 1;
+		else if(cls == 1u) {
+			const uint4 r = __ldg(reinterpret_cast<const uint4*>(rows + (el & EL_SCAF_MASK)));   // {T, n, len}
+			x.a = r.x / 2 + 1;          // the flip element brings itself and the floor(T/2) earlier dps of the scaffold (...Specificity.cpp:41-57)
+			x.b = r.x;
+			x.c = r.y;
+			x.d = aux & 1u;
+			x.e = (unsigned long long)r.z | ((unsigned long long)r.w << 32);
+		}
+	}
+	else {
+		// a: ndps_in_scafs_that_belong of side 1, b: scafs_in of side 1, c: decrease of ndps_in_scafs_that_belong of side 2, d: decrease of scafs_in of side 2
+		if(cls == 2u)
+			x.a = 1;
+		if(aux == 0u && in_range)
+			x.c = 1;
+		if(cls == 1u || aux == 1u) {
+			const uint4 r = __ldg(reinterpret_cast<const uint4*>(rows + (el & EL_SCAF_MASK)));
+			const uint32_t r1 = (uint32_t)ceil(__dmul_rn(fraction_in, (double)r.x));
+			if(cls == 1u) { x.a = r1; x.b = 1; }
+			if(aux == 1u) { x.c = r1; x.d = 1; }
+		}
+	}
+	return x;
+}
+
+template <int STRATEGY>
+__global__ void __launch_bounds__(SW_THREADS, 3) k_sweep(const uint32_t* __restrict__ E, uint64_t N, const ClusterDesc* __restrict__ clusters, uint32_t TT,
+                                                        const uint2* __restrict__ tile_tab, const ScafRow* __restrict__ rows, const uint8_t* __restrict__ pass_tab,
+                                                     uint64_t tab_stride, SweepParams prm, unsigned long long* __restrict__ ticket, uint32_t* __restrict__ status,
+                                                     AggSlot* __restrict__ aggs, AggSlot* __restrict__ prefixes, CandRec* __restrict__ out, int* __restrict__ error_flag)
 {
 	__shared__ Agg sm_agg[SW_THREADS / 32 + 1];
 	__shared__ CandRec sm_best[SW_THREADS / 32];
-	const uint32_t c = blockIdx.x, d = blockIdx.y, D = gridDim.y;
+	__shared__ unsigned long long sm_w;
+	__shared__ Agg sm_carry;
+	// work items are (dimension, tile-table entry), entry fastest: the tiles of a (cluster, dimension) segment are consecutive items
+	if(threadIdx.x == 0)
+		sm_w = atomicAdd(ticket, 1ull);
+	__syncthreads();
+	const uint64_t w = sm_w;
+	const uint32_t d = (uint32_t)(w / TT);
+	const uint2 te = __ldg(tile_tab + (uint32_t)(w - (uint64_t)d * TT));
+	const uint32_t c = te.x, tile = te.y;
 	const ClusterDesc cl = clusters[c];
 	const uint32_t* __restrict__ seg = E + (uint64_t)d * N + cl.off;
 	const uint8_t* __restrict__ tab = (STRATEGY == ABW_SENS_SPEC)? pass_tab + (uint64_t)d * tab_stride + cl.tabOff : nullptr;
 	const uint32_t n = cl.n;
 	CandRec best;
 	best.found = 0; best.k1 = 0; best.k2 = 0; best.p = 0; best.i0 = best.i1 = best.i2 = 0; best.dim0 = d;
-	Agg carry = agg_zero();
-	if(STRATEGY == ABW_SPLIT_SCAFS && !cl.ss_ok) {
+	if(STRATEGY == ABW_SPLIT_SCAFS && !cl.ss_ok) {        // uniform over the tiles of the cluster: nobody waits for these items
 		if(threadIdx.x == 0)
-			out[(uint64_t)c * D + d] = best;
+			out[w] = best;
 		return;
 	}
-	for(uint32_t t0 = 0; t0 < n; t0 += SW_TILE) {
-		const uint32_t i0 = t0 + threadIdx.x * SW_ITEMS;
-		uint32_t el[SW_ITEMS];
-		if(i0 + SW_ITEMS <= n && ((reinterpret_cast<uintptr_t>(seg + i0) & 15) == 0)) {
-			const uint4* p4 = reinterpret_cast<const uint4*>(seg + i0);
-			uint4 x = __ldg(p4), y = __ldg(p4 + 1);
-			el[0] = x.x; el[1] = x.y; el[2] = x.z; el[3] = x.w; el[4] = y.x; el[5] = y.y; el[6] = y.z; el[7] = y.w;
+	const uint32_t t0 = tile * SW_TILE;
+	const uint32_t i0 = t0 + threadIdx.x * SW_ITEMS;
+	uint32_t el[SW_ITEMS];
+	if(i0 + SW_ITEMS <= n && ((reinterpret_cast<uintptr_t>(seg + i0) & 15) == 0)) {
+		const uint4* p4 = reinterpret_cast<const uint4*>(seg + i0);
+#pragma unroll
+		for(int q = 0; q < SW_ITEMS / 4; q++) {
+			const uint4 x = __ldg(p4 + q);
+			el[4 * q] = x.x; el[4 * q + 1] = x.y; el[4 * q + 2] = x.z; el[4 * q + 3] = x.w;
+		}
+	}
+	else {
+#pragma unroll
+		for(int j = 0; j < SW_ITEMS; j++)
+			el[j] = (i0 + j < n)? __ldg(seg + i0 + j) : 0u;   // class 0, no boundary: contributes nothing
+	}
+	// per-element contributions (recomputed in the candidate pass instead of being kept in registers)
+	Agg tsum = agg_zero();
+#pragma unroll
+	for(int j = 0; j < SW_ITEMS; j++)
+		tsum = agg_add(tsum, contribution<STRATEGY>(el[j], i0 + j < n, rows, prm.fraction_in));
+	Agg total;
+	Agg ex = block_excl_scan_agg(tsum, total, sm_agg);
+	// decoupled look-back over the earlier tiles of this (cluster, dimension): warp 0 probes 32 predecessors at a time
+	if(threadIdx.x < 32) {
+		const int ln = threadIdx.x;
+		Agg carry = agg_zero();
+		if(tile == 0) {
+			if(ln == 0) {
+				st_cg_agg(&prefixes[w], total);
+				__threadfence();
+				st_volatile_u32(&status[w], LB_PREFIX);
+			}
 		}
 		else {
+			if(ln == 0) {
+				st_cg_agg(&aggs[w], total);
+				__threadfence();
+				st_volatile_u32(&status[w], LB_AGG);
+			}
+			uint64_t base = w - 1;              // nearest predecessor; lane l looks at base - l
+			uint32_t remaining = tile;          // predecessors left in this segment (tile 0 always ends the walk with a prefix)
+			bool done = false, failed = false;
+			while(!done && !failed) {
+				const uint32_t cnt = min(32u, remaining);
+				uint32_t st, first_prefix, spins = 0;
+				while(true) {
+					st = ((uint32_t)ln < cnt)? ld_volatile_u32(&status[base - ln]) : LB_AGG;
+					const uint32_t pm = __ballot_sync(0xffffffffu, (uint32_t)ln < cnt && st == LB_PREFIX);
+					const uint32_t em = __ballot_sync(0xffffffffu, (uint32_t)ln < cnt && st == LB_EMPTY);
+					first_prefix = pm? (uint32_t)(__ffs(pm) - 1) : 32u;
+					const uint32_t need = (first_prefix >= 32u)? 0xFFFFFFFFu : ((2u << first_prefix) - 1u);
+					if((em & need) == 0)
+						break;
+					if(++spins >= LB_SPIN_LIMIT) {
+						failed = true;
+						break;
+					}
+				}
+				if(failed)
+					break;
+				__threadfence();
+				Agg v = agg_zero();
+				if((uint32_t)ln < cnt) {
+					if((uint32_t)ln < first_prefix)
+						v = ld_cg_agg(&aggs[base - ln]);
+					else if((uint32_t)ln == first_prefix)
+						v = ld_cg_agg(&prefixes[base - ln]);
+				}
 #pragma unroll
-			for(int j = 0; j < SW_ITEMS; j++)
-				el[j] = (i0 + j < n)? __ldg(seg + i0 + j) : 0u;   // class 0, no boundary: contributes nothing
+				for(int o = 16; o > 0; o >>= 1) {
+					Agg t2;
+					t2.a = __shfl_xor_sync(0xffffffffu, v.a, o); t2.b = __shfl_xor_sync(0xffffffffu, v.b, o);
+					t2.c = __shfl_xor_sync(0xffffffffu, v.c, o); t2.d = __shfl_xor_sync(0xffffffffu, v.d, o);
+					t2.e = __shfl_xor_sync(0xffffffffu, v.e, o);
+					v = agg_add(v, t2);
+				}
+				carry = agg_add(carry, v);
+				if(first_prefix < 32u)
+					done = true;
+				else {
+					base -= 32;
+					remaining -= 32;
+				}
+			}
+			if(failed && ln == 0)
+				atomicExch(error_flag, 1);
+			if(ln == 0) {
+				st_cg_agg(&prefixes[w], agg_add(carry, total));
+				__threadfence();
+				st_volatile_u32(&status[w], LB_PREFIX);
+			}
 		}
-		// per-element contributions
-		Agg w[SW_ITEMS];
-		Agg tsum = agg_zero();
+		if(ln == 0)
+			sm_carry = carry;
+	}
+	__syncthreads();
+	ex = agg_add(ex, sm_carry);
+	// candidates: a boundary before element i means "all dps with value <= value[i-1]" is a threshold with p = i
 #pragma unroll
-		for(int j = 0; j < SW_ITEMS; j++) {
-			const uint32_t cls = (el[j] >> EL_CLASS_SHIFT) & 3u, aux = (el[j] >> EL_AUX_SHIFT) & 3u;
-			Agg x = agg_zero();
+	for(int j = 0; j < SW_ITEMS; j++) {
+		const uint32_t p = i0 + j;
+		if((el[j] & EL_BOUNDARY) && p < n && p >= prm.thr && n - p >= prm.thr) {
 			if(STRATEGY == ABW_SENS_SPEC) {
-				// a: TP1 (dps of side 1 whose scaffold is assigned to side 1), b: total_dps_for_assigned_scafs of side 1,
-				// c: dps in the cluster of the scaffolds assigned to side 1, d: SCG-carrying scaffolds flipped, e: their length
-				if(cls == 2u)
-					x.a = 1;
-				else if(cls == 1u) {
-					const ScafRow r = rows[el[j] & EL_SCAF_MASK];
-					x.a = r.T / 2 + 1;          // the flip element brings itself and the floor(T/2) earlier dps of the scaffold (...Specificity.cpp:41-57)
-					x.b = r.T;
-					x.c = r.n;
-					x.d = aux & 1u;
-					x.e = r.len;
-				}
-			}
-			else {
-				// a: ndps_in_scafs_that_belong of side 1, b: scafs_in of side 1, c: decrease of ndps_in_scafs_that_belong of side 2, d: decrease of scafs_in of side 2
-				if(cls == 2u)
-					x.a = 1;
-				if(aux == 0u && i0 + j < n)
-					x.c = 1;
-				if(cls == 1u || aux == 1u) {
-					const ScafRow r = rows[el[j] & EL_SCAF_MASK];
-					const uint32_t r1 = (uint32_t)ceil(__dmul_rn(prm.fraction_in, (double)r.T));
-					if(cls == 1u) { x.a = r1; x.b = 1; }
-					if(aux == 1u) { x.c = r1; x.d = 1; }
-				}
-			}
-			w[j] = x;
-			tsum = agg_add(tsum, x);
-		}
-		Agg total;
-		Agg ex = agg_add(carry, block_excl_scan_agg(tsum, total, sm_agg));
-		// candidates: a boundary before element i means "all dps with value <= value[i-1]" is a threshold with p = i
-#pragma unroll
-		for(int j = 0; j < SW_ITEMS; j++) {
-			const uint32_t p = i0 + j;
-			if((el[j] & EL_BOUNDARY) && p < n && p >= prm.thr && n - p >= prm.thr) {
-				if(STRATEGY == ABW_SENS_SPEC) {
-					// ...Specificity.cpp:146-161 with TP1/FP1/TP2/FP2 written as prefix sums
-					uint32_t TP, tot, u;
-					if(p < n - p) { TP = ex.a; tot = ex.b; u = p; }
-					else { TP = (n - p) - (ex.c - ex.a); tot = cl.totT - ex.b; u = n - p; }
-					if(tot != 0) {
-						const float fTP = (float)TP;
-						if(fTP >= prm.prune * (float)tot && fTP >= prm.prune * (float)u) {
-							const double sens = __ddiv_rn((double)(int)TP, (double)(int)tot), spec = __ddiv_rn((double)(int)TP, (double)(int)u);
-							const double score = __dmul_rn(sens, spec);
-							if(score >= prm.min_score && (!best.found || score > best.k1)) {
-								const uint8_t pt = tab[ex.d];
-								bool ok = (pt == 1);
-								if(pt == 2)
-									ok = (ex.e >= prm.scg_min_size) && (cl.totLen - ex.e >= prm.scg_min_size);
-								if(ok) {
-									best.found = 1; best.k1 = score; best.p = p; best.i0 = TP; best.i1 = tot; best.i2 = u;
-								}
+				// ...Specificity.cpp:146-161 with TP1/FP1/TP2/FP2 written as prefix sums
+				uint32_t TP, tot, u;
+				if(p < n - p) { TP = ex.a; tot = ex.b; u = p; }
+				else { TP = (n - p) - (ex.c - ex.a); tot = cl.totT - ex.b; u = n - p; }
+				if(tot != 0) {
+					const float fTP = (float)TP;
+					if(fTP >= prm.prune * (float)tot && fTP >= prm.prune * (float)u) {
+						const double sens = __ddiv_rn((double)(int)TP, (double)(int)tot), spec = __ddiv_rn((double)(int)TP, (double)(int)u);
+						const double score = __dmul_rn(sens, spec);
+						if(score >= prm.min_score && (!best.found || score > best.k1)) {
+							const uint8_t pt = tab[ex.d];
+							bool ok = (pt == 1);
+							if(pt == 2)
+								ok = (ex.e >= prm.scg_min_size) && (cl.totLen - ex.e >= prm.scg_min_size);
+							if(ok) {
+								best.found = 1; best.k1 = score; best.p = p; best.i0 = TP; best.i1 = tot; best.i2 = u;
 							}
 						}
 					}
 				}
-				else {
-					// ...SplitScafs.cpp:131-154
-					const uint32_t belong1 = ex.a, in1 = ex.b, belong2 = n - ex.c, in2 = cl.U - ex.d;
-					if(belong1 >= prm.thr && belong2 >= prm.thr) {
-						const uint32_t separated = cl.U - in1 - in2;
-						const uint32_t in_small = (p < n - p)? in1 : in2, in_large = (p < n - p)? in2 : in1;
-						const double ratio = __ddiv_rn((double)separated, (double)(int)in_small);
-						double csr = __ddiv_rn((double)(int)in_small, (double)(int)in_large);
-						if(csr < 1)
-							csr = __ddiv_rn(1.0, csr);
-						if(!best.found || ratio < best.k1 || (ratio == best.k1 && csr < best.k2)) {
-							best.found = 1; best.k1 = ratio; best.k2 = csr; best.p = p; best.i0 = separated; best.i1 = in_small; best.i2 = in_large;
-						}
+			}
+			else {
+				// ...SplitScafs.cpp:131-154
+				const uint32_t belong1 = ex.a, in1 = ex.b, belong2 = n - ex.c, in2 = cl.U - ex.d;
+				if(belong1 >= prm.thr && belong2 >= prm.thr) {
+					const uint32_t separated = cl.U - in1 - in2;
+					const uint32_t in_small = (p < n - p)? in1 : in2, in_large = (p < n - p)? in2 : in1;
+					const double ratio = __ddiv_rn((double)separated, (double)(int)in_small);
+					double csr = __ddiv_rn((double)(int)in_small, (double)(int)in_large);
+					if(csr < 1)
+						csr = __ddiv_rn(1.0, csr);
+					if(!best.found || ratio < best.k1 || (ratio == best.k1 && csr < best.k2)) {
+						best.found = 1; best.k1 = ratio; best.k2 = csr; best.p = p; best.i0 = separated; best.i1 = in_small; best.i2 = in_large;
 					}
 				}
 			}
-			ex = agg_add(ex, w[j]);
 		}
-		carry = agg_add(carry, total);
+		ex = agg_add(ex, contribution<STRATEGY>(el[j], i0 + j < n, rows, prm.fraction_in));
 	}
 	// block arg-best: (key, then lowest p); each thread already holds its lowest-p optimum
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if(__syncthreads_or(best.found)) {
 #pragma unroll
-	for(int o = 16; o > 0; o >>= 1) {
-		CandRec other;
-		other.k1 = __shfl_xor_sync(0xffffffffu, best.k1, o); other.k2 = __shfl_xor_sync(0xffffffffu, best.k2, o);
-		other.p = __shfl_xor_sync(0xffffffffu, best.p, o); other.i0 = __shfl_xor_sync(0xffffffffu, best.i0, o);
-		other.i1 = __shfl_xor_sync(0xffffffffu, best.i1, o); other.i2 = __shfl_xor_sync(0xffffffffu, best.i2, o);
-		other.found = __shfl_xor_sync(0xffffffffu, best.found, o); other.dim0 = d;
-		if(cand_better<STRATEGY>(other, best))
-			best = other;
+		for(int o = 16; o > 0; o >>= 1) {
+			CandRec other;
+			other.k1 = __shfl_xor_sync(0xffffffffu, best.k1, o); other.k2 = __shfl_xor_sync(0xffffffffu, best.k2, o);
+			other.p = __shfl_xor_sync(0xffffffffu, best.p, o); other.i0 = __shfl_xor_sync(0xffffffffu, best.i0, o);
+			other.i1 = __shfl_xor_sync(0xffffffffu, best.i1, o); other.i2 = __shfl_xor_sync(0xffffffffu, best.i2, o);
+			other.found = __shfl_xor_sync(0xffffffffu, best.found, o); other.dim0 = d;
+			if(cand_better<STRATEGY>(other, best))
+				best = other;
+		}
+		if(lane == 0)
+			sm_best[warp] = best;
+		__syncthreads();
+		if(threadIdx.x == 0) {
+			CandRec b = sm_best[0];
+			for(int w2 = 1; w2 < SW_THREADS / 32; w2++)
+				if(cand_better<STRATEGY>(sm_best[w2], b))
+					b = sm_best[w2];
+			out[w] = b;
+		}
 	}
-	if(lane == 0)
-		sm_best[warp] = best;
-	__syncthreads();
-	if(threadIdx.x == 0) {
-		CandRec b = sm_best[0];
-		for(int w2 = 1; w2 < SW_THREADS / 32; w2++)
-			if(cand_better<STRATEGY>(sm_best[w2], b))
-				b = sm_best[w2];
-		out[(uint64_t)c * D + d] = b;
-	}
+	else if(threadIdx.x == 0)
+		out[w] = best;
 }
 
-// best candidate of every cluster over its dimensions: ascending dimension, strict improvement only
-// (...Specificity.cpp:137-140 under the mutex; is_better is a total order so thread order never mattered)
+// best candidate of every cluster over its (dimension, tile) items: the reference's total order
+// (score, then lowest dimension, then lowest value; ...Specificity.cpp:137-140 under the mutex, ClusterSeparator.cpp:11-16)
 template <int STRATEGY>
-__global__ void k_reduce_best(const CandRec* __restrict__ per_dim, uint32_t D, CandRec* __restrict__ out)
+__global__ void __launch_bounds__(256) k_reduce_best(const CandRec* __restrict__ per_item, uint32_t TT, uint32_t D, const ClusterDesc* __restrict__ clusters,
+                                                    CandRec* __restrict__ out)
 {
-	__shared__ CandRec sm[32];
+	__shared__ CandRec sm[256];
 	const uint32_t c = blockIdx.x;
+	const uint32_t tiles = (clusters[c].n + SW_TILE - 1) / SW_TILE, tile0 = clusters[c].tile0;
 	CandRec best;
 	best.found = 0; best.k1 = best.k2 = 0; best.p = 0; best.i0 = best.i1 = best.i2 = 0; best.dim0 = 0;
-	for(uint32_t d = threadIdx.x; d < D; d += blockDim.x) {
-		CandRec x = per_dim[(uint64_t)c * D + d];
+	const uint64_t total = (uint64_t)D * tiles;
+	for(uint64_t i = threadIdx.x; i < total; i += blockDim.x) {
+		const uint32_t d = (uint32_t)(i / tiles), t = (uint32_t)(i - (uint64_t)d * tiles);
+		CandRec x = per_item[(uint64_t)d * TT + tile0 + t];
 		x.dim0 = d;
 		if(cand_better<STRATEGY>(x, best))
 			best = x;
 	}
 	sm[threadIdx.x] = best;
 	__syncthreads();
-	if(threadIdx.x == 0) {
-		for(uint32_t t = 1; t < blockDim.x; t++)
-			if(cand_better<STRATEGY>(sm[t], best))
-				best = sm[t];
-		out[c] = best;
+	for(uint32_t s2 = blockDim.x / 2; s2 > 0; s2 >>= 1) {
+		if(threadIdx.x < s2 && cand_better<STRATEGY>(sm[threadIdx.x + s2], sm[threadIdx.x]))
+			sm[threadIdx.x] = sm[threadIdx.x + s2];
+		__syncthreads();
 	}
+	if(threadIdx.x == 0)
+		out[c] = sm[0];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -501,125 +624,221 @@ __device__ __forceinline__ uint32_t map_compose(uint32_t first, uint32_t then)  
 }
 constexpr uint32_t MAP_IDENTITY = 0xE4u;   // 3,2,1,0
 
+// look-back word of a partition tile: [0,32) count of side-1 elements, [32,40) map (aggregate) or state after the tile (prefix), [62,64) status
+__device__ __forceinline__ unsigned long long lb_pack(uint32_t cnt, uint32_t m, uint32_t st) { return (unsigned long long)cnt | ((unsigned long long)m << 32) | ((unsigned long long)st << 62); }
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+
+// one CTA per tile; items are (job, dimension, tile), tile fastest, handed out by ticket (see k_sweep)
 __global__ void __launch_bounds__(SW_THREADS) k_partition(const uint32_t* __restrict__ Ein, uint32_t* __restrict__ Eout, uint64_t N, const PartJob* __restrict__ jobs,
-                                                         const uint8_t* __restrict__ side)
+                                                         uint32_t TT, const uint2* __restrict__ tile_tab, const uint8_t* __restrict__ side,
+                                                         unsigned long long* __restrict__ ticket, unsigned long long* __restrict__ lookback, int* __restrict__ error_flag)
 {
 	__shared__ uint32_t sm_cnt[SW_THREADS / 32 + 1];
 	__shared__ uint32_t sm_map[SW_THREADS / 32 + 1];
-	const PartJob jb = jobs[blockIdx.x];
-	const uint32_t d = blockIdx.y;
+	__shared__ unsigned long long sm_w;
+	__shared__ uint32_t sm_carry[2];
+	if(threadIdx.x == 0)
+		sm_w = atomicAdd(ticket, 1ull);
+	__syncthreads();
+	const uint64_t w = sm_w;
+	const uint32_t d = (uint32_t)(w / TT);
+	const uint2 te = __ldg(tile_tab + (uint32_t)(w - (uint64_t)d * TT));
+	const PartJob jb = jobs[te.x];
+	const uint32_t tile = te.y;
 	const uint32_t* __restrict__ src = Ein + (uint64_t)d * N + jb.off;
 	uint32_t* __restrict__ dst1 = Eout + (uint64_t)d * N + jb.off;
 	uint32_t* __restrict__ dst2 = dst1 + jb.n1;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t carry_cnt = 0, carry_state = 3u;          // the first element of each child gets its boundary flag set
-	for(uint32_t t0 = 0; t0 < jb.n; t0 += SW_TILE) {
-		const uint32_t i0 = t0 + threadIdx.x * SW_ITEMS;
-		uint32_t el[SW_ITEMS], sd[SW_ITEMS];
-		uint32_t cnt1 = 0, tmap = MAP_IDENTITY;
+	const uint32_t i0 = tile * SW_TILE + threadIdx.x * SW_ITEMS;
+	uint32_t el[SW_ITEMS];
+	uint32_t side1 = 0;                                   // bit j: element j goes to child 1
+	uint32_t cnt1 = 0, tmap = MAP_IDENTITY;
+	if(i0 + SW_ITEMS <= jb.n && ((reinterpret_cast<uintptr_t>(src + i0) & 15) == 0)) {
+		const uint4* p4 = reinterpret_cast<const uint4*>(src + i0);
 #pragma unroll
-		for(int j = 0; j < SW_ITEMS; j++) {
-			if(i0 + j < jb.n) {
-				el[j] = __ldg(src + i0 + j);
-				sd[j] = side[el[j] & EL_SCAF_MASK];
-				cnt1 += (sd[j] == 1u);
-				tmap = map_compose(tmap, map_of(sd[j], el[j] >> 31));
-			}
-			else {
-				el[j] = 0;
-				sd[j] = 0;
-			}
+		for(int q = 0; q < SW_ITEMS / 4; q++) {
+			const uint4 x = __ldg(p4 + q);
+			el[4 * q] = x.x; el[4 * q + 1] = x.y; el[4 * q + 2] = x.z; el[4 * q + 3] = x.w;
 		}
-		// inclusive warp scans
-		uint32_t icnt = cnt1, imap = tmap;
+	}
+	else {
 #pragma unroll
-		for(int o = 1; o < 32; o <<= 1) {
-			uint32_t c2 = __shfl_up_sync(0xffffffffu, icnt, o), m2 = __shfl_up_sync(0xffffffffu, imap, o);
-			if(lane >= o) {
-				icnt += c2;
-				imap = map_compose(m2, imap);
-			}
+		for(int j = 0; j < SW_ITEMS; j++)
+			el[j] = (i0 + j < jb.n)? __ldg(src + i0 + j) : 0u;
+	}
+#pragma unroll
+	for(int j = 0; j < SW_ITEMS; j++) {
+		if(i0 + j < jb.n) {
+			const uint32_t sdj = side[el[j] & EL_SCAF_MASK];
+			side1 |= (sdj == 1u)? (1u << j) : 0u;
+			cnt1 += (sdj == 1u);
+			tmap = map_compose(tmap, map_of(sdj, el[j] >> 31));
 		}
-		if(lane == 31) {
-			sm_cnt[warp] = icnt;
-			sm_map[warp] = imap;
+	}
+	// inclusive warp scans
+	uint32_t icnt = cnt1, imap = tmap;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) {
+		uint32_t c2 = __shfl_up_sync(0xffffffffu, icnt, o), m2 = __shfl_up_sync(0xffffffffu, imap, o);
+		if(lane >= o) {
+			icnt += c2;
+			imap = map_compose(m2, imap);
 		}
-		__syncthreads();
-		if(threadIdx.x == 0) {
-			uint32_t rc = 0, rm = MAP_IDENTITY;
-			for(int w = 0; w < SW_THREADS / 32; w++) {
-				uint32_t tc = sm_cnt[w], tm = sm_map[w];
-				sm_cnt[w] = rc;
-				sm_map[w] = rm;
-				rc += tc;
-				rm = map_compose(rm, tm);
-			}
-			sm_cnt[SW_THREADS / 32] = rc;
-			sm_map[SW_THREADS / 32] = rm;
-		}
-		__syncthreads();
-		// exclusive prefix for this thread
-		uint32_t ecnt = __shfl_up_sync(0xffffffffu, icnt, 1), emap = __shfl_up_sync(0xffffffffu, imap, 1);
+	}
+	if(lane == 31) {
+		sm_cnt[warp] = icnt;
+		sm_map[warp] = imap;
+	}
+	__syncthreads();
+	if(threadIdx.x < 32) {
+		uint32_t rc = 0, rm = MAP_IDENTITY;
 		if(lane == 0) {
-			ecnt = 0;
-			emap = MAP_IDENTITY;
+			for(int w2 = 0; w2 < SW_THREADS / 32; w2++) {
+				uint32_t tc = sm_cnt[w2], tm2 = sm_map[w2];
+				sm_cnt[w2] = rc;
+				sm_map[w2] = rm;
+				rc += tc;
+				rm = map_compose(rm, tm2);
+			}
 		}
-		uint32_t before1 = carry_cnt + sm_cnt[warp] + ecnt;
-		uint32_t state = map_apply(emap, map_apply(sm_map[warp], carry_state));
+		rc = __shfl_sync(0xffffffffu, rc, 0);
+		rm = __shfl_sync(0xffffffffu, rm, 0);
+		// look-back: count of side-1 elements and transducer state before this tile; warp 0 probes 32 predecessors at a time
+		uint32_t carry_cnt = 0, carry_state = 3u;      // the first element of each child gets its boundary flag set
+		if(tile > 0) {
+			if(lane == 0)
+				st_volatile_u64(&lookback[w], lb_pack(rc, rm, LB_AGG));
+			uint32_t acc_map = MAP_IDENTITY;            // composition of the maps of the tiles between the probe window and this tile
+			uint64_t base = w - 1;
+			uint32_t remaining = tile;
+			bool done = false, failed = false;
+			while(!done && !failed) {
+				const uint32_t cnt = min(32u, remaining);
+				unsigned long long v;
+				uint32_t first_prefix, spins = 0;
+				while(true) {
+					v = ((uint32_t)lane < cnt)? ld_volatile_u64(&lookback[base - lane]) : lb_pack(0, MAP_IDENTITY, LB_AGG);
+					const uint32_t st = (uint32_t)(v >> 62);
+					const uint32_t pm = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == LB_PREFIX);
+					const uint32_t em = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == LB_EMPTY);
+					first_prefix = pm? (uint32_t)(__ffs(pm) - 1) : 32u;
+					const uint32_t need = (first_prefix >= 32u)? 0xFFFFFFFFu : ((2u << first_prefix) - 1u);
+					if((em & need) == 0)
+						break;
+					if(++spins >= LB_SPIN_LIMIT) {
+						failed = true;
+						break;
+					}
+				}
+				if(failed)
+					break;
+				// counts add up; maps compose in tile order: farthest first
+				uint32_t c = ((uint32_t)lane <= first_prefix && (uint32_t)lane < cnt)? (uint32_t)v : 0u;
 #pragma unroll
-		for(int j = 0; j < SW_ITEMS; j++) {
-			const uint32_t i = i0 + j;
-			if(i < jb.n) {
-				const uint32_t c = el[j] >> 31;
-				uint32_t e = el[j] & 0x7FFFFFFFu;
-				if(sd[j] == 1u) {
-					e |= (c | (state & 1u)) << 31;
-					dst1[before1] = e;
-					before1++;
-					state = ((state >> 1) | c) << 1;               // pend1 = 0, pend2 |= c
+				for(int o = 16; o > 0; o >>= 1)
+					c += __shfl_xor_sync(0xffffffffu, c, o);
+				carry_cnt += c;
+				const uint32_t mine = (uint32_t)(v >> 32) & 0xFFu;
+				const int top = (int)min(first_prefix, cnt - 1);        // farthest lane that takes part
+				uint32_t window_map = MAP_IDENTITY, state_at_prefix = 0;
+				for(int l = top; l >= 0; l--) {
+					const uint32_t m = __shfl_sync(0xffffffffu, mine, l);
+					if((uint32_t)l == first_prefix)
+						state_at_prefix = m & 3u;
+					else
+						window_map = map_compose(window_map, m);
+				}
+				if(first_prefix < 32u) {
+					carry_state = map_apply(acc_map, map_apply(window_map, state_at_prefix));
+					done = true;
 				}
 				else {
-					e |= (c | (state >> 1)) << 31;
-					dst2[i - before1] = e;
-					state = (state & 1u) | c;                      // pend2 = 0, pend1 |= c
+					acc_map = map_compose(window_map, acc_map);
+					base -= 32;
+					remaining -= 32;
 				}
 			}
+			if(failed && lane == 0)
+				atomicExch(error_flag, 1);
 		}
-		const uint32_t tile_cnt = sm_cnt[SW_THREADS / 32], tile_map = sm_map[SW_THREADS / 32];
-		carry_cnt += tile_cnt;
-		carry_state = map_apply(tile_map, carry_state);
-		__syncthreads();
+		if(lane == 0) {
+			st_volatile_u64(&lookback[w], lb_pack(carry_cnt + rc, map_apply(rm, carry_state), LB_PREFIX));
+			sm_carry[0] = carry_cnt;
+			sm_carry[1] = carry_state;
+		}
+	}
+	__syncthreads();
+	// exclusive prefix for this thread
+	uint32_t ecnt = __shfl_up_sync(0xffffffffu, icnt, 1), emap = __shfl_up_sync(0xffffffffu, imap, 1);
+	if(lane == 0) {
+		ecnt = 0;
+		emap = MAP_IDENTITY;
+	}
+	uint32_t before1 = sm_carry[0] + sm_cnt[warp] + ecnt;
+	uint32_t state = map_apply(emap, map_apply(sm_map[warp], sm_carry[1]));
+#pragma unroll
+	for(int j = 0; j < SW_ITEMS; j++) {
+		const uint32_t i = i0 + j;
+		if(i < jb.n) {
+			const uint32_t c = el[j] >> 31;
+			uint32_t e = el[j] & 0x7FFFFFFFu;
+			if((side1 >> j) & 1u) {
+				e |= (c | (state & 1u)) << 31;
+				dst1[before1] = e;
+				before1++;
+				state = ((state >> 1) | c) << 1;               // pend1 = 0, pend2 |= c
+			}
+			else {
+				e |= (c | (state >> 1)) << 31;
+				dst2[i - before1] = e;
+				state = (state & 1u) | c;                      // pend2 = 0, pend1 |= c
+			}
+		}
 	}
 }
 
 // stable partition of small u32 lists of scaffold ids (scaffold list: 1 "dimension"; SCG lists: D dimensions); one warp per (job, dimension)
 struct ListJob { uint32_t off, n, n1; };
-__global__ void k_partition_list(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t stride, const ListJob* __restrict__ jobs, const uint8_t* __restrict__ side,
-                                 uint32_t ndims)
+__global__ void __launch_bounds__(256) k_partition_list(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t stride, const ListJob* __restrict__ jobs,
+                                                       const uint8_t* __restrict__ side)
 {
-	const int lane = threadIdx.x & 31;
-	const uint32_t d = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	if(d >= ndims)
-		return;
+	__shared__ uint32_t sm[9];
+	const uint32_t d = blockIdx.y;
 	const ListJob jb = jobs[blockIdx.x];
 	const uint32_t* __restrict__ src = in + (uint64_t)d * stride + jb.off;
 	uint32_t* __restrict__ dst1 = out + (uint64_t)d * stride + jb.off;
 	uint32_t* __restrict__ dst2 = dst1 + jb.n1;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	uint32_t c1 = 0;
-	for(uint32_t base = 0; base < jb.n; base += 32) {
-		const uint32_t i = base + lane;
-		uint32_t s = 0, sd = 0;
+	for(uint32_t base = 0; base < jb.n; base += blockDim.x) {
+		const uint32_t i = base + threadIdx.x;
+		uint32_t sc = 0, sd = 0;
 		if(i < jb.n) {
-			s = src[i];
-			sd = side[s];
+			sc = src[i];
+			sd = side[sc];
 		}
 		const uint32_t b1 = __ballot_sync(0xffffffffu, sd == 1u);
-		const uint32_t before = __popc(b1 & ((1u << lane) - 1u));
-		if(i < jb.n) {
-			if(sd == 1u) dst1[c1 + before] = s;
-			else dst2[i - (c1 + before)] = s;
+		if(lane == 0)
+			sm[warp] = __popc(b1);
+		__syncthreads();
+		if(threadIdx.x == 0) {
+			uint32_t run = 0;
+			for(int w2 = 0; w2 < 8; w2++) {
+				uint32_t t = sm[w2];
+				sm[w2] = run;
+				run += t;
+			}
+			sm[8] = run;
 		}
-		c1 += __popc(b1);
+		__syncthreads();
+		const uint32_t before = c1 + sm[warp] + __popc(b1 & ((1u << lane) - 1u));
+		if(i < jb.n) {
+			if(sd == 1u) dst1[before] = sc;
+			else dst2[i - before] = sc;
+		}
+		c1 += sm[8];
+		__syncthreads();
 	}
 }
 
@@ -714,6 +933,24 @@ __global__ void k_make_keys(const double* __restrict__ values, uint64_t N, uint3
 	}
 }
 
+// Columns written by abawaca-build hold multiples of 0.001 (int(1000*x)/1000.0, abawaca-build.cpp:603).  When every value v of the chunk
+// satisfies v == (double)k / 1000.0 for the integer k = rint(1000*v), |k| < 2^31, ordering by k is ordering by v (ties included) and the
+// sort runs on 32-bit keys with few significant bits.  Any other value sets `inexact` and the chunk falls back to the 64-bit keys.
+__global__ void k_make_keys_milli(const double* __restrict__ values, uint64_t N, uint32_t nd, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ inexact)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t d = blockIdx.y;
+	if(i < N && d < nd) {
+		const double v = values[(uint64_t)d * N + i];
+		const double k = rint(__dmul_rn(v, 1000.0));
+		bool ok = (k > -2147483000.0) && (k < 2147483000.0) && (__ddiv_rn(k, 1000.0) == v);
+		if(!ok)
+			atomicExch(inexact, 1);
+		keys[(uint64_t)d * N + i] = ok? (uint32_t)((long long)k + 2147483648ll) : 0u;
+		vals[(uint64_t)d * N + i] = (uint32_t)i;
+	}
+}
+
 // class of every datapoint in every dimension of the chunk, from its rank inside its scaffold (ties by datapoint index,
 // the order a stable sort produces).  Thread per (datapoint, dimension).
 __global__ void k_rank_class(const double* __restrict__ values, uint64_t N, uint32_t nd, const uint32_t* __restrict__ dp2scaf, const uint64_t* __restrict__ dp_first,
@@ -748,7 +985,8 @@ __global__ void k_rank_class(const double* __restrict__ values, uint64_t N, uint
 	cls_out[(uint64_t)d * N + i] = (uint8_t)(cls | (aux << 2));
 }
 
-__global__ void k_pack_elements(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t N, uint32_t nd, const uint32_t* __restrict__ dp2scaf,
+template <typename KeyT>
+__global__ void k_pack_elements(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t N, uint32_t nd, const uint32_t* __restrict__ dp2scaf,
                                 const uint8_t* __restrict__ cls, uint32_t* __restrict__ E, const uint32_t* __restrict__ scg_index, uint32_t* __restrict__ flip_pos, uint64_t K)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -946,7 +1184,8 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	DevBuf<unsigned long long> keys, keys_tmp;
 	DevBuf<uint32_t> vals, vals_tmp, flip_pos;
 	DevBuf<uint8_t> cls;
-	DevBuf<int> nan_flag;
+	DevBuf<int> nan_flag, inexact;
+	ABW_CUDA(ctx, inexact.alloc(1));
 	ABW_CUDA(ctx, keys.alloc((size_t)chunk * N));
 	ABW_CUDA(ctx, keys_tmp.alloc((size_t)chunk * N));
 	ABW_CUDA(ctx, vals.alloc((size_t)chunk * N));
@@ -959,11 +1198,24 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		const uint32_t nd = std::min(chunk, D - d0);
 		dim3 grid(abw_div_up(N, 256), nd);
 		const double* vchunk = s->values.p + (uint64_t)d0 * N;
-		ABW_LAUNCH(ctx, k_make_keys, grid, 256, 0, vchunk, N, nd, keys.p, vals.p, nan_flag.p);
 		ABW_LAUNCH(ctx, k_rank_class, grid, 256, 0, vchunk, N, nd, s->dp2scaf.p, s->dp_first.p, s->rows.p, s->has_scg.p, s->strategy, s->prm.fraction_dps_in, cls.p);
-		ABW_CHECK(abw_radix_sort_pairs_u64(ctx, (uint64_t*)keys.p, (uint64_t*)keys_tmp.p, vals.p, vals_tmp.p, N, nd, N, 64));
-		ABW_LAUNCH(ctx, k_pack_elements, grid, 256, 0, keys.p, vals.p, N, nd, s->dp2scaf.p, cls.p, s->E[0].p + (uint64_t)d0 * N, d_scg_index.p,
-		           (s->strategy == ABW_SENS_SPEC && K > 0)? flip_pos.p + (uint64_t)d0 * K : nullptr, K);
+		uint32_t* keys32 = reinterpret_cast<uint32_t*>(keys.p);
+		uint32_t* keys32_tmp = reinterpret_cast<uint32_t*>(keys_tmp.p);
+		ABW_CUDA(ctx, cudaMemsetAsync(inexact.p, 0, sizeof(int), ctx->stream));
+		ABW_LAUNCH(ctx, k_make_keys_milli, grid, 256, 0, vchunk, N, nd, keys32, vals.p, inexact.p);
+		int h_inexact = 0;
+		ABW_CUDA(ctx, cudaMemcpyAsync(&h_inexact, inexact.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		uint32_t* fp = (s->strategy == ABW_SENS_SPEC && K > 0)? flip_pos.p + (uint64_t)d0 * K : nullptr;
+		if(!h_inexact) {
+			ABW_CHECK(abw_radix_sort_pairs_u32(ctx, keys32, keys32_tmp, vals.p, vals_tmp.p, N, nd, N, 32));
+			ABW_LAUNCH(ctx, k_pack_elements<uint32_t>, grid, 256, 0, keys32, vals.p, N, nd, s->dp2scaf.p, cls.p, s->E[0].p + (uint64_t)d0 * N, d_scg_index.p, fp, K);
+		}
+		else {
+			ABW_LAUNCH(ctx, k_make_keys, grid, 256, 0, vchunk, N, nd, keys.p, vals.p, nan_flag.p);
+			ABW_CHECK(abw_radix_sort_pairs_u64(ctx, (uint64_t*)keys.p, (uint64_t*)keys_tmp.p, vals.p, vals_tmp.p, N, nd, N, 64));
+			ABW_LAUNCH(ctx, k_pack_elements<unsigned long long>, grid, 256, 0, keys.p, vals.p, N, nd, s->dp2scaf.p, cls.p, s->E[0].p + (uint64_t)d0 * N, d_scg_index.p, fp, K);
+		}
 	}
 	int h_nan = 0;
 	ABW_CUDA(ctx, cudaMemcpyAsync(&h_nan, nan_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1068,6 +1320,14 @@ int search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t ca
 
 	DevBuf<ClusterDesc> d_clusters;
 	DevBuf<CandRec> d_cand, d_best;
+	DevBuf<uint2> d_tile_tab, d_ptile_tab;
+	DevBuf<uint32_t> d_status;
+	DevBuf<AggSlot> d_aggs, d_prefixes;
+	DevBuf<unsigned long long> d_ticket, d_lookback;
+	DevBuf<int> d_error;
+	ABW_CUDA(ctx, d_ticket.alloc(1));
+	ABW_CUDA(ctx, d_error.alloc(1));
+	ABW_CUDA(ctx, cudaMemsetAsync(d_error.p, 0, sizeof(int), ctx->stream));
 	DevBuf<uint8_t> d_tab;
 	DevBuf<uint64_t> d_suffix, d_never, d_child_never, d_union;
 	DevBuf<SplitJob> d_jobs;
@@ -1100,10 +1360,25 @@ int search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t ca
 			for(uint32_t w = 0; w < W; w++)
 				never[(size_t)c * W + w] = level[c].never.empty()? 0 : level[c].never[w];
 		}
-		ABW_CHECK(to_device(ctx, d_clusters, descs));
 		ABW_CHECK(to_device(ctx, d_never, never));
-		if(d_cand.n < (size_t)C * D)
-			ABW_CUDA(ctx, d_cand.alloc((size_t)C * D));
+		// work items of the level: (dimension, tile-table entry); the table lists the tiles of every cluster
+		std::vector<uint2> tile_tab;
+		for(uint32_t c = 0; c < C; c++) {
+			descs[c].tile0 = (uint32_t)tile_tab.size();
+			const uint32_t tiles = (level[c].desc.n + SW_TILE - 1) / SW_TILE;
+			for(uint32_t t = 0; t < tiles; t++)
+				tile_tab.push_back(make_uint2(c, t));
+		}
+		const uint32_t TT = (uint32_t)tile_tab.size();
+		const uint64_t items = (uint64_t)TT * D;
+		if(items >= (1ull << 31))
+			return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_run: more than 2^31 tiles in one level");
+		ABW_CHECK(to_device(ctx, d_tile_tab, tile_tab));
+		ABW_CHECK(to_device(ctx, d_clusters, descs));
+		if(d_cand.n < items) ABW_CUDA(ctx, d_cand.alloc(items));
+		if(d_status.n < items) ABW_CUDA(ctx, d_status.alloc(items));
+		if(d_aggs.n < items) ABW_CUDA(ctx, d_aggs.alloc(items));
+		if(d_prefixes.n < items) ABW_CUDA(ctx, d_prefixes.alloc(items));
 		if(d_best.n < C)
 			ABW_CUDA(ctx, d_best.alloc(C));
 		const uint64_t tab_stride = tab_total;
@@ -1117,22 +1392,23 @@ int search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t ca
 		}
 		// sweep
 		tm.start();
-		{
-			dim3 grid(C, D);
-			if(s->strategy == ABW_SENS_SPEC)
-				ABW_LAUNCH(ctx, k_sweep<ABW_SENS_SPEC>, grid, SW_THREADS, 0, s->E[cur].p, N, d_clusters.p, s->rows.p, d_tab.p, tab_stride, sp, d_cand.p);
-			else
-				ABW_LAUNCH(ctx, k_sweep<ABW_SPLIT_SCAFS>, grid, SW_THREADS, 0, s->E[cur].p, N, d_clusters.p, s->rows.p, (const uint8_t*)nullptr, tab_stride, sp, d_cand.p);
-		}
+		ABW_CUDA(ctx, cudaMemsetAsync(d_status.p, 0, sizeof(uint32_t) * items, ctx->stream));
+		ABW_CUDA(ctx, cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned long long), ctx->stream));
+		if(s->strategy == ABW_SENS_SPEC)
+			ABW_LAUNCH(ctx, k_sweep<ABW_SENS_SPEC>, (unsigned int)items, SW_THREADS, 0, s->E[cur].p, N, d_clusters.p, TT, d_tile_tab.p, s->rows.p, d_tab.p, tab_stride, sp,
+			           d_ticket.p, d_status.p, d_aggs.p, d_prefixes.p, d_cand.p, d_error.p);
+		else
+			ABW_LAUNCH(ctx, k_sweep<ABW_SPLIT_SCAFS>, (unsigned int)items, SW_THREADS, 0, s->E[cur].p, N, d_clusters.p, TT, d_tile_tab.p, s->rows.p, (const uint8_t*)nullptr,
+			           tab_stride, sp, d_ticket.p, d_status.p, d_aggs.p, d_prefixes.p, d_cand.p, d_error.p);
 		s->prof.sweep_ms += tm.stop();
 		s->prof.sweep_launches++;
 		for(uint32_t c = 0; c < C; c++)
 			s->prof.sweep_elements += (uint64_t)level[c].desc.n * D;
 		tm.start();
 		if(s->strategy == ABW_SENS_SPEC)
-			ABW_LAUNCH(ctx, k_reduce_best<ABW_SENS_SPEC>, C, 32, 0, d_cand.p, D, d_best.p);
+			ABW_LAUNCH(ctx, k_reduce_best<ABW_SENS_SPEC>, C, 256, 0, d_cand.p, TT, D, d_clusters.p, d_best.p);
 		else
-			ABW_LAUNCH(ctx, k_reduce_best<ABW_SPLIT_SCAFS>, C, 32, 0, d_cand.p, D, d_best.p);
+			ABW_LAUNCH(ctx, k_reduce_best<ABW_SPLIT_SCAFS>, C, 256, 0, d_cand.p, TT, D, d_clusters.p, d_best.p);
 		std::vector<CandRec> best(C);
 		ABW_CUDA(ctx, cudaMemcpyAsync(best.data(), d_best.p, sizeof(CandRec) * C, cudaMemcpyDeviceToHost, ctx->stream));
 		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1317,13 +1593,26 @@ int search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t ca
 			{
 				dim3 g(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), P);
 				ABW_LAUNCH(ctx, k_commit_assigned, g, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs.p, s->new_assigned.p, s->assigned.p);
-				ABW_LAUNCH(ctx, k_partition_list, dim3(P, 1), 32, 0, s->scaf_list[cur].p, s->scaf_list[cur ^ 1].p, (uint64_t)S, d_ljobs_scaf.p, s->side.p, 1u);
+				ABW_LAUNCH(ctx, k_partition_list, dim3(P, 1), 256, 0, s->scaf_list[cur].p, s->scaf_list[cur ^ 1].p, (uint64_t)S, d_ljobs_scaf.p, s->side.p);
 				if(s->strategy == ABW_SENS_SPEC && s->K > 0)
-					ABW_LAUNCH(ctx, k_partition_list, dim3(P, abw_div_up(D, 4)), 128, 0, s->scg_list[cur].p, s->scg_list[cur ^ 1].p, (uint64_t)s->K, d_ljobs_scg.p, s->side.p, D);
+					ABW_LAUNCH(ctx, k_partition_list, dim3(P, D), 256, 0, s->scg_list[cur].p, s->scg_list[cur ^ 1].p, (uint64_t)s->K, d_ljobs_scg.p, s->side.p);
 			}
 			s->prof.other_ms += tm.stop();
+			std::vector<uint2> ptile_tab;
+			for(uint32_t i = 0; i < P; i++) {
+				const uint32_t tiles = (pjobs[i].n + SW_TILE - 1) / SW_TILE;
+				for(uint32_t t = 0; t < tiles; t++)
+					ptile_tab.push_back(make_uint2(i, t));
+			}
+			const uint32_t PTT = (uint32_t)ptile_tab.size();
+			const uint64_t pitems = (uint64_t)PTT * D;
+			ABW_CHECK(to_device(ctx, d_ptile_tab, ptile_tab));
+			if(d_lookback.n < pitems) ABW_CUDA(ctx, d_lookback.alloc(pitems));
 			tm.start();
-			ABW_LAUNCH(ctx, k_partition, dim3(P, D), SW_THREADS, 0, s->E[cur].p, s->E[cur ^ 1].p, N, d_pjobs.p, s->side.p);
+			ABW_CUDA(ctx, cudaMemsetAsync(d_lookback.p, 0, sizeof(unsigned long long) * pitems, ctx->stream));
+			ABW_CUDA(ctx, cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned long long), ctx->stream));
+			ABW_LAUNCH(ctx, k_partition, (unsigned int)pitems, SW_THREADS, 0, s->E[cur].p, s->E[cur ^ 1].p, N, d_pjobs.p, PTT, d_ptile_tab.p, s->side.p, d_ticket.p,
+			           d_lookback.p, d_error.p);
 			s->prof.partition_ms += tm.stop();
 			for(uint32_t i = 0; i < P; i++)
 				s->prof.partition_elements += (uint64_t)pjobs[i].n * D;
@@ -1333,6 +1622,13 @@ int search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t ca
 	}
 	if(nrecs)
 		*nrecs = nrec;
+	{
+		int h_error = 0;
+		ABW_CUDA(ctx, cudaMemcpyAsync(&h_error, d_error.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		if(h_error)
+			return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run: internal error, a look-back wait timed out");
+	}
 	if(h_scaf2cluster)
 		ABW_CUDA(ctx, cudaMemcpyAsync(h_scaf2cluster, s->scaf_final.p, sizeof(uint32_t) * S, cudaMemcpyDeviceToHost, ctx->stream));
 	if(h_dp2cluster) {

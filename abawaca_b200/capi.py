@@ -53,7 +53,7 @@ EXPORTS = [
     "abw_ctx_create", "abw_ctx_destroy", "abw_last_error", "abw_version", "abw_default_params", "abw_kernel_launches", "abw_ctx_stream",
     "abw_ctx_synchronize", "abw_profile_enable", "abw_profile_report", "abw_pack_sequences", "abw_seqset_destroy", "abw_seqset_stats", "abw_segment", "abw_segments_destroy",
     "abw_segments_count", "abw_segments_get", "abw_kmer_features", "abw_coverage", "abw_device_alloc", "abw_device_free",
-    "abw_copy_to_device", "abw_copy_to_host", "abw_memset_device", "abw_search_create", "abw_search_destroy", "abw_search_run",
+    "abw_copy_to_device", "abw_copy_to_host", "abw_memset_device", "abw_h2d_async", "abw_wait_h2d", "abw_search_create", "abw_search_destroy", "abw_search_run",
     "abw_search_get_profile", "abw_cluster_scg",
 ]
 
@@ -94,6 +94,8 @@ def load():
     L.abw_copy_to_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.abw_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.abw_memset_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]
+    L.abw_h2d_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
+    L.abw_wait_h2d.argtypes = [C.c_void_p, C.c_uint64]
     L.abw_search_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     L.abw_search_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p]
@@ -176,6 +178,15 @@ class Context:
 
     def to_host(self, arr, dptr):
         self.check(self.lib.abw_copy_to_host(self.h, _p(arr), C.c_void_p(dptr), arr.nbytes))
+
+    def h2d_async(self, dptr, arr):
+        """enqueue a copy of a (pinned) numpy array on the copy stream; returns a ticket for wait_h2d"""
+        t = C.c_uint64()
+        self.check(self.lib.abw_h2d_async(self.h, C.c_void_p(dptr), _p(arr), arr.nbytes, C.byref(t)))
+        return t.value
+
+    def wait_h2d(self, ticket):
+        self.check(self.lib.abw_wait_h2d(self.h, ticket))
 
     def memset(self, dptr, byte, nbytes):
         self.check(self.lib.abw_memset_device(self.h, C.c_void_p(dptr), byte, nbytes))

@@ -11,6 +11,8 @@
 struct abw_ctx {
 	int          device = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t copy_stream = nullptr;       // host->device staging that overlaps kernels of `stream` (abw_h2d_async)
+	std::vector<cudaEvent_t> copy_events;
 	int          sm_count = 148;
 	uint64_t     launches = 0;
 	std::string  err;

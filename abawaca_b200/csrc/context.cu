@@ -41,7 +41,8 @@ int abw_ctx_create(int device, abw_ctx** out)
 		return ABW_ERR_CUDA;
 	abw_ctx* c = new abw_ctx();
 	c->device = device;
-	if(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+	if(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+	   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
 		delete c;
 		return ABW_ERR_CUDA;
 	}
@@ -63,6 +64,10 @@ void abw_ctx_destroy(abw_ctx* ctx)
 	if(!ctx)
 		return;
 	cudaSetDevice(ctx->device);
+	for(cudaEvent_t e : ctx->copy_events)
+		cudaEventDestroy(e);
+	if(ctx->copy_stream)
+		cudaStreamDestroy(ctx->copy_stream);
 	if(ctx->stream)
 		cudaStreamDestroy(ctx->stream);
 	if(ctx->ev_a) {
@@ -82,7 +87,11 @@ int abw_ctx_synchronize(abw_ctx* ctx)
 {
 	if(!ctx)
 		return ABW_ERR_ARG;
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
 	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	for(cudaEvent_t e : ctx->copy_events)      // every staged copy has completed: tickets handed out so far are retired
+		cudaEventDestroy(e);
+	ctx->copy_events.clear();
 	return ABW_OK;
 }
 
@@ -151,6 +160,35 @@ int abw_copy_to_host(abw_ctx* ctx, void* h_dst, const void* d_src, size_t bytes)
 		return ABW_ERR_ARG;
 	ABW_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return ABW_OK;
+}
+
+int abw_h2d_async(abw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, uint64_t* ticket)
+{
+	if(!ctx || !ticket)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_h2d_async: null argument");
+	// the destination may have been allocated in order on the compute stream: let the copy stream see that allocation
+	cudaEvent_t ready;
+	ABW_CUDA(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+	ABW_CUDA(ctx, cudaEventRecord(ready, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
+	ABW_CUDA(ctx, cudaEventDestroy(ready));
+	ABW_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+	cudaEvent_t done;
+	ABW_CUDA(ctx, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+	ABW_CUDA(ctx, cudaEventRecord(done, ctx->copy_stream));
+	ctx->copy_events.push_back(done);
+	*ticket = ctx->copy_events.size();          // 1-based; 0 means "nothing to wait for"
+	return ABW_OK;
+}
+
+int abw_wait_h2d(abw_ctx* ctx, uint64_t ticket)
+{
+	if(!ctx || ticket > ctx->copy_events.size())
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_wait_h2d: unknown ticket");
+	if(ticket == 0)
+		return ABW_OK;
+	ABW_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_events[ticket - 1], 0));
 	return ABW_OK;
 }
 

@@ -70,7 +70,7 @@ class FeatureBuild:
 
 
 def build_features(ctx: capi.Context, seq, offsets, reads, this_sample=0, params=None, kind=capi.FEAT_TRUNC3, skip_A=True,
-                   seq_on_device=False, reads_on_device=False, nreads=None, timings=None) -> FeatureBuild:
+                   seq_on_device=False, reads_on_device=False, nreads=None, timings=None, overlap_h2d=False) -> FeatureBuild:
     """seq: uint8 ASCII (numpy array, or a device pointer int when seq_on_device); offsets: uint64 [nscaf+1];
     reads: one structured array (capi.READ_DTYPE) per sample (or device pointers + nreads)."""
     L = ctx.lib
@@ -85,6 +85,25 @@ def build_features(ctx: capi.Context, seq, offsets, reads, this_sample=0, params
             now = time.perf_counter()
             timings[name] = timings.get(name, 0.0) + 1000.0 * (now - t_last[0])
             t_last[0] = now
+    staged = []
+    tickets = None
+    if overlap_h2d and not seq_on_device and not reads_on_device:
+        # enqueue every host->device copy up front on the copy stream (inputs should be pinned); each stage waits for its own
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        d_seq = ctx.alloc(seq.nbytes + 64)
+        staged.append(d_seq)
+        t_seq = ctx.h2d_async(d_seq, seq)
+        tickets, dev_reads, nreads = [], [], []
+        for r in reads:
+            r = np.ascontiguousarray(r)
+            d = ctx.alloc(max(r.nbytes, 16))
+            staged.append(d)
+            tickets.append(ctx.h2d_async(d, r) if r.nbytes else 0)
+            dev_reads.append(d)
+            nreads.append(int(r.size))
+        ctx.wait_h2d(t_seq)
+        seq, reads = d_seq, dev_reads
+        seq_on_device = reads_on_device = True
     seqset = C.c_void_p()
     if seq_on_device:
         ctx.check(L.abw_pack_sequences(ctx.h, C.c_void_p(seq), 1, capi._p(offsets), nscaf, C.byref(seqset)))
@@ -106,11 +125,15 @@ def build_features(ctx: capi.Context, seq, offsets, reads, this_sample=0, params
     for j, r in enumerate(reads):
         nb = C.c_void_p(d_nbps) if j == this_sample else None
         if reads_on_device:
+            if tickets is not None:
+                ctx.wait_h2d(tickets[j])
             ctx.check(L.abw_coverage(ctx.h, segs, C.c_void_p(r), nreads[j], 1, p.max_snps, kind, C.c_void_p(d_rows), ncols, nk + j, nb))
         else:
             r = np.ascontiguousarray(r)
             ctx.check(L.abw_coverage(ctx.h, segs, capi._p(r), r.size, 0, p.max_snps, kind, C.c_void_p(d_rows), ncols, nk + j, nb))
     ctx.synchronize()
+    for d in staged:
+        ctx.free(d)
     lap("coverage_ms")
     return FeatureBuild(ctx, seqset, segs, d_rows, nseg, ncols, nscaf, d_nbps)
 

@@ -258,7 +258,7 @@ def main():
         if resident:
             fb = pipeline.build_features(ctx, d_seq, mg.offsets, d_reads, this_sample=0, seq_on_device=True, reads_on_device=True, nreads=nreads, timings=timings)
         else:
-            fb = pipeline.build_features(ctx, h_seq.numpy(), mg.offsets, h_reads_np, this_sample=0, timings=timings)
+            fb = pipeline.build_features(ctx, h_seq.numpy(), mg.offsets, h_reads_np, this_sample=0, timings=timings, overlap_h2d=True)
         sg = fb.segments_host()
         keep, dp2scaf, T, kept = pipeline.search_problem_from_features(sg["seg_scaf"], nscaf)
         row_of_dp = None if keep.all() else np.nonzero(keep)[0].astype(np.uint64)   # scaffolds with one window are dropped (ScafDpData.cpp:92-93)

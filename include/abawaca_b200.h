@@ -117,6 +117,12 @@ int abw_device_free(abw_ctx* ctx, void* d_ptr);
 int abw_copy_to_device(abw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 int abw_copy_to_host(abw_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 int abw_memset_device(abw_ctx* ctx, void* d_ptr, int byte, size_t bytes);
+/* Staging that overlaps compute: abw_h2d_async enqueues a copy from PINNED host memory on the context's copy stream and
+ * returns a ticket; abw_wait_h2d makes every later call on this context wait (on the device, not the host) for that copy.
+ * Typical use: enqueue the assembly and all samples' read records up front, then wait for each just before its
+ * abw_pack_sequences / abw_coverage call.  Tickets are retired by abw_ctx_synchronize. */
+int abw_h2d_async(abw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, uint64_t* ticket);
+int abw_wait_h2d(abw_ctx* ctx, uint64_t ticket);
 
 /* ---- split search (abawaca) ----------------------------------------------------------------- */
 

@@ -49,12 +49,20 @@ class SearchProfile(C.Structure):
                 ("sweep_elements", C.c_uint64), ("partition_elements", C.c_uint64), ("levels", C.c_uint32), ("sweep_launches", C.c_uint32)]
 
 
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class Collectives(C.Structure):
+    _fields_ = [("allgather", ALLGATHER_FN), ("allreduce_sum_i64", ALLREDUCE_FN), ("user", C.c_void_p), ("rank", C.c_int), ("world", C.c_int)]
+
+
 EXPORTS = [
     "abw_ctx_create", "abw_ctx_destroy", "abw_last_error", "abw_version", "abw_default_params", "abw_kernel_launches", "abw_ctx_stream",
     "abw_ctx_synchronize", "abw_profile_enable", "abw_profile_report", "abw_pack_sequences", "abw_seqset_destroy", "abw_seqset_stats", "abw_segment", "abw_segments_destroy",
     "abw_segments_count", "abw_segments_get", "abw_kmer_features", "abw_coverage", "abw_device_alloc", "abw_device_free",
     "abw_copy_to_device", "abw_copy_to_host", "abw_memset_device", "abw_h2d_async", "abw_wait_h2d", "abw_search_create", "abw_search_destroy", "abw_search_run",
-    "abw_search_get_profile", "abw_cluster_scg",
+    "abw_search_set_shard", "abw_search_run_sharded", "abw_search_get_profile", "abw_cluster_scg",
 ]
 
 
@@ -99,6 +107,8 @@ def load():
     L.abw_search_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     L.abw_search_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p]
+    L.abw_search_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    L.abw_search_run_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p]
     L.abw_search_get_profile.argtypes = [C.c_void_p, C.c_void_p]
     L.abw_cluster_scg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
     _LIB = L

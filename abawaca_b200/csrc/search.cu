@@ -505,9 +505,11 @@ struct SplitJob {
 	uint32_t dim0;       // winning dimension
 	uint32_t p;          // datapoints with value <= separating value
 	uint32_t swapped;    // cluster1 is the high side (ClusterSeparator.cpp:49-53)
+	uint32_t slot;       // index of the job in the level-wide (all ranks) job list: where its statistics go
+	uint32_t pad;
 };
 
-struct ChildStats {      // [job][2]
+struct ChildStats {      // [job][2]; summed across ranks as 64-bit words in a sharded search (no 32-bit half can overflow)
 	unsigned long long ndps, totLen;
 	uint32_t ns, nassigned, totT, K, viol, pad;
 };
@@ -546,7 +548,7 @@ __global__ void k_scaf_sides(const uint32_t* __restrict__ scaf_list, const Clust
 		const uint32_t sd = A2? 2u : 1u;
 		side[s] = (uint8_t)sd;
 		new_assigned[s] = A1? 1 : (A2? 2 : 0);
-		ChildStats* st = stats + (uint64_t)blockIdx.y * 2 + (sd - 1);
+		ChildStats* st = stats + (uint64_t)jb.slot * 2 + (sd - 1);
 		atomicAdd(&st->ndps, (unsigned long long)r.n);
 		atomicAdd(&st->totLen, (unsigned long long)r.len);
 		atomicAdd(&st->ns, 1u);
@@ -561,7 +563,7 @@ __global__ void k_scaf_sides(const uint32_t* __restrict__ scaf_list, const Clust
 				atomicAdd(&st->K, 1u);
 			else                                             // can never be assigned to side 1 of a sweep: always counted on side 2
 				for(uint32_t w = 0; w < W; w++)
-					atomicOr((unsigned long long*)&child_never[((uint64_t)blockIdx.y * 2 + (sd - 1)) * W + w], (unsigned long long)scgmask[(uint64_t)s * W + w]);
+					atomicOr((unsigned long long*)&child_never[((uint64_t)jb.slot * 2 + (sd - 1)) * W + w], (unsigned long long)scgmask[(uint64_t)s * W + w]);
 		}
 		if(strategy == ABW_SPLIT_SCAFS && !((double)r.n >= __dmul_rn(fraction_in, (double)r.T)))
 			atomicAdd(&st->viol, 1u);
@@ -579,7 +581,7 @@ __global__ void k_scaf_sides(const uint32_t* __restrict__ scaf_list, const Clust
 				if(rank == lo - 1)
 					kth = ka;
 			}
-			atomicMax(&value_key[blockIdx.y], kth);
+			atomicMax(&value_key[jb.slot], kth);
 		}
 	}
 }
@@ -1050,6 +1052,7 @@ struct abw_search {
 	uint32_t root_viol = 0;
 	std::vector<uint64_t> root_never;
 	bool consumed = false;
+	uint32_t dim_offset = 0, D_total = 0;     // sharded search: this object holds dimensions [dim_offset, dim_offset + D) of D_total
 	abw_search_profile prof{};
 };
 
@@ -1245,9 +1248,11 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		ABW_CUDA(ctx, cudaMemcpyAsync(s->scaf_list[0].p, iota.data(), sizeof(uint32_t) * S, cudaMemcpyHostToDevice, ctx->stream));
 		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	}
-	ABW_CUDA(ctx, s->side.alloc(S));
+	ABW_CUDA(ctx, s->side.alloc(((size_t)S + 7) / 8 * 8));            // whole 64-bit words: summed across ranks in a sharded search
 	ABW_CUDA(ctx, s->assigned.alloc(S));
-	ABW_CUDA(ctx, s->new_assigned.alloc(S));
+	ABW_CUDA(ctx, s->new_assigned.alloc(((size_t)S + 7) / 8 * 8));
+	ABW_CUDA(ctx, cudaMemsetAsync(s->side.p, 0, ((size_t)S + 7) / 8 * 8, ctx->stream));
+	ABW_CUDA(ctx, cudaMemsetAsync(s->new_assigned.p, 0, ((size_t)S + 7) / 8 * 8, ctx->stream));
 	ABW_CUDA(ctx, s->low.alloc(S));
 	ABW_CUDA(ctx, s->scaf_member.alloc(S));
 	ABW_CUDA(ctx, s->scaf_final.alloc(S));
@@ -1257,6 +1262,22 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	ABW_CUDA(ctx, cudaMemsetAsync(s->scaf_final.p, 0, sizeof(uint32_t) * S, ctx->stream));
 	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return ABW_OK;
+}
+
+// host copy of cand_better (the reference's total order), used to merge the per-rank bests of a sharded search
+bool host_cand_better(int strategy, const CandRec& x, const CandRec& y)
+{
+	if(!x.found) return false;
+	if(!y.found) return true;
+	if(strategy == ABW_SENS_SPEC) {
+		if(x.k1 != y.k1) return x.k1 > y.k1;
+	}
+	else {
+		if(x.k1 != y.k1) return x.k1 < y.k1;
+		if(x.k2 != y.k2) return x.k2 < y.k2;
+	}
+	if(x.dim0 != y.dim0) return x.dim0 < y.dim0;
+	return x.p < y.p;
 }
 
 bool is_legal(const abw_params& p, int strategy, const abw_best& b)
@@ -1278,8 +1299,38 @@ int to_device(abw_ctx* ctx, DevBuf<T>& buf, const std::vector<T>& h)
 	return ABW_OK;
 }
 
-int search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t cap, uint32_t* nrecs, uint32_t* h_dp2cluster, uint32_t* h_scaf2cluster)
+int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_cluster_rec* h_recs, uint32_t cap, uint32_t* nrecs, uint32_t* h_dp2cluster,
+               uint32_t* h_scaf2cluster)
 {
+	const int world = coll? coll->world : 1, my_rank = coll? coll->rank : 0;
+	if(s->D_total == 0)
+		s->D_total = s->D;
+	// which rank holds which dimensions
+	std::vector<uint32_t> shard_off(world, 0), shard_n(world, s->D);
+	if(coll) {
+		DevBuf<uint32_t> d_mine, d_all;
+		ABW_CUDA(ctx, d_mine.alloc(2));
+		ABW_CUDA(ctx, d_all.alloc(2 * (size_t)world));
+		uint32_t mine[2] = {s->dim_offset, s->D};
+		ABW_CUDA(ctx, cudaMemcpyAsync(d_mine.p, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		if(coll->allgather(coll->user, d_mine.p, d_all.p, sizeof(mine)) != 0)
+			return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run_sharded: allgather callback failed");
+		std::vector<uint32_t> all(2 * (size_t)world);
+		ABW_CUDA(ctx, cudaMemcpyAsync(all.data(), d_all.p, sizeof(uint32_t) * all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		for(int r = 0; r < world; r++) {
+			shard_off[r] = all[2 * r];
+			shard_n[r] = all[2 * r + 1];
+		}
+	}
+	auto owner_of = [&](uint32_t gdim) {
+		for(int r = 0; r < world; r++)
+			if(gdim >= shard_off[r] && gdim < shard_off[r] + shard_n[r])
+				return r;
+		return -1;
+	};
+	DevBuf<CandRec> d_best_all;
 	const uint64_t N = s->N;
 	const uint32_t D = s->D, S = s->S, W = s->W;
 	const abw_params& prm = s->prm;
@@ -1330,7 +1381,7 @@ int search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t ca
 	ABW_CUDA(ctx, cudaMemsetAsync(d_error.p, 0, sizeof(int), ctx->stream));
 	DevBuf<uint8_t> d_tab;
 	DevBuf<uint64_t> d_suffix, d_never, d_child_never, d_union;
-	DevBuf<SplitJob> d_jobs;
+	DevBuf<SplitJob> d_jobs, d_jobs_mine;
 	DevBuf<ChildStats> d_stats;
 	DevBuf<unsigned long long> d_value_key;
 	DevBuf<PartJob> d_pjobs;
@@ -1412,6 +1463,26 @@ int search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t ca
 		std::vector<CandRec> best(C);
 		ABW_CUDA(ctx, cudaMemcpyAsync(best.data(), d_best.p, sizeof(CandRec) * C, cudaMemcpyDeviceToHost, ctx->stream));
 		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		for(uint32_t c = 0; c < C; c++)
+			best[c].dim0 += s->dim_offset;               // global dimension index from here on
+		if(coll) {
+			// gather the per-shard best of every cluster and apply the same total order on every rank
+			ABW_CUDA(ctx, cudaMemcpyAsync(d_best.p, best.data(), sizeof(CandRec) * C, cudaMemcpyHostToDevice, ctx->stream));
+			if(d_best_all.n < (size_t)C * world) ABW_CUDA(ctx, d_best_all.alloc((size_t)C * world));
+			ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			if(coll->allgather(coll->user, d_best.p, d_best_all.p, sizeof(CandRec) * C) != 0)
+				return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run_sharded: allgather callback failed");
+			std::vector<CandRec> all((size_t)C * world);
+			ABW_CUDA(ctx, cudaMemcpyAsync(all.data(), d_best_all.p, sizeof(CandRec) * all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+			ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			for(uint32_t c = 0; c < C; c++) {
+				CandRec b = all[c];
+				for(int r = 1; r < world; r++)
+					if(host_cand_better(s->strategy, all[(size_t)r * C + c], b))
+						b = all[(size_t)r * C + c];
+				best[c] = b;
+			}
+		}
 		// host: scores, legality (same IEEE operations as ClusterStats::get_sensitivity/get_specificity, .h:74-75)
 		std::vector<abw_best> hb(C);
 		std::vector<SplitJob> jobs;          // every cluster with a best separation: value recovery; legal ones: children
@@ -1438,6 +1509,8 @@ int search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t ca
 				jb.dim0 = best[c].dim0;
 				jb.p = best[c].p;
 				jb.swapped = (level[c].desc.n - best[c].p) < best[c].p;      // ClusterSeparator.cpp:49
+				jb.slot = (uint32_t)jobs.size();
+				jb.pad = 0;
 				job_of[c] = (uint32_t)jobs.size();
 				jobs.push_back(jb);
 			}
@@ -1448,19 +1521,50 @@ int search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t ca
 		std::vector<unsigned long long> vkeys(J, 0);
 		std::vector<uint64_t> child_never((size_t)J * 2 * W, 0);
 		if(J > 0) {
+			// jobs whose winning dimension lives on this rank (all of them when the search is not sharded), with local dimension indices
+			std::vector<SplitJob> mine;
+			for(const SplitJob& jb : jobs)
+				if(owner_of(jb.dim0) == my_rank) {
+					SplitJob l = jb;
+					l.dim0 = jb.dim0 - s->dim_offset;
+					mine.push_back(l);
+				}
+			const uint32_t JM = (uint32_t)mine.size();
 			ABW_CHECK(to_device(ctx, d_jobs, jobs));
+			ABW_CHECK(to_device(ctx, d_jobs_mine, mine));
 			if(d_stats.n < (size_t)J * 2) ABW_CUDA(ctx, d_stats.alloc((size_t)J * 2));
 			if(d_value_key.n < J) ABW_CUDA(ctx, d_value_key.alloc(J));
 			if(d_child_never.n < (size_t)J * 2 * W) ABW_CUDA(ctx, d_child_never.alloc((size_t)J * 2 * W));
 			ABW_CUDA(ctx, cudaMemsetAsync(d_stats.p, 0, sizeof(ChildStats) * J * 2, ctx->stream));
 			ABW_CUDA(ctx, cudaMemsetAsync(d_value_key.p, 0, sizeof(unsigned long long) * J, ctx->stream));
 			ABW_CUDA(ctx, cudaMemsetAsync(d_child_never.p, 0, sizeof(uint64_t) * J * 2 * W, ctx->stream));
-			dim3 g1(std::min<uint32_t>(abw_div_up(N, 256), 4u * ctx->sm_count), J);
-			ABW_LAUNCH(ctx, k_count_low, g1, 256, 0, s->E[cur].p, N, d_clusters.p, d_jobs.p, s->low.p);
 			dim3 g2(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), J);
-			ABW_LAUNCH(ctx, k_scaf_sides, g2, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs.p, s->rows.p, s->low.p, s->dp_first.p, s->values.p, N, s->scgmask.p, W,
-			           s->strategy, prm.fraction_dps_in, s->side.p, s->new_assigned.p, d_stats.p, d_child_never.p, d_value_key.p);
-			ABW_LAUNCH(ctx, k_clear_low, g2, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs.p, s->low.p);
+			if(coll) {
+				// whole arrays: stale bytes of earlier levels would otherwise be summed again and carry into their neighbours
+				ABW_CUDA(ctx, cudaMemsetAsync(s->side.p, 0, ((size_t)S + 7) / 8 * 8, ctx->stream));
+				ABW_CUDA(ctx, cudaMemsetAsync(s->new_assigned.p, 0, ((size_t)S + 7) / 8 * 8, ctx->stream));
+			}
+			(void)g2;
+			if(JM > 0) {
+				dim3 g1(std::min<uint32_t>(abw_div_up(N, 256), 4u * ctx->sm_count), JM);
+				dim3 g3(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), JM);
+				ABW_LAUNCH(ctx, k_count_low, g1, 256, 0, s->E[cur].p, N, d_clusters.p, d_jobs_mine.p, s->low.p);
+				ABW_LAUNCH(ctx, k_scaf_sides, g3, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs_mine.p, s->rows.p, s->low.p, s->dp_first.p, s->values.p, N, s->scgmask.p, W,
+				           s->strategy, prm.fraction_dps_in, s->side.p, s->new_assigned.p, d_stats.p, d_child_never.p, d_value_key.p);
+				ABW_LAUNCH(ctx, k_clear_low, g3, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs_mine.p, s->low.p);
+			}
+			if(coll) {
+				// every quantity below is non-zero on exactly one rank (the owner of the winning dimension): a sum is a gather
+				ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+				const size_t s8 = ((size_t)S + 7) / 8;
+				int rc = coll->allreduce_sum_i64(coll->user, s->side.p, s8);
+				rc |= coll->allreduce_sum_i64(coll->user, s->new_assigned.p, s8);
+				rc |= coll->allreduce_sum_i64(coll->user, d_stats.p, (size_t)J * 2 * sizeof(ChildStats) / 8);
+				rc |= coll->allreduce_sum_i64(coll->user, d_value_key.p, J);
+				rc |= coll->allreduce_sum_i64(coll->user, d_child_never.p, (size_t)J * 2 * W);
+				if(rc != 0)
+					return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run_sharded: allreduce callback failed");
+			}
 			ABW_CUDA(ctx, cudaMemcpyAsync(stats.data(), d_stats.p, sizeof(ChildStats) * J * 2, cudaMemcpyDeviceToHost, ctx->stream));
 			ABW_CUDA(ctx, cudaMemcpyAsync(vkeys.data(), d_value_key.p, sizeof(unsigned long long) * J, cudaMemcpyDeviceToHost, ctx->stream));
 			ABW_CUDA(ctx, cudaMemcpyAsync(child_never.data(), d_child_never.p, sizeof(uint64_t) * J * 2 * W, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1697,7 +1801,25 @@ int abw_search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_
 	if(!ctx || !s)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_run: null argument");
 	ABW_ENTER(ctx);
-	return search_run(ctx, s, h_recs, cap, nrecs, h_dp2cluster, h_scaf2cluster);
+	return search_run(ctx, s, nullptr, h_recs, cap, nrecs, h_dp2cluster, h_scaf2cluster);
+}
+
+int abw_search_set_shard(abw_search* s, uint32_t dim_offset, uint32_t D_total)
+{
+	if(!s || (uint64_t)dim_offset + s->D > D_total)
+		return ABW_ERR_ARG;
+	s->dim_offset = dim_offset;
+	s->D_total = D_total;
+	return ABW_OK;
+}
+
+int abw_search_run_sharded(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_cluster_rec* h_recs, uint32_t cap, uint32_t* nrecs, uint32_t* h_dp2cluster,
+                           uint32_t* h_scaf2cluster)
+{
+	if(!ctx || !s || !coll || !coll->allgather || !coll->allreduce_sum_i64 || coll->world < 1 || coll->rank < 0 || coll->rank >= coll->world)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_run_sharded: bad argument");
+	ABW_ENTER(ctx);
+	return search_run(ctx, s, coll, h_recs, cap, nrecs, h_dp2cluster, h_scaf2cluster);
 }
 
 int abw_search_get_profile(const abw_search* s, abw_search_profile* out)

@@ -159,7 +159,8 @@ class SearchResult:
 
 
 def search(ctx: capi.Context, values, dp2scaf, T, length, scgmask, params=None, strategy=capi.SENS_SPEC, layout=capi.LAYOUT_COLMAJOR,
-           values_on_device=False, N=None, D=None, ld=None, want_bins=True, row_of_dp=None, nrows=None, timings=None) -> SearchResult:
+           values_on_device=False, N=None, D=None, ld=None, want_bins=True, row_of_dp=None, nrows=None, timings=None,
+           collectives=None, dim_offset=0, D_total=None) -> SearchResult:
     """values: numpy [D][nrows] (column major) or [nrows][D] (row major), or a device pointer with nrows, D, ld given.
     row_of_dp (uint64 [N], optional): the matrix row of every datapoint; default: N = nrows, datapoint i = row i."""
     L = ctx.lib
@@ -200,7 +201,12 @@ def search(ctx: capi.Context, values, dp2scaf, T, length, scgmask, params=None, 
         n = C.c_uint32()
         dp2c = np.zeros(N, dtype=np.uint32) if want_bins else None
         s2c = np.zeros(S, dtype=np.uint32) if want_bins else None
-        ctx.check(L.abw_search_run(ctx.h, h, recs, cap, C.byref(n), capi._p(dp2c), capi._p(s2c)))
+        if collectives is None:
+            ctx.check(L.abw_search_run(ctx.h, h, recs, cap, C.byref(n), capi._p(dp2c), capi._p(s2c)))
+        else:
+            # dimension-sharded search: `values` holds dimensions [dim_offset, dim_offset + D) of D_total on this rank
+            ctx.check(L.abw_search_set_shard(h, dim_offset, D_total if D_total is not None else D))
+            ctx.check(L.abw_search_run_sharded(ctx.h, h, C.byref(collectives.struct), recs, cap, C.byref(n), capi._p(dp2c), capi._p(s2c)))
         if timings is not None:
             timings["search_create_ms"] = timings.get("search_create_ms", 0.0) + 1000.0 * (t1 - t0)
             timings["search_run_ms"] = timings.get("search_run_ms", 0.0) + 1000.0 * (time.perf_counter() - t1)

@@ -174,6 +174,23 @@ typedef struct {
  * h_dp2cluster[N] / h_scaf2cluster[S] (may be NULL): terminal cluster id, 0 if none (abawaca.cpp:199-210). */
 int abw_search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_t cap, uint32_t* nrecs, uint32_t* h_dp2cluster, uint32_t* h_scaf2cluster);
 
+/* ---- dimension-sharded search over several GPUs (one process per GPU) ---------------------------------------------------
+ * Every rank holds ALL datapoints but only a contiguous block of dimensions (abw_search_create on that block, then
+ * abw_search_set_shard).  Per level each rank sweeps its dimensions; the per-cluster best records are all-gathered and
+ * merged with the reference's total order (ClusterSeparator.cpp:11-16), the rank owning the winning dimension votes the
+ * scaffolds (ClusterSeparator.cpp:94-101) and the result reaches the others through a sum in which every other rank
+ * contributes zeros.  The two collectives are supplied by the caller (NCCL through torch.distributed in bench.py; any MPI
+ * would do): they act on DEVICE buffers of this rank and must have completed when they return. */
+typedef struct {
+	int (*allgather)(void* user, const void* d_send, void* d_recv, size_t bytes_per_rank);   /* recv = rank 0 | rank 1 | ... */
+	int (*allreduce_sum_i64)(void* user, void* d_buf, size_t count);                         /* in place, 64-bit integer sum */
+	void* user;
+	int rank, world;
+} abw_collectives;
+int abw_search_set_shard(abw_search* s, uint32_t dim_offset, uint32_t D_total);
+int abw_search_run_sharded(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_cluster_rec* h_recs, uint32_t cap, uint32_t* nrecs,
+                           uint32_t* h_dp2cluster, uint32_t* h_scaf2cluster);
+
 /* Timing of the last abw_search_run, in milliseconds of device time per kernel family (CUDA events on the context stream) */
 typedef struct {
 	float build_ms;       /* abw_search_create: key transform, sort, element packing */

@@ -1,0 +1,83 @@
+"""GPU test of the dimension-sharded search on ONE device: two ranks run as two host threads with their own contexts, the two
+collectives are implemented by the test through host memory.  The result must equal the single-rank search bit for bit."""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+
+from golden_util import search_problem
+
+pytestmark = pytest.mark.gpu
+
+
+class ThreadCollectives:
+    """abw_collectives for `world` threads of one process (device buffers are staged through numpy)."""
+
+    def __init__(self, ctxs):
+        from abawaca_b200 import capi
+        self.world = len(ctxs)
+        self.barrier = threading.Barrier(self.world)
+        self.slots = [None] * self.world
+        self.structs, self._keep = [], []
+        for rank, ctx in enumerate(ctxs):
+            def allgather(user, d_send, d_recv, nbytes, rank=rank, ctx=ctx):
+                buf = np.empty(nbytes, dtype=np.uint8)
+                ctx.to_host(buf, d_send)
+                self.slots[rank] = buf
+                self.barrier.wait()
+                ctx.to_device(d_recv, np.concatenate(self.slots))
+                self.barrier.wait()
+                return 0
+
+            def allreduce(user, d_buf, count, rank=rank, ctx=ctx):
+                buf = np.empty(count, dtype=np.int64)
+                ctx.to_host(buf, d_buf)
+                self.slots[rank] = buf
+                self.barrier.wait()
+                ctx.to_device(d_buf, np.sum(self.slots, axis=0, dtype=np.int64))
+                self.barrier.wait()
+                return 0
+            ag, ar = capi.ALLGATHER_FN(allgather), capi.ALLREDUCE_FN(allreduce)
+            self._keep += [ag, ar]
+            st = capi.Collectives(ag, ar, None, rank, self.world)
+            self.structs.append(type("S", (), {"struct": st})())
+
+
+@pytest.mark.parametrize("name,strategy,world", [("tiny_noisy", 0, 2), ("tiny_noisy", 1, 2), ("tiny_clean", 0, 3)])
+def test_sharded_search_equals_single_rank(name, strategy, world):
+    from abawaca_b200 import capi, pipeline, distributed
+    prob = search_problem(name)
+    vals = prob["values"]
+    D = vals.shape[0]
+    p = capi.default_params()
+    p.min_reported_score = 0.0
+    ctx0 = capi.Context(0)
+    ref = pipeline.search(ctx0, vals, prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"], params=p, strategy=strategy)
+    ctx0.close()
+    ctxs = [capi.Context(0) for _ in range(world)]
+    coll = ThreadCollectives(ctxs)
+    results, errors = [None] * world, []
+
+    def run(rank):
+        try:
+            off, cnt = distributed.dim_block(D, rank, world)
+            results[rank] = pipeline.search(ctxs[rank], np.ascontiguousarray(vals[off:off + cnt]), prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"], params=p,
+                                            strategy=strategy, collectives=coll.structs[rank], dim_offset=off, D_total=D)
+        except Exception as e:
+            errors.append(e)
+            coll.barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    key = lambda r: (r.id, r.parent, r.ndps, r.nscafs, r.split, r.best.found, r.best.dim, r.best.value, r.best.a, r.best.b, r.child1, r.child2, r.child1_ndps,
+                     r.child2_ndps, r.child1_nscafs, r.child2_nscafs, r.child1_raw, r.child2_raw, r.total_size, r.scg_unique, r.scg_avg)   # noqa: E731
+    for res in results:
+        assert [key(r) for r in res.recs] == [key(r) for r in ref.recs]
+        assert res.scaf2cluster.tolist() == ref.scaf2cluster.tolist() and res.dp2cluster.tolist() == ref.dp2cluster.tolist()
+    for c in ctxs:
+        c.close()

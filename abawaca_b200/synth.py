@@ -62,7 +62,10 @@ class Metagenome:
 def make_metagenome(n_scaffolds, n_samples, n_genomes, seed, *, min_len=4000, mean_extra=6000, max_len=200000,
                     read_len=150, cov_lo=0.5, cov_hi=16.0, n_run_frac=0.005, n_scg=51, scg_p=0.9,
                     bad_read_frac=0.03, q6_reads=False, shuffle_reads=False, with_reads=True,
-                    gc_lo=0.25, gc_hi=0.75, tri_sigma=0.6) -> Metagenome:
+                    gc_lo=0.25, gc_hi=0.75, tri_sigma=0.6, shard=None) -> Metagenome:
+    """shard: when given, the genome models (composition, coverage) still come from `seed` alone, but the scaffolds, reads and gene
+    placements are drawn from (seed, shard): several shards are then pieces of ONE community, which is how bench.py builds the
+    N-GPU workload (every rank generates only its own scaffolds)."""
     rng = np.random.default_rng(seed)
     # genome models
     gc = rng.uniform(gc_lo, gc_hi, n_genomes)
@@ -73,10 +76,14 @@ def make_metagenome(n_scaffolds, n_samples, n_genomes, seed, *, min_len=4000, me
     tri_p *= np.exp(rng.normal(0.0, tri_sigma, (n_genomes, 64)))
     tri_p /= tri_p.sum(axis=1, keepdims=True)
     cov = np.exp(rng.uniform(np.log(cov_lo), np.log(cov_hi), (n_genomes, max(n_samples, 1))))
+    tag = ""
+    if shard is not None:
+        rng = np.random.default_rng([seed, 7919 + int(shard)])
+        tag = f"r{int(shard)}_"
 
     genome = rng.integers(0, n_genomes, n_scaffolds)
     lengths = np.minimum(min_len + rng.exponential(mean_extra, n_scaffolds).astype(np.int64), max_len)
-    names = [f"g{g}_scaffold_{i}" for i, g in enumerate(genome)]
+    names = [f"{tag}g{g}_scaffold_{i}" for i, g in enumerate(genome)]
     order = sorted(range(n_scaffolds), key=lambda i: names[i].encode())
     names = [names[i] for i in order]
     genome = genome[order]

@@ -5,8 +5,9 @@
 
 One "step" = one pass of the hot path over one synthetic metagenome: pack -> windows -> k-mer signature ->
 per-sample coverage -> split search down to the final bins.  At N=1 the workload is BASELINE.json configs[1]
-(50k scaffolds, 10 samples).  At N>1 every rank bins its own metagenome of that size (independent assemblies,
-no data-path collective; weak scaling) and only bin counts are gathered over NCCL.
+(50k scaffolds, 10 samples).  At N>1 the assembly has N x 50k scaffolds of ONE community (weak scaling): scaffolds are
+sharded across the ranks for the feature build (no exchange), the feature rows are all-gathered over NCCL, and the split
+search is sharded by dimension (abw_search_run_sharded: all-gather of per-cluster best records + one sum per level).
 
   value : whole-job scaffolds/s with the inputs (ASCII assembly, read records) already resident in HBM
   e2e   : the same through the C ABI with HOST buffers: H2D of assembly + reads and D2H of the .lrn matrix and bins inside the timed region
@@ -229,16 +230,19 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    w_rank = dict(w, seed=w["seed"] + 1000 * rank)
-    mg = synth.make_metagenome(**w_rank, q6_reads=True)
+    mg = synth.make_metagenome(**w, q6_reads=True, shard=(rank if world > 1 else None))
     ctx = capi.Context(local_rank)
     L = ctx.lib
     import ctypes as C
+    from abawaca_b200 import distributed
     nscaf = mg.nscaf
     lengths = np.diff(mg.offsets.astype(np.int64)).astype(np.uint64)
     masks = mg.scg_masks()
+    if masks.shape[1] != 1:
+        raise SystemExit("bench.py assumes at most 64 SCG names")
     total_bp = int(mg.seq.size)
     nreads = [int(r.size) for r in mg.reads]
+    coll = distributed.TorchCollectives(local_rank) if world > 1 else None
 
     # pinned host copies (e2e) and device-resident copies (value)
     h_seq = torch.from_numpy(mg.seq).pin_memory()
@@ -253,6 +257,7 @@ def main():
 
     state = {}
     h_reads_np = [t.numpy().view(capi.READ_DTYPE).reshape(-1) for t in h_reads]
+    dev = torch.device("cuda", local_rank)
 
     def step(resident, timings=None):
         if resident:
@@ -261,14 +266,41 @@ def main():
             fb = pipeline.build_features(ctx, h_seq.numpy(), mg.offsets, h_reads_np, this_sample=0, timings=timings, overlap_h2d=True)
         sg = fb.segments_host()
         keep, dp2scaf, T, kept = pipeline.search_problem_from_features(sg["seg_scaf"], nscaf)
-        row_of_dp = None if keep.all() else np.nonzero(keep)[0].astype(np.uint64)   # scaffolds with one window are dropped (ScafDpData.cpp:92-93)
         rows_host = None
         if not resident:
             rows_host = fb.rows_host()                 # the .lrn matrix goes back to the host in the end-to-end path
-        res = pipeline.search(ctx, fb.d_rows, dp2scaf, T, lengths[kept], masks[kept], layout=capi.LAYOUT_ROWMAJOR, values_on_device=True,
-                              nrows=fb.nseg, D=fb.ncols, ld=fb.ncols, row_of_dp=row_of_dp, timings=timings)
-        state.update(ndps=int(keep.sum()), nseg=fb.nseg, ncols=fb.ncols, prof=res.profile, nclusters=len(res.recs), nbins=len(set(res.scaf2cluster.tolist()) - {0}),
-                     seg_len=(sg["seg_end"] - sg["seg_start"] + 1), rows_bytes=0 if rows_host is None else rows_host.nbytes, bins=res.scaf2cluster)
+        if world == 1:
+            row_of_dp = None if keep.all() else np.nonzero(keep)[0].astype(np.uint64)   # scaffolds with one window are dropped (ScafDpData.cpp:92-93)
+            res = pipeline.search(ctx, fb.d_rows, dp2scaf, T, lengths[kept], masks[kept], layout=capi.LAYOUT_ROWMAJOR, values_on_device=True,
+                                  nrows=fb.nseg, D=fb.ncols, ld=fb.ncols, row_of_dp=row_of_dp, timings=timings)
+            nbins = len(set(res.scaf2cluster.tolist()) - {0})
+            ndps_total = int(keep.sum())
+        else:
+            # 1) every rank holds the rows of its own scaffolds: all-gather them (NCCL) so that every rank has all datapoints
+            local = torch.as_tensor(distributed._DevArray(fb.d_rows, fb.nseg * fb.ncols * 8, "<f8", 8), device=dev).view(fb.nseg, fb.ncols)
+            if not keep.all():
+                local = local[torch.from_numpy(np.nonzero(keep)[0]).to(dev)]
+            meta = torch.tensor([int(keep.sum()), int(kept.size)], dtype=torch.int64, device=dev)
+            metas = torch.empty(2 * world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(metas, meta)
+            metas = metas.cpu().numpy().reshape(world, 2)
+            full = distributed.allgather_rows(torch, dist, local.contiguous(), [int(x) for x in metas[:, 0]])
+            # 2) per-scaffold tables of all ranks (T, length, SCG mask); scaffold ids are rank-major
+            sc = np.stack([T.astype(np.int64), lengths[kept].astype(np.int64), masks[kept][:, 0].astype(np.int64)], axis=1)
+            sc_all = distributed.allgather_rows(torch, dist, torch.from_numpy(sc).to(dev), [int(x) for x in metas[:, 1]]).cpu().numpy()
+            T_all = sc_all[:, 0].astype(np.uint32)
+            dp2scaf_all = np.repeat(np.arange(T_all.size, dtype=np.uint32), T_all)
+            torch.cuda.synchronize(dev)
+            # 3) dimension-sharded search: this rank sweeps columns [off, off+cnt) of every datapoint
+            off, cnt = distributed.dim_block(fb.ncols, rank, world)
+            res = pipeline.search(ctx, full.data_ptr() + 8 * off, dp2scaf_all, T_all, sc_all[:, 1].astype(np.uint64), sc_all[:, 2].astype(np.uint64),
+                                  layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=int(full.shape[0]), D=cnt, ld=fb.ncols, timings=timings,
+                                  collectives=coll, dim_offset=off, D_total=fb.ncols)
+            nbins = len(set(res.scaf2cluster.tolist()) - {0})
+            ndps_total = int(full.shape[0])
+            del full
+        state.update(ndps=ndps_total, nseg=fb.nseg, ncols=fb.ncols, prof=res.profile, nclusters=len(res.recs), nbins=nbins,
+                     seg_len=(sg["seg_end"] - sg["seg_start"] + 1), bins=res.scaf2cluster)
         fb.close()
         return res
 
@@ -345,19 +377,17 @@ def main():
     # .lrn matrix + window table + per-scaffold bins + per-datapoint bins
     d2h = state["nseg"] * state["ncols"] * 8 + state["nseg"] * (4 + 3 * 8) + (nscaf + 1) * 8 + nscaf * 4 + state["nseg"] * 4
 
-    bins_total = state["nbins"]
-    if world > 1:
-        t = torch.tensor([bins_total], device="cuda")
-        dist.all_reduce(t)                            # NCCL: gather of per-shard bin counts only
-        bins_total = int(t.item())
+    bins_total = state["nbins"]                       # every rank ends with the bins of the whole community
 
     line = {"metric": "scaffolds/sec binned (feature build + split search)", "value": round(value, 2), "unit": "scaffolds/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/int64/f64", "data": "synthetic",
             "config": {"workload": workload_name(w), "per_gpu": f"{nscaf} scaffolds, {total_bp} bp, {state['nseg']} windows x {state['ncols']} dimensions, {sum(nreads)} read records",
-                       "parallelism": f"{world} independent assemblies, one per GPU" if world > 1 else "1 GPU",
+                       "parallelism": (f"one community of {world} x {nscaf} scaffolds: scaffold-sharded feature build, NCCL all-gather of feature rows, "
+                                       f"dimension-sharded split search ({state['ncols']} dimensions over {world} ranks)") if world > 1 else "1 GPU",
                        "l2": "inputs (assembly + read records, > 2 GB) are larger than the 126 MB L2; no explicit flush",
-                       "clusters_evaluated": state["nclusters"], "bins": bins_total, "search_levels": prof.levels},
+                       "clusters_evaluated": state["nclusters"], "bins": bins_total, "search_levels": prof.levels, "datapoints": state["ndps"],
+                       "nccl": None if coll is None else {"callback_collectives_total": coll.calls, "callback_bytes_total": coll.bytes}},
             "e2e": {"value": round(e2e_value, 2), "unit": "scaffolds/s", "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "phase_wall_ms": {k: round(v, 3) for k, v in phase_ms.items()},

@@ -62,7 +62,7 @@ EXPORTS = [
     "abw_ctx_synchronize", "abw_profile_enable", "abw_profile_report", "abw_pack_sequences", "abw_seqset_destroy", "abw_seqset_stats", "abw_segment", "abw_segments_destroy",
     "abw_segments_count", "abw_segments_get", "abw_kmer_features", "abw_coverage", "abw_device_alloc", "abw_device_free",
     "abw_copy_to_device", "abw_copy_to_host", "abw_memset_device", "abw_h2d_async", "abw_wait_h2d", "abw_search_create", "abw_search_destroy", "abw_search_run",
-    "abw_search_set_shard", "abw_search_run_sharded", "abw_search_get_profile", "abw_cluster_scg",
+    "abw_search_set_shard", "abw_search_set_max_levels", "abw_search_run_sharded", "abw_search_get_profile", "abw_cluster_scg",
 ]
 
 
@@ -108,6 +108,7 @@ def load():
                                     C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     L.abw_search_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p]
     L.abw_search_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    L.abw_search_set_max_levels.argtypes = [C.c_void_p, C.c_uint32]
     L.abw_search_run_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p]
     L.abw_search_get_profile.argtypes = [C.c_void_p, C.c_void_p]
     L.abw_cluster_scg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_double)]

@@ -1052,6 +1052,7 @@ struct abw_search {
 	uint32_t root_viol = 0;
 	std::vector<uint64_t> root_never;
 	bool consumed = false;
+	uint32_t max_levels = 0;                  // 0: run to the end; k: stop after k levels, the pending children become the bins
 	uint32_t dim_offset = 0, D_total = 0;     // sharded search: this object holds dimensions [dim_offset, dim_offset + D) of D_total
 	abw_search_profile prof{};
 };
@@ -1399,6 +1400,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 
 	while(!level.empty()) {
 		s->prof.levels++;
+		const bool last_level = s->max_levels > 0 && s->prof.levels >= s->max_levels;
 		const uint32_t C = (uint32_t)level.size();
 		// pass-table offsets
 		uint32_t tab_total = 0;
@@ -1698,10 +1700,16 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 				dim3 g(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), P);
 				ABW_LAUNCH(ctx, k_commit_assigned, g, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs.p, s->new_assigned.p, s->assigned.p);
 				ABW_LAUNCH(ctx, k_partition_list, dim3(P, 1), 256, 0, s->scaf_list[cur].p, s->scaf_list[cur ^ 1].p, (uint64_t)S, d_ljobs_scaf.p, s->side.p);
-				if(s->strategy == ABW_SENS_SPEC && s->K > 0)
+				if(s->strategy == ABW_SENS_SPEC && s->K > 0 && !last_level)
 					ABW_LAUNCH(ctx, k_partition_list, dim3(P, D), 256, 0, s->scg_list[cur].p, s->scg_list[cur ^ 1].p, (uint64_t)s->K, d_ljobs_scg.p, s->side.p);
 			}
 			s->prof.other_ms += tm.stop();
+			if(last_level) {
+				// the children are not going to be evaluated: only their scaffold lists are needed (for the bins)
+				cur ^= 1;
+				level.swap(next);
+				break;
+			}
 			std::vector<uint2> ptile_tab;
 			for(uint32_t i = 0; i < P; i++) {
 				const uint32_t tiles = (pjobs[i].n + SW_TILE - 1) / SW_TILE;
@@ -1723,6 +1731,26 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 			cur ^= 1;
 		}
 		level.swap(next);
+		if(last_level)
+			break;
+	}
+	if(!level.empty()) {
+		// level limit reached: the pending clusters are reported as bins (their ids) without being evaluated
+		std::vector<TermJob> tjobs;
+		for(const HostCluster& hc : level) {
+			TermJob tj;
+			tj.sOff = hc.desc.sOff; tj.ns = hc.desc.ns; tj.id = hc.id; tj.slot = (uint32_t)tjobs.size();
+			tjobs.push_back(tj);
+		}
+		const uint32_t Tn = (uint32_t)tjobs.size();
+		ABW_CHECK(to_device(ctx, d_tjobs, tjobs));
+		if(d_tstats.n < Tn) ABW_CUDA(ctx, d_tstats.alloc(Tn));
+		if(d_union.n < (size_t)Tn * W) ABW_CUDA(ctx, d_union.alloc((size_t)Tn * W));
+		ABW_CUDA(ctx, cudaMemsetAsync(d_tstats.p, 0, sizeof(TermStats) * Tn, ctx->stream));
+		ABW_CUDA(ctx, cudaMemsetAsync(d_union.p, 0, sizeof(uint64_t) * Tn * W, ctx->stream));
+		dim3 g(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), Tn);
+		ABW_LAUNCH(ctx, k_finalize_terminal, g, 128, 0, s->scaf_list[cur].p, d_tjobs.p, s->rows.p, s->assigned.p, s->scgmask.p, W, s->scaf_member.p, s->scaf_final.p,
+		           d_tstats.p, d_union.p);
 	}
 	if(nrecs)
 		*nrecs = nrec;
@@ -1802,6 +1830,14 @@ int abw_search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_run: null argument");
 	ABW_ENTER(ctx);
 	return search_run(ctx, s, nullptr, h_recs, cap, nrecs, h_dp2cluster, h_scaf2cluster);
+}
+
+int abw_search_set_max_levels(abw_search* s, uint32_t max_levels)
+{
+	if(!s)
+		return ABW_ERR_ARG;
+	s->max_levels = max_levels;
+	return ABW_OK;
 }
 
 int abw_search_set_shard(abw_search* s, uint32_t dim_offset, uint32_t D_total)

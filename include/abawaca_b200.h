@@ -191,6 +191,11 @@ int abw_search_set_shard(abw_search* s, uint32_t dim_offset, uint32_t D_total);
 int abw_search_run_sharded(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_cluster_rec* h_recs, uint32_t cap, uint32_t* nrecs,
                            uint32_t* h_dp2cluster, uint32_t* h_scaf2cluster);
 
+/* Stop after `max_levels` levels of the breadth-first search (0 = run to the end).  With 1 this is exactly one
+ * ClusterSeparator::separate() call on the root: record 0 describes the split and dp2cluster/scaf2cluster hold the ids of
+ * the two children (2 = cluster1, 3 = cluster2), which is what a per-cluster adapter needs. */
+int abw_search_set_max_levels(abw_search* s, uint32_t max_levels);
+
 /* Timing of the last abw_search_run, in milliseconds of device time per kernel family (CUDA events on the context stream) */
 typedef struct {
 	float build_ms;       /* abw_search_create: key transform, sort, element packing */

@@ -24,6 +24,10 @@
 #include "Semaphore.h"
 #include "ClusterSeparatorBySensitivitySpecificity.h"
 #include "ClusterSeparatorSplitScafs.h"
+#ifdef ABW_GPU_ADAPTER
+// same driver, but every separate() call goes to libabawaca_b200.so through the drop-in adapter (ref_gpu_adapter.h)
+#include "ref_gpu_adapter.h"
+#endif
 
 int main(int argc, char** argv)
 {
@@ -47,6 +51,13 @@ int main(int argc, char** argv)
 	ClusterQuality	cq(scaf_db, scg_db);
 
 	fprintf(out, "#N\t%lu\tS\t%lu\tD\t%lu\n", scaf_db.ndps(), scaf_db.nscafs(), all_data.ndimensions());
+#ifdef ABW_GPU_ADAPTER
+	abw_ctx* gpu = NULL;
+	if(abw_ctx_create(0, &gpu) != ABW_OK) {
+		fprintf(stderr, "no usable CUDA device\n");
+		return 3;
+	}
+#endif
 
 	std::map<size_t, Cluster*> work;
 	std::map<size_t, size_t> scaf_bin;
@@ -66,10 +77,17 @@ int main(int argc, char** argv)
 		ClusterData* sub = new ClusterData(all_data, cur->get_dps());
 
 		ClusterSeparator* sep;
+#ifdef ABW_GPU_ADAPTER
+		if(splitscafs)
+			sep = new ClusterSeparatorGPUSplitScafs(gpu, scaf_db, scg_db, *sub, sem);
+		else
+			sep = new ClusterSeparatorGPUSensSpec(gpu, scaf_db, scg_db, *sub, sem);
+#else
 		if(splitscafs)
 			sep = new ClusterSeparatorSplitScafs(scaf_db, scg_db, *sub, sem);
 		else
 			sep = new ClusterSeparatorBySensitivitySpecificity(scaf_db, scg_db, *sub, sem);
+#endif
 		bool split = sep->separate();
 
 		double a = 0, b = 0;

@@ -228,8 +228,8 @@ __device__ uint32_t g_dim_tab[ABW_NKMER_DIMS];              // k | code_a << 8 |
 __device__ double   g_milli[1001];                          // m / 1000.0
 
 constexpr int KM_WARPS = 8;
-constexpr int KM_WORDS_PER_LANE = 7;                        // 16-base words per lane per round: <= 112 increments per byte counter
-constexpr int KM_ROUND_WORDS = 32 * KM_WORDS_PER_LANE;      // 224 words = 3584 bases per round
+constexpr int KM_GROUPS = 8;                                // sub-histograms per warp: lanes 4g..4g+3 share one
+constexpr int KM_ROUND_WORDS = 224;                         // 16-base words staged per round (3584 bases)
 constexpr int KM_STAGE_WORDS = KM_ROUND_WORDS + 2;          // + lookahead word + alignment slack
 
 struct __align__(16) KmBlockSmem {
@@ -237,8 +237,11 @@ struct __align__(16) KmBlockSmem {
 	uint32_t dim_tab[ABW_NKMER_DIMS];
 };
 
+// Per warp.  hist is bin-major and interleaved by group: word = bin * 8 + group, so two lanes can only hit the same bank when they are
+// in the same group of four (round-1 micro-benchmark scripts/ubench_hist.cu: 14 updates/clk/SM with fire-and-forget shared atomics,
+// against 8.6 for the byte load/add/store chain the first version used).
 struct __align__(16) KmWarpSmem {
-	uint32_t hist[64 * 32];         // [3-mer row][lane] four byte counters (4th base) : 8 KB, bank = lane
+	uint32_t hist[256 * KM_GROUPS];
 	uint32_t seq[KM_STAGE_WORDS + 2];
 	uint32_t val[KM_STAGE_WORDS / 2 + 4];
 	uint32_t cnt4[256];
@@ -273,19 +276,17 @@ __global__ void __launch_bounds__(KM_WARPS * 32) k_kmer(const uint32_t* __restri
 		bs->milli[i] = g_milli[i];
 	for(int i = threadIdx.x; i < ABW_NKMER_DIMS; i += blockDim.x)
 		bs->dim_tab[i] = g_dim_tab[i];
-	for(int i = lane; i < 64 * 32; i += 32)
+	for(int i = lane; i < 256 * KM_GROUPS; i += 32)
 		sm->hist[i] = 0;
 	__syncthreads();
+	uint32_t* const myhist = sm->hist + (lane >> 2);        // + bin * 8
 	const uint64_t warp0 = (uint64_t)blockIdx.x * KM_WARPS + (threadIdx.x >> 5), nwarps = (uint64_t)gridDim.x * KM_WARPS;
 	for(uint64_t g = warp0; g < nseg; g += nwarps) {
 		const uint64_t gb = seg_gbase[g];
 		const uint64_t L = seg_end[g] - seg_start[g] + 1;
-		for(int i = lane; i < 256; i += 32)
-			sm->cnt4[i] = 0;
 		for(int i = lane; i < 64 + 16 + 4 + 4; i += 32)
-			sm->cnt3[i] = 0;                                // cnt3, cnt2, cnt1, tot are contiguous
+			sm->cnt3[i] = 0;                                // cnt3, cnt2, cnt1, tot are contiguous: these receive the run-end windows
 		__syncwarp();
-		// rounds of at most KM_ROUND_WORDS 16-base words of the packed stream
 		const uint64_t word_first = gb >> 4;
 		const uint64_t nwords = ((gb + L + 15) >> 4) - word_first;
 		for(uint64_t w0 = 0; w0 < nwords; w0 += KM_ROUND_WORDS) {
@@ -293,11 +294,10 @@ __global__ void __launch_bounds__(KM_WARPS * 32) k_kmer(const uint32_t* __restri
 			// stage packed words (+1 lookahead) and validity bits of [w0, w0+rw] into shared memory
 			for(uint32_t i = lane; i < rw + 1; i += 32)
 				sm->seq[i] = packed[word_first + w0 + i];
-			// validity as a bit stream aligned to the same 16-base words: 16 bits per word -> (rw+1)*16 bits
 			const uint64_t vbit0 = (word_first + w0) << 4;   // absolute base index of the first staged position
 			for(uint32_t i = lane; i < (rw + 1 + 1) / 2 + 1; i += 32) {
 				uint64_t p = vbit0 + ((uint64_t)i << 5);      // 32 positions
-				uint32_t v = valid[p >> 5];                   // vbit0 is a multiple of 16; p>>5 word, possibly half offset
+				uint32_t v = valid[p >> 5];
 				uint32_t v2 = valid[(p >> 5) + 1];
 				v = __funnelshift_r(v, v2, (uint32_t)(p & 31));
 				// positions outside [gb, gb+L) never hold a base of this segment
@@ -307,90 +307,88 @@ __global__ void __launch_bounds__(KM_WARPS * 32) k_kmer(const uint32_t* __restri
 				sm->val[i] = v & m_lo & m_hi;
 			}
 			__syncwarp();
-			const uint32_t wpl = (rw + 31) >> 5;              // words per lane this round (<= KM_WORDS_PER_LANE)
-			uint32_t* myhist = sm->hist + lane;
-			for(uint32_t k = lane * wpl; k < min(rw, (lane + 1) * wpl); k++) {
-				const uint64_t win = (uint64_t)sm->seq[k] | ((uint64_t)sm->seq[k + 1] << 32);
+			// main loop: lane l takes words l, l+32, ...; a word whose 16 windows are all valid costs 16 shared atomics, anything else is deferred
+			uint32_t pending = 0;                             // bit j: word lane + 32*j is partial
+			for(uint32_t j = 0, k = lane; k < rw; j++, k += 32) {
 				const uint32_t v = stream_bits(sm->val, (uint64_t)k << 4, 19);   // 16 positions + 3 lookahead
-				const uint32_t v1 = v & 0xFFFFu, v2 = v & (v >> 1) & 0xFFFFu, v3 = v2 & (v >> 2), v4 = v3 & (v >> 3);
+				const uint32_t v4 = v & (v >> 1) & (v >> 2) & (v >> 3) & 0xFFFFu;
 				if(v4 == 0xFFFFu) {
+					const uint64_t win = (uint64_t)sm->seq[k] | ((uint64_t)sm->seq[k + 1] << 32);
 #pragma unroll
 					for(int t = 0; t < 16; t++) {
-						uint32_t x = (uint32_t)(win >> (2 * t)) & 0xFFu;
-						unsigned char* b = reinterpret_cast<unsigned char*>(myhist + (x & 63u) * 32) + (x >> 6);
-						*b = (unsigned char)(*b + 1);
+						const uint32_t x = (uint32_t)(win >> (2 * t)) & 0xFFu;
+						atomicAdd(myhist + x * KM_GROUPS, 1u);
 					}
 				}
-				else {
-					// windows broken by a non-ACGT character or by the end of the segment (:131,147 key = 0)
-					const uint32_t e3 = v3 & ~v4, e2 = v2 & ~v3, e1 = v1 & ~v2;
-#pragma unroll
-					for(int t = 0; t < 16; t++) {
-						uint32_t x = (uint32_t)(win >> (2 * t)) & 0xFFu;
-						if((v4 >> t) & 1u) {
-							unsigned char* b = reinterpret_cast<unsigned char*>(myhist + (x & 63u) * 32) + (x >> 6);
-							*b = (unsigned char)(*b + 1);
-						}
-						else if((e3 >> t) & 1u)
-							atomicAdd(&sm->cnt3[x & 63u], 1u);
-						else if((e2 >> t) & 1u)
-							atomicAdd(&sm->cnt2[x & 15u], 1u);
-						else if((e1 >> t) & 1u)
-							atomicAdd(&sm->cnt1[x & 3u], 1u);
-					}
-				}
+				else if(v & 0xFFFFu)
+					pending |= 1u << j;                       // windows broken by a non-ACGT character or by the end of the segment (:131,147 key = 0)
 			}
-			__syncwarp();
-			// fold the 32 private histograms into cnt4 and clear them; lane handles 3-mer rows lane and lane+32
-#pragma unroll
-			for(int rr = 0; rr < 2; rr++) {
-				const int row = lane + 32 * rr;
-				uint4* rp = reinterpret_cast<uint4*>(sm->hist + row * 32);
-				uint32_t even = 0, odd = 0;
-#pragma unroll
-				for(int q = 0; q < 8; q++) {
-					int qq = (q + lane) & 7;                  // rotate so that a quarter warp touches 8 different 16-byte columns
-					uint4 w = rp[qq];
-					rp[qq] = make_uint4(0, 0, 0, 0);
-					uint32_t a = w.x + w.y, b = w.z + w.w;    // byte counters <= 112 each: no carry between bytes
-					even += (a & 0x00FF00FFu) + (b & 0x00FF00FFu);
-					odd += ((a >> 8) & 0x00FF00FFu) + ((b >> 8) & 0x00FF00FFu);
+			// partial words, one at a time, sixteen lanes each taking one position
+			for(;;) {
+				const uint32_t who = __ballot_sync(0xffffffffu, pending != 0);
+				if(who == 0)
+					break;
+				const int src = __ffs(who) - 1;
+				const uint32_t pj = __shfl_sync(0xffffffffu, pending, src);
+				const uint32_t j = (uint32_t)(__ffs(pj) - 1);
+				if(lane == src)
+					pending &= pending - 1;
+				const uint32_t k = (uint32_t)src + 32 * j;
+				if(lane < 16) {
+					const uint32_t v = stream_bits(sm->val, ((uint64_t)k << 4) + lane, 4);
+					const uint64_t win = (uint64_t)sm->seq[k] | ((uint64_t)sm->seq[k + 1] << 32);
+					const uint32_t x = (uint32_t)(win >> (2 * lane)) & 0xFFu;
+					if((v & 15u) == 15u)
+						atomicAdd(myhist + x * KM_GROUPS, 1u);
+					else if((v & 7u) == 7u)
+						atomicAdd(&sm->cnt3[x & 63u], 1u);
+					else if((v & 3u) == 3u)
+						atomicAdd(&sm->cnt2[x & 15u], 1u);
+					else if(v & 1u)
+						atomicAdd(&sm->cnt1[x & 3u], 1u);
 				}
-				sm->cnt4[row] += even & 0xFFFFu;              // 4th base A
-				sm->cnt4[row + 64] += odd & 0xFFFFu;          // C
-				sm->cnt4[row + 128] += even >> 16;            // G
-				sm->cnt4[row + 192] += odd >> 16;             // T
 			}
 			__syncwarp();
 		}
-		// lower orders: every valid 4-mer start is a valid 3-mer start, etc.; cnt3/cnt2/cnt1 hold the run-end extras
+		// fold the sub-histograms: lane l owns bins l, l+32, ..., l+224 (eight consecutive words each) and clears them
 		{
-			uint32_t a = sm->cnt4[lane] + sm->cnt4[lane + 64] + sm->cnt4[lane + 128] + sm->cnt4[lane + 192];
-			uint32_t b = sm->cnt4[lane + 32] + sm->cnt4[lane + 96] + sm->cnt4[lane + 160] + sm->cnt4[lane + 224];
-			uint32_t t4 = a + b;
+			uint32_t t4 = 0;
+#pragma unroll
+			for(int j = 0; j < 8; j++) {
+				const int bin = lane + 32 * j;
+				uint4* hp = reinterpret_cast<uint4*>(sm->hist + bin * KM_GROUPS);
+				const uint4 a = hp[0], b = hp[1];
+				hp[0] = make_uint4(0, 0, 0, 0);
+				hp[1] = make_uint4(0, 0, 0, 0);
+				const uint32_t c = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+				sm->cnt4[bin] = c;
+				t4 += c;
+			}
 #pragma unroll
 			for(int o = 16; o > 0; o >>= 1)
 				t4 += __shfl_xor_sync(0xffffffffu, t4, o);
+			__syncwarp();
+			// lower orders: every valid 4-mer start is a valid 3-mer start, etc.; cnt3/cnt2/cnt1 hold the run-end extras
+			uint32_t a = sm->cnt4[lane] + sm->cnt4[lane + 64] + sm->cnt4[lane + 128] + sm->cnt4[lane + 192];
+			uint32_t b = sm->cnt4[lane + 32] + sm->cnt4[lane + 96] + sm->cnt4[lane + 160] + sm->cnt4[lane + 224];
 			sm->cnt3[lane] += a;
 			sm->cnt3[lane + 32] += b;
 			__syncwarp();
-			uint32_t c3a = sm->cnt3[lane], c3b = sm->cnt3[lane + 32];
-			uint32_t t3 = c3a + c3b;
+			uint32_t t3 = sm->cnt3[lane] + sm->cnt3[lane + 32];
 #pragma unroll
 			for(int o = 16; o > 0; o >>= 1)
 				t3 += __shfl_xor_sync(0xffffffffu, t3, o);
 			if(lane < 16)
 				sm->cnt2[lane] += sm->cnt3[lane] + sm->cnt3[lane + 16] + sm->cnt3[lane + 32] + sm->cnt3[lane + 48];
 			__syncwarp();
-			uint32_t c2 = (lane < 16)? sm->cnt2[lane] : 0u;
-			uint32_t t2 = c2;
+			uint32_t t2 = (lane < 16)? sm->cnt2[lane] : 0u;
 #pragma unroll
 			for(int o = 16; o > 0; o >>= 1)
 				t2 += __shfl_xor_sync(0xffffffffu, t2, o);
 			if(lane < 4)
 				sm->cnt1[lane] += sm->cnt2[lane] + sm->cnt2[lane + 4] + sm->cnt2[lane + 8] + sm->cnt2[lane + 12];
 			__syncwarp();
-			uint32_t t1 = sm->cnt1[0] + sm->cnt1[1] + sm->cnt1[2] + sm->cnt1[3];
+			const uint32_t t1 = sm->cnt1[0] + sm->cnt1[1] + sm->cnt1[2] + sm->cnt1[3];
 			if(lane == 0) {
 				sm->tot[0] = t1; sm->tot[1] = t2; sm->tot[2] = t3; sm->tot[3] = t4;
 			}

@@ -445,56 +445,137 @@ __device__ __forceinline__ bool read_accepted(const abw_read& r, uint32_t max_sn
 	return !((flag & 0x4u) || (nsnps > max_snps) || (flag & 0x100u)) && r.scaf < nscaf;   // :546-550
 }
 
-// first window of the scaffold whose end is >= s (windows before it are skipped by `continue`, :235-236)
-__device__ __forceinline__ uint64_t first_window_reaching(const uint64_t* __restrict__ seg_end, uint64_t f0, uint64_t f1, uint64_t s)
+// windows [g0, g0 + cnt) hit by an accepted read: first window of the scaffold whose end is >= s, up to the last one whose start is <= e.
+// Windows of a scaffold hold the same number of non-N bases, so window (s-1)/nbps is the answer unless a run of N shifted it (then: binary search).
+__device__ __forceinline__ void read_windows(const abw_read& rd, uint32_t max_snps, uint32_t nscaf, const uint64_t* __restrict__ seg_first, const uint64_t* __restrict__ seg_start,
+                                             const uint64_t* __restrict__ seg_end, const uint64_t* __restrict__ seg_nonN, uint64_t& g0, uint32_t& cnt)
 {
-	uint64_t lo = f0, hi = f1;
-	while(lo < hi) {
-		uint64_t mid = (lo + hi) >> 1;
-		if(seg_end[mid] < s) lo = mid + 1; else hi = mid;
-	}
-	return lo;
-}
-
-__global__ void k_cov_count(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf, const uint64_t* __restrict__ seg_first,
-                            const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end, uint32_t* __restrict__ counts,
-                            unsigned long long* __restrict__ scaf_nbps)
-{
-	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(r >= nreads)
-		return;
-	abw_read rd = reads[r];
-	uint32_t c = 0;
-	if(read_accepted(rd, max_snps, nscaf)) {
-		uint64_t s = rd.pos0, e = (uint64_t)rd.pos0 + rd.len - 1;
-		uint64_t f1 = seg_first[rd.scaf + 1];
-		for(uint64_t g = first_window_reaching(seg_end, seg_first[rd.scaf], f1, s); g < f1 && !(e < seg_start[g]); g++)
-			c++;
-		if(scaf_nbps != nullptr)
-			atomicAdd(&scaf_nbps[rd.scaf], (unsigned long long)rd.len);     // integer: order free (:242-243)
-	}
-	counts[r] = c;
-}
-
-__global__ void k_cov_emit(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf, const uint64_t* __restrict__ seg_first,
-                           const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end, const uint64_t* __restrict__ offs,
-                           uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ per_seg)
-{
-	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(r >= nreads)
-		return;
-	abw_read rd = reads[r];
+	cnt = 0;
+	g0 = 0;
 	if(!read_accepted(rd, max_snps, nscaf))
 		return;
-	uint64_t s = rd.pos0, e = (uint64_t)rd.pos0 + rd.len - 1, o = offs[r];
-	uint64_t f1 = seg_first[rd.scaf + 1];
-	for(uint64_t g = first_window_reaching(seg_end, seg_first[rd.scaf], f1, s); g < f1 && !(e < seg_start[g]); g++) {
-		const uint64_t st = seg_start[g], en = seg_end[g];
-		const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // 0-based read against 1-based window: quirk Q3, kept (:182-183)
-		keys[o] = (uint32_t)g;
-		vals[o] = (uint32_t)(e2 - s2 + 1);                             // the overlap travels with the pair: no gather after the sort
-		o++;
-		atomicAdd(&per_seg[g], 1u);
+	const uint64_t s = rd.pos0, e = (uint64_t)rd.pos0 + rd.len - 1;
+	const uint64_t f0 = __ldg(seg_first + rd.scaf), f1 = __ldg(seg_first + rd.scaf + 1);
+	if(f0 >= f1)
+		return;
+	const uint64_t nbps = max((unsigned long long)__ldg(seg_nonN + f0), 1ull);      // an all-N scaffold has one window per character
+	uint64_t g = (s > 0)? min(f1 - 1, f0 + (s - 1) / nbps) : f0;
+	if(!((g == f0 || __ldg(seg_end + g - 1) < s) && __ldg(seg_end + g) >= s)) {
+		uint64_t lo = f0, hi = f1;                          // runs of N moved the boundaries: binary search
+		while(lo < hi) {
+			const uint64_t mid = (lo + hi) >> 1;
+			if(__ldg(seg_end + mid) < s) lo = mid + 1; else hi = mid;
+		}
+		g = lo;                                             // windows before it are skipped by `continue`, :235-236
+	}
+	g0 = g;
+	while(g < f1 && !(e < __ldg(seg_start + g))) {
+		cnt++;
+		g++;
+	}
+}
+
+constexpr int COV_THREADS = 256;
+constexpr int COV_ITEMS = 4;                                // consecutive reads per thread
+constexpr int COV_TILE = COV_THREADS * COV_ITEMS;
+
+// pass 1: (window, read) pairs per tile of COV_TILE reads; per-scaffold read bases of the -c sample
+__global__ void __launch_bounds__(COV_THREADS) k_cov_count(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf,
+                                                          const uint64_t* __restrict__ seg_first, const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end,
+                                                          const uint64_t* __restrict__ seg_nonN, uint32_t* __restrict__ tile_counts, unsigned long long* __restrict__ scaf_nbps)
+{
+	__shared__ uint32_t sm[COV_THREADS / 32];
+	const uint64_t r0 = (uint64_t)blockIdx.x * COV_TILE + (uint64_t)threadIdx.x * COV_ITEMS;
+	abw_read rd[COV_ITEMS];
+#pragma unroll
+	for(int j = 0; j < COV_ITEMS; j++) {
+		if(r0 + j < nreads) {
+			const uint4 x = __ldg(reinterpret_cast<const uint4*>(reads + r0 + j));
+			rd[j].scaf = x.x; rd[j].pos0 = x.y; rd[j].len = x.z; rd[j].flag_nsnps = x.w;
+		}
+		else {
+			rd[j].scaf = 0xFFFFFFFFu; rd[j].pos0 = 0; rd[j].len = 0; rd[j].flag_nsnps = 0;
+		}
+	}
+	uint32_t c = 0;
+#pragma unroll
+	for(int j = 0; j < COV_ITEMS; j++) {
+		uint64_t g0;
+		uint32_t cj;
+		read_windows(rd[j], max_snps, nscaf, seg_first, seg_start, seg_end, seg_nonN, g0, cj);
+		c += cj;
+		if(scaf_nbps != nullptr && read_accepted(rd[j], max_snps, nscaf))
+			atomicAdd(&scaf_nbps[rd[j].scaf], (unsigned long long)rd[j].len);     // integer: order free (:242-243)
+	}
+	c = __reduce_add_sync(0xffffffffu, c);
+	if((threadIdx.x & 31) == 0)
+		sm[threadIdx.x >> 5] = c;
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		uint32_t t = 0;
+#pragma unroll
+		for(int w = 0; w < COV_THREADS / 32; w++)
+			t += sm[w];
+		tile_counts[blockIdx.x] = t;
+	}
+}
+
+// pass 2: the pairs, in read order (then window order): key = window, value = overlap
+__global__ void __launch_bounds__(COV_THREADS) k_cov_emit(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf,
+                                                         const uint64_t* __restrict__ seg_first, const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end,
+                                                         const uint64_t* __restrict__ seg_nonN, const uint64_t* __restrict__ tile_offs, uint32_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ vals, uint32_t* __restrict__ per_seg)
+{
+	__shared__ uint32_t sm[COV_THREADS / 32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint64_t r0 = (uint64_t)blockIdx.x * COV_TILE + (uint64_t)threadIdx.x * COV_ITEMS;
+	abw_read rd[COV_ITEMS];
+#pragma unroll
+	for(int j = 0; j < COV_ITEMS; j++) {
+		if(r0 + j < nreads) {
+			const uint4 x = __ldg(reinterpret_cast<const uint4*>(reads + r0 + j));
+			rd[j].scaf = x.x; rd[j].pos0 = x.y; rd[j].len = x.z; rd[j].flag_nsnps = x.w;
+		}
+		else {
+			rd[j].scaf = 0xFFFFFFFFu; rd[j].pos0 = 0; rd[j].len = 0; rd[j].flag_nsnps = 0;
+		}
+	}
+	uint64_t g0[COV_ITEMS];
+	uint32_t cj[COV_ITEMS];
+	uint32_t c = 0;
+#pragma unroll
+	for(int j = 0; j < COV_ITEMS; j++) {
+		read_windows(rd[j], max_snps, nscaf, seg_first, seg_start, seg_end, seg_nonN, g0[j], cj[j]);
+		c += cj[j];
+	}
+	uint32_t incl = c;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+		if(lane >= o)
+			incl += t;
+	}
+	if(lane == 31)
+		sm[warp] = incl;
+	__syncthreads();
+	uint32_t wex = 0;
+#pragma unroll
+	for(int w = 0; w < COV_THREADS / 32; w++)
+		if(w < warp)
+			wex += sm[w];
+	uint64_t o = tile_offs[blockIdx.x] + wex + incl - c;
+#pragma unroll
+	for(int j = 0; j < COV_ITEMS; j++) {
+		const uint64_t s = rd[j].pos0, e = (uint64_t)rd[j].pos0 + rd[j].len - 1;
+		for(uint32_t k = 0; k < cj[j]; k++) {
+			const uint64_t g = g0[j] + k;
+			const uint64_t st = __ldg(seg_start + g), en = __ldg(seg_end + g);
+			const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // 0-based read against 1-based window: quirk Q3, kept (:182-183)
+			keys[o] = (uint32_t)g;
+			vals[o] = (uint32_t)(e2 - s2 + 1);                             // the overlap travels with the pair: no gather after the sort
+			o++;
+			atomicAdd(&per_seg[g], 1u);
+		}
 	}
 }
 
@@ -760,19 +841,20 @@ int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uin
 		ABW_CUDA(ctx, cudaMemcpyAsync(d_reads.p, reads, sizeof(abw_read) * nreads, cudaMemcpyHostToDevice, ctx->stream));
 		rd = d_reads.p;
 	}
-	DevBuf<uint32_t> counts, per_seg, keys, keys_tmp, vals, vals_tmp;
-	DevBuf<uint64_t> offs, seg_off, total;
-	ABW_CUDA(ctx, counts.alloc(nreads));
-	ABW_CUDA(ctx, offs.alloc(nreads));
+	DevBuf<uint32_t> tile_counts, per_seg, keys, keys_tmp, vals, vals_tmp;
+	DevBuf<uint64_t> tile_offs, seg_off, total;
+	const unsigned int ntiles = abw_div_up(nreads, COV_TILE);
+	ABW_CUDA(ctx, tile_counts.alloc(ntiles));
+	ABW_CUDA(ctx, tile_offs.alloc(ntiles));
 	ABW_CUDA(ctx, total.alloc(1));
 	ABW_CUDA(ctx, per_seg.alloc(g->nseg));
 	ABW_CUDA(ctx, seg_off.alloc(g->nseg + 1));
 	ABW_CUDA(ctx, cudaMemsetAsync(per_seg.p, 0, sizeof(uint32_t) * g->nseg, ctx->stream));
 	uint64_t npairs = 0;
 	if(nreads) {
-		ABW_LAUNCH(ctx, k_cov_count, abw_div_up(nreads, 256), 256, 0, rd, nreads, max_snps, g->nscaf, g->seg_first.p, g->seg_start.p, g->seg_end.p, counts.p,
+		ABW_LAUNCH(ctx, k_cov_count, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->seg_first.p, g->seg_start.p, g->seg_end.p, g->seg_nonN.p, tile_counts.p,
 		           (unsigned long long*)d_scaf_nbps);
-		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, counts.p, offs.p, nreads, total.p));
+		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, tile_counts.p, tile_offs.p, ntiles, total.p));
 		ABW_CUDA(ctx, cudaMemcpyAsync(&npairs, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
 		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	}
@@ -781,12 +863,13 @@ int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uin
 	ABW_CUDA(ctx, vals.alloc(npairs));
 	ABW_CUDA(ctx, vals_tmp.alloc(npairs));
 	if(npairs) {
-		ABW_LAUNCH(ctx, k_cov_emit, abw_div_up(nreads, 256), 256, 0, rd, nreads, max_snps, g->nscaf, g->seg_first.p, g->seg_start.p, g->seg_end.p, offs.p, keys.p,
+		ABW_LAUNCH(ctx, k_cov_emit, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->seg_first.p, g->seg_start.p, g->seg_end.p, g->seg_nonN.p, tile_offs.p, keys.p,
 		           vals.p, per_seg.p);
 		int nbits = 1;
 		while(nbits < 32 && (1ull << nbits) < g->nseg)
 			nbits++;
-		ABW_CHECK(abw_radix_sort_pairs_u32(ctx, keys.p, keys_tmp.p, vals.p, vals_tmp.p, npairs, 1, npairs, nbits));
+		// window ids are dense: every bit below nbits varies, no need to look
+		ABW_CHECK(abw_radix_sort_pairs_u32(ctx, keys.p, keys_tmp.p, vals.p, vals_tmp.p, npairs, 1, npairs, -nbits));
 	}
 	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, per_seg.p, seg_off.p, g->nseg, seg_off.p + g->nseg));
 	if(g->nseg) {

@@ -255,23 +255,31 @@ int radix_pass(abw_ctx* ctx, const K* src_k, const uint32_t* src_v, K* dst_k, ui
 template <typename K>
 int radix_sort_impl(abw_ctx* ctx, K* d_keys, K* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, uint32_t batch, uint64_t stride, int nbits)
 {
-	if(n == 0 || batch == 0 || nbits <= 0)
+	if(n == 0 || batch == 0 || nbits == 0)
 		return ABW_OK;
 	unsigned int nblocks = abw_div_up(n, RS_TILE);
-	DevBuf<unsigned long long> or_and;
-	ABW_CUDA(ctx, or_and.alloc(2));
-	unsigned long long init[2] = {0ull, ~0ull};
-	ABW_CUDA(ctx, cudaMemcpyAsync(or_and.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-	{
-		dim3 grid(min(nblocks, 4u * (unsigned)ctx->sm_count), batch);
-		ABW_LAUNCH(ctx, k_rs_or_and<K>, grid, RS_THREADS, 0, d_keys, n, stride, or_and.p);
+	unsigned long long varying;
+	if(nbits < 0) {
+		// the caller knows that every key bit below -nbits varies (dense ids): no inspection pass, no host round trip
+		nbits = -nbits;
+		varying = (nbits < 64)? ((1ull << nbits) - 1ull) : ~0ull;
 	}
-	unsigned long long oa[2];
-	ABW_CUDA(ctx, cudaMemcpyAsync(oa, or_and.p, sizeof(oa), cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	unsigned long long varying = oa[0] ^ oa[1];
-	if(nbits < 64)
-		varying &= (1ull << nbits) - 1ull;
+	else {
+		DevBuf<unsigned long long> or_and;
+		ABW_CUDA(ctx, or_and.alloc(2));
+		unsigned long long init[2] = {0ull, ~0ull};
+		ABW_CUDA(ctx, cudaMemcpyAsync(or_and.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+		{
+			dim3 grid(min(nblocks, 4u * (unsigned)ctx->sm_count), batch);
+			ABW_LAUNCH(ctx, k_rs_or_and<K>, grid, RS_THREADS, 0, d_keys, n, stride, or_and.p);
+		}
+		unsigned long long oa[2];
+		ABW_CUDA(ctx, cudaMemcpyAsync(oa, or_and.p, sizeof(oa), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		varying = oa[0] ^ oa[1];
+		if(nbits < 64)
+			varying &= (1ull << nbits) - 1ull;
+	}
 	// plan: cover every varying bit with as few 8- or 9-bit digits as possible (bits that are equal in all keys are skipped)
 	struct Pass { int shift, bits; };
 	Pass plan[16];

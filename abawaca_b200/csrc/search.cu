@@ -31,6 +31,8 @@ constexpr uint32_t EL_CLASS_SHIFT = 27;     // 2 bits: sens/spec: 0 before the f
 constexpr uint32_t EL_AUX_SHIFT = 29;       // 2 bits: sens/spec: bit0 = flip element of an SCG-carrying scaffold
                                             //         split-scafs: position relative to r2
 constexpr uint32_t EL_BOUNDARY = 1u << 31;  // value differs from the previous element of the same cluster
+constexpr uint32_t EL_FLIP_BIT = 1u << EL_CLASS_SHIFT;        // classes are 0, 1, 2: the low class bit is set exactly for class 1 ...
+constexpr uint32_t EL_CLS2_BIT = 2u << EL_CLASS_SHIFT;        // ... and the high one exactly for class 2
 
 struct __align__(16) ScafRow { uint32_t T, n; uint64_t len; };
 
@@ -45,6 +47,7 @@ struct ClusterDesc {
 	uint64_t totLen;     // sum of sequence lengths
 	uint32_t ss_ok;      // split-scafs: every scaffold starts "in" cluster 2 (ClusterSeparatorSplitScafs.cpp:102-106)
 	uint32_t tile0;      // first entry of the cluster in the level's tile table
+	uint32_t fOff, nf;   // sens/spec: segment of the per-dimension flip list (scaffolds that can flip, in flip order)
 };
 
 struct CandRec {
@@ -142,6 +145,8 @@ constexpr uint32_t LB_SPIN_LIMIT = 1u << 28;      // a bug must not hang the GPU
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
 __device__ __forceinline__ Agg ld_cg_agg(const AggSlot* p)
 {
 	const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -154,6 +159,81 @@ __device__ __forceinline__ void st_cg_agg(AggSlot* p, const Agg& v)
 	uint4* q = reinterpret_cast<uint4*>(p);
 	__stcg(q, make_uint4(v.a, v.b, v.c, v.d));
 	__stcg(q + 1, make_uint4((uint32_t)v.e, (uint32_t)(v.e >> 32), 0u, 0u));
+}
+
+// Decoupled look-back of warp 0 over the earlier tiles of a segment (items w - tile .. w - 1): publishes this tile's aggregate, walks back
+// 32 predecessors at a time until it meets a published inclusive prefix, publishes its own inclusive prefix and returns the exclusive one.
+__device__ __forceinline__ Agg agg_lookback(uint64_t w, uint32_t tile, const Agg& total, uint32_t* __restrict__ status, AggSlot* __restrict__ aggs,
+                                            AggSlot* __restrict__ prefixes, int* __restrict__ error_flag)
+{
+	const int ln = threadIdx.x;
+	Agg carry = agg_zero();
+	if(tile == 0) {
+		if(ln == 0) {
+			st_cg_agg(&prefixes[w], total);
+			__threadfence();
+			st_volatile_u32(&status[w], LB_PREFIX);
+		}
+		return carry;
+	}
+	if(ln == 0) {
+		st_cg_agg(&aggs[w], total);
+		__threadfence();
+		st_volatile_u32(&status[w], LB_AGG);
+	}
+	uint64_t base = w - 1;              // nearest predecessor; lane l looks at base - l
+	uint32_t remaining = tile;          // predecessors left in this segment (tile 0 always ends the walk with a prefix)
+	bool done = false, failed = false;
+	while(!done && !failed) {
+		const uint32_t cnt = min(32u, remaining);
+		uint32_t st, first_prefix, spins = 0;
+		while(true) {
+			st = ((uint32_t)ln < cnt)? ld_volatile_u32(&status[base - ln]) : LB_AGG;
+			const uint32_t pm = __ballot_sync(0xffffffffu, (uint32_t)ln < cnt && st == LB_PREFIX);
+			const uint32_t em = __ballot_sync(0xffffffffu, (uint32_t)ln < cnt && st == LB_EMPTY);
+			first_prefix = pm? (uint32_t)(__ffs(pm) - 1) : 32u;
+			const uint32_t need = (first_prefix >= 32u)? 0xFFFFFFFFu : ((2u << first_prefix) - 1u);
+			if((em & need) == 0)
+				break;
+			if(++spins >= LB_SPIN_LIMIT) {
+				failed = true;
+				break;
+			}
+		}
+		if(failed)
+			break;
+		__threadfence();
+		Agg v = agg_zero();
+		if((uint32_t)ln < cnt) {
+			if((uint32_t)ln < first_prefix)
+				v = ld_cg_agg(&aggs[base - ln]);
+			else if((uint32_t)ln == first_prefix)
+				v = ld_cg_agg(&prefixes[base - ln]);
+		}
+#pragma unroll
+		for(int o = 16; o > 0; o >>= 1) {
+			Agg t2;
+			t2.a = __shfl_xor_sync(0xffffffffu, v.a, o); t2.b = __shfl_xor_sync(0xffffffffu, v.b, o);
+			t2.c = __shfl_xor_sync(0xffffffffu, v.c, o); t2.d = __shfl_xor_sync(0xffffffffu, v.d, o);
+			t2.e = __shfl_xor_sync(0xffffffffu, v.e, o);
+			v = agg_add(v, t2);
+		}
+		carry = agg_add(carry, v);
+		if(first_prefix < 32u)
+			done = true;
+		else {
+			base -= 32;
+			remaining -= 32;
+		}
+	}
+	if(failed && ln == 0)
+		atomicExch(error_flag, 1);
+	if(ln == 0) {
+		st_cg_agg(&prefixes[w], agg_add(carry, total));
+		__threadfence();
+		st_volatile_u32(&status[w], LB_PREFIX);
+	}
+	return carry;
 }
 
 // per-element contribution to the running sums (see the table in DESIGN.md section 3)
@@ -244,77 +324,10 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep(const uint32_t* __restr
 		tsum = agg_add(tsum, contribution<STRATEGY>(el[j], i0 + j < n, rows, prm.fraction_in));
 	Agg total;
 	Agg ex = block_excl_scan_agg(tsum, total, sm_agg);
-	// decoupled look-back over the earlier tiles of this (cluster, dimension): warp 0 probes 32 predecessors at a time
+	// decoupled look-back over the earlier tiles of this (cluster, dimension)
 	if(threadIdx.x < 32) {
-		const int ln = threadIdx.x;
-		Agg carry = agg_zero();
-		if(tile == 0) {
-			if(ln == 0) {
-				st_cg_agg(&prefixes[w], total);
-				__threadfence();
-				st_volatile_u32(&status[w], LB_PREFIX);
-			}
-		}
-		else {
-			if(ln == 0) {
-				st_cg_agg(&aggs[w], total);
-				__threadfence();
-				st_volatile_u32(&status[w], LB_AGG);
-			}
-			uint64_t base = w - 1;              // nearest predecessor; lane l looks at base - l
-			uint32_t remaining = tile;          // predecessors left in this segment (tile 0 always ends the walk with a prefix)
-			bool done = false, failed = false;
-			while(!done && !failed) {
-				const uint32_t cnt = min(32u, remaining);
-				uint32_t st, first_prefix, spins = 0;
-				while(true) {
-					st = ((uint32_t)ln < cnt)? ld_volatile_u32(&status[base - ln]) : LB_AGG;
-					const uint32_t pm = __ballot_sync(0xffffffffu, (uint32_t)ln < cnt && st == LB_PREFIX);
-					const uint32_t em = __ballot_sync(0xffffffffu, (uint32_t)ln < cnt && st == LB_EMPTY);
-					first_prefix = pm? (uint32_t)(__ffs(pm) - 1) : 32u;
-					const uint32_t need = (first_prefix >= 32u)? 0xFFFFFFFFu : ((2u << first_prefix) - 1u);
-					if((em & need) == 0)
-						break;
-					if(++spins >= LB_SPIN_LIMIT) {
-						failed = true;
-						break;
-					}
-				}
-				if(failed)
-					break;
-				__threadfence();
-				Agg v = agg_zero();
-				if((uint32_t)ln < cnt) {
-					if((uint32_t)ln < first_prefix)
-						v = ld_cg_agg(&aggs[base - ln]);
-					else if((uint32_t)ln == first_prefix)
-						v = ld_cg_agg(&prefixes[base - ln]);
-				}
-#pragma unroll
-				for(int o = 16; o > 0; o >>= 1) {
-					Agg t2;
-					t2.a = __shfl_xor_sync(0xffffffffu, v.a, o); t2.b = __shfl_xor_sync(0xffffffffu, v.b, o);
-					t2.c = __shfl_xor_sync(0xffffffffu, v.c, o); t2.d = __shfl_xor_sync(0xffffffffu, v.d, o);
-					t2.e = __shfl_xor_sync(0xffffffffu, v.e, o);
-					v = agg_add(v, t2);
-				}
-				carry = agg_add(carry, v);
-				if(first_prefix < 32u)
-					done = true;
-				else {
-					base -= 32;
-					remaining -= 32;
-				}
-			}
-			if(failed && ln == 0)
-				atomicExch(error_flag, 1);
-			if(ln == 0) {
-				st_cg_agg(&prefixes[w], agg_add(carry, total));
-				__threadfence();
-				st_volatile_u32(&status[w], LB_PREFIX);
-			}
-		}
-		if(ln == 0)
+		const Agg carry = agg_lookback(w, tile, total, status, aggs, prefixes, error_flag);
+		if(threadIdx.x == 0)
 			sm_carry = carry;
 	}
 	__syncthreads();
@@ -392,6 +405,299 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep(const uint32_t* __restr
 		out[w] = best;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// sens/spec sweep, second formulation.  Only the class-1 ("flip") elements carry per-scaffold quantities (T/2+1, T, n, SCG flag,
+// length); everything a candidate needs is therefore a function of two COUNTS at its position -- class-2 elements before it and
+// flip elements before it -- plus a table of prefix sums indexed by the flip count.  Those tables are built once per level
+// from the per-dimension flip list (k_flip_prefix), where the per-scaffold gathers are a plain parallel stream; the sweep itself
+// then never looks at a scaffold id: a warp reads 32 rows of 32 consecutive elements (coalesced 128-byte requests), turns the
+// three flag bits of every row into ballot masks, and lane r keeps the masks of row r -- i.e. of 32 CONSECUTIVE elements.  Counts
+// before any position are popcounts; the block scan and the look-back carry two small integers instead of five sums.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SW_WARP_CHUNK = 32 * 32;            // elements per warp: 32 rows of 32
+
+__device__ __forceinline__ unsigned long long cnt_pack(uint32_t nf, uint32_t nc, uint32_t st)
+{
+	return (unsigned long long)nf | ((unsigned long long)nc << 31) | ((unsigned long long)st << 62);     // both counts < 2^31
+}
+
+// Tables of a level, per (cluster, dimension), indexed by the number k of flip elements already passed:
+//   F8[k-1]  = sums over the first k flips: x = T/2+1 (TP brought by the flips), y = T;  FC[k-1] = n (only kept when some scaffold has n < T)
+//   scg_k[i] = k at which the i-th SCG-carrying scaffold flips (the SCG count of a candidate is a binary search in it)
+//   klo, khi = the range of k for which both sides are >= scg_min_size bases long (ClusterQuality.cpp:118-120); lengths only matter through that test
+// Tiles of FP_TILE list entries, items (dimension, tile-table entry) handed out by ticket, running sums across tiles by look-back.
+constexpr int FP_ITEMS = 8;
+constexpr int FP_TILE = SW_THREADS * FP_ITEMS;
+__global__ void __launch_bounds__(SW_THREADS) k_flip_prefix(const uint32_t* __restrict__ flip_list, uint64_t Sf, const ClusterDesc* __restrict__ clusters, uint32_t FTT,
+                                                           const uint2* __restrict__ ftile_tab, const ScafRow* __restrict__ rows, const uint8_t* __restrict__ has_scg,
+                                                           unsigned long long* __restrict__ ticket, uint32_t* __restrict__ status, AggSlot* __restrict__ aggs,
+                                                           AggSlot* __restrict__ prefixes, uint2* __restrict__ F8, uint32_t* __restrict__ FC, uint32_t* __restrict__ scg_k,
+                                                           uint64_t Kstride, uint2* __restrict__ klohi, uint32_t C, unsigned long long scg_min_size,
+                                                           int* __restrict__ error_flag)
+{
+	__shared__ Agg sm_agg[SW_THREADS / 32 + 1];
+	__shared__ unsigned long long sm_w;
+	__shared__ Agg sm_carry;
+	if(threadIdx.x == 0)
+		sm_w = atomicAdd(ticket, 1ull);
+	__syncthreads();
+	const uint64_t w = sm_w;
+	const uint32_t d = (uint32_t)(w / FTT);
+	const uint2 te = __ldg(ftile_tab + (uint32_t)(w - (uint64_t)d * FTT));
+	const ClusterDesc cl = clusters[te.x];
+	const uint32_t tile = te.y;
+	const uint64_t base = (uint64_t)d * Sf + cl.fOff;
+	const uint32_t* __restrict__ list = flip_list + base;
+	const uint32_t i0 = tile * FP_TILE + threadIdx.x * FP_ITEMS;
+	uint32_t sc[FP_ITEMS];
+#pragma unroll
+	for(int j = 0; j < FP_ITEMS; j++)
+		sc[j] = (i0 + j < cl.nf)? (__ldg(list + i0 + j) & EL_SCAF_MASK) : 0xFFFFFFFFu;      // a partition pass may have left a flag bit on the entry
+	Agg x[FP_ITEMS];
+	Agg tsum = agg_zero();
+#pragma unroll
+	for(int j = 0; j < FP_ITEMS; j++) {
+		x[j] = agg_zero();
+		if(sc[j] != 0xFFFFFFFFu) {
+			const uint4 r = __ldg(reinterpret_cast<const uint4*>(rows + sc[j]));   // {T, n, len}
+			x[j].a = r.x / 2 + 1;          // the flip element brings itself and the floor(T/2) earlier dps of the scaffold (...Specificity.cpp:41-57)
+			x[j].b = r.x;
+			x[j].c = r.y;
+			x[j].d = has_scg[sc[j]];
+			x[j].e = (unsigned long long)r.z | ((unsigned long long)r.w << 32);
+		}
+		tsum = agg_add(tsum, x[j]);
+	}
+	Agg total;
+	Agg run = block_excl_scan_agg(tsum, total, sm_agg);
+	if(threadIdx.x < 32) {
+		const Agg carry = agg_lookback(w, tile, total, status, aggs, prefixes, error_flag);
+		if(threadIdx.x == 0)
+			sm_carry = carry;
+	}
+	__syncthreads();
+	run = agg_add(run, sm_carry);
+#pragma unroll
+	for(int j = 0; j < FP_ITEMS; j++) {
+		const unsigned long long e_before = run.e;
+		run = agg_add(run, x[j]);
+		if(sc[j] != 0xFFFFFFFFu) {
+			const uint32_t k = i0 + j + 1;                  // flips passed once this one is
+			F8[base + i0 + j] = make_uint2(run.a, run.b);
+			if(FC != nullptr)
+				FC[base + i0 + j] = run.c;
+			if(x[j].d)
+				scg_k[(uint64_t)d * Kstride + cl.kOff + run.d - 1] = k;
+			// lengths are non-decreasing in k: exactly one flip crosses each limit
+			if(e_before < scg_min_size && run.e >= scg_min_size)
+				klohi[(uint64_t)d * C + te.x].x = k;
+			if(cl.totLen >= scg_min_size && e_before <= cl.totLen - scg_min_size && run.e > cl.totLen - scg_min_size)
+				klohi[(uint64_t)d * C + te.x].y = k - 1;
+		}
+	}
+}
+
+template <int STRATEGY>
+__device__ __forceinline__ void block_best_out(CandRec best, uint32_t d, CandRec* sm_best, CandRec* __restrict__ out, uint64_t w)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if(__syncthreads_or(best.found)) {
+#pragma unroll
+		for(int o = 16; o > 0; o >>= 1) {
+			CandRec other;
+			other.k1 = __shfl_xor_sync(0xffffffffu, best.k1, o); other.k2 = __shfl_xor_sync(0xffffffffu, best.k2, o);
+			other.p = __shfl_xor_sync(0xffffffffu, best.p, o); other.i0 = __shfl_xor_sync(0xffffffffu, best.i0, o);
+			other.i1 = __shfl_xor_sync(0xffffffffu, best.i1, o); other.i2 = __shfl_xor_sync(0xffffffffu, best.i2, o);
+			other.found = __shfl_xor_sync(0xffffffffu, best.found, o); other.dim0 = d;
+			if(cand_better<STRATEGY>(other, best))
+				best = other;
+		}
+		if(lane == 0)
+			sm_best[warp] = best;
+		__syncthreads();
+		if(threadIdx.x == 0) {
+			CandRec b = sm_best[0];
+			for(int w2 = 1; w2 < SW_THREADS / 32; w2++)
+				if(cand_better<STRATEGY>(sm_best[w2], b))
+					b = sm_best[w2];
+			out[w] = b;
+		}
+	}
+	else if(threadIdx.x == 0)
+		out[w] = best;
+}
+
+__global__ void __launch_bounds__(SW_THREADS, 4) k_sweep_ss(const uint32_t* __restrict__ E, uint64_t N, const ClusterDesc* __restrict__ clusters, uint32_t TT,
+                                                           const uint2* __restrict__ tile_tab, const uint2* __restrict__ F8, const uint32_t* __restrict__ FC,
+                                                           const uint32_t* __restrict__ scg_k, uint64_t Kstride, const uint2* __restrict__ klohi, uint32_t C,
+                                                           uint64_t Sf, const uint8_t* __restrict__ pass_tab, uint64_t tab_stride, SweepParams prm,
+                                                           unsigned long long* __restrict__ ticket, unsigned long long* __restrict__ lookback,
+                                                           CandRec* __restrict__ out, int* __restrict__ error_flag)
+{
+	__shared__ uint32_t sm_warp[SW_THREADS / 32];
+	__shared__ CandRec sm_best[SW_THREADS / 32];
+	__shared__ unsigned long long sm_w;
+	__shared__ uint32_t sm_carry[2];
+	if(threadIdx.x == 0)
+		sm_w = atomicAdd(ticket, 1ull);
+	__syncthreads();
+	const uint64_t w = sm_w;
+	const uint32_t d = (uint32_t)(w / TT);
+	const uint2 te = __ldg(tile_tab + (uint32_t)(w - (uint64_t)d * TT));
+	const uint32_t tile = te.y;
+	const ClusterDesc cl = clusters[te.x];
+	const uint32_t* __restrict__ seg = E + (uint64_t)d * N + cl.off;
+	const uint32_t n = cl.n;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t wbase = tile * SW_TILE + warp * SW_WARP_CHUNK;
+	// 32 coalesced rows; lane r ends up with the flag masks of row r = elements [wbase + 32 r, wbase + 32 r + 32)
+	uint32_t mF = 0, mC = 0, mB = 0;
+	if(wbase < n) {
+		uint32_t el[32];
+#pragma unroll
+		for(int r = 0; r < 32; r++) {
+			const uint32_t idx = wbase + r * 32 + lane;
+			el[r] = (idx < n)? __ldg(seg + idx) : 0u;          // class 0, no boundary: contributes nothing
+		}
+#pragma unroll
+		for(int r = 0; r < 32; r++) {
+			const uint32_t f = __ballot_sync(0xffffffffu, el[r] & EL_FLIP_BIT);
+			const uint32_t c2 = __ballot_sync(0xffffffffu, el[r] & EL_CLS2_BIT);
+			const uint32_t b = __ballot_sync(0xffffffffu, el[r] & EL_BOUNDARY);
+			if(lane == r) { mF = f; mC = c2; mB = b; }
+		}
+	}
+	const uint32_t i0 = wbase + lane * 32;                  // first element of this thread's row
+	// exclusive block scan of (flip count, class-2 count), 16 bits each: a tile holds 8192 elements
+	const uint32_t mine = __popc(mF) | (__popc(mC) << 16);
+	uint32_t incl = mine;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+		if(lane >= o)
+			incl += t;
+	}
+	if(lane == 31)
+		sm_warp[warp] = incl;
+	__syncthreads();
+	uint32_t wex = 0, btot = 0;
+#pragma unroll
+	for(int w2 = 0; w2 < SW_THREADS / 32; w2++) {
+		const uint32_t t = sm_warp[w2];
+		if(w2 < warp)
+			wex += t;
+		btot += t;
+	}
+	const uint32_t ex = wex + incl - mine;
+	// decoupled look-back over the earlier tiles of this (cluster, dimension)
+	if(threadIdx.x < 32) {
+		const uint32_t totF = btot & 0xFFFFu, totC = btot >> 16;
+		uint32_t cF = 0, cC = 0;
+		if(tile > 0) {
+			if(lane == 0)
+				st_volatile_u64(&lookback[w], cnt_pack(totF, totC, LB_AGG));
+			uint64_t base = w - 1;
+			uint32_t remaining = tile;
+			bool done = false, failed = false;
+			while(!done && !failed) {
+				const uint32_t cnt = min(32u, remaining);
+				unsigned long long v;
+				uint32_t first_prefix, spins = 0;
+				while(true) {
+					v = ((uint32_t)lane < cnt)? ld_volatile_u64(&lookback[base - lane]) : cnt_pack(0, 0, LB_AGG);
+					const uint32_t st = (uint32_t)(v >> 62);
+					const uint32_t pm = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == LB_PREFIX);
+					const uint32_t em = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == LB_EMPTY);
+					first_prefix = pm? (uint32_t)(__ffs(pm) - 1) : 32u;
+					const uint32_t need = (first_prefix >= 32u)? 0xFFFFFFFFu : ((2u << first_prefix) - 1u);
+					if((em & need) == 0)
+						break;
+					if(++spins >= LB_SPIN_LIMIT) {
+						failed = true;
+						break;
+					}
+				}
+				if(failed)
+					break;
+				const bool take = (uint32_t)lane < cnt && (uint32_t)lane <= first_prefix;
+				uint32_t vf = take? (uint32_t)(v & 0x7FFFFFFFull) : 0u, vc = take? (uint32_t)((v >> 31) & 0x7FFFFFFFull) : 0u;
+				vf = __reduce_add_sync(0xffffffffu, vf);
+				vc = __reduce_add_sync(0xffffffffu, vc);
+				cF += vf;
+				cC += vc;
+				if(first_prefix < 32u)
+					done = true;
+				else {
+					base -= 32;
+					remaining -= 32;
+				}
+			}
+			if(failed && lane == 0)
+				atomicExch(error_flag, 1);
+		}
+		if(lane == 0) {
+			st_volatile_u64(&lookback[w], cnt_pack(cF + totF, cC + totC, LB_PREFIX));
+			sm_carry[0] = cF;
+			sm_carry[1] = cC;
+		}
+	}
+	__syncthreads();
+	const uint32_t nF0 = sm_carry[0] + (ex & 0xFFFFu), nC0 = sm_carry[1] + (ex >> 16);
+	// candidates: a boundary before element i means "all dps with value <= value[i-1]" is a threshold with p = i
+	CandRec best;
+	best.found = 0; best.k1 = 0; best.k2 = 0; best.p = 0; best.i0 = best.i1 = best.i2 = 0; best.dim0 = d;
+	const uint8_t* __restrict__ tab = pass_tab + (uint64_t)d * tab_stride + cl.tabOff;
+	const uint64_t fbase = (uint64_t)d * Sf + cl.fOff;
+	const uint32_t* __restrict__ sk = scg_k + (uint64_t)d * Kstride + cl.kOff;
+	uint32_t bm = mB, lastk = 0;
+	uint2 f = make_uint2(0, 0);
+	uint32_t fc = 0;
+	while(bm) {
+		const int j = __ffs(bm) - 1;
+		bm &= bm - 1;
+		const uint32_t p = i0 + j;                          // p < n: elements past the end have no boundary bit
+		if(p < prm.thr || n - p < prm.thr)
+			continue;
+		const uint32_t lt = (1u << j) - 1u;
+		const uint32_t k = nF0 + __popc(mF & lt);
+		if(k != lastk) {
+			f = __ldg(F8 + fbase + k - 1);                  // k == 0 only before the first reload: f is zero then
+			fc = (FC != nullptr)? __ldg(FC + fbase + k - 1) : f.y;     // n == T for every scaffold unless the caller passed partial scaffolds
+			lastk = k;
+		}
+		const uint32_t a = nC0 + __popc(mC & lt) + f.x;     // TP1
+		// ...Specificity.cpp:146-161 with TP1/FP1/TP2/FP2 written as prefix sums
+		uint32_t TP, tot, u;
+		if(p < n - p) { TP = a; tot = f.y; u = p; }
+		else { TP = (n - p) - (fc - a); tot = cl.totT - f.y; u = n - p; }
+		if(tot == 0)
+			continue;
+		const float fTP = (float)TP;
+		if(!(fTP >= prm.prune * (float)tot && fTP >= prm.prune * (float)u))
+			continue;
+		const double sens = __ddiv_rn((double)(int)TP, (double)(int)tot), spec = __ddiv_rn((double)(int)TP, (double)(int)u);
+		const double score = __dmul_rn(sens, spec);
+		if(score >= prm.min_score && (!best.found || score > best.k1)) {
+			// SCG-carrying scaffolds among the first k flips: the entries of scg_k (increasing) that are <= k
+			uint32_t lo = 0, hi = cl.K;
+			while(lo < hi) {
+				const uint32_t mid = (lo + hi) >> 1;
+				if(__ldg(sk + mid) <= k) lo = mid + 1; else hi = mid;
+			}
+			const uint8_t pt = tab[lo];
+			bool ok = (pt == 1);
+			if(pt == 2) {
+				const uint2 kk = __ldg(klohi + (uint64_t)d * C + te.x);
+				ok = k >= kk.x && k <= kk.y;                // both sides at least scg_min_size bases long
+			}
+			if(ok) {
+				best.found = 1; best.k1 = score; best.p = p; best.i0 = TP; best.i1 = tot; best.i2 = u;
+			}
+		}
+	}
+	block_best_out<ABW_SENS_SPEC>(best, d, sm_best, out, w);
+}
+
 // best candidate of every cluster over its (dimension, tile) items: the reference's total order
 // (score, then lowest dimension, then lowest value; ...Specificity.cpp:137-140 under the mutex, ClusterSeparator.cpp:11-16)
 template <int STRATEGY>
@@ -430,13 +736,15 @@ constexpr uint32_t SCG_WMAX = 8;   // up to 512 distinct SCG names
 
 __global__ void k_pass_table(const uint32_t* __restrict__ scg_list, uint64_t list_stride, const ClusterDesc* __restrict__ clusters, const uint64_t* __restrict__ scgmask,
                              uint32_t W, const uint64_t* __restrict__ never_mask, double overlap_thr, uint64_t* __restrict__ suffix_tmp, uint8_t* __restrict__ tab,
-                             uint64_t tab_stride, uint32_t D)
+                             uint64_t tab_stride, uint32_t D, uint2* __restrict__ klohi, unsigned long long scg_min_size)
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t c = blockIdx.x, d = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
 	if(d >= D)
 		return;
 	const ClusterDesc cl = clusters[c];
+	if(lane == 0)                                          // size test of the level (k_flip_prefix narrows it): with no flip at all side 1 is empty
+		klohi[(uint64_t)d * gridDim.x + c] = (cl.totLen >= scg_min_size)? make_uint2(scg_min_size == 0? 0u : 0xFFFFFFFFu, 0xFFFFFFFFu) : make_uint2(0xFFFFFFFFu, 0u);
 	const uint32_t* __restrict__ list = scg_list + (uint64_t)d * list_stride + cl.kOff;
 	uint64_t* __restrict__ suf = suffix_tmp + ((uint64_t)d * list_stride + cl.kOff) * W;     // suf[k] = OR of masks k..K-1
 	uint8_t* __restrict__ t = tab + (uint64_t)d * tab_stride + cl.tabOff;
@@ -511,7 +819,7 @@ struct SplitJob {
 
 struct ChildStats {      // [job][2]; summed across ranks as 64-bit words in a sharded search (no 32-bit half can overflow)
 	unsigned long long ndps, totLen;
-	uint32_t ns, nassigned, totT, K, viol, pad;
+	uint32_t ns, nassigned, totT, K, viol, nflip;
 };
 
 __global__ void k_count_low(const uint32_t* __restrict__ E, uint64_t N, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs, uint32_t* __restrict__ low)
@@ -529,59 +837,89 @@ __device__ __forceinline__ unsigned long long orderable(double v)
 	unsigned long long b = (unsigned long long)__double_as_longlong(v);
 	return (b >> 63)? ~b : (b | 0x8000000000000000ull);
 }
-// one thread per scaffold of every split cluster: vote (ClusterSeparator.cpp:94-101), child statistics, separating value
-__global__ void k_scaf_sides(const uint32_t* __restrict__ scaf_list, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs, const ScafRow* __restrict__ rows,
-                             const uint32_t* __restrict__ low, const uint64_t* __restrict__ dp_first, const double* __restrict__ values, uint64_t N,
+// one thread per scaffold of every split cluster: vote (ClusterSeparator.cpp:94-101), child statistics, separating value.
+// The statistics of a warp are combined before they reach the two counters of the job (one atomic per warp and field, not per scaffold).
+__global__ void __launch_bounds__(128) k_scaf_sides(const uint32_t* __restrict__ scaf_list, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs,
+                             const ScafRow* __restrict__ rows, const uint32_t* __restrict__ low, const uint64_t* __restrict__ dp_first, const double* __restrict__ values, uint64_t N,
                              const uint64_t* __restrict__ scgmask, uint32_t W, int strategy, double fraction_in, uint8_t* __restrict__ side, uint8_t* __restrict__ new_assigned,
                              ChildStats* __restrict__ stats, uint64_t* __restrict__ child_never, unsigned long long* __restrict__ value_key)
 {
 	const SplitJob jb = jobs[blockIdx.y];
 	const ClusterDesc cl = clusters[jb.cluster];
-	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cl.ns; i += gridDim.x * blockDim.x) {
-		const uint32_t s = scaf_list[cl.sOff + i];
-		const ScafRow r = rows[s];
-		const uint32_t lo = low[s];
-		const uint32_t c1 = jb.swapped? r.n - lo : lo, c2 = r.n - c1;
-		const bool A1 = c1 > 0 && 2ull * c1 >= r.T;          // :95-97
-		const bool A2 = c2 > 0 && 2ull * c2 > r.T;           // :98-101
-		// dps not in a scaffold assigned to cluster2 end up in cluster1 (:104-122)
-		const uint32_t sd = A2? 2u : 1u;
-		side[s] = (uint8_t)sd;
-		new_assigned[s] = A1? 1 : (A2? 2 : 0);
-		ChildStats* st = stats + (uint64_t)jb.slot * 2 + (sd - 1);
-		atomicAdd(&st->ndps, (unsigned long long)r.n);
-		atomicAdd(&st->totLen, (unsigned long long)r.len);
-		atomicAdd(&st->ns, 1u);
-		atomicAdd(&st->totT, r.T);
-		if(A1 || A2)
-			atomicAdd(&st->nassigned, 1u);
-		bool has_scg = false;
-		for(uint32_t w = 0; w < W; w++)
-			has_scg |= scgmask[(uint64_t)s * W + w] != 0;
-		if(has_scg) {
-			if(r.n >= r.T / 2 + 1)
-				atomicAdd(&st->K, 1u);
-			else                                             // can never be assigned to side 1 of a sweep: always counted on side 2
+	const int lane = threadIdx.x & 31;
+	for(uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < cl.ns; base += gridDim.x * blockDim.x) {
+		const uint32_t i = base + lane;
+		const bool active = i < cl.ns;
+		uint32_t sd = 0, rn = 0, rT = 0;
+		unsigned long long rlen = 0, kth = 0;
+		bool assigned_any = false, flippable = false, has_scg = false, viol = false;
+		if(active) {
+			const uint32_t s = scaf_list[cl.sOff + i];
+			const ScafRow r = rows[s];
+			const uint32_t lo = low[s];
+			const uint32_t c1 = jb.swapped? r.n - lo : lo, c2 = r.n - c1;
+			const bool A1 = c1 > 0 && 2ull * c1 >= r.T;          // :95-97
+			const bool A2 = c2 > 0 && 2ull * c2 > r.T;           // :98-101
+			// dps not in a scaffold assigned to cluster2 end up in cluster1 (:104-122)
+			sd = A2? 2u : 1u;
+			side[s] = (uint8_t)sd;
+			new_assigned[s] = A1? 1 : (A2? 2 : 0);
+			rn = r.n; rT = r.T; rlen = r.len;
+			assigned_any = A1 || A2;
+			flippable = r.n >= r.T / 2 + 1;
+			for(uint32_t w = 0; w < W; w++)
+				has_scg |= scgmask[(uint64_t)s * W + w] != 0;
+			if(has_scg && !flippable)                            // can never be assigned to side 1 of a sweep: always counted on side 2
 				for(uint32_t w = 0; w < W; w++)
 					atomicOr((unsigned long long*)&child_never[((uint64_t)jb.slot * 2 + (sd - 1)) * W + w], (unsigned long long)scgmask[(uint64_t)s * W + w]);
-		}
-		if(strategy == ABW_SPLIT_SCAFS && !((double)r.n >= __dmul_rn(fraction_in, (double)r.T)))
-			atomicAdd(&st->viol, 1u);
-		// separating value = largest value on the low side = max over scaffolds of their lo-th smallest value
-		if(lo > 0) {
-			const double* __restrict__ col = values + (uint64_t)jb.dim0 * N + dp_first[s];
-			unsigned long long kth = 0;
-			for(uint32_t a = 0; a < r.n; a++) {
-				const unsigned long long ka = orderable(col[a]);
-				uint32_t rank = 0;
-				for(uint32_t b = 0; b < r.n; b++) {
-					const unsigned long long kb = orderable(col[b]);
-					rank += (kb < ka) || (kb == ka && b < a);
+			viol = strategy == ABW_SPLIT_SCAFS && !((double)r.n >= __dmul_rn(fraction_in, (double)r.T));
+			// separating value = largest value on the low side = max over scaffolds of their lo-th smallest value
+			if(lo > 0) {
+				const double* __restrict__ col = values + (uint64_t)jb.dim0 * N + dp_first[s];
+				for(uint32_t a = 0; a < r.n; a++) {
+					const unsigned long long ka = orderable(col[a]);
+					uint32_t rank = 0;
+					for(uint32_t b = 0; b < r.n; b++) {
+						const unsigned long long kb = orderable(col[b]);
+						rank += (kb < ka) || (kb == ka && b < a);
+					}
+					if(rank == lo - 1)
+						kth = ka;
 				}
-				if(rank == lo - 1)
-					kth = ka;
 			}
+		}
+#pragma unroll
+		for(int o = 16; o > 0; o >>= 1)
+			kth = max(kth, __shfl_xor_sync(0xffffffffu, kth, o));
+		if(lane == 0 && kth != 0)
 			atomicMax(&value_key[jb.slot], kth);
+#pragma unroll
+		for(uint32_t sdv = 1; sdv <= 2; sdv++) {
+			const bool m = active && sd == sdv;
+			const uint32_t ns = __popc(__ballot_sync(0xffffffffu, m));
+			if(ns == 0)
+				continue;                                        // warp-uniform
+			const uint32_t ndps = __reduce_add_sync(0xffffffffu, m? rn : 0u);      // sums stay below 2^31 (N and the sum of T do)
+			const uint32_t totT = __reduce_add_sync(0xffffffffu, m? rT : 0u);
+			unsigned long long len = m? rlen : 0ull;
+#pragma unroll
+			for(int o = 16; o > 0; o >>= 1)
+				len += __shfl_xor_sync(0xffffffffu, len, o);
+			const uint32_t nas = __popc(__ballot_sync(0xffffffffu, m && assigned_any));
+			const uint32_t nK = __popc(__ballot_sync(0xffffffffu, m && has_scg && flippable));
+			const uint32_t nfl = __popc(__ballot_sync(0xffffffffu, m && flippable));
+			const uint32_t nv = __popc(__ballot_sync(0xffffffffu, m && viol));
+			if(lane == 0) {
+				ChildStats* st = stats + (uint64_t)jb.slot * 2 + (sdv - 1);
+				atomicAdd(&st->ndps, (unsigned long long)ndps);
+				atomicAdd(&st->totLen, len);
+				atomicAdd(&st->ns, ns);
+				atomicAdd(&st->totT, totT);
+				if(nas) atomicAdd(&st->nassigned, nas);
+				if(nK) atomicAdd(&st->K, nK);
+				if(nfl) atomicAdd(&st->nflip, nfl);
+				if(nv) atomicAdd(&st->viol, nv);
+			}
 		}
 	}
 }
@@ -603,43 +941,35 @@ struct PartJob {
 	uint32_t n, n1;
 };
 
-// state = (pend1, pend2): a boundary was seen since the last side-1 / side-2 element.  maps on 4 states, 2 bits each
-__device__ __forceinline__ uint32_t map_of(uint32_t sd, uint32_t c)
+// ---------------------------------------------------------------------------------------------------
+// stable partition of every dimension's elements of a split cluster (same warp-striped rows as k_sweep_ss); the boundary flag of an
+// element becomes "value differs from the previous element OF ITS NEW CLUSTER", i.e. the OR of the flags since that element.  Lane r owns the masks of row r:
+//   S1 = elements that go to child 1, S2 = to child 2, B = boundary flags.
+// New flag of an element of child X = OR of the old flags since the previous element of child X (itself included).  With the closers
+// P = SX that is a carry chain:  (B & ~P) + ~P  overflows a run of non-closers exactly when the run holds a boundary, and the carry
+// lands on the closer that ends the run.  A run of elements is summarised per child by H ("contains an element of the child") and
+// T ("a boundary is pending after the last such element"); summaries compose associatively, so rows, warps and tiles chain with a
+// scan and the usual look-back.
+// ---------------------------------------------------------------------------------------------------
+// bits: 0 = H1, 1 = H2, 2 = T1, 3 = T2
+__device__ __forceinline__ uint32_t ht_compose(uint32_t first, uint32_t then)
 {
-	uint32_t m = 0;
-#pragma unroll
-	for(uint32_t s = 0; s < 4; s++) {
-		uint32_t p1 = s & 1u, p2 = s >> 1;
-		uint32_t ns = (sd == 1u)? (0u | ((p2 | c) << 1)) : ((p1 | c) | 0u);
-		m |= ns << (2 * s);
-	}
-	return m;
+	const uint32_t H = (first | then) & 3u;
+	const uint32_t T = ((then >> 2) | ((first >> 2) & ~then)) & 3u;
+	return H | (T << 2);
 }
-__device__ __forceinline__ uint32_t map_apply(uint32_t m, uint32_t s) { return (m >> (2 * s)) & 3u; }
-__device__ __forceinline__ uint32_t map_compose(uint32_t first, uint32_t then)   // then(first(s))
-{
-	uint32_t m = 0;
-#pragma unroll
-	for(uint32_t s = 0; s < 4; s++)
-		m |= map_apply(then, map_apply(first, s)) << (2 * s);
-	return m;
-}
-constexpr uint32_t MAP_IDENTITY = 0xE4u;   // 3,2,1,0
+// pending state (bit 0: child 1, bit 1: child 2) after a run with summary ht entered in `state`
+__device__ __forceinline__ uint32_t ht_apply(uint32_t ht, uint32_t state) { return ((ht >> 2) | (state & ~ht)) & 3u; }
 
-// look-back word of a partition tile: [0,32) count of side-1 elements, [32,40) map (aggregate) or state after the tile (prefix), [62,64) status
-__device__ __forceinline__ unsigned long long lb_pack(uint32_t cnt, uint32_t m, uint32_t st) { return (unsigned long long)cnt | ((unsigned long long)m << 32) | ((unsigned long long)st << 62); }
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
-__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+__device__ __forceinline__ unsigned long long lb2_pack(uint32_t cnt, uint32_t ht, uint32_t st) { return (unsigned long long)cnt | ((unsigned long long)ht << 32) | ((unsigned long long)st << 62); }
 
-// one CTA per tile; items are (job, dimension, tile), tile fastest, handed out by ticket (see k_sweep)
-__global__ void __launch_bounds__(SW_THREADS) k_partition(const uint32_t* __restrict__ Ein, uint32_t* __restrict__ Eout, uint64_t N, const PartJob* __restrict__ jobs,
-                                                         uint32_t TT, const uint2* __restrict__ tile_tab, const uint8_t* __restrict__ side,
-                                                         unsigned long long* __restrict__ ticket, unsigned long long* __restrict__ lookback, int* __restrict__ error_flag)
+__global__ void __launch_bounds__(SW_THREADS, 3) k_partition2(const uint32_t* __restrict__ Ein, uint32_t* __restrict__ Eout, uint64_t N, const PartJob* __restrict__ jobs,
+                                                             uint32_t TT, const uint2* __restrict__ tile_tab, const uint8_t* __restrict__ side,
+                                                             unsigned long long* __restrict__ ticket, unsigned long long* __restrict__ lookback, int* __restrict__ error_flag)
 {
-	__shared__ uint32_t sm_cnt[SW_THREADS / 32 + 1];
-	__shared__ uint32_t sm_map[SW_THREADS / 32 + 1];
+	__shared__ uint32_t sm_cnt[SW_THREADS / 32];
+	__shared__ uint32_t sm_ht[SW_THREADS / 32];
 	__shared__ unsigned long long sm_w;
-	__shared__ uint32_t sm_carry[2];
 	if(threadIdx.x == 0)
 		sm_w = atomicAdd(ticket, 1ull);
 	__syncthreads();
@@ -652,66 +982,66 @@ __global__ void __launch_bounds__(SW_THREADS) k_partition(const uint32_t* __rest
 	uint32_t* __restrict__ dst1 = Eout + (uint64_t)d * N + jb.off;
 	uint32_t* __restrict__ dst2 = dst1 + jb.n1;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t i0 = tile * SW_TILE + threadIdx.x * SW_ITEMS;
-	uint32_t el[SW_ITEMS];
-	uint32_t side1 = 0;                                   // bit j: element j goes to child 1
-	uint32_t cnt1 = 0, tmap = MAP_IDENTITY;
-	if(i0 + SW_ITEMS <= jb.n && ((reinterpret_cast<uintptr_t>(src + i0) & 15) == 0)) {
-		const uint4* p4 = reinterpret_cast<const uint4*>(src + i0);
+	const uint32_t wbase = tile * SW_TILE + warp * SW_WARP_CHUNK;
+	uint32_t el[32];
+	uint32_t my1 = 0;                                      // bit r: my element of row r goes to child 1
+	uint32_t mS1 = 0, mV = 0, mB = 0;                      // masks of row `lane`
+	const bool active = wbase < jb.n;
+	if(active) {
 #pragma unroll
-		for(int q = 0; q < SW_ITEMS / 4; q++) {
-			const uint4 x = __ldg(p4 + q);
-			el[4 * q] = x.x; el[4 * q + 1] = x.y; el[4 * q + 2] = x.z; el[4 * q + 3] = x.w;
+		for(int r = 0; r < 32; r++) {
+			const uint32_t idx = wbase + r * 32 + lane;
+			el[r] = (idx < jb.n)? __ldg(src + idx) : 0xFFFFFFFFu;
+		}
+#pragma unroll
+		for(int r = 0; r < 32; r++) {
+			const uint32_t idx = wbase + r * 32 + lane;
+			const bool valid = idx < jb.n;
+			const bool is1 = valid && side[el[r] & EL_SCAF_MASK] == 1;
+			const uint32_t s1 = __ballot_sync(0xffffffffu, is1);
+			const uint32_t v = __ballot_sync(0xffffffffu, valid);
+			const uint32_t b = __ballot_sync(0xffffffffu, valid && (el[r] >> 31));
+			my1 |= (is1? 1u : 0u) << r;
+			if(lane == r) { mS1 = s1; mV = v; mB = b; }
 		}
 	}
-	else {
-#pragma unroll
-		for(int j = 0; j < SW_ITEMS; j++)
-			el[j] = (i0 + j < jb.n)? __ldg(src + i0 + j) : 0u;
-	}
-#pragma unroll
-	for(int j = 0; j < SW_ITEMS; j++) {
-		if(i0 + j < jb.n) {
-			const uint32_t sdj = side[el[j] & EL_SCAF_MASK];
-			side1 |= (sdj == 1u)? (1u << j) : 0u;
-			cnt1 += (sdj == 1u);
-			tmap = map_compose(tmap, map_of(sdj, el[j] >> 31));
-		}
-	}
-	// inclusive warp scans
-	uint32_t icnt = cnt1, imap = tmap;
+	const uint32_t mS2 = mV & ~mS1;
+	const uint32_t c1 = __popc(mS1);
+	const unsigned long long s1sum = (unsigned long long)(mB & ~mS1) + (unsigned long long)(uint32_t)(~mS1);
+	const unsigned long long s2sum = (unsigned long long)(mB & ~mS2) + (unsigned long long)(uint32_t)(~mS2);
+	uint32_t newflags = (((uint32_t)s1sum | mB) & mS1) | (((uint32_t)s2sum | mB) & mS2);     // assuming nothing is pending when the row starts
+	const uint32_t myht = (mS1? 1u : 0u) | (mS2? 2u : 0u) | ((uint32_t)(s1sum >> 32) << 2) | ((uint32_t)(s2sum >> 32) << 3);
+	// inclusive scans over the rows of the warp
+	uint32_t icnt = c1, iht = myht;
 #pragma unroll
 	for(int o = 1; o < 32; o <<= 1) {
-		uint32_t c2 = __shfl_up_sync(0xffffffffu, icnt, o), m2 = __shfl_up_sync(0xffffffffu, imap, o);
+		const uint32_t c2 = __shfl_up_sync(0xffffffffu, icnt, o), h2 = __shfl_up_sync(0xffffffffu, iht, o);
 		if(lane >= o) {
 			icnt += c2;
-			imap = map_compose(m2, imap);
+			iht = ht_compose(h2, iht);
 		}
 	}
 	if(lane == 31) {
 		sm_cnt[warp] = icnt;
-		sm_map[warp] = imap;
+		sm_ht[warp] = iht;
 	}
 	__syncthreads();
 	if(threadIdx.x < 32) {
-		uint32_t rc = 0, rm = MAP_IDENTITY;
-		if(lane == 0) {
-			for(int w2 = 0; w2 < SW_THREADS / 32; w2++) {
-				uint32_t tc = sm_cnt[w2], tm2 = sm_map[w2];
-				sm_cnt[w2] = rc;
-				sm_map[w2] = rm;
-				rc += tc;
-				rm = map_compose(rm, tm2);
-			}
+		// exclusive over the warps (every lane computes the same), then the look-back over the earlier tiles of this (job, dimension)
+		uint32_t rc = 0, rh = 0;
+		uint32_t wc = 0, wh = 0;
+#pragma unroll
+		for(int w2 = 0; w2 < SW_THREADS / 32; w2++) {
+			const uint32_t tc = sm_cnt[w2], th = sm_ht[w2];
+			if(w2 == lane) { wc = rc; wh = rh; }
+			rc += tc;
+			rh = ht_compose(rh, th);
 		}
-		rc = __shfl_sync(0xffffffffu, rc, 0);
-		rm = __shfl_sync(0xffffffffu, rm, 0);
-		// look-back: count of side-1 elements and transducer state before this tile; warp 0 probes 32 predecessors at a time
-		uint32_t carry_cnt = 0, carry_state = 3u;      // the first element of each child gets its boundary flag set
+		uint32_t carry_cnt = 0, carry_state = 3u;          // the first element of each child gets its boundary flag set
 		if(tile > 0) {
 			if(lane == 0)
-				st_volatile_u64(&lookback[w], lb_pack(rc, rm, LB_AGG));
-			uint32_t acc_map = MAP_IDENTITY;            // composition of the maps of the tiles between the probe window and this tile
+				st_volatile_u64(&lookback[w], lb2_pack(rc, rh, LB_AGG));
+			uint32_t acc = 0;                               // summary of the tiles between the probe window and this tile
 			uint64_t base = w - 1;
 			uint32_t remaining = tile;
 			bool done = false, failed = false;
@@ -720,7 +1050,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_partition(const uint32_t* __rest
 				unsigned long long v;
 				uint32_t first_prefix, spins = 0;
 				while(true) {
-					v = ((uint32_t)lane < cnt)? ld_volatile_u64(&lookback[base - lane]) : lb_pack(0, MAP_IDENTITY, LB_AGG);
+					v = ((uint32_t)lane < cnt)? ld_volatile_u64(&lookback[base - lane]) : lb2_pack(0, 0, LB_AGG);
 					const uint32_t st = (uint32_t)(v >> 62);
 					const uint32_t pm = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == LB_PREFIX);
 					const uint32_t em = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == LB_EMPTY);
@@ -735,28 +1065,24 @@ __global__ void __launch_bounds__(SW_THREADS) k_partition(const uint32_t* __rest
 				}
 				if(failed)
 					break;
-				// counts add up; maps compose in tile order: farthest first
-				uint32_t c = ((uint32_t)lane <= first_prefix && (uint32_t)lane < cnt)? (uint32_t)v : 0u;
+				const bool take = (uint32_t)lane < cnt && (uint32_t)lane <= first_prefix;
+				carry_cnt += __reduce_add_sync(0xffffffffu, take? (uint32_t)v : 0u);
+				// summaries compose in tile order: lane l holds tile base - l, i.e. higher lanes are EARLIER tiles.  Suffix-compose towards lane 0.
+				uint32_t h = (take && (uint32_t)lane != first_prefix)? ((uint32_t)(v >> 32) & 0xFu) : 0u;      // identity for lanes that do not take part
 #pragma unroll
-				for(int o = 16; o > 0; o >>= 1)
-					c += __shfl_xor_sync(0xffffffffu, c, o);
-				carry_cnt += c;
-				const uint32_t mine = (uint32_t)(v >> 32) & 0xFFu;
-				const int top = (int)min(first_prefix, cnt - 1);        // farthest lane that takes part
-				uint32_t window_map = MAP_IDENTITY, state_at_prefix = 0;
-				for(int l = top; l >= 0; l--) {
-					const uint32_t m = __shfl_sync(0xffffffffu, mine, l);
-					if((uint32_t)l == first_prefix)
-						state_at_prefix = m & 3u;
-					else
-						window_map = map_compose(window_map, m);
+				for(int o = 1; o < 32; o <<= 1) {
+					const uint32_t hh = __shfl_down_sync(0xffffffffu, h, o);
+					if(lane + o < 32)
+						h = ht_compose(hh, h);
 				}
+				const uint32_t window = __shfl_sync(0xffffffffu, h, 0);            // all aggregates of the window, earliest first
 				if(first_prefix < 32u) {
-					carry_state = map_apply(acc_map, map_apply(window_map, state_at_prefix));
+					const uint32_t state_at_prefix = (uint32_t)(__shfl_sync(0xffffffffu, v, (int)first_prefix) >> 32) & 3u;
+					carry_state = ht_apply(acc, ht_apply(window, state_at_prefix));
 					done = true;
 				}
 				else {
-					acc_map = map_compose(window_map, acc_map);
+					acc = ht_compose(window, acc);
 					base -= 32;
 					remaining -= 32;
 				}
@@ -764,38 +1090,39 @@ __global__ void __launch_bounds__(SW_THREADS) k_partition(const uint32_t* __rest
 			if(failed && lane == 0)
 				atomicExch(error_flag, 1);
 		}
-		if(lane == 0) {
-			st_volatile_u64(&lookback[w], lb_pack(carry_cnt + rc, map_apply(rm, carry_state), LB_PREFIX));
-			sm_carry[0] = carry_cnt;
-			sm_carry[1] = carry_state;
+		if(lane == 0)
+			st_volatile_u64(&lookback[w], lb2_pack(carry_cnt + rc, ht_apply(rh, carry_state), LB_PREFIX));
+		if(lane < SW_THREADS / 32) {
+			sm_cnt[lane] = carry_cnt + wc;                  // child-1 elements before warp `lane`
+			sm_ht[lane] = ht_apply(wh, carry_state);        // pending state when warp `lane` starts
 		}
 	}
 	__syncthreads();
-	// exclusive prefix for this thread
-	uint32_t ecnt = __shfl_up_sync(0xffffffffu, icnt, 1), emap = __shfl_up_sync(0xffffffffu, imap, 1);
+	if(!active)
+		return;
+	uint32_t ecnt = __shfl_up_sync(0xffffffffu, icnt, 1), eht = __shfl_up_sync(0xffffffffu, iht, 1);
 	if(lane == 0) {
 		ecnt = 0;
-		emap = MAP_IDENTITY;
+		eht = 0;
 	}
-	uint32_t before1 = sm_carry[0] + sm_cnt[warp] + ecnt;
-	uint32_t state = map_apply(emap, map_apply(sm_map[warp], sm_carry[1]));
+	const uint32_t row_before1 = sm_cnt[warp] + ecnt;
+	const uint32_t state = ht_apply(eht, sm_ht[warp]);      // pending when my row starts: lands on the first element of each child in the row
+	if(state & 1u)
+		newflags |= mS1 & (0u - mS1);
+	if(state & 2u)
+		newflags |= mS2 & (0u - mS2);
+	const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-	for(int j = 0; j < SW_ITEMS; j++) {
-		const uint32_t i = i0 + j;
-		if(i < jb.n) {
-			const uint32_t c = el[j] >> 31;
-			uint32_t e = el[j] & 0x7FFFFFFFu;
-			if((side1 >> j) & 1u) {
-				e |= (c | (state & 1u)) << 31;
+	for(int r = 0; r < 32; r++) {
+		const uint32_t S1r = __shfl_sync(0xffffffffu, mS1, r), Fr = __shfl_sync(0xffffffffu, newflags, r), b1 = __shfl_sync(0xffffffffu, row_before1, r);
+		const uint32_t idx = wbase + r * 32 + lane;
+		if(idx < jb.n) {
+			const uint32_t before1 = b1 + __popc(S1r & lt);
+			const uint32_t e = (el[r] & 0x7FFFFFFFu) | (((Fr >> lane) & 1u) << 31);
+			if((my1 >> r) & 1u)
 				dst1[before1] = e;
-				before1++;
-				state = ((state >> 1) | c) << 1;               // pend1 = 0, pend2 |= c
-			}
-			else {
-				e |= (c | (state >> 1)) << 31;
-				dst2[i - before1] = e;
-				state = (state & 1u) | c;                      // pend2 = 0, pend1 |= c
-			}
+			else
+				dst2[idx - before1] = e;
 		}
 	}
 }
@@ -1005,6 +1332,66 @@ __global__ void k_pack_elements(const KeyT* __restrict__ keys, const uint32_t* _
 		flip_pos[(uint64_t)d * K + scg_index[s]] = (uint32_t)i;
 }
 
+// flip list of every dimension: the scaffold ids of the class-1 elements in element order (stream compaction of E).
+// pass 1: class-1 elements per tile of SW_TILE; pass 2: a tile finds its offset by summing the counts of the tiles before it.
+__global__ void __launch_bounds__(256) k_flip_count(const uint32_t* __restrict__ E, uint64_t N, uint32_t tiles, uint32_t* __restrict__ counts)
+{
+	__shared__ uint32_t sm[8];
+	const uint32_t d = blockIdx.y, t = blockIdx.x;
+	const uint32_t* __restrict__ seg = E + (uint64_t)d * N;
+	const uint64_t i1 = min(N, (uint64_t)(t + 1) * SW_TILE);
+	uint32_t c = 0;
+	for(uint64_t i = (uint64_t)t * SW_TILE + threadIdx.x; i < i1; i += 256)
+		c += (seg[i] >> EL_CLASS_SHIFT) & 1u;
+	c = __reduce_add_sync(0xffffffffu, c);
+	if((threadIdx.x & 31) == 0)
+		sm[threadIdx.x >> 5] = c;
+	__syncthreads();
+	if(threadIdx.x == 0)
+		counts[(uint64_t)d * tiles + t] = sm[0] + sm[1] + sm[2] + sm[3] + sm[4] + sm[5] + sm[6] + sm[7];
+}
+
+__global__ void __launch_bounds__(256) k_flip_write(const uint32_t* __restrict__ E, uint64_t N, uint32_t tiles, const uint32_t* __restrict__ counts, uint32_t* __restrict__ list,
+                                                   uint64_t Sf)
+{
+	__shared__ uint32_t sm[9];
+	const uint32_t d = blockIdx.y, t = blockIdx.x;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t before = 0;
+	for(uint32_t i = threadIdx.x; i < t; i += 256)
+		before += counts[(uint64_t)d * tiles + i];
+	before = __reduce_add_sync(0xffffffffu, before);
+	if(lane == 0)
+		sm[warp] = before;
+	__syncthreads();
+	uint32_t run = sm[0] + sm[1] + sm[2] + sm[3] + sm[4] + sm[5] + sm[6] + sm[7];
+	__syncthreads();
+	const uint32_t* __restrict__ seg = E + (uint64_t)d * N;
+	uint32_t* __restrict__ out = list + (uint64_t)d * Sf;
+	const uint64_t i0 = (uint64_t)t * SW_TILE, i1 = min(N, i0 + SW_TILE);
+	for(uint64_t base = i0; base < i1; base += 256) {
+		const uint64_t i = base + threadIdx.x;
+		const uint32_t e = (i < i1)? seg[i] : 0u;
+		const bool flip = (e >> EL_CLASS_SHIFT) & 1u;
+		const uint32_t bal = __ballot_sync(0xffffffffu, flip);
+		if(lane == 0)
+			sm[warp] = __popc(bal);
+		__syncthreads();
+		uint32_t wex = 0, tot = 0;
+#pragma unroll
+		for(int w2 = 0; w2 < 8; w2++) {
+			const uint32_t x = sm[w2];
+			if(w2 < warp)
+				wex += x;
+			tot += x;
+		}
+		if(flip)
+			out[run + wex + __popc(bal & ((1u << lane) - 1u))] = e & EL_SCAF_MASK;
+		run += tot;
+		__syncthreads();
+	}
+}
+
 __global__ void k_iota_pairs(unsigned long long* __restrict__ keys, const uint32_t* __restrict__ flip_pos, uint32_t* __restrict__ vals, const uint32_t* __restrict__ scg_scafs,
                              uint64_t K, uint32_t nd)
 {
@@ -1043,6 +1430,12 @@ struct abw_search {
 	DevBuf<uint32_t> E[2];
 	DevBuf<uint32_t> scg_list[2];
 	DevBuf<uint32_t> scaf_list[2];
+	DevBuf<uint32_t> flip_list[2];            // sens/spec: [D][Sf] scaffolds that can flip, in the order of their flip elements, grouped by live cluster
+	DevBuf<uint2> F8;                         // [D][Sf] prefix sums over the flip list of the level (k_flip_prefix)
+	DevBuf<uint32_t> FC;                      // only when some scaffold has fewer datapoints in the matrix than T
+	DevBuf<uint32_t> scg_k;                   // [D][K]
+	bool partial = false;
+	uint64_t Sf = 0;                          // scaffolds with n >= T/2+1
 	DevBuf<uint8_t> side, assigned, new_assigned;
 	DevBuf<uint32_t> low, scaf_member, scaf_final;
 	std::vector<uint32_t> h_T;
@@ -1124,6 +1517,10 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		}
 		if(!((double)s->h_n[i] >= s->prm.fraction_dps_in * (double)s->h_T[i]))
 			s->root_viol++;
+		if(s->h_n[i] >= s->h_T[i] / 2 + 1)
+			s->Sf++;
+		if(s->h_n[i] != s->h_T[i])
+			s->partial = true;
 	}
 	if(s->root_totT >= (1ull << 31))
 		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: sum of T over scaffolds must be below 2^31");
@@ -1227,6 +1624,21 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	if(h_nan)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: NaN in the feature matrix (comp_by_value is not a strict weak order on NaN)");
 	keys.release(); keys_tmp.release(); vals.release(); vals_tmp.release(); cls.release();
+	// ---- per-dimension flip list: every scaffold that can flip has exactly one class-1 element per dimension
+	if(s->strategy == ABW_SENS_SPEC && s->Sf > 0) {
+		const uint64_t Sf = s->Sf;
+		for(int b = 0; b < 2; b++)
+			ABW_CUDA(ctx, s->flip_list[b].alloc((size_t)D * Sf));
+		ABW_CUDA(ctx, s->F8.alloc((size_t)D * Sf));
+		if(s->partial)
+			ABW_CUDA(ctx, s->FC.alloc((size_t)D * Sf));
+		ABW_CUDA(ctx, s->scg_k.alloc((size_t)D * std::max<uint64_t>(K, 1)));
+		const uint32_t tiles = abw_div_up(N, SW_TILE);
+		DevBuf<uint32_t> counts;
+		ABW_CUDA(ctx, counts.alloc((size_t)D * tiles));
+		ABW_LAUNCH(ctx, k_flip_count, dim3(tiles, D), 256, 0, s->E[0].p, N, tiles, counts.p);
+		ABW_LAUNCH(ctx, k_flip_write, dim3(tiles, D), 256, 0, s->E[0].p, N, tiles, counts.p, s->flip_list[0].p, Sf);
+	}
 	// ---- per-dimension list of SCG-carrying scaffolds in the order their flip element appears
 	if(s->strategy == ABW_SENS_SPEC && K > 0) {
 		DevBuf<unsigned long long> lk, lk_tmp;
@@ -1365,6 +1777,8 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 	level[0].desc.U = S;
 	level[0].desc.totLen = s->root_totLen;
 	level[0].desc.ss_ok = (s->root_viol == 0);
+	level[0].desc.fOff = 0;
+	level[0].desc.nf = (uint32_t)s->Sf;
 	level[0].nassigned = S;
 	level[0].never = s->root_never;
 	uint32_t next_id = 2, nrec = 0;
@@ -1372,7 +1786,9 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 
 	DevBuf<ClusterDesc> d_clusters;
 	DevBuf<CandRec> d_cand, d_best;
-	DevBuf<uint2> d_tile_tab, d_ptile_tab;
+	DevBuf<uint2> d_tile_tab, d_ptile_tab, d_ftile_tab, d_fp_tab;
+	DevBuf<PartJob> d_fjobs;
+	DevBuf<unsigned long long> d_lookback2;
 	DevBuf<uint32_t> d_status;
 	DevBuf<AggSlot> d_aggs, d_prefixes;
 	DevBuf<unsigned long long> d_ticket, d_lookback;
@@ -1381,6 +1797,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 	ABW_CUDA(ctx, d_error.alloc(1));
 	ABW_CUDA(ctx, cudaMemsetAsync(d_error.p, 0, sizeof(int), ctx->stream));
 	DevBuf<uint8_t> d_tab;
+	DevBuf<uint2> d_klohi;
 	DevBuf<uint64_t> d_suffix, d_never, d_child_never, d_union;
 	DevBuf<SplitJob> d_jobs, d_jobs_mine;
 	DevBuf<ChildStats> d_stats;
@@ -1429,9 +1846,14 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 		ABW_CHECK(to_device(ctx, d_tile_tab, tile_tab));
 		ABW_CHECK(to_device(ctx, d_clusters, descs));
 		if(d_cand.n < items) ABW_CUDA(ctx, d_cand.alloc(items));
-		if(d_status.n < items) ABW_CUDA(ctx, d_status.alloc(items));
-		if(d_aggs.n < items) ABW_CUDA(ctx, d_aggs.alloc(items));
-		if(d_prefixes.n < items) ABW_CUDA(ctx, d_prefixes.alloc(items));
+		if(s->strategy == ABW_SENS_SPEC) {
+			if(d_lookback.n < items) ABW_CUDA(ctx, d_lookback.alloc(items));
+		}
+		else {
+			if(d_status.n < items) ABW_CUDA(ctx, d_status.alloc(items));
+			if(d_aggs.n < items) ABW_CUDA(ctx, d_aggs.alloc(items));
+			if(d_prefixes.n < items) ABW_CUDA(ctx, d_prefixes.alloc(items));
+		}
 		if(d_best.n < C)
 			ABW_CUDA(ctx, d_best.alloc(C));
 		const uint64_t tab_stride = tab_total;
@@ -1439,20 +1861,47 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 			if(d_tab.n < (size_t)D * tab_stride)
 				ABW_CUDA(ctx, d_tab.alloc((size_t)D * tab_stride));
 			tm.start();
+			if(d_klohi.n < (size_t)D * C)
+				ABW_CUDA(ctx, d_klohi.alloc((size_t)D * C));
 			ABW_LAUNCH(ctx, k_pass_table, dim3(C, abw_div_up(D, 4)), 128, 0, s->scg_list[cur].p, (uint64_t)s->K, d_clusters.p, s->scgmask.p, W, d_never.p,
-			           prm.scg_overlap_threshold, d_suffix.p, d_tab.p, tab_stride, D);
+			           prm.scg_overlap_threshold, d_suffix.p, d_tab.p, tab_stride, D, d_klohi.p, (unsigned long long)prm.scg_min_size);
 			s->prof.other_ms += tm.stop();
 		}
 		// sweep
 		tm.start();
-		ABW_CUDA(ctx, cudaMemsetAsync(d_status.p, 0, sizeof(uint32_t) * items, ctx->stream));
 		ABW_CUDA(ctx, cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned long long), ctx->stream));
-		if(s->strategy == ABW_SENS_SPEC)
-			ABW_LAUNCH(ctx, k_sweep<ABW_SENS_SPEC>, (unsigned int)items, SW_THREADS, 0, s->E[cur].p, N, d_clusters.p, TT, d_tile_tab.p, s->rows.p, d_tab.p, tab_stride, sp,
-			           d_ticket.p, d_status.p, d_aggs.p, d_prefixes.p, d_cand.p, d_error.p);
-		else
+		if(s->strategy == ABW_SENS_SPEC) {
+			ABW_CUDA(ctx, cudaMemsetAsync(d_lookback.p, 0, sizeof(unsigned long long) * items, ctx->stream));
+			if(s->Sf > 0) {
+				std::vector<uint2> fp_tab;
+				for(uint32_t c = 0; c < C; c++) {
+					const uint32_t tiles = (level[c].desc.nf + FP_TILE - 1) / FP_TILE;
+					for(uint32_t t = 0; t < tiles; t++)
+						fp_tab.push_back(make_uint2(c, t));
+				}
+				const uint32_t FPT = (uint32_t)fp_tab.size();
+				const uint64_t fp_items = (uint64_t)FPT * D;
+				if(fp_items > 0) {
+					ABW_CHECK(to_device(ctx, d_fp_tab, fp_tab));
+					if(d_status.n < fp_items) ABW_CUDA(ctx, d_status.alloc(fp_items));
+					if(d_aggs.n < fp_items) ABW_CUDA(ctx, d_aggs.alloc(fp_items));
+					if(d_prefixes.n < fp_items) ABW_CUDA(ctx, d_prefixes.alloc(fp_items));
+					ABW_CUDA(ctx, cudaMemsetAsync(d_status.p, 0, sizeof(uint32_t) * fp_items, ctx->stream));
+					ABW_LAUNCH(ctx, k_flip_prefix, (unsigned int)fp_items, SW_THREADS, 0, s->flip_list[cur].p, s->Sf, d_clusters.p, FPT, d_fp_tab.p, s->rows.p, s->has_scg.p,
+					           d_ticket.p, d_status.p, d_aggs.p, d_prefixes.p, s->F8.p, s->FC.p, s->scg_k.p, (uint64_t)s->K, d_klohi.p, C,
+					           (unsigned long long)prm.scg_min_size, d_error.p);
+					ABW_CUDA(ctx, cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned long long), ctx->stream));
+				}
+			}
+			ABW_LAUNCH(ctx, k_sweep_ss, (unsigned int)items, SW_THREADS, 0, s->E[cur].p, N, d_clusters.p, TT, d_tile_tab.p, s->F8.p, s->FC.p, s->scg_k.p, (uint64_t)s->K,
+			           d_klohi.p, C, s->Sf, d_tab.p, tab_stride, sp,
+			           d_ticket.p, d_lookback.p, d_cand.p, d_error.p);
+		}
+		else {
+			ABW_CUDA(ctx, cudaMemsetAsync(d_status.p, 0, sizeof(uint32_t) * items, ctx->stream));
 			ABW_LAUNCH(ctx, k_sweep<ABW_SPLIT_SCAFS>, (unsigned int)items, SW_THREADS, 0, s->E[cur].p, N, d_clusters.p, TT, d_tile_tab.p, s->rows.p, (const uint8_t*)nullptr,
 			           tab_stride, sp, d_ticket.p, d_status.p, d_aggs.p, d_prefixes.p, d_cand.p, d_error.p);
+		}
 		s->prof.sweep_ms += tm.stop();
 		s->prof.sweep_launches++;
 		for(uint32_t c = 0; c < C; c++)
@@ -1574,7 +2023,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 		}
 		// decide
 		std::vector<HostCluster> next;
-		std::vector<PartJob> pjobs;
+		std::vector<PartJob> pjobs, fjobs;
 		std::vector<ListJob> ljobs_scaf, ljobs_scg;
 		std::vector<SplitJob> commit_jobs;
 		std::vector<TermJob> tjobs;
@@ -1608,7 +2057,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 						r.child2_raw = level[c].desc.n - r.child1_raw;
 						const ChildStats* st[2] = {&s1, &s2};
 						uint64_t off = level[c].desc.off;
-						uint32_t kOff = level[c].desc.kOff, sOff = level[c].desc.sOff;
+						uint32_t kOff = level[c].desc.kOff, sOff = level[c].desc.sOff, fOff = level[c].desc.fOff;
 						for(int ch = 0; ch < 2; ch++) {
 							HostCluster hc;
 							hc.id = ch? r.child2 : r.child1;
@@ -1623,11 +2072,14 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 							hc.desc.U = st[ch]->ns;
 							hc.desc.totLen = st[ch]->totLen;
 							hc.desc.ss_ok = (st[ch]->viol == 0);
+							hc.desc.fOff = fOff;
+							hc.desc.nf = st[ch]->nflip;
 							hc.nassigned = st[ch]->nassigned;
 							hc.never.assign(child_never.begin() + ((size_t)j * 2 + ch) * W, child_never.begin() + ((size_t)j * 2 + ch + 1) * W);
 							off += st[ch]->ndps;
 							kOff += st[ch]->K;
 							sOff += st[ch]->ns;
+							fOff += st[ch]->nflip;
 							next.push_back(hc);
 						}
 						PartJob pj;
@@ -1637,6 +2089,9 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 						ljobs_scaf.push_back(l1);
 						ListJob l2; l2.off = level[c].desc.kOff; l2.n = level[c].desc.K; l2.n1 = s1.K;
 						ljobs_scg.push_back(l2);
+						PartJob fj;
+						fj.off = level[c].desc.fOff; fj.n = level[c].desc.nf; fj.n1 = s1.nflip;
+						fjobs.push_back(fj);
 						commit_jobs.push_back(jobs[j]);
 					}
 					else {
@@ -1723,8 +2178,28 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 			tm.start();
 			ABW_CUDA(ctx, cudaMemsetAsync(d_lookback.p, 0, sizeof(unsigned long long) * pitems, ctx->stream));
 			ABW_CUDA(ctx, cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned long long), ctx->stream));
-			ABW_LAUNCH(ctx, k_partition, (unsigned int)pitems, SW_THREADS, 0, s->E[cur].p, s->E[cur ^ 1].p, N, d_pjobs.p, PTT, d_ptile_tab.p, s->side.p, d_ticket.p,
+			ABW_LAUNCH(ctx, k_partition2, (unsigned int)pitems, SW_THREADS, 0, s->E[cur].p, s->E[cur ^ 1].p, N, d_pjobs.p, PTT, d_ptile_tab.p, s->side.p, d_ticket.p,
 			           d_lookback.p, d_error.p);
+			if(s->strategy == ABW_SENS_SPEC && s->Sf > 0) {
+				// the flip lists are partitioned like the elements (the flag bit the kernel maintains is ignored by their reader)
+				std::vector<uint2> ftile_tab;
+				for(uint32_t i = 0; i < P; i++) {
+					const uint32_t tiles = (fjobs[i].n + SW_TILE - 1) / SW_TILE;
+					for(uint32_t t = 0; t < tiles; t++)
+						ftile_tab.push_back(make_uint2(i, t));
+				}
+				const uint32_t FTT = (uint32_t)ftile_tab.size();
+				const uint64_t fitems = (uint64_t)FTT * D;
+				if(fitems > 0) {
+					ABW_CHECK(to_device(ctx, d_ftile_tab, ftile_tab));
+					ABW_CHECK(to_device(ctx, d_fjobs, fjobs));
+					if(d_lookback2.n < fitems) ABW_CUDA(ctx, d_lookback2.alloc(fitems));
+					ABW_CUDA(ctx, cudaMemsetAsync(d_lookback2.p, 0, sizeof(unsigned long long) * fitems, ctx->stream));
+					ABW_CUDA(ctx, cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned long long), ctx->stream));
+					ABW_LAUNCH(ctx, k_partition2, (unsigned int)fitems, SW_THREADS, 0, s->flip_list[cur].p, s->flip_list[cur ^ 1].p, s->Sf, d_fjobs.p, FTT, d_ftile_tab.p,
+					           s->side.p, d_ticket.p, d_lookback2.p, d_error.p);
+				}
+			}
 			s->prof.partition_ms += tm.stop();
 			for(uint32_t i = 0; i < P; i++)
 				s->prof.partition_elements += (uint64_t)pjobs[i].n * D;

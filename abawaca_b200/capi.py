@@ -61,7 +61,7 @@ EXPORTS = [
     "abw_ctx_create", "abw_ctx_destroy", "abw_last_error", "abw_version", "abw_default_params", "abw_kernel_launches", "abw_ctx_stream",
     "abw_ctx_synchronize", "abw_profile_enable", "abw_profile_report", "abw_pack_sequences", "abw_seqset_destroy", "abw_seqset_stats", "abw_segment", "abw_segments_destroy",
     "abw_segments_count", "abw_segments_get", "abw_kmer_features", "abw_coverage", "abw_device_alloc", "abw_device_free",
-    "abw_copy_to_device", "abw_copy_to_host", "abw_memset_device", "abw_h2d_async", "abw_wait_h2d", "abw_search_create", "abw_search_destroy", "abw_search_run",
+    "abw_copy_to_device", "abw_copy_to_host", "abw_memset_device", "abw_h2d_async", "abw_wait_h2d", "abw_d2h_async", "abw_search_create", "abw_search_destroy", "abw_search_run",
     "abw_search_set_shard", "abw_search_set_max_levels", "abw_search_run_sharded", "abw_search_get_profile", "abw_cluster_scg",
 ]
 
@@ -104,6 +104,7 @@ def load():
     L.abw_memset_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]
     L.abw_h2d_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
     L.abw_wait_h2d.argtypes = [C.c_void_p, C.c_uint64]
+    L.abw_d2h_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.abw_search_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     L.abw_search_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p]
@@ -198,6 +199,10 @@ class Context:
 
     def wait_h2d(self, ticket):
         self.check(self.lib.abw_wait_h2d(self.h, ticket))
+
+    def d2h_async(self, arr, dptr, nbytes=None):
+        """enqueue a copy into a (pinned) numpy array on the copy stream; complete after synchronize()"""
+        self.check(self.lib.abw_d2h_async(self.h, _p(arr), C.c_void_p(dptr), arr.nbytes if nbytes is None else nbytes))
 
     def memset(self, dptr, byte, nbytes):
         self.check(self.lib.abw_memset_device(self.h, C.c_void_p(dptr), byte, nbytes))

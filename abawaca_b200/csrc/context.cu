@@ -182,6 +182,20 @@ int abw_h2d_async(abw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, ui
 	return ABW_OK;
 }
 
+int abw_d2h_async(abw_ctx* ctx, void* h_dst, const void* d_src, size_t bytes)
+{
+	if(!ctx || (!h_dst && bytes) || (!d_src && bytes))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_d2h_async: null argument");
+	// everything enqueued on the compute stream so far produces d_src; later compute overlaps the copy
+	cudaEvent_t ready;
+	ABW_CUDA(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+	ABW_CUDA(ctx, cudaEventRecord(ready, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
+	ABW_CUDA(ctx, cudaEventDestroy(ready));
+	ABW_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+	return ABW_OK;
+}
+
 int abw_wait_h2d(abw_ctx* ctx, uint64_t ticket)
 {
 	if(!ctx || ticket > ctx->copy_events.size())

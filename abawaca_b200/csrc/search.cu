@@ -754,7 +754,7 @@ __global__ void k_pass_table(const uint32_t* __restrict__ scg_list, uint64_t lis
 		uint64_t carry = 0;
 		for(int64_t base = (int64_t)((K + 31) / 32) * 32 - 32; base >= 0; base -= 32) {
 			const uint32_t k = (uint32_t)base + lane;
-			uint64_t m = (k < K)? scgmask[(uint64_t)list[k] * W + w] : 0ull;
+			uint64_t m = (k < K)? scgmask[(uint64_t)(list[k] & EL_SCAF_MASK) * W + w] : 0ull;
 #pragma unroll
 			for(int o = 1; o < 32; o <<= 1) {
 				uint64_t x = __shfl_down_sync(0xffffffffu, m, o);
@@ -779,7 +779,7 @@ __global__ void k_pass_table(const uint32_t* __restrict__ scg_list, uint64_t lis
 #pragma unroll
 		for(uint32_t w = 0; w < SCG_WMAX; w++) {
 			if(w < W) {
-				uint64_t pre = (k >= 1 && k - 1 < K)? scgmask[(uint64_t)list[k - 1] * W + w] : 0ull;
+				uint64_t pre = (k >= 1 && k - 1 < K)? scgmask[(uint64_t)(list[k - 1] & EL_SCAF_MASK) * W + w] : 0ull;
 #pragma unroll
 				for(int o = 1; o < 32; o <<= 1) {
 					uint64_t x = __shfl_up_sync(0xffffffffu, pre, o);
@@ -854,7 +854,7 @@ __global__ void __launch_bounds__(128) k_scaf_sides(const uint32_t* __restrict__
 		unsigned long long rlen = 0, kth = 0;
 		bool assigned_any = false, flippable = false, has_scg = false, viol = false;
 		if(active) {
-			const uint32_t s = scaf_list[cl.sOff + i];
+			const uint32_t s = scaf_list[cl.sOff + i] & EL_SCAF_MASK;      // the partition kernel leaves its flag bit on list entries
 			const ScafRow r = rows[s];
 			const uint32_t lo = low[s];
 			const uint32_t c1 = jb.swapped? r.n - lo : lo, c2 = r.n - c1;
@@ -929,7 +929,7 @@ __global__ void k_clear_low(const uint32_t* __restrict__ scaf_list, const Cluste
 	const SplitJob jb = jobs[blockIdx.y];
 	const ClusterDesc cl = clusters[jb.cluster];
 	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cl.ns; i += gridDim.x * blockDim.x)
-		low[scaf_list[cl.sOff + i]] = 0;
+		low[scaf_list[cl.sOff + i] & EL_SCAF_MASK] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1127,50 +1127,6 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_partition2(const uint32_t* __
 	}
 }
 
-// stable partition of small u32 lists of scaffold ids (scaffold list: 1 "dimension"; SCG lists: D dimensions); one warp per (job, dimension)
-struct ListJob { uint32_t off, n, n1; };
-__global__ void __launch_bounds__(256) k_partition_list(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t stride, const ListJob* __restrict__ jobs,
-                                                       const uint8_t* __restrict__ side)
-{
-	__shared__ uint32_t sm[9];
-	const uint32_t d = blockIdx.y;
-	const ListJob jb = jobs[blockIdx.x];
-	const uint32_t* __restrict__ src = in + (uint64_t)d * stride + jb.off;
-	uint32_t* __restrict__ dst1 = out + (uint64_t)d * stride + jb.off;
-	uint32_t* __restrict__ dst2 = dst1 + jb.n1;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t c1 = 0;
-	for(uint32_t base = 0; base < jb.n; base += blockDim.x) {
-		const uint32_t i = base + threadIdx.x;
-		uint32_t sc = 0, sd = 0;
-		if(i < jb.n) {
-			sc = src[i];
-			sd = side[sc];
-		}
-		const uint32_t b1 = __ballot_sync(0xffffffffu, sd == 1u);
-		if(lane == 0)
-			sm[warp] = __popc(b1);
-		__syncthreads();
-		if(threadIdx.x == 0) {
-			uint32_t run = 0;
-			for(int w2 = 0; w2 < 8; w2++) {
-				uint32_t t = sm[w2];
-				sm[w2] = run;
-				run += t;
-			}
-			sm[8] = run;
-		}
-		__syncthreads();
-		const uint32_t before = c1 + sm[warp] + __popc(b1 & ((1u << lane) - 1u));
-		if(i < jb.n) {
-			if(sd == 1u) dst1[before] = sc;
-			else dst2[i - before] = sc;
-		}
-		c1 += sm[8];
-		__syncthreads();
-	}
-}
-
 // terminal cluster: bins of its scaffolds and datapoints (abawaca.cpp:135-138), total size and SCG tallies (ClusterQuality.cpp:44-48,78-87)
 struct TermJob { uint32_t sOff, ns, id, slot; };
 struct TermStats { unsigned long long total_size, scg_copies; };
@@ -1180,7 +1136,7 @@ __global__ void k_finalize_terminal(const uint32_t* __restrict__ scaf_list, cons
 {
 	const TermJob jb = jobs[blockIdx.y];
 	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.ns; i += gridDim.x * blockDim.x) {
-		const uint32_t s = scaf_list[jb.sOff + i];
+		const uint32_t s = scaf_list[jb.sOff + i] & EL_SCAF_MASK;
 		scaf_member[s] = jb.id;
 		if(assigned[s]) {
 			scaf_final[s] = jb.id;
@@ -1205,7 +1161,7 @@ __global__ void k_commit_assigned(const uint32_t* __restrict__ scaf_list, const 
 	const SplitJob jb = jobs[blockIdx.y];
 	const ClusterDesc cl = clusters[jb.cluster];
 	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cl.ns; i += gridDim.x * blockDim.x) {
-		const uint32_t s = scaf_list[cl.sOff + i];
+		const uint32_t s = scaf_list[cl.sOff + i] & EL_SCAF_MASK;      // the partition kernel leaves its flag bit on list entries
 		assigned[s] = new_assigned[s] != 0;
 	}
 }
@@ -1786,9 +1742,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 
 	DevBuf<ClusterDesc> d_clusters;
 	DevBuf<CandRec> d_cand, d_best;
-	DevBuf<uint2> d_tile_tab, d_ptile_tab, d_ftile_tab, d_fp_tab;
-	DevBuf<PartJob> d_fjobs;
-	DevBuf<unsigned long long> d_lookback2;
+	DevBuf<uint2> d_tile_tab, d_ptile_tab, d_fp_tab;
 	DevBuf<uint32_t> d_status;
 	DevBuf<AggSlot> d_aggs, d_prefixes;
 	DevBuf<unsigned long long> d_ticket, d_lookback;
@@ -1803,7 +1757,6 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 	DevBuf<ChildStats> d_stats;
 	DevBuf<unsigned long long> d_value_key;
 	DevBuf<PartJob> d_pjobs;
-	DevBuf<ListJob> d_ljobs_scaf, d_ljobs_scg;
 	DevBuf<TermJob> d_tjobs;
 	DevBuf<TermStats> d_tstats;
 	if(s->strategy == ABW_SENS_SPEC)
@@ -2023,8 +1976,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 		}
 		// decide
 		std::vector<HostCluster> next;
-		std::vector<PartJob> pjobs, fjobs;
-		std::vector<ListJob> ljobs_scaf, ljobs_scg;
+		std::vector<PartJob> pjobs, fjobs, sjobs, kjobs;
 		std::vector<SplitJob> commit_jobs;
 		std::vector<TermJob> tjobs;
 		std::vector<abw_cluster_rec> recs(C);
@@ -2085,10 +2037,10 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 						PartJob pj;
 						pj.off = level[c].desc.off; pj.n = level[c].desc.n; pj.n1 = (uint32_t)s1.ndps;
 						pjobs.push_back(pj);
-						ListJob l1; l1.off = level[c].desc.sOff; l1.n = level[c].desc.ns; l1.n1 = s1.ns;
-						ljobs_scaf.push_back(l1);
-						ListJob l2; l2.off = level[c].desc.kOff; l2.n = level[c].desc.K; l2.n1 = s1.K;
-						ljobs_scg.push_back(l2);
+						PartJob l1; l1.off = level[c].desc.sOff; l1.n = level[c].desc.ns; l1.n1 = s1.ns;
+						sjobs.push_back(l1);
+						PartJob l2; l2.off = level[c].desc.kOff; l2.n = level[c].desc.K; l2.n1 = s1.K;
+						kjobs.push_back(l2);
 						PartJob fj;
 						fj.off = level[c].desc.fOff; fj.n = level[c].desc.nf; fj.n1 = s1.nflip;
 						fjobs.push_back(fj);
@@ -2143,67 +2095,66 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 		for(uint32_t c = 0; c < C; c++)
 			emit(recs[c]);
 		s->prof.other_ms += tm.stop();
-		// partition the split clusters
+		// partition the split clusters: elements, flip lists, SCG lists and the scaffold list all go through the same kernel
 		if(!pjobs.empty()) {
 			const uint32_t P = (uint32_t)pjobs.size();
-			ABW_CHECK(to_device(ctx, d_pjobs, pjobs));
-			ABW_CHECK(to_device(ctx, d_ljobs_scaf, ljobs_scaf));
-			ABW_CHECK(to_device(ctx, d_ljobs_scg, ljobs_scg));
 			ABW_CHECK(to_device(ctx, d_jobs, commit_jobs));
 			tm.start();
 			{
 				dim3 g(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), P);
 				ABW_LAUNCH(ctx, k_commit_assigned, g, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs.p, s->new_assigned.p, s->assigned.p);
-				ABW_LAUNCH(ctx, k_partition_list, dim3(P, 1), 256, 0, s->scaf_list[cur].p, s->scaf_list[cur ^ 1].p, (uint64_t)S, d_ljobs_scaf.p, s->side.p);
-				if(s->strategy == ABW_SENS_SPEC && s->K > 0 && !last_level)
-					ABW_LAUNCH(ctx, k_partition_list, dim3(P, D), 256, 0, s->scg_list[cur].p, s->scg_list[cur ^ 1].p, (uint64_t)s->K, d_ljobs_scg.p, s->side.p);
 			}
-			s->prof.other_ms += tm.stop();
+			// which arrays take part, in one plan so that the look-back words and tickets are cleared with a single memset
+			struct PartPlan { const uint32_t* in; uint32_t* out; uint64_t stride; uint32_t ndims; const std::vector<PartJob>* jv; uint32_t TT; uint64_t items, lb_off, tab_off, job_off; };
+			std::vector<PartPlan> plans;
+			plans.push_back({s->scaf_list[cur].p, s->scaf_list[cur ^ 1].p, (uint64_t)S, 1u, &sjobs, 0, 0, 0, 0, 0});
+			if(!last_level) {
+				plans.push_back({s->E[cur].p, s->E[cur ^ 1].p, N, D, &pjobs, 0, 0, 0, 0, 0});
+				if(s->strategy == ABW_SENS_SPEC && s->Sf > 0)
+					plans.push_back({s->flip_list[cur].p, s->flip_list[cur ^ 1].p, s->Sf, D, &fjobs, 0, 0, 0, 0, 0});
+				if(s->strategy == ABW_SENS_SPEC && s->K > 0)
+					plans.push_back({s->scg_list[cur].p, s->scg_list[cur ^ 1].p, (uint64_t)s->K, D, &kjobs, 0, 0, 0, 0, 0});
+			}
+			std::vector<uint2> all_tab;
+			std::vector<PartJob> all_jobs;
+			uint64_t lb_total = 8;                              // words 0..7: tickets
+			for(PartPlan& pl : plans) {
+				pl.tab_off = all_tab.size();
+				pl.job_off = all_jobs.size();
+				for(uint32_t i = 0; i < P; i++) {
+					all_jobs.push_back((*pl.jv)[i]);
+					const uint32_t tiles = ((*pl.jv)[i].n + SW_TILE - 1) / SW_TILE;
+					for(uint32_t t = 0; t < tiles; t++)
+						all_tab.push_back(make_uint2(i, t));
+				}
+				pl.TT = (uint32_t)(all_tab.size() - pl.tab_off);
+				pl.items = (uint64_t)pl.TT * pl.ndims;
+				pl.lb_off = lb_total;
+				lb_total += pl.items;
+				if(pl.items >= (1ull << 31))
+					return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_run: more than 2^31 tiles in one level");
+			}
+			ABW_CHECK(to_device(ctx, d_ptile_tab, all_tab));
+			ABW_CHECK(to_device(ctx, d_pjobs, all_jobs));
+			if(d_lookback.n < lb_total) ABW_CUDA(ctx, d_lookback.alloc(lb_total));
+			ABW_CUDA(ctx, cudaMemsetAsync(d_lookback.p, 0, sizeof(unsigned long long) * lb_total, ctx->stream));
+			for(size_t i = 0; i < plans.size(); i++) {
+				const PartPlan& pl = plans[i];
+				if(pl.items == 0)
+					continue;
+				ABW_LAUNCH(ctx, k_partition2, (unsigned int)pl.items, SW_THREADS, 0, pl.in, pl.out, pl.stride, d_pjobs.p + pl.job_off, pl.TT, d_ptile_tab.p + pl.tab_off, s->side.p,
+				           d_lookback.p + i, d_lookback.p + pl.lb_off, d_error.p);
+			}
+			s->prof.partition_ms += tm.stop();
+			if(!last_level)
+				for(uint32_t i = 0; i < P; i++)
+					s->prof.partition_elements += (uint64_t)pjobs[i].n * D;
+			cur ^= 1;
 			if(last_level) {
 				// the children are not going to be evaluated: only their scaffold lists are needed (for the bins)
-				cur ^= 1;
 				level.swap(next);
 				break;
 			}
-			std::vector<uint2> ptile_tab;
-			for(uint32_t i = 0; i < P; i++) {
-				const uint32_t tiles = (pjobs[i].n + SW_TILE - 1) / SW_TILE;
-				for(uint32_t t = 0; t < tiles; t++)
-					ptile_tab.push_back(make_uint2(i, t));
-			}
-			const uint32_t PTT = (uint32_t)ptile_tab.size();
-			const uint64_t pitems = (uint64_t)PTT * D;
-			ABW_CHECK(to_device(ctx, d_ptile_tab, ptile_tab));
-			if(d_lookback.n < pitems) ABW_CUDA(ctx, d_lookback.alloc(pitems));
-			tm.start();
-			ABW_CUDA(ctx, cudaMemsetAsync(d_lookback.p, 0, sizeof(unsigned long long) * pitems, ctx->stream));
-			ABW_CUDA(ctx, cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned long long), ctx->stream));
-			ABW_LAUNCH(ctx, k_partition2, (unsigned int)pitems, SW_THREADS, 0, s->E[cur].p, s->E[cur ^ 1].p, N, d_pjobs.p, PTT, d_ptile_tab.p, s->side.p, d_ticket.p,
-			           d_lookback.p, d_error.p);
-			if(s->strategy == ABW_SENS_SPEC && s->Sf > 0) {
-				// the flip lists are partitioned like the elements (the flag bit the kernel maintains is ignored by their reader)
-				std::vector<uint2> ftile_tab;
-				for(uint32_t i = 0; i < P; i++) {
-					const uint32_t tiles = (fjobs[i].n + SW_TILE - 1) / SW_TILE;
-					for(uint32_t t = 0; t < tiles; t++)
-						ftile_tab.push_back(make_uint2(i, t));
-				}
-				const uint32_t FTT = (uint32_t)ftile_tab.size();
-				const uint64_t fitems = (uint64_t)FTT * D;
-				if(fitems > 0) {
-					ABW_CHECK(to_device(ctx, d_ftile_tab, ftile_tab));
-					ABW_CHECK(to_device(ctx, d_fjobs, fjobs));
-					if(d_lookback2.n < fitems) ABW_CUDA(ctx, d_lookback2.alloc(fitems));
-					ABW_CUDA(ctx, cudaMemsetAsync(d_lookback2.p, 0, sizeof(unsigned long long) * fitems, ctx->stream));
-					ABW_CUDA(ctx, cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned long long), ctx->stream));
-					ABW_LAUNCH(ctx, k_partition2, (unsigned int)fitems, SW_THREADS, 0, s->flip_list[cur].p, s->flip_list[cur ^ 1].p, s->Sf, d_fjobs.p, FTT, d_ftile_tab.p,
-					           s->side.p, d_ticket.p, d_lookback2.p, d_error.p);
-				}
-			}
-			s->prof.partition_ms += tm.stop();
-			for(uint32_t i = 0; i < P; i++)
-				s->prof.partition_elements += (uint64_t)pjobs[i].n * D;
-			cur ^= 1;
 		}
 		level.swap(next);
 		if(last_level)

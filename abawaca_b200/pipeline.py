@@ -21,10 +21,18 @@ class FeatureBuild:
     def __init__(self, ctx, seqset, segs, d_rows, nseg, ncols, nscaf, d_nbps):
         self.ctx, self.seqset, self.segs, self.d_rows, self.nseg, self.ncols, self.nscaf, self.d_nbps = ctx, seqset, segs, d_rows, nseg, ncols, nscaf, d_nbps
 
-    def rows_host(self):
-        out = np.empty((self.nseg, self.ncols), dtype=np.float64)
+    def rows_host(self, out=None, wait=True):
+        """The .lrn matrix.  `out`: a (pinned) float64 buffer of at least nseg*ncols elements to fill instead of a fresh array;
+        wait=False enqueues the copy on the copy stream (it overlaps later device work; complete after ctx.synchronize())."""
+        if out is None:
+            out = np.empty((self.nseg, self.ncols), dtype=np.float64)
+        else:
+            out = out.reshape(-1)[:self.nseg * self.ncols].reshape(self.nseg, self.ncols)
         if out.size:
-            self.ctx.to_host(out, self.d_rows)
+            if wait:
+                self.ctx.to_host(out, self.d_rows)
+            else:
+                self.ctx.d2h_async(out, self.d_rows)
         return out
 
     def segments_host(self):

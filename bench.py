@@ -264,16 +264,23 @@ def main():
             fb = pipeline.build_features(ctx, d_seq, mg.offsets, d_reads, this_sample=0, seq_on_device=True, reads_on_device=True, nreads=nreads, timings=timings)
         else:
             fb = pipeline.build_features(ctx, h_seq.numpy(), mg.offsets, h_reads_np, this_sample=0, timings=timings, overlap_h2d=True)
+        t_a = time.perf_counter()
         sg = fb.segments_host()
+        t_b = time.perf_counter()
         keep, dp2scaf, T, kept = pipeline.search_problem_from_features(sg["seg_scaf"], nscaf)
-        rows_host = None
+        if timings is not None:
+            timings["segments_host_ms"] = 1000.0 * (t_b - t_a)
+            timings["search_problem_ms"] = 1000.0 * (time.perf_counter() - t_b)
         if not resident:
-            rows_host = fb.rows_host()                 # the .lrn matrix goes back to the host in the end-to-end path
+            # the .lrn matrix goes back to the host (pinned buffer) in the end-to-end path, while the split search runs
+            if state.get("h_rows") is None or state["h_rows"].numel() < fb.nseg * fb.ncols:
+                state["h_rows"] = torch.empty(int(fb.nseg * fb.ncols * 1.05) + 1024, dtype=torch.float64).pin_memory()
+            fb.rows_host(out=state["h_rows"].numpy(), wait=False)
         if world == 1:
             row_of_dp = None if keep.all() else np.nonzero(keep)[0].astype(np.uint64)   # scaffolds with one window are dropped (ScafDpData.cpp:92-93)
             res = pipeline.search(ctx, fb.d_rows, dp2scaf, T, lengths[kept], masks[kept], layout=capi.LAYOUT_ROWMAJOR, values_on_device=True,
                                   nrows=fb.nseg, D=fb.ncols, ld=fb.ncols, row_of_dp=row_of_dp, timings=timings)
-            nbins = len(set(res.scaf2cluster.tolist()) - {0})
+            nbins = int(np.count_nonzero(np.unique(res.scaf2cluster)))
             ndps_total = int(keep.sum())
         else:
             # 1) every rank holds the rows of its own scaffolds: all-gather them (NCCL) so that every rank has all datapoints
@@ -296,9 +303,11 @@ def main():
             res = pipeline.search(ctx, full.data_ptr() + 8 * off, dp2scaf_all, T_all, sc_all[:, 1].astype(np.uint64), sc_all[:, 2].astype(np.uint64),
                                   layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=int(full.shape[0]), D=cnt, ld=fb.ncols, timings=timings,
                                   collectives=coll, dim_offset=off, D_total=fb.ncols)
-            nbins = len(set(res.scaf2cluster.tolist()) - {0})
+            nbins = int(np.count_nonzero(np.unique(res.scaf2cluster)))
             ndps_total = int(full.shape[0])
             del full
+        if not resident:
+            ctx.synchronize()                          # the matrix has arrived on the host (copy stream) before the step counts as done
         state.update(ndps=ndps_total, nseg=fb.nseg, ncols=fb.ncols, prof=res.profile, nclusters=len(res.recs), nbins=nbins,
                      seg_len=(sg["seg_end"] - sg["seg_start"] + 1), bins=res.scaf2cluster)
         fb.close()

@@ -123,6 +123,9 @@ int abw_memset_device(abw_ctx* ctx, void* d_ptr, int byte, size_t bytes);
  * abw_pack_sequences / abw_coverage call.  Tickets are retired by abw_ctx_synchronize. */
 int abw_h2d_async(abw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, uint64_t* ticket);
 int abw_wait_h2d(abw_ctx* ctx, uint64_t ticket);
+/* Device-to-host copy into PINNED host memory on the copy stream, ordered after everything enqueued on the context so far and overlapping
+ * whatever is enqueued next (e.g. the .lrn matrix travels back while the split search runs).  Complete after abw_ctx_synchronize. */
+int abw_d2h_async(abw_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 
 /* ---- split search (abawaca) ----------------------------------------------------------------- */
 

@@ -25,6 +25,7 @@ struct abw_segments {
 	DevBuf<uint32_t> seg_scaf;            // [nseg]
 	DevBuf<uint64_t> seg_start, seg_end, seg_nonN;   // 1-based inclusive, abawaca-build.cpp:216
 	DevBuf<uint64_t> seg_gbase;           // absolute (padded) base index of the first base of the segment
+	DevBuf<uint4> scaf_info;              // per scaffold {first window (low 32 bits), windows, non-N bases per window (u64)}: one load for the coverage kernels
 };
 
 namespace {
@@ -158,7 +159,7 @@ __global__ void k_seg_count(const uint64_t* __restrict__ len, const unsigned lon
 __global__ void __launch_bounds__(256) k_seg_fill(const uint64_t* __restrict__ len, const unsigned long long* __restrict__ countN, const uint64_t* __restrict__ base,
                                                   const uint32_t* __restrict__ nmask, uint32_t nscaf, uint64_t window, const uint64_t* __restrict__ seg_first,
                                                   uint32_t* __restrict__ seg_scaf, uint64_t* __restrict__ seg_start, uint64_t* __restrict__ seg_end,
-                                                  uint64_t* __restrict__ seg_nonN, uint64_t* __restrict__ seg_gbase)
+                                                  uint64_t* __restrict__ seg_nonN, uint64_t* __restrict__ seg_gbase, uint4* __restrict__ scaf_info)
 {
 	const int lane = threadIdx.x & 31;
 	const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -166,6 +167,8 @@ __global__ void __launch_bounds__(256) k_seg_fill(const uint64_t* __restrict__ l
 		const uint64_t L = len[s], b0 = base[s], first = seg_first[s];
 		uint64_t nbps, count;
 		window_plan(L, countN[s], window, nbps, count);
+		if(lane == 0)
+			scaf_info[s] = make_uint4((uint32_t)first, (uint32_t)min(count, (uint64_t)0xFFFFFFFFu), (uint32_t)nbps, (uint32_t)(nbps >> 32));
 		if(count == 0)
 			continue;
 		if(nbps == 0) {
@@ -445,48 +448,82 @@ __device__ __forceinline__ bool read_accepted(const abw_read& r, uint32_t max_sn
 	return !((flag & 0x4u) || (nsnps > max_snps) || (flag & 0x100u)) && r.scaf < nscaf;   // :546-550
 }
 
-// windows [g0, g0 + cnt) hit by an accepted read: first window of the scaffold whose end is >= s, up to the last one whose start is <= e.
-// Windows of a scaffold hold the same number of non-N bases, so window (s-1)/nbps is the answer unless a run of N shifted it (then: binary search).
-__device__ __forceinline__ void read_windows(const abw_read& rd, uint32_t max_snps, uint32_t nscaf, const uint64_t* __restrict__ seg_first, const uint64_t* __restrict__ seg_start,
-                                             const uint64_t* __restrict__ seg_end, const uint64_t* __restrict__ seg_nonN, uint64_t& g0, uint32_t& cnt)
+// Windows hit by the reads of a thread, staged so that the loads of its COV_ITEMS reads are in flight together.
+//   first window g0 = the first one of the scaffold whose end is >= s (windows before it are skipped by `continue`, :235-236); windows of a scaffold hold the
+//   same number of non-N bases, so it is window (s-1)/nbps unless a run of N shifted the boundaries (then: binary search).
+//   Windows of a scaffold are contiguous (start[g] = end[g-1] + 1, start of the first = 1), so only the ends are read.
+// Returns per read: g0, number of windows cnt, and the end of window g0 - 1 (0 for the first window of the scaffold) and of g0.
+constexpr int COV_ITEMS = 4;                                // consecutive reads per thread
+struct ReadHit { uint32_t g0, cnt; uint64_t end_prev, end_cur; };
+__device__ __forceinline__ void read_windows(const abw_read (&rd)[COV_ITEMS], uint32_t max_snps, uint32_t nscaf, const uint4* __restrict__ scaf_info,
+                                             const uint64_t* __restrict__ seg_end, ReadHit (&hit)[COV_ITEMS])
 {
-	cnt = 0;
-	g0 = 0;
-	if(!read_accepted(rd, max_snps, nscaf))
-		return;
-	const uint64_t s = rd.pos0, e = (uint64_t)rd.pos0 + rd.len - 1;
-	const uint64_t f0 = __ldg(seg_first + rd.scaf), f1 = __ldg(seg_first + rd.scaf + 1);
-	if(f0 >= f1)
-		return;
-	const uint64_t nbps = max((unsigned long long)__ldg(seg_nonN + f0), 1ull);      // an all-N scaffold has one window per character
-	uint64_t g = (s > 0)? min(f1 - 1, f0 + (s - 1) / nbps) : f0;
-	if(!((g == f0 || __ldg(seg_end + g - 1) < s) && __ldg(seg_end + g) >= s)) {
-		uint64_t lo = f0, hi = f1;                          // runs of N moved the boundaries: binary search
-		while(lo < hi) {
-			const uint64_t mid = (lo + hi) >> 1;
-			if(__ldg(seg_end + mid) < s) lo = mid + 1; else hi = mid;
-		}
-		g = lo;                                             // windows before it are skipped by `continue`, :235-236
+	bool acc[COV_ITEMS];
+	uint4 si[COV_ITEMS];
+#pragma unroll
+	for(int j = 0; j < COV_ITEMS; j++) {
+		acc[j] = read_accepted(rd[j], max_snps, nscaf);
+		si[j] = acc[j]? __ldg(scaf_info + rd[j].scaf) : make_uint4(0, 0, 1, 0);
+		acc[j] = acc[j] && si[j].y > 0;
 	}
-	g0 = g;
-	while(g < f1 && !(e < __ldg(seg_start + g))) {
-		cnt++;
-		g++;
+	uint32_t g[COV_ITEMS];
+#pragma unroll
+	for(int j = 0; j < COV_ITEMS; j++) {
+		const uint32_t s = rd[j].pos0;
+		uint32_t q = 0;
+		if(s > 0) {
+			// an all-N scaffold (nbps 0) has one window per character
+			if(si[j].w == 0)
+				q = (s - 1) / max(si[j].z, 1u);
+			else
+				q = 0;                                      // more than 2^32 bases per window: every read position lies in the first window or is found by the search
+		}
+		g[j] = si[j].x + min(si[j].y - (acc[j]? 1u : 0u), q);
+	}
+#pragma unroll
+	for(int j = 0; j < COV_ITEMS; j++) {
+		hit[j].end_cur = acc[j]? __ldg(seg_end + g[j]) : 0ull;
+		hit[j].end_prev = (acc[j] && g[j] > si[j].x)? __ldg(seg_end + g[j] - 1) : 0ull;
+	}
+#pragma unroll
+	for(int j = 0; j < COV_ITEMS; j++) {
+		hit[j].g0 = 0; hit[j].cnt = 0;
+		if(!acc[j])
+			continue;
+		const uint64_t s = rd[j].pos0, e = (uint64_t)rd[j].pos0 + rd[j].len - 1;
+		const uint32_t f0 = si[j].x, f1 = si[j].x + si[j].y;
+		uint32_t gg = g[j];
+		if(!((gg == f0 || hit[j].end_prev < s) && hit[j].end_cur >= s)) {
+			uint32_t lo = f0, hi = f1;                      // runs of N moved the boundaries: binary search
+			while(lo < hi) {
+				const uint32_t mid = lo + ((hi - lo) >> 1);
+				if(__ldg(seg_end + mid) < s) lo = mid + 1; else hi = mid;
+			}
+			gg = lo;
+			hit[j].end_cur = (gg < f1)? __ldg(seg_end + gg) : 0ull;
+			hit[j].end_prev = (gg > f0)? __ldg(seg_end + gg - 1) : 0ull;
+		}
+		hit[j].g0 = gg;
+		// windows gg, gg+1, ... while their start is <= e (:233-237)
+		uint32_t c = 0;
+		uint64_t prev_end = hit[j].end_prev, cur_end = hit[j].end_cur;
+		uint32_t w = gg;
+		while(w < f1 && !(e < prev_end + 1)) {                 // first window of a scaffold: prev_end is 0 and the start 1
+			c++;
+			w++;
+			prev_end = cur_end;
+			if(w < f1 && !(e < prev_end + 1))
+				cur_end = __ldg(seg_end + w);
+		}
+		hit[j].cnt = c;
 	}
 }
 
 constexpr int COV_THREADS = 256;
-constexpr int COV_ITEMS = 4;                                // consecutive reads per thread
 constexpr int COV_TILE = COV_THREADS * COV_ITEMS;
 
-// pass 1: (window, read) pairs per tile of COV_TILE reads; per-scaffold read bases of the -c sample
-__global__ void __launch_bounds__(COV_THREADS) k_cov_count(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf,
-                                                          const uint64_t* __restrict__ seg_first, const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end,
-                                                          const uint64_t* __restrict__ seg_nonN, uint32_t* __restrict__ tile_counts, unsigned long long* __restrict__ scaf_nbps)
+__device__ __forceinline__ void load_reads(const abw_read* __restrict__ reads, uint64_t nreads, uint64_t r0, abw_read (&rd)[COV_ITEMS])
 {
-	__shared__ uint32_t sm[COV_THREADS / 32];
-	const uint64_t r0 = (uint64_t)blockIdx.x * COV_TILE + (uint64_t)threadIdx.x * COV_ITEMS;
-	abw_read rd[COV_ITEMS];
 #pragma unroll
 	for(int j = 0; j < COV_ITEMS; j++) {
 		if(r0 + j < nreads) {
@@ -497,13 +534,23 @@ __global__ void __launch_bounds__(COV_THREADS) k_cov_count(const abw_read* __res
 			rd[j].scaf = 0xFFFFFFFFu; rd[j].pos0 = 0; rd[j].len = 0; rd[j].flag_nsnps = 0;
 		}
 	}
+}
+
+// pass 1: (window, read) pairs per tile of COV_TILE reads; per-scaffold read bases of the -c sample
+__global__ void __launch_bounds__(COV_THREADS) k_cov_count(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf,
+                                                          const uint4* __restrict__ scaf_info, const uint64_t* __restrict__ seg_end, uint32_t* __restrict__ tile_counts,
+                                                          unsigned long long* __restrict__ scaf_nbps)
+{
+	__shared__ uint32_t sm[COV_THREADS / 32];
+	const uint64_t r0 = (uint64_t)blockIdx.x * COV_TILE + (uint64_t)threadIdx.x * COV_ITEMS;
+	abw_read rd[COV_ITEMS];
+	load_reads(reads, nreads, r0, rd);
+	ReadHit hit[COV_ITEMS];
+	read_windows(rd, max_snps, nscaf, scaf_info, seg_end, hit);
 	uint32_t c = 0;
 #pragma unroll
 	for(int j = 0; j < COV_ITEMS; j++) {
-		uint64_t g0;
-		uint32_t cj;
-		read_windows(rd[j], max_snps, nscaf, seg_first, seg_start, seg_end, seg_nonN, g0, cj);
-		c += cj;
+		c += hit[j].cnt;
 		if(scaf_nbps != nullptr && read_accepted(rd[j], max_snps, nscaf))
 			atomicAdd(&scaf_nbps[rd[j].scaf], (unsigned long long)rd[j].len);     // integer: order free (:242-243)
 	}
@@ -522,32 +569,20 @@ __global__ void __launch_bounds__(COV_THREADS) k_cov_count(const abw_read* __res
 
 // pass 2: the pairs, in read order (then window order): key = window, value = overlap
 __global__ void __launch_bounds__(COV_THREADS) k_cov_emit(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf,
-                                                         const uint64_t* __restrict__ seg_first, const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end,
-                                                         const uint64_t* __restrict__ seg_nonN, const uint64_t* __restrict__ tile_offs, uint32_t* __restrict__ keys,
-                                                         uint32_t* __restrict__ vals, uint32_t* __restrict__ per_seg)
+                                                         const uint4* __restrict__ scaf_info, const uint64_t* __restrict__ seg_end, const uint64_t* __restrict__ tile_offs,
+                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
 	__shared__ uint32_t sm[COV_THREADS / 32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint64_t r0 = (uint64_t)blockIdx.x * COV_TILE + (uint64_t)threadIdx.x * COV_ITEMS;
 	abw_read rd[COV_ITEMS];
-#pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++) {
-		if(r0 + j < nreads) {
-			const uint4 x = __ldg(reinterpret_cast<const uint4*>(reads + r0 + j));
-			rd[j].scaf = x.x; rd[j].pos0 = x.y; rd[j].len = x.z; rd[j].flag_nsnps = x.w;
-		}
-		else {
-			rd[j].scaf = 0xFFFFFFFFu; rd[j].pos0 = 0; rd[j].len = 0; rd[j].flag_nsnps = 0;
-		}
-	}
-	uint64_t g0[COV_ITEMS];
-	uint32_t cj[COV_ITEMS];
+	load_reads(reads, nreads, r0, rd);
+	ReadHit hit[COV_ITEMS];
+	read_windows(rd, max_snps, nscaf, scaf_info, seg_end, hit);
 	uint32_t c = 0;
 #pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++) {
-		read_windows(rd[j], max_snps, nscaf, seg_first, seg_start, seg_end, seg_nonN, g0[j], cj[j]);
-		c += cj[j];
-	}
+	for(int j = 0; j < COV_ITEMS; j++)
+		c += hit[j].cnt;
 	uint32_t incl = c;
 #pragma unroll
 	for(int o = 1; o < 32; o <<= 1) {
@@ -567,21 +602,37 @@ __global__ void __launch_bounds__(COV_THREADS) k_cov_emit(const abw_read* __rest
 #pragma unroll
 	for(int j = 0; j < COV_ITEMS; j++) {
 		const uint64_t s = rd[j].pos0, e = (uint64_t)rd[j].pos0 + rd[j].len - 1;
-		for(uint32_t k = 0; k < cj[j]; k++) {
-			const uint64_t g = g0[j] + k;
-			const uint64_t st = __ldg(seg_start + g), en = __ldg(seg_end + g);
+		uint64_t prev_end = hit[j].end_prev, cur_end = hit[j].end_cur;
+		for(uint32_t k = 0; k < hit[j].cnt; k++) {
+			const uint32_t g = hit[j].g0 + k;
+			const uint64_t st = prev_end + 1, en = cur_end;             // first window of a scaffold: prev_end is 0 and the start 1
 			const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // 0-based read against 1-based window: quirk Q3, kept (:182-183)
-			keys[o] = (uint32_t)g;
+			keys[o] = g;
 			vals[o] = (uint32_t)(e2 - s2 + 1);                             // the overlap travels with the pair: no gather after the sort
 			o++;
-			atomicAdd(&per_seg[g], 1u);
+			prev_end = cur_end;
+			if(k + 1 < hit[j].cnt)
+				cur_end = __ldg(seg_end + g + 1);
 		}
 	}
 }
 
+// run of every window in the sorted pairs: [run[g].x, run[g].y), both zero (pre-cleared) for a window no read touches
+__global__ void k_cov_runs(const uint32_t* __restrict__ keys, uint64_t npairs, uint2* __restrict__ run)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= npairs)
+		return;
+	const uint32_t k = keys[i];
+	if(i == 0 || keys[i - 1] != k)
+		run[k].x = (uint32_t)i;
+	if(i + 1 == npairs || keys[i + 1] != k)
+		run[k].y = (uint32_t)(i + 1);
+}
+
 // one thread per window: the reads that hit it, in SAM order (the pairs were sorted stably by window)
 template <int KIND>
-__global__ void k_cov_accumulate(const uint32_t* __restrict__ vals, const uint64_t* __restrict__ seg_off, uint64_t nseg,
+__global__ void k_cov_accumulate(const uint32_t* __restrict__ vals, const uint2* __restrict__ run, uint64_t nseg,
                                  const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end, double* __restrict__ rows, uint64_t ld, uint32_t col)
 {
 	uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -590,14 +641,24 @@ __global__ void k_cov_accumulate(const uint32_t* __restrict__ vals, const uint64
 	const double seglen = (double)(seg_end[g] - seg_start[g] + 1);
 	double acc = 0.0, q = 0.0;
 	uint32_t last = 0xFFFFFFFFu;
-	const uint64_t i1 = seg_off[g + 1];
-	for(uint64_t i = seg_off[g]; i < i1; i++) {
-		const uint32_t ov = __ldg(vals + i);
-		if(ov != last) {                                   // most reads lie entirely inside the window: same quotient, computed once
-			q = __ddiv_rn((double)ov, seglen);             // :184
-			last = ov;
+	const uint2 rg = run[g];
+	for(uint32_t i = rg.x; i < rg.y; i += 8) {
+		// eight loads in flight; the additions stay strictly in SAM order (quirk Q5)
+		const uint32_t m = min(8u, rg.y - i);
+		uint32_t ov[8];
+#pragma unroll
+		for(int j = 0; j < 8; j++)
+			ov[j] = ((uint32_t)j < m)? __ldg(vals + i + j) : 0u;
+#pragma unroll
+		for(int j = 0; j < 8; j++) {
+			if((uint32_t)j < m) {
+				if(ov[j] != last) {                            // most reads lie entirely inside the window: same quotient, computed once
+					q = __ddiv_rn((double)ov[j], seglen);      // :184
+					last = ov[j];
+				}
+				acc = __dadd_rn(acc, q);
+			}
 		}
-		acc = __dadd_rn(acc, q);                           // strictly in SAM order (quirk Q5)
 	}
 	if(KIND == ABW_FEAT_TRUNC3)
 		acc = __ddiv_rn((double)__double2int_rz(__dmul_rn(1000.0, acc)), 1000.0);
@@ -761,10 +822,12 @@ int abw_segment(abw_ctx* ctx, const abw_seqset* s, uint32_t window_size, abw_seg
 		ABW_CUDA(ctx, g->seg_end.alloc(g->nseg));
 		ABW_CUDA(ctx, g->seg_nonN.alloc(g->nseg));
 		ABW_CUDA(ctx, g->seg_gbase.alloc(g->nseg));
+		ABW_CUDA(ctx, g->scaf_info.alloc(s->nscaf));
+		ABW_CUDA(ctx, cudaMemsetAsync(g->scaf_info.p, 0, sizeof(uint4) * s->nscaf, ctx->stream));
 		if(s->nscaf > 0 && g->nseg > 0) {
 			unsigned int blocks = (unsigned int)std::min<uint64_t>(abw_div_up((uint64_t)s->nscaf * 32, 256), (uint64_t)ctx->sm_count * 16);
 			ABW_LAUNCH(ctx, k_seg_fill, blocks, 256, 0, s->len.p, s->countN.p, s->base.p, s->nmask.p, s->nscaf, (uint64_t)window_size, g->seg_first.p,
-			           g->seg_scaf.p, g->seg_start.p, g->seg_end.p, g->seg_nonN.p, g->seg_gbase.p);
+			           g->seg_scaf.p, g->seg_start.p, g->seg_end.p, g->seg_nonN.p, g->seg_gbase.p, g->scaf_info.p);
 		}
 		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		return ABW_OK;
@@ -841,42 +904,44 @@ int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uin
 		ABW_CUDA(ctx, cudaMemcpyAsync(d_reads.p, reads, sizeof(abw_read) * nreads, cudaMemcpyHostToDevice, ctx->stream));
 		rd = d_reads.p;
 	}
-	DevBuf<uint32_t> tile_counts, per_seg, keys, keys_tmp, vals, vals_tmp;
-	DevBuf<uint64_t> tile_offs, seg_off, total;
+	DevBuf<uint32_t> tile_counts, keys, keys_tmp, vals, vals_tmp;
+	DevBuf<uint64_t> tile_offs, total;
+	DevBuf<uint2> run;
 	const unsigned int ntiles = abw_div_up(nreads, COV_TILE);
 	ABW_CUDA(ctx, tile_counts.alloc(ntiles));
 	ABW_CUDA(ctx, tile_offs.alloc(ntiles));
 	ABW_CUDA(ctx, total.alloc(1));
-	ABW_CUDA(ctx, per_seg.alloc(g->nseg));
-	ABW_CUDA(ctx, seg_off.alloc(g->nseg + 1));
-	ABW_CUDA(ctx, cudaMemsetAsync(per_seg.p, 0, sizeof(uint32_t) * g->nseg, ctx->stream));
+	ABW_CUDA(ctx, run.alloc(g->nseg));
+	ABW_CUDA(ctx, cudaMemsetAsync(run.p, 0, sizeof(uint2) * g->nseg, ctx->stream));
 	uint64_t npairs = 0;
 	if(nreads) {
-		ABW_LAUNCH(ctx, k_cov_count, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->seg_first.p, g->seg_start.p, g->seg_end.p, g->seg_nonN.p, tile_counts.p,
+		ABW_LAUNCH(ctx, k_cov_count, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, tile_counts.p,
 		           (unsigned long long*)d_scaf_nbps);
 		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, tile_counts.p, tile_offs.p, ntiles, total.p));
 		ABW_CUDA(ctx, cudaMemcpyAsync(&npairs, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
 		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	}
+	if(npairs >= (1ull << 32))
+		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_coverage: more than 2^32-1 (window, read) pairs per call; split the sample");
 	ABW_CUDA(ctx, keys.alloc(npairs));
 	ABW_CUDA(ctx, keys_tmp.alloc(npairs));
 	ABW_CUDA(ctx, vals.alloc(npairs));
 	ABW_CUDA(ctx, vals_tmp.alloc(npairs));
 	if(npairs) {
-		ABW_LAUNCH(ctx, k_cov_emit, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->seg_first.p, g->seg_start.p, g->seg_end.p, g->seg_nonN.p, tile_offs.p, keys.p,
-		           vals.p, per_seg.p);
+		ABW_LAUNCH(ctx, k_cov_emit, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, tile_offs.p, keys.p, vals.p);
 		int nbits = 1;
 		while(nbits < 32 && (1ull << nbits) < g->nseg)
 			nbits++;
 		// window ids are dense: every bit below nbits varies, no need to look
 		ABW_CHECK(abw_radix_sort_pairs_u32(ctx, keys.p, keys_tmp.p, vals.p, vals_tmp.p, npairs, 1, npairs, -nbits));
 	}
-	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, per_seg.p, seg_off.p, g->nseg, seg_off.p + g->nseg));
+	if(npairs)
+		ABW_LAUNCH(ctx, k_cov_runs, abw_div_up(npairs, 256), 256, 0, keys.p, npairs, run.p);
 	if(g->nseg) {
 		if(kind == ABW_FEAT_TRUNC3)
-			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_TRUNC3>, abw_div_up(g->nseg, 64), 64, 0, vals.p, seg_off.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col);
+			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_TRUNC3>, abw_div_up(g->nseg, 64), 64, 0, vals.p, run.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col);
 		else
-			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_RAW>, abw_div_up(g->nseg, 64), 64, 0, vals.p, seg_off.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col);
+			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_RAW>, abw_div_up(g->nseg, 64), 64, 0, vals.p, run.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col);
 	}
 	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return ABW_OK;

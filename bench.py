@@ -337,10 +337,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), ctx.launches - l0
 
-    for _ in range(args.warmup):
-        step(True)
+    # the sampler is started BEFORE the warm-up: nvidia-smi takes driver locks while it starts and would otherwise stall the first timed launches
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for _ in range(args.warmup):
+        step(True)
+    sampler.rows.clear()                               # keep only the samples taken during the timed region
     ms_res, launches = timed(True, args.steps)
     clocks = sampler.stop()
     step(False)                                        # warm the host-buffer path once

@@ -5,12 +5,25 @@
 //   mode 3: LDS + IADD + STS 32-bit words
 #include <cstdio>
 #include <cuda_runtime.h>
+__host__ __device__ inline int words_per_warp(int mode)
+{
+	switch(mode) {
+	case 1: case 3: return 256 * 32;
+	case 6: return 256 * 16;
+	case 7: return 128 * 8;
+	case 8: return 128 * 4;
+	case 9: return 512 * 4;
+	case 10: return 512 * 8;
+	default: return 64 * 32;
+	}
+}
 __global__ void k(int mode, int iters, unsigned* out, unsigned seed)
 {
 	extern __shared__ unsigned sm[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	unsigned* h = sm + warp * (mode == 1 || mode == 3 ? 256 * 32 : (mode == 6 ? 128 * 32 : 64 * 32));
-	for(int i = lane; i < (mode == 1 || mode == 3 ? 256 * 32 : 64 * 32); i += 32) h[i] = 0;
+	const int words = words_per_warp(mode);
+	unsigned* h = sm + warp * words;
+	for(int i = lane; i < words; i += 32) h[i] = 0;
 	__syncwarp();
 	unsigned x = seed * 2654435761u + threadIdx.x * 40503u + blockIdx.x;
 	for(int it = 0; it < iters; it++) {
@@ -34,22 +47,34 @@ __global__ void k(int mode, int iters, unsigned* out, unsigned seed)
 				atomicAdd(h + c * 8 + (lane >> 2), 1u);          // 8 sub-histograms per warp (4 lanes each), bin-major: only lanes of one group can collide
 			else if(mode == 5)
 				atomicAdd(h + c * 4 + (lane >> 3), 1u);          // 4 sub-histograms (8 lanes each)
-			else
+			else if(mode == 6)
 				atomicAdd(h + c * 16 + (lane >> 1), 1u);         // 16 sub-histograms (2 lanes each)
+			else if(mode == 7)
+				atomicAdd(h + (c >> 1) * 8 + (lane >> 2), 1u << ((c & 1u) * 16));   // 16-bit counters, two bins per word, 8 sub-histograms
+			else if(mode == 8)
+				atomicAdd(h + (c >> 1) * 4 + (lane >> 3), 1u << ((c & 1u) * 16));   // 16-bit counters, 4 sub-histograms
+			else if(mode == 9) {
+				unsigned c10 = (x >> 13) & 0x3FFu;               // 5-mer bins (one update covers two 4-mer starts), 16-bit counters, 4 sub-histograms
+				atomicAdd(h + (c10 >> 1) * 4 + (lane >> 3), 1u << ((c10 & 1u) * 16));
+			}
+			else {
+				unsigned c10 = (x >> 13) & 0x3FFu;               // 5-mer bins, 16-bit counters, 8 sub-histograms
+				atomicAdd(h + (c10 >> 1) * 8 + (lane >> 2), 1u << ((c10 & 1u) * 16));
+			}
 		}
 	}
 	__syncwarp();
 	unsigned s = 0;
-	for(int i = lane; i < 64 * 32; i += 32) s += h[i];
+	for(int i = lane; i < words; i += 32) s += h[i];
 	if(s == 0xdeadbeef) out[0] = s;
 }
 int main()
 {
 	unsigned* out; cudaMalloc(&out, 4);
 	const int iters = 2000;
-	for(int mode = 0; mode < 7; mode++) {
+	for(int mode = 0; mode < 11; mode++) {
 		const int warps = (mode == 1 || mode == 3) ? 4 : 8;            // 32 KB vs 8 KB per warp
-		const size_t smem = (size_t)warps * ((mode == 1 || mode == 3) ? 256 : 64) * 32 * 4 * (mode == 6 ? 2 : 1);
+		const size_t smem = (size_t)warps * words_per_warp(mode) * 4;
 		cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		int blocks_per_sm = 0;
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k, warps * 32, smem);

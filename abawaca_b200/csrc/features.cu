@@ -231,179 +231,143 @@ __device__ uint32_t g_dim_tab[ABW_NKMER_DIMS];              // k | code_a << 8 |
 __device__ double   g_milli[1001];                          // m / 1000.0
 
 constexpr int KM_WARPS = 8;
-constexpr int KM_GROUPS = 8;                                // sub-histograms per warp: lanes 4g..4g+3 share one
-constexpr int KM_ROUND_WORDS = 224;                         // 16-base words staged per round (3584 bases)
-constexpr int KM_STAGE_WORDS = KM_ROUND_WORDS + 2;          // + lookahead word + alignment slack
+constexpr int KM_GROUPS = 4;                                // sub-histograms per warp: lanes 8g..8g+7 share one
 
-struct __align__(16) KmBlockSmem {
-	double   milli[1001 + 1];
-	uint32_t dim_tab[ABW_NKMER_DIMS];
-};
-
-// Per warp.  hist is bin-major and interleaved by group: word = bin * 8 + group, so two lanes can only hit the same bank when they are
-// in the same group of four (round-1 micro-benchmark scripts/ubench_hist.cu: 14 updates/clk/SM with fire-and-forget shared atomics,
-// against 8.6 for the byte load/add/store chain the first version used).
+// Per warp.  hist is bin-major and interleaved by group: word = bin * 4 + group, so two lanes can only hit the same bank when they are in the
+// same group of eight (micro-benchmark scripts/ubench_hist.cu on B200, updates per clock and SM: 13.3 in this layout with fire-and-forget
+// shared atomics, 14.0 with eight groups at twice the footprint, 8.6 for a private byte histogram per lane updated with load/add/store,
+// 10.4 for 16-bit counters or for 5-mer bins counted at every second position).  5.4 KB per warp: five CTAs of eight warps per SM.
 struct __align__(16) KmWarpSmem {
 	uint32_t hist[256 * KM_GROUPS];
-	uint32_t seq[KM_STAGE_WORDS + 2];
-	uint32_t val[KM_STAGE_WORDS / 2 + 4];
 	uint32_t cnt4[256];
 	uint32_t cnt3[64];
 	uint32_t cnt2[16];
 	uint32_t cnt1[4];
 	uint32_t tot[4];
-	uint32_t pad[2];
-	double   inv_tot[4];            // 1 / total_k, only used to form an integer quotient that is then verified exactly
+	float    inv_tot[4];            // 1 / total_k, only used to form an integer quotient that is then verified exactly
+	uint32_t pad[4];
 };
 
-__device__ __forceinline__ uint32_t stream_bits(const uint32_t* __restrict__ a, uint64_t bitpos, uint32_t nbits_le32)
-{
-	// nbits (<= 32) bits of the little-endian bit stream `a` starting at bit `bitpos`
-	uint64_t w = bitpos >> 5;
-	uint32_t sh = (uint32_t)(bitpos & 31);
-	uint32_t lo = a[w], hi = a[w + 1];
-	uint32_t r = __funnelshift_r(lo, hi, sh);
-	return (nbits_le32 >= 32)? r : (r & ((1u << nbits_le32) - 1u));
-}
-
+// A warp per window; lane l takes the 16-base words l, l+32, ... of the window straight from global memory (the packed stream and the
+// validity bits of neighbouring words share cache lines).  A word whose 16 four-mers are all valid costs 16 shared atomics; the first and
+// last words of the window and words next to a non-ACGT character go through the per-position path.
 template <int KIND>
 __global__ void __launch_bounds__(KM_WARPS * 32) k_kmer(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid, const uint64_t* __restrict__ seg_gbase,
                                                         const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end, uint64_t nseg, int skip_A,
                                                         double* __restrict__ rows, uint64_t ld, uint32_t col0)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	KmBlockSmem* bs = reinterpret_cast<KmBlockSmem*>(smem_raw);
-	KmWarpSmem* sm = reinterpret_cast<KmWarpSmem*>(smem_raw + sizeof(KmBlockSmem)) + (threadIdx.x >> 5);
+	__shared__ uint32_t sm_dim_tab[ABW_NKMER_DIMS];
+	__shared__ KmWarpSmem sm_warp[KM_WARPS];
+	KmWarpSmem* sm = sm_warp + (threadIdx.x >> 5);
 	const int lane = threadIdx.x & 31;
-	for(int i = threadIdx.x; i <= 1000; i += blockDim.x)
-		bs->milli[i] = g_milli[i];
 	for(int i = threadIdx.x; i < ABW_NKMER_DIMS; i += blockDim.x)
-		bs->dim_tab[i] = g_dim_tab[i];
+		sm_dim_tab[i] = g_dim_tab[i];
 	for(int i = lane; i < 256 * KM_GROUPS; i += 32)
 		sm->hist[i] = 0;
 	__syncthreads();
-	uint32_t* const myhist = sm->hist + (lane >> 2);        // + bin * 8
+	uint32_t* const myhist = sm->hist + (lane >> 3);        // + bin * KM_GROUPS
 	const uint64_t warp0 = (uint64_t)blockIdx.x * KM_WARPS + (threadIdx.x >> 5), nwarps = (uint64_t)gridDim.x * KM_WARPS;
 	for(uint64_t g = warp0; g < nseg; g += nwarps) {
 		const uint64_t gb = seg_gbase[g];
-		const uint64_t L = seg_end[g] - seg_start[g] + 1;
+		const uint64_t pos_end = gb + (seg_end[g] - seg_start[g] + 1);
 		for(int i = lane; i < 64 + 16 + 4 + 4; i += 32)
 			sm->cnt3[i] = 0;                                // cnt3, cnt2, cnt1, tot are contiguous: these receive the run-end windows
 		__syncwarp();
-		const uint64_t word_first = gb >> 4;
-		const uint64_t nwords = ((gb + L + 15) >> 4) - word_first;
-		for(uint64_t w0 = 0; w0 < nwords; w0 += KM_ROUND_WORDS) {
-			const uint32_t rw = (uint32_t)min((uint64_t)KM_ROUND_WORDS, nwords - w0);
-			// stage packed words (+1 lookahead) and validity bits of [w0, w0+rw] into shared memory
-			for(uint32_t i = lane; i < rw + 1; i += 32)
-				sm->seq[i] = packed[word_first + w0 + i];
-			const uint64_t vbit0 = (word_first + w0) << 4;   // absolute base index of the first staged position
-			for(uint32_t i = lane; i < (rw + 1 + 1) / 2 + 1; i += 32) {
-				uint64_t p = vbit0 + ((uint64_t)i << 5);      // 32 positions
-				uint32_t v = valid[p >> 5];
-				uint32_t v2 = valid[(p >> 5) + 1];
-				v = __funnelshift_r(v, v2, (uint32_t)(p & 31));
-				// positions outside [gb, gb+L) never hold a base of this segment
-				uint64_t lo = (gb > p)? gb - p : 0, hi = (gb + L > p)? gb + L - p : 0;
-				uint32_t m_lo = (lo >= 32)? 0u : (0xFFFFFFFFu << (uint32_t)lo);
-				uint32_t m_hi = (hi >= 32)? 0xFFFFFFFFu : ((1u << (uint32_t)hi) - 1u);
-				sm->val[i] = v & m_lo & m_hi;
-			}
-			__syncwarp();
-			// main loop: lane l takes words l, l+32, ...; a word whose 16 windows are all valid costs 16 shared atomics, anything else is deferred
-			uint32_t pending = 0;                             // bit j: word lane + 32*j is partial
-			for(uint32_t j = 0, k = lane; k < rw; j++, k += 32) {
-				const uint32_t v = stream_bits(sm->val, (uint64_t)k << 4, 19);   // 16 positions + 3 lookahead
-				const uint32_t v4 = v & (v >> 1) & (v >> 2) & (v >> 3) & 0xFFFFu;
-				if(v4 == 0xFFFFu) {
-					const uint64_t win = (uint64_t)sm->seq[k] | ((uint64_t)sm->seq[k + 1] << 32);
+		const uint64_t wend = (pos_end + 15) >> 4;
+		for(uint64_t wa = (gb >> 4) + lane; wa < wend; wa += 32) {
+			const uint32_t w_lo = __ldg(packed + wa), w_hi = __ldg(packed + wa + 1);
+			const uint32_t va = __ldg(valid + (wa >> 1)), vb = __ldg(valid + (wa >> 1) + 1);
+			uint32_t v = __funnelshift_r(va, vb, (uint32_t)(wa & 1) * 16) & 0x7FFFFu;       // 16 positions + 3 lookahead
+			const uint64_t p0 = wa << 4;
+			// positions outside [gb, pos_end) never hold a base of this window
+			if(p0 < gb)
+				v &= 0xFFFFFFFFu << (uint32_t)(gb - p0);
+			if(pos_end - p0 < 19)
+				v &= (1u << (uint32_t)(pos_end - p0)) - 1u;
+			const uint32_t v1 = v & 0xFFFFu, v2 = v1 & (v >> 1), v3 = v2 & (v >> 2), v4 = v3 & (v >> 3);
+			// s[i] = the window shifted by i bases: 4-mer t = 4 j + i is byte j of s[i]
+			uint32_t sh[4];
+			sh[0] = w_lo;
+			sh[1] = __funnelshift_r(w_lo, w_hi, 2);
+			sh[2] = __funnelshift_r(w_lo, w_hi, 4);
+			sh[3] = __funnelshift_r(w_lo, w_hi, 6);
+			if(v4 == 0xFFFFu) {
 #pragma unroll
-					for(int t = 0; t < 16; t++) {
-						const uint32_t x = (uint32_t)(win >> (2 * t)) & 0xFFu;
-						atomicAdd(myhist + x * KM_GROUPS, 1u);
+				for(int i = 0; i < 4; i++) {
+#pragma unroll
+					for(int j = 0; j < 4; j++)
+						atomicAdd(myhist + ((sh[i] >> (8 * j)) & 0xFFu) * KM_GROUPS, 1u);
+				}
+			}
+			else if(v1) {
+				// windows broken by a non-ACGT character or by the end of the segment (:131,147 key = 0)
+				const uint32_t e3 = v3 & ~v4, e2 = v2 & ~v3, e1 = v1 & ~v2;
+#pragma unroll
+				for(int i = 0; i < 4; i++) {
+#pragma unroll
+					for(int j = 0; j < 4; j++) {
+						const int t = 4 * j + i;
+						const uint32_t x = (sh[i] >> (8 * j)) & 0xFFu;
+						if((v4 >> t) & 1u)
+							atomicAdd(myhist + x * KM_GROUPS, 1u);
+						else if((e3 >> t) & 1u)
+							atomicAdd(&sm->cnt3[x & 63u], 1u);
+						else if((e2 >> t) & 1u)
+							atomicAdd(&sm->cnt2[x & 15u], 1u);
+						else if((e1 >> t) & 1u)
+							atomicAdd(&sm->cnt1[x & 3u], 1u);
 					}
 				}
-				else if(v & 0xFFFFu)
-					pending |= 1u << j;                       // windows broken by a non-ACGT character or by the end of the segment (:131,147 key = 0)
 			}
-			// partial words, one at a time, sixteen lanes each taking one position
-			for(;;) {
-				const uint32_t who = __ballot_sync(0xffffffffu, pending != 0);
-				if(who == 0)
-					break;
-				const int src = __ffs(who) - 1;
-				const uint32_t pj = __shfl_sync(0xffffffffu, pending, src);
-				const uint32_t j = (uint32_t)(__ffs(pj) - 1);
-				if(lane == src)
-					pending &= pending - 1;
-				const uint32_t k = (uint32_t)src + 32 * j;
-				if(lane < 16) {
-					const uint32_t v = stream_bits(sm->val, ((uint64_t)k << 4) + lane, 4);
-					const uint64_t win = (uint64_t)sm->seq[k] | ((uint64_t)sm->seq[k + 1] << 32);
-					const uint32_t x = (uint32_t)(win >> (2 * lane)) & 0xFFu;
-					if((v & 15u) == 15u)
-						atomicAdd(myhist + x * KM_GROUPS, 1u);
-					else if((v & 7u) == 7u)
-						atomicAdd(&sm->cnt3[x & 63u], 1u);
-					else if((v & 3u) == 3u)
-						atomicAdd(&sm->cnt2[x & 15u], 1u);
-					else if(v & 1u)
-						atomicAdd(&sm->cnt1[x & 3u], 1u);
-				}
-			}
-			__syncwarp();
 		}
-		// fold the sub-histograms: lane l owns bins l, l+32, ..., l+224 (eight consecutive words each) and clears them
+		__syncwarp();
+		// fold the sub-histograms: lane l owns bins l, l+32, ..., l+224 (four consecutive words each) and clears them
 		{
 			uint32_t t4 = 0;
 #pragma unroll
 			for(int j = 0; j < 8; j++) {
 				const int bin = lane + 32 * j;
 				uint4* hp = reinterpret_cast<uint4*>(sm->hist + bin * KM_GROUPS);
-				const uint4 a = hp[0], b = hp[1];
+				const uint4 a = hp[0];
 				hp[0] = make_uint4(0, 0, 0, 0);
-				hp[1] = make_uint4(0, 0, 0, 0);
-				const uint32_t c = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+				const uint32_t c = a.x + a.y + a.z + a.w;
 				sm->cnt4[bin] = c;
 				t4 += c;
 			}
-#pragma unroll
-			for(int o = 16; o > 0; o >>= 1)
-				t4 += __shfl_xor_sync(0xffffffffu, t4, o);
+			t4 = __reduce_add_sync(0xffffffffu, t4);
 			__syncwarp();
 			// lower orders: every valid 4-mer start is a valid 3-mer start, etc.; cnt3/cnt2/cnt1 hold the run-end extras
 			uint32_t a = sm->cnt4[lane] + sm->cnt4[lane + 64] + sm->cnt4[lane + 128] + sm->cnt4[lane + 192];
 			uint32_t b = sm->cnt4[lane + 32] + sm->cnt4[lane + 96] + sm->cnt4[lane + 160] + sm->cnt4[lane + 224];
-			sm->cnt3[lane] += a;
-			sm->cnt3[lane + 32] += b;
+			a += sm->cnt3[lane];
+			b += sm->cnt3[lane + 32];
+			sm->cnt3[lane] = a;
+			sm->cnt3[lane + 32] = b;
+			const uint32_t t3 = __reduce_add_sync(0xffffffffu, a + b);
 			__syncwarp();
-			uint32_t t3 = sm->cnt3[lane] + sm->cnt3[lane + 32];
-#pragma unroll
-			for(int o = 16; o > 0; o >>= 1)
-				t3 += __shfl_xor_sync(0xffffffffu, t3, o);
-			if(lane < 16)
-				sm->cnt2[lane] += sm->cnt3[lane] + sm->cnt3[lane + 16] + sm->cnt3[lane + 32] + sm->cnt3[lane + 48];
-			__syncwarp();
-			uint32_t t2 = (lane < 16)? sm->cnt2[lane] : 0u;
-#pragma unroll
-			for(int o = 16; o > 0; o >>= 1)
-				t2 += __shfl_xor_sync(0xffffffffu, t2, o);
-			if(lane < 4)
-				sm->cnt1[lane] += sm->cnt2[lane] + sm->cnt2[lane + 4] + sm->cnt2[lane + 8] + sm->cnt2[lane + 12];
-			__syncwarp();
-			const uint32_t t1 = sm->cnt1[0] + sm->cnt1[1] + sm->cnt1[2] + sm->cnt1[3];
-			if(lane == 0) {
-				sm->tot[0] = t1; sm->tot[1] = t2; sm->tot[2] = t3; sm->tot[3] = t4;
+			uint32_t c2 = 0;
+			if(lane < 16) {
+				c2 = sm->cnt2[lane] + sm->cnt3[lane] + sm->cnt3[lane + 16] + sm->cnt3[lane + 32] + sm->cnt3[lane + 48];
+				sm->cnt2[lane] = c2;
 			}
+			const uint32_t t2 = __reduce_add_sync(0xffffffffu, c2);
+			__syncwarp();
+			uint32_t c1 = 0;
+			if(lane < 4) {
+				c1 = sm->cnt1[lane] + sm->cnt2[lane] + sm->cnt2[lane + 4] + sm->cnt2[lane + 8] + sm->cnt2[lane + 12];
+				sm->cnt1[lane] = c1;
+			}
+			const uint32_t t1 = __reduce_add_sync(0xffffffffu, c1);
 			if(lane < 4) {
 				const uint32_t tk = (lane == 0)? t1 : (lane == 1)? t2 : (lane == 2)? t3 : t4;
-				sm->inv_tot[lane] = tk? 1.0 / (double)tk : 0.0;
+				sm->tot[lane] = tk;
+				sm->inv_tot[lane] = tk? 1.0f / (float)tk : 0.0f;
 			}
 			__syncwarp();
 		}
 		// 180 canonical dimensions: dims[canon] += count/total for the mer and for its reverse complement (:171)
 		for(int d = lane; d < ABW_NKMER_DIMS; d += 32) {
-			const uint32_t ent = bs->dim_tab[d];
+			const uint32_t ent = sm_dim_tab[d];
 			const int k = ent & 0xFFu;
 			const uint32_t* cnt = (k == 4)? sm->cnt4 : (k == 3)? sm->cnt3 : (k == 2)? sm->cnt2 : sm->cnt1;
 			const uint32_t ca = (ent >> 8) & 0xFFu, cb = (ent >> 16) & 0xFFu;
@@ -411,17 +375,18 @@ __global__ void __launch_bounds__(KM_WARPS * 32) k_kmer(const uint32_t* __restri
 			const uint32_t t = sm->tot[k - 1];
 			double out = 0.0;
 			if(t != 0 && (c1 + c2) != 0) {
-				bool exact_path = (KIND != ABW_FEAT_TRUNC3) || (c1 + c2) > 4000000u;
+				bool exact_path = (KIND != ABW_FEAT_TRUNC3) || (c1 + c2) > 4000000u || t > (1u << 28);
 				if(!exact_path) {
 					// int(1000*(c1/t + c2/t)) equals floor(1000*(c1+c2)/t) whenever the quotient is not an integer: the rounding
-					// error of the three fp64 operations (< 1e-12) is far below the distance 1/t to the next integer
+					// error of the three fp64 operations (< 1e-12) is far below the distance 1/t to the next integer.  The quotient
+					// (at most 1000) is formed in single precision, off by at most one, and verified exactly in integers.
 					const uint32_t num = 1000u * (c1 + c2);
-					uint32_t m = (uint32_t)__double2uint_rz(__dmul_rn((double)num, sm->inv_tot[k - 1]));
-					int32_t r = (int32_t)(num - m * t);               // the approximate quotient is off by at most one: verify exactly
+					uint32_t m = (uint32_t)__float2uint_rz((float)num * sm->inv_tot[k - 1]);
+					int32_t r = (int32_t)(num - m * t);
 					if(r < 0) { m--; r += (int32_t)t; }
 					else if((uint32_t)r >= t) { m++; r -= (int32_t)t; }
 					if(r != 0)
-						out = bs->milli[m];
+						out = g_milli[m];
 					else
 						exact_path = true;
 				}
@@ -874,16 +839,11 @@ int abw_kmer_features(abw_ctx* ctx, const abw_seqset* s, const abw_segments* g, 
 	ABW_CHECK(upload_tables(ctx));
 	if(g->nseg == 0)
 		return ABW_OK;
-	const size_t smem = sizeof(KmBlockSmem) + sizeof(KmWarpSmem) * KM_WARPS;
-	unsigned int blocks = (unsigned int)std::min<uint64_t>(abw_div_up(g->nseg, KM_WARPS), (uint64_t)ctx->sm_count * 2 * 4);
-	if(kind == ABW_FEAT_TRUNC3) {
-		ABW_CUDA(ctx, cudaFuncSetAttribute(k_kmer<ABW_FEAT_TRUNC3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		ABW_LAUNCH(ctx, k_kmer<ABW_FEAT_TRUNC3>, blocks, KM_WARPS * 32, smem, s->packed.p, s->valid.p, g->seg_gbase.p, g->seg_start.p, g->seg_end.p, g->nseg, skip_A, d_rows, ld, col0);
-	}
-	else {
-		ABW_CUDA(ctx, cudaFuncSetAttribute(k_kmer<ABW_FEAT_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		ABW_LAUNCH(ctx, k_kmer<ABW_FEAT_RAW>, blocks, KM_WARPS * 32, smem, s->packed.p, s->valid.p, g->seg_gbase.p, g->seg_start.p, g->seg_end.p, g->nseg, skip_A, d_rows, ld, col0);
-	}
+	unsigned int blocks = (unsigned int)std::min<uint64_t>(abw_div_up(g->nseg, KM_WARPS), (uint64_t)ctx->sm_count * 5 * 4);
+	if(kind == ABW_FEAT_TRUNC3)
+		ABW_LAUNCH(ctx, k_kmer<ABW_FEAT_TRUNC3>, blocks, KM_WARPS * 32, 0, s->packed.p, s->valid.p, g->seg_gbase.p, g->seg_start.p, g->seg_end.p, g->nseg, skip_A, d_rows, ld, col0);
+	else
+		ABW_LAUNCH(ctx, k_kmer<ABW_FEAT_RAW>, blocks, KM_WARPS * 32, 0, s->packed.p, s->valid.p, g->seg_gbase.p, g->seg_start.p, g->seg_end.p, g->nseg, skip_A, d_rows, ld, col0);
 	return ABW_OK;
 }
 

@@ -35,6 +35,12 @@ class FeatureBuild:
                 self.ctx.d2h_async(out, self.d_rows)
         return out
 
+    def seg_first_host(self):
+        """first window of every scaffold (+ the total), uint64 [nscaf+1]"""
+        seg_first = np.zeros(self.nscaf + 1, dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.abw_segments_get(self.ctx.h, self.segs, capi._p(seg_first), None, None, None, None))
+        return seg_first
+
     def segments_host(self):
         seg_first = np.zeros(self.nscaf + 1, dtype=np.uint64)
         seg_scaf = np.zeros(self.nseg, dtype=np.uint32)
@@ -144,6 +150,17 @@ def build_features(ctx: capi.Context, seq, offsets, reads, this_sample=0, params
         ctx.free(d)
     lap("coverage_ms")
     return FeatureBuild(ctx, seqset, segs, d_rows, nseg, ncols, nscaf, d_nbps)
+
+
+def search_problem_from_counts(counts):
+    """Same as search_problem_from_features, from the number of windows of every scaffold (diff of seg_first)"""
+    counts = np.asarray(counts, dtype=np.int64)
+    keep_scaf = counts >= 2
+    kept = np.nonzero(keep_scaf)[0]
+    T = counts[kept].astype(np.uint32)
+    keep_rows = np.repeat(keep_scaf, counts)
+    dp2scaf = np.repeat(np.arange(kept.size, dtype=np.uint32), T)
+    return keep_rows, dp2scaf, T, kept
 
 
 def search_problem_from_features(seg_scaf, nscaf):

@@ -265,9 +265,10 @@ def main():
         else:
             fb = pipeline.build_features(ctx, h_seq.numpy(), mg.offsets, h_reads_np, this_sample=0, timings=timings, overlap_h2d=True)
         t_a = time.perf_counter()
-        sg = fb.segments_host()
+        seg_first = fb.seg_first_host()
         t_b = time.perf_counter()
-        keep, dp2scaf, T, kept = pipeline.search_problem_from_features(sg["seg_scaf"], nscaf)
+        # ScafDpData.cpp:92-93: scaffolds with a single window are dropped
+        keep, dp2scaf, T, kept = pipeline.search_problem_from_counts(np.diff(seg_first.astype(np.int64)))
         if timings is not None:
             timings["segments_host_ms"] = 1000.0 * (t_b - t_a)
             timings["search_problem_ms"] = 1000.0 * (time.perf_counter() - t_b)
@@ -309,7 +310,10 @@ def main():
         if not resident:
             ctx.synchronize()                          # the matrix has arrived on the host (copy stream) before the step counts as done
         state.update(ndps=ndps_total, nseg=fb.nseg, ncols=fb.ncols, prof=res.profile, nclusters=len(res.recs), nbins=nbins,
-                     seg_len=(sg["seg_end"] - sg["seg_start"] + 1), bins=res.scaf2cluster)
+                     bins=res.scaf2cluster)
+        if timings is not None:                        # window lengths: only needed for the algorithmic byte count of the k-mer kernel
+            sg = fb.segments_host()
+            state["seg_len"] = sg["seg_end"] - sg["seg_start"] + 1
         fb.close()
         return res
 

@@ -123,7 +123,7 @@ int scan_impl(abw_ctx* ctx, const Tin* d_in, uint64_t* d_out, uint64_t n, uint64
 // ---------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;                       // keys per lane
+constexpr int RS_ITEMS = 8;                        // keys per lane
 constexpr int RS_WARP_TILE = 32 * RS_ITEMS;        // 512
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;     // 4096
 

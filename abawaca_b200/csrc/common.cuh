@@ -20,6 +20,9 @@ struct abw_ctx {
 	bool         profiling = false;
 	cudaEvent_t  ev_a = nullptr, ev_b = nullptr;
 	std::map<std::string, std::pair<uint64_t, double>> prof;   // kernel -> (launches, total ms)
+	// device blocks freed by this context, kept for reuse (see abw_arena_alloc): capacity -> block
+	std::multimap<size_t, void*> free_blocks;
+	std::map<void*, size_t> block_cap;                         // capacity of every block obtained through the arena, cached or in use
 };
 
 inline int abw_fail(abw_ctx* ctx, int code, const std::string& msg)
@@ -65,22 +68,25 @@ inline int abw_fail(abw_ctx* ctx, int code, const std::string& msg)
 		}                                                                                                            \
 	} while(0)
 
-// Stream of the context whose entry point is executing on this host thread (set by ABW_ENTER).  Device buffers are
-// allocated and freed in stream order from the device's memory pool (cudaMallocAsync), so that after the first call of
-// a given size no entry point pays for cudaMalloc/cudaFree or for the device-wide synchronisation cudaFree implies.
-extern thread_local cudaStream_t abw_tls_stream;
+// Context whose entry point is executing on this host thread (set by ABW_ENTER).  Device buffers come from a per-context arena: blocks are
+// obtained with cudaMallocAsync on the context stream and, when released, cached by the context instead of going back to the driver, so
+// that after the first pass of a given shape no entry point pays for cuMemCreate / pool growth (which showed up as sporadic 10-20 ms stalls).
+// Every block is only ever used in the order of the context stream, which makes immediate reuse safe.
+extern thread_local abw_ctx* abw_tls_ctx;
+cudaError_t abw_arena_alloc(abw_ctx* ctx, size_t bytes, void** out);
+void abw_arena_free(abw_ctx* ctx, void* p);
 
 #define ABW_ENTER(ctx)                                                                                               \
 	do {                                                                                                             \
 		ABW_CUDA((ctx), cudaSetDevice((ctx)->device));                                                               \
-		abw_tls_stream = (ctx)->stream;                                                                              \
+		abw_tls_ctx = (ctx);                                                                                         \
 	} while(0)
 
 template <typename T>
 struct DevBuf {
-	T*           p = nullptr;
-	size_t       n = 0;
-	cudaStream_t st = nullptr;
+	T*       p = nullptr;
+	size_t   n = 0;
+	abw_ctx* owner = nullptr;
 	DevBuf() {}
 	DevBuf(const DevBuf&) = delete;
 	DevBuf& operator=(const DevBuf&) = delete;
@@ -88,7 +94,7 @@ struct DevBuf {
 	void release()
 	{
 		if(p)
-			cudaFreeAsync(p, st);
+			abw_arena_free(owner, p);
 		p = nullptr;
 		n = 0;
 	}
@@ -96,8 +102,8 @@ struct DevBuf {
 	{
 		release();
 		n = count;
-		st = abw_tls_stream;
-		return cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), st);
+		owner = abw_tls_ctx;
+		return abw_arena_alloc(owner, (count ? count : 1) * sizeof(T), (void**)&p);
 	}
 };
 

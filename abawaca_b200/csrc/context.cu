@@ -1,9 +1,74 @@
 // Context, error text and raw device-memory helpers of the C ABI.
 #include "common.cuh"
+#include <mutex>
+#include <set>
 #include <algorithm>
 #include <cstring>
 
-thread_local cudaStream_t abw_tls_stream = nullptr;
+thread_local abw_ctx* abw_tls_ctx = nullptr;
+
+namespace {
+std::mutex g_live_mutex;
+std::set<abw_ctx*> g_live;                                 // contexts that still exist: a buffer may be released after its context is gone
+}
+
+cudaError_t abw_arena_alloc(abw_ctx* ctx, size_t bytes, void** out)
+{
+	if(!ctx)
+		return cudaMalloc(out, bytes);
+	// best fit among the cached blocks, as long as it does not waste more than a quarter of the block
+	auto it = ctx->free_blocks.lower_bound(bytes);
+	if(it != ctx->free_blocks.end() && it->first <= bytes + bytes / 4 + 65536) {
+		*out = it->second;
+		ctx->free_blocks.erase(it);
+		return cudaSuccess;
+	}
+	// round up so that slightly different sizes of later passes (pair counts, cluster counts) still fit the cached block
+	size_t cap = bytes;
+	if(cap < 4096)
+		cap = 4096;
+	size_t step = 256;
+	while(step * 16 < cap)
+		step <<= 1;
+	cap = (cap + step - 1) / step * step;
+	cudaError_t e = cudaMallocAsync(out, cap, ctx->stream);
+	if(e != cudaSuccess) {
+		// out of memory: give the cached blocks back and try once more
+		cudaGetLastError();
+		for(auto& kv : ctx->free_blocks) {
+			cudaFreeAsync(kv.second, ctx->stream);
+			ctx->block_cap.erase(kv.second);
+		}
+		ctx->free_blocks.clear();
+		cudaStreamSynchronize(ctx->stream);
+		e = cudaMallocAsync(out, cap, ctx->stream);
+		if(e != cudaSuccess)
+			return e;
+	}
+	ctx->block_cap[*out] = cap;
+	return cudaSuccess;
+}
+
+void abw_arena_free(abw_ctx* ctx, void* p)
+{
+	if(!p)
+		return;
+	bool alive = false;
+	if(ctx) {
+		std::lock_guard<std::mutex> lk(g_live_mutex);
+		alive = g_live.count(ctx) != 0;
+	}
+	if(!alive) {
+		cudaFree(p);
+		return;
+	}
+	auto it = ctx->block_cap.find(p);
+	if(it == ctx->block_cap.end()) {
+		cudaFreeAsync(p, ctx->stream);
+		return;
+	}
+	ctx->free_blocks.insert(std::make_pair(it->second, p));
+}
 
 extern "C" {
 
@@ -55,6 +120,10 @@ int abw_ctx_create(int device, abw_ctx** out)
 		uint64_t keep = UINT64_MAX;
 		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
 	}
+	{
+		std::lock_guard<std::mutex> lk(g_live_mutex);
+		g_live.insert(c);
+	}
 	*out = c;
 	return ABW_OK;
 }
@@ -64,6 +133,14 @@ void abw_ctx_destroy(abw_ctx* ctx)
 	if(!ctx)
 		return;
 	cudaSetDevice(ctx->device);
+	{
+		std::lock_guard<std::mutex> lk(g_live_mutex);
+		g_live.erase(ctx);
+	}
+	cudaStreamSynchronize(ctx->stream);
+	for(auto& kv : ctx->free_blocks)
+		cudaFree(kv.second);
+	ctx->free_blocks.clear();
 	for(cudaEvent_t e : ctx->copy_events)
 		cudaEventDestroy(e);
 	if(ctx->copy_stream)
@@ -132,7 +209,7 @@ int abw_device_alloc(abw_ctx* ctx, size_t bytes, void** d_out)
 	if(!ctx || !d_out)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_device_alloc: null argument");
 	ABW_ENTER(ctx);
-	ABW_CUDA(ctx, cudaMallocAsync(d_out, bytes? bytes : 1, ctx->stream));
+	ABW_CUDA(ctx, abw_arena_alloc(ctx, bytes? bytes : 1, d_out));
 	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return ABW_OK;
 }
@@ -141,7 +218,7 @@ int abw_device_free(abw_ctx* ctx, void* d_ptr)
 {
 	if(!ctx)
 		return ABW_ERR_ARG;
-	ABW_CUDA(ctx, cudaFreeAsync(d_ptr, ctx->stream));
+	abw_arena_free(ctx, d_ptr);                            // cached for reuse in the order of the context stream
 	return ABW_OK;
 }
 

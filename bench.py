@@ -329,17 +329,20 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.launches
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         e0.record(ext)
-        for _ in range(steps):
+        for i in range(steps):
             step(resident)
+            marks[i].record(ext)
         e1.record(ext)
         e1.synchronize()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+        per_step = [round(([e0] + marks)[i].elapsed_time(marks[i]), 3) for i in range(steps)]
         t = torch.tensor([ms], device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), ctx.launches - l0
+        return float(t.item()), ctx.launches - l0, per_step
 
     # the sampler is started BEFORE the warm-up: nvidia-smi takes driver locks while it starts and would otherwise stall the first timed launches
     sampler = ClockSampler(local_rank)
@@ -347,10 +350,11 @@ def main():
     for _ in range(args.warmup):
         step(True)
     sampler.rows.clear()                               # keep only the samples taken during the timed region
-    ms_res, launches = timed(True, args.steps)
+    ms_res, launches, steps_res = timed(True, args.steps)
     clocks = sampler.stop()
-    step(False)                                        # warm the host-buffer path once
-    ms_e2e, _ = timed(False, args.steps)
+    for _ in range(max(1, args.warmup)):               # warm the host-buffer path (staging buffers enter the context's block cache)
+        step(False)
+    ms_e2e, _, steps_e2e = timed(False, args.steps)
 
     # one extra profiled step: per-kernel CUDA-event durations (launches serialised while profiling)
     phase_ms = {}
@@ -404,7 +408,7 @@ def main():
                        "clusters_evaluated": state["nclusters"], "bins": bins_total, "search_levels": prof.levels, "datapoints": state["ndps"],
                        "nccl": None if coll is None else {"callback_collectives_total": coll.calls, "callback_bytes_total": coll.bytes}},
             "e2e": {"value": round(e2e_value, 2), "unit": "scaffolds/s", "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "gpu_launches": int(launches), "step_ms": {"resident": steps_res, "e2e": steps_e2e}, "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "phase_wall_ms": {k: round(v, 3) for k, v in phase_ms.items()},
             "search_profile_ms": {"build": round(prof.build_ms, 3), "sweep": round(prof.sweep_ms, 3), "partition": round(prof.partition_ms, 3), "other": round(prof.other_ms, 3)}}
 

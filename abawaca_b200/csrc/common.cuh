@@ -23,7 +23,17 @@ struct abw_ctx {
 	// device blocks freed by this context, kept for reuse (see abw_arena_alloc): capacity -> block
 	std::multimap<size_t, void*> free_blocks;
 	std::map<void*, size_t> block_cap;                         // capacity of every block obtained through the arena, cached or in use
+	// pinned staging for the many small host->device uploads of a search level: two halves used alternately (see abw_stage_flip)
+	unsigned char* h_stage = nullptr;
+	size_t stage_half = 0, stage_used = 0;
+	int stage_side = 0;
 };
+
+// Small uploads (descriptors, job lists, tile tables) go through pinned memory so that cudaMemcpyAsync really is asynchronous.
+// abw_stage_flip switches to the other half; the caller guarantees that the copies enqueued two flips ago have completed
+// (the split search synchronises at least once per level and flips once per level).
+void abw_stage_flip(abw_ctx* ctx);
+cudaError_t abw_stage_upload(abw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 
 inline int abw_fail(abw_ctx* ctx, int code, const std::string& msg)
 {

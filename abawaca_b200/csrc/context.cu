@@ -49,6 +49,34 @@ cudaError_t abw_arena_alloc(abw_ctx* ctx, size_t bytes, void** out)
 	return cudaSuccess;
 }
 
+void abw_stage_flip(abw_ctx* ctx)
+{
+	ctx->stage_side ^= 1;
+	ctx->stage_used = 0;
+}
+
+cudaError_t abw_stage_upload(abw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes)
+{
+	if(bytes == 0)
+		return cudaSuccess;
+	if(!ctx->h_stage) {
+		ctx->stage_half = (size_t)4 << 20;
+		if(cudaMallocHost((void**)&ctx->h_stage, 2 * ctx->stage_half) != cudaSuccess) {
+			cudaGetLastError();
+			ctx->h_stage = nullptr;
+			ctx->stage_half = 0;
+		}
+	}
+	const size_t need = (bytes + 255) & ~(size_t)255;
+	if(ctx->h_stage && ctx->stage_used + need <= ctx->stage_half) {
+		unsigned char* slot = ctx->h_stage + (size_t)ctx->stage_side * ctx->stage_half + ctx->stage_used;
+		memcpy(slot, h_src, bytes);
+		ctx->stage_used += need;
+		return cudaMemcpyAsync(d_dst, slot, bytes, cudaMemcpyHostToDevice, ctx->stream);
+	}
+	return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream);      // too large for the staging half: the driver stages it
+}
+
 void abw_arena_free(abw_ctx* ctx, void* p)
 {
 	if(!p)
@@ -141,6 +169,9 @@ void abw_ctx_destroy(abw_ctx* ctx)
 	for(auto& kv : ctx->free_blocks)
 		cudaFree(kv.second);
 	ctx->free_blocks.clear();
+	if(ctx->h_stage)
+		cudaFreeHost(ctx->h_stage);
+	ctx->h_stage = nullptr;
 	for(cudaEvent_t e : ctx->copy_events)
 		cudaEventDestroy(e);
 	if(ctx->copy_stream)

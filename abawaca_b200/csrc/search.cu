@@ -1408,13 +1408,16 @@ struct abw_search {
 
 namespace {
 
+// Device time of a family of kernels (abw_search_profile).  Only measured while the context is profiling (abw_profile_enable): stopping the
+// timer waits for the device, which would keep the host from preparing the next launches of a level while the current ones run.
 struct EventTimer {
 	cudaEvent_t a = nullptr, b = nullptr;
 	cudaStream_t st;
-	explicit EventTimer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); }
-	~EventTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
-	void start() { cudaEventRecord(a, st); }
-	float stop() { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+	bool on;
+	EventTimer(cudaStream_t s, bool enabled) : st(s), on(enabled) { if(on) { cudaEventCreate(&a); cudaEventCreate(&b); } }
+	~EventTimer() { if(on) { cudaEventDestroy(a); cudaEventDestroy(b); } }
+	void start() { if(on) cudaEventRecord(a, st); }
+	float stop() { if(!on) return 0.0f; cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 };
 
 template <typename T>
@@ -1664,7 +1667,7 @@ int to_device(abw_ctx* ctx, DevBuf<T>& buf, const std::vector<T>& h)
 	if(buf.n < h.size())
 		ABW_CUDA(ctx, buf.alloc(std::max<size_t>(h.size(), 64)));
 	if(!h.empty())
-		ABW_CUDA(ctx, cudaMemcpyAsync(buf.p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+		ABW_CUDA(ctx, abw_stage_upload(ctx, buf.p, h.data(), sizeof(T) * h.size()));
 	return ABW_OK;
 }
 
@@ -1706,7 +1709,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 	if(s->consumed)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_run: this search object was already run (element arrays are consumed); create a new one");
 	s->consumed = true;
-	EventTimer tm(ctx->stream);
+	EventTimer tm(ctx->stream, ctx->profiling);
 	s->prof.sweep_ms = s->prof.partition_ms = s->prof.other_ms = 0;
 	s->prof.sweep_elements = s->prof.partition_elements = 0;
 	s->prof.levels = s->prof.sweep_launches = 0;
@@ -1769,6 +1772,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 	};
 
 	while(!level.empty()) {
+		abw_stage_flip(ctx);                              // uploads of this level use the other half of the pinned staging area
 		s->prof.levels++;
 		const bool last_level = s->max_levels > 0 && s->prof.levels >= s->max_levels;
 		const uint32_t C = (uint32_t)level.size();
@@ -2236,7 +2240,7 @@ int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, 
 	s->h_mask.assign((size_t)S * s->W, 0);
 	if(W > 0)
 		memcpy(s->h_mask.data(), h_scgmask, sizeof(uint64_t) * (size_t)S * W);
-	EventTimer tm(ctx->stream);
+	EventTimer tm(ctx->stream, ctx->profiling);
 	tm.start();
 	int rc = search_build(ctx, s, values, values_on_device, layout, ld, nrows, h_row_of_dp, h_dp2scaf);
 	s->prof.build_ms = tm.stop();

@@ -199,7 +199,8 @@ int abw_search_run_sharded(abw_ctx* ctx, abw_search* s, const abw_collectives* c
  * the two children (2 = cluster1, 3 = cluster2), which is what a per-cluster adapter needs. */
 int abw_search_set_max_levels(abw_search* s, uint32_t max_levels);
 
-/* Timing of the last abw_search_run, in milliseconds of device time per kernel family (CUDA events on the context stream) */
+/* Counters of the last abw_search_run, and -- only while abw_profile_enable(ctx, 1) is in force, because measuring them makes the host wait
+ * for the device several times per level -- milliseconds of device time per kernel family (CUDA events on the context stream), else 0 */
 typedef struct {
 	float build_ms;       /* abw_search_create: key transform, sort, element packing */
 	float sweep_ms;       /* threshold-sweep kernels, all levels */

@@ -1,0 +1,372 @@
+// SAM text -> read records on the device (host text parsing is > 80 % of abawaca-build).
+//
+// Replaces, for one chunk of SAM text,
+//   SAMReader::next_mapping            ReadMappingReader.cpp:80-116  (lines; '@' header lines and empty lines are skipped)
+//   ReadMapping::ReadMapping(line)     ReadMapping.cpp:23-72         (tab-separated fields: FLAG, RNAME, POS-1, CIGAR, SEQ, the field holding "MD:Z:")
+//   ReadMapping::determine_snps        ReadMapping.cpp:78-185        (only num_snps() reaches the hot path: one per mismatch letter of MD:Z, one per
+//                                                                     deleted reference base after '^', one per insertion operation of the CIGAR string)
+//   scafs.find(ref_name)               abawaca-build.cpp:549         (reference name -> scaffold index; unknown names give index 0xFFFFFFFF)
+// The output is the abw_read record stream abw_coverage consumes, in file order.
+//
+// Data flow: newline positions are counted per 4 KB tile and scanned, which gives every line its index; a second pass writes the line starts;
+// the first byte of a line decides whether it is a record, and a scan over those flags gives the record its slot; one thread then parses one line.
+#include "common.cuh"
+#include <algorithm>
+#include <cstring>
+
+struct abw_names {
+	uint32_t nscaf = 0, nslots = 0;
+	DevBuf<unsigned long long> slot_hash;     // open addressing, 0 = empty (hashes are forced non-zero)
+	DevBuf<uint32_t> slot_index;
+	DevBuf<char> blob;                        // concatenated names
+	DevBuf<uint64_t> off;                     // [nscaf+1]
+};
+
+namespace {
+
+constexpr int LN_THREADS = 256;
+constexpr int LN_BYTES_PER_THREAD = 16;
+constexpr int LN_TILE = LN_THREADS * LN_BYTES_PER_THREAD;      // 4 KB of text per block
+
+__host__ __device__ __forceinline__ unsigned long long fnv1a(const char* s, uint64_t n)
+{
+	unsigned long long h = 1469598103934665603ull;
+	for(uint64_t i = 0; i < n; i++) {
+		h ^= (unsigned char)s[i];
+		h *= 1099511628211ull;
+	}
+	return h? h : 1ull;
+}
+
+__global__ void __launch_bounds__(LN_THREADS) k_sam_count_newlines(const char* __restrict__ text, uint64_t nbytes, uint32_t* __restrict__ tile_counts)
+{
+	__shared__ uint32_t sm[LN_THREADS / 32];
+	const uint64_t i0 = (uint64_t)blockIdx.x * LN_TILE + (uint64_t)threadIdx.x * LN_BYTES_PER_THREAD;
+	uint32_t c = 0;
+	if(i0 + LN_BYTES_PER_THREAD <= nbytes && ((reinterpret_cast<uintptr_t>(text + i0) & 15) == 0)) {
+		const uint4 w = __ldg(reinterpret_cast<const uint4*>(text + i0));
+		c = __popc(__vcmpeq4(w.x, 0x0A0A0A0Au) & 0x01010101u) + __popc(__vcmpeq4(w.y, 0x0A0A0A0Au) & 0x01010101u) +
+		    __popc(__vcmpeq4(w.z, 0x0A0A0A0Au) & 0x01010101u) + __popc(__vcmpeq4(w.w, 0x0A0A0A0Au) & 0x01010101u);
+	}
+	else {
+		for(int j = 0; j < LN_BYTES_PER_THREAD; j++)
+			if(i0 + j < nbytes && text[i0 + j] == '\n')
+				c++;
+	}
+	c = __reduce_add_sync(0xffffffffu, c);
+	if((threadIdx.x & 31) == 0)
+		sm[threadIdx.x >> 5] = c;
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		uint32_t t = 0;
+		for(int w = 0; w < LN_THREADS / 32; w++)
+			t += sm[w];
+		tile_counts[blockIdx.x] = t;
+	}
+}
+
+// line l (l >= 1) starts after the l-th newline; line 0 starts at 0.  A final newline opens an empty last line, which is not a record.
+__global__ void __launch_bounds__(LN_THREADS) k_sam_line_starts(const char* __restrict__ text, uint64_t nbytes, const uint64_t* __restrict__ tile_offs, uint64_t* __restrict__ line_start)
+{
+	__shared__ uint32_t sm[LN_THREADS / 32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint64_t i0 = (uint64_t)blockIdx.x * LN_TILE + (uint64_t)threadIdx.x * LN_BYTES_PER_THREAD;
+	uint32_t mask = 0;
+	for(int j = 0; j < LN_BYTES_PER_THREAD; j++)
+		if(i0 + j < nbytes && text[i0 + j] == '\n')
+			mask |= 1u << j;
+	const uint32_t c = __popc(mask);
+	uint32_t incl = c;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+		if(lane >= o)
+			incl += t;
+	}
+	if(lane == 31)
+		sm[warp] = incl;
+	__syncthreads();
+	uint32_t wex = 0;
+	for(int w = 0; w < warp; w++)
+		wex += sm[w];
+	uint64_t rank = tile_offs[blockIdx.x] + wex + incl - c;      // newlines before this thread's bytes
+	if(blockIdx.x == 0 && threadIdx.x == 0)
+		line_start[0] = 0;
+	while(mask) {
+		const int j = __ffs(mask) - 1;
+		mask &= mask - 1;
+		rank++;
+		line_start[rank] = i0 + j + 1;
+	}
+}
+
+// 1 for a line that becomes a record: not empty after chomp (ReadMappingReader.cpp:113) and not a header line (:108)
+__global__ void k_sam_is_record(const char* __restrict__ text, uint64_t nbytes, const uint64_t* __restrict__ line_start, uint64_t nlines, uint32_t* __restrict__ is_record)
+{
+	const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(l >= nlines)
+		return;
+	const uint64_t a = line_start[l];
+	uint64_t b = (l + 1 < nlines)? line_start[l + 1] - 1 : nbytes;   // exclusive end, without the newline
+	// fgets-based reading stops a line at '\n'; a line that is just "\n" or "\r\n" has next_line[0] == '\n' (not 0 and not '@'), so the reference
+	// would try to parse it and fail on fs[1]; real SAM files have no such lines and abawaca_b200's host parser skips them, as does this one
+	while(b > a && (text[b - 1] == '\r' || text[b - 1] == '\n'))
+		b--;
+	is_record[l] = (b > a && text[a] != '@')? 1u : 0u;
+}
+
+__device__ __forceinline__ bool dev_isspace(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
+// atoi on a field [p, e): optional white space, optional sign, digits (ReadMapping.cpp:39,41 call atoi on the field text)
+__device__ __forceinline__ int dev_atoi(const char* __restrict__ p, const char* __restrict__ e)
+{
+	while(p < e && dev_isspace(*p))
+		p++;
+	bool neg = false;
+	if(p < e && (*p == '+' || *p == '-')) {
+		neg = *p == '-';
+		p++;
+	}
+	unsigned int v = 0;
+	while(p < e && *p >= '0' && *p <= '9') {
+		v = v * 10u + (unsigned int)(*p - '0');
+		p++;
+	}
+	return neg? -(int)v : (int)v;
+}
+
+constexpr int SAM_ERR_FEW_FIELDS = 1, SAM_ERR_LOWER_N = 2, SAM_ERR_MDZ = 4;
+
+__global__ void __launch_bounds__(128) k_sam_parse(const char* __restrict__ text, uint64_t nbytes, const uint64_t* __restrict__ line_start, uint64_t nlines,
+                                                   const uint32_t* __restrict__ is_record, const uint64_t* __restrict__ rec_slot, const unsigned long long* __restrict__ slot_hash,
+                                                   const uint32_t* __restrict__ slot_index, uint32_t nslots, const char* __restrict__ name_blob,
+                                                   const uint64_t* __restrict__ name_off, abw_read* __restrict__ out, uint64_t cap, int* __restrict__ err)
+{
+	const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(l >= nlines || !is_record[l])
+		return;
+	const uint64_t slot = rec_slot[l];
+	if(slot >= cap)
+		return;
+	const char* p = text + line_start[l];
+	const char* e = text + ((l + 1 < nlines)? line_start[l + 1] - 1 : nbytes);
+	while(e > p && (e[-1] == '\r' || e[-1] == '\n'))       // chomp, ReadMappingReader.cpp:113
+		e--;
+	// walk the tab-separated fields (split('\t', ...), ReadMapping.cpp:36)
+	int field = 0;
+	const char* fs = p;                                    // start of the current field
+	uint32_t flag = 0, scaf = 0xFFFFFFFFu, pos0 = 0, len = 0, nsnps = 0, cigar_ins = 0;
+	bool have_md = false;
+	int bad = 0;
+	for(const char* q = p;; q++) {
+		if(q == e || *q == '\t') {
+			const char* fe = q;
+			if(field == 1)
+				flag = (uint32_t)dev_atoi(fs, fe);
+			else if(field == 2) {
+				const uint64_t n = (uint64_t)(fe - fs);
+				const unsigned long long h = fnv1a(fs, n);
+				uint32_t s = (uint32_t)(h & (nslots - 1));
+				for(uint32_t probe = 0; probe < nslots; probe++) {
+					const unsigned long long sh = slot_hash[s];
+					if(sh == 0)
+						break;
+					if(sh == h) {
+						const uint32_t idx = slot_index[s];
+						const uint64_t a = name_off[idx], b = name_off[idx + 1];
+						bool same = (b - a) == n;
+						for(uint64_t i = 0; same && i < n; i++)
+							same = name_blob[a + i] == fs[i];
+						if(same) {
+							scaf = idx;
+							break;
+						}
+					}
+					s = (s + 1) & (nslots - 1);
+				}
+			}
+			else if(field == 3)
+				pos0 = (uint32_t)(dev_atoi(fs, fe) - 1);    // stored 0-based, ReadMapping.cpp:41
+			else if(field == 5) {
+				for(const char* c = fs; c < fe; c++)
+					cigar_ins += (*c == 'I');                   // one INSERTION entry per I operation, ReadMapping.cpp:160-173
+			}
+			else if(field == 9) {
+				len = (uint32_t)(fe - fs);                      // SEQ.size(), ReadMapping.h:44
+				for(const char* c = fs; c < fe; c++)
+					if(*c == 'n')
+						bad |= SAM_ERR_LOWER_N;                 // Bio::DNAString throws, String.cpp:47-49
+			}
+			else if(field >= 11 && !have_md) {
+				// the first optional field that contains "MD:Z:" anywhere; the description runs to the first space or the end of the field (:53-66)
+				for(const char* c = fs; c + 5 <= fe; c++) {
+					if(c[0] == 'M' && c[1] == 'D' && c[2] == ':' && c[3] == 'Z' && c[4] == ':') {
+						have_md = true;
+						const char* m = c + 5;
+						const char* me = m;
+						while(me < fe && *me != ' ')
+							me++;
+						// MD:Z:[0-9]+(([A-Z]|\^[^0-9]+)[0-9]+)*  as determine_snps walks it (:94-125)
+						while(m < me && *m >= '0' && *m <= '9')
+							m++;
+						while(m < me) {
+							if(*m == '^') {
+								m++;
+								while(m < me && !(*m >= '0' && *m <= '9')) {
+									nsnps++;
+									m++;
+								}
+							}
+							else if(*m >= 'A' && *m <= 'Z') {
+								nsnps++;
+								m++;
+							}
+							else {
+								bad |= SAM_ERR_MDZ;
+								break;
+							}
+							if(m >= me || !(*m >= '0' && *m <= '9')) {
+								bad |= SAM_ERR_MDZ;
+								break;
+							}
+							while(m < me && *m >= '0' && *m <= '9')
+								m++;
+						}
+						break;
+					}
+				}
+			}
+			field++;
+			fs = q + 1;
+			if(q == e)
+				break;
+		}
+	}
+	if(field < 11)
+		bad |= SAM_ERR_FEW_FIELDS;                          // fs[10] is read unconditionally, ReadMapping.cpp:51
+	if(have_md)
+		nsnps += cigar_ins;                                 // without an MD:Z field determine_snps returns at once (:80-81)
+	else
+		nsnps = 0;
+	if(nsnps > 0xFFFFu)
+		nsnps = 0xFFFFu;
+	abw_read r;
+	r.scaf = scaf;
+	r.pos0 = pos0;
+	r.len = len;
+	r.flag_nsnps = (flag & 0xFFFFu) | (nsnps << 16);
+	out[slot] = r;
+	if(bad)
+		atomicOr(err, bad);
+}
+
+}  // namespace
+
+extern "C" {
+
+int abw_names_create(abw_ctx* ctx, const char* names_blob, const uint64_t* h_name_off, uint32_t nscaf, abw_names** out)
+{
+	if(!ctx || !out || !h_name_off || (!names_blob && nscaf && h_name_off[nscaf] > 0))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_names_create: null argument");
+	ABW_ENTER(ctx);
+	abw_names* nm = new abw_names();
+	int rc = [&]() -> int {
+		nm->nscaf = nscaf;
+		uint32_t nslots = 16;
+		while(nslots < 2ull * nscaf + 1)
+			nslots <<= 1;
+		nm->nslots = nslots;
+		std::vector<unsigned long long> sh(nslots, 0);
+		std::vector<uint32_t> si(nslots, 0);
+		for(uint32_t i = 0; i < nscaf; i++) {
+			if(h_name_off[i + 1] < h_name_off[i])
+				return abw_fail(ctx, ABW_ERR_ARG, "abw_names_create: offsets must be non-decreasing");
+			const unsigned long long h = fnv1a(names_blob + h_name_off[i], h_name_off[i + 1] - h_name_off[i]);
+			uint32_t s = (uint32_t)(h & (nslots - 1));
+			while(sh[s] != 0)
+				s = (s + 1) & (nslots - 1);
+			sh[s] = h;
+			si[s] = i;
+		}
+		const uint64_t blob_bytes = h_name_off[nscaf];
+		ABW_CUDA(ctx, nm->slot_hash.alloc(nslots));
+		ABW_CUDA(ctx, nm->slot_index.alloc(nslots));
+		ABW_CUDA(ctx, nm->blob.alloc(blob_bytes + 1));
+		ABW_CUDA(ctx, nm->off.alloc((size_t)nscaf + 1));
+		ABW_CUDA(ctx, cudaMemcpyAsync(nm->slot_hash.p, sh.data(), sizeof(unsigned long long) * nslots, cudaMemcpyHostToDevice, ctx->stream));
+		ABW_CUDA(ctx, cudaMemcpyAsync(nm->slot_index.p, si.data(), sizeof(uint32_t) * nslots, cudaMemcpyHostToDevice, ctx->stream));
+		if(blob_bytes)
+			ABW_CUDA(ctx, cudaMemcpyAsync(nm->blob.p, names_blob, blob_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		ABW_CUDA(ctx, cudaMemcpyAsync(nm->off.p, h_name_off, sizeof(uint64_t) * ((size_t)nscaf + 1), cudaMemcpyHostToDevice, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		return ABW_OK;
+	}();
+	if(rc != ABW_OK) {
+		delete nm;
+		return rc;
+	}
+	*out = nm;
+	return ABW_OK;
+}
+
+void abw_names_destroy(abw_names* n) { delete n; }
+
+int abw_parse_sam(abw_ctx* ctx, const abw_names* names, const char* text, uint64_t nbytes, int text_on_device, abw_read* d_reads, uint64_t cap, uint64_t* nreads)
+{
+	if(!ctx || !names || !nreads || (!text && nbytes) || (!d_reads && cap))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_parse_sam: null argument");
+	ABW_ENTER(ctx);
+	*nreads = 0;
+	if(nbytes == 0)
+		return ABW_OK;
+	DevBuf<char> d_text;
+	const char* src = text;
+	if(!text_on_device) {
+		ABW_CUDA(ctx, d_text.alloc(nbytes + 16));
+		ABW_CUDA(ctx, cudaMemcpyAsync(d_text.p, text, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+		src = d_text.p;
+	}
+	const unsigned int ntiles = abw_div_up(nbytes, LN_TILE);
+	DevBuf<uint32_t> tile_counts, is_record;
+	DevBuf<uint64_t> tile_offs, total, line_start, rec_slot;
+	DevBuf<int> d_err;
+	ABW_CUDA(ctx, tile_counts.alloc(ntiles));
+	ABW_CUDA(ctx, tile_offs.alloc(ntiles));
+	ABW_CUDA(ctx, total.alloc(2));
+	ABW_CUDA(ctx, d_err.alloc(1));
+	ABW_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
+	ABW_LAUNCH(ctx, k_sam_count_newlines, ntiles, LN_THREADS, 0, src, nbytes, tile_counts.p);
+	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, tile_counts.p, tile_offs.p, ntiles, total.p));
+	uint64_t nnl = 0;
+	ABW_CUDA(ctx, cudaMemcpyAsync(&nnl, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	const uint64_t nlines = nnl + 1;
+	ABW_CUDA(ctx, line_start.alloc(nlines));
+	ABW_CUDA(ctx, is_record.alloc(nlines));
+	ABW_CUDA(ctx, rec_slot.alloc(nlines));
+	ABW_LAUNCH(ctx, k_sam_line_starts, ntiles, LN_THREADS, 0, src, nbytes, tile_offs.p, line_start.p);
+	ABW_LAUNCH(ctx, k_sam_is_record, abw_div_up(nlines, 256), 256, 0, src, nbytes, line_start.p, nlines, is_record.p);
+	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, is_record.p, rec_slot.p, nlines, total.p + 1));
+	uint64_t nrec = 0;
+	ABW_CUDA(ctx, cudaMemcpyAsync(&nrec, total.p + 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	*nreads = nrec;
+	if(nrec > cap)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_parse_sam: the record buffer is too small for this chunk (nreads holds the number needed)");
+	if(nrec) {
+		ABW_LAUNCH(ctx, k_sam_parse, abw_div_up(nlines, 128), 128, 0, src, nbytes, line_start.p, nlines, is_record.p, rec_slot.p, names->slot_hash.p, names->slot_index.p,
+		           names->nslots, names->blob.p, names->off.p, d_reads, cap, d_err.p);
+	}
+	int h_err = 0;
+	ABW_CUDA(ctx, cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if(h_err & SAM_ERR_LOWER_N)
+		return abw_fail(ctx, ABW_ERR_ILLEGAL_DNA, "Illegal_DNAString: lower-case 'n' in a read sequence (String.cpp:47-49)");
+	if(h_err & SAM_ERR_FEW_FIELDS)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_parse_sam: a SAM line has fewer than 11 tab-separated fields (ReadMapping.cpp:36-51 reads fs[10])");
+	if(h_err & SAM_ERR_MDZ)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_parse_sam: Illegal SNPs description in an MD:Z field (Illegal_mapping, ReadMapping.cpp:100-113)");
+	return ABW_OK;
+}
+
+}  // extern "C"

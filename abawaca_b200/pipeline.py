@@ -15,6 +15,46 @@ import numpy as np
 from . import capi
 
 
+class SamParser:
+    """SAM text -> abw_read records on the device (abw_names_create / abw_parse_sam)."""
+
+    def __init__(self, ctx, names):
+        self.ctx = ctx
+        blob = "".join(names).encode()
+        off = np.zeros(len(names) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(n.encode()) for n in names])
+        self._blob = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, dtype=np.uint8)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.abw_names_create(ctx.h, capi._p(self._blob), capi._p(off), len(names), C.byref(h)))
+        self.h = h
+
+    def parse(self, text, d_reads, cap):
+        """text: bytes or uint8 array (host), ending at a line boundary.  Returns the number of records written to d_reads."""
+        arr = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, dtype=np.uint8)
+        n = C.c_uint64()
+        self.ctx.check(self.ctx.lib.abw_parse_sam(self.ctx.h, self.h, capi._p(arr) if arr.size else None, arr.size, 0, C.c_void_p(d_reads), cap, C.byref(n)))
+        return int(n.value)
+
+    def parse_to_host(self, text):
+        """convenience for tests: parse one chunk and fetch the records"""
+        arr = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, dtype=np.uint8)
+        cap = int(np.count_nonzero(arr == 10)) + 1
+        d = self.ctx.alloc(max(cap, 1) * 16)
+        try:
+            n = self.parse(arr, d, cap)
+            out = np.zeros(n, dtype=capi.READ_DTYPE)
+            if n:
+                self.ctx.to_host(out, d)
+            return out
+        finally:
+            self.ctx.free(d)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.abw_names_destroy(self.h)
+            self.h = None
+
+
 class FeatureBuild:
     """Device-resident result of the feature stage; `rows_host()` fetches the .lrn matrix."""
 

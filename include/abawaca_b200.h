@@ -111,6 +111,21 @@ int abw_kmer_features(abw_ctx* ctx, const abw_seqset* s, const abw_segments* g, 
 int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uint64_t nreads, int reads_on_device, uint32_t max_snps,
                  int kind, double* d_rows, uint64_t ld, uint32_t col, uint64_t* d_scaf_nbps);
 
+/* ---- SAM text -> read records on the device ------------------------------------------------
+ * abw_names: the scaffold names as a device-side hash table; name i is names_blob[h_name_off[i] .. h_name_off[i+1]) and gets index i
+ * (replaces the std::map<string, Scaf*> lookup scafs.find(ref_name), abawaca-build.cpp:482,549). */
+typedef struct abw_names abw_names;
+int  abw_names_create(abw_ctx* ctx, const char* names_blob, const uint64_t* h_name_off, uint32_t nscaf, abw_names** out);
+void abw_names_destroy(abw_names* n);
+/* Replaces SAMReader::next_mapping (ReadMappingReader.cpp:80-116), ReadMapping::ReadMapping(const char*) (ReadMapping.cpp:23-72) and the SNP count
+ * of ReadMapping::determine_snps (ReadMapping.cpp:78-185) for one chunk of SAM text that ends at a line boundary (the caller carries an
+ * unfinished last line over to the next chunk).  Every line that is neither empty nor a '@' header line becomes one abw_read, in file
+ * order, written to d_reads[0 .. *nreads) (device memory, capacity cap records): scaf = index of RNAME (0xFFFFFFFF if unknown),
+ * pos0 = POS - 1, len = length of SEQ, flag_nsnps = FLAG | num_snps << 16.  If the chunk holds more than cap records nothing is written,
+ * *nreads holds the number needed and ABW_ERR_ARG is returned.  Errors the reference throws on are reported as a status:
+ * lower-case 'n' in SEQ (ABW_ERR_ILLEGAL_DNA), fewer than 11 fields or a malformed MD:Z description (ABW_ERR_ARG). */
+int abw_parse_sam(abw_ctx* ctx, const abw_names* names, const char* text, uint64_t nbytes, int text_on_device, abw_read* d_reads, uint64_t cap, uint64_t* nreads);
+
 /* device memory helpers so that hosts without a CUDA runtime binding can drive the ABI */
 int abw_device_alloc(abw_ctx* ctx, size_t bytes, void** d_out);
 int abw_device_free(abw_ctx* ctx, void* d_ptr);

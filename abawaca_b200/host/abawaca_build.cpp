@@ -3,7 +3,8 @@
 //   Scaf::Scaf                      -> abw_pack_sequences + abw_segment
 //   Scaf_segment::Scaf_segment      -> abw_kmer_features
 //   Scaf::add_mapped_read           -> abw_coverage (one call per SAM file, reads in file order)
-// FASTA/SAM parsing and the text writers stay on the host.  Not ported (out of the hot path):
+//   SAMReader / ReadMapping(line)   -> abw_parse_sam (SAM text goes to the device in 64 MB chunks cut at line boundaries)
+// FASTA parsing and the text writers stay on the host.  Not ported (out of the hot path):
 // paired-end link counting (abawaca.links is written empty: `abawaca` only checks that it exists) and the calls to
 // the external gene predictor / SCG script.
 #include "abw_host.h"
@@ -133,64 +134,74 @@ int main(int argc, const char* argv[])
 		ABWH_CHECK(ctx, abw_memset_device(ctx, d_nbps, 0, std::max<uint32_t>(nscaf, 1) * sizeof(uint64_t)));
 		ABWH_CHECK(ctx, abw_kmer_features(ctx, ss, sg, ABW_FEAT_TRUNC3, 1, d_rows, ld, 0));
 
+		// the scaffold names as a device-side table: SAM text is parsed on the device (abw_parse_sam)
+		abw_names* names = nullptr;
+		{
+			std::string blob;
+			std::vector<uint64_t> noff(1, 0);
+			for(auto& kv : by_name) {
+				blob += kv.first;
+				noff.push_back(blob.size());
+			}
+			ABWH_CHECK(ctx, abw_names_create(ctx, blob.data(), noff.data(), nscaf, &names));
+		}
+		const size_t CHUNK = (size_t)64 << 20;
+		std::vector<char> buf(CHUNK + 1);
 		for(size_t j = 0; j < sam_files.size(); j++) {
 			std::cerr << stamp() << "Reading SAM file " << sam_files[j] << std::endl;
 			const bool is_this_sample = (sam_files[j] == this_sample_str);
-			FILE* fp = fopen(sam_files[j].c_str(), "r");
+			FILE* fp = fopen(sam_files[j].c_str(), "rb");
 			if(!fp)
 				throw std::runtime_error("Failed to open SAM file " + sam_files[j]);
-			std::vector<abw_read> reads;
-			char* line = nullptr;
-			size_t cap = 0;
-			ssize_t n;
-			std::vector<std::pair<const char*, size_t>> f;
-			while((n = getline(&line, &cap, fp)) >= 0) {
-				while(n > 0 && (line[n - 1] == '\n' || line[n - 1] == '\r')) line[--n] = 0;
-				if(n == 0 || line[0] == '@')
-					continue;                                      // header lines, ReadMappingReader.cpp:80-116
-				f.clear();
-				const char* p = line;
-				for(;;) {
-					const char* q = strchr(p, '\t');
-					f.push_back(std::make_pair(p, q? (size_t)(q - p) : strlen(p)));
-					if(!q) break;
-					p = q + 1;
-				}
-				if(f.size() < 11)
-					throw std::runtime_error("SAM line with fewer than 11 fields in " + sam_files[j]);
-				abw_read r;
-				const uint32_t flag = (uint32_t)atoi(std::string(f[1].first, f[1].second).c_str());
-				const std::string rname(f[2].first, f[2].second);
-				auto it = scaf_index.find(rname);
-				r.scaf = (it == scaf_index.end())? 0xFFFFFFFFu : it->second;
-				r.pos0 = (uint32_t)(atoi(std::string(f[3].first, f[3].second).c_str()) - 1);    // ReadMapping.cpp:41
-				r.len = (uint32_t)f[9].second;                                                // SEQ.size()
-				for(size_t k = 0; k < f[9].second; k++)
-					if(f[9].first[k] == 'n')
-						throw std::runtime_error("Illegal_DNAString: lower-case 'n' in a read of " + sam_files[j]);
-				std::string mdz;
-				for(size_t k = 11; k < f.size(); k++) {
-					std::string fld(f[k].first, f[k].second);
-					size_t pos = fld.find("MD:Z:");
-					if(pos != std::string::npos) {
-						size_t e = fld.find(' ', pos);
-						mdz = (e == std::string::npos)? fld.substr(pos) : fld.substr(pos, e - pos);
-						break;
+			// one record per line at most: the number of newlines bounds the number of records
+			uint64_t nlines = 1;
+			for(size_t n; (n = fread(buf.data(), 1, CHUNK, fp)) > 0;)
+				for(const char* q = buf.data(); (q = (const char*)memchr(q, '\n', buf.data() + n - q)) != nullptr; q++)
+					nlines++;
+			rewind(fp);
+			abw_read* d_reads = nullptr;
+			ABWH_CHECK(ctx, abw_device_alloc(ctx, std::max<uint64_t>(nlines, 1) * sizeof(abw_read), (void**)&d_reads));
+			uint64_t nreads = 0;
+			size_t have = 0;                                       // bytes of an unfinished line carried over from the previous chunk
+			for(;;) {
+				if(have == buf.size() - 1)
+					buf.resize(2 * buf.size());                    // a line longer than the chunk
+				const size_t n = fread(buf.data() + have, 1, buf.size() - 1 - have, fp);
+				const size_t total = have + n;
+				if(total == 0)
+					break;
+				size_t cut = total;
+				if(n > 0) {                                        // not at the end of the file: cut after the last complete line
+					while(cut > 0 && buf[cut - 1] != '\n')
+						cut--;
+					if(cut == 0) {
+						have = total;
+						continue;
 					}
 				}
-				uint32_t nsnps = count_snps(std::string(f[5].first, f[5].second), mdz);
-				if(nsnps > 0xFFFFu) nsnps = 0xFFFFu;
-				r.flag_nsnps = (flag & 0xFFFFu) | (nsnps << 16);
-				reads.push_back(r);
+				uint64_t got = 0;
+				int prc = abw_parse_sam(ctx, names, buf.data(), cut, 0, d_reads + nreads, nlines - nreads, &got);
+				if(prc == ABW_ERR_ILLEGAL_DNA) {
+					std::cerr << "Fatal error, attempted to initialize DNAString with illegal string: " << abw_last_error(ctx) << std::endl;
+					return -1;
+				}
+				if(prc != ABW_OK)
+					throw std::runtime_error(std::string("abw_parse_sam failed on ") + sam_files[j] + ": " + abw_last_error(ctx));
+				nreads += got;
+				have = total - cut;
+				memmove(buf.data(), buf.data() + cut, have);
+				if(n == 0)
+					break;
 			}
-			free(line);
 			fclose(fp);
-			ABWH_CHECK(ctx, abw_coverage(ctx, sg, reads.data(), reads.size(), 0, max_snps, ABW_FEAT_TRUNC3, d_rows, ld, (uint32_t)(179 + j), is_this_sample? d_nbps : nullptr));
+			ABWH_CHECK(ctx, abw_coverage(ctx, sg, d_reads, nreads, 1, max_snps, ABW_FEAT_TRUNC3, d_rows, ld, (uint32_t)(179 + j), is_this_sample? d_nbps : nullptr));
+			ABWH_CHECK(ctx, abw_device_free(ctx, d_reads));
 			if(is_this_sample) {
 				FILE* fl = fopen(links_file.c_str(), "w");     // scaffold-end links are not computed; the file must exist
 				if(fl) fclose(fl);
 			}
 		}
+		abw_names_destroy(names);
 
 		// fetch everything the three text files need
 		std::vector<double> rows((size_t)ndps * ld);

@@ -153,11 +153,9 @@ int main(int argc, const char* argv[])
 			FILE* fp = fopen(sam_files[j].c_str(), "rb");
 			if(!fp)
 				throw std::runtime_error("Failed to open SAM file " + sam_files[j]);
-			// one record per line at most: the number of newlines bounds the number of records
-			uint64_t nlines = 1;
-			for(size_t n; (n = fread(buf.data(), 1, CHUNK, fp)) > 0;)
-				for(const char* q = buf.data(); (q = (const char*)memchr(q, '\n', buf.data() + n - q)) != nullptr; q++)
-					nlines++;
+			// a record line has at least 11 fields, i.e. at least 10 tabs and a newline: the file size bounds the number of records
+			fseek(fp, 0, SEEK_END);
+			const uint64_t nlines = (uint64_t)ftell(fp) / 11 + 2;
 			rewind(fp);
 			abw_read* d_reads = nullptr;
 			ABWH_CHECK(ctx, abw_device_alloc(ctx, std::max<uint64_t>(nlines, 1) * sizeof(abw_read), (void**)&d_reads));

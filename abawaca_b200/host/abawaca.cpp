@@ -314,6 +314,29 @@ static void load_model(const Params& P, Model& M)
 }
 
 // size-weighted mean and standard deviation in scaffold-id order (ClusterQuality.cpp:6-27)
+// "%lf" of a value (ClusterWriter.cpp:92-98).  Columns written by abawaca-build are multiples of 0.001: for v == k / 1000.0 with a small integer k the
+// six-decimal rendering is k / 1000 "." k % 1000 "000" (the representation error of v is far below half a unit of the sixth decimal); anything else
+// goes through printf.  The cluster dumps are the host-side throughput ceiling of this program.
+static char* format_lf(char* w, double v)
+{
+	const double k = rint(v * 1000.0);
+	if(k >= 0 && k < 2.0e9 && !std::signbit(v) && k / 1000.0 == v) {
+		const unsigned long ki = (unsigned long)k;
+		unsigned long ip = ki / 1000, fp = ki % 1000;
+		char tmp[16];
+		int n = 0;
+		do { tmp[n++] = (char)('0' + ip % 10); ip /= 10; } while(ip);
+		while(n) *w++ = tmp[--n];
+		*w++ = '.';
+		*w++ = (char)('0' + fp / 100);
+		*w++ = (char)('0' + fp / 10 % 10);
+		*w++ = (char)('0' + fp % 10);
+		*w++ = '0'; *w++ = '0'; *w++ = '0';
+		return w;
+	}
+	return w + sprintf(w, "%lf", v);
+}
+
 static void weighted_stats(const std::vector<std::pair<size_t, double>>& data, double& mean, double& stdev)
 {
 	if(data.empty()) { mean = stdev = -1; return; }
@@ -378,10 +401,16 @@ int main(int argc, const char** argv)
 			fprintf(fp, "\n%c Key", '%');
 			for(size_t d = 0; d < D; d++) fprintf(fp, "\t%s", M.dim_names[d].c_str());
 			fprintf(fp, "\n");
+			std::vector<char> row(32 + D * 32);
 			for(uint32_t dp : dps) {            // the reference writes these rows in unordered_set order (quirk Q9); here ascending dp id
-				fprintf(fp, "%lu", (unsigned long)(dp + 1));
-				for(size_t d = 0; d < D; d++) fprintf(fp, "\t%lf", M.values[d * N + dp]);
-				fprintf(fp, "\n");
+				char* w = row.data();
+				w += sprintf(w, "%lu", (unsigned long)(dp + 1));
+				for(size_t d = 0; d < D; d++) {
+					*w++ = '\t';
+					w = format_lf(w, M.values[d * N + dp]);
+				}
+				*w++ = '\n';
+				fwrite(row.data(), 1, (size_t)(w - row.data()), fp);
 			}
 			fclose(fp);
 		};

@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <chrono>
+#include <cstdlib>
 
 namespace {
 
@@ -1392,7 +1394,8 @@ struct abw_search {
 	DevBuf<uint32_t> scg_k;                   // [D][K]
 	bool partial = false;
 	uint64_t Sf = 0;                          // scaffolds with n >= T/2+1
-	DevBuf<uint8_t> side, assigned, new_assigned;
+	DevBuf<uint8_t> assigned;
+	DevBuf<unsigned long long> xchg;          // per-level exchange buffer (side, new assignment, child statistics, ...), see search_run
 	DevBuf<uint32_t> low, scaf_member, scaf_final;
 	std::vector<uint32_t> h_T;
 	std::vector<uint64_t> h_len, h_mask;
@@ -1420,6 +1423,24 @@ struct EventTimer {
 	float stop() { if(!on) return 0.0f; cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 };
 
+// ABW_TRACE=1: wall-clock milestones of abw_search_create / abw_search_run on stderr (the stream is synchronised at every milestone)
+struct Trace {
+	bool on;
+	cudaStream_t st;
+	std::chrono::steady_clock::time_point t0;
+	const char* what;
+	Trace(cudaStream_t s, const char* w) : on(getenv("ABW_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()), what(w) {}
+	void mark(const char* label)
+	{
+		if(!on)
+			return;
+		cudaStreamSynchronize(st);
+		const auto t1 = std::chrono::steady_clock::now();
+		fprintf(stderr, "[abw trace] %s: %-28s %8.3f ms\n", what, label, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		t0 = t1;
+	}
+};
+
 template <typename T>
 int upload(abw_ctx* ctx, DevBuf<T>& buf, const std::vector<T>& h)
 {
@@ -1434,6 +1455,7 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 {
 	const uint64_t N = s->N;
 	const uint32_t D = s->D, S = s->S, W = s->W;
+	Trace tr(ctx->stream, "create");
 	// ---- host-side per-scaffold tables
 	s->h_n.assign(S, 0);
 	std::vector<uint64_t> first((size_t)S + 1, 0);
@@ -1485,17 +1507,17 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: sum of T over scaffolds must be below 2^31");
 	s->K = (uint32_t)scg_scafs.size();
 	const uint64_t K = s->K;
+	tr.mark("host tables");
 	ABW_CHECK(upload(ctx, s->rows, rows));
 	ABW_CHECK(upload(ctx, s->has_scg, has));
 	ABW_CHECK(upload(ctx, s->dp_first, first));
 	ABW_CHECK(upload(ctx, s->scgmask, s->h_mask));
-	{
-		std::vector<uint32_t> v(h_dp2scaf, h_dp2scaf + N);
-		ABW_CHECK(upload(ctx, s->dp2scaf, v));
-	}
+	ABW_CUDA(ctx, s->dp2scaf.alloc(N));
+	ABW_CUDA(ctx, cudaMemcpyAsync(s->dp2scaf.p, h_dp2scaf, sizeof(uint32_t) * N, cudaMemcpyHostToDevice, ctx->stream));
 	DevBuf<uint32_t> d_scg_scafs, d_scg_index;
 	ABW_CHECK(upload(ctx, d_scg_scafs, scg_scafs));
 	ABW_CHECK(upload(ctx, d_scg_index, scg_index));
+	tr.mark("uploads");
 	// ---- values, column major on the device (datapoint i lives in row row_of_dp[i] of the caller's matrix)
 	ABW_CUDA(ctx, s->values.alloc((size_t)D * N));
 	{
@@ -1531,6 +1553,7 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		}
 		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	}
+	tr.mark("values to column major");
 	// ---- per-dimension order, classes, elements; dimensions are processed in chunks to bound scratch memory
 	for(int b = 0; b < 2; b++) {
 		ABW_CUDA(ctx, s->E[b].alloc((size_t)D * N));
@@ -1582,6 +1605,7 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	if(h_nan)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: NaN in the feature matrix (comp_by_value is not a strict weak order on NaN)");
+	tr.mark("classes, sort, elements");
 	keys.release(); keys_tmp.release(); vals.release(); vals_tmp.release(); cls.release();
 	// ---- per-dimension flip list: every scaffold that can flip has exactly one class-1 element per dimension
 	if(s->strategy == ABW_SENS_SPEC && s->Sf > 0) {
@@ -1598,6 +1622,7 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		ABW_LAUNCH(ctx, k_flip_count, dim3(tiles, D), 256, 0, s->E[0].p, N, tiles, counts.p);
 		ABW_LAUNCH(ctx, k_flip_write, dim3(tiles, D), 256, 0, s->E[0].p, N, tiles, counts.p, s->flip_list[0].p, Sf);
 	}
+	tr.mark("flip lists");
 	// ---- per-dimension list of SCG-carrying scaffolds in the order their flip element appears
 	if(s->strategy == ABW_SENS_SPEC && K > 0) {
 		DevBuf<unsigned long long> lk, lk_tmp;
@@ -1612,6 +1637,7 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 			nbits++;
 		ABW_CHECK(abw_radix_sort_pairs_u64(ctx, (uint64_t*)lk.p, (uint64_t*)lk_tmp.p, s->scg_list[0].p, lv_tmp.p, K, D, K, nbits));
 	}
+	tr.mark("SCG lists");
 	// ---- root cluster
 	{
 		std::vector<uint32_t> iota(S);
@@ -1620,11 +1646,7 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		ABW_CUDA(ctx, cudaMemcpyAsync(s->scaf_list[0].p, iota.data(), sizeof(uint32_t) * S, cudaMemcpyHostToDevice, ctx->stream));
 		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	}
-	ABW_CUDA(ctx, s->side.alloc(((size_t)S + 7) / 8 * 8));            // whole 64-bit words: summed across ranks in a sharded search
 	ABW_CUDA(ctx, s->assigned.alloc(S));
-	ABW_CUDA(ctx, s->new_assigned.alloc(((size_t)S + 7) / 8 * 8));
-	ABW_CUDA(ctx, cudaMemsetAsync(s->side.p, 0, ((size_t)S + 7) / 8 * 8, ctx->stream));
-	ABW_CUDA(ctx, cudaMemsetAsync(s->new_assigned.p, 0, ((size_t)S + 7) / 8 * 8, ctx->stream));
 	ABW_CUDA(ctx, s->low.alloc(S));
 	ABW_CUDA(ctx, s->scaf_member.alloc(S));
 	ABW_CUDA(ctx, s->scaf_final.alloc(S));
@@ -1633,6 +1655,7 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	ABW_CUDA(ctx, cudaMemsetAsync(s->scaf_member.p, 0, sizeof(uint32_t) * S, ctx->stream));
 	ABW_CUDA(ctx, cudaMemsetAsync(s->scaf_final.p, 0, sizeof(uint32_t) * S, ctx->stream));
 	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	tr.mark("root cluster");
 	return ABW_OK;
 }
 
@@ -1755,10 +1778,12 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 	ABW_CUDA(ctx, cudaMemsetAsync(d_error.p, 0, sizeof(int), ctx->stream));
 	DevBuf<uint8_t> d_tab;
 	DevBuf<uint2> d_klohi;
-	DevBuf<uint64_t> d_suffix, d_never, d_child_never, d_union;
+	DevBuf<uint64_t> d_suffix, d_never, d_union;
+	uint8_t *d_side = nullptr, *d_new_assigned = nullptr;      // slices of s->xchg, set at every level that has a best separation
+	ChildStats* d_stats = nullptr;
+	unsigned long long* d_value_key = nullptr;
+	uint64_t* d_child_never = nullptr;
 	DevBuf<SplitJob> d_jobs, d_jobs_mine;
-	DevBuf<ChildStats> d_stats;
-	DevBuf<unsigned long long> d_value_key;
 	DevBuf<PartJob> d_pjobs;
 	DevBuf<TermJob> d_tjobs;
 	DevBuf<TermStats> d_tstats;
@@ -1940,42 +1965,35 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 			const uint32_t JM = (uint32_t)mine.size();
 			ABW_CHECK(to_device(ctx, d_jobs, jobs));
 			ABW_CHECK(to_device(ctx, d_jobs_mine, mine));
-			if(d_stats.n < (size_t)J * 2) ABW_CUDA(ctx, d_stats.alloc((size_t)J * 2));
-			if(d_value_key.n < J) ABW_CUDA(ctx, d_value_key.alloc(J));
-			if(d_child_never.n < (size_t)J * 2 * W) ABW_CUDA(ctx, d_child_never.alloc((size_t)J * 2 * W));
-			ABW_CUDA(ctx, cudaMemsetAsync(d_stats.p, 0, sizeof(ChildStats) * J * 2, ctx->stream));
-			ABW_CUDA(ctx, cudaMemsetAsync(d_value_key.p, 0, sizeof(unsigned long long) * J, ctx->stream));
-			ABW_CUDA(ctx, cudaMemsetAsync(d_child_never.p, 0, sizeof(uint64_t) * J * 2 * W, ctx->stream));
-			dim3 g2(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), J);
-			if(coll) {
-				// whole arrays: stale bytes of earlier levels would otherwise be summed again and carry into their neighbours
-				ABW_CUDA(ctx, cudaMemsetAsync(s->side.p, 0, ((size_t)S + 7) / 8 * 8, ctx->stream));
-				ABW_CUDA(ctx, cudaMemsetAsync(s->new_assigned.p, 0, ((size_t)S + 7) / 8 * 8, ctx->stream));
-			}
-			(void)g2;
+			// Everything the owner of a winning dimension produces for the others lives in ONE buffer, so that a sharded search needs one sum per
+			// level: side bytes | assignment bytes | child statistics | separating-value keys | masks of scaffolds that can never flip
+			const size_t s8 = ((size_t)S + 7) / 8, stat_words = sizeof(ChildStats) / 8;
+			const size_t xwords = 2 * s8 + (size_t)J * (2 * stat_words + 1 + 2 * W);
+			if(s->xchg.n < xwords) ABW_CUDA(ctx, s->xchg.alloc(xwords + xwords / 2));
+			d_side = reinterpret_cast<uint8_t*>(s->xchg.p);
+			d_new_assigned = d_side + 8 * s8;
+			d_stats = reinterpret_cast<ChildStats*>(s->xchg.p + 2 * s8);
+			d_value_key = s->xchg.p + 2 * s8 + (size_t)J * 2 * stat_words;
+			d_child_never = reinterpret_cast<uint64_t*>(d_value_key + J);
+			// whole buffer: stale bytes of earlier levels would otherwise be summed again and carry into their neighbours
+			ABW_CUDA(ctx, cudaMemsetAsync(s->xchg.p, 0, sizeof(unsigned long long) * xwords, ctx->stream));
 			if(JM > 0) {
 				dim3 g1(std::min<uint32_t>(abw_div_up(N, 256), 4u * ctx->sm_count), JM);
 				dim3 g3(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), JM);
 				ABW_LAUNCH(ctx, k_count_low, g1, 256, 0, s->E[cur].p, N, d_clusters.p, d_jobs_mine.p, s->low.p);
 				ABW_LAUNCH(ctx, k_scaf_sides, g3, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs_mine.p, s->rows.p, s->low.p, s->dp_first.p, s->values.p, N, s->scgmask.p, W,
-				           s->strategy, prm.fraction_dps_in, s->side.p, s->new_assigned.p, d_stats.p, d_child_never.p, d_value_key.p);
+				           s->strategy, prm.fraction_dps_in, d_side, d_new_assigned, d_stats, d_child_never, d_value_key);
 				ABW_LAUNCH(ctx, k_clear_low, g3, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs_mine.p, s->low.p);
 			}
 			if(coll) {
-				// every quantity below is non-zero on exactly one rank (the owner of the winning dimension): a sum is a gather
+				// every quantity is non-zero on exactly one rank (the owner of the winning dimension): a sum is a gather
 				ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-				const size_t s8 = ((size_t)S + 7) / 8;
-				int rc = coll->allreduce_sum_i64(coll->user, s->side.p, s8);
-				rc |= coll->allreduce_sum_i64(coll->user, s->new_assigned.p, s8);
-				rc |= coll->allreduce_sum_i64(coll->user, d_stats.p, (size_t)J * 2 * sizeof(ChildStats) / 8);
-				rc |= coll->allreduce_sum_i64(coll->user, d_value_key.p, J);
-				rc |= coll->allreduce_sum_i64(coll->user, d_child_never.p, (size_t)J * 2 * W);
-				if(rc != 0)
+				if(coll->allreduce_sum_i64(coll->user, s->xchg.p, xwords) != 0)
 					return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run_sharded: allreduce callback failed");
 			}
-			ABW_CUDA(ctx, cudaMemcpyAsync(stats.data(), d_stats.p, sizeof(ChildStats) * J * 2, cudaMemcpyDeviceToHost, ctx->stream));
-			ABW_CUDA(ctx, cudaMemcpyAsync(vkeys.data(), d_value_key.p, sizeof(unsigned long long) * J, cudaMemcpyDeviceToHost, ctx->stream));
-			ABW_CUDA(ctx, cudaMemcpyAsync(child_never.data(), d_child_never.p, sizeof(uint64_t) * J * 2 * W, cudaMemcpyDeviceToHost, ctx->stream));
+			ABW_CUDA(ctx, cudaMemcpyAsync(stats.data(), d_stats, sizeof(ChildStats) * J * 2, cudaMemcpyDeviceToHost, ctx->stream));
+			ABW_CUDA(ctx, cudaMemcpyAsync(vkeys.data(), d_value_key, sizeof(unsigned long long) * J, cudaMemcpyDeviceToHost, ctx->stream));
+			ABW_CUDA(ctx, cudaMemcpyAsync(child_never.data(), d_child_never, sizeof(uint64_t) * J * 2 * W, cudaMemcpyDeviceToHost, ctx->stream));
 			ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		}
 		// decide
@@ -2106,7 +2124,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 			tm.start();
 			{
 				dim3 g(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), P);
-				ABW_LAUNCH(ctx, k_commit_assigned, g, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs.p, s->new_assigned.p, s->assigned.p);
+				ABW_LAUNCH(ctx, k_commit_assigned, g, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs.p, d_new_assigned, s->assigned.p);
 			}
 			// which arrays take part, in one plan so that the look-back words and tickets are cleared with a single memset
 			struct PartPlan { const uint32_t* in; uint32_t* out; uint64_t stride; uint32_t ndims; const std::vector<PartJob>* jv; uint32_t TT; uint64_t items, lb_off, tab_off, job_off; };
@@ -2146,7 +2164,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 				const PartPlan& pl = plans[i];
 				if(pl.items == 0)
 					continue;
-				ABW_LAUNCH(ctx, k_partition2, (unsigned int)pl.items, SW_THREADS, 0, pl.in, pl.out, pl.stride, d_pjobs.p + pl.job_off, pl.TT, d_ptile_tab.p + pl.tab_off, s->side.p,
+				ABW_LAUNCH(ctx, k_partition2, (unsigned int)pl.items, SW_THREADS, 0, pl.in, pl.out, pl.stride, d_pjobs.p + pl.job_off, pl.TT, d_ptile_tab.p + pl.tab_off, d_side,
 				           d_lookback.p + i, d_lookback.p + pl.lb_off, d_error.p);
 			}
 			s->prof.partition_ms += tm.stop();

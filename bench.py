@@ -6,7 +6,7 @@
 One "step" = one pass of the hot path over one synthetic metagenome: pack -> windows -> k-mer signature ->
 per-sample coverage -> split search down to the final bins.  At N=1 the workload is BASELINE.json configs[1]
 (50k scaffolds, 10 samples).  At N>1 the assembly has N x 50k scaffolds of ONE community (weak scaling): scaffolds are
-sharded across the ranks for the feature build (no exchange), the feature rows are all-gathered over NCCL, and the split
+sharded across the ranks for the feature build (no exchange), one NCCL all-to-all hands every rank its block of columns of all rows, and the split
 search is sharded by dimension (abw_search_run_sharded: all-gather of per-cluster best records + one sum per level).
 
   value : whole-job scaffolds/s with the inputs (ASCII assembly, read records) already resident in HBM
@@ -246,6 +246,14 @@ def main():
     total_bp = int(mg.seq.size)
     nreads = [int(r.size) for r in mg.reads]
     coll = distributed.TorchCollectives(local_rank) if world > 1 else None
+    lengths_all = masks_all = None
+    if world > 1:
+        # static per-scaffold inputs of all ranks (sequence length, SCG mask), exchanged once: they are inputs, not results of a step
+        st_local = torch.from_numpy(np.stack([lengths.astype(np.int64), masks[:, 0].astype(np.int64)], axis=1)).to(torch.device("cuda", local_rank))
+        st_all = torch.empty((world * nscaf, 2), dtype=torch.int64, device=st_local.device)
+        dist.all_gather_into_tensor(st_all, st_local)
+        st_all = st_all.cpu().numpy()
+        lengths_all, masks_all = st_all[:, 0].astype(np.uint64), st_all[:, 1].astype(np.uint64)
 
     # pinned host copies (e2e) and device-resident copies (value)
     h_seq = torch.from_numpy(mg.seq).pin_memory()
@@ -287,25 +295,37 @@ def main():
             nbins = int(np.count_nonzero(np.unique(res.scaf2cluster)))
             ndps_total = int(keep.sum())
         else:
-            # 1) every rank holds the rows of its own scaffolds: all-gather them (NCCL) so that every rank has all datapoints
+            # 1) windows per scaffold of every rank (the only per-scaffold quantity this step computed; lengths and SCG masks of all ranks were
+            #    exchanged once at set-up): everybody derives the same global scaffold table, scaffold ids rank-major
+            t_x0 = time.perf_counter()
+            cnt_local = torch.from_numpy(np.diff(seg_first.astype(np.int64)).astype(np.int32)).to(dev)
+            cnt_all = torch.empty(world * nscaf, dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(cnt_all, cnt_local)
+            cnt_all = cnt_all.cpu().numpy()
+            keep_all = cnt_all >= 2                                            # ScafDpData.cpp:92-93
+            T_all = cnt_all[keep_all].astype(np.uint32)
+            dp2scaf_all = np.repeat(np.arange(T_all.size, dtype=np.uint32), T_all)
+            rows_per_rank = [int(cnt_all[r * nscaf:(r + 1) * nscaf][keep_all[r * nscaf:(r + 1) * nscaf]].sum()) for r in range(world)]
+            if timings is not None:
+                timings["exchange_tables_ms"] = 1000.0 * (time.perf_counter() - t_x0)
+                t_x0 = time.perf_counter()
+            # 2) every rank holds the rows of its own scaffolds and will search a block of COLUMNS of all datapoints: one all-to-all (NCCL) in which
+            #    rank q receives from everybody the columns it owns -- 1/world of what an all-gather of whole rows would move
             local = torch.as_tensor(distributed._DevArray(fb.d_rows, fb.nseg * fb.ncols * 8, "<f8", 8), device=dev).view(fb.nseg, fb.ncols)
             if not keep.all():
                 local = local[torch.from_numpy(np.nonzero(keep)[0]).to(dev)]
-            meta = torch.tensor([int(keep.sum()), int(kept.size)], dtype=torch.int64, device=dev)
-            metas = torch.empty(2 * world, dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(metas, meta)
-            metas = metas.cpu().numpy().reshape(world, 2)
-            full = distributed.allgather_rows(torch, dist, local.contiguous(), [int(x) for x in metas[:, 0]])
-            # 2) per-scaffold tables of all ranks (T, length, SCG mask); scaffold ids are rank-major
-            sc = np.stack([T.astype(np.int64), lengths[kept].astype(np.int64), masks[kept][:, 0].astype(np.int64)], axis=1)
-            sc_all = distributed.allgather_rows(torch, dist, torch.from_numpy(sc).to(dev), [int(x) for x in metas[:, 1]]).cpu().numpy()
-            T_all = sc_all[:, 0].astype(np.uint32)
-            dp2scaf_all = np.repeat(np.arange(T_all.size, dtype=np.uint32), T_all)
+            blocks = [distributed.dim_block(fb.ncols, r, world) for r in range(world)]
+            off, cnt = blocks[rank]
+            n_local = int(local.shape[0])
+            send = torch.cat([local[:, o:o + c].reshape(-1) for o, c in blocks])
+            full = torch.empty((sum(rows_per_rank), cnt), dtype=torch.float64, device=dev)
+            dist.all_to_all_single(full.view(-1), send, output_split_sizes=[n * cnt for n in rows_per_rank], input_split_sizes=[n_local * c for _, c in blocks])
             torch.cuda.synchronize(dev)
+            if timings is not None:
+                timings["exchange_columns_ms"] = 1000.0 * (time.perf_counter() - t_x0)
             # 3) dimension-sharded search: this rank sweeps columns [off, off+cnt) of every datapoint
-            off, cnt = distributed.dim_block(fb.ncols, rank, world)
-            res = pipeline.search(ctx, full.data_ptr() + 8 * off, dp2scaf_all, T_all, sc_all[:, 1].astype(np.uint64), sc_all[:, 2].astype(np.uint64),
-                                  layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=int(full.shape[0]), D=cnt, ld=fb.ncols, timings=timings,
+            res = pipeline.search(ctx, full.data_ptr(), dp2scaf_all, T_all, lengths_all[keep_all], masks_all[keep_all],
+                                  layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=int(full.shape[0]), D=cnt, ld=cnt, timings=timings,
                                   collectives=coll, dim_offset=off, D_total=fb.ncols)
             nbins = int(np.count_nonzero(np.unique(res.scaf2cluster)))
             ndps_total = int(full.shape[0])
@@ -421,7 +441,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/int64/f64", "data": "synthetic",
             "config": {"workload": workload_name(w), "per_gpu": f"{nscaf} scaffolds, {total_bp} bp, {state['nseg']} windows x {state['ncols']} dimensions, {sum(nreads)} read records",
-                       "parallelism": (f"one community of {world} x {nscaf} scaffolds: scaffold-sharded feature build, NCCL all-gather of feature rows, "
+                       "parallelism": (f"one community of {world} x {nscaf} scaffolds: scaffold-sharded feature build, NCCL all-to-all of feature columns, "
                                        f"dimension-sharded split search ({state['ncols']} dimensions over {world} ranks)") if world > 1 else "1 GPU",
                        "l2": "inputs (assembly + read records, > 2 GB) are larger than the 126 MB L2; no explicit flush",
                        "clusters_evaluated": state["nclusters"], "bins": bins_total, "search_levels": prof.levels, "datapoints": state["ndps"],

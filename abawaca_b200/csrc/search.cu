@@ -736,27 +736,46 @@ __global__ void __launch_bounds__(256) k_reduce_best(const CandRec* __restrict__
 // ---------------------------------------------------------------------------------------------------
 constexpr uint32_t SCG_WMAX = 8;   // up to 512 distinct SCG names
 
-__global__ void k_pass_table(const uint32_t* __restrict__ scg_list, uint64_t list_stride, const ClusterDesc* __restrict__ clusters, const uint64_t* __restrict__ scgmask,
-                             uint32_t W, const uint64_t* __restrict__ never_mask, double overlap_thr, uint64_t* __restrict__ suffix_tmp, uint8_t* __restrict__ tab,
-                             uint64_t tab_stride, uint32_t D, uint2* __restrict__ klohi, unsigned long long scg_min_size)
+constexpr int PT_WARPS = 8;
+// one CTA per (cluster, dimension): the K events are cut into PT_WARPS chunks; a first pass ORs the masks of every chunk, then every warp
+// runs the suffix and prefix passes over its own chunk, seeded with the ORs of the chunks after / before it
+__global__ void __launch_bounds__(PT_WARPS * 32) k_pass_table(const uint32_t* __restrict__ scg_list, uint64_t list_stride, const ClusterDesc* __restrict__ clusters,
+                             const uint64_t* __restrict__ scgmask, uint32_t W, const uint64_t* __restrict__ never_mask, double overlap_thr, uint64_t* __restrict__ suffix_tmp,
+                             uint8_t* __restrict__ tab, uint64_t tab_stride, uint32_t D, uint2* __restrict__ klohi, unsigned long long scg_min_size)
 {
-	const int lane = threadIdx.x & 31;
-	const uint32_t c = blockIdx.x, d = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	if(d >= D)
-		return;
+	__shared__ unsigned long long chunk_or[PT_WARPS][SCG_WMAX];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t c = blockIdx.x, d = blockIdx.y;
 	const ClusterDesc cl = clusters[c];
-	if(lane == 0)                                          // size test of the level (k_flip_prefix narrows it): with no flip at all side 1 is empty
+	if(threadIdx.x == 0)                                   // size test of the level (k_flip_prefix narrows it): with no flip at all side 1 is empty
 		klohi[(uint64_t)d * gridDim.x + c] = (cl.totLen >= scg_min_size)? make_uint2(scg_min_size == 0? 0u : 0xFFFFFFFFu, 0xFFFFFFFFu) : make_uint2(0xFFFFFFFFu, 0u);
 	const uint32_t* __restrict__ list = scg_list + (uint64_t)d * list_stride + cl.kOff;
 	uint64_t* __restrict__ suf = suffix_tmp + ((uint64_t)d * list_stride + cl.kOff) * W;     // suf[k] = OR of masks k..K-1
 	uint8_t* __restrict__ t = tab + (uint64_t)d * tab_stride + cl.tabOff;
 	const uint32_t K = cl.K;
+	// entries 0..K (K+1 of them) and masks 0..K-1 share the chunk boundaries
+	const uint32_t ech = ((K + 1 + PT_WARPS - 1) / PT_WARPS + 31u) & ~31u;
+	const uint32_t e0 = min(K + 1, warp * ech), e1 = min(K + 1, e0 + ech);      // entries of this warp
+	const uint32_t m1 = min(K, e1);                                            // its masks: [e0, m1)
+	for(uint32_t w = 0; w < W; w++) {
+		unsigned long long o = 0;
+		for(uint32_t k = e0 + lane; k < m1; k += 32)
+			o |= scgmask[(uint64_t)(list[k] & EL_SCAF_MASK) * W + w];
+		o = (unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)o) | ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(o >> 32)) << 32);
+		if(lane == 0)
+			chunk_or[warp][w] = o;
+	}
+	__syncthreads();
+	if(e0 >= e1)
+		return;
 	// pass 1 (backwards): suffix ORs, one mask word at a time
 	for(uint32_t w = 0; w < W; w++) {
 		uint64_t carry = 0;
-		for(int64_t base = (int64_t)((K + 31) / 32) * 32 - 32; base >= 0; base -= 32) {
+		for(int w2 = warp + 1; w2 < PT_WARPS; w2++)
+			carry |= chunk_or[w2][w];
+		for(int64_t base = (int64_t)e0 + (int64_t)((m1 > e0? m1 - e0 + 31 : 0) / 32) * 32 - 32; base >= (int64_t)e0; base -= 32) {
 			const uint32_t k = (uint32_t)base + lane;
-			uint64_t m = (k < K)? scgmask[(uint64_t)(list[k] & EL_SCAF_MASK) * W + w] : 0ull;
+			uint64_t m = (k < m1)? scgmask[(uint64_t)(list[k] & EL_SCAF_MASK) * W + w] : 0ull;
 #pragma unroll
 			for(int o = 1; o < 32; o <<= 1) {
 				uint64_t x = __shfl_down_sync(0xffffffffu, m, o);
@@ -764,24 +783,33 @@ __global__ void k_pass_table(const uint32_t* __restrict__ scg_list, uint64_t lis
 					m |= x;
 			}
 			m |= carry;
-			if(k < K)
+			if(k < m1)
 				suf[(uint64_t)k * W + w] = m;
 			carry = __shfl_sync(0xffffffffu, m, 0);
 		}
 	}
 	__syncwarp();
 	// pass 2 (forwards): entry k sees side 1 = events [0, k), side 2 = events [k, K) plus the scaffolds that can never flip
-	uint64_t carry[SCG_WMAX];
+	uint64_t carry[SCG_WMAX], after[SCG_WMAX];
 #pragma unroll
-	for(uint32_t w = 0; w < SCG_WMAX; w++)
+	for(uint32_t w = 0; w < SCG_WMAX; w++) {
 		carry[w] = 0;
-	for(uint32_t base = 0; base <= K; base += 32) {
+		after[w] = 0;
+		if(w < W) {
+			for(int w2 = 0; w2 < warp; w2++)
+				carry[w] |= chunk_or[w2][w];
+			for(int w2 = warp + 1; w2 < PT_WARPS; w2++)
+				after[w] |= chunk_or[w2][w];                    // suffix of an entry that lies past the masks of this chunk (k == m1)
+		}
+	}
+	for(uint32_t base = e0; base < e1; base += 32) {
 		const uint32_t k = base + lane;
 		uint32_t g1 = 0, g2 = 0, g12 = 0;
 #pragma unroll
 		for(uint32_t w = 0; w < SCG_WMAX; w++) {
 			if(w < W) {
-				uint64_t pre = (k >= 1 && k - 1 < K)? scgmask[(uint64_t)(list[k - 1] & EL_SCAF_MASK) * W + w] : 0ull;
+				// mask of event k-1, unless it belongs to an earlier chunk (then it is already in the carry)
+				uint64_t pre = (k >= 1 && k - 1 >= e0 && k - 1 < K)? scgmask[(uint64_t)(list[k - 1] & EL_SCAF_MASK) * W + w] : 0ull;
 #pragma unroll
 				for(int o = 1; o < 32; o <<= 1) {
 					uint64_t x = __shfl_up_sync(0xffffffffu, pre, o);
@@ -790,13 +818,13 @@ __global__ void k_pass_table(const uint32_t* __restrict__ scg_list, uint64_t lis
 				}
 				pre |= carry[w];
 				carry[w] = __shfl_sync(0xffffffffu, pre, 31);
-				const uint64_t s2 = ((k < K)? suf[(uint64_t)k * W + w] : 0ull) | never_mask[(uint64_t)c * W + w];
+				const uint64_t s2 = ((k < m1)? suf[(uint64_t)k * W + w] : after[w]) | never_mask[(uint64_t)c * W + w];
 				g1 += __popcll(pre);
 				g2 += __popcll(s2);
 				g12 += __popcll(pre & s2);
 			}
 		}
-		if(k <= K) {
+		if(k < e1) {
 			uint8_t r;
 			if(g1 == 0 || g2 == 0)
 				r = 2;                                                  // ClusterQuality.cpp:118-120: decided on the two total sizes
@@ -1845,7 +1873,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 			tm.start();
 			if(d_klohi.n < (size_t)D * C)
 				ABW_CUDA(ctx, d_klohi.alloc((size_t)D * C));
-			ABW_LAUNCH(ctx, k_pass_table, dim3(C, abw_div_up(D, 4)), 128, 0, s->scg_list[cur].p, (uint64_t)s->K, d_clusters.p, s->scgmask.p, W, d_never.p,
+			ABW_LAUNCH(ctx, k_pass_table, dim3(C, D), PT_WARPS * 32, 0, s->scg_list[cur].p, (uint64_t)s->K, d_clusters.p, s->scgmask.p, W, d_never.p,
 			           prm.scg_overlap_threshold, d_suffix.p, d_tab.p, tab_stride, D, d_klohi.p, (unsigned long long)prm.scg_min_size);
 			s->prof.other_ms += tm.stop();
 		}

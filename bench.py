@@ -17,6 +17,7 @@ search is sharded by dimension (abw_search_run_sharded: all-gather of per-cluste
 `--impl reference` times only that reference arm (rank 0; other ranks exit 0).
 """
 import argparse
+import gc
 import json
 import os
 import shutil
@@ -56,7 +57,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "250"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -353,6 +354,8 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.launches
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        gc.collect()
+        gc.disable()                                   # no interpreter garbage collection pause inside the timed region
         e0.record(ext)
         for i in range(steps):
             step(resident)
@@ -360,6 +363,7 @@ def main():
         e1.record(ext)
         e1.synchronize()
         torch.cuda.synchronize()
+        gc.enable()
         ms = e0.elapsed_time(e1)
         per_step = [round(([e0] + marks)[i].elapsed_time(marks[i]), 3) for i in range(steps)]
         t = torch.tensor([ms], device="cuda")
@@ -369,7 +373,8 @@ def main():
 
     # the sampler is started BEFORE the warm-up: nvidia-smi takes driver locks while it starts and would otherwise stall the first timed launches
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:                                      # one nvidia-smi poller per job: every query takes driver locks that all ranks' launches wait on
+        sampler.start()
     for _ in range(args.warmup):
         step(True)
     sampler.rows.clear()                               # keep only the samples taken during the timed region

@@ -22,6 +22,15 @@ struct abw_names {
 	DevBuf<uint64_t> off;                     // [nscaf+1]
 };
 
+struct abw_fasta {
+	uint64_t nbytes = 0, nlines = 0, nrec = 0;
+	DevBuf<char> text;                        // the text, when it was given on the host
+	const char* d_text = nullptr;
+	DevBuf<uint64_t> line_a, hdr_before, chars_before, rec_id_off, rec_chars0;
+	DevBuf<uint32_t> line_len, rec_id_len;
+	std::vector<uint64_t> h_seq_len;
+};
+
 namespace {
 
 constexpr int LN_THREADS = 256;
@@ -260,6 +269,87 @@ __global__ void __launch_bounds__(128) k_sam_parse(const char* __restrict__ text
 		atomicOr(err, bad);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// FASTA text -> records (SeqIORead_fasta<S>::next_seq, SeqIORead_fasta.h:51-103, with SeqIORead<S>::getline(true), SeqIORead.h:85-121)
+//   every line is trimmed of white space on both ends (:88-96); blank lines are skipped (getline(true)); a line whose first character is '>'
+//   opens a record, its id is the text up to the first white space (:57-76); every other line is appended to the sequence of the open
+//   record, interior white space included (:97).
+// ---------------------------------------------------------------------------------------------------
+constexpr int FA_ERR_NO_HEADER = 1, FA_ERR_EMPTY_ID = 2;
+
+// one thread per line: trimmed extent and kind (0 blank, 1 header, 2 sequence)
+__global__ void k_fa_classify(const char* __restrict__ text, uint64_t nbytes, const uint64_t* __restrict__ line_start, uint64_t nlines, uint64_t* __restrict__ line_a,
+                              uint32_t* __restrict__ line_len, uint32_t* __restrict__ is_header, uint32_t* __restrict__ id_len, int* __restrict__ err)
+{
+	const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(l >= nlines)
+		return;
+	uint64_t a = line_start[l], b = (l + 1 < nlines)? line_start[l + 1] : nbytes;
+	while(a < b && dev_isspace(text[a]))
+		a++;
+	while(b > a && dev_isspace(text[b - 1]))
+		b--;
+	uint32_t hdr = 0, len = 0, idl = 0;
+	if(b > a) {
+		if(text[a] == '>') {
+			hdr = 1;
+			uint64_t q = a + 1;
+			while(q < b && !dev_isspace(text[q]))
+				q++;
+			idl = (uint32_t)(q - (a + 1));
+			if(idl == 0)
+				atomicOr(err, FA_ERR_EMPTY_ID);          // "Was expeecting a header line ..." (:58-62)
+		}
+		else
+			len = (uint32_t)min((uint64_t)0xFFFFFFFFu, b - a);
+	}
+	line_a[l] = a;
+	line_len[l] = len;
+	is_header[l] = hdr;
+	id_len[l] = idl;
+}
+
+// per line: its record (headers seen so far - 1); header lines publish where the record starts in the running sum of sequence characters
+__global__ void k_fa_records(const uint64_t* __restrict__ line_a, const uint32_t* __restrict__ line_len, const uint32_t* __restrict__ is_header, const uint32_t* __restrict__ id_len,
+                             const uint64_t* __restrict__ hdr_before, const uint64_t* __restrict__ chars_before, uint64_t nlines, uint64_t nrec,
+                             uint64_t* __restrict__ rec_id_off, uint32_t* __restrict__ rec_id_len, uint64_t* __restrict__ rec_chars0, int* __restrict__ err)
+{
+	const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(l >= nlines)
+		return;
+	if(is_header[l]) {
+		const uint64_t r = hdr_before[l];
+		rec_id_off[r] = line_a[l] + 1;
+		rec_id_len[r] = id_len[l];
+		rec_chars0[r] = chars_before[l];
+	}
+	else if(line_len[l] && hdr_before[l] == 0)
+		atomicOr(err, FA_ERR_NO_HEADER);                  // sequence text before the first header line (:58-62)
+}
+
+// one warp per sequence line: copy its trimmed text to where the record goes in the requested order
+__global__ void __launch_bounds__(256) k_fa_copy(const char* __restrict__ text, const uint64_t* __restrict__ line_a, const uint32_t* __restrict__ line_len,
+                                                 const uint64_t* __restrict__ hdr_before, const uint64_t* __restrict__ chars_before, uint64_t nlines,
+                                                 const uint64_t* __restrict__ rec_chars0, const uint64_t* __restrict__ rec_dst, char* __restrict__ out)
+{
+	const int lane = threadIdx.x & 31;
+	const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	for(uint64_t l = warp0; l < nlines; l += nwarps) {
+		const uint32_t len = line_len[l];
+		if(len == 0)
+			continue;
+		const uint64_t r = hdr_before[l] - 1;
+		const uint64_t dst0 = rec_dst[r];
+		if(dst0 == ~0ull)
+			continue;                                       // record not wanted (e.g. a later record with a name already seen)
+		const char* __restrict__ src = text + line_a[l];
+		char* __restrict__ dst = out + dst0 + (chars_before[l] - rec_chars0[r]);
+		for(uint32_t i = lane; i < len; i += 32)
+			dst[i] = src[i];
+	}
+}
+
 }  // namespace
 
 extern "C" {
@@ -367,6 +457,130 @@ int abw_parse_sam(abw_ctx* ctx, const abw_names* names, const char* text, uint64
 	if(h_err & SAM_ERR_MDZ)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_parse_sam: Illegal SNPs description in an MD:Z field (Illegal_mapping, ReadMapping.cpp:100-113)");
 	return ABW_OK;
+}
+
+int abw_fasta_scan(abw_ctx* ctx, const char* text, uint64_t nbytes, int text_on_device, abw_fasta** out)
+{
+	if(!ctx || !out || (!text && nbytes))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_fasta_scan: null argument");
+	ABW_ENTER(ctx);
+	abw_fasta* f = new abw_fasta();
+	int rc = [&]() -> int {
+		f->nbytes = nbytes;
+		if(nbytes == 0)
+			return ABW_OK;
+		if(!text_on_device) {
+			ABW_CUDA(ctx, f->text.alloc(nbytes + 16));
+			ABW_CUDA(ctx, cudaMemcpyAsync(f->text.p, text, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+			f->d_text = f->text.p;
+		}
+		else
+			f->d_text = text;
+		const unsigned int ntiles = abw_div_up(nbytes, LN_TILE);
+		DevBuf<uint32_t> tile_counts, is_header, id_len;
+		DevBuf<uint64_t> tile_offs, total, line_start;
+		DevBuf<int> d_err;
+		ABW_CUDA(ctx, tile_counts.alloc(ntiles));
+		ABW_CUDA(ctx, tile_offs.alloc(ntiles));
+		ABW_CUDA(ctx, total.alloc(3));
+		ABW_CUDA(ctx, d_err.alloc(1));
+		ABW_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
+		ABW_LAUNCH(ctx, k_sam_count_newlines, ntiles, LN_THREADS, 0, f->d_text, nbytes, tile_counts.p);
+		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, tile_counts.p, tile_offs.p, ntiles, total.p));
+		uint64_t nnl = 0;
+		ABW_CUDA(ctx, cudaMemcpyAsync(&nnl, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		const uint64_t nlines = nnl + 1;
+		f->nlines = nlines;
+		ABW_CUDA(ctx, line_start.alloc(nlines));
+		ABW_CUDA(ctx, f->line_a.alloc(nlines));
+		ABW_CUDA(ctx, f->line_len.alloc(nlines));
+		ABW_CUDA(ctx, is_header.alloc(nlines));
+		ABW_CUDA(ctx, id_len.alloc(nlines));
+		ABW_CUDA(ctx, f->hdr_before.alloc(nlines));
+		ABW_CUDA(ctx, f->chars_before.alloc(nlines));
+		ABW_LAUNCH(ctx, k_sam_line_starts, ntiles, LN_THREADS, 0, f->d_text, nbytes, tile_offs.p, line_start.p);
+		ABW_LAUNCH(ctx, k_fa_classify, abw_div_up(nlines, 256), 256, 0, f->d_text, nbytes, line_start.p, nlines, f->line_a.p, f->line_len.p, is_header.p, id_len.p, d_err.p);
+		// hdr_before[l] = header lines strictly before l; a header line itself gets its own record index, a sequence line index + 1 of its record
+		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, is_header.p, f->hdr_before.p, nlines, total.p + 1));
+		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, f->line_len.p, f->chars_before.p, nlines, total.p + 2));
+		uint64_t tot[2] = {0, 0};
+		ABW_CUDA(ctx, cudaMemcpyAsync(tot, total.p + 1, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		const uint64_t nrec = tot[0], nchars = tot[1];
+		f->nrec = nrec;
+		ABW_CUDA(ctx, f->rec_id_off.alloc(nrec));
+		ABW_CUDA(ctx, f->rec_id_len.alloc(nrec));
+		ABW_CUDA(ctx, f->rec_chars0.alloc(nrec + 1));
+		ABW_LAUNCH(ctx, k_fa_records, abw_div_up(nlines, 256), 256, 0, f->line_a.p, f->line_len.p, is_header.p, id_len.p, f->hdr_before.p, f->chars_before.p, nlines, nrec,
+		           f->rec_id_off.p, f->rec_id_len.p, f->rec_chars0.p, d_err.p);
+		ABW_CUDA(ctx, cudaMemcpyAsync(f->rec_chars0.p + nrec, &nchars, sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+		int h_err = 0;
+		ABW_CUDA(ctx, cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		std::vector<uint64_t> c0(nrec + 1);
+		ABW_CUDA(ctx, cudaMemcpyAsync(c0.data(), f->rec_chars0.p, sizeof(uint64_t) * (nrec + 1), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		if(h_err)
+			return abw_fail(ctx, ABW_ERR_ARG, "Bad_file: was expecting a header line for the next sequence in a fasta file but got something else (SeqIORead_fasta.h:58-62)");
+		f->h_seq_len.resize(nrec);
+		for(uint64_t r = 0; r < nrec; r++)
+			f->h_seq_len[r] = c0[r + 1] - c0[r];
+		// from here on a sequence line looks its record up as hdr_before - 1
+		return ABW_OK;
+	}();
+	if(rc != ABW_OK) {
+		delete f;
+		return rc;
+	}
+	*out = f;
+	return ABW_OK;
+}
+
+void abw_fasta_destroy(abw_fasta* f) { delete f; }
+
+uint64_t abw_fasta_count(const abw_fasta* f) { return f? f->nrec : 0; }
+
+int abw_fasta_get(abw_ctx* ctx, const abw_fasta* f, uint64_t* h_id_off, uint32_t* h_id_len, uint64_t* h_seq_len)
+{
+	if(!ctx || !f)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_fasta_get: null argument");
+	if(f->nrec == 0)
+		return ABW_OK;
+	if(h_id_off)
+		ABW_CUDA(ctx, cudaMemcpyAsync(h_id_off, f->rec_id_off.p, sizeof(uint64_t) * f->nrec, cudaMemcpyDeviceToHost, ctx->stream));
+	if(h_id_len)
+		ABW_CUDA(ctx, cudaMemcpyAsync(h_id_len, f->rec_id_len.p, sizeof(uint32_t) * f->nrec, cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if(h_seq_len)
+		memcpy(h_seq_len, f->h_seq_len.data(), sizeof(uint64_t) * f->nrec);
+	return ABW_OK;
+}
+
+int abw_fasta_pack(abw_ctx* ctx, const abw_fasta* f, const uint32_t* h_order, uint32_t nout, abw_seqset** out)
+{
+	if(!ctx || !f || !out || (!h_order && nout))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_fasta_pack: null argument");
+	ABW_ENTER(ctx);
+	std::vector<uint64_t> offsets((size_t)nout + 1, 0), rec_dst(f->nrec, ~0ull);
+	for(uint32_t i = 0; i < nout; i++) {
+		if(h_order[i] >= f->nrec)
+			return abw_fail(ctx, ABW_ERR_ARG, "abw_fasta_pack: record index out of range");
+		if(rec_dst[h_order[i]] != ~0ull)
+			return abw_fail(ctx, ABW_ERR_ARG, "abw_fasta_pack: a record may appear only once in the order");
+		rec_dst[h_order[i]] = offsets[i];
+		offsets[i + 1] = offsets[i] + f->h_seq_len[h_order[i]];
+	}
+	DevBuf<char> ascii;
+	DevBuf<uint64_t> d_dst;
+	ABW_CUDA(ctx, ascii.alloc(offsets[nout] + 64));
+	ABW_CUDA(ctx, d_dst.alloc(f->nrec));
+	if(f->nrec) {
+		ABW_CUDA(ctx, cudaMemcpyAsync(d_dst.p, rec_dst.data(), sizeof(uint64_t) * f->nrec, cudaMemcpyHostToDevice, ctx->stream));
+		const unsigned int blocks = (unsigned int)std::min<uint64_t>(abw_div_up(f->nlines * 32, 256), (uint64_t)ctx->sm_count * 16);
+		ABW_LAUNCH(ctx, k_fa_copy, blocks, 256, 0, f->d_text, f->line_a.p, f->line_len.p, f->hdr_before.p, f->chars_before.p, f->nlines, f->rec_chars0.p, d_dst.p, ascii.p);
+	}
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // rec_dst is a local
+	return abw_pack_sequences(ctx, ascii.p, 1, offsets.data(), nout, out);
 }
 
 }  // extern "C"

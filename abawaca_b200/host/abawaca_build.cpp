@@ -1,10 +1,11 @@
 // abawaca-build (B200): same command line and same output files as the reference program
 // (/root/reference/src/abawaca-build.cpp main, :434-634), with the feature stage on the device:
-//   Scaf::Scaf                      -> abw_pack_sequences + abw_segment
+//   SeqIORead_fasta::next_seq       -> abw_fasta_scan / abw_fasta_pack (the FASTA text goes to the device as it is)
+//   Scaf::Scaf                      -> abw_segment
 //   Scaf_segment::Scaf_segment      -> abw_kmer_features
 //   Scaf::add_mapped_read           -> abw_coverage (one call per SAM file, reads in file order)
 //   SAMReader / ReadMapping(line)   -> abw_parse_sam (SAM text goes to the device in 64 MB chunks cut at line boundaries)
-// FASTA parsing and the text writers stay on the host.  Not ported (out of the hot path):
+// The text writers stay on the host.  Not ported (out of the hot path):
 // paired-end link counting (abawaca.links is written empty: `abawaca` only checks that it exists) and the calls to
 // the external gene predictor / SCG script.
 #include "abw_host.h"
@@ -78,36 +79,52 @@ int main(int argc, const char* argv[])
 
 	try {
 		std::cerr << stamp() << "Reading assembly file (" << assembly_file << ")" << std::endl;
-		std::vector<FastaRecord> recs = read_fasta(assembly_file);
-		// scaffolds in name order; the first record of a name wins (std::map::insert, abawaca-build.cpp:482-490)
-		std::map<std::string, size_t> by_name;
-		for(size_t i = 0; i < recs.size(); i++)
-			by_name.insert(std::make_pair(recs[i].id, i));
-		const uint32_t nscaf = (uint32_t)by_name.size();
-		std::vector<const FastaRecord*> scafs;
-		std::vector<uint64_t> offsets(1, 0);
-		std::string ascii;
-		{
-			size_t total = 0;
-			for(auto& kv : by_name)
-				total += recs[kv.second].seq.size();
-			ascii.reserve(total);
-		}
-		std::map<std::string, uint32_t> scaf_index;
-		for(auto& kv : by_name) {
-			scaf_index[kv.first] = (uint32_t)scafs.size();
-			scafs.push_back(&recs[kv.second]);
-			ascii += recs[kv.second].seq;
-			offsets.push_back(ascii.size());
-		}
-
 		abw_ctx* ctx = nullptr;
 		if(abw_ctx_create(0, &ctx) != ABW_OK) {
 			std::cerr << "Error: no usable CUDA device (abawaca_b200 has no CPU path)" << std::endl;
 			return -1;
 		}
+		// the FASTA text goes to the device as it is: records are indexed there (abw_fasta_scan), the host only reads the names
+		std::string fasta_text;
+		{
+			FILE* fp = fopen(assembly_file.c_str(), "rb");
+			if(!fp)
+				throw std::runtime_error("Failed to open file " + assembly_file);
+			fseek(fp, 0, SEEK_END);
+			const long sz = ftell(fp);
+			rewind(fp);
+			fasta_text.resize((size_t)std::max<long>(sz, 0));
+			if(sz > 0 && fread(&fasta_text[0], 1, (size_t)sz, fp) != (size_t)sz)
+				throw std::runtime_error("Failed to read file " + assembly_file);
+			fclose(fp);
+		}
+		abw_fasta* fa = nullptr;
+		if(abw_fasta_scan(ctx, fasta_text.data(), fasta_text.size(), 0, &fa) != ABW_OK)
+			throw std::runtime_error(std::string(abw_last_error(ctx)) + " (" + assembly_file + ")");
+		const uint64_t nrec = abw_fasta_count(fa);
+		std::vector<uint64_t> id_off(nrec), rec_len(nrec);
+		std::vector<uint32_t> id_len(nrec);
+		ABWH_CHECK(ctx, abw_fasta_get(ctx, fa, id_off.data(), id_len.data(), rec_len.data()));
+		// scaffolds in name order; the first record of a name wins (std::map::insert, abawaca-build.cpp:482-490)
+		std::map<std::string, size_t> by_name;
+		for(size_t i = 0; i < nrec; i++) {
+			if(rec_len[i] == 0)
+				std::cerr << "Warning: sequence " << fasta_text.substr(id_off[i], id_len[i]) << " is empty" << std::endl;      // SeqIORead_fasta.h:99-101
+			by_name.insert(std::make_pair(fasta_text.substr(id_off[i], id_len[i]), i));
+		}
+		const uint32_t nscaf = (uint32_t)by_name.size();
+		std::vector<std::string> scaf_name;
+		std::vector<uint64_t> scaf_len;
+		std::vector<uint32_t> order;
+		for(auto& kv : by_name) {
+			scaf_name.push_back(kv.first);
+			scaf_len.push_back(rec_len[kv.second]);
+			order.push_back((uint32_t)kv.second);
+		}
 		abw_seqset* ss = nullptr;
-		int rc = abw_pack_sequences(ctx, ascii.data(), 0, offsets.data(), nscaf, &ss);
+		int rc = abw_fasta_pack(ctx, fa, order.data(), nscaf, &ss);
+		abw_fasta_destroy(fa);
+		std::string().swap(fasta_text);
 		if(rc != ABW_OK) {
 			std::cerr << "Fatal error, attempted to initialize DNAString with illegal string: " << abw_last_error(ctx) << std::endl;
 			return -1;
@@ -230,12 +247,12 @@ int main(int argc, const char* argv[])
 		fprintf(flrn, "\n");
 		uint64_t g = 0;
 		for(uint32_t s = 0; s < nscaf; s++) {
-			const std::string& id = scafs[s]->id;
-			const double len = (double)scafs[s]->seq.size();
+			const std::string& id = scaf_name[s];
+			const double len = (double)scaf_len[s];
 			const double cvg = (double)nbps[s] / len;
 			const double denom = len - (double)nN[s];
 			const double gc = (denom == 0)? 0 : (double)nGC[s] / denom;
-			fprintf(finfo, "%s\t%lu\t%.3lf\t%.3lf\t%lu\n", id.c_str(), (unsigned long)scafs[s]->seq.size(), int(1000.0 * cvg) / 1000.0, int(1000.0 * gc) / 1000.0,
+			fprintf(finfo, "%s\t%lu\t%.3lf\t%.3lf\t%lu\n", id.c_str(), (unsigned long)scaf_len[s], int(1000.0 * cvg) / 1000.0, int(1000.0 * gc) / 1000.0,
 			        (unsigned long)nN[s]);
 			unsigned long k = 0;
 			for(; g < ndps && seg_scaf[g] == s; g++) {

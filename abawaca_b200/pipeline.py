@@ -55,6 +55,32 @@ class SamParser:
             self.h = None
 
 
+def fasta_to_seqset(ctx, text):
+    """FASTA text (bytes) -> (seqset handle, names in scaffold order, lengths): records indexed on the device (abw_fasta_scan), the first record of
+    every name kept, scaffolds in byte-wise name order (abawaca-build.cpp:482-490), sequences packed by abw_fasta_pack."""
+    L = ctx.lib
+    arr = np.frombuffer(text, dtype=np.uint8)
+    f = C.c_void_p()
+    ctx.check(L.abw_fasta_scan(ctx.h, capi._p(arr) if arr.size else None, arr.size, 0, C.byref(f)))
+    try:
+        n = int(L.abw_fasta_count(f))
+        id_off = np.zeros(n, dtype=np.uint64)
+        id_len = np.zeros(n, dtype=np.uint32)
+        seq_len = np.zeros(n, dtype=np.uint64)
+        ctx.check(L.abw_fasta_get(ctx.h, f, capi._p(id_off), capi._p(id_len), capi._p(seq_len)))
+        first = {}
+        for i in range(n):
+            name = bytes(text[int(id_off[i]):int(id_off[i]) + int(id_len[i])])
+            first.setdefault(name, i)
+        names = sorted(first)
+        order = np.array([first[k] for k in names], dtype=np.uint32)
+        ss = C.c_void_p()
+        ctx.check(L.abw_fasta_pack(ctx.h, f, capi._p(order), order.size, C.byref(ss)))
+        return ss, [k.decode() for k in names], seq_len[order]
+    finally:
+        L.abw_fasta_destroy(f)
+
+
 class FeatureBuild:
     """Device-resident result of the feature stage; `rows_host()` fetches the .lrn matrix."""
 
@@ -124,7 +150,7 @@ class FeatureBuild:
 
 
 def build_features(ctx: capi.Context, seq, offsets, reads, this_sample=0, params=None, kind=capi.FEAT_TRUNC3, skip_A=True,
-                   seq_on_device=False, reads_on_device=False, nreads=None, timings=None, overlap_h2d=False) -> FeatureBuild:
+                   seq_on_device=False, reads_on_device=False, nreads=None, timings=None, overlap_h2d=False, seqset=None) -> FeatureBuild:
     """seq: uint8 ASCII (numpy array, or a device pointer int when seq_on_device); offsets: uint64 [nscaf+1];
     reads: one structured array (capi.READ_DTYPE) per sample (or device pointers + nreads)."""
     L = ctx.lib
@@ -158,10 +184,13 @@ def build_features(ctx: capi.Context, seq, offsets, reads, this_sample=0, params
         ctx.wait_h2d(t_seq)
         seq, reads = d_seq, dev_reads
         seq_on_device = reads_on_device = True
-    seqset = C.c_void_p()
-    if seq_on_device:
+    if seqset is not None:
+        pass                                               # packed elsewhere (fasta_to_seqset); offsets only carry the scaffold count
+    elif seq_on_device:
+        seqset = C.c_void_p()
         ctx.check(L.abw_pack_sequences(ctx.h, C.c_void_p(seq), 1, capi._p(offsets), nscaf, C.byref(seqset)))
     else:
+        seqset = C.c_void_p()
         seq = np.ascontiguousarray(seq, dtype=np.uint8)
         ctx.check(L.abw_pack_sequences(ctx.h, capi._p(seq), 0, capi._p(offsets), nscaf, C.byref(seqset)))
     lap("pack_ms")

@@ -126,6 +126,22 @@ void abw_names_destroy(abw_names* n);
  * lower-case 'n' in SEQ (ABW_ERR_ILLEGAL_DNA), fewer than 11 fields or a malformed MD:Z description (ABW_ERR_ARG). */
 int abw_parse_sam(abw_ctx* ctx, const abw_names* names, const char* text, uint64_t nbytes, int text_on_device, abw_read* d_reads, uint64_t cap, uint64_t* nreads);
 
+/* ---- FASTA text -> packed assembly on the device -----------------------------------------------------------------------
+ * Replaces SeqIORead_fasta<DNASequence>::next_seq (SeqIORead_fasta.h:51-103, with SeqIORead::getline(true), SeqIORead.h:85-121) for a whole
+ * file: lines are trimmed of white space on both ends, blank lines skipped, a line starting with '>' opens a record whose id is the text up
+ * to the first white space, every other line is appended to the open record (interior white space included).
+ * abw_fasta_scan indexes the text (kept on the device; a device text must stay alive until abw_fasta_destroy) and returns ABW_ERR_ARG where
+ * the reference throws Bad_file (sequence text before the first header, '>' followed by white space).  abw_fasta_get returns, per record in
+ * file order, where its id lies in the text and how long its sequence is; the host reads the names from its own copy of the text, decides
+ * the order (abawaca-build keeps the first record of every name, in name order: std::map::insert, abawaca-build.cpp:482-490) and
+ * abw_fasta_pack builds the abw_seqset of records h_order[0 .. nout) exactly as abw_pack_sequences would from the concatenated sequences. */
+typedef struct abw_fasta abw_fasta;
+int      abw_fasta_scan(abw_ctx* ctx, const char* text, uint64_t nbytes, int text_on_device, abw_fasta** out);
+void     abw_fasta_destroy(abw_fasta* f);
+uint64_t abw_fasta_count(const abw_fasta* f);
+int      abw_fasta_get(abw_ctx* ctx, const abw_fasta* f, uint64_t* h_id_off, uint32_t* h_id_len, uint64_t* h_seq_len);
+int      abw_fasta_pack(abw_ctx* ctx, const abw_fasta* f, const uint32_t* h_order, uint32_t nout, abw_seqset** out);
+
 /* device memory helpers so that hosts without a CUDA runtime binding can drive the ABI */
 int abw_device_alloc(abw_ctx* ctx, size_t bytes, void** d_out);
 int abw_device_free(abw_ctx* ctx, void* d_ptr);

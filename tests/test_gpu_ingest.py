@@ -178,3 +178,95 @@ def test_chunked_parsing_of_a_larger_file(ctx, tmp_path):
         assert n == src.size and np.array_equal(got[mapped], src[mapped])
     finally:
         sp.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# FASTA ingest (abw_fasta_scan / abw_fasta_pack)
+# ---------------------------------------------------------------------------------------------------
+def ref_read_fasta(text):
+    """[(id, sequence)] as SeqIORead_fasta<S>::next_seq (SeqIORead_fasta.h:51-103) with getline(true) (SeqIORead.h:85-121) reads the file"""
+    ws = " \t\n\v\f\r"
+    out = []
+    for line in text.split("\n"):
+        t = line.strip(ws)
+        if t == "":
+            continue
+        if t[0] == ">":
+            i = 1
+            while i < len(t) and t[i] not in ws:
+                i += 1
+            assert i > 1
+            out.append([t[1:i], ""])
+        else:
+            assert out
+            out[-1][1] += t
+    return [(a, b) for a, b in out]
+
+
+FASTA_EDGE = "\n".join([
+    "", "   ",
+    ">s2 some description here",
+    "ACGTACGTAC  ",
+    "  acgtNNNNacgt",
+    "",
+    ">s1\tdesc",
+    "AC GT\tAC",                    # interior white space is part of the sequence
+    "RYKM" * 10 + "\r",
+    "> s0",                          # never reached in the good file: see the error test
+])
+
+
+def _pack_and_compare(ctx, text):
+    from abawaca_b200 import pipeline
+    recs = ref_read_fasta(text)
+    first = {}
+    for i, (name, _) in enumerate(recs):
+        first.setdefault(name.encode(), i)
+    names = sorted(first)
+    seqs = [recs[first[k]][1] for k in names]
+    ss, got_names, lens = pipeline.fasta_to_seqset(ctx, text.encode())
+    assert got_names == [k.decode() for k in names]
+    assert lens.tolist() == [len(s) for s in seqs]
+    # the same windows, k-mer rows and per-scaffold statistics as packing the host-parsed sequences
+    seq = np.frombuffer("".join(seqs).encode(), dtype=np.uint8)
+    offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(s) for s in seqs])
+    a = pipeline.build_features(ctx, None, offsets, [], seqset=ss)
+    b = pipeline.build_features(ctx, seq, offsets, [])
+    assert np.array_equal(a.rows_host(), b.rows_host())
+    sa, sb = a.segments_host(), b.segments_host()
+    assert all(np.array_equal(sa[k], sb[k]) for k in sa)
+    lengths = np.diff(offsets.astype(np.int64))
+    ta, tb = a.scaffold_stats_host(lengths), b.scaffold_stats_host(lengths)
+    assert np.array_equal(ta["gc"], tb["gc"]) and np.array_equal(ta["Ns"], tb["Ns"])
+    a.close(); b.close()
+
+
+def test_fasta_edge_cases(ctx):
+    from abawaca_b200 import capi, pipeline
+    good = FASTA_EDGE.rsplit("\n", 1)[0]
+    for text in (good, good + "\n", good.replace("\n", "\r\n"), ">a\nACGT" * 1 + "\n>a\nTTTT\n>b\n" + "ACGT" * 700 + "\n"):
+        _pack_and_compare(ctx, text)
+    with pytest.raises(capi.AbwError, match="header line"):
+        pipeline.fasta_to_seqset(ctx, FASTA_EDGE.encode())            # '>' followed by white space
+    with pytest.raises(capi.AbwError, match="header line"):
+        pipeline.fasta_to_seqset(ctx, b"ACGT\n>a\nACGT\n")              # sequence text before the first header
+
+
+@pytest.mark.parametrize("name", ["tiny_clean", "tiny_noisy"])
+def test_fasta_text_of_the_golden_sets(ctx, tmp_path, name):
+    """the FASTA file the reference read -> the committed .lrn / .info (k-mer columns, GC, N counts) through the device-side reader"""
+    from abawaca_b200 import pipeline, synth
+    g = load_set(name)
+    mg = g["mg"]
+    paths = synth.write_reference_inputs(mg, str(tmp_path))
+    text = open(paths["fasta"], "rb").read()
+    ss, names, lens = pipeline.fasta_to_seqset(ctx, text)
+    assert names == mg.names and np.array_equal(lens.astype(np.int64), np.diff(mg.offsets.astype(np.int64)))
+    fb = pipeline.build_features(ctx, None, mg.offsets, mg.reads, this_sample=0, seqset=ss)
+    heads, vals = parse_lrn_text(g["lrn_text"])
+    assert np.array_equal(fb.rows_host(), vals)
+    st = fb.scaffold_stats_host(np.diff(mg.offsets.astype(np.int64)))
+    info = [l.split("\t") for l in g["info_text"].splitlines()]
+    assert ["%.3f" % v for v in st["gc"]] == [x[3] for x in info] and [int(x[4]) for x in info] == st["Ns"].tolist()
+    fb.close()

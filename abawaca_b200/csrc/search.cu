@@ -430,14 +430,18 @@ __device__ __forceinline__ unsigned long long cnt_pack(uint32_t nf, uint32_t nc,
 // Tiles of FP_TILE list entries, items (dimension, tile-table entry) handed out by ticket, running sums across tiles by look-back.
 constexpr int FP_ITEMS = 8;
 constexpr int FP_TILE = SW_THREADS * FP_ITEMS;
-__global__ void __launch_bounds__(SW_THREADS) k_flip_prefix(const uint32_t* __restrict__ flip_list, uint64_t Sf, const ClusterDesc* __restrict__ clusters, uint32_t FTT,
-                                                           const uint2* __restrict__ ftile_tab, const ScafRow* __restrict__ rows, const uint8_t* __restrict__ has_scg,
-                                                           unsigned long long* __restrict__ ticket, uint32_t* __restrict__ status, AggSlot* __restrict__ aggs,
-                                                           AggSlot* __restrict__ prefixes, uint2* __restrict__ F8, uint32_t* __restrict__ FC, uint32_t* __restrict__ scg_k,
-                                                           uint64_t Kstride, uint2* __restrict__ klohi, uint32_t C, unsigned long long scg_min_size,
-                                                           int* __restrict__ error_flag)
+// The per-scaffold records of a tile are staged in shared memory (coalesced list reads, the gathers of all eight entries of a thread in flight,
+// 16-byte slots swizzled so that both the strided stores and the blocked loads are conflict free) instead of living in registers across the
+// scan and the look-back: 40 registers instead of 128, six CTAs per SM instead of two.
+__global__ void __launch_bounds__(SW_THREADS, 4) k_flip_prefix(const uint32_t* __restrict__ flip_list, uint64_t Sf, const ClusterDesc* __restrict__ clusters, uint32_t FTT,
+                                                              const uint2* __restrict__ ftile_tab, const ScafRow* __restrict__ rows, const uint8_t* __restrict__ has_scg,
+                                                              unsigned long long* __restrict__ ticket, uint32_t* __restrict__ status, AggSlot* __restrict__ aggs,
+                                                              AggSlot* __restrict__ prefixes, uint2* __restrict__ F8, uint32_t* __restrict__ FC, uint32_t* __restrict__ scg_k,
+                                                              uint64_t Kstride, uint2* __restrict__ klohi, uint32_t C, unsigned long long scg_min_size,
+                                                              int* __restrict__ error_flag)
 {
-	__shared__ Agg sm_agg[SW_THREADS / 32 + 1];
+	__shared__ uint4 sm_r[FP_TILE];                        // {T (0: no entry), n | SCG flag << 31, length}
+	__shared__ Agg sm_agg[SW_THREADS / 32];
 	__shared__ unsigned long long sm_w;
 	__shared__ Agg sm_carry;
 	if(threadIdx.x == 0)
@@ -446,54 +450,93 @@ __global__ void __launch_bounds__(SW_THREADS) k_flip_prefix(const uint32_t* __re
 	const uint64_t w = sm_w;
 	const uint32_t d = (uint32_t)(w / FTT);
 	const uint2 te = __ldg(ftile_tab + (uint32_t)(w - (uint64_t)d * FTT));
-	const ClusterDesc cl = clusters[te.x];
 	const uint32_t tile = te.y;
-	const uint64_t base = (uint64_t)d * Sf + cl.fOff;
+	const uint32_t nf = clusters[te.x].nf, fOff = clusters[te.x].fOff;
+	const uint64_t base = (uint64_t)d * Sf + fOff;
 	const uint32_t* __restrict__ list = flip_list + base;
-	const uint32_t i0 = tile * FP_TILE + threadIdx.x * FP_ITEMS;
-	uint32_t sc[FP_ITEMS];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	{
+		uint32_t sc[FP_ITEMS];
 #pragma unroll
-	for(int j = 0; j < FP_ITEMS; j++)
-		sc[j] = (i0 + j < cl.nf)? (__ldg(list + i0 + j) & EL_SCAF_MASK) : 0xFFFFFFFFu;      // a partition pass may have left a flag bit on the entry
-	Agg x[FP_ITEMS];
+		for(int j = 0; j < FP_ITEMS; j++) {
+			const uint32_t idx = tile * FP_TILE + j * SW_THREADS + threadIdx.x;
+			sc[j] = (idx < nf)? (__ldg(list + idx) & EL_SCAF_MASK) : 0xFFFFFFFFu;      // a partition pass may have left a flag bit on the entry
+		}
+#pragma unroll
+		for(int j = 0; j < FP_ITEMS; j++) {
+			uint4 r = make_uint4(0, 0, 0, 0);
+			if(sc[j] != 0xFFFFFFFFu) {
+				r = __ldg(reinterpret_cast<const uint4*>(rows + sc[j]));
+				r.y |= (uint32_t)(has_scg[sc[j]] != 0) << 31;
+			}
+			const uint32_t e = j * SW_THREADS + threadIdx.x;
+			sm_r[e ^ ((e >> 3) & 7u)] = r;
+		}
+	}
+	__syncthreads();
+	const uint32_t e0 = threadIdx.x * FP_ITEMS, swz = threadIdx.x & 7u;     // this thread's eight consecutive entries
 	Agg tsum = agg_zero();
 #pragma unroll
 	for(int j = 0; j < FP_ITEMS; j++) {
-		x[j] = agg_zero();
-		if(sc[j] != 0xFFFFFFFFu) {
-			const uint4 r = __ldg(reinterpret_cast<const uint4*>(rows + sc[j]));   // {T, n, len}
-			x[j].a = r.x / 2 + 1;          // the flip element brings itself and the floor(T/2) earlier dps of the scaffold (...Specificity.cpp:41-57)
-			x[j].b = r.x;
-			x[j].c = r.y;
-			x[j].d = has_scg[sc[j]];
-			x[j].e = (unsigned long long)r.z | ((unsigned long long)r.w << 32);
+		const uint4 r = sm_r[e0 + ((uint32_t)j ^ swz)];
+		if(r.x) {
+			tsum.a += r.x / 2 + 1;         // the flip element brings itself and the floor(T/2) earlier dps of the scaffold (...Specificity.cpp:41-57)
+			tsum.b += r.x;
+			tsum.c += r.y & 0x7FFFFFFFu;
+			tsum.d += r.y >> 31;
+			tsum.e += (unsigned long long)r.z | ((unsigned long long)r.w << 32);
 		}
-		tsum = agg_add(tsum, x[j]);
 	}
-	Agg total;
-	Agg run = block_excl_scan_agg(tsum, total, sm_agg);
+	Agg incl = tsum;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) {
+		const Agg t = agg_shfl_up(incl, o);
+		if(lane >= o)
+			incl = agg_add(incl, t);
+	}
+	if(lane == 31)
+		sm_agg[warp] = incl;
+	__syncthreads();
+	Agg wex = agg_zero(), total = agg_zero();
+#pragma unroll
+	for(int w2 = 0; w2 < SW_THREADS / 32; w2++) {
+		const Agg t = sm_agg[w2];
+		if(w2 < warp)
+			wex = agg_add(wex, t);
+		total = agg_add(total, t);
+	}
 	if(threadIdx.x < 32) {
 		const Agg carry = agg_lookback(w, tile, total, status, aggs, prefixes, error_flag);
 		if(threadIdx.x == 0)
 			sm_carry = carry;
 	}
 	__syncthreads();
-	run = agg_add(run, sm_carry);
+	Agg run = agg_add(agg_add(sm_carry, wex), incl);
+	run.a -= tsum.a; run.b -= tsum.b; run.c -= tsum.c; run.d -= tsum.d; run.e -= tsum.e;
+	const uint32_t kOff = clusters[te.x].kOff;
+	const unsigned long long totLen = clusters[te.x].totLen;
+	const uint32_t i0 = tile * FP_TILE + e0;
 #pragma unroll
 	for(int j = 0; j < FP_ITEMS; j++) {
-		const unsigned long long e_before = run.e;
-		run = agg_add(run, x[j]);
-		if(sc[j] != 0xFFFFFFFFu) {
+		const uint4 r = sm_r[e0 + ((uint32_t)j ^ swz)];
+		if(r.x) {
+			const unsigned long long e_before = run.e;
+			run.a += r.x / 2 + 1;
+			run.b += r.x;
+			run.c += r.y & 0x7FFFFFFFu;
+			run.e += (unsigned long long)r.z | ((unsigned long long)r.w << 32);
 			const uint32_t k = i0 + j + 1;                  // flips passed once this one is
 			F8[base + i0 + j] = make_uint2(run.a, run.b);
 			if(FC != nullptr)
 				FC[base + i0 + j] = run.c;
-			if(x[j].d)
-				scg_k[(uint64_t)d * Kstride + cl.kOff + run.d - 1] = k;
+			if(r.y >> 31) {
+				run.d++;
+				scg_k[(uint64_t)d * Kstride + kOff + run.d - 1] = k;
+			}
 			// lengths are non-decreasing in k: exactly one flip crosses each limit
 			if(e_before < scg_min_size && run.e >= scg_min_size)
 				klohi[(uint64_t)d * C + te.x].x = k;
-			if(cl.totLen >= scg_min_size && e_before <= cl.totLen - scg_min_size && run.e > cl.totLen - scg_min_size)
+			if(totLen >= scg_min_size && e_before <= totLen - scg_min_size && run.e > totLen - scg_min_size)
 				klohi[(uint64_t)d * C + te.x].y = k - 1;
 		}
 	}

@@ -373,7 +373,7 @@ def main():
 
     # the sampler is started BEFORE the warm-up: nvidia-smi takes driver locks while it starts and would otherwise stall the first timed launches
     sampler = ClockSampler(local_rank)
-    if rank == 0:                                      # one nvidia-smi poller per job: every query takes driver locks that all ranks' launches wait on
+    if rank == 0 and not os.environ.get("ABW_NO_CLOCK_SAMPLER"):   # one nvidia-smi poller per job: every query takes driver locks that all ranks' launches wait on
         sampler.start()
     for _ in range(args.warmup):
         step(True)

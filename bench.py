@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "250"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -199,7 +199,7 @@ def gpu_bins_for(ctx, mg, pipeline, capi):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaffolds", type=int, default=0)
@@ -377,9 +377,13 @@ def main():
         sampler.start()
     for _ in range(args.warmup):
         step(True)
-    sampler.rows.clear()                               # keep only the samples taken during the timed region
+    n_warm_samples = len(sampler.rows)                 # samples before this index were taken during the warm-up (same load)
     ms_res, launches, steps_res = timed(True, args.steps)
+    timed_rows = sampler.rows[n_warm_samples:]
+    if len(timed_rows) >= 2:                           # enough samples inside the timed region itself; else keep the warm-up samples (same kernels, same load) as well
+        sampler.rows = timed_rows
     clocks = sampler.stop()
+    clocks["window"] = "timed region" if len(timed_rows) >= 2 else "warm-up + timed region"
     for _ in range(max(1, args.warmup)):               # warm the host-buffer path (staging buffers enter the context's block cache)
         step(False)
     ms_e2e, _, steps_e2e = timed(False, args.steps)

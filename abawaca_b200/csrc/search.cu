@@ -1361,6 +1361,115 @@ __global__ void k_pack_elements(const KeyT* __restrict__ keys, const uint32_t* _
 		flip_pos[(uint64_t)d * K + scg_index[s]] = (uint32_t)i;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// per-scaffold tables of a problem, built on the device from the caller's arrays (dp2scaf, T, len, scgmask)
+// ---------------------------------------------------------------------------------------------------
+constexpr int TB_ERR_RANGE = 1, TB_ERR_ORDER = 2, TB_ERR_COUNT = 4, TB_ERR_T = 8;
+struct RootStats {
+	unsigned long long totT, totLen;
+	uint32_t viol, Sf, partial, err;
+	unsigned long long never[SCG_WMAX];
+};
+
+// one thread per datapoint: dp2scaf must be non-decreasing, below S and without gaps; first[s] = first datapoint of scaffold s
+__global__ void k_tab_runs(const uint32_t* __restrict__ dp2scaf, uint64_t N, uint32_t S, uint64_t* __restrict__ first, RootStats* __restrict__ rs)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N)
+		return;
+	const uint32_t sc = dp2scaf[i];
+	int err = 0;
+	if(sc >= S)
+		err |= TB_ERR_RANGE;
+	else if(i == 0) {
+		if(sc != 0)
+			err |= TB_ERR_COUNT;                            // scaffold 0 has no datapoint
+		first[0] = 0;
+	}
+	else {
+		const uint32_t prev = dp2scaf[i - 1];
+		if(prev > sc)
+			err |= TB_ERR_ORDER;
+		else if(prev != sc) {
+			if(sc - prev > 1)
+				err |= TB_ERR_COUNT;                        // a scaffold in between has no datapoint
+			first[sc] = i;
+		}
+	}
+	if(i == N - 1) {
+		if(sc < S && sc != S - 1)
+			err |= TB_ERR_COUNT;
+		first[S] = N;
+	}
+	if(err)
+		atomicOr(&rs->err, (uint32_t)err);
+}
+
+// one thread per scaffold: {T, n, len} row, SCG flag, root statistics (warp-aggregated)
+__global__ void __launch_bounds__(256) k_tab_scaffolds(const uint64_t* __restrict__ first, const uint32_t* __restrict__ T, const uint64_t* __restrict__ len,
+                                                       const uint64_t* __restrict__ scgmask, uint32_t S, uint32_t W, double fraction_in, ScafRow* __restrict__ rows,
+                                                       uint8_t* __restrict__ has_scg, uint32_t* __restrict__ scg_flag, uint32_t* __restrict__ scaf_iota, RootStats* __restrict__ rs)
+{
+	const uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool active = sidx < S;
+	uint32_t t = 0, n = 0, err = 0;
+	unsigned long long l = 0;
+	bool any = false, flippable = false, viol = false, partial = false;
+	if(active) {
+		t = T[sidx];
+		l = len[sidx];
+		const uint64_t n64 = first[sidx + 1] - first[sidx];
+		n = (uint32_t)min(n64, (uint64_t)0xFFFFFFFFu);
+		if(t < 2)
+			err |= TB_ERR_T;
+		if(n == 0 || n > t)
+			err |= TB_ERR_COUNT;
+		for(uint32_t w = 0; w < W; w++)
+			any |= scgmask[(uint64_t)sidx * W + w] != 0;
+		flippable = n >= t / 2 + 1;
+		viol = !((double)n >= fraction_in * (double)t);
+		partial = n != t;
+		ScafRow r;
+		r.T = t; r.n = n; r.len = l;
+		rows[sidx] = r;
+		has_scg[sidx] = any;
+		scg_flag[sidx] = (any && flippable)? 1u : 0u;
+		scaf_iota[sidx] = sidx;
+		if(any && !flippable)                               // can never be assigned to side 1 of a sweep: always counted on side 2
+			for(uint32_t w = 0; w < W; w++)
+				atomicOr(&rs->never[w], (unsigned long long)scgmask[(uint64_t)sidx * W + w]);
+	}
+	unsigned long long st = t, sl = l;
+#pragma unroll
+	for(int o = 16; o > 0; o >>= 1) {
+		st += __shfl_xor_sync(0xffffffffu, st, o);
+		sl += __shfl_xor_sync(0xffffffffu, sl, o);
+	}
+	const uint32_t nv = __popc(__ballot_sync(0xffffffffu, active && viol)), nf = __popc(__ballot_sync(0xffffffffu, active && flippable)),
+	               np = __popc(__ballot_sync(0xffffffffu, active && partial));
+	err = __reduce_or_sync(0xffffffffu, err);
+	if((threadIdx.x & 31) == 0) {
+		atomicAdd(&rs->totT, st);
+		atomicAdd(&rs->totLen, sl);
+		if(nv) atomicAdd(&rs->viol, nv);
+		if(nf) atomicAdd(&rs->Sf, nf);
+		if(np) atomicAdd(&rs->partial, np);
+		if(err) atomicOr(&rs->err, err);
+	}
+}
+
+// SCG-carrying scaffolds that can flip, in scaffold order, and the index of each in that list
+__global__ void k_tab_scg(const uint32_t* __restrict__ scg_flag, const uint64_t* __restrict__ scg_before, uint32_t S, uint32_t* __restrict__ scg_index, uint32_t* __restrict__ scg_scafs)
+{
+	const uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(sidx >= S)
+		return;
+	const uint32_t k = (uint32_t)scg_before[sidx];
+	scg_index[sidx] = scg_flag[sidx]? k : 0u;
+	if(scg_flag[sidx])
+		scg_scafs[k] = sidx;
+}
+
 // flip list of every dimension: the scaffold ids of the class-1 elements in element order (stream compaction of E).
 // pass 1: class-1 elements per tile of SW_TILE; pass 2: a tile finds its offset by summing the counts of the tiles before it.
 __global__ void __launch_bounds__(256) k_flip_count(const uint32_t* __restrict__ E, uint64_t N, uint32_t tiles, uint32_t* __restrict__ counts)
@@ -1468,9 +1577,6 @@ struct abw_search {
 	DevBuf<uint8_t> assigned;
 	DevBuf<unsigned long long> xchg;          // per-level exchange buffer (side, new assignment, child statistics, ...), see search_run
 	DevBuf<uint32_t> low, scaf_member, scaf_final;
-	std::vector<uint32_t> h_T;
-	std::vector<uint64_t> h_len, h_mask;
-	std::vector<uint32_t> h_n;
 	uint64_t root_totT = 0, root_totLen = 0;
 	uint32_t root_viol = 0;
 	std::vector<uint64_t> root_never;
@@ -1522,73 +1628,70 @@ int upload(abw_ctx* ctx, DevBuf<T>& buf, const std::vector<T>& h)
 }
 
 int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_on_device, int layout, uint64_t ld, uint64_t nrows, const uint64_t* h_row_of_dp,
-                 const uint32_t* h_dp2scaf)
+                 const uint32_t* h_dp2scaf, const uint32_t* h_T, const uint64_t* h_len, const uint64_t* h_scgmask)
 {
 	const uint64_t N = s->N;
 	const uint32_t D = s->D, S = s->S, W = s->W;
 	Trace tr(ctx->stream, "create");
-	// ---- host-side per-scaffold tables
-	s->h_n.assign(S, 0);
-	std::vector<uint64_t> first((size_t)S + 1, 0);
-	for(uint64_t i = 0; i < N; i++) {
-		if(h_dp2scaf[i] >= S)
-			return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: dp2scaf entry out of range");
-		if(i > 0 && h_dp2scaf[i] < h_dp2scaf[i - 1])
-			return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: datapoints must be grouped by scaffold in scaffold order (ScafDpData.cpp:91-99)");
-		s->h_n[h_dp2scaf[i]]++;
-	}
-	std::vector<ScafRow> rows(S);
-	std::vector<uint8_t> has(S, 0);
-	std::vector<uint32_t> scg_scafs, scg_index(S, 0);
-	s->root_never.assign(W, 0);
-	s->root_totT = s->root_totLen = 0;
-	s->root_viol = 0;
-	for(uint32_t i = 0; i < S; i++) {
-		first[i + 1] = first[i] + s->h_n[i];
-		if(s->h_T[i] < 2)
-			return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: every scaffold needs T >= 2 datapoints (ScafDpData.cpp:92-93 drops the others)");
-		if(s->h_n[i] == 0 || s->h_n[i] > s->h_T[i])
-			return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: every scaffold needs between 1 and T datapoints in the matrix");
-		rows[i].T = s->h_T[i];
-		rows[i].n = s->h_n[i];
-		rows[i].len = s->h_len[i];
-		s->root_totT += s->h_T[i];
-		s->root_totLen += s->h_len[i];
-		bool any = false;
-		for(uint32_t w = 0; w < W; w++)
-			any |= s->h_mask[(size_t)i * W + w] != 0;
-		has[i] = any;
-		if(any) {
-			if(s->h_n[i] >= s->h_T[i] / 2 + 1) {
-				scg_index[i] = (uint32_t)scg_scafs.size();
-				scg_scafs.push_back(i);
-			}
-			else
-				for(uint32_t w = 0; w < W; w++)
-					s->root_never[w] |= s->h_mask[(size_t)i * W + w];
-		}
-		if(!((double)s->h_n[i] >= s->prm.fraction_dps_in * (double)s->h_T[i]))
-			s->root_viol++;
-		if(s->h_n[i] >= s->h_T[i] / 2 + 1)
-			s->Sf++;
-		if(s->h_n[i] != s->h_T[i])
-			s->partial = true;
-	}
-	if(s->root_totT >= (1ull << 31))
-		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: sum of T over scaffolds must be below 2^31");
-	s->K = (uint32_t)scg_scafs.size();
-	const uint64_t K = s->K;
-	tr.mark("host tables");
-	ABW_CHECK(upload(ctx, s->rows, rows));
-	ABW_CHECK(upload(ctx, s->has_scg, has));
-	ABW_CHECK(upload(ctx, s->dp_first, first));
-	ABW_CHECK(upload(ctx, s->scgmask, s->h_mask));
+	// ---- per-scaffold tables, built on the device from the caller's arrays
 	ABW_CUDA(ctx, s->dp2scaf.alloc(N));
 	ABW_CUDA(ctx, cudaMemcpyAsync(s->dp2scaf.p, h_dp2scaf, sizeof(uint32_t) * N, cudaMemcpyHostToDevice, ctx->stream));
-	DevBuf<uint32_t> d_scg_scafs, d_scg_index;
-	ABW_CHECK(upload(ctx, d_scg_scafs, scg_scafs));
-	ABW_CHECK(upload(ctx, d_scg_index, scg_index));
+	ABW_CUDA(ctx, s->scgmask.alloc((size_t)S * W));
+	if(h_scgmask)
+		ABW_CUDA(ctx, cudaMemcpyAsync(s->scgmask.p, h_scgmask, sizeof(uint64_t) * (size_t)S * W, cudaMemcpyHostToDevice, ctx->stream));
+	else
+		ABW_CUDA(ctx, cudaMemsetAsync(s->scgmask.p, 0, sizeof(uint64_t) * (size_t)S * W, ctx->stream));
+	DevBuf<uint32_t> d_T, d_scg_flag, d_scg_scafs, d_scg_index;
+	DevBuf<uint64_t> d_len, d_scg_before, d_total;
+	DevBuf<RootStats> d_rs;
+	ABW_CUDA(ctx, d_T.alloc(S));
+	ABW_CUDA(ctx, d_len.alloc(S));
+	ABW_CUDA(ctx, cudaMemcpyAsync(d_T.p, h_T, sizeof(uint32_t) * S, cudaMemcpyHostToDevice, ctx->stream));
+	ABW_CUDA(ctx, cudaMemcpyAsync(d_len.p, h_len, sizeof(uint64_t) * S, cudaMemcpyHostToDevice, ctx->stream));
 	tr.mark("uploads");
+	ABW_CUDA(ctx, d_rs.alloc(1));
+	ABW_CUDA(ctx, cudaMemsetAsync(d_rs.p, 0, sizeof(RootStats), ctx->stream));
+	ABW_CUDA(ctx, s->rows.alloc(S));
+	ABW_CUDA(ctx, s->has_scg.alloc(S));
+	ABW_CUDA(ctx, s->dp_first.alloc((size_t)S + 1));
+	ABW_CUDA(ctx, cudaMemsetAsync(s->dp_first.p, 0, sizeof(uint64_t) * ((size_t)S + 1), ctx->stream));
+	ABW_CUDA(ctx, d_scg_flag.alloc(S));
+	ABW_CUDA(ctx, d_scg_before.alloc(S));
+	ABW_CUDA(ctx, d_scg_index.alloc(S));
+	ABW_CUDA(ctx, d_total.alloc(1));
+	for(int b = 0; b < 2; b++)
+		ABW_CUDA(ctx, s->scaf_list[b].alloc(S));
+	ABW_LAUNCH(ctx, k_tab_runs, abw_div_up(N, 256), 256, 0, s->dp2scaf.p, N, S, s->dp_first.p, d_rs.p);
+	ABW_LAUNCH(ctx, k_tab_scaffolds, abw_div_up(S, 256), 256, 0, s->dp_first.p, d_T.p, d_len.p, s->scgmask.p, S, W, s->prm.fraction_dps_in, s->rows.p, s->has_scg.p,
+	           d_scg_flag.p, s->scaf_list[0].p, d_rs.p);
+	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, d_scg_flag.p, d_scg_before.p, S, d_total.p));
+	RootStats h_rs;
+	uint64_t h_K = 0;
+	ABW_CUDA(ctx, cudaMemcpyAsync(&h_rs, d_rs.p, sizeof(RootStats), cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaMemcpyAsync(&h_K, d_total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if(h_rs.err & TB_ERR_RANGE)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: dp2scaf entry out of range");
+	if(h_rs.err & TB_ERR_ORDER)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: datapoints must be grouped by scaffold in scaffold order (ScafDpData.cpp:91-99)");
+	if(h_rs.err & TB_ERR_T)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: every scaffold needs T >= 2 datapoints (ScafDpData.cpp:92-93 drops the others)");
+	if(h_rs.err & TB_ERR_COUNT)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: every scaffold needs between 1 and T datapoints in the matrix");
+	s->root_totT = h_rs.totT;
+	s->root_totLen = h_rs.totLen;
+	s->root_viol = h_rs.viol;
+	s->Sf = h_rs.Sf;
+	s->partial = h_rs.partial != 0;
+	s->root_never.assign(h_rs.never, h_rs.never + W);
+	if(s->root_totT >= (1ull << 31))
+		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: sum of T over scaffolds must be below 2^31");
+	s->K = (uint32_t)h_K;
+	const uint64_t K = s->K;
+	ABW_CUDA(ctx, d_scg_scafs.alloc(std::max<uint64_t>(K, 1)));
+	ABW_LAUNCH(ctx, k_tab_scg, abw_div_up(S, 256), 256, 0, d_scg_flag.p, d_scg_before.p, S, d_scg_index.p, d_scg_scafs.p);
+	tr.mark("tables on the device");
+
 	// ---- values, column major on the device (datapoint i lives in row row_of_dp[i] of the caller's matrix)
 	ABW_CUDA(ctx, s->values.alloc((size_t)D * N));
 	{
@@ -1629,7 +1732,6 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	for(int b = 0; b < 2; b++) {
 		ABW_CUDA(ctx, s->E[b].alloc((size_t)D * N));
 		ABW_CUDA(ctx, s->scg_list[b].alloc((size_t)D * K));
-		ABW_CUDA(ctx, s->scaf_list[b].alloc(S));
 	}
 	size_t free_b = 0, total_b = 0;
 	ABW_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
@@ -1709,14 +1811,7 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		ABW_CHECK(abw_radix_sort_pairs_u64(ctx, (uint64_t*)lk.p, (uint64_t*)lk_tmp.p, s->scg_list[0].p, lv_tmp.p, K, D, K, nbits));
 	}
 	tr.mark("SCG lists");
-	// ---- root cluster
-	{
-		std::vector<uint32_t> iota(S);
-		for(uint32_t i = 0; i < S; i++)
-			iota[i] = i;
-		ABW_CUDA(ctx, cudaMemcpyAsync(s->scaf_list[0].p, iota.data(), sizeof(uint32_t) * S, cudaMemcpyHostToDevice, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	}
+	// ---- root cluster (its scaffold list 0..S-1 was written by k_tab_scaffolds)
 	ABW_CUDA(ctx, s->assigned.alloc(S));
 	ABW_CUDA(ctx, s->low.alloc(S));
 	ABW_CUDA(ctx, s->scaf_member.alloc(S));
@@ -2324,14 +2419,9 @@ int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, 
 		s->prm = *params;
 	else
 		abw_default_params(&s->prm);
-	s->h_T.assign(h_T, h_T + S);
-	s->h_len.assign(h_len, h_len + S);
-	s->h_mask.assign((size_t)S * s->W, 0);
-	if(W > 0)
-		memcpy(s->h_mask.data(), h_scgmask, sizeof(uint64_t) * (size_t)S * W);
 	EventTimer tm(ctx->stream, ctx->profiling);
 	tm.start();
-	int rc = search_build(ctx, s, values, values_on_device, layout, ld, nrows, h_row_of_dp, h_dp2scaf);
+	int rc = search_build(ctx, s, values, values_on_device, layout, ld, nrows, h_row_of_dp, h_dp2scaf, h_T, h_len, (W > 0)? h_scgmask : nullptr);
 	s->prof.build_ms = tm.stop();
 	if(rc != ABW_OK) {
 		delete s;

@@ -1405,6 +1405,17 @@ __global__ void k_tab_runs(const uint32_t* __restrict__ dp2scaf, uint64_t N, uin
 		atomicOr(&rs->err, (uint32_t)err);
 }
 
+// dp2scaf of a matrix that holds every datapoint of every scaffold (n == T, the reference's own flow): datapoints [first[s], first[s+1]) belong to s
+__global__ void k_tab_fill_dp2scaf(const uint64_t* __restrict__ first, uint32_t S, uint64_t N, uint32_t* __restrict__ dp2scaf)
+{
+	const uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(sidx >= S)
+		return;
+	const uint64_t a = first[sidx], b = min(first[sidx + 1], N);
+	for(uint64_t i = a; i < b; i++)
+		dp2scaf[i] = sidx;
+}
+
 // one thread per scaffold: {T, n, len} row, SCG flag, root statistics (warp-aggregated)
 __global__ void __launch_bounds__(256) k_tab_scaffolds(const uint64_t* __restrict__ first, const uint32_t* __restrict__ T, const uint64_t* __restrict__ len,
                                                        const uint64_t* __restrict__ scgmask, uint32_t S, uint32_t W, double fraction_in, ScafRow* __restrict__ rows,
@@ -1635,7 +1646,8 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	Trace tr(ctx->stream, "create");
 	// ---- per-scaffold tables, built on the device from the caller's arrays
 	ABW_CUDA(ctx, s->dp2scaf.alloc(N));
-	ABW_CUDA(ctx, cudaMemcpyAsync(s->dp2scaf.p, h_dp2scaf, sizeof(uint32_t) * N, cudaMemcpyHostToDevice, ctx->stream));
+	if(h_dp2scaf)
+		ABW_CUDA(ctx, cudaMemcpyAsync(s->dp2scaf.p, h_dp2scaf, sizeof(uint32_t) * N, cudaMemcpyHostToDevice, ctx->stream));
 	ABW_CUDA(ctx, s->scgmask.alloc((size_t)S * W));
 	if(h_scgmask)
 		ABW_CUDA(ctx, cudaMemcpyAsync(s->scgmask.p, h_scgmask, sizeof(uint64_t) * (size_t)S * W, cudaMemcpyHostToDevice, ctx->stream));
@@ -1661,7 +1673,18 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	ABW_CUDA(ctx, d_total.alloc(1));
 	for(int b = 0; b < 2; b++)
 		ABW_CUDA(ctx, s->scaf_list[b].alloc(S));
-	ABW_LAUNCH(ctx, k_tab_runs, abw_div_up(N, 256), 256, 0, s->dp2scaf.p, N, S, s->dp_first.p, d_rs.p);
+	if(h_dp2scaf)
+		ABW_LAUNCH(ctx, k_tab_runs, abw_div_up(N, 256), 256, 0, s->dp2scaf.p, N, S, s->dp_first.p, d_rs.p);
+	else {
+		// no dp2scaf: the matrix holds all T datapoints of every scaffold, in scaffold order
+		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, d_T.p, s->dp_first.p, S, s->dp_first.p + S));
+		uint64_t sumT = 0;
+		ABW_CUDA(ctx, cudaMemcpyAsync(&sumT, s->dp_first.p + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		if(sumT != N)
+			return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: without dp2scaf the matrix must hold exactly sum(T) datapoints");
+		ABW_LAUNCH(ctx, k_tab_fill_dp2scaf, abw_div_up(S, 256), 256, 0, s->dp_first.p, S, N, s->dp2scaf.p);
+	}
 	ABW_LAUNCH(ctx, k_tab_scaffolds, abw_div_up(S, 256), 256, 0, s->dp_first.p, d_T.p, d_len.p, s->scgmask.p, S, W, s->prm.fraction_dps_in, s->rows.p, s->has_scg.p,
 	           d_scg_flag.p, s->scaf_list[0].p, d_rs.p);
 	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, d_scg_flag.p, d_scg_before.p, S, d_total.p));
@@ -2396,7 +2419,7 @@ int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, 
                       uint64_t N, uint32_t D, const uint32_t* h_dp2scaf, uint32_t S, const uint32_t* h_T, const uint64_t* h_len, const uint64_t* h_scgmask, uint32_t W,
                       const abw_params* params, int strategy, abw_search** out)
 {
-	if(!ctx || !out || !values || !h_dp2scaf || !h_T || !h_len || (W > 0 && !h_scgmask))
+	if(!ctx || !out || !values || !h_T || !h_len || (W > 0 && !h_scgmask))
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: null argument");
 	if(strategy != ABW_SENS_SPEC && strategy != ABW_SPLIT_SCAFS)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: unknown strategy");

@@ -277,7 +277,8 @@ def search(ctx: capi.Context, values, dp2scaf, T, length, scgmask, params=None, 
         N = row_of_dp.size
     else:
         N = nrows
-    dp2scaf = np.ascontiguousarray(dp2scaf, dtype=np.uint32)
+    if dp2scaf is not None:                            # None: the matrix holds all T datapoints of every scaffold, in scaffold order
+        dp2scaf = np.ascontiguousarray(dp2scaf, dtype=np.uint32)
     T = np.ascontiguousarray(T, dtype=np.uint32)
     length = np.ascontiguousarray(length, dtype=np.uint64)
     scgmask = np.ascontiguousarray(scgmask, dtype=np.uint64)

@@ -280,7 +280,11 @@ def main():
         seg_first = fb.seg_first_host()
         t_b = time.perf_counter()
         # ScafDpData.cpp:92-93: scaffolds with a single window are dropped
-        keep, dp2scaf, T, kept = pipeline.search_problem_from_counts(np.diff(seg_first.astype(np.int64)))
+        counts = np.diff(seg_first.astype(np.int64))
+        if world == 1:
+            keep, dp2scaf, T, kept = pipeline.search_problem_from_counts(counts)
+        else:                                          # the global tables are derived from all ranks' window counts further down
+            keep = np.repeat(counts >= 2, counts) if (counts < 2).any() else np.ones(int(counts.sum()), dtype=bool)
         if timings is not None:
             timings["segments_host_ms"] = 1000.0 * (t_b - t_a)
             timings["search_problem_ms"] = 1000.0 * (time.perf_counter() - t_b)
@@ -299,13 +303,12 @@ def main():
             # 1) windows per scaffold of every rank (the only per-scaffold quantity this step computed; lengths and SCG masks of all ranks were
             #    exchanged once at set-up): everybody derives the same global scaffold table, scaffold ids rank-major
             t_x0 = time.perf_counter()
-            cnt_local = torch.from_numpy(np.diff(seg_first.astype(np.int64)).astype(np.int32)).to(dev)
+            cnt_local = torch.from_numpy(counts.astype(np.int32)).to(dev)
             cnt_all = torch.empty(world * nscaf, dtype=torch.int32, device=dev)
             dist.all_gather_into_tensor(cnt_all, cnt_local)
             cnt_all = cnt_all.cpu().numpy()
             keep_all = cnt_all >= 2                                            # ScafDpData.cpp:92-93
             T_all = cnt_all[keep_all].astype(np.uint32)
-            dp2scaf_all = np.repeat(np.arange(T_all.size, dtype=np.uint32), T_all)
             rows_per_rank = [int(cnt_all[r * nscaf:(r + 1) * nscaf][keep_all[r * nscaf:(r + 1) * nscaf]].sum()) for r in range(world)]
             if timings is not None:
                 timings["exchange_tables_ms"] = 1000.0 * (time.perf_counter() - t_x0)
@@ -325,7 +328,7 @@ def main():
             if timings is not None:
                 timings["exchange_columns_ms"] = 1000.0 * (time.perf_counter() - t_x0)
             # 3) dimension-sharded search: this rank sweeps columns [off, off+cnt) of every datapoint
-            res = pipeline.search(ctx, full.data_ptr(), dp2scaf_all, T_all, lengths_all[keep_all], masks_all[keep_all],
+            res = pipeline.search(ctx, full.data_ptr(), None, T_all, lengths_all[keep_all], masks_all[keep_all],
                                   layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=int(full.shape[0]), D=cnt, ld=cnt, timings=timings,
                                   collectives=coll, dim_offset=off, D_total=fb.ncols)
             nbins = int(np.count_nonzero(np.unique(res.scaf2cluster)))

@@ -170,6 +170,7 @@ int abw_d2h_async(abw_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
  * ScafDpData.cpp:91-99, SCGdb.cpp:86-117): N datapoints x D dimensions, dp2scaf[N] (non-decreasing),
  * T[S] = scaf_db.ndps(scaf) (must be >= 2: ScafDpData drops scaffolds with one dp, quirk Q1),
  * len[S] = sequence length, scgmask[S][W] = bit set of SCG names per scaffold.
+ * h_dp2scaf may be NULL when the matrix holds all T datapoints of every scaffold in scaffold order (N = sum of T, the reference's own flow).
  * The value matrix has nrows rows; datapoint i is row h_row_of_dp[i] of it (NULL: nrows = N and datapoint i is row i).
  * This is how the rows of scaffolds with a single window, which abawaca-build writes but ScafDpData drops, are skipped
  * without copying the matrix.  The all-inclusive cluster 1 (init_cluster, abawaca.cpp:242-251) is the root. */

@@ -213,3 +213,17 @@ def test_row_index_skips_dropped_rows(ctx):
         res = pipeline.search(ctx, mat, prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"], layout=layout, row_of_dp=pos)
         assert res.scaf2cluster.tolist() == ref.scaf2cluster.tolist() and res.dp2cluster.tolist() == ref.dp2cluster.tolist()
         assert [(r.id, r.split, r.best.dim, r.best.value) for r in res.recs] == [(r.id, r.split, r.best.dim, r.best.value) for r in ref.recs]
+
+
+def test_search_without_dp2scaf(ctx):
+    """dp2scaf may be omitted when the matrix holds all T datapoints of every scaffold (the reference's own flow): the device derives it from T"""
+    from abawaca_b200 import pipeline
+    prob = search_problem("tiny_clean")
+    assert np.array_equal(np.bincount(prob["dp2scaf"]), prob["T"])
+    ref = pipeline.search(ctx, prob["values"], prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"])
+    res = pipeline.search(ctx, prob["values"], None, prob["T"], prob["len"], prob["scgmask"])
+    assert res.scaf2cluster.tolist() == ref.scaf2cluster.tolist() and res.dp2cluster.tolist() == ref.dp2cluster.tolist()
+    assert [(r.id, r.split, r.best.dim, r.best.value) for r in res.recs] == [(r.id, r.split, r.best.dim, r.best.value) for r in ref.recs]
+    from abawaca_b200 import capi
+    with pytest.raises(capi.AbwError, match="sum\\(T\\)"):
+        pipeline.search(ctx, prob["values"][:, :-1], None, prob["T"], prob["len"], prob["scgmask"])

@@ -55,10 +55,21 @@ class TorchCollectives:
         self.calls = 0
         self.bytes = 0
 
+        views = {}                                         # (pointer, bytes, dtype) -> tensor view: the search reuses the same device buffers level after level
+
+        def view(ptr, nbytes, typestr="|u1", itemsize=1):
+            key = (ptr, nbytes, typestr)
+            t = views.get(key)
+            if t is None:
+                if len(views) > 256:
+                    views.clear()
+                t = views[key] = torch.as_tensor(_DevArray(ptr, nbytes, typestr, itemsize), device=self.device)
+            return t
+
         def allgather(user, d_send, d_recv, nbytes):
             try:
-                send = torch.as_tensor(_DevArray(d_send, nbytes), device=self.device)
-                recv = torch.as_tensor(_DevArray(d_recv, nbytes * self.world), device=self.device)
+                send = view(d_send, nbytes)
+                recv = view(d_recv, nbytes * self.world)
                 dist.all_gather_into_tensor(recv, send)
                 torch.cuda.synchronize(self.device)
                 self.calls += 1
@@ -70,7 +81,7 @@ class TorchCollectives:
 
         def allreduce(user, d_buf, count):
             try:
-                t = torch.as_tensor(_DevArray(d_buf, count * 8, "<i8", 8), device=self.device)
+                t = view(d_buf, count * 8, "<i8", 8)
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)
                 torch.cuda.synchronize(self.device)
                 self.calls += 1
@@ -82,6 +93,30 @@ class TorchCollectives:
 
         self._ag, self._ar = capi.ALLGATHER_FN(allgather), capi.ALLREDUCE_FN(allreduce)
         self.struct = capi.Collectives(self._ag, self._ar, None, self.rank, self.world)
+
+
+class NcclCollectives:
+    """abw_collectives implemented inside libabawaca_b200.so on NCCL (abw_nccl_collectives_create): the operations are enqueued on the context
+    stream, nothing returns to the interpreter during a search.  torch.distributed only carries the 128-byte NCCL id to the other ranks."""
+
+    def __init__(self, ctx, device_index):
+        import torch
+        import torch.distributed as dist
+        self.ctx = ctx
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        idbuf = (C.c_ubyte * 128)()
+        if self.rank == 0:
+            ctx.check(ctx.lib.abw_nccl_unique_id(ctx.h, idbuf))
+        t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device=torch.device("cuda", device_index))
+        dist.broadcast(t, src=0)
+        idbytes = bytes(t.cpu().tolist())
+        self.struct = capi.Collectives()
+        ctx.check(ctx.lib.abw_nccl_collectives_create(ctx.h, idbytes, self.rank, self.world, C.byref(self.struct)))
+        self.calls = self.bytes = None                     # not counted: no callback into the interpreter
+
+    def close(self):
+        if self.struct.user:
+            self.ctx.lib.abw_nccl_collectives_destroy(C.byref(self.struct))
 
 
 def allgather_rows(torch, dist, local_rows, counts):

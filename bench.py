@@ -246,7 +246,10 @@ def main():
         raise SystemExit("bench.py assumes at most 64 SCG names")
     total_bp = int(mg.seq.size)
     nreads = [int(r.size) for r in mg.reads]
-    coll = distributed.TorchCollectives(local_rank) if world > 1 else None
+    coll = None
+    if world > 1:
+        # the per-level collectives of the sharded search: NCCL from inside the library; ABW_TORCH_COLLECTIVES=1 selects the torch.distributed callbacks instead
+        coll = distributed.TorchCollectives(local_rank) if os.environ.get("ABW_TORCH_COLLECTIVES") else distributed.NcclCollectives(ctx, local_rank)
     lengths_all = masks_all = None
     if world > 1:
         # static per-scaffold inputs of all ranks (sequence length, SCG mask), exchanged once: they are inputs, not results of a step
@@ -457,7 +460,7 @@ def main():
                                        f"dimension-sharded split search ({state['ncols']} dimensions over {world} ranks)") if world > 1 else "1 GPU",
                        "l2": "inputs (assembly + read records, > 2 GB) are larger than the 126 MB L2; no explicit flush",
                        "clusters_evaluated": state["nclusters"], "bins": bins_total, "search_levels": prof.levels, "datapoints": state["ndps"],
-                       "nccl": None if coll is None else {"callback_collectives_total": coll.calls, "callback_bytes_total": coll.bytes}},
+                       "nccl": None if coll is None else {"search_collectives": type(coll).__name__, "callback_collectives_total": coll.calls, "callback_bytes_total": coll.bytes}},
             "e2e": {"value": round(e2e_value, 2), "unit": "scaffolds/s", "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "step_ms": {"resident": steps_res, "e2e": steps_e2e}, "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "phase_wall_ms": {k: round(v, 3) for k, v in phase_ms.items()},
@@ -502,6 +505,8 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "scaffolds/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e!r}"}
     if rank == 0:
         print(json.dumps(line))
+    if coll is not None and hasattr(coll, "close"):
+        coll.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -226,6 +226,14 @@ int abw_search_set_shard(abw_search* s, uint32_t dim_offset, uint32_t D_total);
 int abw_search_run_sharded(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_cluster_rec* h_recs, uint32_t cap, uint32_t* nrecs,
                            uint32_t* h_dp2cluster, uint32_t* h_scaf2cluster);
 
+/* Native collectives: NCCL operations enqueued on the context stream (no host synchronisation).  libnccl.so.2 is resolved at run time
+ * (ABW_ERR_UNSUPPORTED if it cannot be found; set ABW_NCCL_LIB to its path).  Rank 0 obtains an id and hands its ABW_NCCL_ID_BYTES bytes to
+ * the other ranks by any means; every rank then creates its abw_collectives, on its own context. */
+#define ABW_NCCL_ID_BYTES 128
+int  abw_nccl_unique_id(abw_ctx* ctx, void* id128);
+int  abw_nccl_collectives_create(abw_ctx* ctx, const void* id128, int rank, int world, abw_collectives* out);
+void abw_nccl_collectives_destroy(abw_collectives* c);
+
 /* Stop after `max_levels` levels of the breadth-first search (0 = run to the end).  With 1 this is exactly one
  * ClusterSeparator::separate() call on the root: record 0 describes the split and dp2cluster/scaf2cluster hold the ids of
  * the two children (2 = cluster1, 3 = cluster2), which is what a per-cluster adapter needs. */

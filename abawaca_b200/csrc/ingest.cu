@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
+#include <vector>
 
 struct abw_names {
 	uint32_t nscaf = 0, nslots = 0;
@@ -350,6 +352,145 @@ __global__ void __launch_bounds__(256) k_fa_copy(const char* __restrict__ text, 
 	}
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// .lrn data lines -> keys and a row-major matrix of doubles (ClusterData::ClusterData, ClusterData.cpp:110-168: one line per datapoint,
+// "<key>\t<v1>\t...\t<vD>", values read with atof (:159); lines that are empty or start with '%' are skipped)
+// ---------------------------------------------------------------------------------------------------
+constexpr int LRN_ERR_FIELDS = 1;
+
+__device__ double g_pow10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+
+// atof of the field [p, e).  Decimal numbers whose digits form an integer below 2^53 and whose decimal exponent is within +-22 are converted with ONE
+// correctly rounded operation on two exactly representable doubles (the classic fast path of strtod), which is the correctly rounded result strtod
+// returns; everything else (more digits, large exponents, "inf", "nan", hexadecimal) is left to the host: *exact = false.
+__device__ __forceinline__ double dev_atof(const char* __restrict__ p, const char* __restrict__ e, bool* exact)
+{
+	*exact = true;
+	while(p < e && dev_isspace(*p))
+		p++;
+	bool neg = false;
+	if(p < e && (*p == '+' || *p == '-')) {
+		neg = *p == '-';
+		p++;
+	}
+	if(p < e && ((*p | 0x20) == 'i' || (*p | 0x20) == 'n')) {       // inf / nan
+		*exact = false;
+		return 0.0;
+	}
+	if(p + 1 < e && p[0] == '0' && (p[1] | 0x20) == 'x') {          // hexadecimal floating point
+		*exact = false;
+		return 0.0;
+	}
+	unsigned long long m = 0;
+	int ndig = 0, frac = 0, sig = 0;
+	bool any = false;
+	while(p < e && *p >= '0' && *p <= '9') {
+		if(sig > 0 || *p != '0') {
+			if(sig < 19) m = m * 10 + (unsigned long long)(*p - '0');
+			sig++;
+		}
+		any = true; ndig++; p++;
+	}
+	if(p < e && *p == '.') {
+		p++;
+		while(p < e && *p >= '0' && *p <= '9') {
+			if(sig > 0 || *p != '0') {
+				if(sig < 19) m = m * 10 + (unsigned long long)(*p - '0');
+				sig++;
+			}
+			frac++;
+			any = true; p++;
+		}
+	}
+	if(!any)
+		return 0.0;                                                // no conversion: atof returns 0
+	int ex = 0;
+	if(p < e && (*p | 0x20) == 'e') {
+		const char* q = p + 1;
+		bool eneg = false;
+		if(q < e && (*q == '+' || *q == '-')) {
+			eneg = *q == '-';
+			q++;
+		}
+		if(q < e && *q >= '0' && *q <= '9') {
+			int v = 0;
+			while(q < e && *q >= '0' && *q <= '9') {
+				if(v < 100000) v = v * 10 + (*q - '0');
+				q++;
+			}
+			ex = eneg? -v : v;
+		}
+	}
+	const int e10 = ex - frac;
+	if(m == 0)
+		return neg? -0.0 : 0.0;
+	if(sig > 19 || m >= (1ull << 53) || e10 < -22 || e10 > 22) {
+		*exact = false;
+		return 0.0;
+	}
+	const double md = (double)m;                                  // exact
+	const double r = (e10 >= 0)? __dmul_rn(md, g_pow10[e10]) : __ddiv_rn(md, g_pow10[-e10]);
+	return neg? -r : r;
+}
+
+// which lines are data lines: not empty after trimming trailing white space, not starting with '%'
+__global__ void k_lrn_is_row(const char* __restrict__ text, uint64_t nbytes, const uint64_t* __restrict__ line_start, uint64_t nlines, uint32_t* __restrict__ is_row)
+{
+	const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(l >= nlines)
+		return;
+	const uint64_t a = line_start[l];
+	uint64_t b = (l + 1 < nlines)? line_start[l + 1] : nbytes;
+	while(b > a && dev_isspace(text[b - 1]))
+		b--;
+	is_row[l] = (b > a && text[a] != '%')? 1u : 0u;
+}
+
+struct LrnFallback { uint64_t row; uint32_t col; uint32_t len; uint64_t off; };
+
+__global__ void __launch_bounds__(128) k_lrn_parse(const char* __restrict__ text, uint64_t nbytes, const uint64_t* __restrict__ line_start, uint64_t nlines,
+                                                   const uint32_t* __restrict__ is_row, const uint64_t* __restrict__ row_slot, uint32_t D, uint64_t cap,
+                                                   uint64_t* __restrict__ keys, double* __restrict__ values, LrnFallback* __restrict__ fb, uint32_t fb_cap,
+                                                   uint32_t* __restrict__ fb_count, int* __restrict__ err)
+{
+	const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(l >= nlines || !is_row[l])
+		return;
+	const uint64_t row = row_slot[l];
+	if(row >= cap)
+		return;
+	const char* p = text + line_start[l];
+	const char* e = text + ((l + 1 < nlines)? line_start[l + 1] : nbytes);
+	while(e > p && dev_isspace(e[-1]))
+		e--;
+	uint32_t field = 0;
+	const char* fs = p;
+	for(const char* q = p;; q++) {
+		if(q == e || *q == '\t') {
+			if(field == 0)
+				keys[row] = (uint64_t)(unsigned long)dev_atoi(fs, q);          // atoi of the key, ClusterData.cpp:151
+			else if(field <= D) {
+				bool exact;
+				const double v = dev_atof(fs, q, &exact);
+				values[row * D + (field - 1)] = v;
+				if(!exact) {
+					const uint32_t k = atomicAdd(fb_count, 1u);
+					if(k < fb_cap) {
+						fb[k].row = row; fb[k].col = field - 1; fb[k].len = (uint32_t)(q - fs); fb[k].off = (uint64_t)(fs - text);
+					}
+				}
+			}
+			field++;
+			fs = q + 1;
+			if(q == e)
+				break;
+		}
+	}
+	if(field != D + 1)
+		atomicOr(err, LRN_ERR_FIELDS);                       // "number of dimensions found is ...", ClusterData.cpp:137-141
+}
+
 }  // namespace
 
 extern "C" {
@@ -581,6 +722,86 @@ int abw_fasta_pack(abw_ctx* ctx, const abw_fasta* f, const uint32_t* h_order, ui
 	}
 	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // rec_dst is a local
 	return abw_pack_sequences(ctx, ascii.p, 1, offsets.data(), nout, out);
+}
+
+int abw_parse_lrn(abw_ctx* ctx, const char* text, uint64_t nbytes, int text_on_device, uint32_t D, uint64_t* d_keys, double* d_values, uint64_t cap_rows, uint64_t* nrows)
+{
+	if(!ctx || !nrows || (!text && nbytes) || D == 0 || ((!d_keys || !d_values) && cap_rows))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_parse_lrn: bad argument");
+	ABW_ENTER(ctx);
+	*nrows = 0;
+	if(nbytes == 0)
+		return ABW_OK;
+	DevBuf<char> d_text;
+	const char* src = text;
+	if(!text_on_device) {
+		ABW_CUDA(ctx, d_text.alloc(nbytes + 16));
+		ABW_CUDA(ctx, cudaMemcpyAsync(d_text.p, text, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+		src = d_text.p;
+	}
+	const unsigned int ntiles = abw_div_up(nbytes, LN_TILE);
+	DevBuf<uint32_t> tile_counts, is_row, fb_count;
+	DevBuf<uint64_t> tile_offs, total, line_start, row_slot;
+	DevBuf<LrnFallback> fb;
+	DevBuf<int> d_err;
+	const uint32_t fb_cap = 1u << 20;
+	ABW_CUDA(ctx, tile_counts.alloc(ntiles));
+	ABW_CUDA(ctx, tile_offs.alloc(ntiles));
+	ABW_CUDA(ctx, total.alloc(2));
+	ABW_CUDA(ctx, d_err.alloc(1));
+	ABW_CUDA(ctx, fb_count.alloc(1));
+	ABW_CUDA(ctx, fb.alloc(fb_cap));
+	ABW_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
+	ABW_CUDA(ctx, cudaMemsetAsync(fb_count.p, 0, sizeof(uint32_t), ctx->stream));
+	ABW_LAUNCH(ctx, k_sam_count_newlines, ntiles, LN_THREADS, 0, src, nbytes, tile_counts.p);
+	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, tile_counts.p, tile_offs.p, ntiles, total.p));
+	uint64_t nnl = 0;
+	ABW_CUDA(ctx, cudaMemcpyAsync(&nnl, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	const uint64_t nlines = nnl + 1;
+	ABW_CUDA(ctx, line_start.alloc(nlines));
+	ABW_CUDA(ctx, is_row.alloc(nlines));
+	ABW_CUDA(ctx, row_slot.alloc(nlines));
+	ABW_LAUNCH(ctx, k_sam_line_starts, ntiles, LN_THREADS, 0, src, nbytes, tile_offs.p, line_start.p);
+	ABW_LAUNCH(ctx, k_lrn_is_row, abw_div_up(nlines, 256), 256, 0, src, nbytes, line_start.p, nlines, is_row.p);
+	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, is_row.p, row_slot.p, nlines, total.p + 1));
+	uint64_t nr = 0;
+	ABW_CUDA(ctx, cudaMemcpyAsync(&nr, total.p + 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	*nrows = nr;
+	if(nr > cap_rows)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_parse_lrn: more data lines than the caller made room for (nrows holds the number found)");
+	if(nr == 0)
+		return ABW_OK;
+	ABW_LAUNCH(ctx, k_lrn_parse, abw_div_up(nlines, 128), 128, 0, src, nbytes, line_start.p, nlines, is_row.p, row_slot.p, D, cap_rows, d_keys, d_values, fb.p, fb_cap,
+	           fb_count.p, d_err.p);
+	int h_err = 0;
+	uint32_t h_fb = 0;
+	ABW_CUDA(ctx, cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaMemcpyAsync(&h_fb, fb_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if(h_err & LRN_ERR_FIELDS)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_parse_lrn: a data line does not have the expected number of tab-separated fields (ClusterData.cpp:137-141)");
+	if(h_fb > fb_cap)
+		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_parse_lrn: too many values outside the exact decimal fast path");
+	if(h_fb > 0) {
+		// values that need full strtod (more than 19 digits, exponents beyond +-22, inf/nan, hexadecimal): converted on the host with the C library, as atof does
+		std::vector<LrnFallback> h(h_fb);
+		ABW_CUDA(ctx, cudaMemcpyAsync(h.data(), fb.p, sizeof(LrnFallback) * h_fb, cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		std::vector<char> tmp;
+		for(const LrnFallback& f : h) {
+			tmp.assign((size_t)f.len + 1, 0);
+			if(text_on_device)
+				ABW_CUDA(ctx, cudaMemcpy(tmp.data(), src + f.off, f.len, cudaMemcpyDeviceToHost));
+			else
+				memcpy(tmp.data(), text + f.off, f.len);
+			const double v = atof(tmp.data());
+			ABW_CUDA(ctx, cudaMemcpyAsync(d_values + f.row * D + f.col, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+			ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		}
+	}
+	return ABW_OK;
 }
 
 }  // extern "C"

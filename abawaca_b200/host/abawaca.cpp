@@ -134,7 +134,7 @@ struct Model {
 	size_t D() const { return dim_names.size(); }
 };
 
-static void load_model(const Params& P, Model& M)
+static void load_model(const Params& P, Model& M, abw_ctx* ctx)
 {
 	// .info: scaffold -> coverage (ScafDpData.cpp:21-32)
 	std::map<std::string, double> name2cvg;
@@ -249,33 +249,46 @@ static void load_model(const Params& P, Model& M)
 		const size_t N = M.N(), D = ndims;
 		M.values.assign(D * N, 0.0);
 		std::vector<char> seen(N, 0);
-		size_t entry = 0;
-		while(next()) {
-			while(n > 0 && isspace((unsigned char)line[n - 1])) line[--n] = 0;
-			if(n == 0 || line[0] == '%')
-				continue;
-			if(entry >= ndps) { std::cerr << "Fatal error: number of datapoint lines found is higher than expected (" << ndps << "), file " << P.lrn_file << std::endl; exit(-1); }
-			size_t t = 1;
-			for(char* p = line; *p; p++) t += (*p == '\t');
-			if(t != D + 1) { std::cerr << "Fatal error: number of dimensions found is " << t << ", expected to find " << D << ": " << line << std::endl; exit(-1); }
-			char* p = strchr(line, '\t');
-			*p = 0;
-			auto it = dp_name2id.find((unsigned long)atoi(line));
-			if(it != dp_name2id.end()) {
-				const size_t dp = it->second - 1;
-				seen[dp] = 1;
-				for(size_t d = 0; d < D; d++) {
-					char* q = strchr(p + 1, '\t');
-					if(q) *q = 0;
-					M.values[d * N + dp] = atof(p + 1);      // ClusterData.cpp:159
-					p = q;
-				}
-			}
-			entry++;
+		// the datapoint lines are parsed on the device (abw_parse_lrn): keys and a row-major matrix come back
+		std::string body;
+		{
+			char buf[1 << 16];
+			size_t got;
+			while((got = fread(buf, 1, sizeof(buf), fp)) > 0)
+				body.append(buf, got);
 		}
 		free(line);
 		fclose(fp);
+		uint64_t cap_rows = 1;
+		for(char ch : body) cap_rows += (ch == '\n');
+		uint64_t* d_keys = nullptr;
+		double* d_vals = nullptr;
+		ABWH_CHECK(ctx, abw_device_alloc(ctx, cap_rows * sizeof(uint64_t), (void**)&d_keys));
+		ABWH_CHECK(ctx, abw_device_alloc(ctx, std::max<uint64_t>(cap_rows * D, 1) * sizeof(double), (void**)&d_vals));
+		uint64_t entry = 0;
+		if(abw_parse_lrn(ctx, body.data(), body.size(), 0, (uint32_t)D, d_keys, d_vals, cap_rows, &entry) != ABW_OK) {
+			std::cerr << "Fatal error: " << abw_last_error(ctx) << ", file " << P.lrn_file << std::endl;
+			exit(-1);
+		}
+		if(entry > ndps) { std::cerr << "Fatal error: number of datapoint lines found is higher than expected (" << ndps << "), file " << P.lrn_file << std::endl; exit(-1); }
 		if(entry != ndps) { std::cerr << "Fatal error: number of datapoint lines found (" << entry << ") is different than expected (" << ndps << "), file " << P.lrn_file << std::endl; exit(-1); }
+		std::vector<uint64_t> keys(entry);
+		std::vector<double> rows_rm(entry * D);
+		if(entry) {
+			ABWH_CHECK(ctx, abw_copy_to_host(ctx, keys.data(), d_keys, entry * sizeof(uint64_t)));
+			ABWH_CHECK(ctx, abw_copy_to_host(ctx, rows_rm.data(), d_vals, entry * D * sizeof(double)));
+		}
+		ABWH_CHECK(ctx, abw_device_free(ctx, d_keys));
+		ABWH_CHECK(ctx, abw_device_free(ctx, d_vals));
+		for(uint64_t r = 0; r < entry; r++) {
+			auto it = dp_name2id.find((unsigned long)keys[r]);
+			if(it != dp_name2id.end()) {
+				const size_t dp = it->second - 1;
+				seen[dp] = 1;
+				for(size_t d = 0; d < D; d++)
+					M.values[d * N + dp] = rows_rm[r * D + d];
+			}
+		}
 		for(size_t i = 0; i < N; i++)
 			if(!seen[i])
 				throw std::invalid_argument("datapoint " + std::to_string(M.dp_name[i]) + " of " + P.names_file + " has no row in " + P.lrn_file);
@@ -362,16 +375,16 @@ int main(int argc, const char** argv)
 	log << '[' << get_time() << ']' << " Starting" << std::endl;
 	log << '[' << get_time() << ']' << " Creatinf databases based on " << P.names_file << " and " << P.lrn_file << std::endl;
 	try {
-		Model M;
-		load_model(P, M);
-		const size_t N = M.N(), S = M.S(), D = M.D();
-		summary << "Cluster\t# scafs\t# dps\t# bps\t%G+C\tStdev\tCvg\tstdev\t#SCG" << '/' << M.total_num_scgs << "\tAvg" << std::endl;
-
 		abw_ctx* ctx = nullptr;
 		if(abw_ctx_create(0, &ctx) != ABW_OK) {
 			std::cerr << "Error: no usable CUDA device (abawaca_b200 has no CPU path)" << std::endl;
 			return -1;
 		}
+		Model M;
+		load_model(P, M, ctx);
+		const size_t N = M.N(), S = M.S(), D = M.D();
+		summary << "Cluster\t# scafs\t# dps\t# bps\t%G+C\tStdev\tCvg\tstdev\t#SCG" << '/' << M.total_num_scgs << "\tAvg" << std::endl;
+
 		abw_params prm;
 		abw_default_params(&prm);
 		prm.min_reported_score = 0;                 // also report the best separation of terminal clusters, as the reference's log does

@@ -55,6 +55,26 @@ class SamParser:
             self.h = None
 
 
+def parse_lrn_rows(ctx, text, D):
+    """data lines of a .lrn file (bytes, after the four header lines) -> (keys uint64 [n], device pointer of the row-major [n][D] matrix, n).
+    The caller frees the matrix with ctx.free()."""
+    arr = np.frombuffer(text, dtype=np.uint8)
+    cap = int(np.count_nonzero(arr == 10)) + 1
+    d_keys = ctx.alloc(cap * 8)
+    d_vals = ctx.alloc(max(cap * D, 1) * 8)
+    n = C.c_uint64()
+    try:
+        ctx.check(ctx.lib.abw_parse_lrn(ctx.h, capi._p(arr) if arr.size else None, arr.size, 0, D, C.c_void_p(d_keys), C.c_void_p(d_vals), cap, C.byref(n)))
+    except Exception:
+        ctx.free(d_keys); ctx.free(d_vals)
+        raise
+    keys = np.zeros(int(n.value), dtype=np.uint64)
+    if keys.size:
+        ctx.to_host(keys, d_keys)
+    ctx.free(d_keys)
+    return keys, d_vals, int(n.value)
+
+
 def fasta_to_seqset(ctx, text):
     """FASTA text (bytes) -> (seqset handle, names in scaffold order, lengths): records indexed on the device (abw_fasta_scan), the first record of
     every name kept, scaffolds in byte-wise name order (abawaca-build.cpp:482-490), sequences packed by abw_fasta_pack."""

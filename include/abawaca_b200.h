@@ -142,6 +142,14 @@ uint64_t abw_fasta_count(const abw_fasta* f);
 int      abw_fasta_get(abw_ctx* ctx, const abw_fasta* f, uint64_t* h_id_off, uint32_t* h_id_len, uint64_t* h_seq_len);
 int      abw_fasta_pack(abw_ctx* ctx, const abw_fasta* f, const uint32_t* h_order, uint32_t nout, abw_seqset** out);
 
+/* ---- .lrn data lines -> matrix on the device ---------------------------------------------------------------------------------
+ * Replaces the datapoint loop of ClusterData::ClusterData (ClusterData.cpp:110-168) for the text after the four header lines: every line that is
+ * not empty and does not start with '%' is "<key>\t<v1>\t...\t<vD>"; keys are read with atoi, values with atof (:151,159).  Row r of the
+ * file goes to d_keys[r] and d_values[r*D .. r*D+D) (device memory, room for cap_rows rows); *nrows = rows found.  The matrix can be handed to
+ * abw_search_create as it is (ABW_LAYOUT_ROWMAJOR, values_on_device, h_row_of_dp built from the keys).  Decimal values take the exact
+ * one-operation conversion on the device; the rare others (more than 19 digits, exponents beyond +-22, inf/nan) are converted with the host's atof. */
+int abw_parse_lrn(abw_ctx* ctx, const char* text, uint64_t nbytes, int text_on_device, uint32_t D, uint64_t* d_keys, double* d_values, uint64_t cap_rows, uint64_t* nrows);
+
 /* device memory helpers so that hosts without a CUDA runtime binding can drive the ABI */
 int abw_device_alloc(abw_ctx* ctx, size_t bytes, void** d_out);
 int abw_device_free(abw_ctx* ctx, void* d_ptr);

@@ -270,3 +270,57 @@ def test_fasta_text_of_the_golden_sets(ctx, tmp_path, name):
     info = [l.split("\t") for l in g["info_text"].splitlines()]
     assert ["%.3f" % v for v in st["gc"]] == [x[3] for x in info] and [int(x[4]) for x in info] == st["Ns"].tolist()
     fb.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# .lrn data lines (abw_parse_lrn)
+# ---------------------------------------------------------------------------------------------------
+def test_lrn_values_equal_atof(ctx):
+    """every value must be the double the C library's strtod gives (atof, ClusterData.cpp:159): device fast path and host fallback"""
+    from abawaca_b200 import capi, pipeline
+    rng = np.random.default_rng(5)
+    special = ["0", "-0", "0.000", "1", "-1.5", "0.001", "123456789.123", "1e5", "1E-5", "2.5e+3", ".5", "5.", "+7.25", "9007199254740991", "9007199254740993",
+               "0.1234567890123456789", "1e22", "1e23", "1e-22", "1e-23", "1e400", "-1e-400", "inf", "-inf", "nan", "0x1p-3", "12abc", "abc", "", " 3.5", "4.25e", "1.7976931348623157e308",
+               "4.9e-324", "0.30000000000000004", "179769313486231570000000000000000000000", "-2147483.648", "65.432"]
+    D = 7
+    rows = []
+    vals = special + ["%.3f" % x for x in rng.uniform(0, 70, 400)] + [repr(float(x)) for x in rng.normal(0, 1e3, 200)] + ["%.17g" % x for x in rng.uniform(-1, 1, 100)]
+    while len(vals) % D:
+        vals.append("0.5")
+    for i in range(0, len(vals), D):
+        rows.append(vals[i:i + D])
+    text = "% a comment line\n\n" + "".join("%d\t%s\n" % (10 * r + 3, "\t".join(row)) for r, row in enumerate(rows)) + "%\n"
+    keys, d_vals, n = pipeline.parse_lrn_rows(ctx, text.encode(), D)
+    got = np.zeros((n, D), dtype=np.float64)
+    ctx.to_host(got, d_vals)
+    ctx.free(d_vals)
+    assert n == len(rows) and keys.tolist() == [10 * r + 3 for r in range(len(rows))]
+    import ctypes
+    libc = ctypes.CDLL(None)
+    libc.atof.restype = ctypes.c_double
+    exp = np.array([[libc.atof(v.encode()) for v in row] for row in rows])
+    assert np.array_equal(got.view(np.uint64), exp.view(np.uint64)), [(v, g, e) for v, g, e in zip(sum(rows, []), got.ravel(), exp.ravel()) if np.float64(g).view(np.uint64) != np.float64(e).view(np.uint64)][:10]
+    with pytest.raises(capi.AbwError, match="number of tab-separated fields"):
+        pipeline.parse_lrn_rows(ctx, b"1\t0.5\t0.25\n2\t0.5\n", 2)
+
+
+@pytest.mark.parametrize("name", ["tiny_clean", "tiny_noisy"])
+def test_lrn_text_of_the_golden_sets(ctx, name):
+    """the .lrn file written by the unmodified reference abawaca-build -> the matrix, handed to the split search without leaving the device"""
+    from abawaca_b200 import capi, pipeline
+    from golden_util import search_problem
+    g = load_set(name)
+    lines = g["lrn_text"].split("\n")
+    heads, vals = parse_lrn_text(g["lrn_text"])
+    D = vals.shape[1]
+    body = "\n".join(lines[4:]).encode()
+    keys, d_vals, n = pipeline.parse_lrn_rows(ctx, body, D)
+    got = np.zeros((n, D), dtype=np.float64)
+    ctx.to_host(got, d_vals)
+    assert n == vals.shape[0] and np.array_equal(got, vals) and keys.tolist() == list(range(1, n + 1))
+    prob = search_problem(name)
+    ref = pipeline.search(ctx, prob["values"], prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"])
+    if prob["values"].shape[1] == n:                     # (rows of scaffolds with a single window would need row_of_dp: none in these sets)
+        res = pipeline.search(ctx, d_vals, prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"], layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=n, D=D, ld=D)
+        assert res.scaf2cluster.tolist() == ref.scaf2cluster.tolist() and [(r.id, r.split, r.best.dim, r.best.value) for r in res.recs] == [(r.id, r.split, r.best.dim, r.best.value) for r in ref.recs]
+    ctx.free(d_vals)

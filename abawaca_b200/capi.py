@@ -41,7 +41,8 @@ class ClusterRec(C.Structure):
     _fields_ = [("id", C.c_uint32), ("parent", C.c_uint32), ("ndps", C.c_uint64), ("nscafs", C.c_uint32), ("split", C.c_int32),
                 ("best", Best), ("child1", C.c_uint32), ("child2", C.c_uint32), ("child1_ndps", C.c_uint64), ("child2_ndps", C.c_uint64),
                 ("child1_nscafs", C.c_uint32), ("child2_nscafs", C.c_uint32), ("child1_raw", C.c_uint64), ("child2_raw", C.c_uint64),
-                ("total_size", C.c_uint64), ("scg_unique", C.c_uint32), ("scg_avg", C.c_double)]
+                ("total_size", C.c_uint64), ("scg_unique", C.c_uint32), ("scg_avg", C.c_double),
+                ("gc_avg", C.c_double), ("gc_sd", C.c_double), ("cvg_avg", C.c_double), ("cvg_sd", C.c_double)]
 
 
 class SearchProfile(C.Structure):
@@ -63,7 +64,7 @@ EXPORTS = [
     "abw_segments_count", "abw_segments_get", "abw_kmer_features", "abw_coverage", "abw_device_alloc", "abw_device_free",
     "abw_copy_to_device", "abw_copy_to_host", "abw_memset_device", "abw_h2d_async", "abw_wait_h2d", "abw_d2h_async", "abw_search_create", "abw_search_destroy", "abw_search_run",
     "abw_search_set_shard", "abw_search_set_max_levels", "abw_search_run_sharded", "abw_search_get_profile", "abw_cluster_scg",
-    "abw_names_create", "abw_names_destroy", "abw_parse_sam", "abw_fasta_scan", "abw_fasta_destroy", "abw_fasta_count", "abw_fasta_get", "abw_fasta_pack", "abw_nccl_unique_id", "abw_nccl_collectives_create", "abw_nccl_collectives_destroy", "abw_parse_lrn",
+    "abw_names_create", "abw_names_destroy", "abw_parse_sam", "abw_fasta_scan", "abw_fasta_destroy", "abw_fasta_count", "abw_fasta_get", "abw_fasta_pack", "abw_nccl_unique_id", "abw_nccl_collectives_create", "abw_nccl_collectives_destroy", "abw_parse_lrn", "abw_search_set_scaffold_stats",
 ]
 
 
@@ -126,6 +127,7 @@ def load():
     L.abw_nccl_collectives_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.abw_nccl_collectives_destroy.argtypes = [C.c_void_p]
     L.abw_parse_lrn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.abw_search_set_scaffold_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.abw_cluster_scg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
     _LIB = L
     return L

@@ -1228,6 +1228,48 @@ __global__ void k_finalize_terminal(const uint32_t* __restrict__ scaf_list, cons
 	}
 }
 
+// Summary statistics of a terminal bin (ClusterQuality::gc / cvg with standard_deviation, ClusterQuality.cpp:6-27,51-75): over the ASSIGNED scaffolds of
+// the bin in scaffold-id order (std::set iteration), mean = sum(len * x) / sum(len), stdev = sqrt(sum(len * (x - mean) * (x - mean)) / (sum(len) - 1)),
+// evaluated with exactly those fp64 operations in that order; (-1, -1) for a bin without assigned scaffolds.  The scaffold list of a cluster stays in
+// ascending id order through the stable partitions, so one thread walks its bin.  out[job][2 * which + {0, 1}] = mean, stdev (which: 0 gc, 1 coverage).
+__global__ void k_terminal_moments(const uint32_t* __restrict__ scaf_list, const TermJob* __restrict__ jobs, uint32_t njobs, const ScafRow* __restrict__ rows,
+                                   const uint8_t* __restrict__ assigned, const double* __restrict__ x_gc, const double* __restrict__ x_cvg, double* __restrict__ out)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if(t >= njobs * 2)
+		return;
+	const TermJob jb = jobs[t >> 1];
+	const double* __restrict__ x = (t & 1)? x_cvg : x_gc;
+	unsigned long long total = 0;
+	uint32_t count = 0;
+	double mean = 0.0;
+	for(uint32_t i = 0; i < jb.ns; i++) {
+		const uint32_t sc = scaf_list[jb.sOff + i] & EL_SCAF_MASK;
+		if(assigned[sc]) {
+			const unsigned long long l = rows[sc].len;
+			mean = __dadd_rn(mean, __dmul_rn(__ull2double_rn(l), x[sc]));
+			total += l;
+			count++;
+		}
+	}
+	double sd = 0.0;
+	if(count == 0)
+		mean = sd = -1.0;
+	else {
+		mean = __ddiv_rn(mean, __ull2double_rn(total));
+		for(uint32_t i = 0; i < jb.ns; i++) {
+			const uint32_t sc = scaf_list[jb.sOff + i] & EL_SCAF_MASK;
+			if(assigned[sc]) {
+				const double dlt = __dsub_rn(x[sc], mean);
+				sd = __dadd_rn(sd, __dmul_rn(__dmul_rn(__ull2double_rn(rows[sc].len), dlt), dlt));
+			}
+		}
+		sd = __dsqrt_rn(__ddiv_rn(sd, __ull2double_rn(total - 1ull)));
+	}
+	out[(size_t)(t >> 1) * 4 + (t & 1) * 2] = mean;
+	out[(size_t)(t >> 1) * 4 + (t & 1) * 2 + 1] = sd;
+}
+
 __global__ void k_commit_assigned(const uint32_t* __restrict__ scaf_list, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs,
                                   const uint8_t* __restrict__ new_assigned, uint8_t* __restrict__ assigned)
 {
@@ -1586,6 +1628,7 @@ struct abw_search {
 	bool partial = false;
 	uint64_t Sf = 0;                          // scaffolds with n >= T/2+1
 	DevBuf<uint8_t> assigned;
+	DevBuf<double> x_gc, x_cvg;               // optional per-scaffold G+C and coverage for the terminal-bin statistics (abw_search_set_scaffold_stats)
 	DevBuf<unsigned long long> xchg;          // per-level exchange buffer (side, new assignment, child statistics, ...), see search_run
 	DevBuf<uint32_t> low, scaf_member, scaf_final;
 	uint64_t root_totT = 0, root_totLen = 0;
@@ -1976,6 +2019,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 	DevBuf<PartJob> d_pjobs;
 	DevBuf<TermJob> d_tjobs;
 	DevBuf<TermStats> d_tstats;
+	DevBuf<double> d_moments;
 	if(s->strategy == ABW_SENS_SPEC)
 		ABW_CUDA(ctx, d_suffix.alloc((size_t)D * std::max<uint32_t>(s->K, 1) * W));
 
@@ -2287,6 +2331,12 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 			           d_tstats.p, d_union.p);
 			std::vector<TermStats> ts(Tn);
 			std::vector<uint64_t> un((size_t)Tn * W);
+			std::vector<double> mom((size_t)Tn * 4, -1.0);
+			if(s->x_gc.p != nullptr) {
+				if(d_moments.n < (size_t)Tn * 4) ABW_CUDA(ctx, d_moments.alloc((size_t)Tn * 4));
+				ABW_LAUNCH(ctx, k_terminal_moments, abw_div_up(2 * Tn, 64), 64, 0, s->scaf_list[cur].p, d_tjobs.p, Tn, s->rows.p, s->assigned.p, s->x_gc.p, s->x_cvg.p, d_moments.p);
+				ABW_CUDA(ctx, cudaMemcpyAsync(mom.data(), d_moments.p, sizeof(double) * Tn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+			}
 			ABW_CUDA(ctx, cudaMemcpyAsync(ts.data(), d_tstats.p, sizeof(TermStats) * Tn, cudaMemcpyDeviceToHost, ctx->stream));
 			ABW_CUDA(ctx, cudaMemcpyAsync(un.data(), d_union.p, sizeof(uint64_t) * Tn * W, cudaMemcpyDeviceToHost, ctx->stream));
 			ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2300,6 +2350,8 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 				recs[c].total_size = ts[t].total_size;
 				recs[c].scg_unique = u;
 				recs[c].scg_avg = (ts[t].scg_copies == 0)? 0 : (double)ts[t].scg_copies / (double)u;   // SCGdb.cpp:54
+				recs[c].gc_avg = mom[(size_t)t * 4]; recs[c].gc_sd = mom[(size_t)t * 4 + 1];
+				recs[c].cvg_avg = mom[(size_t)t * 4 + 2]; recs[c].cvg_sd = mom[(size_t)t * 4 + 3];
 				t++;
 			}
 		}
@@ -2462,6 +2514,19 @@ int abw_search_run(abw_ctx* ctx, abw_search* s, abw_cluster_rec* h_recs, uint32_
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_run: null argument");
 	ABW_ENTER(ctx);
 	return search_run(ctx, s, nullptr, h_recs, cap, nrecs, h_dp2cluster, h_scaf2cluster);
+}
+
+int abw_search_set_scaffold_stats(abw_ctx* ctx, abw_search* s, const double* h_gc, const double* h_cvg)
+{
+	if(!ctx || !s || !h_gc || !h_cvg)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_set_scaffold_stats: null argument");
+	ABW_ENTER(ctx);
+	ABW_CUDA(ctx, s->x_gc.alloc(s->S));
+	ABW_CUDA(ctx, s->x_cvg.alloc(s->S));
+	ABW_CUDA(ctx, cudaMemcpyAsync(s->x_gc.p, h_gc, sizeof(double) * s->S, cudaMemcpyHostToDevice, ctx->stream));
+	ABW_CUDA(ctx, cudaMemcpyAsync(s->x_cvg.p, h_cvg, sizeof(double) * s->S, cudaMemcpyHostToDevice, ctx->stream));
+	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return ABW_OK;
 }
 
 int abw_search_set_max_levels(abw_search* s, uint32_t max_levels)

@@ -394,6 +394,7 @@ int main(int argc, const char** argv)
 		std::vector<abw_cluster_rec> recs(2 * N / std::max<uint32_t>(prm.cluster_ndps_threshold, 1) + 64);
 		std::vector<uint32_t> dp2cluster(N), scaf2cluster(S);
 		uint32_t nrec = 0;
+		ABWH_CHECK(ctx, abw_search_set_scaffold_stats(ctx, search, M.scaf_gc.data(), M.scaf_cvg.data()));
 		ABWH_CHECK(ctx, abw_search_run(ctx, search, recs.data(), (uint32_t)recs.size(), &nrec, dp2cluster.data(), scaf2cluster.data()));
 		recs.resize(std::min<size_t>(nrec, recs.size()));
 		abw_search_destroy(search);
@@ -486,7 +487,8 @@ int main(int argc, const char** argv)
 				}
 				double nunique, avg_copies, avg_gc, sd_gc, avg_cvg = -1, sd_cvg = -1;
 				scg_of(assigned, nunique, avg_copies);
-				gc_cvg_of(assigned, avg_gc, sd_gc, avg_cvg, sd_cvg);
+				// ClusterQuality::gc / cvg of the bin come back with its record (abw_search_set_scaffold_stats)
+				avg_gc = r.gc_avg; sd_gc = r.gc_sd; avg_cvg = r.cvg_avg; sd_cvg = r.cvg_sd;
 				summary << r.id << '\t' << assigned.size() << '\t' << cur_dps.size() << '\t' << r.total_size << '\t' << int(1000 * avg_gc) / 10.0 << '\t' << int(1000 * sd_gc) / 100.0
 				        << '\t' << int(10 * avg_cvg) / 10.0 << '\t' << int(10 * sd_cvg) / 10.0 << '\t' << nunique << '\t' << int(100 * avg_copies) / 100.0 << std::endl;
 				continue;

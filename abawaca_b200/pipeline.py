@@ -274,7 +274,7 @@ class SearchResult:
 
 def search(ctx: capi.Context, values, dp2scaf, T, length, scgmask, params=None, strategy=capi.SENS_SPEC, layout=capi.LAYOUT_COLMAJOR,
            values_on_device=False, N=None, D=None, ld=None, want_bins=True, row_of_dp=None, nrows=None, timings=None,
-           collectives=None, dim_offset=0, D_total=None) -> SearchResult:
+           collectives=None, dim_offset=0, D_total=None, scaf_gc=None, scaf_cvg=None) -> SearchResult:
     """values: numpy [D][nrows] (column major) or [nrows][D] (row major), or a device pointer with nrows, D, ld given.
     row_of_dp (uint64 [N], optional): the matrix row of every datapoint; default: N = nrows, datapoint i = row i."""
     L = ctx.lib
@@ -311,6 +311,9 @@ def search(ctx: capi.Context, values, dp2scaf, T, length, scgmask, params=None, 
                                   capi._p(scgmask), W, C.byref(p), strategy, C.byref(h)))
     t1 = time.perf_counter()
     try:
+        if scaf_gc is not None:
+            gc_a, cv_a = np.ascontiguousarray(scaf_gc, dtype=np.float64), np.ascontiguousarray(scaf_cvg, dtype=np.float64)
+            ctx.check(L.abw_search_set_scaffold_stats(ctx.h, h, capi._p(gc_a), capi._p(cv_a)))
         cap = int(max(64, 2 * (N // max(p.cluster_ndps_threshold, 1)) + 64))
         recs = (capi.ClusterRec * cap)()
         n = C.c_uint32()

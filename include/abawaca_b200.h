@@ -209,6 +209,9 @@ typedef struct {
 	uint64_t total_size;        /* terminal clusters: ClusterQuality::total_size */
 	uint32_t scg_unique;        /* terminal clusters: SCGdb::num_unique_scgs */
 	double   scg_avg;           /* terminal clusters: SCGdb::average_num_copies_for_unique_scgs */
+	/* terminal clusters, when abw_search_set_scaffold_stats was called (else -1): ClusterQuality::gc / cvg (ClusterQuality.cpp:51-75),
+	 * length-weighted mean and standard deviation over the assigned scaffolds in scaffold order (standard_deviation, :6-27) */
+	double   gc_avg, gc_sd, cvg_avg, cvg_sd;
 } abw_cluster_rec;
 
 /* Replaces the work-list loop abawaca.cpp:98-197 with ClusterSeparator::separate() (ClusterSeparator.cpp:57-135) inside:
@@ -241,6 +244,10 @@ int abw_search_run_sharded(abw_ctx* ctx, abw_search* s, const abw_collectives* c
 int  abw_nccl_unique_id(abw_ctx* ctx, void* id128);
 int  abw_nccl_collectives_create(abw_ctx* ctx, const void* id128, int rank, int world, abw_collectives* out);
 void abw_nccl_collectives_destroy(abw_collectives* c);
+
+/* Per-scaffold G+C fraction and coverage (ScafDpData::Seq::get_gc / get_cvg, the .info columns), host arrays [S]: the terminal records then
+ * carry the summary.txt statistics ClusterQuality::gc and ClusterQuality::cvg compute.  Call between abw_search_create and abw_search_run. */
+int abw_search_set_scaffold_stats(abw_ctx* ctx, abw_search* s, const double* h_gc, const double* h_cvg);
 
 /* Stop after `max_levels` levels of the breadth-first search (0 = run to the end).  With 1 this is exactly one
  * ClusterSeparator::separate() call on the root: record 0 describes the split and dp2cluster/scaf2cluster hold the ids of

@@ -227,3 +227,37 @@ def test_search_without_dp2scaf(ctx):
     from abawaca_b200 import capi
     with pytest.raises(capi.AbwError, match="sum\\(T\\)"):
         pipeline.search(ctx, prob["values"][:, :-1], None, prob["T"], prob["len"], prob["scgmask"])
+
+
+def test_terminal_bin_statistics(ctx):
+    """ClusterQuality::gc / cvg of the terminal bins (ClusterQuality.cpp:6-27,51-75): length-weighted mean and standard deviation over the assigned
+    scaffolds in scaffold order, the same fp64 operations in the same order (python floats are IEEE doubles, evaluated left to right)"""
+    import math
+    from abawaca_b200 import pipeline
+    prob = search_problem("tiny_noisy")
+    rng = np.random.default_rng(17)
+    S = prob["T"].size
+    gc = np.trunc(1000 * rng.uniform(0.25, 0.75, S)) / 1000
+    cvg = np.trunc(1000 * rng.uniform(0.0, 40.0, S)) / 1000
+    res = pipeline.search(ctx, prob["values"], prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"], scaf_gc=gc, scaf_cvg=cvg)
+    nterm = 0
+    for r in res.recs:
+        if r.split:
+            continue
+        nterm += 1
+        scafs = np.nonzero(res.scaf2cluster == r.id)[0]          # assigned scaffolds of the bin, ascending id
+        for x, got_mean, got_sd in ((gc, r.gc_avg, r.gc_sd), (cvg, r.cvg_avg, r.cvg_sd)):
+            if scafs.size == 0:
+                assert (got_mean, got_sd) == (-1.0, -1.0)
+                continue
+            mean, total = 0.0, 0
+            for s in scafs:
+                mean += float(int(prob["len"][s])) * float(x[s])
+                total += int(prob["len"][s])
+            mean /= float(total)
+            sd = 0.0
+            for s in scafs:
+                sd += float(int(prob["len"][s])) * (float(x[s]) - mean) * (float(x[s]) - mean)
+            sd = math.sqrt(sd / float(total - 1))
+            assert (got_mean, got_sd) == (mean, sd)
+    assert nterm >= 2

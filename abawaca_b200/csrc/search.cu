@@ -1060,7 +1060,22 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_partition2(const uint32_t* __
 	uint32_t my1 = 0;                                      // bit r: my element of row r goes to child 1
 	uint32_t mS1 = 0, mV = 0, mB = 0;                      // masks of row `lane`
 	const bool active = wbase < jb.n;
-	if(active) {
+	const bool full = wbase + SW_WARP_CHUNK <= jb.n;       // warp uniform: all 1024 elements of the chunk exist, no bounds checks
+	if(full) {
+#pragma unroll
+		for(int r = 0; r < 32; r++)
+			el[r] = __ldg(src + wbase + r * 32 + lane);
+		mV = 0xFFFFFFFFu;
+#pragma unroll
+		for(int r = 0; r < 32; r++) {
+			const bool is1 = side[el[r] & EL_SCAF_MASK] == 1;
+			const uint32_t s1 = __ballot_sync(0xffffffffu, is1);
+			const uint32_t b = __ballot_sync(0xffffffffu, el[r] >> 31);
+			my1 |= (is1? 1u : 0u) << r;
+			if(lane == r) { mS1 = s1; mB = b; }
+		}
+	}
+	else if(active) {
 #pragma unroll
 		for(int r = 0; r < 32; r++) {
 			const uint32_t idx = wbase + r * 32 + lane;
@@ -1185,6 +1200,18 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_partition2(const uint32_t* __
 	if(state & 2u)
 		newflags |= mS2 & (0u - mS2);
 	const uint32_t lt = (1u << lane) - 1u;
+	if(full) {
+#pragma unroll
+		for(int r = 0; r < 32; r++) {
+			const uint32_t S1r = __shfl_sync(0xffffffffu, mS1, r), Fr = __shfl_sync(0xffffffffu, newflags, r), b1 = __shfl_sync(0xffffffffu, row_before1, r);
+			const uint32_t idx = wbase + r * 32 + lane;
+			const uint32_t before1 = b1 + __popc(S1r & lt);
+			const uint32_t e = (el[r] & 0x7FFFFFFFu) | (((Fr >> lane) & 1u) << 31);
+			uint32_t* const dst = ((my1 >> r) & 1u)? dst1 + before1 : dst2 + (idx - before1);
+			*dst = e;
+		}
+		return;
+	}
 #pragma unroll
 	for(int r = 0; r < 32; r++) {
 		const uint32_t S1r = __shfl_sync(0xffffffffu, mS1, r), Fr = __shfl_sync(0xffffffffu, newflags, r), b1 = __shfl_sync(0xffffffffu, row_before1, r);

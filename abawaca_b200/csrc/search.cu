@@ -599,10 +599,17 @@ __global__ void __launch_bounds__(SW_THREADS, 4) k_sweep_ss(const uint32_t* __re
 	uint32_t mF = 0, mC = 0, mB = 0;
 	if(wbase < n) {
 		uint32_t el[32];
+		if(wbase + SW_WARP_CHUNK <= n) {                    // warp uniform: the whole chunk exists
 #pragma unroll
-		for(int r = 0; r < 32; r++) {
-			const uint32_t idx = wbase + r * 32 + lane;
-			el[r] = (idx < n)? __ldg(seg + idx) : 0u;          // class 0, no boundary: contributes nothing
+			for(int r = 0; r < 32; r++)
+				el[r] = __ldg(seg + wbase + r * 32 + lane);
+		}
+		else {
+#pragma unroll
+			for(int r = 0; r < 32; r++) {
+				const uint32_t idx = wbase + r * 32 + lane;
+				el[r] = (idx < n)? __ldg(seg + idx) : 0u;      // class 0, no boundary: contributes nothing
+			}
 		}
 #pragma unroll
 		for(int r = 0; r < 32; r++) {

@@ -15,6 +15,7 @@ struct abw_ctx {
 	std::vector<cudaEvent_t> copy_events;
 	int          sm_count = 148;
 	uint64_t     launches = 0;
+	uint64_t     arena_misses = 0;             // device blocks obtained from the driver (cudaMallocAsync) rather than from the context's cache
 	std::string  err;
 	// optional per-kernel timing (abw_profile_enable): every launch is bracketed by events and waited for
 	bool         profiling = false;

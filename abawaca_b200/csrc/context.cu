@@ -31,6 +31,7 @@ cudaError_t abw_arena_alloc(abw_ctx* ctx, size_t bytes, void** out)
 	while(step * 16 < cap)
 		step <<= 1;
 	cap = (cap + step - 1) / step * step;
+	ctx->arena_misses++;
 	cudaError_t e = cudaMallocAsync(out, cap, ctx->stream);
 	if(e != cudaSuccess) {
 		// out of memory: give the cached blocks back and try once more
@@ -188,6 +189,8 @@ void abw_ctx_destroy(abw_ctx* ctx)
 const char* abw_last_error(const abw_ctx* ctx) { return ctx? ctx->err.c_str() : "no context (is a CUDA device present?)"; }
 
 uint64_t abw_kernel_launches(const abw_ctx* ctx) { return ctx? ctx->launches : 0; }
+
+uint64_t abw_arena_misses(const abw_ctx* ctx) { return ctx? ctx->arena_misses : 0; }
 
 void* abw_ctx_stream(const abw_ctx* ctx) { return ctx? (void*)ctx->stream : nullptr; }
 

@@ -363,8 +363,11 @@ def main():
         gc.collect()
         gc.disable()                                   # no interpreter garbage collection pause inside the timed region
         e0.record(ext)
+        host = []
         for i in range(steps):
+            m0, h0 = ctx.arena_misses, time.perf_counter()
             step(resident)
+            host.append((round(1000.0 * (time.perf_counter() - h0), 3), ctx.arena_misses - m0))
             marks[i].record(ext)
         e1.record(ext)
         e1.synchronize()
@@ -375,6 +378,7 @@ def main():
         t = torch.tensor([ms], device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        state["host_ms_and_driver_allocations_" + ("resident" if resident else "e2e")] = host
         return float(t.item()), ctx.launches - l0, per_step
 
     # the sampler is started BEFORE the warm-up: nvidia-smi takes driver locks while it starts and would otherwise stall the first timed launches
@@ -462,7 +466,9 @@ def main():
                        "clusters_evaluated": state["nclusters"], "bins": bins_total, "search_levels": prof.levels, "datapoints": state["ndps"],
                        "nccl": None if coll is None else {"search_collectives": type(coll).__name__, "callback_collectives_total": coll.calls, "callback_bytes_total": coll.bytes}},
             "e2e": {"value": round(e2e_value, 2), "unit": "scaffolds/s", "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches), "step_ms": {"resident": steps_res, "e2e": steps_e2e}, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "gpu_launches": int(launches), "step_ms": {"resident": steps_res, "e2e": steps_e2e,
+                                                     "host_ms_and_driver_allocations": {"resident": state.get("host_ms_and_driver_allocations_resident"),
+                                                                                        "e2e": state.get("host_ms_and_driver_allocations_e2e")}}, "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "phase_wall_ms": {k: round(v, 3) for k, v in phase_ms.items()},
             "search_profile_ms": {"build": round(prof.build_ms, 3), "sweep": round(prof.sweep_ms, 3), "partition": round(prof.partition_ms, 3), "other": round(prof.other_ms, 3)}}
 

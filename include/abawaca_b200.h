@@ -71,6 +71,8 @@ const char* abw_version(void);
 void        abw_default_params(abw_params* p);
 /* number of kernel launches issued through this context so far (bench.py reports it) */
 uint64_t    abw_kernel_launches(const abw_ctx* ctx);
+/* number of device blocks this context had to obtain from the driver so far (0 per pass once its block cache is warm) */
+uint64_t    abw_arena_misses(const abw_ctx* ctx);
 /* the stream every kernel of this context is launched on (a cudaStream_t), for event timing */
 void*       abw_ctx_stream(const abw_ctx* ctx);
 int         abw_ctx_synchronize(abw_ctx* ctx);

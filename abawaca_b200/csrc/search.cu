@@ -1833,10 +1833,13 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		ABW_CUDA(ctx, s->E[b].alloc((size_t)D * N));
 		ABW_CUDA(ctx, s->scg_list[b].alloc((size_t)D * K));
 	}
-	size_t free_b = 0, total_b = 0;
-	ABW_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+	// scratch of the sort is bounded by a fixed budget (the driver is not asked for the free memory: the context caches its blocks, and the query
+	// takes driver-wide locks); ABW_SORT_SCRATCH_GB overrides the 16 GB default
 	const uint64_t per_dim = N * (8 + 8 + 4 + 4 + 1) + 4096;
-	uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(D, (free_b / 2) / per_dim));
+	uint64_t budget = 16ull << 30;
+	if(const char* e = getenv("ABW_SORT_SCRATCH_GB"))
+		budget = std::max<uint64_t>(1, strtoull(e, nullptr, 10)) << 30;
+	uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(D, budget / per_dim));
 	DevBuf<unsigned long long> keys, keys_tmp;
 	DevBuf<uint32_t> vals, vals_tmp, flip_pos;
 	DevBuf<uint8_t> cls;

@@ -274,7 +274,7 @@ class SearchResult:
 
 def search(ctx: capi.Context, values, dp2scaf, T, length, scgmask, params=None, strategy=capi.SENS_SPEC, layout=capi.LAYOUT_COLMAJOR,
            values_on_device=False, N=None, D=None, ld=None, want_bins=True, row_of_dp=None, nrows=None, timings=None,
-           collectives=None, dim_offset=0, D_total=None, scaf_gc=None, scaf_cvg=None) -> SearchResult:
+           collectives=None, dim_offset=0, D_total=None, scaf_gc=None, scaf_cvg=None, buffers=None) -> SearchResult:
     """values: numpy [D][nrows] (column major) or [nrows][D] (row major), or a device pointer with nrows, D, ld given.
     row_of_dp (uint64 [N], optional): the matrix row of every datapoint; default: N = nrows, datapoint i = row i."""
     L = ctx.lib
@@ -315,10 +315,18 @@ def search(ctx: capi.Context, values, dp2scaf, T, length, scgmask, params=None, 
             gc_a, cv_a = np.ascontiguousarray(scaf_gc, dtype=np.float64), np.ascontiguousarray(scaf_cvg, dtype=np.float64)
             ctx.check(L.abw_search_set_scaffold_stats(ctx.h, h, capi._p(gc_a), capi._p(cv_a)))
         cap = int(max(64, 2 * (N // max(p.cluster_ndps_threshold, 1)) + 64))
-        recs = (capi.ClusterRec * cap)()
         n = C.c_uint32()
-        dp2c = np.zeros(N, dtype=np.uint32) if want_bins else None
-        s2c = np.zeros(S, dtype=np.uint32) if want_bins else None
+        if buffers is not None:
+            # result buffers kept by the caller across calls (no fresh pages to fault in on every pass)
+            if buffers.get("cap", 0) < cap or buffers.get("N", 0) < N or buffers.get("S", 0) < S:
+                buffers.update(cap=cap, N=N, S=S, recs=(capi.ClusterRec * cap)(), dp2c=np.zeros(N, dtype=np.uint32), s2c=np.zeros(S, dtype=np.uint32))
+            recs, cap = buffers["recs"], buffers["cap"]
+            dp2c = buffers["dp2c"][:N] if want_bins else None
+            s2c = buffers["s2c"][:S] if want_bins else None
+        else:
+            recs = (capi.ClusterRec * cap)()
+            dp2c = np.zeros(N, dtype=np.uint32) if want_bins else None
+            s2c = np.zeros(S, dtype=np.uint32) if want_bins else None
         if collectives is None:
             ctx.check(L.abw_search_run(ctx.h, h, recs, cap, C.byref(n), capi._p(dp2c), capi._p(s2c)))
         else:

@@ -271,6 +271,7 @@ def main():
         d_reads.append(p)
 
     state = {}
+    result_buffers = {}                                # records and bin arrays of the search, reused by every step
     h_reads_np = [t.numpy().view(capi.READ_DTYPE).reshape(-1) for t in h_reads]
     dev = torch.device("cuda", local_rank)
 
@@ -299,7 +300,7 @@ def main():
         if world == 1:
             row_of_dp = None if keep.all() else np.nonzero(keep)[0].astype(np.uint64)   # scaffolds with one window are dropped (ScafDpData.cpp:92-93)
             res = pipeline.search(ctx, fb.d_rows, dp2scaf, T, lengths[kept], masks[kept], layout=capi.LAYOUT_ROWMAJOR, values_on_device=True,
-                                  nrows=fb.nseg, D=fb.ncols, ld=fb.ncols, row_of_dp=row_of_dp, timings=timings)
+                                  nrows=fb.nseg, D=fb.ncols, ld=fb.ncols, row_of_dp=row_of_dp, timings=timings, buffers=result_buffers)
             nbins = int(np.count_nonzero(np.unique(res.scaf2cluster)))
             ndps_total = int(keep.sum())
         else:
@@ -333,7 +334,7 @@ def main():
             # 3) dimension-sharded search: this rank sweeps columns [off, off+cnt) of every datapoint
             res = pipeline.search(ctx, full.data_ptr(), None, T_all, lengths_all[keep_all], masks_all[keep_all],
                                   layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=int(full.shape[0]), D=cnt, ld=cnt, timings=timings,
-                                  collectives=coll, dim_offset=off, D_total=fb.ncols)
+                                  collectives=coll, dim_offset=off, D_total=fb.ncols, buffers=result_buffers)
             nbins = int(np.count_nonzero(np.unique(res.scaf2cluster)))
             ndps_total = int(full.shape[0])
             del full

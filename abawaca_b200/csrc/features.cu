@@ -596,12 +596,16 @@ __global__ void k_cov_runs(const uint32_t* __restrict__ keys, uint64_t npairs, u
 }
 
 // one thread per window: the reads that hit it, in SAM order (the pairs were sorted stably by window)
+// `only` (may be null): windows whose flag is zero already hold their value (k_cov_quotient) and are left alone
 template <int KIND>
 __global__ void k_cov_accumulate(const uint32_t* __restrict__ vals, const uint2* __restrict__ run, uint64_t nseg,
-                                 const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end, double* __restrict__ rows, uint64_t ld, uint32_t col)
+                                 const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end, double* __restrict__ rows, uint64_t ld, uint32_t col,
+                                 const uint8_t* __restrict__ only)
 {
 	uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(g >= nseg)
+		return;
+	if(only != nullptr && only[g] == 0)
 		return;
 	const double seglen = (double)(seg_end[g] - seg_start[g] + 1);
 	double acc = 0.0, q = 0.0;
@@ -628,6 +632,166 @@ __global__ void k_cov_accumulate(const uint32_t* __restrict__ vals, const uint2*
 	if(KIND == ABW_FEAT_TRUNC3)
 		acc = __ddiv_rn((double)__double2int_rz(__dmul_rn(1000.0, acc)), 1000.0);
 	rows[g * ld + col] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Coverage written with three decimals (ABW_FEAT_TRUNC3, what abawaca-build prints, abawaca-build.cpp:578-607) without sorting the reads.
+//
+// The reference adds fl(ov_i / len) in SAM order and prints int(1000 * sum) / 1000.0.  With A = sum of the overlaps (an integer, order free)
+// the exact value of 1000 * sum is 1000 A / len = m + r / len (m, r integers, 0 <= r < len).  The floating-point sum of n <= A terms differs
+// from A / len by at most (n + 1) u A / len (u = 2^-53: one rounding per quotient, one per addition, one for the product with 1000), so the
+// product the reference truncates lies within E = 1000 (A + 1) u A / len (1 + 1e-10) of m + r / len.  Whenever r != 0 and
+// E < min(r, len - r) / len the truncation is m whatever the order of the reads was: those windows are finished by k_cov_quotient from the
+// integer sum alone (the test is made with twice that bound).  The others (r == 0: the exact value IS a multiple of 0.001 and the rounding
+// direction decides, a fraction of about gcd(1000, len) / len of the windows; or a huge sum) are flagged, and only the reads that touch a
+// flagged window go through the stable sort and the in-order accumulation below.  ABW_FEAT_RAW always takes the sorted path.
+// ---------------------------------------------------------------------------------------------------
+// pass 1: integer sum of the overlaps per window (order free), first window and window count of every read for the second pass,
+// per-scaffold read bases of the -c sample.  status[0] |= 1 when a read touches more than 255 windows (the caller then sorts everything).
+__global__ void __launch_bounds__(COV_THREADS) k_cov_sum(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf,
+                                                        const uint4* __restrict__ scaf_info, const uint64_t* __restrict__ seg_end,
+                                                        unsigned long long* __restrict__ sum_ov, uint4* __restrict__ hit_g0, uchar4* __restrict__ hit_cnt,
+                                                        unsigned long long* __restrict__ scaf_nbps, uint32_t* __restrict__ status)
+{
+	const uint64_t t = (uint64_t)blockIdx.x * COV_THREADS + threadIdx.x;
+	const uint64_t r0 = t * COV_ITEMS;
+	abw_read rd[COV_ITEMS];
+	load_reads(reads, nreads, r0, rd);
+	ReadHit hit[COV_ITEMS];
+	read_windows(rd, max_snps, nscaf, scaf_info, seg_end, hit);
+	uint32_t g0[COV_ITEMS], cn[COV_ITEMS];
+#pragma unroll
+	for(int j = 0; j < COV_ITEMS; j++) {
+		if(scaf_nbps != nullptr && read_accepted(rd[j], max_snps, nscaf))
+			atomicAdd(&scaf_nbps[rd[j].scaf], (unsigned long long)rd[j].len);     // integer: order free (:242-243)
+		g0[j] = hit[j].g0;
+		cn[j] = hit[j].cnt;
+		if(cn[j] > 255u) {
+			atomicOr(status, 1u);
+			cn[j] = 255u;
+		}
+		const uint64_t s = rd[j].pos0, e = (uint64_t)rd[j].pos0 + rd[j].len - 1;
+		uint64_t prev_end = hit[j].end_prev, cur_end = hit[j].end_cur;
+		for(uint32_t k = 0; k < hit[j].cnt; k++) {
+			const uint32_t g = hit[j].g0 + k;
+			const uint64_t st = prev_end + 1, en = cur_end;             // first window of a scaffold: prev_end is 0 and the start 1
+			const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // 0-based read against 1-based window: quirk Q3, kept (:182-183)
+			atomicAdd(&sum_ov[g], (unsigned long long)(e2 - s2 + 1));
+			prev_end = cur_end;
+			if(k + 1 < hit[j].cnt)
+				cur_end = __ldg(seg_end + g + 1);
+		}
+	}
+	static_assert(COV_ITEMS == 4, "hit records are stored four at a time");
+	hit_g0[t] = make_uint4(g0[0], g0[1], g0[2], g0[3]);
+	hit_cnt[t] = make_uchar4((unsigned char)cn[0], (unsigned char)cn[1], (unsigned char)cn[2], (unsigned char)cn[3]);
+}
+
+// one thread per window: the value from the integer sum where the truncation cannot depend on the order of the reads, a flag elsewhere
+__global__ void k_cov_quotient(const unsigned long long* __restrict__ sum_ov, uint64_t nseg, const uint64_t* __restrict__ seg_start,
+                               const uint64_t* __restrict__ seg_end, double* __restrict__ rows, uint64_t ld, uint32_t col, uint8_t* __restrict__ flag)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(g >= nseg)
+		return;
+	const uint64_t A = sum_ov[g], len = seg_end[g] - seg_start[g] + 1;
+	uint8_t f = 0;
+	if(A == 0)
+		rows[g * ld + col] = 0.0;                              // no read: the sum is 0.0 and so is int(0.0) / 1000.0
+	else {
+		f = 1;
+		if(A < (1ull << 40)) {
+			const uint64_t num = 1000ull * A, m = num / len, r = num - m * len;
+			if(r != 0 && m < (1ull << 31)) {
+				const uint64_t dist = (r < len - r)? r : len - r;
+				const double bound = 2000.0 * (double)(A + 2) * (double)A * 1.1102230246251565e-16;   // 2 x 1000 (A + 1) u A, in units of 1 / len
+				if(bound < (double)dist) {
+					f = 0;
+					rows[g * ld + col] = __ddiv_rn((double)(int)m, 1000.0);
+				}
+			}
+		}
+	}
+	flag[g] = f;
+}
+
+// pass 2a: (flagged window, read) pairs per tile of COV_TILE reads
+__global__ void __launch_bounds__(COV_THREADS) k_cov_count_flagged(const uint4* __restrict__ hit_g0, const uchar4* __restrict__ hit_cnt, const uint8_t* __restrict__ flag,
+                                                                  uint32_t* __restrict__ tile_counts)
+{
+	__shared__ uint32_t sm[COV_THREADS / 32];
+	const uint64_t t = (uint64_t)blockIdx.x * COV_THREADS + threadIdx.x;
+	const uint4 g4 = __ldg(hit_g0 + t);
+	const uchar4 c4 = __ldg(hit_cnt + t);
+	const uint32_t g0[4] = {g4.x, g4.y, g4.z, g4.w}, cn[4] = {c4.x, c4.y, c4.z, c4.w};
+	uint32_t c = 0;
+#pragma unroll
+	for(int j = 0; j < 4; j++)
+		for(uint32_t k = 0; k < cn[j]; k++)
+			c += __ldg(flag + g0[j] + k);
+	c = __reduce_add_sync(0xffffffffu, c);
+	if((threadIdx.x & 31) == 0)
+		sm[threadIdx.x >> 5] = c;
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		uint32_t tot = 0;
+#pragma unroll
+		for(int w = 0; w < COV_THREADS / 32; w++)
+			tot += sm[w];
+		tile_counts[blockIdx.x] = tot;
+	}
+}
+
+// pass 2b: those pairs in read order (then window order): key = window, value = overlap
+__global__ void __launch_bounds__(COV_THREADS) k_cov_emit_flagged(const abw_read* __restrict__ reads, const uint4* __restrict__ hit_g0, const uchar4* __restrict__ hit_cnt,
+                                                                 const uint8_t* __restrict__ flag, const uint64_t* __restrict__ seg_start,
+                                                                 const uint64_t* __restrict__ seg_end, const uint64_t* __restrict__ tile_offs,
+                                                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+	__shared__ uint32_t sm[COV_THREADS / 32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint64_t t = (uint64_t)blockIdx.x * COV_THREADS + threadIdx.x;
+	const uint4 g4 = __ldg(hit_g0 + t);
+	const uchar4 c4 = __ldg(hit_cnt + t);
+	const uint32_t g0[4] = {g4.x, g4.y, g4.z, g4.w}, cn[4] = {c4.x, c4.y, c4.z, c4.w};
+	uint32_t c = 0;
+#pragma unroll
+	for(int j = 0; j < 4; j++)
+		for(uint32_t k = 0; k < cn[j]; k++)
+			c += __ldg(flag + g0[j] + k);
+	uint32_t incl = c;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) {
+		const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+		if(lane >= o)
+			incl += x;
+	}
+	if(lane == 31)
+		sm[warp] = incl;
+	__syncthreads();
+	if(c == 0)
+		return;
+	uint32_t wex = 0;
+#pragma unroll
+	for(int w = 0; w < COV_THREADS / 32; w++)
+		if(w < warp)
+			wex += sm[w];
+	uint64_t o = tile_offs[blockIdx.x] + wex + incl - c;
+#pragma unroll
+	for(int j = 0; j < 4; j++) {
+		for(uint32_t k = 0; k < cn[j]; k++) {
+			const uint32_t g = g0[j] + k;
+			if(__ldg(flag + g) == 0)
+				continue;
+			const uint4 x = __ldg(reinterpret_cast<const uint4*>(reads + t * COV_ITEMS + j));   // scaf, pos0, len, flag_nsnps
+			const uint64_t s = x.y, e = (uint64_t)x.y + x.z - 1;
+			const uint64_t st = __ldg(seg_start + g), en = __ldg(seg_end + g);
+			const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // as in k_cov_emit
+			keys[o] = g;
+			vals[o] = (uint32_t)(e2 - s2 + 1);
+			o++;
+		}
+	}
 }
 
 bool g_tables_ready[64] = {};
@@ -847,6 +1011,66 @@ int abw_kmer_features(abw_ctx* ctx, const abw_seqset* s, const abw_segments* g, 
 	return ABW_OK;
 }
 
+// every (window, read) pair through the stable sort and the in-order accumulation; with `only` just the flagged windows, whose pairs
+// are found from the hit records of k_cov_sum
+static int coverage_sorted(abw_ctx* ctx, const abw_segments* g, const abw_read* rd, uint64_t nreads, uint32_t max_snps, int kind, double* d_rows, uint64_t ld,
+                           uint32_t col, uint64_t* d_scaf_nbps, const uint8_t* only, const uint4* hit_g0, const uchar4* hit_cnt, const uint32_t* d_status,
+                           bool* too_many_windows)
+{
+	DevBuf<uint32_t> tile_counts, keys, keys_tmp, vals, vals_tmp;
+	DevBuf<uint64_t> tile_offs, total;
+	DevBuf<uint2> run;
+	const unsigned int ntiles = abw_div_up(nreads, COV_TILE);
+	ABW_CUDA(ctx, tile_counts.alloc(ntiles));
+	ABW_CUDA(ctx, tile_offs.alloc(ntiles));
+	ABW_CUDA(ctx, total.alloc(1));
+	ABW_CUDA(ctx, run.alloc(g->nseg));
+	ABW_CUDA(ctx, cudaMemsetAsync(run.p, 0, sizeof(uint2) * g->nseg, ctx->stream));
+	uint64_t npairs = 0;
+	if(nreads) {
+		if(only)
+			ABW_LAUNCH(ctx, k_cov_count_flagged, ntiles, COV_THREADS, 0, hit_g0, hit_cnt, only, tile_counts.p);
+		else
+			ABW_LAUNCH(ctx, k_cov_count, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, tile_counts.p,
+			           (unsigned long long*)d_scaf_nbps);
+		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, tile_counts.p, tile_offs.p, ntiles, total.p));
+		uint32_t status = 0;
+		ABW_CUDA(ctx, cudaMemcpyAsync(&npairs, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+		if(d_status)
+			ABW_CUDA(ctx, cudaMemcpyAsync(&status, d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		if(status & 1u) {
+			*too_many_windows = true;
+			return ABW_OK;
+		}
+	}
+	if(npairs >= (1ull << 32))
+		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_coverage: more than 2^32-1 (window, read) pairs per call; split the sample");
+	ABW_CUDA(ctx, keys.alloc(npairs));
+	ABW_CUDA(ctx, keys_tmp.alloc(npairs));
+	ABW_CUDA(ctx, vals.alloc(npairs));
+	ABW_CUDA(ctx, vals_tmp.alloc(npairs));
+	if(npairs) {
+		if(only)
+			ABW_LAUNCH(ctx, k_cov_emit_flagged, ntiles, COV_THREADS, 0, rd, hit_g0, hit_cnt, only, g->seg_start.p, g->seg_end.p, tile_offs.p, keys.p, vals.p);
+		else
+			ABW_LAUNCH(ctx, k_cov_emit, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, tile_offs.p, keys.p, vals.p);
+		int nbits = 1;
+		while(nbits < 32 && (1ull << nbits) < g->nseg)
+			nbits++;
+		// window ids are dense: every bit below nbits varies, no need to look
+		ABW_CHECK(abw_radix_sort_pairs_u32(ctx, keys.p, keys_tmp.p, vals.p, vals_tmp.p, npairs, 1, npairs, -nbits));
+		ABW_LAUNCH(ctx, k_cov_runs, abw_div_up(npairs, 256), 256, 0, keys.p, npairs, run.p);
+	}
+	if(g->nseg && (npairs || !only)) {
+		if(kind == ABW_FEAT_TRUNC3)
+			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_TRUNC3>, abw_div_up(g->nseg, 64), 64, 0, vals.p, run.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col, only);
+		else
+			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_RAW>, abw_div_up(g->nseg, 64), 64, 0, vals.p, run.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col, only);
+	}
+	return ABW_OK;
+}
+
 int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uint64_t nreads, int reads_on_device, uint32_t max_snps,
                  int kind, double* d_rows, uint64_t ld, uint32_t col, uint64_t* d_scaf_nbps)
 {
@@ -864,45 +1088,32 @@ int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uin
 		ABW_CUDA(ctx, cudaMemcpyAsync(d_reads.p, reads, sizeof(abw_read) * nreads, cudaMemcpyHostToDevice, ctx->stream));
 		rd = d_reads.p;
 	}
-	DevBuf<uint32_t> tile_counts, keys, keys_tmp, vals, vals_tmp;
-	DevBuf<uint64_t> tile_offs, total;
-	DevBuf<uint2> run;
-	const unsigned int ntiles = abw_div_up(nreads, COV_TILE);
-	ABW_CUDA(ctx, tile_counts.alloc(ntiles));
-	ABW_CUDA(ctx, tile_offs.alloc(ntiles));
-	ABW_CUDA(ctx, total.alloc(1));
-	ABW_CUDA(ctx, run.alloc(g->nseg));
-	ABW_CUDA(ctx, cudaMemsetAsync(run.p, 0, sizeof(uint2) * g->nseg, ctx->stream));
-	uint64_t npairs = 0;
-	if(nreads) {
-		ABW_LAUNCH(ctx, k_cov_count, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, tile_counts.p,
-		           (unsigned long long*)d_scaf_nbps);
-		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, tile_counts.p, tile_offs.p, ntiles, total.p));
-		ABW_CUDA(ctx, cudaMemcpyAsync(&npairs, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	// ABW_COVERAGE_SORT_ALL=1: every read through the sort also for three-decimal output (the first formulation; used by the tests to compare the two)
+	static const bool sort_all = [] { const char* e = getenv("ABW_COVERAGE_SORT_ALL"); return e && *e && *e != '0'; }();
+	bool too_many_windows = false;
+	if(kind == ABW_FEAT_TRUNC3 && !sort_all && nreads && g->nseg) {
+		DevBuf<unsigned long long> sum_ov;
+		DevBuf<uint8_t> flag;
+		DevBuf<uint4> hit_g0;
+		DevBuf<uchar4> hit_cnt;
+		DevBuf<uint32_t> status;
+		const unsigned int ntiles = abw_div_up(nreads, COV_TILE);
+		ABW_CUDA(ctx, sum_ov.alloc(g->nseg));
+		ABW_CUDA(ctx, flag.alloc(g->nseg));
+		ABW_CUDA(ctx, hit_g0.alloc((size_t)ntiles * COV_THREADS));
+		ABW_CUDA(ctx, hit_cnt.alloc((size_t)ntiles * COV_THREADS));
+		ABW_CUDA(ctx, status.alloc(1));
+		ABW_CUDA(ctx, cudaMemsetAsync(sum_ov.p, 0, sizeof(unsigned long long) * g->nseg, ctx->stream));
+		ABW_CUDA(ctx, cudaMemsetAsync(status.p, 0, sizeof(uint32_t), ctx->stream));
+		ABW_LAUNCH(ctx, k_cov_sum, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, sum_ov.p, hit_g0.p, hit_cnt.p,
+		           (unsigned long long*)d_scaf_nbps, status.p);
+		ABW_LAUNCH(ctx, k_cov_quotient, abw_div_up(g->nseg, 256), 256, 0, sum_ov.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col, flag.p);
+		ABW_CHECK(coverage_sorted(ctx, g, rd, nreads, max_snps, kind, d_rows, ld, col, nullptr, flag.p, hit_g0.p, hit_cnt.p, status.p, &too_many_windows));
+		if(too_many_windows)                                   // a read over more than 255 windows: everything again through the sort (the read bases are counted already)
+			ABW_CHECK(coverage_sorted(ctx, g, rd, nreads, max_snps, kind, d_rows, ld, col, nullptr, nullptr, nullptr, nullptr, nullptr, &too_many_windows));
 	}
-	if(npairs >= (1ull << 32))
-		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_coverage: more than 2^32-1 (window, read) pairs per call; split the sample");
-	ABW_CUDA(ctx, keys.alloc(npairs));
-	ABW_CUDA(ctx, keys_tmp.alloc(npairs));
-	ABW_CUDA(ctx, vals.alloc(npairs));
-	ABW_CUDA(ctx, vals_tmp.alloc(npairs));
-	if(npairs) {
-		ABW_LAUNCH(ctx, k_cov_emit, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, tile_offs.p, keys.p, vals.p);
-		int nbits = 1;
-		while(nbits < 32 && (1ull << nbits) < g->nseg)
-			nbits++;
-		// window ids are dense: every bit below nbits varies, no need to look
-		ABW_CHECK(abw_radix_sort_pairs_u32(ctx, keys.p, keys_tmp.p, vals.p, vals_tmp.p, npairs, 1, npairs, -nbits));
-	}
-	if(npairs)
-		ABW_LAUNCH(ctx, k_cov_runs, abw_div_up(npairs, 256), 256, 0, keys.p, npairs, run.p);
-	if(g->nseg) {
-		if(kind == ABW_FEAT_TRUNC3)
-			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_TRUNC3>, abw_div_up(g->nseg, 64), 64, 0, vals.p, run.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col);
-		else
-			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_RAW>, abw_div_up(g->nseg, 64), 64, 0, vals.p, run.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col);
-	}
+	else
+		ABW_CHECK(coverage_sorted(ctx, g, rd, nreads, max_snps, kind, d_rows, ld, col, d_scaf_nbps, nullptr, nullptr, nullptr, nullptr, &too_many_windows));
 	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return ABW_OK;
 }

@@ -97,3 +97,40 @@ def compare_cluster_records(ref_clusters, recs, strategy, check_illegal_best=Tru
         if not ok:
             bad.append(f"cluster {r['id']}: reference {r} != ({o.id},{o.ndps},{o.nscafs},{o.split},{odim},{o.best.value},{o.best.a},{o.best.b})")
     return bad
+
+
+def coverage_edge_workload(seed=7, nscaf=160, nsamples=3, depth=40):
+    """Scaffolds whose windows have round lengths (2000, 2500, 2048, 3125 ...), so that 1000 * (sum of overlaps) / length is an integer for a
+    large share of the windows -- the case in which the order of the reads decides the third decimal (quirk Q5) -- plus an all-N scaffold (one
+    window per character, a read over more than 255 windows), N runs, reads hanging over window and scaffold ends, shuffled read order.
+    Returns (seq, offsets, reads) in the layout of abw_pack_sequences / abw_coverage."""
+    read_dtype = np.dtype([("scaf", "<u4"), ("pos0", "<u4"), ("len", "<u4"), ("flag_nsnps", "<u4")])   # abw_read
+    rng = np.random.default_rng(seed)
+    lens = [int(rng.choice([4000, 5000, 4096, 6000, 6250, 8000, 7500, 10000, 12000, 4001, 9999])) for _ in range(nscaf)]
+    seqs = []
+    for i, n in enumerate(lens):
+        s = rng.integers(0, 4, n).astype(np.uint8)
+        a = np.frombuffer(b"ACGT", dtype=np.uint8)[s].copy()
+        if i % 17 == 3:                                     # a run of N inside the scaffold
+            p = int(rng.integers(100, n - 400)); a[p:p + int(rng.integers(10, 300))] = ord("N")
+        seqs.append(a)
+    seqs.append(np.full(400, ord("N"), dtype=np.uint8))     # all-N scaffold: 400 windows of one character
+    lens.append(400)
+    offsets = np.zeros(len(lens) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    seq = np.concatenate(seqs)
+    reads = []
+    for _ in range(nsamples):
+        recs = []
+        for i, n in enumerate(lens):
+            k = int(depth * n / 100 * rng.uniform(0.3, 1.5))
+            rl = rng.choice([100, 100, 100, 100, 50, 150, 75, 300 if n == 400 else 100], k).astype(np.uint32)
+            pos = rng.integers(0, n, k).astype(np.uint32)
+            r = np.zeros(k, dtype=read_dtype)
+            r["scaf"], r["pos0"], r["len"] = i, pos, rl
+            r["flag_nsnps"] = np.where(rng.random(k) < 0.02, 4, 0) | (rng.integers(0, 4, k).astype(np.uint32) << 16)
+            recs.append(r)
+        r = np.concatenate(recs)
+        rng.shuffle(r)
+        reads.append(r)
+    return seq, offsets, reads

@@ -261,3 +261,28 @@ def test_terminal_bin_statistics(ctx):
             sd = math.sqrt(sd / float(total - 1))
             assert (got_mean, got_sd) == (mean, sd)
     assert nterm >= 2
+
+
+def test_coverage_when_the_order_of_the_reads_decides_the_third_decimal(ctx, oracle):
+    """Round window lengths: for many windows 1000 * sum(overlaps) / length is an integer, which is where abw_coverage cannot take the value
+    from the integer sum and falls back to the in-order accumulation; plus a read over more than 255 windows."""
+    from abawaca_b200 import capi, pipeline
+    from golden_util import coverage_edge_workload
+    seq, offsets, reads = coverage_edge_workload()
+    f = oracle.build_features(seq, offsets, reads, this_sample=1, want_raw=True)
+    fb = pipeline.build_features(ctx, seq, offsets, reads, this_sample=1)
+    rows = fb.rows_host()
+    assert np.array_equal(rows, f["rows"])
+    st = fb.scaffold_stats_host(np.diff(offsets.astype(np.int64)))
+    assert np.array_equal(st["cvg"], f["info_cvg"])
+    fb.close()
+    fb = pipeline.build_features(ctx, seq, offsets, reads, this_sample=1, kind=capi.FEAT_RAW, skip_A=False)
+    assert np.array_equal(fb.rows_host(), f["raw"])
+    fb.close()
+    # without the all-N scaffold no read covers more than 255 windows: the integer-sum path with its in-order remainder
+    keep = offsets.size - 2
+    reads2 = [r[r["scaf"] < keep] for r in reads]
+    f2 = oracle.build_features(seq[:int(offsets[keep])], offsets[:keep + 1], reads2, this_sample=0)
+    fb = pipeline.build_features(ctx, seq[:int(offsets[keep])], offsets[:keep + 1], reads2, this_sample=0)
+    assert np.array_equal(fb.rows_host(), f2["rows"])
+    fb.close()

@@ -122,3 +122,38 @@ def test_search_threads_do_not_change_result(oracle):
     r8, _, s8 = S.run(nthreads=8)
     assert s1.tolist() == s8.tolist()
     assert [(r.best.dim, r.best.value, r.best.a, r.best.b) for r in r1] == [(r.best.dim, r.best.value, r.best.a, r.best.b) for r in r8]
+
+
+def test_three_decimal_coverage_from_the_integer_sum(oracle):
+    """The shortcut abw_coverage takes for three-decimal output (k_cov_quotient), restated in numpy: wherever it claims
+    that the truncation cannot depend on the order of the reads, floor(1000 * A / len) / 1000 must be the sequential value of the oracle; and
+    on this workload (round window lengths) the windows it leaves to the in-order path must include some where the naive quotient is wrong."""
+    from golden_util import coverage_edge_workload
+    seq, offsets, reads = coverage_edge_workload()
+    f = oracle.build_features(seq, offsets, reads, this_sample=0)
+    seg_scaf, seg_start, seg_end = f["seg_scaf"].astype(np.int64), f["seg_start"].astype(np.int64), f["seg_end"].astype(np.int64)
+    nscaf = offsets.size - 1
+    first = np.searchsorted(seg_scaf, np.arange(nscaf + 1))
+    claimed = wrong_if_naive = undecided = 0
+    for j, r in enumerate(reads):
+        flag, nsnps = r["flag_nsnps"] & 0xFFFF, r["flag_nsnps"] >> 16
+        ok = ~(((flag & 0x4) != 0) | (nsnps > 15) | ((flag & 0x100) != 0)) & (r["scaf"] < nscaf)
+        A = np.zeros(seg_scaf.size, dtype=np.int64)
+        for sc, s, ln in zip(r["scaf"][ok].astype(np.int64), r["pos0"][ok].astype(np.int64), r["len"][ok].astype(np.int64)):
+            e = s + ln - 1
+            for g in range(first[sc], first[sc + 1]):
+                if s > seg_end[g]:
+                    continue
+                if e < seg_start[g]:
+                    break
+                A[g] += min(e, seg_end[g]) - max(s, seg_start[g]) + 1
+        ln = seg_end - seg_start + 1
+        m, rem = np.divmod(1000 * A, ln)
+        bound = 2000.0 * (A + 2) * A * 2.0 ** -53
+        safe = (A == 0) | ((rem != 0) & (bound < np.minimum(rem, ln - rem)))
+        got = f["rows"][:, 179 + j]
+        assert np.array_equal((m / 1000.0)[safe], got[safe])
+        claimed += int(safe.sum())
+        undecided += int((~safe).sum())
+        wrong_if_naive += int(((m / 1000.0) != got)[~safe].sum())
+    assert claimed > 0 and undecided > 100 and wrong_if_naive > 0

@@ -133,3 +133,6 @@ int abw_radix_sort_pairs_u64(abw_ctx* ctx, uint64_t* d_keys, uint64_t* d_keys_tm
                              uint64_t stride, int nbits);
 int abw_radix_sort_pairs_u32(abw_ctx* ctx, uint32_t* d_keys, uint32_t* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, uint32_t batch,
                              uint64_t stride, int nbits);
+// the same with the set of key bits that differ between any two keys (OR of all keys ^ AND of all keys) supplied by the caller: no inspection pass
+int abw_radix_sort_pairs_u32_varying(abw_ctx* ctx, uint32_t* d_keys, uint32_t* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, uint32_t batch,
+                                     uint64_t stride, unsigned long long varying);

@@ -145,6 +145,8 @@ __device__ __forceinline__ void window_plan(uint64_t len, uint64_t nN, uint64_t 
 	count = (nbps > 0)? nonN / nbps : len;
 }
 
+constexpr uint32_t COV_REGULAR = 0x80000000u;              // scaf_info.w of a scaffold whose windows are all nbps characters long (no N)
+
 __global__ void k_seg_count(const uint64_t* __restrict__ len, const unsigned long long* __restrict__ countN, uint32_t nscaf, uint64_t window, uint64_t* __restrict__ counts)
 {
 	uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,7 +170,14 @@ __global__ void __launch_bounds__(256) k_seg_fill(const uint64_t* __restrict__ l
 		uint64_t nbps, count;
 		window_plan(L, countN[s], window, nbps, count);
 		if(lane == 0)
-			scaf_info[s] = make_uint4((uint32_t)first, (uint32_t)min(count, (uint64_t)0xFFFFFFFFu), (uint32_t)nbps, (uint32_t)(nbps >> 32));
+			{
+			// .w: bits 32.. of nbps (coverage then searches instead of guessing), or COV_REGULAR for a scaffold without N whose windows
+			// are exactly [j nbps + 1, (j + 1) nbps]: coverage then needs no window table at all
+			uint32_t hi = (uint32_t)min(nbps >> 32, (uint64_t)0x7FFFFFFFu);
+			if(countN[s] == 0 && nbps > 0 && hi == 0)
+				hi = COV_REGULAR;
+			scaf_info[s] = make_uint4((uint32_t)first, (uint32_t)min(count, (uint64_t)0xFFFFFFFFu), (uint32_t)nbps, hi);
+		}
 		if(count == 0)
 			continue;
 		if(nbps == 0) {
@@ -438,7 +447,7 @@ __device__ __forceinline__ void read_windows(const abw_read (&rd)[COV_ITEMS], ui
 		uint32_t q = 0;
 		if(s > 0) {
 			// an all-N scaffold (nbps 0) has one window per character
-			if(si[j].w == 0)
+			if(si[j].w == 0 || si[j].w == COV_REGULAR)
 				q = (s - 1) / max(si[j].z, 1u);
 			else
 				q = 0;                                      // more than 2^32 bases per window: every read position lies in the first window or is found by the search
@@ -597,29 +606,30 @@ __global__ void k_cov_runs(const uint32_t* __restrict__ keys, uint64_t npairs, u
 
 // one thread per window: the reads that hit it, in SAM order (the pairs were sorted stably by window)
 // `only` (may be null): windows whose flag is zero already hold their value (k_cov_quotient) and are left alone
-template <int KIND>
+template <int KIND, int BATCH>
 __global__ void k_cov_accumulate(const uint32_t* __restrict__ vals, const uint2* __restrict__ run, uint64_t nseg,
                                  const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end, double* __restrict__ rows, uint64_t ld, uint32_t col,
-                                 const uint8_t* __restrict__ only)
+                                 const uint32_t* __restrict__ only)
 {
 	uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(g >= nseg)
 		return;
-	if(only != nullptr && only[g] == 0)
+	if(only != nullptr && ((only[g >> 5] >> (g & 31u)) & 1u) == 0)
 		return;
 	const double seglen = (double)(seg_end[g] - seg_start[g] + 1);
 	double acc = 0.0, q = 0.0;
 	uint32_t last = 0xFFFFFFFFu;
 	const uint2 rg = run[g];
-	for(uint32_t i = rg.x; i < rg.y; i += 8) {
-		// eight loads in flight; the additions stay strictly in SAM order (quirk Q5)
-		const uint32_t m = min(8u, rg.y - i);
-		uint32_t ov[8];
+	for(uint32_t i = rg.x; i < rg.y; i += BATCH) {
+		// BATCH loads in flight (8 when every window is summed, 32 when only the few flagged ones are and the longest run sets the time);
+		// the additions stay strictly in SAM order (quirk Q5)
+		const uint32_t m = min((uint32_t)BATCH, rg.y - i);
+		uint32_t ov[BATCH];
 #pragma unroll
-		for(int j = 0; j < 8; j++)
+		for(int j = 0; j < BATCH; j++)
 			ov[j] = ((uint32_t)j < m)? __ldg(vals + i + j) : 0u;
 #pragma unroll
-		for(int j = 0; j < 8; j++) {
+		for(int j = 0; j < BATCH; j++) {
 			if((uint32_t)j < m) {
 				if(ov[j] != last) {                            // most reads lie entirely inside the window: same quotient, computed once
 					q = __ddiv_rn((double)ov[j], seglen);      // :184
@@ -648,87 +658,179 @@ __global__ void k_cov_accumulate(const uint32_t* __restrict__ vals, const uint2*
 // ---------------------------------------------------------------------------------------------------
 // pass 1: integer sum of the overlaps per window (order free), first window and window count of every read for the second pass,
 // per-scaffold read bases of the -c sample.  status[0] |= 1 when a read touches more than 255 windows (the caller then sorts everything).
-__global__ void __launch_bounds__(COV_THREADS) k_cov_sum(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf,
-                                                        const uint4* __restrict__ scaf_info, const uint64_t* __restrict__ seg_end,
-                                                        unsigned long long* __restrict__ sum_ov, uint4* __restrict__ hit_g0, uchar4* __restrict__ hit_cnt,
-                                                        unsigned long long* __restrict__ scaf_nbps, uint32_t* __restrict__ status)
+// A scaffold without N (COV_REGULAR) has the windows [l nbps + 1, (l + 1) nbps]: its reads need the 16-byte scaffold record and nothing
+// else.  The other scaffolds go through the window table one read at a time (guess, verify, binary search: as read_windows).
+__device__ __noinline__ void cov_sum_irregular(uint32_t pos0, uint32_t rlen, const uint4 si, const uint64_t* __restrict__ seg_end,
+                                               unsigned long long* __restrict__ sum_ov, uint32_t& g0_out, uint32_t& cnt_out)
 {
+	const uint64_t s = pos0, e = (uint64_t)pos0 + rlen - 1;
+	const uint32_t f0 = si.x, f1 = si.x + si.y;
+	uint32_t q = 0;
+	if(pos0 > 0 && si.w == 0)
+		q = (pos0 - 1) / max(si.z, 1u);                     // an all-N scaffold (nbps 0) has one window per character
+	uint32_t gg = f0 + min(si.y - 1u, q);
+	uint64_t cur_end = __ldg(seg_end + gg), prev_end = (gg > f0)? __ldg(seg_end + gg - 1) : 0ull;
+	if(!((gg == f0 || prev_end < s) && cur_end >= s)) {
+		uint32_t lo = f0, hi = f1;                          // runs of N moved the boundaries: binary search for the first window whose end is >= s
+		while(lo < hi) {
+			const uint32_t mid = lo + ((hi - lo) >> 1);
+			if(__ldg(seg_end + mid) < s) lo = mid + 1; else hi = mid;
+		}
+		gg = lo;
+		cur_end = (gg < f1)? __ldg(seg_end + gg) : 0ull;
+		prev_end = (gg > f0)? __ldg(seg_end + gg - 1) : 0ull;
+	}
+	uint32_t c = 0, w = gg;
+	while(w < f1 && !(e < prev_end + 1)) {                     // windows gg, gg+1, ... while their start is <= e (:233-237)
+		const uint64_t st = prev_end + 1, en = cur_end;
+		const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // 0-based read against 1-based window: quirk Q3, kept (:182-183)
+		atomicAdd(&sum_ov[w], (unsigned long long)(e2 - s2 + 1));
+		c++;
+		w++;
+		prev_end = cur_end;
+		if(w < f1)
+			cur_end = __ldg(seg_end + w);
+	}
+	g0_out = gg;
+	cnt_out = c;
+}
+
+__global__ void __launch_bounds__(COV_THREADS, 5) k_cov_sum(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf,
+                                                           const uint4* __restrict__ scaf_info, const uint64_t* __restrict__ seg_end,
+                                                           unsigned long long* __restrict__ sum_ov, uint4* __restrict__ hit_g0, uchar4* __restrict__ hit_cnt,
+                                                           unsigned long long* __restrict__ scaf_nbps, uint32_t* __restrict__ status)
+{
+	static_assert(COV_ITEMS == 4, "hit records are stored four at a time");
 	const uint64_t t = (uint64_t)blockIdx.x * COV_THREADS + threadIdx.x;
 	const uint64_t r0 = t * COV_ITEMS;
-	abw_read rd[COV_ITEMS];
-	load_reads(reads, nreads, r0, rd);
-	ReadHit hit[COV_ITEMS];
-	read_windows(rd, max_snps, nscaf, scaf_info, seg_end, hit);
+	uint4 x[COV_ITEMS], si[COV_ITEMS];                        // read: scaf, pos0, len, flag_nsnps; scaffold: first window, windows, nbps, kind
+	bool acc[COV_ITEMS];
+#pragma unroll
+	for(int j = 0; j < COV_ITEMS; j++)
+		x[j] = (r0 + j < nreads)? __ldg(reinterpret_cast<const uint4*>(reads + r0 + j)) : make_uint4(0xFFFFFFFFu, 0, 0, 0);
+#pragma unroll
+	for(int j = 0; j < COV_ITEMS; j++) {
+		const uint32_t flag = x[j].w & 0xFFFFu, nsnps = x[j].w >> 16;
+		acc[j] = !((flag & 0x4u) || (nsnps > max_snps) || (flag & 0x100u)) && x[j].x < nscaf;   // :546-550
+		si[j] = acc[j]? __ldg(scaf_info + x[j].x) : make_uint4(0, 0, 1, 0);
+	}
 	uint32_t g0[COV_ITEMS], cn[COV_ITEMS];
 #pragma unroll
 	for(int j = 0; j < COV_ITEMS; j++) {
-		if(scaf_nbps != nullptr && read_accepted(rd[j], max_snps, nscaf))
-			atomicAdd(&scaf_nbps[rd[j].scaf], (unsigned long long)rd[j].len);     // integer: order free (:242-243)
-		g0[j] = hit[j].g0;
-		cn[j] = hit[j].cnt;
+		g0[j] = 0;
+		cn[j] = 0;
+		if(!acc[j])
+			continue;
+		if(scaf_nbps != nullptr)
+			atomicAdd(&scaf_nbps[x[j].x], (unsigned long long)x[j].z);        // integer: order free (:242-243)
+		if(si[j].y == 0)
+			continue;
+		if(si[j].w == COV_REGULAR) {
+			const uint32_t nb = si[j].z, pos0 = x[j].y;
+			const uint32_t q = pos0? (pos0 - 1) / nb : 0u;     // position s >= 1 lies in window (s - 1) / nbps; position 0 before the first one
+			if(q >= si[j].y)
+				continue;                                   // behind the last window (the trailing bases no window holds)
+			const uint64_t s = pos0, e = (uint64_t)pos0 + x[j].z - 1;
+			uint32_t l = q, c = 0;
+			uint64_t st = (uint64_t)q * nb + 1;
+			while(l < si[j].y && !(e < st)) {
+				const uint64_t en = st + nb - 1;
+				const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // quirk Q3, as above
+				atomicAdd(&sum_ov[si[j].x + l], (unsigned long long)(e2 - s2 + 1));
+				c++;
+				l++;
+				st = en + 1;
+			}
+			g0[j] = si[j].x + q;
+			cn[j] = c;
+		}
+		else
+			cov_sum_irregular(x[j].y, x[j].z, si[j], seg_end, sum_ov, g0[j], cn[j]);
 		if(cn[j] > 255u) {
 			atomicOr(status, 1u);
 			cn[j] = 255u;
 		}
-		const uint64_t s = rd[j].pos0, e = (uint64_t)rd[j].pos0 + rd[j].len - 1;
-		uint64_t prev_end = hit[j].end_prev, cur_end = hit[j].end_cur;
-		for(uint32_t k = 0; k < hit[j].cnt; k++) {
-			const uint32_t g = hit[j].g0 + k;
-			const uint64_t st = prev_end + 1, en = cur_end;             // first window of a scaffold: prev_end is 0 and the start 1
-			const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // 0-based read against 1-based window: quirk Q3, kept (:182-183)
-			atomicAdd(&sum_ov[g], (unsigned long long)(e2 - s2 + 1));
-			prev_end = cur_end;
-			if(k + 1 < hit[j].cnt)
-				cur_end = __ldg(seg_end + g + 1);
-		}
 	}
-	static_assert(COV_ITEMS == 4, "hit records are stored four at a time");
 	hit_g0[t] = make_uint4(g0[0], g0[1], g0[2], g0[3]);
 	hit_cnt[t] = make_uchar4((unsigned char)cn[0], (unsigned char)cn[1], (unsigned char)cn[2], (unsigned char)cn[3]);
 }
 
 // one thread per window: the value from the integer sum where the truncation cannot depend on the order of the reads, a flag elsewhere
-__global__ void k_cov_quotient(const unsigned long long* __restrict__ sum_ov, uint64_t nseg, const uint64_t* __restrict__ seg_start,
-                               const uint64_t* __restrict__ seg_end, double* __restrict__ rows, uint64_t ld, uint32_t col, uint8_t* __restrict__ flag)
+__global__ void __launch_bounds__(256) k_cov_quotient(const unsigned long long* __restrict__ sum_ov, uint64_t nseg, const uint64_t* __restrict__ seg_start,
+                                                      const uint64_t* __restrict__ seg_end, double* __restrict__ rows, uint64_t ld, uint32_t col,
+                                                      uint32_t* __restrict__ flag_bits)
 {
 	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(g >= nseg)
-		return;
-	const uint64_t A = sum_ov[g], len = seg_end[g] - seg_start[g] + 1;
-	uint8_t f = 0;
-	if(A == 0)
-		rows[g * ld + col] = 0.0;                              // no read: the sum is 0.0 and so is int(0.0) / 1000.0
-	else {
-		f = 1;
-		if(A < (1ull << 40)) {
-			const uint64_t num = 1000ull * A, m = num / len, r = num - m * len;
-			if(r != 0 && m < (1ull << 31)) {
-				const uint64_t dist = (r < len - r)? r : len - r;
-				const double bound = 2000.0 * (double)(A + 2) * (double)A * 1.1102230246251565e-16;   // 2 x 1000 (A + 1) u A, in units of 1 / len
-				if(bound < (double)dist) {
-					f = 0;
-					rows[g * ld + col] = __ddiv_rn((double)(int)m, 1000.0);
+	bool f = false;
+	if(g < nseg) {
+		const uint64_t A = sum_ov[g], len = seg_end[g] - seg_start[g] + 1;
+		if(A == 0)
+			rows[g * ld + col] = 0.0;                          // no read: the sum is 0.0 and so is int(0.0) / 1000.0
+		else {
+			f = true;
+			if(A < (1ull << 40)) {
+				const uint64_t num = 1000ull * A, m = num / len, r = num - m * len;
+				if(r != 0 && m < (1ull << 31)) {
+					const uint64_t dist = (r < len - r)? r : len - r;
+					const double bound = 2000.0 * (double)(A + 2) * (double)A * 1.1102230246251565e-16;   // 2 x 1000 (A + 1) u A, in units of 1 / len
+					if(bound < (double)dist) {
+						f = false;
+						rows[g * ld + col] = __ddiv_rn((double)(int)m, 1000.0);
+					}
 				}
 			}
 		}
 	}
-	flag[g] = f;
+	// one bit per window (28 KB for 227 k windows: the second pass tests it for every read out of L1)
+	const uint32_t bits = __ballot_sync(0xffffffffu, f);
+	if((threadIdx.x & 31) == 0 && g < nseg)
+		flag_bits[g >> 5] = bits;
 }
 
-// pass 2a: (flagged window, read) pairs per tile of COV_TILE reads
-__global__ void __launch_bounds__(COV_THREADS) k_cov_count_flagged(const uint4* __restrict__ hit_g0, const uchar4* __restrict__ hit_cnt, const uint8_t* __restrict__ flag,
-                                                                  uint32_t* __restrict__ tile_counts)
+__device__ __forceinline__ uint32_t window_flagged(const uint32_t* __restrict__ flag_bits, uint32_t g)
 {
-	__shared__ uint32_t sm[COV_THREADS / 32];
-	const uint64_t t = (uint64_t)blockIdx.x * COV_THREADS + threadIdx.x;
-	const uint4 g4 = __ldg(hit_g0 + t);
-	const uchar4 c4 = __ldg(hit_cnt + t);
-	const uint32_t g0[4] = {g4.x, g4.y, g4.z, g4.w}, cn[4] = {c4.x, c4.y, c4.z, c4.w};
+	return (__ldg(flag_bits + (g >> 5)) >> (g & 31u)) & 1u;
+}
+
+// Second pass over the hit records: a thread takes FL_GROUPS groups of four consecutive reads, a CTA 256 * FL_GROUPS * 4 consecutive reads;
+// pairs come out in read order.  The flag of the first window of every read is tested unconditionally (independent loads, all in flight);
+// the few reads over several windows loop.  (Measured: these kernels are bound by the chain load record -> load flag of each thread, and
+// four groups per thread were slower than one.)
+constexpr int FL_GROUPS = 1;
+constexpr int FL_TILE_GROUPS = COV_THREADS * FL_GROUPS;
+
+__device__ __forceinline__ uint32_t flagged_hits(const uint4* __restrict__ hit_g0, const uchar4* __restrict__ hit_cnt, uint64_t ngroups, uint64_t t0,
+                                                const uint32_t* __restrict__ flag, uint4 (&g4)[FL_GROUPS], uchar4 (&c4)[FL_GROUPS])
+{
+#pragma unroll
+	for(int q = 0; q < FL_GROUPS; q++) {
+		const bool in = t0 + q < ngroups;
+		g4[q] = in? __ldg(hit_g0 + t0 + q) : make_uint4(0, 0, 0, 0);
+		c4[q] = in? __ldg(hit_cnt + t0 + q) : make_uchar4(0, 0, 0, 0);
+	}
 	uint32_t c = 0;
 #pragma unroll
-	for(int j = 0; j < 4; j++)
-		for(uint32_t k = 0; k < cn[j]; k++)
-			c += __ldg(flag + g0[j] + k);
+	for(int q = 0; q < FL_GROUPS; q++) {
+		const uint32_t fx = window_flagged(flag, g4[q].x), fy = window_flagged(flag, g4[q].y);      // window 0 for a read without window: any valid word
+		const uint32_t fz = window_flagged(flag, g4[q].z), fw = window_flagged(flag, g4[q].w);
+		c += (c4[q].x? fx : 0u) + (c4[q].y? fy : 0u) + (c4[q].z? fz : 0u) + (c4[q].w? fw : 0u);
+		for(uint32_t k = 1; k < c4[q].x; k++) c += window_flagged(flag, g4[q].x + k);
+		for(uint32_t k = 1; k < c4[q].y; k++) c += window_flagged(flag, g4[q].y + k);
+		for(uint32_t k = 1; k < c4[q].z; k++) c += window_flagged(flag, g4[q].z + k);
+		for(uint32_t k = 1; k < c4[q].w; k++) c += window_flagged(flag, g4[q].w + k);
+	}
+	return c;
+}
+
+// pass 2a: (flagged window, read) pairs per tile
+__global__ void __launch_bounds__(COV_THREADS) k_cov_count_flagged(const uint4* __restrict__ hit_g0, const uchar4* __restrict__ hit_cnt, uint64_t ngroups,
+                                                                  const uint32_t* __restrict__ flag, uint32_t* __restrict__ tile_counts)
+{
+	__shared__ uint32_t sm[COV_THREADS / 32];
+	const uint64_t t0 = ((uint64_t)blockIdx.x * COV_THREADS + threadIdx.x) * FL_GROUPS;
+	uint4 g4[FL_GROUPS];
+	uchar4 c4[FL_GROUPS];
+	uint32_t c = flagged_hits(hit_g0, hit_cnt, ngroups, t0, flag, g4, c4);
 	c = __reduce_add_sync(0xffffffffu, c);
 	if((threadIdx.x & 31) == 0)
 		sm[threadIdx.x >> 5] = c;
@@ -744,21 +846,16 @@ __global__ void __launch_bounds__(COV_THREADS) k_cov_count_flagged(const uint4* 
 
 // pass 2b: those pairs in read order (then window order): key = window, value = overlap
 __global__ void __launch_bounds__(COV_THREADS) k_cov_emit_flagged(const abw_read* __restrict__ reads, const uint4* __restrict__ hit_g0, const uchar4* __restrict__ hit_cnt,
-                                                                 const uint8_t* __restrict__ flag, const uint64_t* __restrict__ seg_start,
+                                                                 uint64_t ngroups, const uint32_t* __restrict__ flag, const uint64_t* __restrict__ seg_start,
                                                                  const uint64_t* __restrict__ seg_end, const uint64_t* __restrict__ tile_offs,
                                                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
 	__shared__ uint32_t sm[COV_THREADS / 32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint64_t t = (uint64_t)blockIdx.x * COV_THREADS + threadIdx.x;
-	const uint4 g4 = __ldg(hit_g0 + t);
-	const uchar4 c4 = __ldg(hit_cnt + t);
-	const uint32_t g0[4] = {g4.x, g4.y, g4.z, g4.w}, cn[4] = {c4.x, c4.y, c4.z, c4.w};
-	uint32_t c = 0;
-#pragma unroll
-	for(int j = 0; j < 4; j++)
-		for(uint32_t k = 0; k < cn[j]; k++)
-			c += __ldg(flag + g0[j] + k);
+	const uint64_t t0 = ((uint64_t)blockIdx.x * COV_THREADS + threadIdx.x) * FL_GROUPS;
+	uint4 g4[FL_GROUPS];
+	uchar4 c4[FL_GROUPS];
+	const uint32_t c = flagged_hits(hit_g0, hit_cnt, ngroups, t0, flag, g4, c4);
 	uint32_t incl = c;
 #pragma unroll
 	for(int o = 1; o < 32; o <<= 1) {
@@ -778,18 +875,22 @@ __global__ void __launch_bounds__(COV_THREADS) k_cov_emit_flagged(const abw_read
 			wex += sm[w];
 	uint64_t o = tile_offs[blockIdx.x] + wex + incl - c;
 #pragma unroll
-	for(int j = 0; j < 4; j++) {
-		for(uint32_t k = 0; k < cn[j]; k++) {
-			const uint32_t g = g0[j] + k;
-			if(__ldg(flag + g) == 0)
-				continue;
-			const uint4 x = __ldg(reinterpret_cast<const uint4*>(reads + t * COV_ITEMS + j));   // scaf, pos0, len, flag_nsnps
-			const uint64_t s = x.y, e = (uint64_t)x.y + x.z - 1;
-			const uint64_t st = __ldg(seg_start + g), en = __ldg(seg_end + g);
-			const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // as in k_cov_emit
-			keys[o] = g;
-			vals[o] = (uint32_t)(e2 - s2 + 1);
-			o++;
+	for(int q = 0; q < FL_GROUPS; q++) {
+		const uint32_t g0[4] = {g4[q].x, g4[q].y, g4[q].z, g4[q].w}, cn[4] = {c4[q].x, c4[q].y, c4[q].z, c4[q].w};
+#pragma unroll
+		for(int j = 0; j < 4; j++) {
+			for(uint32_t k = 0; k < cn[j]; k++) {
+				const uint32_t g = g0[j] + k;
+				if(window_flagged(flag, g) == 0)
+					continue;
+				const uint4 x = __ldg(reinterpret_cast<const uint4*>(reads + (t0 + q) * COV_ITEMS + j));   // scaf, pos0, len, flag_nsnps
+				const uint64_t s = x.y, e = (uint64_t)x.y + x.z - 1;
+				const uint64_t st = __ldg(seg_start + g), en = __ldg(seg_end + g);
+				const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // as in k_cov_emit
+				keys[o] = g;
+				vals[o] = (uint32_t)(e2 - s2 + 1);
+				o++;
+			}
 		}
 	}
 }
@@ -1014,13 +1115,14 @@ int abw_kmer_features(abw_ctx* ctx, const abw_seqset* s, const abw_segments* g, 
 // every (window, read) pair through the stable sort and the in-order accumulation; with `only` just the flagged windows, whose pairs
 // are found from the hit records of k_cov_sum
 static int coverage_sorted(abw_ctx* ctx, const abw_segments* g, const abw_read* rd, uint64_t nreads, uint32_t max_snps, int kind, double* d_rows, uint64_t ld,
-                           uint32_t col, uint64_t* d_scaf_nbps, const uint8_t* only, const uint4* hit_g0, const uchar4* hit_cnt, const uint32_t* d_status,
+                           uint32_t col, uint64_t* d_scaf_nbps, const uint32_t* only, const uint4* hit_g0, const uchar4* hit_cnt, const uint32_t* d_status,
                            bool* too_many_windows)
 {
 	DevBuf<uint32_t> tile_counts, keys, keys_tmp, vals, vals_tmp;
 	DevBuf<uint64_t> tile_offs, total;
 	DevBuf<uint2> run;
-	const unsigned int ntiles = abw_div_up(nreads, COV_TILE);
+	const uint64_t ngroups = (uint64_t)abw_div_up(nreads, COV_TILE) * COV_THREADS;   // hit records (groups of four reads) written by k_cov_sum
+	const unsigned int ntiles = only? abw_div_up(ngroups, FL_TILE_GROUPS) : abw_div_up(nreads, COV_TILE);
 	ABW_CUDA(ctx, tile_counts.alloc(ntiles));
 	ABW_CUDA(ctx, tile_offs.alloc(ntiles));
 	ABW_CUDA(ctx, total.alloc(1));
@@ -1029,7 +1131,7 @@ static int coverage_sorted(abw_ctx* ctx, const abw_segments* g, const abw_read* 
 	uint64_t npairs = 0;
 	if(nreads) {
 		if(only)
-			ABW_LAUNCH(ctx, k_cov_count_flagged, ntiles, COV_THREADS, 0, hit_g0, hit_cnt, only, tile_counts.p);
+			ABW_LAUNCH(ctx, k_cov_count_flagged, ntiles, COV_THREADS, 0, hit_g0, hit_cnt, ngroups, only, tile_counts.p);
 		else
 			ABW_LAUNCH(ctx, k_cov_count, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, tile_counts.p,
 			           (unsigned long long*)d_scaf_nbps);
@@ -1052,7 +1154,7 @@ static int coverage_sorted(abw_ctx* ctx, const abw_segments* g, const abw_read* 
 	ABW_CUDA(ctx, vals_tmp.alloc(npairs));
 	if(npairs) {
 		if(only)
-			ABW_LAUNCH(ctx, k_cov_emit_flagged, ntiles, COV_THREADS, 0, rd, hit_g0, hit_cnt, only, g->seg_start.p, g->seg_end.p, tile_offs.p, keys.p, vals.p);
+			ABW_LAUNCH(ctx, k_cov_emit_flagged, ntiles, COV_THREADS, 0, rd, hit_g0, hit_cnt, ngroups, only, g->seg_start.p, g->seg_end.p, tile_offs.p, keys.p, vals.p);
 		else
 			ABW_LAUNCH(ctx, k_cov_emit, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, tile_offs.p, keys.p, vals.p);
 		int nbits = 1;
@@ -1063,10 +1165,12 @@ static int coverage_sorted(abw_ctx* ctx, const abw_segments* g, const abw_read* 
 		ABW_LAUNCH(ctx, k_cov_runs, abw_div_up(npairs, 256), 256, 0, keys.p, npairs, run.p);
 	}
 	if(g->nseg && (npairs || !only)) {
-		if(kind == ABW_FEAT_TRUNC3)
-			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_TRUNC3>, abw_div_up(g->nseg, 64), 64, 0, vals.p, run.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col, only);
+		if(kind == ABW_FEAT_TRUNC3 && only)
+			ABW_LAUNCH(ctx, (k_cov_accumulate<ABW_FEAT_TRUNC3, 32>), abw_div_up(g->nseg, 64), 64, 0, vals.p, run.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col, only);
+		else if(kind == ABW_FEAT_TRUNC3)
+			ABW_LAUNCH(ctx, (k_cov_accumulate<ABW_FEAT_TRUNC3, 8>), abw_div_up(g->nseg, 64), 64, 0, vals.p, run.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col, only);
 		else
-			ABW_LAUNCH(ctx, k_cov_accumulate<ABW_FEAT_RAW>, abw_div_up(g->nseg, 64), 64, 0, vals.p, run.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col, only);
+			ABW_LAUNCH(ctx, (k_cov_accumulate<ABW_FEAT_RAW, 8>), abw_div_up(g->nseg, 64), 64, 0, vals.p, run.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col, only);
 	}
 	return ABW_OK;
 }
@@ -1093,13 +1197,13 @@ int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uin
 	bool too_many_windows = false;
 	if(kind == ABW_FEAT_TRUNC3 && !sort_all && nreads && g->nseg) {
 		DevBuf<unsigned long long> sum_ov;
-		DevBuf<uint8_t> flag;
+		DevBuf<uint32_t> flag;                             // one bit per window
 		DevBuf<uint4> hit_g0;
 		DevBuf<uchar4> hit_cnt;
 		DevBuf<uint32_t> status;
 		const unsigned int ntiles = abw_div_up(nreads, COV_TILE);
 		ABW_CUDA(ctx, sum_ov.alloc(g->nseg));
-		ABW_CUDA(ctx, flag.alloc(g->nseg));
+		ABW_CUDA(ctx, flag.alloc((g->nseg + 31) / 32));
 		ABW_CUDA(ctx, hit_g0.alloc((size_t)ntiles * COV_THREADS));
 		ABW_CUDA(ctx, hit_cnt.alloc((size_t)ntiles * COV_THREADS));
 		ABW_CUDA(ctx, status.alloc(1));
@@ -1114,7 +1218,10 @@ int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uin
 	}
 	else
 		ABW_CHECK(coverage_sorted(ctx, g, rd, nreads, max_snps, kind, d_rows, ld, col, d_scaf_nbps, nullptr, nullptr, nullptr, nullptr, &too_many_windows));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	// results stay on the device and every later entry point works in the order of the context stream: only a host buffer of reads has to be
+	// released by the time the call returns
+	if(!reads_on_device)
+		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return ABW_OK;
 }
 

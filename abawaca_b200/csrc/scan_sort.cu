@@ -253,13 +253,22 @@ int radix_pass(abw_ctx* ctx, const K* src_k, const uint32_t* src_v, K* dst_k, ui
 }
 
 template <typename K>
-int radix_sort_impl(abw_ctx* ctx, K* d_keys, K* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, uint32_t batch, uint64_t stride, int nbits)
+int radix_sort_impl(abw_ctx* ctx, K* d_keys, K* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, uint32_t batch, uint64_t stride, int nbits,
+                    const unsigned long long* known_varying = nullptr)
 {
 	if(n == 0 || batch == 0 || nbits == 0)
 		return ABW_OK;
 	unsigned int nblocks = abw_div_up(n, RS_TILE);
 	unsigned long long varying;
-	if(nbits < 0) {
+	if(known_varying) {
+		// the caller looked at the keys while it made them
+		varying = *known_varying;
+		if(nbits > 0 && nbits < 64)
+			varying &= (1ull << nbits) - 1ull;
+		if(varying == 0)
+			return ABW_OK;                                  // all keys equal: already sorted (stable)
+	}
+	else if(nbits < 0) {
 		// the caller knows that every key bit below -nbits varies (dense ids): no inspection pass, no host round trip
 		nbits = -nbits;
 		varying = (nbits < 64)? ((1ull << nbits) - 1ull) : ~0ull;
@@ -350,4 +359,10 @@ int abw_radix_sort_pairs_u32(abw_ctx* ctx, uint32_t* d_keys, uint32_t* d_keys_tm
                              uint64_t stride, int nbits)
 {
 	return radix_sort_impl<uint32_t>(ctx, d_keys, d_keys_tmp, d_vals, d_vals_tmp, n, batch, stride, nbits);
+}
+
+int abw_radix_sort_pairs_u32_varying(abw_ctx* ctx, uint32_t* d_keys, uint32_t* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, uint32_t batch,
+                                     uint64_t stride, unsigned long long varying)
+{
+	return radix_sort_impl<uint32_t>(ctx, d_keys, d_keys_tmp, d_vals, d_vals_tmp, n, batch, stride, 32, &varying);
 }

@@ -1367,21 +1367,53 @@ __global__ void k_make_keys(const double* __restrict__ values, uint64_t N, uint3
 	}
 }
 
+__global__ void k_fill_or_and(uint32_t* __restrict__ or_and, uint32_t nd)
+{
+	const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+	if(d < nd) {
+		or_and[2 * d] = 0u;
+		or_and[2 * d + 1] = ~0u;
+	}
+}
+
 // Columns written by abawaca-build hold multiples of 0.001 (int(1000*x)/1000.0, abawaca-build.cpp:603).  When every value v of the chunk
 // satisfies v == (double)k / 1000.0 for the integer k = rint(1000*v), |k| < 2^31, ordering by k is ordering by v (ties included) and the
 // sort runs on 32-bit keys with few significant bits.  Any other value sets `inexact` and the chunk falls back to the 64-bit keys.
-__global__ void k_make_keys_milli(const double* __restrict__ values, uint64_t N, uint32_t nd, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ inexact)
+// or_and[2 d], or_and[2 d + 1] (preset to 0 and ~0): OR and AND of the keys of dimension d, so that the sort knows which key bits differ at all
+// without another pass over the keys.
+__global__ void __launch_bounds__(256) k_make_keys_milli(const double* __restrict__ values, uint64_t N, uint32_t nd, uint32_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ vals, int* __restrict__ inexact, uint32_t* __restrict__ or_and)
 {
+	__shared__ uint32_t sm_or[8], sm_and[8];
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t d = blockIdx.y;
+	uint32_t key_or = 0u, key_and = ~0u;
 	if(i < N && d < nd) {
 		const double v = values[(uint64_t)d * N + i];
 		const double k = rint(__dmul_rn(v, 1000.0));
 		bool ok = (k > -2147483000.0) && (k < 2147483000.0) && (__ddiv_rn(k, 1000.0) == v);
 		if(!ok)
 			atomicExch(inexact, 1);
-		keys[(uint64_t)d * N + i] = ok? (uint32_t)((long long)k + 2147483648ll) : 0u;
+		const uint32_t key = ok? (uint32_t)((long long)k + 2147483648ll) : 0u;
+		keys[(uint64_t)d * N + i] = key;
 		vals[(uint64_t)d * N + i] = (uint32_t)i;
+		key_or = key_and = key;
+	}
+	key_or = __reduce_or_sync(0xffffffffu, key_or);
+	key_and = __reduce_and_sync(0xffffffffu, key_and);
+	if((threadIdx.x & 31) == 0) {
+		sm_or[threadIdx.x >> 5] = key_or;
+		sm_and[threadIdx.x >> 5] = key_and;
+	}
+	__syncthreads();
+	if(threadIdx.x == 0 && d < nd) {
+#pragma unroll
+		for(int w = 1; w < 8; w++) {
+			key_or |= sm_or[w];
+			key_and &= sm_and[w];
+		}
+		atomicOr(&or_and[2 * d], key_or);
+		atomicAnd(&or_and[2 * d + 1], key_and);
 	}
 }
 
@@ -1845,6 +1877,9 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	DevBuf<uint8_t> cls;
 	DevBuf<int> nan_flag, inexact;
 	ABW_CUDA(ctx, inexact.alloc(1));
+	DevBuf<uint32_t> or_and;
+	std::vector<uint32_t> h_or_and;
+	ABW_CUDA(ctx, or_and.alloc((size_t)2 * chunk));
 	ABW_CUDA(ctx, keys.alloc((size_t)chunk * N));
 	ABW_CUDA(ctx, keys_tmp.alloc((size_t)chunk * N));
 	ABW_CUDA(ctx, vals.alloc((size_t)chunk * N));
@@ -1861,13 +1896,21 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		uint32_t* keys32 = reinterpret_cast<uint32_t*>(keys.p);
 		uint32_t* keys32_tmp = reinterpret_cast<uint32_t*>(keys_tmp.p);
 		ABW_CUDA(ctx, cudaMemsetAsync(inexact.p, 0, sizeof(int), ctx->stream));
-		ABW_LAUNCH(ctx, k_make_keys_milli, grid, 256, 0, vchunk, N, nd, keys32, vals.p, inexact.p);
+		ABW_LAUNCH(ctx, k_fill_or_and, abw_div_up(nd, 256), 256, 0, or_and.p, nd);
+		ABW_LAUNCH(ctx, k_make_keys_milli, grid, 256, 0, vchunk, N, nd, keys32, vals.p, inexact.p, or_and.p);
 		int h_inexact = 0;
+		h_or_and.resize((size_t)2 * nd);
 		ABW_CUDA(ctx, cudaMemcpyAsync(&h_inexact, inexact.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, cudaMemcpyAsync(h_or_and.data(), or_and.p, sizeof(uint32_t) * 2 * nd, cudaMemcpyDeviceToHost, ctx->stream));
 		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		uint32_t all_or = 0u, all_and = ~0u;                  // over all dimensions of the chunk: one digit plan for the batch
+		for(uint32_t d = 0; d < nd; d++) {
+			all_or |= h_or_and[2 * d];
+			all_and &= h_or_and[2 * d + 1];
+		}
 		uint32_t* fp = (s->strategy == ABW_SENS_SPEC && K > 0)? flip_pos.p + (uint64_t)d0 * K : nullptr;
 		if(!h_inexact) {
-			ABW_CHECK(abw_radix_sort_pairs_u32(ctx, keys32, keys32_tmp, vals.p, vals_tmp.p, N, nd, N, 32));
+			ABW_CHECK(abw_radix_sort_pairs_u32_varying(ctx, keys32, keys32_tmp, vals.p, vals_tmp.p, N, nd, N, (unsigned long long)(all_or ^ all_and)));
 			ABW_LAUNCH(ctx, k_pack_elements<uint32_t>, grid, 256, 0, keys32, vals.p, N, nd, s->dp2scaf.p, cls.p, s->E[0].p + (uint64_t)d0 * N, d_scg_index.p, fp, K);
 		}
 		else {
@@ -1911,7 +1954,8 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		int nbits = 1;
 		while(nbits < 32 && (1ull << nbits) < N)
 			nbits++;
-		ABW_CHECK(abw_radix_sort_pairs_u64(ctx, (uint64_t*)lk.p, (uint64_t*)lk_tmp.p, s->scg_list[0].p, lv_tmp.p, K, D, K, nbits));
+		// positions spread over [0, N): every bit below nbits is taken as varying, which saves the inspection pass and its host round trip
+		ABW_CHECK(abw_radix_sort_pairs_u64(ctx, (uint64_t*)lk.p, (uint64_t*)lk_tmp.p, s->scg_list[0].p, lv_tmp.p, K, D, K, -nbits));
 	}
 	tr.mark("SCG lists");
 	// ---- root cluster (its scaffold list 0..S-1 was written by k_tab_scaffolds)

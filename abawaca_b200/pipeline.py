@@ -252,6 +252,22 @@ def search_problem_from_counts(counts):
     return keep_rows, dp2scaf, T, kept
 
 
+def search_rows_from_counts(counts):
+    """The same problem in the form abw_search_create derives the rest from: (row_of_dp or None, T, kept_scaffolds or None, N).
+    Scaffolds with fewer than two windows are dropped (quirk Q1); row_of_dp lists the matrix rows that remain (None: all of them) and
+    dp2scaf is left to the library (datapoints of a scaffold are consecutive)."""
+    counts = np.asarray(counts, dtype=np.int64)
+    drop = counts < 2
+    if not drop.any():
+        return None, counts.astype(np.uint32), None, int(counts.sum())
+    kept = np.flatnonzero(~drop)
+    end = np.cumsum(counts)
+    mask = np.ones(int(end[-1]), dtype=bool)
+    mask[(end - counts)[counts == 1]] = False              # the single row of every dropped scaffold
+    row_of_dp = np.flatnonzero(mask).view(np.uint64)       # int64 >= 0: the same bits
+    return row_of_dp, counts[kept].astype(np.uint32), kept, int(row_of_dp.size)
+
+
 def search_problem_from_features(seg_scaf, nscaf):
     """ScafDpData.cpp:91-99: drop scaffolds with exactly one datapoint (quirk Q1), renumber the rest in order.
 

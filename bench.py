@@ -286,7 +286,10 @@ def main():
         # ScafDpData.cpp:92-93: scaffolds with a single window are dropped
         counts = np.diff(seg_first.astype(np.int64))
         if world == 1:
-            keep, dp2scaf, T, kept = pipeline.search_problem_from_counts(counts)
+            # rows that stay (None: all), windows per kept scaffold; dp2scaf is derived on the device from T
+            row_of_dp, T, kept, ndps_total = pipeline.search_rows_from_counts(counts)
+            if kept is None:
+                kept = slice(None)
         else:                                          # the global tables are derived from all ranks' window counts further down
             keep = np.repeat(counts >= 2, counts) if (counts < 2).any() else np.ones(int(counts.sum()), dtype=bool)
         if timings is not None:
@@ -298,11 +301,9 @@ def main():
                 state["h_rows"] = torch.empty(int(fb.nseg * fb.ncols * 1.05) + 1024, dtype=torch.float64).pin_memory()
             fb.rows_host(out=state["h_rows"].numpy(), wait=False)
         if world == 1:
-            row_of_dp = None if keep.all() else np.nonzero(keep)[0].astype(np.uint64)   # scaffolds with one window are dropped (ScafDpData.cpp:92-93)
-            res = pipeline.search(ctx, fb.d_rows, dp2scaf, T, lengths[kept], masks[kept], layout=capi.LAYOUT_ROWMAJOR, values_on_device=True,
+            res = pipeline.search(ctx, fb.d_rows, None, T, lengths[kept], masks[kept], layout=capi.LAYOUT_ROWMAJOR, values_on_device=True,
                                   nrows=fb.nseg, D=fb.ncols, ld=fb.ncols, row_of_dp=row_of_dp, timings=timings, buffers=result_buffers)
-            nbins = int(np.count_nonzero(np.unique(res.scaf2cluster)))
-            ndps_total = int(keep.sum())
+            nbins = int(np.count_nonzero(np.bincount(res.scaf2cluster)[1:]))
         else:
             # 1) windows per scaffold of every rank (the only per-scaffold quantity this step computed; lengths and SCG masks of all ranks were
             #    exchanged once at set-up): everybody derives the same global scaffold table, scaffold ids rank-major
@@ -335,7 +336,7 @@ def main():
             res = pipeline.search(ctx, full.data_ptr(), None, T_all, lengths_all[keep_all], masks_all[keep_all],
                                   layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=int(full.shape[0]), D=cnt, ld=cnt, timings=timings,
                                   collectives=coll, dim_offset=off, D_total=fb.ncols, buffers=result_buffers)
-            nbins = int(np.count_nonzero(np.unique(res.scaf2cluster)))
+            nbins = int(np.count_nonzero(np.bincount(res.scaf2cluster)[1:]))
             ndps_total = int(full.shape[0])
             del full
         if not resident:
@@ -398,6 +399,19 @@ def main():
     for _ in range(max(1, args.warmup)):               # warm the host-buffer path (staging buffers enter the context's block cache)
         step(False)
     ms_e2e, _, steps_e2e = timed(False, args.steps)
+
+    # what the host link gives on this box: the end-to-end step moves h2d_bytes_per_step over it (pinned read records of one sample, best of 3)
+    pcie = None
+    if h_reads and h_reads[0].numel():
+        dst = torch.empty_like(h_reads[0], device=dev)
+        best = None
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); dst.copy_(h_reads[0], non_blocking=True); b.record(); b.synchronize()
+            best = a.elapsed_time(b) if best is None else min(best, a.elapsed_time(b))
+        nb = h_reads[0].numel() * h_reads[0].element_size()
+        pcie = {"h2d_GBps": round(nb / best / 1e6, 2), "bytes": int(nb)}
+        del dst
 
     # one extra profiled step: per-kernel CUDA-event durations (launches serialised while profiling)
     phase_ms = {}
@@ -467,7 +481,7 @@ def main():
                        "clusters_evaluated": state["nclusters"], "bins": bins_total, "search_levels": prof.levels, "datapoints": state["ndps"],
                        "nccl": None if coll is None else {"search_collectives": type(coll).__name__, "callback_collectives_total": coll.calls, "callback_bytes_total": coll.bytes}},
             "e2e": {"value": round(e2e_value, 2), "unit": "scaffolds/s", "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches), "step_ms": {"resident": steps_res, "e2e": steps_e2e,
+            "pcie": pcie, "gpu_launches": int(launches), "step_ms": {"resident": steps_res, "e2e": steps_e2e,
                                                      "host_ms_and_driver_allocations": {"resident": state.get("host_ms_and_driver_allocations_resident"),
                                                                                         "e2e": state.get("host_ms_and_driver_allocations_e2e")}}, "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "phase_wall_ms": {k: round(v, 3) for k, v in phase_ms.items()},

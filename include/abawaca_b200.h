@@ -109,7 +109,9 @@ int abw_kmer_features(abw_ctx* ctx, const abw_seqset* s, const abw_segments* g, 
 
 /* Replaces the SAM loop body abawaca-build.cpp:546-551 with Scaf::add_mapped_read (:231-244) and
  * Scaf_segment::add_mapped_read (:177-185) for ONE sample: reads in SAM order.  Writes column `col` of `rows`.
- * d_scaf_nbps (may be NULL): per scaffold sum of accepted read lengths (the -c sample, :242-243), uint64 [nscaf]. */
+ * d_scaf_nbps (may be NULL): per scaffold sum of accepted read lengths (the -c sample, :242-243), uint64 [nscaf].
+ * With reads_on_device != 0 the call returns once the work is enqueued on the context stream (like every entry point, later calls on the
+ * same context see its results; a host that reads d_rows through its own stream calls abw_ctx_synchronize first). */
 int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uint64_t nreads, int reads_on_device, uint32_t max_snps,
                  int kind, double* d_rows, uint64_t ld, uint32_t col, uint64_t* d_scaf_nbps);
 

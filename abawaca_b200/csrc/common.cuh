@@ -28,6 +28,11 @@ struct abw_ctx {
 	unsigned char* h_stage = nullptr;
 	size_t stage_half = 0, stage_used = 0;
 	int stage_side = 0;
+	// small device->host results fetched by a kernel into mapped pinned memory instead of through the copy engine (abw_fetch, abw_sync)
+	struct Fetch { void* h_dst; const unsigned char* slot; size_t bytes; };
+	unsigned char* h_bounce = nullptr;
+	size_t bounce_cap = 0, bounce_used = 0;
+	std::vector<Fetch> pending;
 };
 
 // Small uploads (descriptors, job lists, tile tables) go through pinned memory so that cudaMemcpyAsync really is asynchronous.
@@ -35,6 +40,20 @@ struct abw_ctx {
 // (the split search synchronises at least once per level and flips once per level).
 void abw_stage_flip(abw_ctx* ctx);
 cudaError_t abw_stage_upload(abw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+
+// Small transfers and the copy engines.  Copies of one direction execute in the order they were issued, whatever their stream: an 8-byte
+// cudaMemcpyAsync on the compute stream waits for every bulk copy (read records in, .lrn matrix out) that was enqueued before it on the copy
+// stream, and the kernels behind it wait too -- measured: end-to-end step = H2D + resident step + D2H, no overlap at all.
+// With ABW_SMALL_COPIES=kernel the small transfers bypass the engines: abw_stage_upload lets a kernel read the pinned staging slot, and
+// abw_fetch lets a kernel write the result into mapped pinned memory, from where abw_sync (cudaStreamSynchronize + copy-out) hands it to the
+// caller's buffer.  Default (unset): plain cudaMemcpyAsync, as before.  Every device->host result of an entry point is requested with
+// abw_fetch and every wait on the context stream is abw_sync; ABW_ENTER drops requests an earlier, failed call may have left behind.
+bool abw_small_copies_by_kernel();
+cudaError_t abw_fetch(abw_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+cudaError_t abw_sync(abw_ctx* ctx);
+// host->device upload of a small array on the context stream: cudaMemcpyAsync by default, through the pinned staging area and a kernel with
+// ABW_SMALL_COPIES=kernel (the caller waits for the stream before it changes h_src or returns)
+cudaError_t abw_upload_small(abw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 
 inline int abw_fail(abw_ctx* ctx, int code, const std::string& msg)
 {
@@ -91,6 +110,8 @@ void abw_arena_free(abw_ctx* ctx, void* p);
 	do {                                                                                                             \
 		ABW_CUDA((ctx), cudaSetDevice((ctx)->device));                                                               \
 		abw_tls_ctx = (ctx);                                                                                         \
+		(ctx)->pending.clear();                                                                                      \
+		(ctx)->bounce_used = 0;                                                                                      \
 	} while(0)
 
 template <typename T>

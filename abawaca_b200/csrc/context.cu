@@ -56,6 +56,72 @@ void abw_stage_flip(abw_ctx* ctx)
 	ctx->stage_used = 0;
 }
 
+bool abw_small_copies_by_kernel()
+{
+	static const bool on = [] { const char* e = getenv("ABW_SMALL_COPIES"); return e && strcmp(e, "kernel") == 0; }();
+	return on;
+}
+
+// bytes from src to dst, one of them mapped pinned host memory; word-wise when both are 4-byte aligned
+__global__ void k_copy_small(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, size_t bytes)
+{
+	const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+	if(((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 3u) == 0) {
+		const size_t words = bytes >> 2;
+		for(size_t i = i0; i < words; i += stride)
+			reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+		for(size_t i = (words << 2) + i0; i < bytes; i += stride)
+			dst[i] = src[i];
+	}
+	else {
+		for(size_t i = i0; i < bytes; i += stride)
+			dst[i] = src[i];
+	}
+}
+
+static cudaError_t copy_small(abw_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+	const unsigned int blocks = (unsigned int)std::min<size_t>(64, (bytes / 4 + 255) / 256 + 1);
+	k_copy_small<<<blocks, 256, 0, ctx->stream>>>((unsigned char*)dst, (const unsigned char*)src, bytes);
+	ctx->launches++;
+	return cudaGetLastError();
+}
+
+cudaError_t abw_fetch(abw_ctx* ctx, void* h_dst, const void* d_src, size_t bytes)
+{
+	if(bytes == 0)
+		return cudaSuccess;
+	if(abw_small_copies_by_kernel() && bytes <= ((size_t)256 << 10)) {
+		if(!ctx->h_bounce) {
+			ctx->bounce_cap = (size_t)2 << 20;
+			if(cudaHostAlloc((void**)&ctx->h_bounce, ctx->bounce_cap, cudaHostAllocMapped) != cudaSuccess) {
+				cudaGetLastError();
+				ctx->h_bounce = nullptr;
+				ctx->bounce_cap = 0;
+			}
+		}
+		const size_t need = (bytes + 255) & ~(size_t)255;
+		if(ctx->h_bounce && ctx->bounce_used + need <= ctx->bounce_cap) {
+			unsigned char* slot = ctx->h_bounce + ctx->bounce_used;
+			ctx->bounce_used += need;
+			ctx->pending.push_back({h_dst, slot, bytes});
+			return copy_small(ctx, slot, d_src, bytes);
+		}
+	}
+	return cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+}
+
+cudaError_t abw_sync(abw_ctx* ctx)
+{
+	const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+	if(e == cudaSuccess)
+		for(const abw_ctx::Fetch& f : ctx->pending)
+			memcpy(f.h_dst, f.slot, f.bytes);
+	ctx->pending.clear();
+	ctx->bounce_used = 0;
+	return e;
+}
+
 cudaError_t abw_stage_upload(abw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes)
 {
 	if(bytes == 0)
@@ -73,9 +139,20 @@ cudaError_t abw_stage_upload(abw_ctx* ctx, void* d_dst, const void* h_src, size_
 		unsigned char* slot = ctx->h_stage + (size_t)ctx->stage_side * ctx->stage_half + ctx->stage_used;
 		memcpy(slot, h_src, bytes);
 		ctx->stage_used += need;
+		if(abw_small_copies_by_kernel())
+			return copy_small(ctx, d_dst, slot, bytes);        // pinned memory is mapped into the device's address space (unified addressing)
 		return cudaMemcpyAsync(d_dst, slot, bytes, cudaMemcpyHostToDevice, ctx->stream);
 	}
 	return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream);      // too large for the staging half: the driver stages it
+}
+
+cudaError_t abw_upload_small(abw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes)
+{
+	if(bytes == 0)
+		return cudaSuccess;
+	if(abw_small_copies_by_kernel())
+		return abw_stage_upload(ctx, d_dst, h_src, bytes);     // falls back to cudaMemcpyAsync when the staging half is full
+	return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream);
 }
 
 void abw_arena_free(abw_ctx* ctx, void* p)
@@ -173,6 +250,9 @@ void abw_ctx_destroy(abw_ctx* ctx)
 	if(ctx->h_stage)
 		cudaFreeHost(ctx->h_stage);
 	ctx->h_stage = nullptr;
+	if(ctx->h_bounce)
+		cudaFreeHost(ctx->h_bounce);
+	ctx->h_bounce = nullptr;
 	for(cudaEvent_t e : ctx->copy_events)
 		cudaEventDestroy(e);
 	if(ctx->copy_stream)

@@ -971,12 +971,14 @@ static int pack_impl(abw_ctx* ctx, abw_seqset* s, const char* ascii, int ascii_o
 		src = d_ascii.p;
 		readable = bytes + 64;
 	}
+	if(abw_small_copies_by_kernel())
+		abw_stage_flip(ctx);                                   // this call waits for the stream before it returns: the half used two flips ago is free
 	ABW_CUDA(ctx, d_off.alloc((size_t)nscaf + 1));
-	ABW_CUDA(ctx, cudaMemcpyAsync(d_off.p, h_offsets, sizeof(uint64_t) * ((size_t)nscaf + 1), cudaMemcpyHostToDevice, ctx->stream));
+	ABW_CUDA(ctx, abw_upload_small(ctx, d_off.p, h_offsets, sizeof(uint64_t) * ((size_t)nscaf + 1)));
 	ABW_CUDA(ctx, s->len.alloc(nscaf));
 	ABW_CUDA(ctx, s->base.alloc((size_t)nscaf + 1));
-	ABW_CUDA(ctx, cudaMemcpyAsync(s->len.p, s->h_len.data(), sizeof(uint64_t) * nscaf, cudaMemcpyHostToDevice, ctx->stream));
-	ABW_CUDA(ctx, cudaMemcpyAsync(s->base.p, s->h_base.data(), sizeof(uint64_t) * ((size_t)nscaf + 1), cudaMemcpyHostToDevice, ctx->stream));
+	ABW_CUDA(ctx, abw_upload_small(ctx, s->len.p, s->h_len.data(), sizeof(uint64_t) * nscaf));
+	ABW_CUDA(ctx, abw_upload_small(ctx, s->base.p, s->h_base.data(), sizeof(uint64_t) * ((size_t)nscaf + 1)));
 	// + slack so that the k-mer kernel may read one word past a segment
 	ABW_CUDA(ctx, s->packed.alloc(b / 16 + 16));
 	ABW_CUDA(ctx, s->valid.alloc(b / 32 + 16));
@@ -993,8 +995,8 @@ static int pack_impl(abw_ctx* ctx, abw_seqset* s, const char* ascii, int ascii_o
 		ABW_LAUNCH(ctx, k_pack, blocks, 256, 0, src, readable, d_off.p, s->base.p, nscaf, s->packed.p, s->valid.p, s->nmask.p, s->countN.p, s->countGC.p, d_err.p);
 	}
 	int h_err = 0;
-	ABW_CUDA(ctx, cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ABW_CUDA(ctx, abw_fetch(ctx, &h_err, d_err.p, sizeof(int)));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	if(h_err)
 		return abw_fail(ctx, ABW_ERR_ILLEGAL_DNA, "Illegal_DNAString: lower-case 'n' in a sequence (String.cpp:47-49)");
 	return ABW_OK;
@@ -1022,10 +1024,10 @@ int abw_seqset_stats(abw_ctx* ctx, const abw_seqset* s, uint64_t* h_count_N, uin
 	if(!ctx || !s)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_seqset_stats: null argument");
 	if(h_count_N)
-		ABW_CUDA(ctx, cudaMemcpyAsync(h_count_N, s->countN.p, sizeof(uint64_t) * s->nscaf, cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, h_count_N, s->countN.p, sizeof(uint64_t) * s->nscaf));
 	if(h_count_GC)
-		ABW_CUDA(ctx, cudaMemcpyAsync(h_count_GC, s->countGC.p, sizeof(uint64_t) * s->nscaf, cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, h_count_GC, s->countGC.p, sizeof(uint64_t) * s->nscaf));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	return ABW_OK;
 }
 
@@ -1044,9 +1046,9 @@ int abw_segment(abw_ctx* ctx, const abw_seqset* s, uint32_t window_size, abw_seg
 		if(s->nscaf > 0)
 			ABW_LAUNCH(ctx, k_seg_count, abw_div_up(s->nscaf, 256), 256, 0, s->len.p, s->countN.p, s->nscaf, (uint64_t)window_size, counts.p);
 		ABW_CHECK(abw_exclusive_scan_u64(ctx, counts.p, g->seg_first.p, s->nscaf, total.p));
-		ABW_CUDA(ctx, cudaMemcpyAsync(&g->nseg, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-		ABW_CUDA(ctx, cudaMemcpyAsync(g->seg_first.p + s->nscaf, &g->nseg, sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, &g->nseg, total.p, sizeof(uint64_t)));
+		ABW_CUDA(ctx, abw_sync(ctx));
+		ABW_CUDA(ctx, abw_upload_small(ctx, g->seg_first.p + s->nscaf, &g->nseg, sizeof(uint64_t)));
 		ABW_CUDA(ctx, g->seg_scaf.alloc(g->nseg));
 		ABW_CUDA(ctx, g->seg_start.alloc(g->nseg));
 		ABW_CUDA(ctx, g->seg_end.alloc(g->nseg));
@@ -1059,7 +1061,7 @@ int abw_segment(abw_ctx* ctx, const abw_seqset* s, uint32_t window_size, abw_seg
 			ABW_LAUNCH(ctx, k_seg_fill, blocks, 256, 0, s->len.p, s->countN.p, s->base.p, s->nmask.p, s->nscaf, (uint64_t)window_size, g->seg_first.p,
 			           g->seg_scaf.p, g->seg_start.p, g->seg_end.p, g->seg_nonN.p, g->seg_gbase.p, g->scaf_info.p);
 		}
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_sync(ctx));
 		return ABW_OK;
 	}();
 	if(rc != ABW_OK) {
@@ -1079,16 +1081,16 @@ int abw_segments_get(abw_ctx* ctx, const abw_segments* g, uint64_t* h_seg_first,
 	if(!ctx || !g)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_segments_get: null argument");
 	if(h_seg_first)
-		ABW_CUDA(ctx, cudaMemcpyAsync(h_seg_first, g->seg_first.p, sizeof(uint64_t) * ((size_t)g->nscaf + 1), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, h_seg_first, g->seg_first.p, sizeof(uint64_t) * ((size_t)g->nscaf + 1)));
 	if(h_seg_scaf)
-		ABW_CUDA(ctx, cudaMemcpyAsync(h_seg_scaf, g->seg_scaf.p, sizeof(uint32_t) * g->nseg, cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, h_seg_scaf, g->seg_scaf.p, sizeof(uint32_t) * g->nseg));
 	if(h_seg_start)
-		ABW_CUDA(ctx, cudaMemcpyAsync(h_seg_start, g->seg_start.p, sizeof(uint64_t) * g->nseg, cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, h_seg_start, g->seg_start.p, sizeof(uint64_t) * g->nseg));
 	if(h_seg_end)
-		ABW_CUDA(ctx, cudaMemcpyAsync(h_seg_end, g->seg_end.p, sizeof(uint64_t) * g->nseg, cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, h_seg_end, g->seg_end.p, sizeof(uint64_t) * g->nseg));
 	if(h_seg_nonN)
-		ABW_CUDA(ctx, cudaMemcpyAsync(h_seg_nonN, g->seg_nonN.p, sizeof(uint64_t) * g->nseg, cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, h_seg_nonN, g->seg_nonN.p, sizeof(uint64_t) * g->nseg));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	return ABW_OK;
 }
 
@@ -1137,10 +1139,10 @@ static int coverage_sorted(abw_ctx* ctx, const abw_segments* g, const abw_read* 
 			           (unsigned long long*)d_scaf_nbps);
 		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, tile_counts.p, tile_offs.p, ntiles, total.p));
 		uint32_t status = 0;
-		ABW_CUDA(ctx, cudaMemcpyAsync(&npairs, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, &npairs, total.p, sizeof(uint64_t)));
 		if(d_status)
-			ABW_CUDA(ctx, cudaMemcpyAsync(&status, d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			ABW_CUDA(ctx, abw_fetch(ctx, &status, d_status, sizeof(uint32_t)));
+		ABW_CUDA(ctx, abw_sync(ctx));
 		if(status & 1u) {
 			*too_many_windows = true;
 			return ABW_OK;
@@ -1221,7 +1223,7 @@ int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uin
 	// results stay on the device and every later entry point works in the order of the context stream: only a host buffer of reads has to be
 	// released by the time the call returns
 	if(!reads_on_device)
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_sync(ctx));
 	return ABW_OK;
 }
 

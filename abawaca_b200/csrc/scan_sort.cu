@@ -283,8 +283,8 @@ int radix_sort_impl(abw_ctx* ctx, K* d_keys, K* d_keys_tmp, uint32_t* d_vals, ui
 			ABW_LAUNCH(ctx, k_rs_or_and<K>, grid, RS_THREADS, 0, d_keys, n, stride, or_and.p);
 		}
 		unsigned long long oa[2];
-		ABW_CUDA(ctx, cudaMemcpyAsync(oa, or_and.p, sizeof(oa), cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, oa, or_and.p, sizeof(oa)));
+		ABW_CUDA(ctx, abw_sync(ctx));
 		varying = oa[0] ^ oa[1];
 		if(nbits < 64)
 			varying &= (1ull << nbits) - 1ull;

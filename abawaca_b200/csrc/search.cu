@@ -1788,8 +1788,8 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		// no dp2scaf: the matrix holds all T datapoints of every scaffold, in scaffold order
 		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, d_T.p, s->dp_first.p, S, s->dp_first.p + S));
 		uint64_t sumT = 0;
-		ABW_CUDA(ctx, cudaMemcpyAsync(&sumT, s->dp_first.p + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, &sumT, s->dp_first.p + S, sizeof(uint64_t)));
+		ABW_CUDA(ctx, abw_sync(ctx));
 		if(sumT != N)
 			return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: without dp2scaf the matrix must hold exactly sum(T) datapoints");
 		ABW_LAUNCH(ctx, k_tab_fill_dp2scaf, abw_div_up(S, 256), 256, 0, s->dp_first.p, S, N, s->dp2scaf.p);
@@ -1799,9 +1799,9 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, d_scg_flag.p, d_scg_before.p, S, d_total.p));
 	RootStats h_rs;
 	uint64_t h_K = 0;
-	ABW_CUDA(ctx, cudaMemcpyAsync(&h_rs, d_rs.p, sizeof(RootStats), cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaMemcpyAsync(&h_K, d_total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ABW_CUDA(ctx, abw_fetch(ctx, &h_rs, d_rs.p, sizeof(RootStats)));
+	ABW_CUDA(ctx, abw_fetch(ctx, &h_K, d_total.p, sizeof(uint64_t)));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	if(h_rs.err & TB_ERR_RANGE)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: dp2scaf entry out of range");
 	if(h_rs.err & TB_ERR_ORDER)
@@ -1857,7 +1857,7 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 				ABW_LAUNCH(ctx, k_gather_columns, grid, 256, 0, src, ld, N, (const uint64_t*)d_rowidx.p, s->values.p);
 			}
 		}
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_sync(ctx));
 	}
 	tr.mark("values to column major");
 	// ---- per-dimension order, classes, elements; dimensions are processed in chunks to bound scratch memory
@@ -1900,9 +1900,9 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		ABW_LAUNCH(ctx, k_make_keys_milli, grid, 256, 0, vchunk, N, nd, keys32, vals.p, inexact.p, or_and.p);
 		int h_inexact = 0;
 		h_or_and.resize((size_t)2 * nd);
-		ABW_CUDA(ctx, cudaMemcpyAsync(&h_inexact, inexact.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaMemcpyAsync(h_or_and.data(), or_and.p, sizeof(uint32_t) * 2 * nd, cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, &h_inexact, inexact.p, sizeof(int)));
+		ABW_CUDA(ctx, abw_fetch(ctx, h_or_and.data(), or_and.p, sizeof(uint32_t) * 2 * nd));
+		ABW_CUDA(ctx, abw_sync(ctx));
 		uint32_t all_or = 0u, all_and = ~0u;                  // over all dimensions of the chunk: one digit plan for the batch
 		for(uint32_t d = 0; d < nd; d++) {
 			all_or |= h_or_and[2 * d];
@@ -1920,8 +1920,8 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		}
 	}
 	int h_nan = 0;
-	ABW_CUDA(ctx, cudaMemcpyAsync(&h_nan, nan_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ABW_CUDA(ctx, abw_fetch(ctx, &h_nan, nan_flag.p, sizeof(int)));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	if(h_nan)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: NaN in the feature matrix (comp_by_value is not a strict weak order on NaN)");
 	tr.mark("classes, sort, elements");
@@ -1967,7 +1967,7 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	ABW_CUDA(ctx, cudaMemsetAsync(s->low.p, 0, sizeof(uint32_t) * S, ctx->stream));
 	ABW_CUDA(ctx, cudaMemsetAsync(s->scaf_member.p, 0, sizeof(uint32_t) * S, ctx->stream));
 	ABW_CUDA(ctx, cudaMemsetAsync(s->scaf_final.p, 0, sizeof(uint32_t) * S, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	tr.mark("root cluster");
 	return ABW_OK;
 }
@@ -2021,12 +2021,12 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 		ABW_CUDA(ctx, d_all.alloc(2 * (size_t)world));
 		uint32_t mine[2] = {s->dim_offset, s->D};
 		ABW_CUDA(ctx, cudaMemcpyAsync(d_mine.p, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_sync(ctx));
 		if(coll->allgather(coll->user, d_mine.p, d_all.p, sizeof(mine)) != 0)
 			return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run_sharded: allgather callback failed");
 		std::vector<uint32_t> all(2 * (size_t)world);
-		ABW_CUDA(ctx, cudaMemcpyAsync(all.data(), d_all.p, sizeof(uint32_t) * all.size(), cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, all.data(), d_all.p, sizeof(uint32_t) * all.size()));
+		ABW_CUDA(ctx, abw_sync(ctx));
 		for(int r = 0; r < world; r++) {
 			shard_off[r] = all[2 * r];
 			shard_n[r] = all[2 * r + 1];
@@ -2208,20 +2208,20 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 		else
 			ABW_LAUNCH(ctx, k_reduce_best<ABW_SPLIT_SCAFS>, C, 256, 0, d_cand.p, TT, D, d_clusters.p, d_best.p);
 		std::vector<CandRec> best(C);
-		ABW_CUDA(ctx, cudaMemcpyAsync(best.data(), d_best.p, sizeof(CandRec) * C, cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, best.data(), d_best.p, sizeof(CandRec) * C));
+		ABW_CUDA(ctx, abw_sync(ctx));
 		for(uint32_t c = 0; c < C; c++)
 			best[c].dim0 += s->dim_offset;               // global dimension index from here on
 		if(coll) {
 			// gather the per-shard best of every cluster and apply the same total order on every rank
 			ABW_CUDA(ctx, cudaMemcpyAsync(d_best.p, best.data(), sizeof(CandRec) * C, cudaMemcpyHostToDevice, ctx->stream));
 			if(d_best_all.n < (size_t)C * world) ABW_CUDA(ctx, d_best_all.alloc((size_t)C * world));
-			ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			ABW_CUDA(ctx, abw_sync(ctx));
 			if(coll->allgather(coll->user, d_best.p, d_best_all.p, sizeof(CandRec) * C) != 0)
 				return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run_sharded: allgather callback failed");
 			std::vector<CandRec> all((size_t)C * world);
-			ABW_CUDA(ctx, cudaMemcpyAsync(all.data(), d_best_all.p, sizeof(CandRec) * all.size(), cudaMemcpyDeviceToHost, ctx->stream));
-			ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			ABW_CUDA(ctx, abw_fetch(ctx, all.data(), d_best_all.p, sizeof(CandRec) * all.size()));
+			ABW_CUDA(ctx, abw_sync(ctx));
 			for(uint32_t c = 0; c < C; c++) {
 				CandRec b = all[c];
 				for(int r = 1; r < world; r++)
@@ -2301,14 +2301,14 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 			}
 			if(coll) {
 				// every quantity is non-zero on exactly one rank (the owner of the winning dimension): a sum is a gather
-				ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+				ABW_CUDA(ctx, abw_sync(ctx));
 				if(coll->allreduce_sum_i64(coll->user, s->xchg.p, xwords) != 0)
 					return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run_sharded: allreduce callback failed");
 			}
-			ABW_CUDA(ctx, cudaMemcpyAsync(stats.data(), d_stats, sizeof(ChildStats) * J * 2, cudaMemcpyDeviceToHost, ctx->stream));
-			ABW_CUDA(ctx, cudaMemcpyAsync(vkeys.data(), d_value_key, sizeof(unsigned long long) * J, cudaMemcpyDeviceToHost, ctx->stream));
-			ABW_CUDA(ctx, cudaMemcpyAsync(child_never.data(), d_child_never, sizeof(uint64_t) * J * 2 * W, cudaMemcpyDeviceToHost, ctx->stream));
-			ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			ABW_CUDA(ctx, abw_fetch(ctx, stats.data(), d_stats, sizeof(ChildStats) * J * 2));
+			ABW_CUDA(ctx, abw_fetch(ctx, vkeys.data(), d_value_key, sizeof(unsigned long long) * J));
+			ABW_CUDA(ctx, abw_fetch(ctx, child_never.data(), d_child_never, sizeof(uint64_t) * J * 2 * W));
+			ABW_CUDA(ctx, abw_sync(ctx));
 		}
 		// decide
 		std::vector<HostCluster> next;
@@ -2416,11 +2416,11 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 			if(s->x_gc.p != nullptr) {
 				if(d_moments.n < (size_t)Tn * 4) ABW_CUDA(ctx, d_moments.alloc((size_t)Tn * 4));
 				ABW_LAUNCH(ctx, k_terminal_moments, abw_div_up(2 * Tn, 64), 64, 0, s->scaf_list[cur].p, d_tjobs.p, Tn, s->rows.p, s->assigned.p, s->x_gc.p, s->x_cvg.p, d_moments.p);
-				ABW_CUDA(ctx, cudaMemcpyAsync(mom.data(), d_moments.p, sizeof(double) * Tn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+				ABW_CUDA(ctx, abw_fetch(ctx, mom.data(), d_moments.p, sizeof(double) * Tn * 4));
 			}
-			ABW_CUDA(ctx, cudaMemcpyAsync(ts.data(), d_tstats.p, sizeof(TermStats) * Tn, cudaMemcpyDeviceToHost, ctx->stream));
-			ABW_CUDA(ctx, cudaMemcpyAsync(un.data(), d_union.p, sizeof(uint64_t) * Tn * W, cudaMemcpyDeviceToHost, ctx->stream));
-			ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			ABW_CUDA(ctx, abw_fetch(ctx, ts.data(), d_tstats.p, sizeof(TermStats) * Tn));
+			ABW_CUDA(ctx, abw_fetch(ctx, un.data(), d_union.p, sizeof(uint64_t) * Tn * W));
+			ABW_CUDA(ctx, abw_sync(ctx));
 			uint32_t t = 0;
 			for(uint32_t c = 0; c < C; c++) {
 				if(recs[c].split)
@@ -2526,21 +2526,21 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 		*nrecs = nrec;
 	{
 		int h_error = 0;
-		ABW_CUDA(ctx, cudaMemcpyAsync(&h_error, d_error.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, &h_error, d_error.p, sizeof(int)));
+		ABW_CUDA(ctx, abw_sync(ctx));
 		if(h_error)
 			return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run: internal error, a look-back wait timed out");
 	}
 	if(h_scaf2cluster)
-		ABW_CUDA(ctx, cudaMemcpyAsync(h_scaf2cluster, s->scaf_final.p, sizeof(uint32_t) * S, cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, h_scaf2cluster, s->scaf_final.p, sizeof(uint32_t) * S));
 	if(h_dp2cluster) {
 		DevBuf<uint32_t> d_dp;
 		ABW_CUDA(ctx, d_dp.alloc(N));
 		ABW_LAUNCH(ctx, k_dp_bins, abw_div_up(N, 256), 256, 0, s->dp2scaf.p, s->scaf_member.p, N, d_dp.p);
-		ABW_CUDA(ctx, cudaMemcpyAsync(h_dp2cluster, d_dp.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, h_dp2cluster, d_dp.p, sizeof(uint32_t) * N));
+		ABW_CUDA(ctx, abw_sync(ctx));
 	}
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	return ABW_OK;
 }
 
@@ -2606,7 +2606,7 @@ int abw_search_set_scaffold_stats(abw_ctx* ctx, abw_search* s, const double* h_g
 	ABW_CUDA(ctx, s->x_cvg.alloc(s->S));
 	ABW_CUDA(ctx, cudaMemcpyAsync(s->x_gc.p, h_gc, sizeof(double) * s->S, cudaMemcpyHostToDevice, ctx->stream));
 	ABW_CUDA(ctx, cudaMemcpyAsync(s->x_cvg.p, h_cvg, sizeof(double) * s->S, cudaMemcpyHostToDevice, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	return ABW_OK;
 }
 
@@ -2677,9 +2677,9 @@ int abw_cluster_scg(abw_ctx* ctx, const abw_search* s, const uint32_t* h_scafs, 
 		ABW_LAUNCH(ctx, k_finalize_terminal, dim3(abw_div_up(nscafs, 128), 1), 128, 0, d_list.p, d_job.p, s->rows.p, d_assigned.p, s->scgmask.p, s->W, d_member.p, d_final.p, d_st.p, d_un.p);
 	TermStats ts;
 	std::vector<uint64_t> un(s->W);
-	ABW_CUDA(ctx, cudaMemcpyAsync(&ts, d_st.p, sizeof(ts), cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaMemcpyAsync(un.data(), d_un.p, sizeof(uint64_t) * s->W, cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ABW_CUDA(ctx, abw_fetch(ctx, &ts, d_st.p, sizeof(ts)));
+	ABW_CUDA(ctx, abw_fetch(ctx, un.data(), d_un.p, sizeof(uint64_t) * s->W));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	uint32_t u = 0;
 	for(uint32_t w = 0; w < s->W; w++)
 		u += (uint32_t)__builtin_popcountll(un[w]);

@@ -59,3 +59,21 @@ def test_allgather_rows_gloo_world2(counts):
         p.join(timeout=60)
     expect = np.arange(sum(counts) * 5, dtype=np.float64).reshape(sum(counts), 5)
     assert np.array_equal(got[0], expect) and np.array_equal(got[1], expect)
+
+
+def test_search_rows_from_counts_matches_the_explicit_problem():
+    """pipeline.search_rows_from_counts (row index + T, dp2scaf left to the library) against search_problem_from_counts (explicit dp2scaf):
+    scaffolds with fewer than two windows are dropped (quirk Q1, ScafDpData.cpp:92-93)."""
+    from abawaca_b200 import pipeline
+    rng = np.random.default_rng(5)
+    for counts in (rng.integers(0, 7, 5000), rng.integers(2, 9, 300), np.array([1, 1, 5, 0, 2]), np.array([3])):
+        counts = counts.astype(np.int64)
+        keep, dp2scaf, T, kept = pipeline.search_problem_from_counts(counts)
+        rows, T2, kept2, n = pipeline.search_rows_from_counts(counts)
+        assert n == int(keep.sum()) and np.array_equal(T, T2)
+        if keep.all():
+            assert rows is None and kept2 is None
+        else:
+            assert rows.dtype == np.uint64 and np.array_equal(rows, np.nonzero(keep)[0]) and np.array_equal(kept, kept2)
+        # dp2scaf as the library derives it from T: datapoints of a scaffold are consecutive
+        assert np.array_equal(dp2scaf, np.repeat(np.arange(T.size, dtype=np.uint32), T))

@@ -5,6 +5,7 @@ Runs only where /root/reference was available to build oracle/_ref (the developm
 container).  The GPU box has neither, so tests read the fixtures written here:
 
   kat_*.json          known-answer vectors: hand-made FASTA/SAM edge cases -> reference outputs
+  kat_coverage_order  windows of round lengths: the order of the reads decides the third decimal of the coverage (quirk Q5)
   tiny_clean.*        400 scaffolds / 3 samples / 4 well separated genomes
   tiny_noisy.*        700 scaffolds / 4 samples / 14 similar genomes (imperfect scores, SCG filter active)
 
@@ -196,9 +197,58 @@ def make_kat():
     print("kat done")
 
 
+COVERAGE_ORDER_ARGS = dict(seed=11, nscaf=60, nsamples=2, depth=25, cover_all_n=True)
+
+
+def make_coverage_order():
+    """Round window lengths (2000, 2048, 2500, 3125 ...): for many windows 1000 * (sum of overlaps) / length is an integer, so the order in which
+    the reference adds fl(overlap / length) decides the third decimal (quirk Q5).  Inputs come from tests/golden_util.coverage_edge_workload;
+    the fixture keeps the reference's .lrn and its un-truncated coverage columns."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import coverage_edge_workload
+    seq, offsets, reads = coverage_edge_workload(**COVERAGE_ORDER_ARGS)
+    nscaf = offsets.size - 1
+    names = ["e%04d" % i for i in range(nscaf)]
+    with tempfile.TemporaryDirectory() as wd:
+        fa = os.path.join(wd, "assembly.fa")
+        with open(fa, "w") as f:
+            for i, n in enumerate(names):
+                s = seq[int(offsets[i]):int(offsets[i + 1])].tobytes().decode()
+                f.write(f">{n}\n")
+                for o in range(0, len(s), 80):
+                    f.write(s[o:o + 80] + "\n")
+        sams = []
+        for j, r in enumerate(reads):
+            path = os.path.join(wd, f"sample{j:02d}.sam")
+            with open(path, "w") as f:
+                f.write("@HD\tVN:1.0\n")
+                for k in range(r.size):
+                    sc, pos0, ln, fn = int(r["scaf"][k]), int(r["pos0"][k]), int(r["len"][k]), int(r["flag_nsnps"][k])
+                    flag, nsnps = fn & 0xFFFF, fn >> 16
+                    md = "MD:Z:" + "0C" * nsnps + str(ln - nsnps)
+                    f.write(f"q{k}/1\t{flag}\t{names[sc]}\t{pos0 + 1}\t42\t{ln}M\t*\t0\t0\t{'A' * ln}\t{'I' * ln}\t{md}\n")
+            sams.append(path)
+        build = os.path.join(wd, "build")
+        os.makedirs(build)
+        subprocess.run([os.path.join(REF, "abawaca-build"), "-f", fa, "-o", build, "-s", os.path.join(wd, "sample*.sam"), "-c", sams[0]], check=True,
+                       stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
+        raw = os.path.join(wd, "raw.tsv")
+        subprocess.run([os.path.join(REF, "ref_features"), fa, raw] + sams, check=True)
+        rawcov = [[float(x) for x in line.rstrip("\n").split("\t")[3 + 180:]] for line in open(raw) if line.startswith("SEG")]
+        fix = dict(args=COVERAGE_ORDER_ARGS, digests=dict(seq=sha(seq), offsets=sha(offsets), reads=[sha(r) for r in reads]),
+                   lrn=open(os.path.join(build, "abawaca.lrn")).read(), info=open(os.path.join(build, "abawaca.info")).read(), rawcov=rawcov)
+        with gzip.GzipFile(os.path.join(HERE, "kat_coverage_order.json.gz"), "wb", mtime=0) as g:
+            g.write(json.dumps(fix).encode())
+    print("coverage order done:", len(rawcov), "windows")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "coverage_order":
+        make_coverage_order()
+        sys.exit(0)
     if not os.path.exists(os.path.join(REF, "abawaca")):
         sys.exit("oracle/_ref is not built: run `make -C oracle ref` where /root/reference is mounted")
     make_kat()
+    make_coverage_order()
     for name, args in SETS.items():
         make_synthetic(name, args)

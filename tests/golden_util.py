@@ -99,10 +99,11 @@ def compare_cluster_records(ref_clusters, recs, strategy, check_illegal_best=Tru
     return bad
 
 
-def coverage_edge_workload(seed=7, nscaf=160, nsamples=3, depth=40):
+def coverage_edge_workload(seed=7, nscaf=160, nsamples=3, depth=40, cover_all_n=False):
     """Scaffolds whose windows have round lengths (2000, 2500, 2048, 3125 ...), so that 1000 * (sum of overlaps) / length is an integer for a
     large share of the windows -- the case in which the order of the reads decides the third decimal (quirk Q5) -- plus an all-N scaffold (one
     window per character, a read over more than 255 windows), N runs, reads hanging over window and scaffold ends, shuffled read order.
+    cover_all_n: see below (needed when the unmodified reference is to print the rows).
     Returns (seq, offsets, reads) in the layout of abw_pack_sequences / abw_coverage."""
     read_dtype = np.dtype([("scaf", "<u4"), ("pos0", "<u4"), ("len", "<u4"), ("flag_nsnps", "<u4")])   # abw_read
     rng = np.random.default_rng(seed)
@@ -133,4 +134,10 @@ def coverage_edge_workload(seed=7, nscaf=160, nsamples=3, depth=40):
         r = np.concatenate(recs)
         rng.shuffle(r)
         reads.append(r)
+    if cover_all_n:
+        # every window needs a read in the LAST sample or the reference reads past a vector when it prints the row (quirk Q6): two reads that
+        # cover all 400 one-character windows of the all-N scaffold
+        extra = np.zeros(2, dtype=read_dtype)
+        extra["scaf"], extra["pos0"], extra["len"] = len(lens) - 1, [0, 250], 300
+        reads[-1] = np.concatenate([reads[-1], extra])
     return seq, offsets, reads

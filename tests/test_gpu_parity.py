@@ -286,3 +286,25 @@ def test_coverage_when_the_order_of_the_reads_decides_the_third_decimal(ctx, ora
     fb = pipeline.build_features(ctx, seq[:int(offsets[keep])], offsets[:keep + 1], reads2, this_sample=0)
     assert np.array_equal(fb.rows_host(), f2["rows"])
     fb.close()
+
+
+def test_coverage_order_windows_match_reference_files(ctx):
+    """tests/golden/kat_coverage_order.json.gz: the unmodified reference on windows of round lengths, where the order of the reads decides the
+    third decimal of the coverage (the same fixture pins the oracle in tests/test_oracle_vs_reference.py)."""
+    import hashlib
+    from abawaca_b200 import capi, pipeline
+    from golden_util import coverage_edge_workload
+    fix = json.loads(gzip.open(os.path.join(GOLDEN, "kat_coverage_order.json.gz"), "rb").read())
+    seq, offsets, reads = coverage_edge_workload(**fix["args"])
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()   # noqa: E731
+    assert fix["digests"] == dict(seq=sha(seq), offsets=sha(offsets), reads=[sha(r) for r in reads])
+    heads, vals = parse_lrn_text(fix["lrn"])
+    fb = pipeline.build_features(ctx, seq, offsets, reads, this_sample=0)
+    assert np.array_equal(fb.rows_host(), vals)
+    st = fb.scaffold_stats_host(np.diff(offsets.astype(np.int64)))
+    for i, l in enumerate(fix["info"].splitlines()):
+        assert "%.3f" % st["cvg"][i] == l.split("\t")[2]
+    fb.close()
+    fb = pipeline.build_features(ctx, seq, offsets, reads, this_sample=0, kind=capi.FEAT_RAW, skip_A=False)
+    assert np.array_equal(fb.rows_host()[:, 180:], np.array(fix["rawcov"], dtype=np.float64))
+    fb.close()

@@ -157,3 +157,35 @@ def test_three_decimal_coverage_from_the_integer_sum(oracle):
         undecided += int((~safe).sum())
         wrong_if_naive += int(((m / 1000.0) != got)[~safe].sum())
     assert claimed > 0 and undecided > 100 and wrong_if_naive > 0
+
+
+def _coverage_order_fixture():
+    import hashlib
+    from golden_util import coverage_edge_workload
+    fix = json.loads(gzip.open(os.path.join(GOLDEN, "kat_coverage_order.json.gz"), "rb").read())
+    seq, offsets, reads = coverage_edge_workload(**fix["args"])
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()   # noqa: E731
+    assert fix["digests"] == dict(seq=sha(seq), offsets=sha(offsets), reads=[sha(r) for r in reads]), "generator drift: regenerate with make_golden.py coverage_order"
+    heads, vals = parse_lrn_text(fix["lrn"])
+    return fix, seq, offsets, reads, vals
+
+
+def test_coverage_order_windows_match_reference(oracle):
+    """Windows of round lengths, produced by the unmodified reference: the third decimal depends on the order in which the reference adds the
+    reads (quirk Q5).  Pins the oracle's sequential sum on exactly the windows where abw_coverage's integer shortcut does not apply."""
+    fix, seq, offsets, reads, vals = _coverage_order_fixture()
+    f = oracle.build_features(seq, offsets, reads, this_sample=0, want_raw=True)
+    assert f["rows"].shape == vals.shape and np.array_equal(f["rows"], vals)
+    rawcov = np.array(fix["rawcov"], dtype=np.float64)
+    assert np.array_equal(f["raw"][:, 180:], rawcov)
+    for i, l in enumerate(fix["info"].splitlines()):
+        assert "%.3f" % f["info_cvg"][i] == l.split("\t")[2]
+    # the fixture does contain windows whose exact value is a multiple of 0.001, and some where truncating the exact quotient would be wrong
+    ln = (f["seg_end"] - f["seg_start"] + 1).astype(np.int64)
+    undecided = wrong = 0
+    for j in range(rawcov.shape[1]):
+        A = np.rint(rawcov[:, j] * ln).astype(np.int64)
+        m, rem = np.divmod(1000 * A, ln)
+        undecided += int(((rem == 0) & (A > 0)).sum())
+        wrong += int(((m / 1000.0) != vals[:, 179 + j]).sum())
+    assert undecided > 50 and wrong > 0

@@ -308,3 +308,31 @@ def test_coverage_order_windows_match_reference_files(ctx):
     fb = pipeline.build_features(ctx, seq, offsets, reads, this_sample=0, kind=capi.FEAT_RAW, skip_A=False)
     assert np.array_equal(fb.rows_host()[:, 180:], np.array(fix["rawcov"], dtype=np.float64))
     fb.close()
+
+
+def test_cfg1_matches_reference_files(ctx):
+    """BASELINE.json configs[0] (2 000 scaffolds, 3 samples, 8 genomes), the one configuration the unmodified reference runs in full: its .lrn,
+    .info, un-truncated coverage, every evaluated cluster of the live strategy and the bins of the real `abawaca` binary (tests/golden/cfg1.*)."""
+    from abawaca_b200 import capi, pipeline
+    g = load_set("cfg1")
+    mg = g["mg"]
+    fb = pipeline.build_features(ctx, mg.seq, mg.offsets, mg.reads, this_sample=0)
+    heads, vals = parse_lrn_text(g["lrn_text"])
+    assert np.array_equal(fb.rows_host(), vals)
+    st = fb.scaffold_stats_host(np.diff(mg.offsets.astype(np.int64)))
+    info = [l.split("\t") for l in g["info_text"].splitlines()]
+    assert ["%.3f" % v for v in st["cvg"]] == [x[2] for x in info]
+    assert ["%.3f" % v for v in st["gc"]] == [x[3] for x in info]
+    assert [int(x[4]) for x in info] == st["Ns"].tolist()
+    fb.close()
+    fb = pipeline.build_features(ctx, mg.seq, mg.offsets, mg.reads, this_sample=0, kind=capi.FEAT_RAW, skip_A=False)
+    assert np.array_equal(fb.rows_host()[:, 180:], g["rawcov"])
+    fb.close()
+    prob = search_problem("cfg1")
+    ref_clusters, ref_bins = parse_ref_search(g["meta"]["ref_search"]["sensspec"])
+    res = pipeline.search(ctx, prob["values"], prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"])
+    assert compare_cluster_records(ref_clusters, res.recs, 0, check_illegal_best=False) == []
+    assert [b for _, b in ref_bins] == res.scaf2cluster.tolist()
+    lines = [l.split("\t") for l in g["meta"]["scaf2cluster"].splitlines()]      # the real binary's scaf2cluster.txt (abawaca.cpp:205-210)
+    assert [int(x[1]) for x in lines] == res.scaf2cluster.tolist()
+    assert len(set(res.scaf2cluster.tolist()) - {0}) == 8

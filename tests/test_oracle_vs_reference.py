@@ -83,7 +83,7 @@ def test_kat_survey_known_answers(oracle):
     assert len(names) == 180 and names[:12] == ["A", "C", "AA", "AC", "AG", "AT", "CA", "CC", "CG", "GA", "GC", "TA"] and names[-1] == "TTAA"
 
 
-@pytest.mark.parametrize("name", ["tiny_clean", "tiny_noisy"])
+@pytest.mark.parametrize("name", ["tiny_clean", "tiny_noisy", "cfg1"])
 def test_features_match_reference_files(oracle, name):
     g = load_set(name)
     mg = g["mg"]
@@ -98,7 +98,7 @@ def test_features_match_reference_files(oracle, name):
     assert [int(x[4]) for x in info] == f["info_Ns"].tolist()
 
 
-@pytest.mark.parametrize("name", ["tiny_clean", "tiny_noisy"])
+@pytest.mark.parametrize("name", ["tiny_clean", "tiny_noisy", "cfg1"])
 @pytest.mark.parametrize("strategy", [0, 1])
 def test_search_matches_reference(oracle, name, strategy):
     g = load_set(name)

@@ -20,6 +20,8 @@ LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0, 1
 FEAT_TRUNC3, FEAT_RAW = 0, 1
 
 READ_DTYPE = np.dtype([("scaf", "<u4"), ("pos0", "<u4"), ("len", "<u4"), ("flag_nsnps", "<u4")])
+READ8_DTYPE = np.dtype([("scaf", "<u4"), ("pos0", "<u4")])      # abw_read8: reads the host parser already filtered
+READS_FULL, READS_COMPACT = 0, 1
 
 
 class AbwError(RuntimeError):
@@ -45,6 +47,11 @@ class ClusterRec(C.Structure):
                 ("gc_avg", C.c_double), ("gc_sd", C.c_double), ("cvg_avg", C.c_double), ("cvg_sd", C.c_double)]
 
 
+class Sample(C.Structure):
+    """abw_sample"""
+    _fields_ = [("reads", C.c_void_p), ("nreads", C.c_uint64), ("format", C.c_int32), ("len", C.c_uint32), ("len16", C.c_void_p), ("h2d_ticket", C.c_uint64)]
+
+
 class SearchProfile(C.Structure):
     _fields_ = [("build_ms", C.c_float), ("sweep_ms", C.c_float), ("partition_ms", C.c_float), ("other_ms", C.c_float),
                 ("sweep_elements", C.c_uint64), ("partition_elements", C.c_uint64), ("levels", C.c_uint32), ("sweep_launches", C.c_uint32)]
@@ -61,7 +68,7 @@ class Collectives(C.Structure):
 EXPORTS = [
     "abw_ctx_create", "abw_ctx_destroy", "abw_last_error", "abw_version", "abw_default_params", "abw_kernel_launches", "abw_arena_misses", "abw_ctx_stream",
     "abw_ctx_synchronize", "abw_profile_enable", "abw_profile_report", "abw_pack_sequences", "abw_seqset_destroy", "abw_seqset_stats", "abw_segment", "abw_segments_destroy",
-    "abw_segments_count", "abw_segments_get", "abw_kmer_features", "abw_coverage", "abw_device_alloc", "abw_device_free",
+    "abw_segments_count", "abw_segments_get", "abw_segments_get_async", "abw_kmer_features", "abw_coverage", "abw_coverage_batch", "abw_rows_to_milli", "abw_device_alloc", "abw_device_free",
     "abw_copy_to_device", "abw_copy_to_host", "abw_memset_device", "abw_h2d_async", "abw_wait_h2d", "abw_d2h_async", "abw_search_create", "abw_search_destroy", "abw_search_run",
     "abw_search_set_shard", "abw_search_set_max_levels", "abw_search_run_sharded", "abw_search_get_profile", "abw_cluster_scg",
     "abw_names_create", "abw_names_destroy", "abw_parse_sam", "abw_fasta_scan", "abw_fasta_destroy", "abw_fasta_count", "abw_fasta_get", "abw_fasta_pack", "abw_nccl_unique_id", "abw_nccl_collectives_create", "abw_nccl_collectives_destroy", "abw_parse_lrn", "abw_search_set_scaffold_stats",
@@ -99,8 +106,11 @@ def load():
     L.abw_seqset_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.abw_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
     L.abw_segments_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.abw_segments_get_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.abw_kmer_features.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_uint32]
     L.abw_coverage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+    L.abw_coverage_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.c_void_p]
+    L.abw_rows_to_milli.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
     L.abw_device_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     L.abw_device_free.argtypes = [C.c_void_p, C.c_void_p]
     L.abw_copy_to_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]

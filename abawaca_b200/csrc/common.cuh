@@ -12,7 +12,8 @@ struct abw_ctx {
 	int          device = 0;
 	cudaStream_t stream = nullptr;
 	cudaStream_t copy_stream = nullptr;       // host->device staging that overlaps kernels of `stream` (abw_h2d_async)
-	std::vector<cudaEvent_t> copy_events;
+	std::vector<cudaEvent_t> copy_events;     // events of the tickets copy_retired + 1 ... (abw_h2d_async)
+	uint64_t     copy_retired = 0;            // tickets retired by abw_ctx_synchronize so far
 	int          sm_count = 148;
 	uint64_t     launches = 0;
 	uint64_t     arena_misses = 0;             // device blocks obtained from the driver (cudaMallocAsync) rather than from the context's cache
@@ -44,15 +45,15 @@ cudaError_t abw_stage_upload(abw_ctx* ctx, void* d_dst, const void* h_src, size_
 // Small transfers and the copy engines.  Copies of one direction execute in the order they were issued, whatever their stream: an 8-byte
 // cudaMemcpyAsync on the compute stream waits for every bulk copy (read records in, .lrn matrix out) that was enqueued before it on the copy
 // stream, and the kernels behind it wait too -- measured: end-to-end step = H2D + resident step + D2H, no overlap at all.
-// With ABW_SMALL_COPIES=kernel the small transfers bypass the engines: abw_stage_upload lets a kernel read the pinned staging slot, and
+// Therefore the small transfers bypass the engines: abw_stage_upload lets a kernel read the pinned staging slot, and
 // abw_fetch lets a kernel write the result into mapped pinned memory, from where abw_sync (cudaStreamSynchronize + copy-out) hands it to the
-// caller's buffer.  Default (unset): plain cudaMemcpyAsync, as before.  Every device->host result of an entry point is requested with
-// abw_fetch and every wait on the context stream is abw_sync; ABW_ENTER drops requests an earlier, failed call may have left behind.
+// caller's buffer.  ABW_SMALL_COPIES=memcpy selects plain cudaMemcpyAsync (the round-1 behaviour).  Every device->host result of an entry point
+// is requested with abw_fetch and every wait on the context stream is abw_sync; ABW_ENTER drops requests an earlier, failed call may have left behind.
 bool abw_small_copies_by_kernel();
 cudaError_t abw_fetch(abw_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 cudaError_t abw_sync(abw_ctx* ctx);
-// host->device upload of a small array on the context stream: cudaMemcpyAsync by default, through the pinned staging area and a kernel with
-// ABW_SMALL_COPIES=kernel (the caller waits for the stream before it changes h_src or returns)
+// host->device upload of a small array on the context stream: cudaMemcpyAsync by default, through the pinned staging area and a kernel (cudaMemcpyAsync with
+// ABW_SMALL_COPIES=memcpy) (the caller waits for the stream before it changes h_src or returns)
 cudaError_t abw_upload_small(abw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 
 inline int abw_fail(abw_ctx* ctx, int code, const std::string& msg)

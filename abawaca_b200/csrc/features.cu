@@ -9,24 +9,7 @@
 #include "common.cuh"
 #include <algorithm>
 
-struct abw_seqset {
-	uint32_t nscaf = 0;
-	uint64_t total_padded = 0;            // bases
-	DevBuf<uint64_t> len, base;           // [nscaf], [nscaf+1]
-	DevBuf<uint32_t> packed, valid, nmask;
-	DevBuf<unsigned long long> countN, countGC;
-	std::vector<uint64_t> h_len, h_base;
-};
-
-struct abw_segments {
-	uint32_t nscaf = 0;
-	uint64_t nseg = 0;
-	DevBuf<uint64_t> seg_first;           // [nscaf+1]
-	DevBuf<uint32_t> seg_scaf;            // [nseg]
-	DevBuf<uint64_t> seg_start, seg_end, seg_nonN;   // 1-based inclusive, abawaca-build.cpp:216
-	DevBuf<uint64_t> seg_gbase;           // absolute (padded) base index of the first base of the segment
-	DevBuf<uint4> scaf_info;              // per scaffold {first window (low 32 bits), windows, non-N bases per window (u64)}: one load for the coverage kernels
-};
+#include "features.cuh"
 
 namespace {
 
@@ -145,7 +128,6 @@ __device__ __forceinline__ void window_plan(uint64_t len, uint64_t nN, uint64_t 
 	count = (nbps > 0)? nonN / nbps : len;
 }
 
-constexpr uint32_t COV_REGULAR = 0x80000000u;              // scaf_info.w of a scaffold whose windows are all nbps characters long (no N)
 
 __global__ void k_seg_count(const uint64_t* __restrict__ len, const unsigned long long* __restrict__ countN, uint32_t nscaf, uint64_t window, uint64_t* __restrict__ counts)
 {
@@ -413,486 +395,26 @@ __global__ void __launch_bounds__(KM_WARPS * 32) k_kmer(const uint32_t* __restri
 	}
 }
 
-// ---------------------------------------------------------------------------------------------------
-// coverage, abawaca-build.cpp:177-185, 231-244, 546-551
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool read_accepted(const abw_read& r, uint32_t max_snps, uint32_t nscaf)
-{
-	uint32_t flag = r.flag_nsnps & 0xFFFFu, nsnps = r.flag_nsnps >> 16;
-	return !((flag & 0x4u) || (nsnps > max_snps) || (flag & 0x100u)) && r.scaf < nscaf;   // :546-550
-}
-
-// Windows hit by the reads of a thread, staged so that the loads of its COV_ITEMS reads are in flight together.
-//   first window g0 = the first one of the scaffold whose end is >= s (windows before it are skipped by `continue`, :235-236); windows of a scaffold hold the
-//   same number of non-N bases, so it is window (s-1)/nbps unless a run of N shifted the boundaries (then: binary search).
-//   Windows of a scaffold are contiguous (start[g] = end[g-1] + 1, start of the first = 1), so only the ends are read.
-// Returns per read: g0, number of windows cnt, and the end of window g0 - 1 (0 for the first window of the scaffold) and of g0.
-constexpr int COV_ITEMS = 4;                                // consecutive reads per thread
-struct ReadHit { uint32_t g0, cnt; uint64_t end_prev, end_cur; };
-__device__ __forceinline__ void read_windows(const abw_read (&rd)[COV_ITEMS], uint32_t max_snps, uint32_t nscaf, const uint4* __restrict__ scaf_info,
-                                             const uint64_t* __restrict__ seg_end, ReadHit (&hit)[COV_ITEMS])
-{
-	bool acc[COV_ITEMS];
-	uint4 si[COV_ITEMS];
-#pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++) {
-		acc[j] = read_accepted(rd[j], max_snps, nscaf);
-		si[j] = acc[j]? __ldg(scaf_info + rd[j].scaf) : make_uint4(0, 0, 1, 0);
-		acc[j] = acc[j] && si[j].y > 0;
-	}
-	uint32_t g[COV_ITEMS];
-#pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++) {
-		const uint32_t s = rd[j].pos0;
-		uint32_t q = 0;
-		if(s > 0) {
-			// an all-N scaffold (nbps 0) has one window per character
-			if(si[j].w == 0 || si[j].w == COV_REGULAR)
-				q = (s - 1) / max(si[j].z, 1u);
-			else
-				q = 0;                                      // more than 2^32 bases per window: every read position lies in the first window or is found by the search
-		}
-		g[j] = si[j].x + min(si[j].y - (acc[j]? 1u : 0u), q);
-	}
-#pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++) {
-		hit[j].end_cur = acc[j]? __ldg(seg_end + g[j]) : 0ull;
-		hit[j].end_prev = (acc[j] && g[j] > si[j].x)? __ldg(seg_end + g[j] - 1) : 0ull;
-	}
-#pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++) {
-		hit[j].g0 = 0; hit[j].cnt = 0;
-		if(!acc[j])
-			continue;
-		const uint64_t s = rd[j].pos0, e = (uint64_t)rd[j].pos0 + rd[j].len - 1;
-		const uint32_t f0 = si[j].x, f1 = si[j].x + si[j].y;
-		uint32_t gg = g[j];
-		if(!((gg == f0 || hit[j].end_prev < s) && hit[j].end_cur >= s)) {
-			uint32_t lo = f0, hi = f1;                      // runs of N moved the boundaries: binary search
-			while(lo < hi) {
-				const uint32_t mid = lo + ((hi - lo) >> 1);
-				if(__ldg(seg_end + mid) < s) lo = mid + 1; else hi = mid;
-			}
-			gg = lo;
-			hit[j].end_cur = (gg < f1)? __ldg(seg_end + gg) : 0ull;
-			hit[j].end_prev = (gg > f0)? __ldg(seg_end + gg - 1) : 0ull;
-		}
-		hit[j].g0 = gg;
-		// windows gg, gg+1, ... while their start is <= e (:233-237)
-		uint32_t c = 0;
-		uint64_t prev_end = hit[j].end_prev, cur_end = hit[j].end_cur;
-		uint32_t w = gg;
-		while(w < f1 && !(e < prev_end + 1)) {                 // first window of a scaffold: prev_end is 0 and the start 1
-			c++;
-			w++;
-			prev_end = cur_end;
-			if(w < f1 && !(e < prev_end + 1))
-				cur_end = __ldg(seg_end + w);
-		}
-		hit[j].cnt = c;
-	}
-}
-
-constexpr int COV_THREADS = 256;
-constexpr int COV_TILE = COV_THREADS * COV_ITEMS;
-
-__device__ __forceinline__ void load_reads(const abw_read* __restrict__ reads, uint64_t nreads, uint64_t r0, abw_read (&rd)[COV_ITEMS])
-{
-#pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++) {
-		if(r0 + j < nreads) {
-			const uint4 x = __ldg(reinterpret_cast<const uint4*>(reads + r0 + j));
-			rd[j].scaf = x.x; rd[j].pos0 = x.y; rd[j].len = x.z; rd[j].flag_nsnps = x.w;
-		}
-		else {
-			rd[j].scaf = 0xFFFFFFFFu; rd[j].pos0 = 0; rd[j].len = 0; rd[j].flag_nsnps = 0;
-		}
-	}
-}
-
-// pass 1: (window, read) pairs per tile of COV_TILE reads; per-scaffold read bases of the -c sample
-__global__ void __launch_bounds__(COV_THREADS) k_cov_count(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf,
-                                                          const uint4* __restrict__ scaf_info, const uint64_t* __restrict__ seg_end, uint32_t* __restrict__ tile_counts,
-                                                          unsigned long long* __restrict__ scaf_nbps)
-{
-	__shared__ uint32_t sm[COV_THREADS / 32];
-	const uint64_t r0 = (uint64_t)blockIdx.x * COV_TILE + (uint64_t)threadIdx.x * COV_ITEMS;
-	abw_read rd[COV_ITEMS];
-	load_reads(reads, nreads, r0, rd);
-	ReadHit hit[COV_ITEMS];
-	read_windows(rd, max_snps, nscaf, scaf_info, seg_end, hit);
-	uint32_t c = 0;
-#pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++) {
-		c += hit[j].cnt;
-		if(scaf_nbps != nullptr && read_accepted(rd[j], max_snps, nscaf))
-			atomicAdd(&scaf_nbps[rd[j].scaf], (unsigned long long)rd[j].len);     // integer: order free (:242-243)
-	}
-	c = __reduce_add_sync(0xffffffffu, c);
-	if((threadIdx.x & 31) == 0)
-		sm[threadIdx.x >> 5] = c;
-	__syncthreads();
-	if(threadIdx.x == 0) {
-		uint32_t t = 0;
-#pragma unroll
-		for(int w = 0; w < COV_THREADS / 32; w++)
-			t += sm[w];
-		tile_counts[blockIdx.x] = t;
-	}
-}
-
-// pass 2: the pairs, in read order (then window order): key = window, value = overlap
-__global__ void __launch_bounds__(COV_THREADS) k_cov_emit(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf,
-                                                         const uint4* __restrict__ scaf_info, const uint64_t* __restrict__ seg_end, const uint64_t* __restrict__ tile_offs,
-                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
-{
-	__shared__ uint32_t sm[COV_THREADS / 32];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint64_t r0 = (uint64_t)blockIdx.x * COV_TILE + (uint64_t)threadIdx.x * COV_ITEMS;
-	abw_read rd[COV_ITEMS];
-	load_reads(reads, nreads, r0, rd);
-	ReadHit hit[COV_ITEMS];
-	read_windows(rd, max_snps, nscaf, scaf_info, seg_end, hit);
-	uint32_t c = 0;
-#pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++)
-		c += hit[j].cnt;
-	uint32_t incl = c;
-#pragma unroll
-	for(int o = 1; o < 32; o <<= 1) {
-		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-		if(lane >= o)
-			incl += t;
-	}
-	if(lane == 31)
-		sm[warp] = incl;
-	__syncthreads();
-	uint32_t wex = 0;
-#pragma unroll
-	for(int w = 0; w < COV_THREADS / 32; w++)
-		if(w < warp)
-			wex += sm[w];
-	uint64_t o = tile_offs[blockIdx.x] + wex + incl - c;
-#pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++) {
-		const uint64_t s = rd[j].pos0, e = (uint64_t)rd[j].pos0 + rd[j].len - 1;
-		uint64_t prev_end = hit[j].end_prev, cur_end = hit[j].end_cur;
-		for(uint32_t k = 0; k < hit[j].cnt; k++) {
-			const uint32_t g = hit[j].g0 + k;
-			const uint64_t st = prev_end + 1, en = cur_end;             // first window of a scaffold: prev_end is 0 and the start 1
-			const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // 0-based read against 1-based window: quirk Q3, kept (:182-183)
-			keys[o] = g;
-			vals[o] = (uint32_t)(e2 - s2 + 1);                             // the overlap travels with the pair: no gather after the sort
-			o++;
-			prev_end = cur_end;
-			if(k + 1 < hit[j].cnt)
-				cur_end = __ldg(seg_end + g + 1);
-		}
-	}
-}
-
-// run of every window in the sorted pairs: [run[g].x, run[g].y), both zero (pre-cleared) for a window no read touches
-__global__ void k_cov_runs(const uint32_t* __restrict__ keys, uint64_t npairs, uint2* __restrict__ run)
+// integer thousandths of the columns [col0, col0 + ncols) of a row-major matrix (abw_rows_to_milli)
+template <typename OutT>
+__global__ void __launch_bounds__(256) k_rows_milli(const double* __restrict__ rows, uint64_t nrows, uint64_t ld, uint32_t col0, uint32_t ncols, OutT* __restrict__ out,
+                                                    int* __restrict__ inexact)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= npairs)
-		return;
-	const uint32_t k = keys[i];
-	if(i == 0 || keys[i - 1] != k)
-		run[k].x = (uint32_t)i;
-	if(i + 1 == npairs || keys[i + 1] != k)
-		run[k].y = (uint32_t)(i + 1);
-}
-
-// one thread per window: the reads that hit it, in SAM order (the pairs were sorted stably by window)
-// `only` (may be null): windows whose flag is zero already hold their value (k_cov_quotient) and are left alone
-template <int KIND, int BATCH>
-__global__ void k_cov_accumulate(const uint32_t* __restrict__ vals, const uint2* __restrict__ run, uint64_t nseg,
-                                 const uint64_t* __restrict__ seg_start, const uint64_t* __restrict__ seg_end, double* __restrict__ rows, uint64_t ld, uint32_t col,
-                                 const uint32_t* __restrict__ only)
-{
-	uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(g >= nseg)
-		return;
-	if(only != nullptr && ((only[g >> 5] >> (g & 31u)) & 1u) == 0)
-		return;
-	const double seglen = (double)(seg_end[g] - seg_start[g] + 1);
-	double acc = 0.0, q = 0.0;
-	uint32_t last = 0xFFFFFFFFu;
-	const uint2 rg = run[g];
-	for(uint32_t i = rg.x; i < rg.y; i += BATCH) {
-		// BATCH loads in flight (8 when every window is summed, 32 when only the few flagged ones are and the longest run sets the time);
-		// the additions stay strictly in SAM order (quirk Q5)
-		const uint32_t m = min((uint32_t)BATCH, rg.y - i);
-		uint32_t ov[BATCH];
-#pragma unroll
-		for(int j = 0; j < BATCH; j++)
-			ov[j] = ((uint32_t)j < m)? __ldg(vals + i + j) : 0u;
-#pragma unroll
-		for(int j = 0; j < BATCH; j++) {
-			if((uint32_t)j < m) {
-				if(ov[j] != last) {                            // most reads lie entirely inside the window: same quotient, computed once
-					q = __ddiv_rn((double)ov[j], seglen);      // :184
-					last = ov[j];
-				}
-				acc = __dadd_rn(acc, q);
-			}
-		}
+	bool bad = false;
+	if(i < nrows * ncols) {
+		const uint64_t r = i / ncols;
+		const uint32_t c = (uint32_t)(i - r * ncols);
+		const double v = rows[r * ld + col0 + c];
+		const double k = rint(__dmul_rn(v, 1000.0));
+		const double kmax = (sizeof(OutT) == 2)? 65535.0 : 4294967295.0;
+		const bool ok = (k >= 0.0) && (k <= kmax) && (__ddiv_rn(k, 1000.0) == v) && !(v == 0.0 && signbit(v));
+		out[i] = ok? (OutT)(unsigned long long)k : (OutT)0;
+		bad = !ok;
 	}
-	if(KIND == ABW_FEAT_TRUNC3)
-		acc = __ddiv_rn((double)__double2int_rz(__dmul_rn(1000.0, acc)), 1000.0);
-	rows[g * ld + col] = acc;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Coverage written with three decimals (ABW_FEAT_TRUNC3, what abawaca-build prints, abawaca-build.cpp:578-607) without sorting the reads.
-//
-// The reference adds fl(ov_i / len) in SAM order and prints int(1000 * sum) / 1000.0.  With A = sum of the overlaps (an integer, order free)
-// the exact value of 1000 * sum is 1000 A / len = m + r / len (m, r integers, 0 <= r < len).  The floating-point sum of n <= A terms differs
-// from A / len by at most (n + 1) u A / len (u = 2^-53: one rounding per quotient, one per addition, one for the product with 1000), so the
-// product the reference truncates lies within E = 1000 (A + 1) u A / len (1 + 1e-10) of m + r / len.  Whenever r != 0 and
-// E < min(r, len - r) / len the truncation is m whatever the order of the reads was: those windows are finished by k_cov_quotient from the
-// integer sum alone (the test is made with twice that bound).  The others (r == 0: the exact value IS a multiple of 0.001 and the rounding
-// direction decides, a fraction of about gcd(1000, len) / len of the windows; or a huge sum) are flagged, and only the reads that touch a
-// flagged window go through the stable sort and the in-order accumulation below.  ABW_FEAT_RAW always takes the sorted path.
-// ---------------------------------------------------------------------------------------------------
-// pass 1: integer sum of the overlaps per window (order free), first window and window count of every read for the second pass,
-// per-scaffold read bases of the -c sample.  status[0] |= 1 when a read touches more than 255 windows (the caller then sorts everything).
-// A scaffold without N (COV_REGULAR) has the windows [l nbps + 1, (l + 1) nbps]: its reads need the 16-byte scaffold record and nothing
-// else.  The other scaffolds go through the window table one read at a time (guess, verify, binary search: as read_windows).
-__device__ __noinline__ void cov_sum_irregular(uint32_t pos0, uint32_t rlen, const uint4 si, const uint64_t* __restrict__ seg_end,
-                                               unsigned long long* __restrict__ sum_ov, uint32_t& g0_out, uint32_t& cnt_out)
-{
-	const uint64_t s = pos0, e = (uint64_t)pos0 + rlen - 1;
-	const uint32_t f0 = si.x, f1 = si.x + si.y;
-	uint32_t q = 0;
-	if(pos0 > 0 && si.w == 0)
-		q = (pos0 - 1) / max(si.z, 1u);                     // an all-N scaffold (nbps 0) has one window per character
-	uint32_t gg = f0 + min(si.y - 1u, q);
-	uint64_t cur_end = __ldg(seg_end + gg), prev_end = (gg > f0)? __ldg(seg_end + gg - 1) : 0ull;
-	if(!((gg == f0 || prev_end < s) && cur_end >= s)) {
-		uint32_t lo = f0, hi = f1;                          // runs of N moved the boundaries: binary search for the first window whose end is >= s
-		while(lo < hi) {
-			const uint32_t mid = lo + ((hi - lo) >> 1);
-			if(__ldg(seg_end + mid) < s) lo = mid + 1; else hi = mid;
-		}
-		gg = lo;
-		cur_end = (gg < f1)? __ldg(seg_end + gg) : 0ull;
-		prev_end = (gg > f0)? __ldg(seg_end + gg - 1) : 0ull;
-	}
-	uint32_t c = 0, w = gg;
-	while(w < f1 && !(e < prev_end + 1)) {                     // windows gg, gg+1, ... while their start is <= e (:233-237)
-		const uint64_t st = prev_end + 1, en = cur_end;
-		const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // 0-based read against 1-based window: quirk Q3, kept (:182-183)
-		atomicAdd(&sum_ov[w], (unsigned long long)(e2 - s2 + 1));
-		c++;
-		w++;
-		prev_end = cur_end;
-		if(w < f1)
-			cur_end = __ldg(seg_end + w);
-	}
-	g0_out = gg;
-	cnt_out = c;
-}
-
-__global__ void __launch_bounds__(COV_THREADS, 5) k_cov_sum(const abw_read* __restrict__ reads, uint64_t nreads, uint32_t max_snps, uint32_t nscaf,
-                                                           const uint4* __restrict__ scaf_info, const uint64_t* __restrict__ seg_end,
-                                                           unsigned long long* __restrict__ sum_ov, uint4* __restrict__ hit_g0, uchar4* __restrict__ hit_cnt,
-                                                           unsigned long long* __restrict__ scaf_nbps, uint32_t* __restrict__ status)
-{
-	static_assert(COV_ITEMS == 4, "hit records are stored four at a time");
-	const uint64_t t = (uint64_t)blockIdx.x * COV_THREADS + threadIdx.x;
-	const uint64_t r0 = t * COV_ITEMS;
-	uint4 x[COV_ITEMS], si[COV_ITEMS];                        // read: scaf, pos0, len, flag_nsnps; scaffold: first window, windows, nbps, kind
-	bool acc[COV_ITEMS];
-#pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++)
-		x[j] = (r0 + j < nreads)? __ldg(reinterpret_cast<const uint4*>(reads + r0 + j)) : make_uint4(0xFFFFFFFFu, 0, 0, 0);
-#pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++) {
-		const uint32_t flag = x[j].w & 0xFFFFu, nsnps = x[j].w >> 16;
-		acc[j] = !((flag & 0x4u) || (nsnps > max_snps) || (flag & 0x100u)) && x[j].x < nscaf;   // :546-550
-		si[j] = acc[j]? __ldg(scaf_info + x[j].x) : make_uint4(0, 0, 1, 0);
-	}
-	uint32_t g0[COV_ITEMS], cn[COV_ITEMS];
-#pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++) {
-		g0[j] = 0;
-		cn[j] = 0;
-		if(!acc[j])
-			continue;
-		if(scaf_nbps != nullptr)
-			atomicAdd(&scaf_nbps[x[j].x], (unsigned long long)x[j].z);        // integer: order free (:242-243)
-		if(si[j].y == 0)
-			continue;
-		if(si[j].w == COV_REGULAR) {
-			const uint32_t nb = si[j].z, pos0 = x[j].y;
-			const uint32_t q = pos0? (pos0 - 1) / nb : 0u;     // position s >= 1 lies in window (s - 1) / nbps; position 0 before the first one
-			if(q >= si[j].y)
-				continue;                                   // behind the last window (the trailing bases no window holds)
-			const uint64_t s = pos0, e = (uint64_t)pos0 + x[j].z - 1;
-			uint32_t l = q, c = 0;
-			uint64_t st = (uint64_t)q * nb + 1;
-			while(l < si[j].y && !(e < st)) {
-				const uint64_t en = st + nb - 1;
-				const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // quirk Q3, as above
-				atomicAdd(&sum_ov[si[j].x + l], (unsigned long long)(e2 - s2 + 1));
-				c++;
-				l++;
-				st = en + 1;
-			}
-			g0[j] = si[j].x + q;
-			cn[j] = c;
-		}
-		else
-			cov_sum_irregular(x[j].y, x[j].z, si[j], seg_end, sum_ov, g0[j], cn[j]);
-		if(cn[j] > 255u) {
-			atomicOr(status, 1u);
-			cn[j] = 255u;
-		}
-	}
-	hit_g0[t] = make_uint4(g0[0], g0[1], g0[2], g0[3]);
-	hit_cnt[t] = make_uchar4((unsigned char)cn[0], (unsigned char)cn[1], (unsigned char)cn[2], (unsigned char)cn[3]);
-}
-
-// one thread per window: the value from the integer sum where the truncation cannot depend on the order of the reads, a flag elsewhere
-__global__ void __launch_bounds__(256) k_cov_quotient(const unsigned long long* __restrict__ sum_ov, uint64_t nseg, const uint64_t* __restrict__ seg_start,
-                                                      const uint64_t* __restrict__ seg_end, double* __restrict__ rows, uint64_t ld, uint32_t col,
-                                                      uint32_t* __restrict__ flag_bits)
-{
-	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	bool f = false;
-	if(g < nseg) {
-		const uint64_t A = sum_ov[g], len = seg_end[g] - seg_start[g] + 1;
-		if(A == 0)
-			rows[g * ld + col] = 0.0;                          // no read: the sum is 0.0 and so is int(0.0) / 1000.0
-		else {
-			f = true;
-			if(A < (1ull << 40)) {
-				const uint64_t num = 1000ull * A, m = num / len, r = num - m * len;
-				if(r != 0 && m < (1ull << 31)) {
-					const uint64_t dist = (r < len - r)? r : len - r;
-					const double bound = 2000.0 * (double)(A + 2) * (double)A * 1.1102230246251565e-16;   // 2 x 1000 (A + 1) u A, in units of 1 / len
-					if(bound < (double)dist) {
-						f = false;
-						rows[g * ld + col] = __ddiv_rn((double)(int)m, 1000.0);
-					}
-				}
-			}
-		}
-	}
-	// one bit per window (28 KB for 227 k windows: the second pass tests it for every read out of L1)
-	const uint32_t bits = __ballot_sync(0xffffffffu, f);
-	if((threadIdx.x & 31) == 0 && g < nseg)
-		flag_bits[g >> 5] = bits;
-}
-
-__device__ __forceinline__ uint32_t window_flagged(const uint32_t* __restrict__ flag_bits, uint32_t g)
-{
-	return (__ldg(flag_bits + (g >> 5)) >> (g & 31u)) & 1u;
-}
-
-// Second pass over the hit records: a thread takes FL_GROUPS groups of four consecutive reads, a CTA 256 * FL_GROUPS * 4 consecutive reads;
-// pairs come out in read order.  The flag of the first window of every read is tested unconditionally (independent loads, all in flight);
-// the few reads over several windows loop.  (Measured: these kernels are bound by the chain load record -> load flag of each thread, and
-// four groups per thread were slower than one.)
-constexpr int FL_GROUPS = 1;
-constexpr int FL_TILE_GROUPS = COV_THREADS * FL_GROUPS;
-
-__device__ __forceinline__ uint32_t flagged_hits(const uint4* __restrict__ hit_g0, const uchar4* __restrict__ hit_cnt, uint64_t ngroups, uint64_t t0,
-                                                const uint32_t* __restrict__ flag, uint4 (&g4)[FL_GROUPS], uchar4 (&c4)[FL_GROUPS])
-{
-#pragma unroll
-	for(int q = 0; q < FL_GROUPS; q++) {
-		const bool in = t0 + q < ngroups;
-		g4[q] = in? __ldg(hit_g0 + t0 + q) : make_uint4(0, 0, 0, 0);
-		c4[q] = in? __ldg(hit_cnt + t0 + q) : make_uchar4(0, 0, 0, 0);
-	}
-	uint32_t c = 0;
-#pragma unroll
-	for(int q = 0; q < FL_GROUPS; q++) {
-		const uint32_t fx = window_flagged(flag, g4[q].x), fy = window_flagged(flag, g4[q].y);      // window 0 for a read without window: any valid word
-		const uint32_t fz = window_flagged(flag, g4[q].z), fw = window_flagged(flag, g4[q].w);
-		c += (c4[q].x? fx : 0u) + (c4[q].y? fy : 0u) + (c4[q].z? fz : 0u) + (c4[q].w? fw : 0u);
-		for(uint32_t k = 1; k < c4[q].x; k++) c += window_flagged(flag, g4[q].x + k);
-		for(uint32_t k = 1; k < c4[q].y; k++) c += window_flagged(flag, g4[q].y + k);
-		for(uint32_t k = 1; k < c4[q].z; k++) c += window_flagged(flag, g4[q].z + k);
-		for(uint32_t k = 1; k < c4[q].w; k++) c += window_flagged(flag, g4[q].w + k);
-	}
-	return c;
-}
-
-// pass 2a: (flagged window, read) pairs per tile
-__global__ void __launch_bounds__(COV_THREADS) k_cov_count_flagged(const uint4* __restrict__ hit_g0, const uchar4* __restrict__ hit_cnt, uint64_t ngroups,
-                                                                  const uint32_t* __restrict__ flag, uint32_t* __restrict__ tile_counts)
-{
-	__shared__ uint32_t sm[COV_THREADS / 32];
-	const uint64_t t0 = ((uint64_t)blockIdx.x * COV_THREADS + threadIdx.x) * FL_GROUPS;
-	uint4 g4[FL_GROUPS];
-	uchar4 c4[FL_GROUPS];
-	uint32_t c = flagged_hits(hit_g0, hit_cnt, ngroups, t0, flag, g4, c4);
-	c = __reduce_add_sync(0xffffffffu, c);
-	if((threadIdx.x & 31) == 0)
-		sm[threadIdx.x >> 5] = c;
-	__syncthreads();
-	if(threadIdx.x == 0) {
-		uint32_t tot = 0;
-#pragma unroll
-		for(int w = 0; w < COV_THREADS / 32; w++)
-			tot += sm[w];
-		tile_counts[blockIdx.x] = tot;
-	}
-}
-
-// pass 2b: those pairs in read order (then window order): key = window, value = overlap
-__global__ void __launch_bounds__(COV_THREADS) k_cov_emit_flagged(const abw_read* __restrict__ reads, const uint4* __restrict__ hit_g0, const uchar4* __restrict__ hit_cnt,
-                                                                 uint64_t ngroups, const uint32_t* __restrict__ flag, const uint64_t* __restrict__ seg_start,
-                                                                 const uint64_t* __restrict__ seg_end, const uint64_t* __restrict__ tile_offs,
-                                                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
-{
-	__shared__ uint32_t sm[COV_THREADS / 32];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint64_t t0 = ((uint64_t)blockIdx.x * COV_THREADS + threadIdx.x) * FL_GROUPS;
-	uint4 g4[FL_GROUPS];
-	uchar4 c4[FL_GROUPS];
-	const uint32_t c = flagged_hits(hit_g0, hit_cnt, ngroups, t0, flag, g4, c4);
-	uint32_t incl = c;
-#pragma unroll
-	for(int o = 1; o < 32; o <<= 1) {
-		const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
-		if(lane >= o)
-			incl += x;
-	}
-	if(lane == 31)
-		sm[warp] = incl;
-	__syncthreads();
-	if(c == 0)
-		return;
-	uint32_t wex = 0;
-#pragma unroll
-	for(int w = 0; w < COV_THREADS / 32; w++)
-		if(w < warp)
-			wex += sm[w];
-	uint64_t o = tile_offs[blockIdx.x] + wex + incl - c;
-#pragma unroll
-	for(int q = 0; q < FL_GROUPS; q++) {
-		const uint32_t g0[4] = {g4[q].x, g4[q].y, g4[q].z, g4[q].w}, cn[4] = {c4[q].x, c4[q].y, c4[q].z, c4[q].w};
-#pragma unroll
-		for(int j = 0; j < 4; j++) {
-			for(uint32_t k = 0; k < cn[j]; k++) {
-				const uint32_t g = g0[j] + k;
-				if(window_flagged(flag, g) == 0)
-					continue;
-				const uint4 x = __ldg(reinterpret_cast<const uint4*>(reads + (t0 + q) * COV_ITEMS + j));   // scaf, pos0, len, flag_nsnps
-				const uint64_t s = x.y, e = (uint64_t)x.y + x.z - 1;
-				const uint64_t st = __ldg(seg_start + g), en = __ldg(seg_end + g);
-				const uint64_t s2 = (s < st)? st : s, e2 = (e > en)? en : e;   // as in k_cov_emit
-				keys[o] = g;
-				vals[o] = (uint32_t)(e2 - s2 + 1);
-				o++;
-			}
-		}
-	}
+	const uint32_t nb = __popc(__ballot_sync(0xffffffffu, bad));
+	if(nb && (threadIdx.x & 31) == 0)
+		atomicAdd(inexact, (int)nb);
 }
 
 bool g_tables_ready[64] = {};
@@ -1074,6 +596,23 @@ int abw_segment(abw_ctx* ctx, const abw_seqset* s, uint32_t window_size, abw_seg
 
 void abw_segments_destroy(abw_segments* g) { delete g; }
 
+int abw_rows_to_milli(abw_ctx* ctx, const double* d_rows, uint64_t nrows, uint64_t ld, uint32_t col0, uint32_t ncols, int bits, void* d_out, int32_t* d_inexact)
+{
+	if(!ctx || !d_rows || !d_out || !d_inexact || (bits != 16 && bits != 32))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_rows_to_milli: bad argument");
+	if(ld < (uint64_t)col0 + ncols)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_rows_to_milli: row stride too small");
+	ABW_ENTER(ctx);
+	if(nrows == 0 || ncols == 0)
+		return ABW_OK;
+	const unsigned int blocks = abw_div_up(nrows * ncols, 256);
+	if(bits == 16)
+		ABW_LAUNCH(ctx, k_rows_milli<uint16_t>, blocks, 256, 0, d_rows, nrows, ld, col0, ncols, (uint16_t*)d_out, (int*)d_inexact);
+	else
+		ABW_LAUNCH(ctx, k_rows_milli<uint32_t>, blocks, 256, 0, d_rows, nrows, ld, col0, ncols, (uint32_t*)d_out, (int*)d_inexact);
+	return ABW_OK;
+}
+
 uint64_t abw_segments_count(const abw_segments* g) { return g? g->nseg : 0; }
 
 int abw_segments_get(abw_ctx* ctx, const abw_segments* g, uint64_t* h_seg_first, uint32_t* h_seg_scaf, uint64_t* h_seg_start, uint64_t* h_seg_end, uint64_t* h_seg_nonN)
@@ -1094,6 +633,21 @@ int abw_segments_get(abw_ctx* ctx, const abw_segments* g, uint64_t* h_seg_first,
 	return ABW_OK;
 }
 
+int abw_segments_get_async(abw_ctx* ctx, const abw_segments* g, uint32_t* h_seg_scaf, uint64_t* h_seg_start, uint64_t* h_seg_end, uint64_t* h_seg_nonN)
+{
+	if(!ctx || !g)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_segments_get_async: null argument");
+	if(h_seg_scaf)
+		ABW_CHECK(abw_d2h_async(ctx, h_seg_scaf, g->seg_scaf.p, sizeof(uint32_t) * g->nseg));
+	if(h_seg_start)
+		ABW_CHECK(abw_d2h_async(ctx, h_seg_start, g->seg_start.p, sizeof(uint64_t) * g->nseg));
+	if(h_seg_end)
+		ABW_CHECK(abw_d2h_async(ctx, h_seg_end, g->seg_end.p, sizeof(uint64_t) * g->nseg));
+	if(h_seg_nonN)
+		ABW_CHECK(abw_d2h_async(ctx, h_seg_nonN, g->seg_nonN.p, sizeof(uint64_t) * g->nseg));
+	return ABW_OK;
+}
+
 int abw_kmer_features(abw_ctx* ctx, const abw_seqset* s, const abw_segments* g, int kind, int skip_A, double* d_rows, uint64_t ld, uint32_t col0)
 {
 	if(!ctx || !s || !g || !d_rows)
@@ -1111,119 +665,6 @@ int abw_kmer_features(abw_ctx* ctx, const abw_seqset* s, const abw_segments* g, 
 		ABW_LAUNCH(ctx, k_kmer<ABW_FEAT_TRUNC3>, blocks, KM_WARPS * 32, 0, s->packed.p, s->valid.p, g->seg_gbase.p, g->seg_start.p, g->seg_end.p, g->nseg, skip_A, d_rows, ld, col0);
 	else
 		ABW_LAUNCH(ctx, k_kmer<ABW_FEAT_RAW>, blocks, KM_WARPS * 32, 0, s->packed.p, s->valid.p, g->seg_gbase.p, g->seg_start.p, g->seg_end.p, g->nseg, skip_A, d_rows, ld, col0);
-	return ABW_OK;
-}
-
-// every (window, read) pair through the stable sort and the in-order accumulation; with `only` just the flagged windows, whose pairs
-// are found from the hit records of k_cov_sum
-static int coverage_sorted(abw_ctx* ctx, const abw_segments* g, const abw_read* rd, uint64_t nreads, uint32_t max_snps, int kind, double* d_rows, uint64_t ld,
-                           uint32_t col, uint64_t* d_scaf_nbps, const uint32_t* only, const uint4* hit_g0, const uchar4* hit_cnt, const uint32_t* d_status,
-                           bool* too_many_windows)
-{
-	DevBuf<uint32_t> tile_counts, keys, keys_tmp, vals, vals_tmp;
-	DevBuf<uint64_t> tile_offs, total;
-	DevBuf<uint2> run;
-	const uint64_t ngroups = (uint64_t)abw_div_up(nreads, COV_TILE) * COV_THREADS;   // hit records (groups of four reads) written by k_cov_sum
-	const unsigned int ntiles = only? abw_div_up(ngroups, FL_TILE_GROUPS) : abw_div_up(nreads, COV_TILE);
-	ABW_CUDA(ctx, tile_counts.alloc(ntiles));
-	ABW_CUDA(ctx, tile_offs.alloc(ntiles));
-	ABW_CUDA(ctx, total.alloc(1));
-	ABW_CUDA(ctx, run.alloc(g->nseg));
-	ABW_CUDA(ctx, cudaMemsetAsync(run.p, 0, sizeof(uint2) * g->nseg, ctx->stream));
-	uint64_t npairs = 0;
-	if(nreads) {
-		if(only)
-			ABW_LAUNCH(ctx, k_cov_count_flagged, ntiles, COV_THREADS, 0, hit_g0, hit_cnt, ngroups, only, tile_counts.p);
-		else
-			ABW_LAUNCH(ctx, k_cov_count, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, tile_counts.p,
-			           (unsigned long long*)d_scaf_nbps);
-		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, tile_counts.p, tile_offs.p, ntiles, total.p));
-		uint32_t status = 0;
-		ABW_CUDA(ctx, abw_fetch(ctx, &npairs, total.p, sizeof(uint64_t)));
-		if(d_status)
-			ABW_CUDA(ctx, abw_fetch(ctx, &status, d_status, sizeof(uint32_t)));
-		ABW_CUDA(ctx, abw_sync(ctx));
-		if(status & 1u) {
-			*too_many_windows = true;
-			return ABW_OK;
-		}
-	}
-	if(npairs >= (1ull << 32))
-		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_coverage: more than 2^32-1 (window, read) pairs per call; split the sample");
-	ABW_CUDA(ctx, keys.alloc(npairs));
-	ABW_CUDA(ctx, keys_tmp.alloc(npairs));
-	ABW_CUDA(ctx, vals.alloc(npairs));
-	ABW_CUDA(ctx, vals_tmp.alloc(npairs));
-	if(npairs) {
-		if(only)
-			ABW_LAUNCH(ctx, k_cov_emit_flagged, ntiles, COV_THREADS, 0, rd, hit_g0, hit_cnt, ngroups, only, g->seg_start.p, g->seg_end.p, tile_offs.p, keys.p, vals.p);
-		else
-			ABW_LAUNCH(ctx, k_cov_emit, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, tile_offs.p, keys.p, vals.p);
-		int nbits = 1;
-		while(nbits < 32 && (1ull << nbits) < g->nseg)
-			nbits++;
-		// window ids are dense: every bit below nbits varies, no need to look
-		ABW_CHECK(abw_radix_sort_pairs_u32(ctx, keys.p, keys_tmp.p, vals.p, vals_tmp.p, npairs, 1, npairs, -nbits));
-		ABW_LAUNCH(ctx, k_cov_runs, abw_div_up(npairs, 256), 256, 0, keys.p, npairs, run.p);
-	}
-	if(g->nseg && (npairs || !only)) {
-		if(kind == ABW_FEAT_TRUNC3 && only)
-			ABW_LAUNCH(ctx, (k_cov_accumulate<ABW_FEAT_TRUNC3, 32>), abw_div_up(g->nseg, 64), 64, 0, vals.p, run.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col, only);
-		else if(kind == ABW_FEAT_TRUNC3)
-			ABW_LAUNCH(ctx, (k_cov_accumulate<ABW_FEAT_TRUNC3, 8>), abw_div_up(g->nseg, 64), 64, 0, vals.p, run.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col, only);
-		else
-			ABW_LAUNCH(ctx, (k_cov_accumulate<ABW_FEAT_RAW, 8>), abw_div_up(g->nseg, 64), 64, 0, vals.p, run.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col, only);
-	}
-	return ABW_OK;
-}
-
-int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uint64_t nreads, int reads_on_device, uint32_t max_snps,
-                 int kind, double* d_rows, uint64_t ld, uint32_t col, uint64_t* d_scaf_nbps)
-{
-	if(!ctx || !g || !d_rows || (!reads && nreads))
-		return abw_fail(ctx, ABW_ERR_ARG, "abw_coverage: null argument");
-	if(nreads >= (1ull << 32))
-		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_coverage: more than 2^32-1 reads per call; split the sample");
-	if(g->nseg >= (1ull << 32))
-		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_coverage: more than 2^32-1 windows");
-	ABW_ENTER(ctx);
-	DevBuf<abw_read> d_reads;
-	const abw_read* rd = reads;
-	if(!reads_on_device && nreads) {
-		ABW_CUDA(ctx, d_reads.alloc(nreads));
-		ABW_CUDA(ctx, cudaMemcpyAsync(d_reads.p, reads, sizeof(abw_read) * nreads, cudaMemcpyHostToDevice, ctx->stream));
-		rd = d_reads.p;
-	}
-	// ABW_COVERAGE_SORT_ALL=1: every read through the sort also for three-decimal output (the first formulation; used by the tests to compare the two)
-	static const bool sort_all = [] { const char* e = getenv("ABW_COVERAGE_SORT_ALL"); return e && *e && *e != '0'; }();
-	bool too_many_windows = false;
-	if(kind == ABW_FEAT_TRUNC3 && !sort_all && nreads && g->nseg) {
-		DevBuf<unsigned long long> sum_ov;
-		DevBuf<uint32_t> flag;                             // one bit per window
-		DevBuf<uint4> hit_g0;
-		DevBuf<uchar4> hit_cnt;
-		DevBuf<uint32_t> status;
-		const unsigned int ntiles = abw_div_up(nreads, COV_TILE);
-		ABW_CUDA(ctx, sum_ov.alloc(g->nseg));
-		ABW_CUDA(ctx, flag.alloc((g->nseg + 31) / 32));
-		ABW_CUDA(ctx, hit_g0.alloc((size_t)ntiles * COV_THREADS));
-		ABW_CUDA(ctx, hit_cnt.alloc((size_t)ntiles * COV_THREADS));
-		ABW_CUDA(ctx, status.alloc(1));
-		ABW_CUDA(ctx, cudaMemsetAsync(sum_ov.p, 0, sizeof(unsigned long long) * g->nseg, ctx->stream));
-		ABW_CUDA(ctx, cudaMemsetAsync(status.p, 0, sizeof(uint32_t), ctx->stream));
-		ABW_LAUNCH(ctx, k_cov_sum, ntiles, COV_THREADS, 0, rd, nreads, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, sum_ov.p, hit_g0.p, hit_cnt.p,
-		           (unsigned long long*)d_scaf_nbps, status.p);
-		ABW_LAUNCH(ctx, k_cov_quotient, abw_div_up(g->nseg, 256), 256, 0, sum_ov.p, g->nseg, g->seg_start.p, g->seg_end.p, d_rows, ld, col, flag.p);
-		ABW_CHECK(coverage_sorted(ctx, g, rd, nreads, max_snps, kind, d_rows, ld, col, nullptr, flag.p, hit_g0.p, hit_cnt.p, status.p, &too_many_windows));
-		if(too_many_windows)                                   // a read over more than 255 windows: everything again through the sort (the read bases are counted already)
-			ABW_CHECK(coverage_sorted(ctx, g, rd, nreads, max_snps, kind, d_rows, ld, col, nullptr, nullptr, nullptr, nullptr, nullptr, &too_many_windows));
-	}
-	else
-		ABW_CHECK(coverage_sorted(ctx, g, rd, nreads, max_snps, kind, d_rows, ld, col, d_scaf_nbps, nullptr, nullptr, nullptr, nullptr, &too_many_windows));
-	// results stay on the device and every later entry point works in the order of the context stream: only a host buffer of reads has to be
-	// released by the time the call returns
-	if(!reads_on_device)
-		ABW_CUDA(ctx, abw_sync(ctx));
 	return ABW_OK;
 }
 

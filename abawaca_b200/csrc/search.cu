@@ -2052,8 +2052,10 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 
 	SweepParams sp;
 	sp.thr = prm.cluster_ndps_threshold;
-	sp.min_score = prm.min_reported_score;
-	sp.prune = (float)(prm.min_reported_score * (1.0 - 1e-5)) ;
+	// candidates below min_reported_score are not examined; that must never hide a candidate is_legal would accept, so the cut is never above
+	// the caller's product threshold (a caller who lowers product_threshold and leaves min_reported_score alone still gets every legal split)
+	sp.min_score = (s->strategy == ABW_SENS_SPEC)? std::min(prm.min_reported_score, prm.product_threshold) : prm.min_reported_score;
+	sp.prune = (float)(sp.min_score * (1.0 - 1e-5));
 	if(!(sp.prune > 0.0f))
 		sp.prune = 0.0f;
 	sp.scg_min_size = prm.scg_min_size;

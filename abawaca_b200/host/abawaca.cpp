@@ -29,6 +29,7 @@ struct Params {
 	std::string lrn_file, names_file, info_file, links_file, fasta_file, root_dir, gene2scg_file;
 	std::string scg_list_file = "/home/itaish/software/cpp/abawaca/curr-version/scg.list";   // abawaca.cpp:42; $ABW_SCG_LIST overrides it here
 	std::string build_dir, cluster_dir, fasta_dir;
+	bool scg_from_cli = false;          // -c was given: it wins over the SCG line of data.txt whatever the order of the flags
 	int ncpus = 1;          // accepted and checked like the reference (1..40); the device does not need it
 	int strategy = ABW_SENS_SPEC;
 };
@@ -67,7 +68,7 @@ static int read_params(Params& P, int argc, const char** argv)
 				else if(!strcmp(line, "Names")) P.names_file = p;
 				else if(!strcmp(line, "Lrn")) P.lrn_file = p;
 				else if(!strcmp(line, "Assembly")) P.fasta_file = p;
-				else if(!strcmp(line, "SCG")) P.gene2scg_file = p;
+				else if(!strcmp(line, "SCG")) { if(!P.scg_from_cli) P.gene2scg_file = p; }
 			}
 			fclose(fp);
 		}
@@ -80,7 +81,7 @@ static int read_params(Params& P, int argc, const char** argv)
 				return -1;
 			}
 		}
-		else if(!strcmp(argv[i], "-c") && i + 1 < argc) P.gene2scg_file = argv[++i];
+		else if(!strcmp(argv[i], "-c") && i + 1 < argc) { P.gene2scg_file = argv[++i]; P.scg_from_cli = true; }
 		else if(!strcmp(argv[i], "--split-scafs")) P.strategy = ABW_SPLIT_SCAFS;   // the alternative strategy the reference compiles but never selects (abawaca.cpp:110)
 		else {
 			std::cerr << "Unrecognizes flag: " << argv[i] << std::endl;
@@ -100,7 +101,12 @@ static int read_params(Params& P, int argc, const char** argv)
 			return -1;
 		}
 	if(!file_readable(P.fasta_file)) { std::cerr << "Could not read " << P.fasta_file << std::endl; return -1; }
-	if(!P.gene2scg_file.empty() && !file_readable(P.gene2scg_file)) { std::cerr << "Could not read " << P.gene2scg_file << std::endl; return -1; }
+	if(!P.gene2scg_file.empty() && !file_readable(P.gene2scg_file)) {
+		if(P.scg_from_cli) { std::cerr << "Could not read " << P.gene2scg_file << std::endl; return -1; }
+		// the path came from data.txt and abawaca-build could not produce the file (no gene caller on this host): run without an SCG database
+		std::cerr << "Warning: " << P.gene2scg_file << " (SCG line of data.txt) is not readable; continuing without SCG information (pass -c <gene2scg>)" << std::endl;
+		P.gene2scg_file.clear();
+	}
 	if(!file_readable(P.scg_list_file)) { std::cerr << "Could not read " << P.scg_list_file << std::endl; return -1; }
 	P.cluster_dir = P.root_dir + "/clusters";
 	P.fasta_dir = P.root_dir + "/final-clusters";
@@ -198,7 +204,7 @@ static void load_model(const Params& P, Model& M, abw_ctx* ctx)
 	M.scaf_cvg.assign(M.S(), 0);
 	for(auto& r : M.fasta) {
 		auto it = scaf_name2id.find(r.id);
-		if(it != scaf_name2id.end() && M.scaf_seq[it->second - 1] == nullptr) {
+		if(it != scaf_name2id.end()) {                 // a repeated id overwrites the earlier record (scafs[id] = Seq(...), ScafDpData.cpp:110)
 			M.scaf_seq[it->second - 1] = &r;
 			auto ci = name2cvg.find(r.id);
 			M.scaf_cvg[it->second - 1] = (ci == name2cvg.end())? 0 : ci->second;
@@ -396,7 +402,11 @@ int main(int argc, const char** argv)
 		uint32_t nrec = 0;
 		ABWH_CHECK(ctx, abw_search_set_scaffold_stats(ctx, search, M.scaf_gc.data(), M.scaf_cvg.data()));
 		ABWH_CHECK(ctx, abw_search_run(ctx, search, recs.data(), (uint32_t)recs.size(), &nrec, dp2cluster.data(), scaf2cluster.data()));
-		recs.resize(std::min<size_t>(nrec, recs.size()));
+		if(nrec > recs.size()) {
+			std::cerr << "Fatal error: " << nrec << " clusters were evaluated but only " << recs.size() << " records fit" << std::endl;
+			return -1;
+		}
+		recs.resize(nrec);
 		abw_search_destroy(search);
 
 		// membership of every evaluated cluster: terminal bins bubble up to their ancestors

@@ -276,7 +276,13 @@ int main(int argc, const char* argv[])
 		const std::string data = out_directory + "/data.txt";
 		FILE* fp = fopen(data.c_str(), "w");
 		if(!fp) { std::cerr << "Could not write to " << data << std::endl << std::endl; return -1; }
-		fprintf(fp, "SCG\t%s\n", scg_file.c_str());
+		{
+		// the reference's prepare_scgs leaves this file behind (abawaca-build.cpp:401-431); without the external gene caller it is created empty so that
+		// the two-step command line (abawaca-build, then abawaca -u DIR -o OUT) runs: no SCG information unless abawaca gets -c <gene2scg>
+		FILE* fs = fopen(scg_file.c_str(), "a");
+		if(fs) fclose(fs);
+	}
+	fprintf(fp, "SCG\t%s\n", scg_file.c_str());
 		fprintf(fp, "Links\t%s\n", links_file.c_str());
 		fprintf(fp, "Info\t%s\n", info_file.c_str());
 		fprintf(fp, "Names\t%s\n", names_file.c_str());

@@ -104,8 +104,42 @@ def fasta_to_seqset(ctx, text):
 class FeatureBuild:
     """Device-resident result of the feature stage; `rows_host()` fetches the .lrn matrix."""
 
-    def __init__(self, ctx, seqset, segs, d_rows, nseg, ncols, nscaf, d_nbps):
+    def __init__(self, ctx, seqset, segs, d_rows, nseg, ncols, nscaf, d_nbps, nk=None):
         self.ctx, self.seqset, self.segs, self.d_rows, self.nseg, self.ncols, self.nscaf, self.d_nbps = ctx, seqset, segs, d_rows, nseg, ncols, nscaf, d_nbps
+        self.nk = ncols if nk is None else nk              # k-mer columns; the remaining ncols - nk are coverage columns
+        self._milli = None
+
+    def rows_milli(self, out16=None, out32=None, wait=True):
+        """The .lrn matrix as integer thousandths (abw_rows_to_milli): uint16 [nseg][nk] k-mer columns and uint32 [nseg][ncols - nk] coverage columns,
+        a quarter of the bytes of the doubles.  out16 / out32: (pinned) buffers to fill; wait=False enqueues the copies on the copy stream
+        (complete after ctx.synchronize(); milli_inexact() then tells whether every value was an exact multiple of 0.001)."""
+        L, ctx = self.ctx.lib, self.ctx
+        ns = self.ncols - self.nk
+        n16, n32 = self.nseg * self.nk, self.nseg * ns
+        if self._milli is None:
+            self._milli = (ctx.alloc(max(n16, 1) * 2), ctx.alloc(max(n32, 1) * 4), ctx.alloc(16))
+        d16, d32, dflag = self._milli
+        ctx.memset(dflag, 0, 16)
+        ctx.check(L.abw_rows_to_milli(ctx.h, C.c_void_p(self.d_rows), self.nseg, self.ncols, 0, self.nk, 16, C.c_void_p(d16), C.c_void_p(dflag)))
+        ctx.check(L.abw_rows_to_milli(ctx.h, C.c_void_p(self.d_rows), self.nseg, self.ncols, self.nk, ns, 32, C.c_void_p(d32), C.c_void_p(dflag)))
+        k16 = np.empty(n16, dtype=np.uint16) if out16 is None else out16.reshape(-1)[:n16]
+        k32 = np.empty(n32, dtype=np.uint32) if out32 is None else out32.reshape(-1)[:n32]
+        for arr, d in ((k16, d16), (k32, d32)):
+            if arr.size:
+                if wait:
+                    ctx.to_host(arr, d)
+                else:
+                    ctx.d2h_async(arr, d)
+        return k16.reshape(self.nseg, self.nk), k32.reshape(self.nseg, ns)
+
+    def milli_inexact(self):
+        flag = np.zeros(4, dtype=np.int32)
+        self.ctx.to_host(flag, self._milli[2])
+        return int(flag[0])
+
+    def rows_milli_host(self):
+        k16, k32 = self.rows_milli()
+        return k16, k32, self.milli_inexact()
 
     def rows_host(self, out=None, wait=True):
         """The .lrn matrix.  `out`: a (pinned) float64 buffer of at least nseg*ncols elements to fill instead of a fresh array;
@@ -137,6 +171,10 @@ class FeatureBuild:
         self.ctx.check(L.abw_segments_get(self.ctx.h, self.segs, capi._p(seg_first), capi._p(seg_scaf), capi._p(seg_start), capi._p(seg_end), capi._p(seg_nonN)))
         return dict(seg_first=seg_first, seg_scaf=seg_scaf, seg_start=seg_start, seg_end=seg_end, seg_nonN=seg_nonN)
 
+    def segments_async(self, seg_scaf, seg_start, seg_end, seg_nonN):
+        """the window table into pinned numpy buffers (uint32, 3 x uint64, at least nseg elements each) on the copy stream; complete after ctx.synchronize()"""
+        self.ctx.check(self.ctx.lib.abw_segments_get_async(self.ctx.h, self.segs, capi._p(seg_scaf), capi._p(seg_start), capi._p(seg_end), capi._p(seg_nonN)))
+
     def scaffold_stats_host(self, lengths):
         """(.info columns) length-normalised coverage of the -c sample, GC and N count -- abawaca-build.cpp:597"""
         nN = np.zeros(self.nscaf, dtype=np.uint64)
@@ -161,6 +199,10 @@ class FeatureBuild:
         if self.d_nbps:
             self.ctx.free(self.d_nbps)
             self.d_nbps = None
+        if self._milli is not None:
+            for d in self._milli:
+                self.ctx.free(d)
+            self._milli = None
         if self.segs:
             L.abw_segments_destroy(self.segs)
             self.segs = None
@@ -169,10 +211,39 @@ class FeatureBuild:
             self.seqset = None
 
 
+class ReadSample:
+    """One sample's read records for build_features: either abw_read records (READ_DTYPE, the device applies the filter of abawaca-build.cpp:546-550)
+    or compact abw_read8 records of the reads that passed it on the host (compact_reads), as host arrays or as device pointers."""
+
+    def __init__(self, fmt, n, recs=None, length=0, len16=None, d_recs=None, d_len16=None):
+        self.fmt, self.n, self.recs, self.length, self.len16, self.d_recs, self.d_len16 = fmt, int(n), recs, int(length), len16, d_recs, d_len16
+
+    @property
+    def nbytes(self):
+        return self.n * (16 if self.fmt == capi.READS_FULL else 8) + (2 * self.n if (self.len16 is not None or self.d_len16) else 0)
+
+
+def compact_reads(r, nscaf, max_snps=15) -> ReadSample:
+    """What a host-side SAM parser hands over when it applies the read filter itself (abawaca-build.cpp:546-550: mapped, not a secondary alignment,
+    at most max_snps mismatches, scaffold known): 8-byte records in SAM order, one length for the sample or uint16 lengths."""
+    flag, nsnps = r["flag_nsnps"] & 0xFFFF, r["flag_nsnps"] >> 16
+    ok = ((flag & 0x104) == 0) & (nsnps <= max_snps) & (r["scaf"] < nscaf)
+    rr = r[ok]
+    out = np.empty(rr.size, dtype=capi.READ8_DTYPE)
+    out["scaf"], out["pos0"] = rr["scaf"], rr["pos0"]
+    lens = rr["len"]
+    if lens.size == 0 or bool((lens == lens[0]).all()):
+        return ReadSample(capi.READS_COMPACT, out.size, out, int(lens[0]) if lens.size else 0)
+    if int(lens.max()) > 65535:
+        raise ValueError("reads longer than 65535 bases need the full record format")
+    return ReadSample(capi.READS_COMPACT, out.size, out, 0, lens.astype(np.uint16))
+
+
 def build_features(ctx: capi.Context, seq, offsets, reads, this_sample=0, params=None, kind=capi.FEAT_TRUNC3, skip_A=True,
-                   seq_on_device=False, reads_on_device=False, nreads=None, timings=None, overlap_h2d=False, seqset=None) -> FeatureBuild:
+                   seq_on_device=False, reads_on_device=False, nreads=None, timings=None, overlap_h2d=False, seqset=None, per_sample_calls=False) -> FeatureBuild:
     """seq: uint8 ASCII (numpy array, or a device pointer int when seq_on_device); offsets: uint64 [nscaf+1];
-    reads: one structured array (capi.READ_DTYPE) per sample (or device pointers + nreads)."""
+    reads: per sample a structured array (capi.READ_DTYPE), a ReadSample, or a device pointer of abw_read records (reads_on_device, with nreads).
+    All samples go through ONE abw_coverage_batch call (per_sample_calls=True: one abw_coverage call per sample, full records only)."""
     L = ctx.lib
     p = params or capi.default_params()
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
@@ -185,25 +256,47 @@ def build_features(ctx: capi.Context, seq, offsets, reads, this_sample=0, params
             now = time.perf_counter()
             timings[name] = timings.get(name, 0.0) + 1000.0 * (now - t_last[0])
             t_last[0] = now
+    samples = []
+    for j, r in enumerate(reads):
+        if isinstance(r, ReadSample):
+            samples.append(r)
+        elif reads_on_device:
+            samples.append(ReadSample(capi.READS_FULL, nreads[j], d_recs=r))
+        else:
+            r = np.ascontiguousarray(r)
+            samples.append(ReadSample(capi.READS_FULL, r.size, r))
     staged = []
-    tickets = None
-    if overlap_h2d and not seq_on_device and not reads_on_device:
-        # enqueue every host->device copy up front on the copy stream (inputs should be pinned); each stage waits for its own
+    tickets = [0] * len(samples)
+    t_seq = 0
+    if not seq_on_device and seqset is None and overlap_h2d:
         seq = np.ascontiguousarray(seq, dtype=np.uint8)
         d_seq = ctx.alloc(seq.nbytes + 64)
         staged.append(d_seq)
-        t_seq = ctx.h2d_async(d_seq, seq)
-        tickets, dev_reads, nreads = [], [], []
-        for r in reads:
-            r = np.ascontiguousarray(r)
-            d = ctx.alloc(max(r.nbytes, 16))
-            staged.append(d)
-            tickets.append(ctx.h2d_async(d, r) if r.nbytes else 0)
-            dev_reads.append(d)
-            nreads.append(int(r.size))
+        t_seq = ctx.h2d_async(d_seq, seq)                  # enqueue every host->device copy up front on the copy stream (inputs should be pinned)
+        seq, seq_on_device = d_seq, True
+    dev = []                                               # (records, len16) device pointers per sample
+    for j, sm in enumerate(samples):
+        if sm.d_recs is not None:
+            dev.append((sm.d_recs, sm.d_len16))
+            continue
+        recs = np.ascontiguousarray(sm.recs)
+        d = ctx.alloc(max(recs.nbytes, 16))
+        staged.append(d)
+        d16 = None
+        if sm.len16 is not None:
+            d16 = ctx.alloc(max(sm.len16.nbytes, 16))
+            staged.append(d16)
+        if overlap_h2d:
+            if sm.len16 is not None and sm.n:
+                ctx.h2d_async(d16, sm.len16)
+            tickets[j] = ctx.h2d_async(d, recs) if sm.n else 0   # copies of one stream complete in order: the later ticket covers both
+        elif sm.n:
+            ctx.to_device(d, recs)
+            if sm.len16 is not None:
+                ctx.to_device(d16, sm.len16)
+        dev.append((d, d16))
+    if t_seq:
         ctx.wait_h2d(t_seq)
-        seq, reads = d_seq, dev_reads
-        seq_on_device = reads_on_device = True
     if seqset is not None:
         pass                                               # packed elsewhere (fasta_to_seqset); offsets only carry the scaffold count
     elif seq_on_device:
@@ -219,26 +312,29 @@ def build_features(ctx: capi.Context, seq, offsets, reads, this_sample=0, params
     lap("segment_ms")
     nseg = int(L.abw_segments_count(segs))
     nk = capi.NKMER - (1 if skip_A else 0)
-    ncols = nk + len(reads)
+    ncols = nk + len(samples)
     d_rows = ctx.alloc(max(nseg * ncols, 1) * 8)
     d_nbps = ctx.alloc(max(nscaf, 1) * 8)
     ctx.memset(d_nbps, 0, max(nscaf, 1) * 8)
     ctx.check(L.abw_kmer_features(ctx.h, seqset, segs, kind, 1 if skip_A else 0, C.c_void_p(d_rows), ncols, 0))
     lap("kmer_ms")
-    for j, r in enumerate(reads):
-        nb = C.c_void_p(d_nbps) if j == this_sample else None
-        if reads_on_device:
-            if tickets is not None:
-                ctx.wait_h2d(tickets[j])
-            ctx.check(L.abw_coverage(ctx.h, segs, C.c_void_p(r), nreads[j], 1, p.max_snps, kind, C.c_void_p(d_rows), ncols, nk + j, nb))
-        else:
-            r = np.ascontiguousarray(r)
-            ctx.check(L.abw_coverage(ctx.h, segs, capi._p(r), r.size, 0, p.max_snps, kind, C.c_void_p(d_rows), ncols, nk + j, nb))
+    if per_sample_calls:
+        for j, sm in enumerate(samples):
+            assert sm.fmt == capi.READS_FULL
+            ctx.wait_h2d(tickets[j])
+            nb = C.c_void_p(d_nbps) if j == this_sample else None
+            ctx.check(L.abw_coverage(ctx.h, segs, C.c_void_p(dev[j][0]), sm.n, 1, p.max_snps, kind, C.c_void_p(d_rows), ncols, nk + j, nb))
+    elif samples:
+        arr = (capi.Sample * len(samples))()
+        for j, sm in enumerate(samples):
+            arr[j].reads, arr[j].nreads, arr[j].format, arr[j].len, arr[j].len16, arr[j].h2d_ticket = dev[j][0], sm.n, sm.fmt, sm.length, dev[j][1], tickets[j]
+        ctx.check(L.abw_coverage_batch(ctx.h, segs, arr, len(samples), p.max_snps, kind, C.c_void_p(d_rows), ncols, nk,
+                                       this_sample if this_sample is not None else -1, C.c_void_p(d_nbps)))
     ctx.synchronize()
     for d in staged:
         ctx.free(d)
     lap("coverage_ms")
-    return FeatureBuild(ctx, seqset, segs, d_rows, nseg, ncols, nscaf, d_nbps)
+    return FeatureBuild(ctx, seqset, segs, d_rows, nseg, ncols, nscaf, d_nbps, nk)
 
 
 def search_problem_from_counts(counts):

@@ -262,6 +262,18 @@ def main():
     # pinned host copies (e2e) and device-resident copies (value)
     h_seq = torch.from_numpy(mg.seq).pin_memory()
     h_reads = [torch.from_numpy(r.view(np.uint32).reshape(-1, 4)).pin_memory() for r in mg.reads]
+    # end-to-end path: what a host-side SAM parser hands over when it applies the read filter itself (abawaca-build.cpp:546-550):
+    # 8-byte records {scaffold, position} of the accepted reads in SAM order, one read length per sample (pipeline.compact_reads), in pinned memory
+    h_compact = []
+    for r in mg.reads:
+        c = pipeline.compact_reads(r, mg.nscaf)
+        t = torch.from_numpy(c.recs.view(np.uint32).reshape(-1, 2)).pin_memory()
+        c.recs = t.numpy().view(capi.READ8_DTYPE).reshape(-1)
+        c._pin = t
+        if c.len16 is not None:
+            t16 = torch.from_numpy(c.len16).pin_memory()
+            c.len16, c._pin16 = t16.numpy(), t16
+        h_compact.append(c)
     d_seq = ctx.alloc(total_bp + 64)
     ctx.to_device(d_seq, mg.seq)
     d_reads = []
@@ -272,14 +284,13 @@ def main():
 
     state = {}
     result_buffers = {}                                # records and bin arrays of the search, reused by every step
-    h_reads_np = [t.numpy().view(capi.READ_DTYPE).reshape(-1) for t in h_reads]
     dev = torch.device("cuda", local_rank)
 
     def step(resident, timings=None):
         if resident:
             fb = pipeline.build_features(ctx, d_seq, mg.offsets, d_reads, this_sample=0, seq_on_device=True, reads_on_device=True, nreads=nreads, timings=timings)
         else:
-            fb = pipeline.build_features(ctx, h_seq.numpy(), mg.offsets, h_reads_np, this_sample=0, timings=timings, overlap_h2d=True)
+            fb = pipeline.build_features(ctx, h_seq.numpy(), mg.offsets, h_compact, this_sample=0, timings=timings, overlap_h2d=True)
         t_a = time.perf_counter()
         seg_first = fb.seg_first_host()
         t_b = time.perf_counter()
@@ -296,10 +307,17 @@ def main():
             timings["segments_host_ms"] = 1000.0 * (t_b - t_a)
             timings["search_problem_ms"] = 1000.0 * (time.perf_counter() - t_b)
         if not resident:
-            # the .lrn matrix goes back to the host (pinned buffer) in the end-to-end path, while the split search runs
-            if state.get("h_rows") is None or state["h_rows"].numel() < fb.nseg * fb.ncols:
-                state["h_rows"] = torch.empty(int(fb.nseg * fb.ncols * 1.05) + 1024, dtype=torch.float64).pin_memory()
-            fb.rows_host(out=state["h_rows"].numpy(), wait=False)
+            # the .lrn matrix goes back to the host (pinned buffers) in the end-to-end path, while the split search runs: as integer thousandths
+            # (uint16 k-mer columns, uint32 coverage columns; abw_rows_to_milli), which is what the text writer prints anyway
+            ns_cov = fb.ncols - fb.nk
+            if state.get("h_k16") is None or state["h_k16"].numel() < fb.nseg * fb.nk or state["h_k32"].numel() < fb.nseg * ns_cov:
+                state["h_k16"] = torch.empty(int(fb.nseg * fb.nk * 1.05) + 1024, dtype=torch.int16).pin_memory()
+                state["h_k32"] = torch.empty(int(fb.nseg * ns_cov * 1.05) + 1024, dtype=torch.int32).pin_memory()
+            if state.get("h_seg") is None or state["h_seg"][0].numel() < fb.nseg:
+                cap = int(fb.nseg * 1.05) + 1024
+                state["h_seg"] = [torch.empty(cap, dtype=torch.int32).pin_memory()] + [torch.empty(cap, dtype=torch.int64).pin_memory() for _ in range(3)]
+            fb.segments_async(state["h_seg"][0].numpy().view(np.uint32), *[t.numpy().view(np.uint64) for t in state["h_seg"][1:]])   # the .names columns
+            fb.rows_milli(out16=state["h_k16"].numpy().view(np.uint16), out32=state["h_k32"].numpy().view(np.uint32), wait=False)
         if world == 1:
             res = pipeline.search(ctx, fb.d_rows, None, T, lengths[kept], masks[kept], layout=capi.LAYOUT_ROWMAJOR, values_on_device=True,
                                   nrows=fb.nseg, D=fb.ncols, ld=fb.ncols, row_of_dp=row_of_dp, timings=timings, buffers=result_buffers)
@@ -341,6 +359,8 @@ def main():
             del full
         if not resident:
             ctx.synchronize()                          # the matrix has arrived on the host (copy stream) before the step counts as done
+            if fb.milli_inexact():
+                raise SystemExit("bench.py: a feature value is not a multiple of 0.001")
         state.update(ndps=ndps_total, nseg=fb.nseg, ncols=fb.ncols, prof=res.profile, nclusters=len(res.recs), nbins=nbins,
                      bins=res.scaf2cluster)
         if timings is not None:                        # window lengths: only needed for the algorithmic byte count of the k-mer kernel
@@ -465,9 +485,9 @@ def main():
     total_scaf = nscaf * world
     value = total_scaf * args.steps / (ms_res * 1e-3)
     e2e_value = total_scaf * args.steps / (ms_e2e * 1e-3)
-    h2d = total_bp + sum(r.nbytes for r in mg.reads) + mg.offsets.nbytes + state["nseg"] * 4 + nscaf * (4 + 8 + 8 * masks.shape[1])
-    # .lrn matrix + window table + per-scaffold bins + per-datapoint bins
-    d2h = state["nseg"] * state["ncols"] * 8 + state["nseg"] * (4 + 3 * 8) + (nscaf + 1) * 8 + nscaf * 4 + state["nseg"] * 4
+    h2d = total_bp + sum(c.nbytes for c in h_compact) + mg.offsets.nbytes + state["nseg"] * 4 + nscaf * (4 + 8 + 8 * masks.shape[1])
+    # .lrn matrix as integer thousandths (2 bytes per k-mer value, 4 per coverage value) + window table + per-scaffold bins + per-datapoint bins
+    d2h = state["nseg"] * (179 * 2 + len(mg.reads) * 4) + state["nseg"] * (4 + 3 * 8) + (nscaf + 1) * 8 + nscaf * 4 + state["nseg"] * 4
 
     bins_total = state["nbins"]                       # every rank ends with the bins of the whole community
 

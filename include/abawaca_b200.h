@@ -49,10 +49,11 @@ typedef struct {
 	double   split_scaf_ratio_threshold; /* 0.1     ClusterSeparatorSplitScafs.h:44 */
 	uint32_t max_snps;                   /* 15      abawaca-build.cpp:437 */
 	uint32_t window_size;                /* 2000    abawaca-build.cpp:436 */
-	/* Not in the reference: candidates scoring below this are not examined.  The default, equal to
-	 * product_threshold, cannot change any split (a best separation below it fails is_legal), but the
-	 * best separation reported for a TERMINAL cluster is then only found if it is legal.  Set to 0 to
-	 * also reproduce the reference's log line for terminal clusters. */
+	/* Not in the reference: candidates scoring below min(min_reported_score, product_threshold) are not
+	 * examined.  That cannot change any split (a best separation below product_threshold fails is_legal,
+	 * whatever the other thresholds are), but the best separation reported for a TERMINAL cluster is
+	 * then only found if it scores at least that much.  Set to 0 to also reproduce the reference's log
+	 * line for terminal clusters. */
 	double   min_reported_score;
 } abw_params;
 
@@ -100,6 +101,10 @@ uint64_t abw_segments_count(const abw_segments* g);
 /* host copies (any pointer may be NULL): seg_first[nscaf+1], and per segment scaffold, 1-based inclusive start/end, non-N bases */
 int abw_segments_get(abw_ctx* ctx, const abw_segments* g, uint64_t* h_seg_first, uint32_t* h_seg_scaf, uint64_t* h_seg_start, uint64_t* h_seg_end, uint64_t* h_seg_nonN);
 
+/* the same per-window arrays into PINNED host buffers on the copy stream (like abw_d2h_async: overlaps what is enqueued next, complete after
+ * abw_ctx_synchronize); the segments object must stay alive until then */
+int abw_segments_get_async(abw_ctx* ctx, const abw_segments* g, uint32_t* h_seg_scaf, uint64_t* h_seg_start, uint64_t* h_seg_end, uint64_t* h_seg_nonN);
+
 #define ABW_FEAT_TRUNC3 0   /* int(1000*x)/1000.0, the value abawaca-build prints with %.3lf (abawaca-build.cpp:603) */
 #define ABW_FEAT_RAW    1   /* the un-truncated double */
 /* Replaces Scaf_segment::Scaf_segment (abawaca-build.cpp:103-174).  Writes, for every segment, the 180 canonical
@@ -114,6 +119,37 @@ int abw_kmer_features(abw_ctx* ctx, const abw_seqset* s, const abw_segments* g, 
  * same context see its results; a host that reads d_rows through its own stream calls abw_ctx_synchronize first). */
 int abw_coverage(abw_ctx* ctx, const abw_segments* g, const abw_read* reads, uint64_t nreads, int reads_on_device, uint32_t max_snps,
                  int kind, double* d_rows, uint64_t ld, uint32_t col, uint64_t* d_scaf_nbps);
+
+/* Several samples in one call, in either record format.  ABW_READS_FULL: abw_read records, the read filter (:546-550) is applied on the device.
+ * ABW_READS_COMPACT: abw_read8 records of the reads that PASSED that filter on the host (the host parser may pre-filter), in SAM
+ * order, 8 bytes instead of 16 over the host link; every read is `len` bases long unless len16 gives per-read lengths (reads longer than 65535 bases
+ * need the full format).  Record arrays (and len16) are DEVICE memory; h2d_ticket (0: none) is the abw_h2d_async ticket they depend on -- the call
+ * waits for it on the device just before the sample's first kernel, so the records of later samples may still be in flight when it is made.
+ * Writes columns [col0, col0 + nsamples) of `rows`.  With three-decimal output the windows whose third decimal depends on the order of the reads
+ *  are collected over ALL samples and go through one stable sort instead of one per sample.
+ * this_sample (-1: none): index of the -c sample whose accepted read lengths are added to d_scaf_nbps (:242-243). */
+typedef struct {
+	uint32_t scaf;        /* 0-based scaffold index */
+	uint32_t pos0;        /* SAM POS - 1 */
+} abw_read8;
+#define ABW_READS_FULL    0
+#define ABW_READS_COMPACT 1
+typedef struct {
+	const void*     reads;       /* abw_read[nreads] or abw_read8[nreads], device memory */
+	uint64_t        nreads;
+	int32_t         format;
+	uint32_t        len;         /* compact: read length when len16 is NULL */
+	const uint16_t* len16;       /* compact, optional: per-read lengths, device memory */
+	uint64_t        h2d_ticket;
+} abw_sample;
+int abw_coverage_batch(abw_ctx* ctx, const abw_segments* g, const abw_sample* h_samples, uint32_t nsamples, uint32_t max_snps, int kind, double* d_rows, uint64_t ld,
+                       uint32_t col0, int32_t this_sample, uint64_t* d_scaf_nbps);
+
+/* The values abawaca-build prints are multiples of 0.001 (int(1000*x)/1000.0, abawaca-build.cpp:603): columns [col0, col0 + ncols) of the row-major
+ * matrix as integer thousandths, row-major [nrows][ncols] of uint16_t (bits = 16; k-mer frequencies are at most 1000) or uint32_t (bits = 32; coverage),
+ * a quarter / half of the bytes for the trip to the host; k / 1000.0 gives back the identical double.  Enqueued on the context stream; *d_inexact
+ * (device int32, set to 0 by the caller) is incremented for every value that is not exactly k / 1000.0 with k in range -- the caller then fetches the doubles. */
+int abw_rows_to_milli(abw_ctx* ctx, const double* d_rows, uint64_t nrows, uint64_t ld, uint32_t col0, uint32_t ncols, int bits, void* d_out, int32_t* d_inexact);
 
 /* ---- SAM text -> read records on the device ------------------------------------------------
  * abw_names: the scaffold names as a device-side hash table; name i is names_blob[h_name_off[i] .. h_name_off[i+1]) and gets index i

@@ -4,9 +4,9 @@
 // The reference adds fl(overlap_i / window length) in SAM order (an order-dependent fp64 sum, quirk Q5) and prints int(1000 * sum) / 1000.0.
 // Formulation here:
 //   pass 1  k_cov_sum       one pass over the read records: window(s) of every read by arithmetic on a 16-byte scaffold record, overlap added to a
-//                           64-bit integer sum per (sample, window).  Reads of a warp that hit the same window are combined first
-//                           (__match_any_sync + __reduce_add_sync): one atomic per distinct window and warp instead of one per read.  Every tile of
-//                           1024 reads also leaves the range of windows it touched.
+//                           64-bit integer sum per (sample, window).  The overlaps of a tile of 1024 reads are first combined in a shared-memory
+//                           table indexed by window (shared atomics): one global atomic per touched window and tile instead of one per read.  Every
+//                           tile also leaves the range of windows it touched.
 //           k_cov_quotient  one thread per (sample, window): where the truncation to three decimals cannot depend on the order of the reads the value
 //                           follows from the integer sum alone; the other windows (the exact value IS a multiple of 0.001, or a huge sum) are flagged.
 //   pass 2  k_cov_pairs     only tiles whose window range holds a flagged window are read again; their (flagged window, overlap) pairs of ALL samples are
@@ -143,7 +143,8 @@ struct WinIter {
 	}
 };
 
-// dst[key] += v for the lanes with `valid`, one atomic per distinct key of the warp.  Every lane of the warp calls it.
+// dst[key] += v for the lanes with `valid`, one atomic per distinct key of the warp.  Every lane of the warp calls it.  (Used where it runs once per
+// thread; in the hot loop of k_cov_sum the per-group reduction of a non-uniform mask compiles to a loop over the groups and was the bottleneck.)
 __device__ __forceinline__ void warp_add_by_key(unsigned long long* __restrict__ dst, uint32_t key, uint32_t v, bool valid)
 {
 	if(__any_sync(FULL, valid && v >= (1u << 26))) {           // a 32-bit warp sum could overflow: plain atomics (reads are never that long in practice)
@@ -157,13 +158,33 @@ __device__ __forceinline__ void warp_add_by_key(unsigned long long* __restrict__
 		atomicAdd(&dst[key], (unsigned long long)sum);
 }
 
-// pass 1: integer sum of the overlaps per window (order free), window range of every tile, per-scaffold read bases of the -c sample (:242-243)
+// pass 1: integer sum of the overlaps per window (order free), window range of every tile, per-scaffold read bases of the -c sample (:242-243).
+// A tile of 1024 consecutive reads of a SAM file in scaffold or coordinate order touches a handful of neighbouring windows: the overlaps are first
+// added up in a shared-memory table indexed by (window - lowest window of the tile) with shared atomics, and every touched window then costs ONE
+// 64-bit global atomic per tile.  Windows beyond the table (reads in no particular order) and overlaps of 2^20 bases or more go to global memory directly.
+constexpr uint32_t CS_RANGE = 2048;                         // windows per tile held in shared memory
+constexpr uint32_t CS_SCAFS = 512;                          // scaffolds per tile held in shared memory (-c sample only)
+constexpr uint32_t CS_MAX_OV = 1u << 20;                    // 2048 overlaps below 2^20 cannot overflow a 32-bit table entry
+
 template <bool NBPS>
 __global__ void __launch_bounds__(COV_THREADS, 4) k_cov_sum(const ReadSrc src, uint32_t max_snps, uint32_t nscaf, const uint4* __restrict__ scaf_info,
                                                            const uint64_t* __restrict__ seg_end, unsigned long long* __restrict__ sum_ov,
                                                            uint2* __restrict__ tile_range, unsigned long long* __restrict__ scaf_nbps)
 {
-	__shared__ uint32_t sm_min[COV_THREADS / 32], sm_max[COV_THREADS / 32];
+	__shared__ uint32_t sm_acc[CS_RANGE];
+	__shared__ uint32_t sm_nb[NBPS? CS_SCAFS : 1];
+	__shared__ uint32_t sm_min, sm_max, sm_smin;
+	for(uint32_t i = threadIdx.x; i < CS_RANGE; i += COV_THREADS)
+		sm_acc[i] = 0;
+	if(NBPS)
+		for(uint32_t i = threadIdx.x; i < CS_SCAFS; i += COV_THREADS)
+			sm_nb[i] = 0;
+	if(threadIdx.x == 0) {
+		sm_min = 0xFFFFFFFFu;
+		sm_max = 0;
+		sm_smin = 0xFFFFFFFFu;
+	}
+	__syncthreads();
 	const uint64_t r0 = ((uint64_t)blockIdx.x * COV_THREADS + threadIdx.x) * COV_ITEMS;
 	Rd4 rd;
 	load_reads4(src, r0, max_snps, nscaf, rd);
@@ -171,56 +192,89 @@ __global__ void __launch_bounds__(COV_THREADS, 4) k_cov_sum(const ReadSrc src, u
 #pragma unroll
 	for(int j = 0; j < COV_ITEMS; j++)
 		si[j] = rd.acc[j]? __ldg(scaf_info + rd.scaf[j]) : make_uint4(0, 0, 1, 0);
-	uint32_t gmin = 0xFFFFFFFFu, gmax = 0;
+	// first and second window of every read; further windows (reads longer than a window: rare) go to global memory at once
+	uint32_t g1[COV_ITEMS], ov1[COV_ITEMS], ov2[COV_ITEMS];    // ov == 0: no such window (an overlap is at least 1)
+	uint32_t gmin = 0xFFFFFFFFu, gmax = 0, smin = 0xFFFFFFFFu;
 #pragma unroll
 	for(int j = 0; j < COV_ITEMS; j++) {
-		if(NBPS)
-			warp_add_by_key(scaf_nbps, rd.scaf[j], rd.len[j], rd.acc[j]);
+		g1[j] = 0; ov1[j] = 0; ov2[j] = 0;
+		if(NBPS && rd.acc[j])
+			smin = min(smin, rd.scaf[j]);
+		if(!(rd.acc[j] && si[j].y > 0))
+			continue;
 		WinIter it;
-		bool has = false;
-		if(rd.acc[j] && si[j].y > 0) {
-			it.init(rd.pos0[j], rd.len[j], si[j], seg_end);
-			has = it.valid();
-		}
-		if(has) {
-			gmin = min(gmin, it.g);
+		it.init(rd.pos0[j], rd.len[j], si[j], seg_end);
+		if(!it.valid())
+			continue;
+		g1[j] = it.g;
+		ov1[j] = it.overlap();
+		gmin = min(gmin, it.g);
+		gmax = max(gmax, it.g);
+		it.next();
+		if(it.valid()) {
+			ov2[j] = it.overlap();
 			gmax = max(gmax, it.g);
-		}
-		warp_add_by_key(sum_ov, has? it.g : 0u, has? it.overlap() : 0u, has);
-		bool has2 = false;
-		if(has) {
-			it.next();
-			has2 = it.valid();
-		}
-		if(__any_sync(FULL, has2)) {                            // reads over a window boundary (7 % with 150-base reads and 2000-base windows)
-			if(has2)
+			for(it.next(); it.valid(); it.next()) {
+				atomicAdd(&sum_ov[it.g], (unsigned long long)it.overlap());
 				gmax = max(gmax, it.g);
-			warp_add_by_key(sum_ov, has2? it.g : 0u, has2? it.overlap() : 0u, has2);
-			if(has2) {
-				it.next();
-				while(it.valid()) {                             // reads longer than a window: rare, plain atomics
-					atomicAdd(&sum_ov[it.g], (unsigned long long)it.overlap());
-					gmax = max(gmax, it.g);
-					it.next();
-				}
 			}
 		}
 	}
 	gmin = __reduce_min_sync(FULL, gmin);
 	gmax = __reduce_max_sync(FULL, gmax);
+	if(NBPS)
+		smin = __reduce_min_sync(FULL, smin);
 	if((threadIdx.x & 31) == 0) {
-		sm_min[threadIdx.x >> 5] = gmin;
-		sm_max[threadIdx.x >> 5] = gmax;
+		if(gmin <= gmax) {
+			atomicMin(&sm_min, gmin);
+			atomicMax(&sm_max, gmax);
+		}
+		if(NBPS && smin != 0xFFFFFFFFu)
+			atomicMin(&sm_smin, smin);
 	}
 	__syncthreads();
-	if(threadIdx.x == 0) {
+	const uint32_t base = sm_min, top = sm_max, sbase = sm_smin;
+	if(threadIdx.x == 0)
+		tile_range[src.tile0 + blockIdx.x] = make_uint2(base, top);        // base > top: the tile touches no window
 #pragma unroll
-		for(int w = 1; w < COV_THREADS / 32; w++) {
-			gmin = min(gmin, sm_min[w]);
-			gmax = max(gmax, sm_max[w]);
+	for(int j = 0; j < COV_ITEMS; j++) {
+		if(NBPS && rd.acc[j]) {
+			const uint32_t rel = rd.scaf[j] - sbase;
+			if(rel < CS_SCAFS && rd.len[j] < CS_MAX_OV)
+				atomicAdd(&sm_nb[rel], rd.len[j]);
+			else
+				atomicAdd(&scaf_nbps[rd.scaf[j]], (unsigned long long)rd.len[j]);
 		}
-		tile_range[src.tile0 + blockIdx.x] = make_uint2(gmin, gmax);        // gmin > gmax: the tile touches no window
+		if(ov1[j]) {
+			const uint32_t rel = g1[j] - base;
+			if(rel < CS_RANGE && ov1[j] < CS_MAX_OV)
+				atomicAdd(&sm_acc[rel], ov1[j]);
+			else
+				atomicAdd(&sum_ov[g1[j]], (unsigned long long)ov1[j]);
+		}
+		if(ov2[j]) {
+			const uint32_t rel = g1[j] + 1 - base;
+			if(rel < CS_RANGE && ov2[j] < CS_MAX_OV)
+				atomicAdd(&sm_acc[rel], ov2[j]);
+			else
+				atomicAdd(&sum_ov[g1[j] + 1], (unsigned long long)ov2[j]);
+		}
 	}
+	__syncthreads();
+	if(base <= top) {
+		const uint32_t n = min(top - base + 1, CS_RANGE);
+		for(uint32_t i = threadIdx.x; i < n; i += COV_THREADS) {
+			const uint32_t v = sm_acc[i];
+			if(v)
+				atomicAdd(&sum_ov[base + i], (unsigned long long)v);
+		}
+	}
+	if(NBPS && sbase != 0xFFFFFFFFu)
+		for(uint32_t i = threadIdx.x; i < CS_SCAFS && sbase + i < nscaf; i += COV_THREADS) {
+			const uint32_t v = sm_nb[i];
+			if(v)
+				atomicAdd(&scaf_nbps[sbase + i], (unsigned long long)v);
+		}
 }
 
 // one thread per (sample, window): the value from the integer sum where the truncation cannot depend on the order of the reads, a flag elsewhere.
@@ -263,125 +317,143 @@ __global__ void __launch_bounds__(256) k_cov_quotient(const unsigned long long* 
 	}
 }
 
-// pass 2, count (EMIT = false) and emit (EMIT = true): the (window, overlap) pairs of the reads of a tile, in read order then window order, for the
-// flagged windows only (ALL = false) or for every window (ALL = true).  key = sample * nseg + window.  grid = (tiles of the longest sample, samples).
+// pass 2, tile filter: one thread per tile of the batch.  A tile whose window range holds no flagged window (reads in scaffold or coordinate order: a
+// tile spans a few scaffolds, and most tiles stop here) gets a pair count of zero; the others are listed (in no particular order: every tile writes
+// its pairs at its own offset).  ALL: every tile is listed.
+__global__ void __launch_bounds__(256) k_cov_tile_filter(const ReadSrc* __restrict__ srcs, uint32_t ns, uint32_t total_tiles, const uint32_t* __restrict__ flag_bits,
+                                                         uint32_t nwords, const uint32_t* __restrict__ nflagged, const uint2* __restrict__ tile_range, int all,
+                                                         uint32_t* __restrict__ tile_counts, uint2* __restrict__ list, uint32_t* __restrict__ nlist)
+{
+	const uint32_t flat = blockIdx.x * blockDim.x + threadIdx.x;
+	bool go = false;
+	uint32_t sample = 0;
+	if(flat < total_tiles) {
+		while(sample + 1 < ns && srcs[sample + 1].tile0 <= flat)
+			sample++;
+		go = all != 0;
+		if(!all) {
+			const uint2 tr = tile_range[flat];
+			if(tr.x <= tr.y && nflagged[sample] > 0) {
+				const uint32_t* __restrict__ flags = flag_bits + (uint64_t)sample * nwords;
+				const uint32_t w0 = tr.x >> 5, w1 = tr.y >> 5;
+				if(w1 - w0 >= 256u)
+					go = true;                                  // reads in no particular order: the tile spans everything
+				else
+					for(uint32_t w = w0; w <= w1 && !go; w++) {
+						uint32_t m = __ldg(flags + w);
+						if(w == w0) m &= 0xFFFFFFFFu << (tr.x & 31u);
+						if(w == w1) m &= 0xFFFFFFFFu >> (31u - (tr.y & 31u));
+						go = m != 0;
+					}
+			}
+			if(!go)
+				tile_counts[flat] = 0;
+		}
+	}
+	// warp-aggregated append
+	const uint32_t m = __ballot_sync(FULL, go);
+	if(m) {
+		const int lane = threadIdx.x & 31;
+		uint32_t base = 0;
+		if(lane == __ffs(m) - 1)
+			base = atomicAdd(nlist, (uint32_t)__popc(m));
+		base = __shfl_sync(FULL, base, __ffs(m) - 1);
+		if(go)
+			list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2(sample, flat - srcs[sample].tile0);
+	}
+}
+
+// pass 2, count (EMIT = false) and emit (EMIT = true): the (window, overlap) pairs of the reads of a listed tile, in read order then window order, for the
+// flagged windows only (ALL = false) or for every window (ALL = true).  key = sample * nseg + window.  CTAs walk the list.
 template <bool EMIT, bool ALL>
 __global__ void __launch_bounds__(COV_THREADS) k_cov_pairs(const ReadSrc* __restrict__ srcs, uint32_t max_snps, uint32_t nscaf, const uint4* __restrict__ scaf_info,
                                                           const uint64_t* __restrict__ seg_end, uint64_t nseg, const uint32_t* __restrict__ flag_bits, uint32_t nwords,
-                                                          const uint32_t* __restrict__ nflagged, const uint2* __restrict__ tile_range, uint32_t* __restrict__ tile_counts,
+                                                          const uint2* __restrict__ list, const uint32_t* __restrict__ nlist, uint32_t* __restrict__ tile_counts,
                                                           const uint64_t* __restrict__ tile_offs, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                           unsigned long long* __restrict__ scaf_nbps, int nbps_sample)
 {
 	__shared__ uint32_t sm[COV_THREADS / 32];
-	__shared__ int sm_go;
-	const uint32_t sample = blockIdx.y;
-	const ReadSrc src = srcs[sample];
-	if(blockIdx.x >= src.ntiles)
-		return;
-	const uint32_t flat = src.tile0 + blockIdx.x;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t* __restrict__ flags = ALL? nullptr : flag_bits + (uint64_t)sample * nwords;
-	if(EMIT) {
-		if(tile_counts[flat] == 0)
-			return;
-	}
-	else if(!ALL) {
-		// does the tile touch a flagged window at all?  (reads in scaffold or coordinate order: a tile spans a few scaffolds, and most tiles stop here)
-		if(threadIdx.x < 32) {
-			const uint2 tr = tile_range[flat];
-			bool go = false;
-			if(tr.x <= tr.y && nflagged[sample] > 0) {
-				const uint32_t w0 = tr.x >> 5, w1 = tr.y >> 5;
-				if(w1 - w0 >= 2048u)
-					go = true;                                  // reads in no particular order: the tile spans everything
-				else {
-					for(uint32_t w = w0 + lane; w <= w1; w += 32) {
-						uint32_t m = __ldg(flags + w);
-						if(w == w0) m &= 0xFFFFFFFFu << (tr.x & 31u);
-						if(w == w1) m &= 0xFFFFFFFFu >> (31u - (tr.y & 31u));
-						go |= m != 0;
-					}
-				}
-			}
-			go = __any_sync(FULL, go);
-			if(lane == 0)
-				sm_go = go;
-		}
-		__syncthreads();
-		if(!sm_go) {
-			if(threadIdx.x == 0)
-				tile_counts[flat] = 0;
-			return;
-		}
-	}
-	const uint64_t r0 = ((uint64_t)blockIdx.x * COV_THREADS + threadIdx.x) * COV_ITEMS;
-	Rd4 rd;
-	load_reads4(src, r0, max_snps, nscaf, rd);
-	uint4 si[COV_ITEMS];
-#pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++)
-		si[j] = rd.acc[j]? __ldg(scaf_info + rd.scaf[j]) : make_uint4(0, 0, 1, 0);
-	if(!EMIT && ALL && scaf_nbps != nullptr && (int)sample == nbps_sample) {
+	const uint32_t n = *nlist;
+	for(uint32_t li = blockIdx.x; li < n; li += gridDim.x) {
+		const uint2 ent = list[li];
+		const uint32_t sample = ent.x, tile = ent.y;
+		const ReadSrc src = srcs[sample];
+		const uint32_t flat = src.tile0 + tile;
+		const uint32_t* __restrict__ flags = ALL? nullptr : flag_bits + (uint64_t)sample * nwords;
+		if(EMIT && tile_counts[flat] == 0)
+			continue;                                           // uniform over the CTA
+		const uint64_t r0 = ((uint64_t)tile * COV_THREADS + threadIdx.x) * COV_ITEMS;
+		Rd4 rd;
+		load_reads4(src, r0, max_snps, nscaf, rd);
+		uint4 si[COV_ITEMS];
 #pragma unroll
 		for(int j = 0; j < COV_ITEMS; j++)
-			warp_add_by_key(scaf_nbps, rd.scaf[j], rd.len[j], rd.acc[j]);
-	}
-	uint32_t c = 0;
+			si[j] = rd.acc[j]? __ldg(scaf_info + rd.scaf[j]) : make_uint4(0, 0, 1, 0);
+		if(!EMIT && ALL && scaf_nbps != nullptr && (int)sample == nbps_sample) {
 #pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++) {
-		if(!(rd.acc[j] && si[j].y > 0))
-			continue;
-		WinIter it;
-		it.init(rd.pos0[j], rd.len[j], si[j], seg_end);
-		for(; it.valid(); it.next())
-			if(ALL || ((__ldg(flags + (it.g >> 5)) >> (it.g & 31u)) & 1u))
-				c++;
-	}
-	if(!EMIT) {
-		c = __reduce_add_sync(FULL, c);
-		if(lane == 0)
-			sm[warp] = c;
-		__syncthreads();
-		if(threadIdx.x == 0) {
-			uint32_t t = 0;
-#pragma unroll
-			for(int w = 0; w < COV_THREADS / 32; w++)
-				t += sm[w];
-			tile_counts[flat] = t;
+			for(int j = 0; j < COV_ITEMS; j++)
+				warp_add_by_key(scaf_nbps, rd.scaf[j], rd.len[j], rd.acc[j]);
 		}
-		return;
-	}
-	uint32_t incl = c;
+		uint32_t c = 0;
 #pragma unroll
-	for(int o = 1; o < 32; o <<= 1) {
-		const uint32_t t = __shfl_up_sync(FULL, incl, o);
-		if(lane >= o)
-			incl += t;
-	}
-	if(lane == 31)
-		sm[warp] = incl;
-	__syncthreads();
-	if(c == 0)
-		return;
-	uint32_t wex = 0;
+		for(int j = 0; j < COV_ITEMS; j++) {
+			if(!(rd.acc[j] && si[j].y > 0))
+				continue;
+			WinIter it;
+			it.init(rd.pos0[j], rd.len[j], si[j], seg_end);
+			for(; it.valid(); it.next())
+				if(ALL || ((__ldg(flags + (it.g >> 5)) >> (it.g & 31u)) & 1u))
+					c++;
+		}
+		if(!EMIT) {
+			c = __reduce_add_sync(FULL, c);
+			if(lane == 0)
+				sm[warp] = c;
+			__syncthreads();
+			if(threadIdx.x == 0) {
+				uint32_t t = 0;
 #pragma unroll
-	for(int w = 0; w < COV_THREADS / 32; w++)
-		if(w < warp)
-			wex += sm[w];
-	uint64_t o = tile_offs[flat] + wex + incl - c;
-	const uint32_t key0 = (uint32_t)((uint64_t)sample * nseg);
-#pragma unroll
-	for(int j = 0; j < COV_ITEMS; j++) {
-		if(!(rd.acc[j] && si[j].y > 0))
-			continue;
-		WinIter it;
-		it.init(rd.pos0[j], rd.len[j], si[j], seg_end);
-		for(; it.valid(); it.next())
-			if(ALL || ((__ldg(flags + (it.g >> 5)) >> (it.g & 31u)) & 1u)) {
-				keys[o] = key0 + it.g;
-				vals[o] = it.overlap();                         // the overlap travels with the pair: no gather after the sort
-				o++;
+				for(int w = 0; w < COV_THREADS / 32; w++)
+					t += sm[w];
+				tile_counts[flat] = t;
 			}
+			__syncthreads();
+			continue;
+		}
+		uint32_t incl = c;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(FULL, incl, o);
+			if(lane >= o)
+				incl += t;
+		}
+		if(lane == 31)
+			sm[warp] = incl;
+		__syncthreads();
+		uint32_t wex = 0;
+#pragma unroll
+		for(int w = 0; w < COV_THREADS / 32; w++)
+			if(w < warp)
+				wex += sm[w];
+		__syncthreads();
+		if(c == 0)
+			continue;
+		uint64_t o = tile_offs[flat] + wex + incl - c;
+		const uint32_t key0 = (uint32_t)((uint64_t)sample * nseg);
+#pragma unroll
+		for(int j = 0; j < COV_ITEMS; j++) {
+			if(!(rd.acc[j] && si[j].y > 0))
+				continue;
+			WinIter it;
+			it.init(rd.pos0[j], rd.len[j], si[j], seg_end);
+			for(; it.valid(); it.next())
+				if(ALL || ((__ldg(flags + (it.g >> 5)) >> (it.g & 31u)) & 1u)) {
+					keys[o] = key0 + it.g;
+					vals[o] = it.overlap();                     // the overlap travels with the pair: no gather after the sort
+					o++;
+				}
+		}
 	}
 }
 
@@ -444,18 +516,26 @@ int coverage_pairs(abw_ctx* ctx, const abw_segments* g, const ReadSrc* d_srcs, u
 {
 	if(total_tiles == 0 || g->nseg == 0)
 		return ABW_OK;
-	DevBuf<uint32_t> tile_counts, keys, keys_tmp, vals, vals_tmp;
+	DevBuf<uint32_t> tile_counts, keys, keys_tmp, vals, vals_tmp, nlist;
 	DevBuf<uint64_t> tile_offs, total;
+	DevBuf<uint2> list;
 	ABW_CUDA(ctx, tile_counts.alloc(total_tiles));
 	ABW_CUDA(ctx, tile_offs.alloc(total_tiles));
 	ABW_CUDA(ctx, total.alloc(1));
-	const dim3 grid(max_tiles, ns);
+	ABW_CUDA(ctx, list.alloc(total_tiles));
+	ABW_CUDA(ctx, nlist.alloc(1));
+	ABW_CUDA(ctx, cudaMemsetAsync(nlist.p, 0, sizeof(uint32_t), ctx->stream));
+	ABW_LAUNCH(ctx, k_cov_tile_filter, abw_div_up(total_tiles, 256), 256, 0, d_srcs, ns, total_tiles, flags, nwords, nflagged, tile_range, all? 1 : 0, tile_counts.p, list.p,
+	           nlist.p);
+	(void)max_tiles;
+	const unsigned int grid = std::min<unsigned int>(total_tiles, 8u * (unsigned)ctx->sm_count);
 	if(all)
-		ABW_LAUNCH(ctx, (k_cov_pairs<false, true>), grid, COV_THREADS, 0, d_srcs, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, g->nseg, flags, nwords, nflagged,
-		           tile_range, tile_counts.p, (const uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, d_scaf_nbps, nbps_sample);
+		ABW_LAUNCH(ctx, (k_cov_pairs<false, true>), grid, COV_THREADS, 0, d_srcs, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, g->nseg, flags, nwords,
+		           (const uint2*)list.p, (const uint32_t*)nlist.p, tile_counts.p, (const uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, d_scaf_nbps, nbps_sample);
 	else
-		ABW_LAUNCH(ctx, (k_cov_pairs<false, false>), grid, COV_THREADS, 0, d_srcs, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, g->nseg, flags, nwords, nflagged,
-		           tile_range, tile_counts.p, (const uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (unsigned long long*)nullptr, -1);
+		ABW_LAUNCH(ctx, (k_cov_pairs<false, false>), grid, COV_THREADS, 0, d_srcs, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, g->nseg, flags, nwords,
+		           (const uint2*)list.p, (const uint32_t*)nlist.p, tile_counts.p, (const uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+		           (unsigned long long*)nullptr, -1);
 	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, tile_counts.p, tile_offs.p, total_tiles, total.p));
 	uint64_t npairs = 0;
 	ABW_CUDA(ctx, abw_fetch(ctx, &npairs, total.p, sizeof(uint64_t)));
@@ -469,11 +549,11 @@ int coverage_pairs(abw_ctx* ctx, const abw_segments* g, const ReadSrc* d_srcs, u
 	ABW_CUDA(ctx, vals.alloc(npairs));
 	ABW_CUDA(ctx, vals_tmp.alloc(npairs));
 	if(all)
-		ABW_LAUNCH(ctx, (k_cov_pairs<true, true>), grid, COV_THREADS, 0, d_srcs, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, g->nseg, flags, nwords, nflagged,
-		           tile_range, tile_counts.p, (const uint64_t*)tile_offs.p, keys.p, vals.p, (unsigned long long*)nullptr, -1);
+		ABW_LAUNCH(ctx, (k_cov_pairs<true, true>), grid, COV_THREADS, 0, d_srcs, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, g->nseg, flags, nwords,
+		           (const uint2*)list.p, (const uint32_t*)nlist.p, tile_counts.p, (const uint64_t*)tile_offs.p, keys.p, vals.p, (unsigned long long*)nullptr, -1);
 	else
-		ABW_LAUNCH(ctx, (k_cov_pairs<true, false>), grid, COV_THREADS, 0, d_srcs, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, g->nseg, flags, nwords, nflagged,
-		           tile_range, tile_counts.p, (const uint64_t*)tile_offs.p, keys.p, vals.p, (unsigned long long*)nullptr, -1);
+		ABW_LAUNCH(ctx, (k_cov_pairs<true, false>), grid, COV_THREADS, 0, d_srcs, max_snps, g->nscaf, g->scaf_info.p, g->seg_end.p, g->nseg, flags, nwords,
+		           (const uint2*)list.p, (const uint32_t*)nlist.p, tile_counts.p, (const uint64_t*)tile_offs.p, keys.p, vals.p, (unsigned long long*)nullptr, -1);
 	int nbits = 1;
 	while(nbits < 32 && (1ull << nbits) < (uint64_t)ns * g->nseg)
 		nbits++;

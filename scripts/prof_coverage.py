@@ -32,6 +32,12 @@ for fmt in ("full", "compact"):
         fb = pipeline.build_features(ctx, mg.seq, mg.offsets, samples, timings=t)
         print(fmt, order, i, fb.nseg, sum(s.n for s in samples), {k: round(v, 3) for k, v in t.items()}, flush=True)
         fb.close()
+    ctx.profile(True)
+    fb = pipeline.build_features(ctx, mg.seq, mg.offsets, samples)
+    fb.close()
+    rep = ctx.profile_report()
+    ctx.profile(False)
+    print("  " + "  ".join(f"{k}:{c}x{ms * 1000:.0f}us" for k, (c, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1]) if "cov" in k or "rs_" in k or "scan" in k))
     for s in samples:
         ctx.free(s.d_recs)
 ctx.close()

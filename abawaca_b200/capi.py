@@ -62,7 +62,8 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
 
 
 class Collectives(C.Structure):
-    _fields_ = [("allgather", ALLGATHER_FN), ("allreduce_sum_i64", ALLREDUCE_FN), ("user", C.c_void_p), ("rank", C.c_int), ("world", C.c_int)]
+    _fields_ = [("allgather", ALLGATHER_FN), ("allreduce_sum_i64", ALLREDUCE_FN), ("user", C.c_void_p), ("rank", C.c_int), ("world", C.c_int),
+                ("stream_ordered", C.c_int)]
 
 
 EXPORTS = [

@@ -34,6 +34,8 @@ struct abw_ctx {
 	unsigned char* h_bounce = nullptr;
 	size_t bounce_cap = 0, bounce_used = 0;
 	std::vector<Fetch> pending;
+	// progress words of a running split search, written by the device (mapped pinned memory, search.cu)
+	void* h_prog = nullptr;
 };
 
 // Small uploads (descriptors, job lists, tile tables) go through pinned memory so that cudaMemcpyAsync really is asynchronous.

@@ -254,6 +254,9 @@ void abw_ctx_destroy(abw_ctx* ctx)
 	if(ctx->h_bounce)
 		cudaFreeHost(ctx->h_bounce);
 	ctx->h_bounce = nullptr;
+	if(ctx->h_prog)
+		cudaFreeHost(ctx->h_prog);
+	ctx->h_prog = nullptr;
 	for(cudaEvent_t e : ctx->copy_events)
 		cudaEventDestroy(e);
 	if(ctx->copy_stream)

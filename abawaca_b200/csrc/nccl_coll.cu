@@ -110,6 +110,7 @@ int abw_nccl_collectives_create(abw_ctx* ctx, const void* id128, int rank, int w
 	out->user = u;
 	out->rank = rank;
 	out->world = world;
+	out->stream_ordered = 1;
 	return ABW_OK;
 }
 

@@ -57,7 +57,35 @@ struct CandRec {
 	uint32_t p;          // number of datapoints with value <= candidate value
 	uint32_t i0, i1, i2; // sens/spec: TP, total, TP+FP of the small side.  split-scafs: separated, in_small, in_large
 	uint32_t found;
-	uint32_t dim0;       // 0-based dimension (filled by the reduction)
+	uint32_t dim0;       // 0-based dimension (filled by the reduction; global index over all ranks of a sharded search)
+};
+
+constexpr uint32_t SCG_WMAX = 8;   // up to 512 distinct SCG names
+
+// A live cluster of the current level, as the device keeps it (the work list of abawaca.cpp:98-197 lives on the device: no level waits for the host)
+struct LevelCluster {
+	ClusterDesc d;
+	uint32_t id, parent, nassigned, pad;
+	unsigned long long never[SCG_WMAX];      // SCG names on scaffolds that can never flip to side 1 of a sweep (n < T/2+1): always counted on side 2
+};
+
+// Control block of the breadth-first search, device resident.  The single-CTA kernels k_level_jobs / k_level_decide write it, every other kernel of a level
+// reads its work sizes from it, so the host can enqueue level after level without knowing how many clusters, tiles or splits a level has.
+struct LevelCtl {
+	uint32_t C, TT, FPT, tab_total;          // current level: clusters, sweep tile-table entries, flip-prefix tile-table entries, pass-table entries per dimension
+	uint32_t J, JM, CL_items, SS_items;      // best separations found, those whose dimension this rank holds, work items of k_count_low / k_scaf_sides
+	uint32_t P, Tn, TM_items, term_blocks_done;   // splits, terminal clusters, work items of k_finalize_terminal, its CTAs that have finished
+	uint32_t part_TT[4], part_tab_off[4], part_job_off[4];   // partition plans (scaffold list, elements, flip lists, SCG lists): tile-table entries and offsets
+	unsigned long long part_item_end[4];      // cumulative work items of the plans (item = (dimension, tile-table entry))
+	uint32_t next_id, nrec, level, done;
+	uint32_t error, sweep_launches, pad0, pad1;
+	unsigned long long tickets[4];            // flip-prefix, sweep, partition
+	unsigned long long sweep_elements, partition_elements;
+};
+
+// what the host polls (mapped pinned memory): written by k_level_decide at the end of every level
+struct LevelProgress {
+	volatile uint32_t levels_done, done, nrec, error;
 };
 
 template <int STRATEGY>
@@ -142,7 +170,10 @@ struct SweepParams {
 // ---------------------------------------------------------------------------------------------------
 struct __align__(16) AggSlot { Agg v; unsigned long long pad; };   // 32 bytes
 
+// status words carry the epoch (level number + 1) of the search level that wrote them: words of earlier levels read as empty, so the look-back arrays are
+// cleared once per search and not once per level (nothing in a level depends on a host-side memset of a size only the device knows)
 constexpr uint32_t LB_EMPTY = 0, LB_AGG = 1, LB_PREFIX = 2;
+__device__ __forceinline__ uint32_t lb_state(uint32_t raw, uint32_t epoch) { return ((raw >> 2) == epoch)? (raw & 3u) : LB_EMPTY; }
 constexpr uint32_t LB_SPIN_LIMIT = 1u << 28;      // a bug must not hang the GPU: give up, flag the error, produce garbage that the host rejects
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
@@ -166,7 +197,7 @@ __device__ __forceinline__ void st_cg_agg(AggSlot* p, const Agg& v)
 // Decoupled look-back of warp 0 over the earlier tiles of a segment (items w - tile .. w - 1): publishes this tile's aggregate, walks back
 // 32 predecessors at a time until it meets a published inclusive prefix, publishes its own inclusive prefix and returns the exclusive one.
 __device__ __forceinline__ Agg agg_lookback(uint64_t w, uint32_t tile, const Agg& total, uint32_t* __restrict__ status, AggSlot* __restrict__ aggs,
-                                            AggSlot* __restrict__ prefixes, int* __restrict__ error_flag)
+                                            AggSlot* __restrict__ prefixes, uint32_t epoch, uint32_t* __restrict__ error_flag)
 {
 	const int ln = threadIdx.x;
 	Agg carry = agg_zero();
@@ -174,14 +205,14 @@ __device__ __forceinline__ Agg agg_lookback(uint64_t w, uint32_t tile, const Agg
 		if(ln == 0) {
 			st_cg_agg(&prefixes[w], total);
 			__threadfence();
-			st_volatile_u32(&status[w], LB_PREFIX);
+			st_volatile_u32(&status[w], (epoch << 2) | LB_PREFIX);
 		}
 		return carry;
 	}
 	if(ln == 0) {
 		st_cg_agg(&aggs[w], total);
 		__threadfence();
-		st_volatile_u32(&status[w], LB_AGG);
+		st_volatile_u32(&status[w], (epoch << 2) | LB_AGG);
 	}
 	uint64_t base = w - 1;              // nearest predecessor; lane l looks at base - l
 	uint32_t remaining = tile;          // predecessors left in this segment (tile 0 always ends the walk with a prefix)
@@ -190,7 +221,7 @@ __device__ __forceinline__ Agg agg_lookback(uint64_t w, uint32_t tile, const Agg
 		const uint32_t cnt = min(32u, remaining);
 		uint32_t st, first_prefix, spins = 0;
 		while(true) {
-			st = ((uint32_t)ln < cnt)? ld_volatile_u32(&status[base - ln]) : LB_AGG;
+			st = ((uint32_t)ln < cnt)? lb_state(ld_volatile_u32(&status[base - ln]), epoch) : LB_AGG;
 			const uint32_t pm = __ballot_sync(0xffffffffu, (uint32_t)ln < cnt && st == LB_PREFIX);
 			const uint32_t em = __ballot_sync(0xffffffffu, (uint32_t)ln < cnt && st == LB_EMPTY);
 			first_prefix = pm? (uint32_t)(__ffs(pm) - 1) : 32u;
@@ -229,11 +260,11 @@ __device__ __forceinline__ Agg agg_lookback(uint64_t w, uint32_t tile, const Agg
 		}
 	}
 	if(failed && ln == 0)
-		atomicExch(error_flag, 1);
+		atomicExch(error_flag, 1u);
 	if(ln == 0) {
 		st_cg_agg(&prefixes[w], agg_add(carry, total));
 		__threadfence();
-		st_volatile_u32(&status[w], LB_PREFIX);
+		st_volatile_u32(&status[w], (epoch << 2) | LB_PREFIX);
 	}
 	return carry;
 }
@@ -275,274 +306,6 @@ __device__ __forceinline__ Agg contribution(uint32_t el, bool in_range, const Sc
 }
 
 template <int STRATEGY>
-__global__ void __launch_bounds__(SW_THREADS, 3) k_sweep(const uint32_t* __restrict__ E, uint64_t N, const ClusterDesc* __restrict__ clusters, uint32_t TT,
-                                                        const uint2* __restrict__ tile_tab, const ScafRow* __restrict__ rows, const uint8_t* __restrict__ pass_tab,
-                                                     uint64_t tab_stride, SweepParams prm, unsigned long long* __restrict__ ticket, uint32_t* __restrict__ status,
-                                                     AggSlot* __restrict__ aggs, AggSlot* __restrict__ prefixes, CandRec* __restrict__ out, int* __restrict__ error_flag)
-{
-	__shared__ Agg sm_agg[SW_THREADS / 32 + 1];
-	__shared__ CandRec sm_best[SW_THREADS / 32];
-	__shared__ unsigned long long sm_w;
-	__shared__ Agg sm_carry;
-	// work items are (dimension, tile-table entry), entry fastest: the tiles of a (cluster, dimension) segment are consecutive items
-	if(threadIdx.x == 0)
-		sm_w = atomicAdd(ticket, 1ull);
-	__syncthreads();
-	const uint64_t w = sm_w;
-	const uint32_t d = (uint32_t)(w / TT);
-	const uint2 te = __ldg(tile_tab + (uint32_t)(w - (uint64_t)d * TT));
-	const uint32_t c = te.x, tile = te.y;
-	const ClusterDesc cl = clusters[c];
-	const uint32_t* __restrict__ seg = E + (uint64_t)d * N + cl.off;
-	const uint8_t* __restrict__ tab = (STRATEGY == ABW_SENS_SPEC)? pass_tab + (uint64_t)d * tab_stride + cl.tabOff : nullptr;
-	const uint32_t n = cl.n;
-	CandRec best;
-	best.found = 0; best.k1 = 0; best.k2 = 0; best.p = 0; best.i0 = best.i1 = best.i2 = 0; best.dim0 = d;
-	if(STRATEGY == ABW_SPLIT_SCAFS && !cl.ss_ok) {        // uniform over the tiles of the cluster: nobody waits for these items
-		if(threadIdx.x == 0)
-			out[w] = best;
-		return;
-	}
-	const uint32_t t0 = tile * SW_TILE;
-	const uint32_t i0 = t0 + threadIdx.x * SW_ITEMS;
-	uint32_t el[SW_ITEMS];
-	if(i0 + SW_ITEMS <= n && ((reinterpret_cast<uintptr_t>(seg + i0) & 15) == 0)) {
-		const uint4* p4 = reinterpret_cast<const uint4*>(seg + i0);
-#pragma unroll
-		for(int q = 0; q < SW_ITEMS / 4; q++) {
-			const uint4 x = __ldg(p4 + q);
-			el[4 * q] = x.x; el[4 * q + 1] = x.y; el[4 * q + 2] = x.z; el[4 * q + 3] = x.w;
-		}
-	}
-	else {
-#pragma unroll
-		for(int j = 0; j < SW_ITEMS; j++)
-			el[j] = (i0 + j < n)? __ldg(seg + i0 + j) : 0u;   // class 0, no boundary: contributes nothing
-	}
-	// per-element contributions (recomputed in the candidate pass instead of being kept in registers)
-	Agg tsum = agg_zero();
-#pragma unroll
-	for(int j = 0; j < SW_ITEMS; j++)
-		tsum = agg_add(tsum, contribution<STRATEGY>(el[j], i0 + j < n, rows, prm.fraction_in));
-	Agg total;
-	Agg ex = block_excl_scan_agg(tsum, total, sm_agg);
-	// decoupled look-back over the earlier tiles of this (cluster, dimension)
-	if(threadIdx.x < 32) {
-		const Agg carry = agg_lookback(w, tile, total, status, aggs, prefixes, error_flag);
-		if(threadIdx.x == 0)
-			sm_carry = carry;
-	}
-	__syncthreads();
-	ex = agg_add(ex, sm_carry);
-	// candidates: a boundary before element i means "all dps with value <= value[i-1]" is a threshold with p = i
-#pragma unroll
-	for(int j = 0; j < SW_ITEMS; j++) {
-		const uint32_t p = i0 + j;
-		if((el[j] & EL_BOUNDARY) && p < n && p >= prm.thr && n - p >= prm.thr) {
-			if(STRATEGY == ABW_SENS_SPEC) {
-				// ...Specificity.cpp:146-161 with TP1/FP1/TP2/FP2 written as prefix sums
-				uint32_t TP, tot, u;
-				if(p < n - p) { TP = ex.a; tot = ex.b; u = p; }
-				else { TP = (n - p) - (ex.c - ex.a); tot = cl.totT - ex.b; u = n - p; }
-				if(tot != 0) {
-					const float fTP = (float)TP;
-					if(fTP >= prm.prune * (float)tot && fTP >= prm.prune * (float)u) {
-						const double sens = __ddiv_rn((double)(int)TP, (double)(int)tot), spec = __ddiv_rn((double)(int)TP, (double)(int)u);
-						const double score = __dmul_rn(sens, spec);
-						if(score >= prm.min_score && (!best.found || score > best.k1)) {
-							const uint8_t pt = tab[ex.d];
-							bool ok = (pt == 1);
-							if(pt == 2)
-								ok = (ex.e >= prm.scg_min_size) && (cl.totLen - ex.e >= prm.scg_min_size);
-							if(ok) {
-								best.found = 1; best.k1 = score; best.p = p; best.i0 = TP; best.i1 = tot; best.i2 = u;
-							}
-						}
-					}
-				}
-			}
-			else {
-				// ...SplitScafs.cpp:131-154
-				const uint32_t belong1 = ex.a, in1 = ex.b, belong2 = n - ex.c, in2 = cl.U - ex.d;
-				if(belong1 >= prm.thr && belong2 >= prm.thr) {
-					const uint32_t separated = cl.U - in1 - in2;
-					const uint32_t in_small = (p < n - p)? in1 : in2, in_large = (p < n - p)? in2 : in1;
-					const double ratio = __ddiv_rn((double)separated, (double)(int)in_small);
-					double csr = __ddiv_rn((double)(int)in_small, (double)(int)in_large);
-					if(csr < 1)
-						csr = __ddiv_rn(1.0, csr);
-					if(!best.found || ratio < best.k1 || (ratio == best.k1 && csr < best.k2)) {
-						best.found = 1; best.k1 = ratio; best.k2 = csr; best.p = p; best.i0 = separated; best.i1 = in_small; best.i2 = in_large;
-					}
-				}
-			}
-		}
-		ex = agg_add(ex, contribution<STRATEGY>(el[j], i0 + j < n, rows, prm.fraction_in));
-	}
-	// block arg-best: (key, then lowest p); each thread already holds its lowest-p optimum
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if(__syncthreads_or(best.found)) {
-#pragma unroll
-		for(int o = 16; o > 0; o >>= 1) {
-			CandRec other;
-			other.k1 = __shfl_xor_sync(0xffffffffu, best.k1, o); other.k2 = __shfl_xor_sync(0xffffffffu, best.k2, o);
-			other.p = __shfl_xor_sync(0xffffffffu, best.p, o); other.i0 = __shfl_xor_sync(0xffffffffu, best.i0, o);
-			other.i1 = __shfl_xor_sync(0xffffffffu, best.i1, o); other.i2 = __shfl_xor_sync(0xffffffffu, best.i2, o);
-			other.found = __shfl_xor_sync(0xffffffffu, best.found, o); other.dim0 = d;
-			if(cand_better<STRATEGY>(other, best))
-				best = other;
-		}
-		if(lane == 0)
-			sm_best[warp] = best;
-		__syncthreads();
-		if(threadIdx.x == 0) {
-			CandRec b = sm_best[0];
-			for(int w2 = 1; w2 < SW_THREADS / 32; w2++)
-				if(cand_better<STRATEGY>(sm_best[w2], b))
-					b = sm_best[w2];
-			out[w] = b;
-		}
-	}
-	else if(threadIdx.x == 0)
-		out[w] = best;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// sens/spec sweep, second formulation.  Only the class-1 ("flip") elements carry per-scaffold quantities (T/2+1, T, n, SCG flag,
-// length); everything a candidate needs is therefore a function of two COUNTS at its position -- class-2 elements before it and
-// flip elements before it -- plus a table of prefix sums indexed by the flip count.  Those tables are built once per level
-// from the per-dimension flip list (k_flip_prefix), where the per-scaffold gathers are a plain parallel stream; the sweep itself
-// then never looks at a scaffold id: a warp reads 32 rows of 32 consecutive elements (coalesced 128-byte requests), turns the
-// three flag bits of every row into ballot masks, and lane r keeps the masks of row r -- i.e. of 32 CONSECUTIVE elements.  Counts
-// before any position are popcounts; the block scan and the look-back carry two small integers instead of five sums.
-// ---------------------------------------------------------------------------------------------------
-constexpr int SW_WARP_CHUNK = 32 * 32;            // elements per warp: 32 rows of 32
-
-__device__ __forceinline__ unsigned long long cnt_pack(uint32_t nf, uint32_t nc, uint32_t st)
-{
-	return (unsigned long long)nf | ((unsigned long long)nc << 31) | ((unsigned long long)st << 62);     // both counts < 2^31
-}
-
-// Tables of a level, per (cluster, dimension), indexed by the number k of flip elements already passed:
-//   F8[k-1]  = sums over the first k flips: x = T/2+1 (TP brought by the flips), y = T;  FC[k-1] = n (only kept when some scaffold has n < T)
-//   scg_k[i] = k at which the i-th SCG-carrying scaffold flips (the SCG count of a candidate is a binary search in it)
-//   klo, khi = the range of k for which both sides are >= scg_min_size bases long (ClusterQuality.cpp:118-120); lengths only matter through that test
-// Tiles of FP_TILE list entries, items (dimension, tile-table entry) handed out by ticket, running sums across tiles by look-back.
-constexpr int FP_ITEMS = 8;
-constexpr int FP_TILE = SW_THREADS * FP_ITEMS;
-// The per-scaffold records of a tile are staged in shared memory (coalesced list reads, the gathers of all eight entries of a thread in flight,
-// 16-byte slots swizzled so that both the strided stores and the blocked loads are conflict free) instead of living in registers across the
-// scan and the look-back: 40 registers instead of 128, six CTAs per SM instead of two.
-__global__ void __launch_bounds__(SW_THREADS, 4) k_flip_prefix(const uint32_t* __restrict__ flip_list, uint64_t Sf, const ClusterDesc* __restrict__ clusters, uint32_t FTT,
-                                                              const uint2* __restrict__ ftile_tab, const ScafRow* __restrict__ rows, const uint8_t* __restrict__ has_scg,
-                                                              unsigned long long* __restrict__ ticket, uint32_t* __restrict__ status, AggSlot* __restrict__ aggs,
-                                                              AggSlot* __restrict__ prefixes, uint2* __restrict__ F8, uint32_t* __restrict__ FC, uint32_t* __restrict__ scg_k,
-                                                              uint64_t Kstride, uint2* __restrict__ klohi, uint32_t C, unsigned long long scg_min_size,
-                                                              int* __restrict__ error_flag)
-{
-	__shared__ uint4 sm_r[FP_TILE];                        // {T (0: no entry), n | SCG flag << 31, length}
-	__shared__ Agg sm_agg[SW_THREADS / 32];
-	__shared__ unsigned long long sm_w;
-	__shared__ Agg sm_carry;
-	if(threadIdx.x == 0)
-		sm_w = atomicAdd(ticket, 1ull);
-	__syncthreads();
-	const uint64_t w = sm_w;
-	const uint32_t d = (uint32_t)(w / FTT);
-	const uint2 te = __ldg(ftile_tab + (uint32_t)(w - (uint64_t)d * FTT));
-	const uint32_t tile = te.y;
-	const uint32_t nf = clusters[te.x].nf, fOff = clusters[te.x].fOff;
-	const uint64_t base = (uint64_t)d * Sf + fOff;
-	const uint32_t* __restrict__ list = flip_list + base;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	{
-		uint32_t sc[FP_ITEMS];
-#pragma unroll
-		for(int j = 0; j < FP_ITEMS; j++) {
-			const uint32_t idx = tile * FP_TILE + j * SW_THREADS + threadIdx.x;
-			sc[j] = (idx < nf)? (__ldg(list + idx) & EL_SCAF_MASK) : 0xFFFFFFFFu;      // a partition pass may have left a flag bit on the entry
-		}
-#pragma unroll
-		for(int j = 0; j < FP_ITEMS; j++) {
-			uint4 r = make_uint4(0, 0, 0, 0);
-			if(sc[j] != 0xFFFFFFFFu) {
-				r = __ldg(reinterpret_cast<const uint4*>(rows + sc[j]));
-				r.y |= (uint32_t)(has_scg[sc[j]] != 0) << 31;
-			}
-			const uint32_t e = j * SW_THREADS + threadIdx.x;
-			sm_r[e ^ ((e >> 3) & 7u)] = r;
-		}
-	}
-	__syncthreads();
-	const uint32_t e0 = threadIdx.x * FP_ITEMS, swz = threadIdx.x & 7u;     // this thread's eight consecutive entries
-	Agg tsum = agg_zero();
-#pragma unroll
-	for(int j = 0; j < FP_ITEMS; j++) {
-		const uint4 r = sm_r[e0 + ((uint32_t)j ^ swz)];
-		if(r.x) {
-			tsum.a += r.x / 2 + 1;         // the flip element brings itself and the floor(T/2) earlier dps of the scaffold (...Specificity.cpp:41-57)
-			tsum.b += r.x;
-			tsum.c += r.y & 0x7FFFFFFFu;
-			tsum.d += r.y >> 31;
-			tsum.e += (unsigned long long)r.z | ((unsigned long long)r.w << 32);
-		}
-	}
-	Agg incl = tsum;
-#pragma unroll
-	for(int o = 1; o < 32; o <<= 1) {
-		const Agg t = agg_shfl_up(incl, o);
-		if(lane >= o)
-			incl = agg_add(incl, t);
-	}
-	if(lane == 31)
-		sm_agg[warp] = incl;
-	__syncthreads();
-	Agg wex = agg_zero(), total = agg_zero();
-#pragma unroll
-	for(int w2 = 0; w2 < SW_THREADS / 32; w2++) {
-		const Agg t = sm_agg[w2];
-		if(w2 < warp)
-			wex = agg_add(wex, t);
-		total = agg_add(total, t);
-	}
-	if(threadIdx.x < 32) {
-		const Agg carry = agg_lookback(w, tile, total, status, aggs, prefixes, error_flag);
-		if(threadIdx.x == 0)
-			sm_carry = carry;
-	}
-	__syncthreads();
-	Agg run = agg_add(agg_add(sm_carry, wex), incl);
-	run.a -= tsum.a; run.b -= tsum.b; run.c -= tsum.c; run.d -= tsum.d; run.e -= tsum.e;
-	const uint32_t kOff = clusters[te.x].kOff;
-	const unsigned long long totLen = clusters[te.x].totLen;
-	const uint32_t i0 = tile * FP_TILE + e0;
-#pragma unroll
-	for(int j = 0; j < FP_ITEMS; j++) {
-		const uint4 r = sm_r[e0 + ((uint32_t)j ^ swz)];
-		if(r.x) {
-			const unsigned long long e_before = run.e;
-			run.a += r.x / 2 + 1;
-			run.b += r.x;
-			run.c += r.y & 0x7FFFFFFFu;
-			run.e += (unsigned long long)r.z | ((unsigned long long)r.w << 32);
-			const uint32_t k = i0 + j + 1;                  // flips passed once this one is
-			F8[base + i0 + j] = make_uint2(run.a, run.b);
-			if(FC != nullptr)
-				FC[base + i0 + j] = run.c;
-			if(r.y >> 31) {
-				run.d++;
-				scg_k[(uint64_t)d * Kstride + kOff + run.d - 1] = k;
-			}
-			// lengths are non-decreasing in k: exactly one flip crosses each limit
-			if(e_before < scg_min_size && run.e >= scg_min_size)
-				klohi[(uint64_t)d * C + te.x].x = k;
-			if(totLen >= scg_min_size && e_before <= totLen - scg_min_size && run.e > totLen - scg_min_size)
-				klohi[(uint64_t)d * C + te.x].y = k - 1;
-		}
-	}
-}
-
-template <int STRATEGY>
 __device__ __forceinline__ void block_best_out(CandRec best, uint32_t d, CandRec* sm_best, CandRec* __restrict__ out, uint64_t w)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -572,329 +335,614 @@ __device__ __forceinline__ void block_best_out(CandRec best, uint32_t d, CandRec
 		out[w] = best;
 }
 
-__global__ void __launch_bounds__(SW_THREADS, 4) k_sweep_ss(const uint32_t* __restrict__ E, uint64_t N, const ClusterDesc* __restrict__ clusters, uint32_t TT,
-                                                           const uint2* __restrict__ tile_tab, const uint2* __restrict__ F8, const uint32_t* __restrict__ FC,
-                                                           const uint32_t* __restrict__ scg_k, uint64_t Kstride, const uint2* __restrict__ klohi, uint32_t C,
-                                                           uint64_t Sf, const uint8_t* __restrict__ pass_tab, uint64_t tab_stride, SweepParams prm,
-                                                           unsigned long long* __restrict__ ticket, unsigned long long* __restrict__ lookback,
-                                                           CandRec* __restrict__ out, int* __restrict__ error_flag)
+template <int STRATEGY>
+__global__ void __launch_bounds__(SW_THREADS, 3) k_sweep(const uint32_t* __restrict__ E, uint64_t N, const LevelCluster* __restrict__ clusters, uint32_t D,
+                                                        LevelCtl* __restrict__ ctl, const uint2* __restrict__ tile_tab, const ScafRow* __restrict__ rows,
+                                                        const uint8_t* __restrict__ pass_tab, SweepParams prm, uint32_t epoch, uint32_t* __restrict__ status,
+                                                        AggSlot* __restrict__ aggs, AggSlot* __restrict__ prefixes, CandRec* __restrict__ out)
+{
+	__shared__ Agg sm_agg[SW_THREADS / 32 + 1];
+	__shared__ CandRec sm_best[SW_THREADS / 32];
+	__shared__ unsigned long long sm_w;
+	__shared__ Agg sm_carry;
+	const uint32_t TT = ctl->TT;
+	const uint64_t items = (uint64_t)TT * D, tab_stride = ctl->tab_total;
+	// work items are (dimension, tile-table entry), entry fastest: the tiles of a (cluster, dimension) segment are consecutive items.  CTAs take items
+	// through a ticket until none is left, so an item only ever waits for items taken earlier by CTAs that are running (forward progress).
+	while(true) {
+		if(threadIdx.x == 0)
+			sm_w = atomicAdd(&ctl->tickets[1], 1ull);
+		__syncthreads();
+		const uint64_t w = sm_w;
+		if(w >= items)
+			break;
+		const uint32_t d = (uint32_t)(w / TT);
+		const uint2 te = __ldg(tile_tab + (uint32_t)(w - (uint64_t)d * TT));
+		const uint32_t c = te.x, tile = te.y;
+		const ClusterDesc cl = clusters[c].d;
+		const uint32_t* __restrict__ seg = E + (uint64_t)d * N + cl.off;
+		const uint8_t* __restrict__ tab = (STRATEGY == ABW_SENS_SPEC)? pass_tab + (uint64_t)d * tab_stride + cl.tabOff : nullptr;
+		const uint32_t n = cl.n;
+		CandRec best;
+		best.found = 0; best.k1 = 0; best.k2 = 0; best.p = 0; best.i0 = best.i1 = best.i2 = 0; best.dim0 = d;
+		if(STRATEGY == ABW_SPLIT_SCAFS && !cl.ss_ok) {        // uniform over the tiles of the cluster: nobody waits for these items
+			if(threadIdx.x == 0)
+				out[w] = best;
+			__syncthreads();
+			continue;
+		}
+		const uint32_t t0 = tile * SW_TILE;
+		const uint32_t i0 = t0 + threadIdx.x * SW_ITEMS;
+		uint32_t el[SW_ITEMS];
+		if(i0 + SW_ITEMS <= n && ((reinterpret_cast<uintptr_t>(seg + i0) & 15) == 0)) {
+			const uint4* p4 = reinterpret_cast<const uint4*>(seg + i0);
+#pragma unroll
+			for(int q = 0; q < SW_ITEMS / 4; q++) {
+				const uint4 x = __ldg(p4 + q);
+				el[4 * q] = x.x; el[4 * q + 1] = x.y; el[4 * q + 2] = x.z; el[4 * q + 3] = x.w;
+			}
+		}
+		else {
+#pragma unroll
+			for(int j = 0; j < SW_ITEMS; j++)
+				el[j] = (i0 + j < n)? __ldg(seg + i0 + j) : 0u;   // class 0, no boundary: contributes nothing
+		}
+		// per-element contributions (recomputed in the candidate pass instead of being kept in registers)
+		Agg tsum = agg_zero();
+#pragma unroll
+		for(int j = 0; j < SW_ITEMS; j++)
+			tsum = agg_add(tsum, contribution<STRATEGY>(el[j], i0 + j < n, rows, prm.fraction_in));
+		Agg total;
+		Agg ex = block_excl_scan_agg(tsum, total, sm_agg);
+		// decoupled look-back over the earlier tiles of this (cluster, dimension)
+		if(threadIdx.x < 32) {
+			const Agg carry = agg_lookback(w, tile, total, status, aggs, prefixes, epoch, &ctl->error);
+			if(threadIdx.x == 0)
+				sm_carry = carry;
+		}
+		__syncthreads();
+		ex = agg_add(ex, sm_carry);
+		// candidates: a boundary before element i means "all dps with value <= value[i-1]" is a threshold with p = i
+#pragma unroll
+		for(int j = 0; j < SW_ITEMS; j++) {
+			const uint32_t p = i0 + j;
+			if((el[j] & EL_BOUNDARY) && p < n && p >= prm.thr && n - p >= prm.thr) {
+				if(STRATEGY == ABW_SENS_SPEC) {
+					// ...Specificity.cpp:146-161 with TP1/FP1/TP2/FP2 written as prefix sums
+					uint32_t TP, tot, u;
+					if(p < n - p) { TP = ex.a; tot = ex.b; u = p; }
+					else { TP = (n - p) - (ex.c - ex.a); tot = cl.totT - ex.b; u = n - p; }
+					if(tot != 0) {
+						const float fTP = (float)TP;
+						if(fTP >= prm.prune * (float)tot && fTP >= prm.prune * (float)u) {
+							const double sens = __ddiv_rn((double)(int)TP, (double)(int)tot), spec = __ddiv_rn((double)(int)TP, (double)(int)u);
+							const double score = __dmul_rn(sens, spec);
+							if(score >= prm.min_score && (!best.found || score > best.k1)) {
+								const uint8_t pt = tab[ex.d];
+								bool ok = (pt == 1);
+								if(pt == 2)
+									ok = (ex.e >= prm.scg_min_size) && (cl.totLen - ex.e >= prm.scg_min_size);
+								if(ok) {
+									best.found = 1; best.k1 = score; best.p = p; best.i0 = TP; best.i1 = tot; best.i2 = u;
+								}
+							}
+						}
+					}
+				}
+				else {
+					// ...SplitScafs.cpp:131-154
+					const uint32_t belong1 = ex.a, in1 = ex.b, belong2 = n - ex.c, in2 = cl.U - ex.d;
+					if(belong1 >= prm.thr && belong2 >= prm.thr) {
+						const uint32_t separated = cl.U - in1 - in2;
+						const uint32_t in_small = (p < n - p)? in1 : in2, in_large = (p < n - p)? in2 : in1;
+						const double ratio = __ddiv_rn((double)separated, (double)(int)in_small);
+						double csr = __ddiv_rn((double)(int)in_small, (double)(int)in_large);
+						if(csr < 1)
+							csr = __ddiv_rn(1.0, csr);
+						if(!best.found || ratio < best.k1 || (ratio == best.k1 && csr < best.k2)) {
+							best.found = 1; best.k1 = ratio; best.k2 = csr; best.p = p; best.i0 = separated; best.i1 = in_small; best.i2 = in_large;
+						}
+					}
+				}
+			}
+			ex = agg_add(ex, contribution<STRATEGY>(el[j], i0 + j < n, rows, prm.fraction_in));
+		}
+		block_best_out<STRATEGY>(best, d, sm_best, out, w);
+		__syncthreads();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sens/spec sweep, second formulation.  Only the class-1 ("flip") elements carry per-scaffold quantities (T/2+1, T, n, SCG flag,
+// length); everything a candidate needs is therefore a function of two COUNTS at its position -- class-2 elements before it and
+// flip elements before it -- plus a table of prefix sums indexed by the flip count.  Those tables are built once per level
+// from the per-dimension flip list (k_flip_prefix), where the per-scaffold gathers are a plain parallel stream; the sweep itself
+// then never looks at a scaffold id: a warp reads 32 rows of 32 consecutive elements (coalesced 128-byte requests), turns the
+// three flag bits of every row into ballot masks, and lane r keeps the masks of row r -- i.e. of 32 CONSECUTIVE elements.  Counts
+// before any position are popcounts; the block scan and the look-back carry two small integers instead of five sums.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SW_WARP_CHUNK = 32 * 32;            // elements per warp: 32 rows of 32
+
+// look-back word of the sweep: two counts below 2^28 (a problem holds fewer than 2^28 datapoints), the epoch of the level (6 bits) and the state
+__device__ __forceinline__ unsigned long long cnt_pack(uint32_t nf, uint32_t nc, uint32_t st, uint32_t epoch)
+{
+	return (unsigned long long)nf | ((unsigned long long)nc << 28) | ((unsigned long long)(epoch & 63u) << 56) | ((unsigned long long)st << 62);
+}
+__device__ __forceinline__ uint32_t cnt_state(unsigned long long v, uint32_t epoch)
+{
+	return (((uint32_t)(v >> 56) & 63u) == (epoch & 63u))? (uint32_t)(v >> 62) : LB_EMPTY;
+}
+
+// Tables of a level, per (cluster, dimension), indexed by the number k of flip elements already passed:
+//   F8[k-1]  = sums over the first k flips: x = T/2+1 (TP brought by the flips), y = T;  FC[k-1] = n (only kept when some scaffold has n < T)
+//   scg_k[i] = k at which the i-th SCG-carrying scaffold flips (the SCG count of a candidate is a binary search in it)
+//   klo, khi = the range of k for which both sides are >= scg_min_size bases long (ClusterQuality.cpp:118-120); lengths only matter through that test
+// Tiles of FP_TILE list entries, items (dimension, tile-table entry) handed out by ticket, running sums across tiles by look-back.
+constexpr int FP_ITEMS = 8;
+constexpr int FP_TILE = SW_THREADS * FP_ITEMS;
+// The per-scaffold records of a tile are staged in shared memory (coalesced list reads, the gathers of all eight entries of a thread in flight,
+// 16-byte slots swizzled so that both the strided stores and the blocked loads are conflict free) instead of living in registers across the
+// scan and the look-back: 40 registers instead of 128, six CTAs per SM instead of two.
+__global__ void __launch_bounds__(SW_THREADS, 4) k_flip_prefix(const uint32_t* __restrict__ flip_list, uint64_t Sf, const LevelCluster* __restrict__ clusters, uint32_t D,
+                                                              LevelCtl* __restrict__ ctl, const uint2* __restrict__ ftile_tab, const ScafRow* __restrict__ rows,
+                                                              const uint8_t* __restrict__ has_scg, uint32_t epoch, uint32_t* __restrict__ status, AggSlot* __restrict__ aggs,
+                                                              AggSlot* __restrict__ prefixes, uint2* __restrict__ F8, uint32_t* __restrict__ FC, uint32_t* __restrict__ scg_k,
+                                                              uint64_t Kstride, uint2* __restrict__ klohi, uint32_t Cstride, unsigned long long scg_min_size)
+{
+	__shared__ uint4 sm_r[FP_TILE];                        // {T (0: no entry), n | SCG flag << 31, length}
+	__shared__ Agg sm_agg[SW_THREADS / 32];
+	__shared__ unsigned long long sm_w;
+	__shared__ Agg sm_carry;
+	const uint32_t FTT = ctl->FPT;
+	const uint64_t items = (uint64_t)FTT * D;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	while(true) {
+		if(threadIdx.x == 0)
+			sm_w = atomicAdd(&ctl->tickets[0], 1ull);
+		__syncthreads();
+		const uint64_t w = sm_w;
+		if(w >= items)
+			break;
+		const uint32_t d = (uint32_t)(w / FTT);
+		const uint2 te = __ldg(ftile_tab + (uint32_t)(w - (uint64_t)d * FTT));
+		const uint32_t tile = te.y;
+		const uint32_t nf = clusters[te.x].d.nf, fOff = clusters[te.x].d.fOff;
+		const uint64_t base = (uint64_t)d * Sf + fOff;
+		const uint32_t* __restrict__ list = flip_list + base;
+		{
+			uint32_t sc[FP_ITEMS];
+#pragma unroll
+			for(int j = 0; j < FP_ITEMS; j++) {
+				const uint32_t idx = tile * FP_TILE + j * SW_THREADS + threadIdx.x;
+				sc[j] = (idx < nf)? (__ldg(list + idx) & EL_SCAF_MASK) : 0xFFFFFFFFu;      // a partition pass may have left a flag bit on the entry
+			}
+#pragma unroll
+			for(int j = 0; j < FP_ITEMS; j++) {
+				uint4 r = make_uint4(0, 0, 0, 0);
+				if(sc[j] != 0xFFFFFFFFu) {
+					r = __ldg(reinterpret_cast<const uint4*>(rows + sc[j]));
+					r.y |= (uint32_t)(has_scg[sc[j]] != 0) << 31;
+				}
+				const uint32_t e = j * SW_THREADS + threadIdx.x;
+				sm_r[e ^ ((e >> 3) & 7u)] = r;
+			}
+		}
+		__syncthreads();
+		const uint32_t e0 = threadIdx.x * FP_ITEMS, swz = threadIdx.x & 7u;     // this thread's eight consecutive entries
+		Agg tsum = agg_zero();
+#pragma unroll
+		for(int j = 0; j < FP_ITEMS; j++) {
+			const uint4 r = sm_r[e0 + ((uint32_t)j ^ swz)];
+			if(r.x) {
+				tsum.a += r.x / 2 + 1;         // the flip element brings itself and the floor(T/2) earlier dps of the scaffold (...Specificity.cpp:41-57)
+				tsum.b += r.x;
+				tsum.c += r.y & 0x7FFFFFFFu;
+				tsum.d += r.y >> 31;
+				tsum.e += (unsigned long long)r.z | ((unsigned long long)r.w << 32);
+			}
+		}
+		Agg incl = tsum;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) {
+			const Agg t = agg_shfl_up(incl, o);
+			if(lane >= o)
+				incl = agg_add(incl, t);
+		}
+		if(lane == 31)
+			sm_agg[warp] = incl;
+		__syncthreads();
+		Agg wex = agg_zero(), total = agg_zero();
+#pragma unroll
+		for(int w2 = 0; w2 < SW_THREADS / 32; w2++) {
+			const Agg t = sm_agg[w2];
+			if(w2 < warp)
+				wex = agg_add(wex, t);
+			total = agg_add(total, t);
+		}
+		if(threadIdx.x < 32) {
+			const Agg carry = agg_lookback(w, tile, total, status, aggs, prefixes, epoch, &ctl->error);
+			if(threadIdx.x == 0)
+				sm_carry = carry;
+		}
+		__syncthreads();
+		Agg run = agg_add(agg_add(sm_carry, wex), incl);
+		run.a -= tsum.a; run.b -= tsum.b; run.c -= tsum.c; run.d -= tsum.d; run.e -= tsum.e;
+		const uint32_t kOff = clusters[te.x].d.kOff;
+		const unsigned long long totLen = clusters[te.x].d.totLen;
+		const uint32_t i0 = tile * FP_TILE + e0;
+#pragma unroll
+		for(int j = 0; j < FP_ITEMS; j++) {
+			const uint4 r = sm_r[e0 + ((uint32_t)j ^ swz)];
+			if(r.x) {
+				const unsigned long long e_before = run.e;
+				run.a += r.x / 2 + 1;
+				run.b += r.x;
+				run.c += r.y & 0x7FFFFFFFu;
+				run.e += (unsigned long long)r.z | ((unsigned long long)r.w << 32);
+				const uint32_t k = i0 + j + 1;                  // flips passed once this one is
+				F8[base + i0 + j] = make_uint2(run.a, run.b);
+				if(FC != nullptr)
+					FC[base + i0 + j] = run.c;
+				if(r.y >> 31) {
+					run.d++;
+					scg_k[(uint64_t)d * Kstride + kOff + run.d - 1] = k;
+				}
+				// lengths are non-decreasing in k: exactly one flip crosses each limit
+				if(e_before < scg_min_size && run.e >= scg_min_size)
+					klohi[(uint64_t)d * Cstride + te.x].x = k;
+				if(totLen >= scg_min_size && e_before <= totLen - scg_min_size && run.e > totLen - scg_min_size)
+					klohi[(uint64_t)d * Cstride + te.x].y = k - 1;
+			}
+		}
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(SW_THREADS, 4) k_sweep_ss(const uint32_t* __restrict__ E, uint64_t N, const LevelCluster* __restrict__ clusters, uint32_t D,
+                                                           LevelCtl* __restrict__ ctl, const uint2* __restrict__ tile_tab, const uint2* __restrict__ F8,
+                                                           const uint32_t* __restrict__ FC, const uint32_t* __restrict__ scg_k, uint64_t Kstride,
+                                                           const uint2* __restrict__ klohi, uint32_t Cstride, uint64_t Sf, const uint8_t* __restrict__ pass_tab,
+                                                           SweepParams prm, uint32_t epoch, unsigned long long* __restrict__ lookback, CandRec* __restrict__ out)
 {
 	__shared__ uint32_t sm_warp[SW_THREADS / 32];
 	__shared__ CandRec sm_best[SW_THREADS / 32];
 	__shared__ unsigned long long sm_w;
 	__shared__ uint32_t sm_carry[2];
-	if(threadIdx.x == 0)
-		sm_w = atomicAdd(ticket, 1ull);
-	__syncthreads();
-	const uint64_t w = sm_w;
-	const uint32_t d = (uint32_t)(w / TT);
-	const uint2 te = __ldg(tile_tab + (uint32_t)(w - (uint64_t)d * TT));
-	const uint32_t tile = te.y;
-	const ClusterDesc cl = clusters[te.x];
-	const uint32_t* __restrict__ seg = E + (uint64_t)d * N + cl.off;
-	const uint32_t n = cl.n;
+	const uint32_t TT = ctl->TT;
+	const uint64_t items = (uint64_t)TT * D, tab_stride = ctl->tab_total;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t wbase = tile * SW_TILE + warp * SW_WARP_CHUNK;
-	// 32 coalesced rows; lane r ends up with the flag masks of row r = elements [wbase + 32 r, wbase + 32 r + 32)
-	uint32_t mF = 0, mC = 0, mB = 0;
-	if(wbase < n) {
-		uint32_t el[32];
-		if(wbase + SW_WARP_CHUNK <= n) {                    // warp uniform: the whole chunk exists
+	while(true) {
+		if(threadIdx.x == 0)
+			sm_w = atomicAdd(&ctl->tickets[1], 1ull);
+		__syncthreads();
+		const uint64_t w = sm_w;
+		if(w >= items)
+			break;
+		const uint32_t d = (uint32_t)(w / TT);
+		const uint2 te = __ldg(tile_tab + (uint32_t)(w - (uint64_t)d * TT));
+		const uint32_t tile = te.y;
+		const ClusterDesc cl = clusters[te.x].d;
+		const uint32_t* __restrict__ seg = E + (uint64_t)d * N + cl.off;
+		const uint32_t n = cl.n;
+		const uint32_t wbase = tile * SW_TILE + warp * SW_WARP_CHUNK;
+		// 32 coalesced rows; lane r ends up with the flag masks of row r = elements [wbase + 32 r, wbase + 32 r + 32)
+		uint32_t mF = 0, mC = 0, mB = 0;
+		if(wbase < n) {
+			uint32_t el[32];
+			if(wbase + SW_WARP_CHUNK <= n) {                    // warp uniform: the whole chunk exists
 #pragma unroll
-			for(int r = 0; r < 32; r++)
-				el[r] = __ldg(seg + wbase + r * 32 + lane);
-		}
-		else {
+				for(int r = 0; r < 32; r++)
+					el[r] = __ldg(seg + wbase + r * 32 + lane);
+			}
+			else {
+#pragma unroll
+				for(int r = 0; r < 32; r++) {
+					const uint32_t idx = wbase + r * 32 + lane;
+					el[r] = (idx < n)? __ldg(seg + idx) : 0u;      // class 0, no boundary: contributes nothing
+				}
+			}
 #pragma unroll
 			for(int r = 0; r < 32; r++) {
-				const uint32_t idx = wbase + r * 32 + lane;
-				el[r] = (idx < n)? __ldg(seg + idx) : 0u;      // class 0, no boundary: contributes nothing
+				const uint32_t f = __ballot_sync(0xffffffffu, el[r] & EL_FLIP_BIT);
+				const uint32_t c2 = __ballot_sync(0xffffffffu, el[r] & EL_CLS2_BIT);
+				const uint32_t b = __ballot_sync(0xffffffffu, el[r] & EL_BOUNDARY);
+				if(lane == r) { mF = f; mC = c2; mB = b; }
 			}
 		}
+		const uint32_t i0 = wbase + lane * 32;                  // first element of this thread's row
+		// exclusive block scan of (flip count, class-2 count), 16 bits each: a tile holds 8192 elements
+		const uint32_t mine = __popc(mF) | (__popc(mC) << 16);
+		uint32_t incl = mine;
 #pragma unroll
-		for(int r = 0; r < 32; r++) {
-			const uint32_t f = __ballot_sync(0xffffffffu, el[r] & EL_FLIP_BIT);
-			const uint32_t c2 = __ballot_sync(0xffffffffu, el[r] & EL_CLS2_BIT);
-			const uint32_t b = __ballot_sync(0xffffffffu, el[r] & EL_BOUNDARY);
-			if(lane == r) { mF = f; mC = c2; mB = b; }
+		for(int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if(lane >= o)
+				incl += t;
 		}
-	}
-	const uint32_t i0 = wbase + lane * 32;                  // first element of this thread's row
-	// exclusive block scan of (flip count, class-2 count), 16 bits each: a tile holds 8192 elements
-	const uint32_t mine = __popc(mF) | (__popc(mC) << 16);
-	uint32_t incl = mine;
+		if(lane == 31)
+			sm_warp[warp] = incl;
+		__syncthreads();
+		uint32_t wex = 0, btot = 0;
 #pragma unroll
-	for(int o = 1; o < 32; o <<= 1) {
-		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-		if(lane >= o)
-			incl += t;
-	}
-	if(lane == 31)
-		sm_warp[warp] = incl;
-	__syncthreads();
-	uint32_t wex = 0, btot = 0;
-#pragma unroll
-	for(int w2 = 0; w2 < SW_THREADS / 32; w2++) {
-		const uint32_t t = sm_warp[w2];
-		if(w2 < warp)
-			wex += t;
-		btot += t;
-	}
-	const uint32_t ex = wex + incl - mine;
-	// decoupled look-back over the earlier tiles of this (cluster, dimension)
-	if(threadIdx.x < 32) {
-		const uint32_t totF = btot & 0xFFFFu, totC = btot >> 16;
-		uint32_t cF = 0, cC = 0;
-		if(tile > 0) {
-			if(lane == 0)
-				st_volatile_u64(&lookback[w], cnt_pack(totF, totC, LB_AGG));
-			uint64_t base = w - 1;
-			uint32_t remaining = tile;
-			bool done = false, failed = false;
-			while(!done && !failed) {
-				const uint32_t cnt = min(32u, remaining);
-				unsigned long long v;
-				uint32_t first_prefix, spins = 0;
-				while(true) {
-					v = ((uint32_t)lane < cnt)? ld_volatile_u64(&lookback[base - lane]) : cnt_pack(0, 0, LB_AGG);
-					const uint32_t st = (uint32_t)(v >> 62);
-					const uint32_t pm = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == LB_PREFIX);
-					const uint32_t em = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == LB_EMPTY);
-					first_prefix = pm? (uint32_t)(__ffs(pm) - 1) : 32u;
-					const uint32_t need = (first_prefix >= 32u)? 0xFFFFFFFFu : ((2u << first_prefix) - 1u);
-					if((em & need) == 0)
+		for(int w2 = 0; w2 < SW_THREADS / 32; w2++) {
+			const uint32_t t = sm_warp[w2];
+			if(w2 < warp)
+				wex += t;
+			btot += t;
+		}
+		const uint32_t ex = wex + incl - mine;
+		// decoupled look-back over the earlier tiles of this (cluster, dimension)
+		if(threadIdx.x < 32) {
+			const uint32_t totF = btot & 0xFFFFu, totC = btot >> 16;
+			uint32_t cF = 0, cC = 0;
+			if(tile > 0) {
+				if(lane == 0)
+					st_volatile_u64(&lookback[w], cnt_pack(totF, totC, LB_AGG, epoch));
+				uint64_t base = w - 1;
+				uint32_t remaining = tile;
+				bool done = false, failed = false;
+				while(!done && !failed) {
+					const uint32_t cnt = min(32u, remaining);
+					unsigned long long v;
+					uint32_t first_prefix, spins = 0;
+					while(true) {
+						v = ((uint32_t)lane < cnt)? ld_volatile_u64(&lookback[base - lane]) : cnt_pack(0, 0, LB_AGG, epoch);
+						const uint32_t st = cnt_state(v, epoch);
+						const uint32_t pm = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == LB_PREFIX);
+						const uint32_t em = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == LB_EMPTY);
+						first_prefix = pm? (uint32_t)(__ffs(pm) - 1) : 32u;
+						const uint32_t need = (first_prefix >= 32u)? 0xFFFFFFFFu : ((2u << first_prefix) - 1u);
+						if((em & need) == 0)
+							break;
+						if(++spins >= LB_SPIN_LIMIT) {
+							failed = true;
+							break;
+						}
+					}
+					if(failed)
 						break;
-					if(++spins >= LB_SPIN_LIMIT) {
-						failed = true;
-						break;
+					const bool take = (uint32_t)lane < cnt && (uint32_t)lane <= first_prefix;
+					uint32_t vf = take? (uint32_t)(v & 0xFFFFFFFull) : 0u, vc = take? (uint32_t)((v >> 28) & 0xFFFFFFFull) : 0u;
+					vf = __reduce_add_sync(0xffffffffu, vf);
+					vc = __reduce_add_sync(0xffffffffu, vc);
+					cF += vf;
+					cC += vc;
+					if(first_prefix < 32u)
+						done = true;
+					else {
+						base -= 32;
+						remaining -= 32;
 					}
 				}
-				if(failed)
-					break;
-				const bool take = (uint32_t)lane < cnt && (uint32_t)lane <= first_prefix;
-				uint32_t vf = take? (uint32_t)(v & 0x7FFFFFFFull) : 0u, vc = take? (uint32_t)((v >> 31) & 0x7FFFFFFFull) : 0u;
-				vf = __reduce_add_sync(0xffffffffu, vf);
-				vc = __reduce_add_sync(0xffffffffu, vc);
-				cF += vf;
-				cC += vc;
-				if(first_prefix < 32u)
-					done = true;
-				else {
-					base -= 32;
-					remaining -= 32;
+				if(failed && lane == 0)
+					atomicExch(&ctl->error, 1u);
+			}
+			if(lane == 0) {
+				st_volatile_u64(&lookback[w], cnt_pack(cF + totF, cC + totC, LB_PREFIX, epoch));
+				sm_carry[0] = cF;
+				sm_carry[1] = cC;
+			}
+		}
+		__syncthreads();
+		const uint32_t nF0 = sm_carry[0] + (ex & 0xFFFFu), nC0 = sm_carry[1] + (ex >> 16);
+		// candidates: a boundary before element i means "all dps with value <= value[i-1]" is a threshold with p = i
+		CandRec best;
+		best.found = 0; best.k1 = 0; best.k2 = 0; best.p = 0; best.i0 = best.i1 = best.i2 = 0; best.dim0 = d;
+		const uint8_t* __restrict__ tab = pass_tab + (uint64_t)d * tab_stride + cl.tabOff;
+		const uint64_t fbase = (uint64_t)d * Sf + cl.fOff;
+		const uint32_t* __restrict__ sk = scg_k + (uint64_t)d * Kstride + cl.kOff;
+		uint32_t bm = mB, lastk = 0;
+		uint2 f = make_uint2(0, 0);
+		uint32_t fc = 0;
+		while(bm) {
+			const int j = __ffs(bm) - 1;
+			bm &= bm - 1;
+			const uint32_t p = i0 + j;                          // p < n: elements past the end have no boundary bit
+			if(p < prm.thr || n - p < prm.thr)
+				continue;
+			const uint32_t lt = (1u << j) - 1u;
+			const uint32_t k = nF0 + __popc(mF & lt);
+			if(k != lastk) {
+				f = __ldg(F8 + fbase + k - 1);                  // k == 0 only before the first reload: f is zero then
+				fc = (FC != nullptr)? __ldg(FC + fbase + k - 1) : f.y;     // n == T for every scaffold unless the caller passed partial scaffolds
+				lastk = k;
+			}
+			const uint32_t a = nC0 + __popc(mC & lt) + f.x;     // TP1
+			// ...Specificity.cpp:146-161 with TP1/FP1/TP2/FP2 written as prefix sums
+			uint32_t TP, tot, u;
+			if(p < n - p) { TP = a; tot = f.y; u = p; }
+			else { TP = (n - p) - (fc - a); tot = cl.totT - f.y; u = n - p; }
+			if(tot == 0)
+				continue;
+			const float fTP = (float)TP;
+			if(!(fTP >= prm.prune * (float)tot && fTP >= prm.prune * (float)u))
+				continue;
+			const double sens = __ddiv_rn((double)(int)TP, (double)(int)tot), spec = __ddiv_rn((double)(int)TP, (double)(int)u);
+			const double score = __dmul_rn(sens, spec);
+			if(score >= prm.min_score && (!best.found || score > best.k1)) {
+				// SCG-carrying scaffolds among the first k flips: the entries of scg_k (increasing) that are <= k
+				uint32_t lo = 0, hi = cl.K;
+				while(lo < hi) {
+					const uint32_t mid = (lo + hi) >> 1;
+					if(__ldg(sk + mid) <= k) lo = mid + 1; else hi = mid;
+				}
+				const uint8_t pt = tab[lo];
+				bool ok = (pt == 1);
+				if(pt == 2) {
+					const uint2 kk = __ldg(klohi + (uint64_t)d * Cstride + te.x);
+					ok = k >= kk.x && k <= kk.y;                // both sides at least scg_min_size bases long
+				}
+				if(ok) {
+					best.found = 1; best.k1 = score; best.p = p; best.i0 = TP; best.i1 = tot; best.i2 = u;
 				}
 			}
-			if(failed && lane == 0)
-				atomicExch(error_flag, 1);
 		}
-		if(lane == 0) {
-			st_volatile_u64(&lookback[w], cnt_pack(cF + totF, cC + totC, LB_PREFIX));
-			sm_carry[0] = cF;
-			sm_carry[1] = cC;
-		}
+		block_best_out<ABW_SENS_SPEC>(best, d, sm_best, out, w);
+		__syncthreads();
 	}
-	__syncthreads();
-	const uint32_t nF0 = sm_carry[0] + (ex & 0xFFFFu), nC0 = sm_carry[1] + (ex >> 16);
-	// candidates: a boundary before element i means "all dps with value <= value[i-1]" is a threshold with p = i
-	CandRec best;
-	best.found = 0; best.k1 = 0; best.k2 = 0; best.p = 0; best.i0 = best.i1 = best.i2 = 0; best.dim0 = d;
-	const uint8_t* __restrict__ tab = pass_tab + (uint64_t)d * tab_stride + cl.tabOff;
-	const uint64_t fbase = (uint64_t)d * Sf + cl.fOff;
-	const uint32_t* __restrict__ sk = scg_k + (uint64_t)d * Kstride + cl.kOff;
-	uint32_t bm = mB, lastk = 0;
-	uint2 f = make_uint2(0, 0);
-	uint32_t fc = 0;
-	while(bm) {
-		const int j = __ffs(bm) - 1;
-		bm &= bm - 1;
-		const uint32_t p = i0 + j;                          // p < n: elements past the end have no boundary bit
-		if(p < prm.thr || n - p < prm.thr)
-			continue;
-		const uint32_t lt = (1u << j) - 1u;
-		const uint32_t k = nF0 + __popc(mF & lt);
-		if(k != lastk) {
-			f = __ldg(F8 + fbase + k - 1);                  // k == 0 only before the first reload: f is zero then
-			fc = (FC != nullptr)? __ldg(FC + fbase + k - 1) : f.y;     // n == T for every scaffold unless the caller passed partial scaffolds
-			lastk = k;
-		}
-		const uint32_t a = nC0 + __popc(mC & lt) + f.x;     // TP1
-		// ...Specificity.cpp:146-161 with TP1/FP1/TP2/FP2 written as prefix sums
-		uint32_t TP, tot, u;
-		if(p < n - p) { TP = a; tot = f.y; u = p; }
-		else { TP = (n - p) - (fc - a); tot = cl.totT - f.y; u = n - p; }
-		if(tot == 0)
-			continue;
-		const float fTP = (float)TP;
-		if(!(fTP >= prm.prune * (float)tot && fTP >= prm.prune * (float)u))
-			continue;
-		const double sens = __ddiv_rn((double)(int)TP, (double)(int)tot), spec = __ddiv_rn((double)(int)TP, (double)(int)u);
-		const double score = __dmul_rn(sens, spec);
-		if(score >= prm.min_score && (!best.found || score > best.k1)) {
-			// SCG-carrying scaffolds among the first k flips: the entries of scg_k (increasing) that are <= k
-			uint32_t lo = 0, hi = cl.K;
-			while(lo < hi) {
-				const uint32_t mid = (lo + hi) >> 1;
-				if(__ldg(sk + mid) <= k) lo = mid + 1; else hi = mid;
-			}
-			const uint8_t pt = tab[lo];
-			bool ok = (pt == 1);
-			if(pt == 2) {
-				const uint2 kk = __ldg(klohi + (uint64_t)d * C + te.x);
-				ok = k >= kk.x && k <= kk.y;                // both sides at least scg_min_size bases long
-			}
-			if(ok) {
-				best.found = 1; best.k1 = score; best.p = p; best.i0 = TP; best.i1 = tot; best.i2 = u;
-			}
-		}
-	}
-	block_best_out<ABW_SENS_SPEC>(best, d, sm_best, out, w);
 }
 
 // best candidate of every cluster over its (dimension, tile) items: the reference's total order
 // (score, then lowest dimension, then lowest value; ...Specificity.cpp:137-140 under the mutex, ClusterSeparator.cpp:11-16)
 template <int STRATEGY>
-__global__ void __launch_bounds__(256) k_reduce_best(const CandRec* __restrict__ per_item, uint32_t TT, uint32_t D, const ClusterDesc* __restrict__ clusters,
-                                                    CandRec* __restrict__ out)
+__global__ void __launch_bounds__(256) k_reduce_best(const CandRec* __restrict__ per_item, uint32_t D, const LevelCtl* __restrict__ ctl,
+                                                    const LevelCluster* __restrict__ clusters, uint32_t dim_offset, CandRec* __restrict__ out)
 {
 	__shared__ CandRec sm[256];
-	const uint32_t c = blockIdx.x;
-	const uint32_t tiles = (clusters[c].n + SW_TILE - 1) / SW_TILE, tile0 = clusters[c].tile0;
-	CandRec best;
-	best.found = 0; best.k1 = best.k2 = 0; best.p = 0; best.i0 = best.i1 = best.i2 = 0; best.dim0 = 0;
-	const uint64_t total = (uint64_t)D * tiles;
-	for(uint64_t i = threadIdx.x; i < total; i += blockDim.x) {
-		const uint32_t d = (uint32_t)(i / tiles), t = (uint32_t)(i - (uint64_t)d * tiles);
-		CandRec x = per_item[(uint64_t)d * TT + tile0 + t];
-		x.dim0 = d;
-		if(cand_better<STRATEGY>(x, best))
-			best = x;
-	}
-	sm[threadIdx.x] = best;
-	__syncthreads();
-	for(uint32_t s2 = blockDim.x / 2; s2 > 0; s2 >>= 1) {
-		if(threadIdx.x < s2 && cand_better<STRATEGY>(sm[threadIdx.x + s2], sm[threadIdx.x]))
-			sm[threadIdx.x] = sm[threadIdx.x + s2];
+	const uint32_t C = ctl->C, TT = ctl->TT;
+	for(uint32_t c = blockIdx.x; c < C; c += gridDim.x) {
+		const uint32_t tiles = (clusters[c].d.n + SW_TILE - 1) / SW_TILE, tile0 = clusters[c].d.tile0;
+		CandRec best;
+		best.found = 0; best.k1 = best.k2 = 0; best.p = 0; best.i0 = best.i1 = best.i2 = 0; best.dim0 = 0;
+		const uint64_t total = (uint64_t)D * tiles;
+		for(uint64_t i = threadIdx.x; i < total; i += blockDim.x) {
+			const uint32_t d = (uint32_t)(i / tiles), t = (uint32_t)(i - (uint64_t)d * tiles);
+			CandRec x = per_item[(uint64_t)d * TT + tile0 + t];
+			x.dim0 = d;
+			if(cand_better<STRATEGY>(x, best))
+				best = x;
+		}
+		sm[threadIdx.x] = best;
+		__syncthreads();
+		for(uint32_t s2 = blockDim.x / 2; s2 > 0; s2 >>= 1) {
+			if(threadIdx.x < s2 && cand_better<STRATEGY>(sm[threadIdx.x + s2], sm[threadIdx.x]))
+				sm[threadIdx.x] = sm[threadIdx.x + s2];
+			__syncthreads();
+		}
+		if(threadIdx.x == 0) {
+			CandRec b = sm[0];
+			b.dim0 += dim_offset;                               // global dimension index from here on
+			out[c] = b;
+		}
 		__syncthreads();
 	}
-	if(threadIdx.x == 0)
-		out[c] = sm[0];
 }
 
 // ---------------------------------------------------------------------------------------------------
-// SCG acceptance table, ClusterQuality.cpp:96-136 + SCGdb.cpp:21-38.  One warp per (cluster, dimension).
+// SCG acceptance table, ClusterQuality.cpp:96-136 + SCGdb.cpp:21-38.  One CTA per (cluster, dimension).
 // entry k (k SCG-carrying scaffolds already assigned to side 1): 0 reject, 1 accept, 2 decide on the sizes.
 // ---------------------------------------------------------------------------------------------------
-constexpr uint32_t SCG_WMAX = 8;   // up to 512 distinct SCG names
-
 constexpr int PT_WARPS = 8;
-// one CTA per (cluster, dimension): the K events are cut into PT_WARPS chunks; a first pass ORs the masks of every chunk, then every warp
+// the K events are cut into PT_WARPS chunks; a first pass ORs the masks of every chunk, then every warp
 // runs the suffix and prefix passes over its own chunk, seeded with the ORs of the chunks after / before it
-__global__ void __launch_bounds__(PT_WARPS * 32) k_pass_table(const uint32_t* __restrict__ scg_list, uint64_t list_stride, const ClusterDesc* __restrict__ clusters,
-                             const uint64_t* __restrict__ scgmask, uint32_t W, const uint64_t* __restrict__ never_mask, double overlap_thr, uint64_t* __restrict__ suffix_tmp,
-                             uint8_t* __restrict__ tab, uint64_t tab_stride, uint32_t D, uint2* __restrict__ klohi, unsigned long long scg_min_size)
+__global__ void __launch_bounds__(PT_WARPS * 32) k_pass_table(const uint32_t* __restrict__ scg_list, uint64_t list_stride, const LevelCluster* __restrict__ clusters,
+                             const LevelCtl* __restrict__ ctl, const uint64_t* __restrict__ scgmask, uint32_t W, double overlap_thr, uint64_t* __restrict__ suffix_tmp,
+                             uint8_t* __restrict__ tab, uint32_t D, uint2* __restrict__ klohi, uint32_t Cstride, unsigned long long scg_min_size)
 {
 	__shared__ unsigned long long chunk_or[PT_WARPS][SCG_WMAX];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t c = blockIdx.x, d = blockIdx.y;
-	const ClusterDesc cl = clusters[c];
-	if(threadIdx.x == 0)                                   // size test of the level (k_flip_prefix narrows it): with no flip at all side 1 is empty
-		klohi[(uint64_t)d * gridDim.x + c] = (cl.totLen >= scg_min_size)? make_uint2(scg_min_size == 0? 0u : 0xFFFFFFFFu, 0xFFFFFFFFu) : make_uint2(0xFFFFFFFFu, 0u);
-	const uint32_t* __restrict__ list = scg_list + (uint64_t)d * list_stride + cl.kOff;
-	uint64_t* __restrict__ suf = suffix_tmp + ((uint64_t)d * list_stride + cl.kOff) * W;     // suf[k] = OR of masks k..K-1
-	uint8_t* __restrict__ t = tab + (uint64_t)d * tab_stride + cl.tabOff;
-	const uint32_t K = cl.K;
-	// entries 0..K (K+1 of them) and masks 0..K-1 share the chunk boundaries
-	const uint32_t ech = ((K + 1 + PT_WARPS - 1) / PT_WARPS + 31u) & ~31u;
-	const uint32_t e0 = min(K + 1, warp * ech), e1 = min(K + 1, e0 + ech);      // entries of this warp
-	const uint32_t m1 = min(K, e1);                                            // its masks: [e0, m1)
-	for(uint32_t w = 0; w < W; w++) {
-		unsigned long long o = 0;
-		for(uint32_t k = e0 + lane; k < m1; k += 32)
-			o |= scgmask[(uint64_t)(list[k] & EL_SCAF_MASK) * W + w];
-		o = (unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)o) | ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(o >> 32)) << 32);
-		if(lane == 0)
-			chunk_or[warp][w] = o;
-	}
-	__syncthreads();
-	if(e0 >= e1)
-		return;
-	// pass 1 (backwards): suffix ORs, one mask word at a time
-	for(uint32_t w = 0; w < W; w++) {
-		uint64_t carry = 0;
-		for(int w2 = warp + 1; w2 < PT_WARPS; w2++)
-			carry |= chunk_or[w2][w];
-		for(int64_t base = (int64_t)e0 + (int64_t)((m1 > e0? m1 - e0 + 31 : 0) / 32) * 32 - 32; base >= (int64_t)e0; base -= 32) {
-			const uint32_t k = (uint32_t)base + lane;
-			uint64_t m = (k < m1)? scgmask[(uint64_t)(list[k] & EL_SCAF_MASK) * W + w] : 0ull;
-#pragma unroll
-			for(int o = 1; o < 32; o <<= 1) {
-				uint64_t x = __shfl_down_sync(0xffffffffu, m, o);
-				if(lane + o < 32)
-					m |= x;
-			}
-			m |= carry;
-			if(k < m1)
-				suf[(uint64_t)k * W + w] = m;
-			carry = __shfl_sync(0xffffffffu, m, 0);
+	const uint32_t C = ctl->C;
+	const uint64_t tab_stride = ctl->tab_total, items = (uint64_t)C * D;
+	for(uint64_t item = blockIdx.x; item < items; item += gridDim.x) {
+		const uint32_t c = (uint32_t)(item % C), d = (uint32_t)(item / C);
+		const ClusterDesc cl = clusters[c].d;
+		const unsigned long long* __restrict__ never_mask = clusters[c].never;
+		if(threadIdx.x == 0)                               // size test of the level (k_flip_prefix narrows it): with no flip at all side 1 is empty
+			klohi[(uint64_t)d * Cstride + c] = (cl.totLen >= scg_min_size)? make_uint2(scg_min_size == 0? 0u : 0xFFFFFFFFu, 0xFFFFFFFFu) : make_uint2(0xFFFFFFFFu, 0u);
+		const uint32_t* __restrict__ list = scg_list + (uint64_t)d * list_stride + cl.kOff;
+		uint64_t* __restrict__ suf = suffix_tmp + ((uint64_t)d * list_stride + cl.kOff) * W;     // suf[k] = OR of masks k..K-1
+		uint8_t* __restrict__ t = tab + (uint64_t)d * tab_stride + cl.tabOff;
+		const uint32_t K = cl.K;
+		// entries 0..K (K+1 of them) and masks 0..K-1 share the chunk boundaries
+		const uint32_t ech = ((K + 1 + PT_WARPS - 1) / PT_WARPS + 31u) & ~31u;
+		const uint32_t e0 = min(K + 1, warp * ech), e1 = min(K + 1, e0 + ech);      // entries of this warp
+		const uint32_t m1 = min(K, e1);                                            // its masks: [e0, m1)
+		for(uint32_t w = 0; w < W; w++) {
+			unsigned long long o = 0;
+			for(uint32_t k = e0 + lane; k < m1; k += 32)
+				o |= scgmask[(uint64_t)(list[k] & EL_SCAF_MASK) * W + w];
+			o = (unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)o) | ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(o >> 32)) << 32);
+			if(lane == 0)
+				chunk_or[warp][w] = o;
 		}
-	}
-	__syncwarp();
-	// pass 2 (forwards): entry k sees side 1 = events [0, k), side 2 = events [k, K) plus the scaffolds that can never flip
-	uint64_t carry[SCG_WMAX], after[SCG_WMAX];
+		__syncthreads();
+		if(e0 < e1) {
+			// pass 1 (backwards): suffix ORs, one mask word at a time
+			for(uint32_t w = 0; w < W; w++) {
+				uint64_t carry = 0;
+				for(int w2 = warp + 1; w2 < PT_WARPS; w2++)
+					carry |= chunk_or[w2][w];
+				for(int64_t base = (int64_t)e0 + (int64_t)((m1 > e0? m1 - e0 + 31 : 0) / 32) * 32 - 32; base >= (int64_t)e0; base -= 32) {
+					const uint32_t k = (uint32_t)base + lane;
+					uint64_t m = (k < m1)? scgmask[(uint64_t)(list[k] & EL_SCAF_MASK) * W + w] : 0ull;
 #pragma unroll
-	for(uint32_t w = 0; w < SCG_WMAX; w++) {
-		carry[w] = 0;
-		after[w] = 0;
-		if(w < W) {
-			for(int w2 = 0; w2 < warp; w2++)
-				carry[w] |= chunk_or[w2][w];
-			for(int w2 = warp + 1; w2 < PT_WARPS; w2++)
-				after[w] |= chunk_or[w2][w];                    // suffix of an entry that lies past the masks of this chunk (k == m1)
-		}
-	}
-	for(uint32_t base = e0; base < e1; base += 32) {
-		const uint32_t k = base + lane;
-		uint32_t g1 = 0, g2 = 0, g12 = 0;
-#pragma unroll
-		for(uint32_t w = 0; w < SCG_WMAX; w++) {
-			if(w < W) {
-				// mask of event k-1, unless it belongs to an earlier chunk (then it is already in the carry)
-				uint64_t pre = (k >= 1 && k - 1 >= e0 && k - 1 < K)? scgmask[(uint64_t)(list[k - 1] & EL_SCAF_MASK) * W + w] : 0ull;
-#pragma unroll
-				for(int o = 1; o < 32; o <<= 1) {
-					uint64_t x = __shfl_up_sync(0xffffffffu, pre, o);
-					if(lane >= o)
-						pre |= x;
+					for(int o = 1; o < 32; o <<= 1) {
+						uint64_t x = __shfl_down_sync(0xffffffffu, m, o);
+						if(lane + o < 32)
+							m |= x;
+					}
+					m |= carry;
+					if(k < m1)
+						suf[(uint64_t)k * W + w] = m;
+					carry = __shfl_sync(0xffffffffu, m, 0);
 				}
-				pre |= carry[w];
-				carry[w] = __shfl_sync(0xffffffffu, pre, 31);
-				const uint64_t s2 = ((k < m1)? suf[(uint64_t)k * W + w] : after[w]) | never_mask[(uint64_t)c * W + w];
-				g1 += __popcll(pre);
-				g2 += __popcll(s2);
-				g12 += __popcll(pre & s2);
+			}
+			__syncwarp();
+			// pass 2 (forwards): entry k sees side 1 = events [0, k), side 2 = events [k, K) plus the scaffolds that can never flip
+			uint64_t carry[SCG_WMAX], after[SCG_WMAX];
+#pragma unroll
+			for(uint32_t w = 0; w < SCG_WMAX; w++) {
+				carry[w] = 0;
+				after[w] = 0;
+				if(w < W) {
+					for(int w2 = 0; w2 < warp; w2++)
+						carry[w] |= chunk_or[w2][w];
+					for(int w2 = warp + 1; w2 < PT_WARPS; w2++)
+						after[w] |= chunk_or[w2][w];                    // suffix of an entry that lies past the masks of this chunk (k == m1)
+				}
+			}
+			for(uint32_t base = e0; base < e1; base += 32) {
+				const uint32_t k = base + lane;
+				uint32_t g1 = 0, g2 = 0, g12 = 0;
+#pragma unroll
+				for(uint32_t w = 0; w < SCG_WMAX; w++) {
+					if(w < W) {
+						// mask of event k-1, unless it belongs to an earlier chunk (then it is already in the carry)
+						uint64_t pre = (k >= 1 && k - 1 >= e0 && k - 1 < K)? scgmask[(uint64_t)(list[k - 1] & EL_SCAF_MASK) * W + w] : 0ull;
+#pragma unroll
+						for(int o = 1; o < 32; o <<= 1) {
+							uint64_t x = __shfl_up_sync(0xffffffffu, pre, o);
+							if(lane >= o)
+								pre |= x;
+						}
+						pre |= carry[w];
+						carry[w] = __shfl_sync(0xffffffffu, pre, 31);
+						const uint64_t s2 = ((k < m1)? suf[(uint64_t)k * W + w] : after[w]) | never_mask[w];
+						g1 += __popcll(pre);
+						g2 += __popcll(s2);
+						g12 += __popcll(pre & s2);
+					}
+				}
+				if(k < e1) {
+					uint8_t r;
+					if(g1 == 0 || g2 == 0)
+						r = 2;                                                  // ClusterQuality.cpp:118-120: decided on the two total sizes
+					else
+						r = (__ddiv_rn((double)g12, (double)min(g1, g2)) < overlap_thr)? 0 : 1;   // :130
+					t[k] = r;
+				}
 			}
 		}
-		if(k < e1) {
-			uint8_t r;
-			if(g1 == 0 || g2 == 0)
-				r = 2;                                                  // ClusterQuality.cpp:118-120: decided on the two total sizes
-			else
-				r = (__ddiv_rn((double)g12, (double)min(g1, g2)) < overlap_thr)? 0 : 1;   // :130
-			t[k] = r;
-		}
+		__syncthreads();
 	}
 }
 
 // ---------------------------------------------------------------------------------------------------
-// children, ClusterSeparator.cpp:25-54, 82-134
+// The work list on the device (abawaca.cpp:98-197, ClusterSeparator.cpp:25-54, 82-134).  Per level:
+//   k_level_jobs    (one CTA)  merges the per-rank bests, applies is_legal, lists the clusters with a best separation ("jobs") and the work items of the next two kernels
+//   k_count_low                datapoints of every scaffold on the low side of the separating value
+//   k_scaf_sides               scaffold vote, re-homing, child statistics, separating value
+//   k_level_decide  (one CTA)  >= 100 check, ids, records, the clusters of the next level with their tile tables, the partition plans, the terminal clusters
+//   k_finalize_terminal        bins, total size and SCG tallies of the terminal clusters (its last CTA fills their records)
+//   k_partition2               stable partition of scaffold list, elements, flip lists and SCG lists of the split clusters
 // ---------------------------------------------------------------------------------------------------
 struct SplitJob {
 	uint32_t cluster;    // index into the level's cluster array
-	uint32_t dim0;       // winning dimension
+	uint32_t dim0;       // winning dimension (global index)
 	uint32_t p;          // datapoints with value <= separating value
 	uint32_t swapped;    // cluster1 is the high side (ClusterSeparator.cpp:49-53)
 	uint32_t slot;       // index of the job in the level-wide (all ranks) job list: where its statistics go
-	uint32_t pad;
+	uint32_t sstar;      // scaffold of the last datapoint on the low side (set on the rank that holds the dimension): it carries the separating value
 };
 
 struct ChildStats {      // [job][2]; summed across ranks as 64-bit words in a sharded search (no 32-bit half can overflow)
@@ -902,13 +950,221 @@ struct ChildStats {      // [job][2]; summed across ranks as 64-bit words in a s
 	uint32_t ns, nassigned, totT, K, viol, nflip;
 };
 
-__global__ void k_count_low(const uint32_t* __restrict__ E, uint64_t N, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs, uint32_t* __restrict__ low)
+struct PartJob {
+	uint64_t off;        // parent segment (child 1 is written at off, child 2 at off + n1)
+	uint32_t n, n1;
+};
+
+struct TermJob { uint32_t sOff, ns, id, rec; };          // rec: index of the cluster's record (0xFFFFFFFF: none)
+struct TermStats { unsigned long long total_size, scg_copies; };
+
+constexpr int LV_THREADS = 1024;                            // the single-CTA kernels
+constexpr uint32_t CL_CHUNK = 4096;                         // elements per work item of k_count_low
+constexpr uint32_t SS_CHUNK = 128;                          // scaffolds per work item of k_scaf_sides
+constexpr uint32_t TM_CHUNK = 512;                          // scaffolds per work item of k_finalize_terminal
+
+// buffers of a search run that the level kernels share (device pointers; passed by value)
+struct LevelBufs {
+	LevelCtl* ctl;
+	LevelProgress* prog;                                    // mapped pinned host memory
+	LevelCluster* cl[2];
+	CandRec *best, *best_all;                               // [Cmax] of this rank; [world][Cstride] gathered
+	SplitJob* jobs;
+	uint32_t *jobs_mine, *job_of;
+	abw_best* bestrec;
+	uint2 *cl_tab, *ss_tab, *tile_tab, *fp_tab, *part_tab, *tm_tab;
+	PartJob* part_jobs;                                     // [4][Pmax]
+	TermJob* tjobs;
+	TermStats* tstats;
+	uint64_t* tunion;
+	abw_cluster_rec* recs;
+	uint32_t rec_cap, Cmax, Pmax, pad;
+	uint32_t* low;
+};
+
+// exclusive scan of one value per thread over a CTA of LV_THREADS threads; total = sum.  sm: uint32_t[33]
+__device__ __forceinline__ uint32_t cta_excl_scan(uint32_t v, uint32_t& total, uint32_t* sm)
 {
-	const SplitJob jb = jobs[blockIdx.y];
-	const ClusterDesc cl = clusters[jb.cluster];
-	const uint32_t* __restrict__ seg = E + (uint64_t)jb.dim0 * N + cl.off;
-	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.p; i += gridDim.x * blockDim.x)
-		atomicAdd(&low[seg[i] & EL_SCAF_MASK], 1u);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t incl = v;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+		if(lane >= o)
+			incl += t;
+	}
+	if(lane == 31)
+		sm[warp] = incl;
+	__syncthreads();
+	if(warp == 0) {
+		const uint32_t w = sm[lane];
+		uint32_t wi = w;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+			if(lane >= o)
+				wi += t;
+		}
+		sm[lane] = wi - w;
+		if(lane == 31)
+			sm[32] = wi;
+	}
+	__syncthreads();
+	const uint32_t r = sm[warp] + incl - v;
+	total = sm[32];
+	__syncthreads();
+	return r;
+}
+
+// entry i of n owns cnt(i) consecutive slots of a table: first(i, slot) is told where they start and, if tab is not null, tab[slot + t] = (i, t).
+// Returns the number of slots.  Called by all LV_THREADS threads of the CTA.
+template <class CountF, class FirstF>
+__device__ __forceinline__ uint32_t cta_expand(uint32_t n, uint2* __restrict__ tab, CountF cnt, FirstF first, uint32_t* sm)
+{
+	uint32_t run = 0;
+	for(uint32_t b = 0; b < n; b += LV_THREADS) {
+		const uint32_t i = b + threadIdx.x;
+		const uint32_t c = (i < n)? cnt(i) : 0u;
+		uint32_t total;
+		const uint32_t ex = cta_excl_scan(c, total, sm);
+		if(i < n) {
+			first(i, run + ex);
+			if(tab != nullptr)
+				for(uint32_t t = 0; t < c; t++)
+					tab[run + ex + t] = make_uint2(i, t);
+		}
+		run += total;
+	}
+	return run;
+}
+
+__device__ __forceinline__ void best_reset(abw_best& b, int strategy)
+{
+	b.found = 0; b.dim = 0; b.value = -1; b.a = 0; b.b = 0; b.legal = 0;
+	if(strategy == ABW_SPLIT_SCAFS) { b.a = 1000000; b.b = 1000000; }       // ClusteringResult::reset of the split-scafs strategy
+}
+
+__global__ void __launch_bounds__(LV_THREADS) k_level_jobs(const LevelBufs B, int cur, uint32_t world, uint32_t Cstride, int strategy, const abw_params prm,
+                                                         uint32_t dim_offset, uint32_t Dlocal, const uint32_t* __restrict__ E, uint64_t N,
+                                                         ChildStats* __restrict__ stats, unsigned long long* __restrict__ value_key, uint64_t* __restrict__ child_never, uint32_t W)
+{
+	__shared__ uint32_t sm[33];
+	__shared__ unsigned long long sm_el;
+	LevelCtl* const ctl = B.ctl;
+	const LevelCluster* __restrict__ cls = B.cl[cur];
+	const uint32_t C = ctl->C;
+	if(threadIdx.x == 0)
+		sm_el = 0;
+	__syncthreads();
+	uint32_t J = 0;
+	unsigned long long el = 0;
+	for(uint32_t b0 = 0; b0 < C; b0 += LV_THREADS) {
+		const uint32_t c = b0 + threadIdx.x;
+		CandRec best;
+		best.found = 0;
+		if(c < C) {
+			best = B.best[c];
+			if(world > 1) {
+				// the per-rank bests of the cluster, gathered: the same total order on every rank (ClusterSeparator.cpp:11-16)
+				best = B.best_all[c];
+				for(uint32_t r = 1; r < world; r++) {
+					const CandRec x = B.best_all[(size_t)r * Cstride + c];
+					if((strategy == ABW_SENS_SPEC)? cand_better<ABW_SENS_SPEC>(x, best) : cand_better<ABW_SPLIT_SCAFS>(x, best))
+						best = x;
+				}
+			}
+		}
+		const bool found = c < C && best.found;
+		uint32_t total;
+		const uint32_t ex = cta_excl_scan(found? 1u : 0u, total, sm);
+		if(c < C) {
+			const uint32_t n = cls[c].d.n;
+			el += (unsigned long long)n * Dlocal;
+			abw_best hb;
+			best_reset(hb, strategy);
+			if(found) {
+				hb.found = 1;
+				hb.dim = best.dim0 + 1;
+				if(strategy == ABW_SENS_SPEC) {
+					// same IEEE operations as ClusterStats::get_sensitivity / get_specificity (...Specificity.h:74-75) and is_legal (:31-35)
+					hb.a = __ddiv_rn((double)(int)best.i0, (double)(int)best.i1);
+					hb.b = __ddiv_rn((double)(int)best.i0, (double)(int)best.i2);
+					hb.legal = (hb.a >= prm.sensitivity_threshold) && (hb.b >= prm.specificity_threshold) && (__dadd_rn(hb.a, hb.b) >= prm.sum_threshold) &&
+					           (__dmul_rn(hb.a, hb.b) >= prm.product_threshold);
+				}
+				else {
+					hb.a = best.k1;
+					hb.b = best.k2;
+					hb.legal = hb.a <= prm.split_scaf_ratio_threshold;     // ...SplitScafs.h:38
+				}
+				SplitJob jb;
+				jb.cluster = c; jb.dim0 = best.dim0; jb.p = best.p;
+				jb.swapped = (n - best.p) < best.p;             // ClusterSeparator.cpp:49
+				jb.slot = J + ex;
+				jb.sstar = 0xFFFFFFFFu;
+				B.jobs[J + ex] = jb;
+				B.job_of[c] = J + ex;
+			}
+			else
+				B.job_of[c] = 0xFFFFFFFFu;
+			B.bestrec[c] = hb;
+		}
+		J += total;
+	}
+	__syncthreads();
+	// jobs whose winning dimension lives on this rank (all of them when the search is not sharded)
+	uint32_t JM = 0;
+	for(uint32_t b0 = 0; b0 < J; b0 += LV_THREADS) {
+		const uint32_t j = b0 + threadIdx.x;
+		bool mine = false;
+		if(j < J) {
+			const uint32_t d = B.jobs[j].dim0;
+			mine = d >= dim_offset && d < dim_offset + Dlocal;
+		}
+		uint32_t total;
+		const uint32_t ex = cta_excl_scan(mine? 1u : 0u, total, sm);
+		if(mine) {
+			B.jobs_mine[JM + ex] = j;
+			const SplitJob jb = B.jobs[j];
+			B.jobs[j].sstar = E[(uint64_t)(jb.dim0 - dim_offset) * N + cls[jb.cluster].d.off + jb.p - 1] & EL_SCAF_MASK;   // p >= 1: a candidate has datapoints on both sides
+		}
+		JM += total;
+	}
+	__syncthreads();
+	const uint32_t cl_items = cta_expand(JM, B.cl_tab, [&](uint32_t k) { return (B.jobs[B.jobs_mine[k]].p + CL_CHUNK - 1) / CL_CHUNK; }, [](uint32_t, uint32_t) {}, sm);
+	const uint32_t ss_items = cta_expand(JM, B.ss_tab, [&](uint32_t k) { return (cls[B.jobs[B.jobs_mine[k]].cluster].d.ns + SS_CHUNK - 1) / SS_CHUNK; },
+	                                     [](uint32_t, uint32_t) {}, sm);
+	for(uint32_t i = threadIdx.x; i < 2 * J; i += LV_THREADS) {
+		ChildStats z;
+		z.ndps = 0; z.totLen = 0; z.ns = z.nassigned = z.totT = z.K = z.viol = z.nflip = 0;
+		stats[i] = z;
+	}
+	for(uint32_t i = threadIdx.x; i < J; i += LV_THREADS)
+		value_key[i] = 0;
+	for(uint32_t i = threadIdx.x; i < 2 * J * W; i += LV_THREADS)
+		child_never[i] = 0;
+	atomicAdd(&sm_el, el);
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		ctl->J = J; ctl->JM = JM; ctl->CL_items = cl_items; ctl->SS_items = ss_items;
+		ctl->sweep_elements += sm_el;
+		if(C > 0)
+			ctl->sweep_launches++;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_count_low(const uint32_t* __restrict__ E, uint64_t N, const LevelBufs B, int cur, uint32_t dim_offset, uint32_t* __restrict__ low)
+{
+	const LevelCluster* __restrict__ cls = B.cl[cur];
+	const uint32_t items = B.ctl->CL_items;
+	for(uint32_t it = blockIdx.x; it < items; it += gridDim.x) {
+		const uint2 te = B.cl_tab[it];
+		const SplitJob jb = B.jobs[B.jobs_mine[te.x]];
+		const uint32_t* __restrict__ seg = E + (uint64_t)(jb.dim0 - dim_offset) * N + cls[jb.cluster].d.off;
+		const uint32_t i0 = te.y * CL_CHUNK, i1 = min(jb.p, i0 + CL_CHUNK);
+		for(uint32_t i = i0 + threadIdx.x; i < i1; i += blockDim.x)
+			atomicAdd(&low[seg[i] & EL_SCAF_MASK], 1u);
+	}
 }
 
 __device__ __forceinline__ unsigned long long orderable(double v)
@@ -917,26 +1173,56 @@ __device__ __forceinline__ unsigned long long orderable(double v)
 	unsigned long long b = (unsigned long long)__double_as_longlong(v);
 	return (b >> 63)? ~b : (b | 0x8000000000000000ull);
 }
-// one thread per scaffold of every split cluster: vote (ClusterSeparator.cpp:94-101), child statistics, separating value.
-// The statistics of a warp are combined before they reach the two counters of the job (one atomic per warp and field, not per scaffold).
-__global__ void __launch_bounds__(128) k_scaf_sides(const uint32_t* __restrict__ scaf_list, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs,
-                             const ScafRow* __restrict__ rows, const uint32_t* __restrict__ low, const uint64_t* __restrict__ dp_first, const double* __restrict__ values, uint64_t N,
+// one thread per scaffold of every cluster with a best separation: vote (ClusterSeparator.cpp:94-101), child statistics; the first warp of a job's first item
+// recovers the separating value.  The statistics of a warp are combined before they reach the two counters of the job (one atomic per warp and field).
+// low[] is cleared on the way (the entry of the scaffold that carries the separating value by k_level_decide).
+__global__ void __launch_bounds__(SS_CHUNK) k_scaf_sides(const uint32_t* __restrict__ scaf_list, const LevelBufs B, int cur, uint32_t dim_offset,
+                             const ScafRow* __restrict__ rows, uint32_t* __restrict__ low, const uint64_t* __restrict__ dp_first, const double* __restrict__ values, uint64_t N,
                              const uint64_t* __restrict__ scgmask, uint32_t W, int strategy, double fraction_in, uint8_t* __restrict__ side, uint8_t* __restrict__ new_assigned,
                              ChildStats* __restrict__ stats, uint64_t* __restrict__ child_never, unsigned long long* __restrict__ value_key)
 {
-	const SplitJob jb = jobs[blockIdx.y];
-	const ClusterDesc cl = clusters[jb.cluster];
+	const LevelCluster* __restrict__ cls = B.cl[cur];
+	const uint32_t items = B.ctl->SS_items;
 	const int lane = threadIdx.x & 31;
-	for(uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < cl.ns; base += gridDim.x * blockDim.x) {
-		const uint32_t i = base + lane;
+	for(uint32_t it = blockIdx.x; it < items; it += gridDim.x) {
+		const uint2 te = B.ss_tab[it];
+		const SplitJob jb = B.jobs[B.jobs_mine[te.x]];
+		const ClusterDesc cl = cls[jb.cluster].d;
+		if(te.y == 0 && threadIdx.x < 32) {
+			// separating value = largest value on the low side = value of the datapoint at position p - 1 of the winning dimension; that datapoint belongs to
+			// scaffold sstar and is its lo-th smallest (the sort is stable and the datapoints of a scaffold are consecutive: ties go by datapoint index)
+			const uint32_t s = jb.sstar;
+			const ScafRow r = rows[s];
+			const uint32_t lo = low[s];
+			const double* __restrict__ col = values + (uint64_t)(jb.dim0 - dim_offset) * N + dp_first[s];
+			unsigned long long kth = 0;
+			for(uint32_t a = lane; a < r.n; a += 32) {
+				const unsigned long long ka = orderable(col[a]);
+				uint32_t rank = 0;
+				for(uint32_t b = 0; b < r.n; b++) {
+					const unsigned long long kb = orderable(col[b]);
+					rank += (kb < ka) || (kb == ka && b < a);
+				}
+				if(rank + 1 == lo)
+					kth = ka;
+			}
+#pragma unroll
+			for(int o = 16; o > 0; o >>= 1)
+				kth = max(kth, __shfl_xor_sync(0xffffffffu, kth, o));
+			if(lane == 0)
+				value_key[jb.slot] = kth;
+		}
+		const uint32_t i = te.y * SS_CHUNK + threadIdx.x;
 		const bool active = i < cl.ns;
 		uint32_t sd = 0, rn = 0, rT = 0;
-		unsigned long long rlen = 0, kth = 0;
+		unsigned long long rlen = 0;
 		bool assigned_any = false, flippable = false, has_scg = false, viol = false;
 		if(active) {
 			const uint32_t s = scaf_list[cl.sOff + i] & EL_SCAF_MASK;      // the partition kernel leaves its flag bit on list entries
 			const ScafRow r = rows[s];
 			const uint32_t lo = low[s];
+			if(s != jb.sstar)
+				low[s] = 0;
 			const uint32_t c1 = jb.swapped? r.n - lo : lo, c2 = r.n - c1;
 			const bool A1 = c1 > 0 && 2ull * c1 >= r.T;          // :95-97
 			const bool A2 = c2 > 0 && 2ull * c2 > r.T;           // :98-101
@@ -953,26 +1239,7 @@ __global__ void __launch_bounds__(128) k_scaf_sides(const uint32_t* __restrict__
 				for(uint32_t w = 0; w < W; w++)
 					atomicOr((unsigned long long*)&child_never[((uint64_t)jb.slot * 2 + (sd - 1)) * W + w], (unsigned long long)scgmask[(uint64_t)s * W + w]);
 			viol = strategy == ABW_SPLIT_SCAFS && !((double)r.n >= __dmul_rn(fraction_in, (double)r.T));
-			// separating value = largest value on the low side = max over scaffolds of their lo-th smallest value
-			if(lo > 0) {
-				const double* __restrict__ col = values + (uint64_t)jb.dim0 * N + dp_first[s];
-				for(uint32_t a = 0; a < r.n; a++) {
-					const unsigned long long ka = orderable(col[a]);
-					uint32_t rank = 0;
-					for(uint32_t b = 0; b < r.n; b++) {
-						const unsigned long long kb = orderable(col[b]);
-						rank += (kb < ka) || (kb == ka && b < a);
-					}
-					if(rank == lo - 1)
-						kth = ka;
-				}
-			}
 		}
-#pragma unroll
-		for(int o = 16; o > 0; o >>= 1)
-			kth = max(kth, __shfl_xor_sync(0xffffffffu, kth, o));
-		if(lane == 0 && kth != 0)
-			atomicMax(&value_key[jb.slot], kth);
 #pragma unroll
 		for(uint32_t sdv = 1; sdv <= 2; sdv++) {
 			const bool m = active && sd == sdv;
@@ -1004,32 +1271,303 @@ __global__ void __launch_bounds__(128) k_scaf_sides(const uint32_t* __restrict__
 	}
 }
 
-__global__ void k_clear_low(const uint32_t* __restrict__ scaf_list, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs, uint32_t* __restrict__ low)
+// what a level leaves for the next one.  plan_dims[pl]: dimensions of partition plan pl (0: the plan does not exist in this search or at the last level)
+__global__ void __launch_bounds__(LV_THREADS) k_level_decide(const LevelBufs B, int cur, int strategy, const abw_params prm, uint32_t Dlocal, uint32_t W,
+                                                           uint32_t dim_offset, const uint32_t pd0, const uint32_t pd1, const uint32_t pd2, const uint32_t pd3,
+                                                           int build_next, const ChildStats* __restrict__ stats, const unsigned long long* __restrict__ value_key,
+                                                           const uint64_t* __restrict__ child_never)
 {
-	const SplitJob jb = jobs[blockIdx.y];
-	const ClusterDesc cl = clusters[jb.cluster];
-	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cl.ns; i += gridDim.x * blockDim.x)
-		low[scaf_list[cl.sOff + i] & EL_SCAF_MASK] = 0;
+	__shared__ uint32_t sm[33];
+	__shared__ unsigned long long sm_el;
+	LevelCtl* const ctl = B.ctl;
+	const LevelCluster* __restrict__ cls = B.cl[cur];
+	LevelCluster* __restrict__ nxt = B.cl[cur ^ 1];
+	const uint32_t C = ctl->C, nrec0 = ctl->nrec, next_id0 = ctl->next_id, thr = prm.cluster_ndps_threshold, Pmax = B.Pmax;
+	if(threadIdx.x == 0)
+		sm_el = 0;
+	__syncthreads();
+	uint32_t P = 0, Tn = 0;
+	unsigned long long el = 0;
+	for(uint32_t b0 = 0; b0 < C; b0 += LV_THREADS) {
+		const uint32_t c = b0 + threadIdx.x;
+		const bool valid = c < C;
+		bool split = false;
+		abw_best br;
+		best_reset(br, strategy);
+		uint32_t j = 0xFFFFFFFFu;
+		if(valid) {
+			br = B.bestrec[c];
+			j = B.job_of[c];
+			if(br.found) {
+				const unsigned long long k = value_key[j];
+				const unsigned long long bits = (k >> 63)? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+				br.value = __longlong_as_double((long long)bits);
+				if(br.legal) {
+					split = !(stats[2 * (size_t)j].ndps < thr || stats[2 * (size_t)j + 1].ndps < thr);      // ClusterSeparator.cpp:125
+					if(!split)
+						best_reset(br, strategy);                // children too small: best_separation->reset() (:125-132)
+				}
+			}
+		}
+		uint32_t tot_s, tot_t;
+		const uint32_t exs = cta_excl_scan(split? 1u : 0u, tot_s, sm);
+		const uint32_t ext = cta_excl_scan((valid && !split)? 1u : 0u, tot_t, sm);
+		if(valid) {
+			const LevelCluster lc = cls[c];
+			abw_cluster_rec r;
+			memset(&r, 0, sizeof(r));
+			r.id = lc.id; r.parent = lc.parent; r.ndps = lc.d.n; r.nscafs = lc.nassigned; r.best = br;
+			r.gc_avg = r.gc_sd = r.cvg_avg = r.cvg_sd = -1.0;
+			if(split) {
+				const ChildStats s1 = stats[2 * (size_t)j], s2 = stats[2 * (size_t)j + 1];
+				const SplitJob jb = B.jobs[j];
+				const uint32_t q = P + exs;
+				r.split = 1;
+				r.child1 = next_id0 + 2 * q;                     // ids handed out in cluster order, cluster1 first (abawaca.cpp:164-193)
+				r.child2 = r.child1 + 1;
+				r.child1_ndps = s1.ndps; r.child2_ndps = s2.ndps;
+				r.child1_nscafs = s1.nassigned; r.child2_nscafs = s2.nassigned;
+				r.child1_raw = jb.swapped? lc.d.n - jb.p : jb.p;
+				r.child2_raw = lc.d.n - r.child1_raw;
+				uint64_t off = lc.d.off;
+				uint32_t kOff = lc.d.kOff, sOff = lc.d.sOff, fOff = lc.d.fOff;
+				for(int ch = 0; ch < 2; ch++) {
+					const ChildStats& st = ch? s2 : s1;
+					LevelCluster hc;
+					memset(&hc, 0, sizeof(hc));
+					hc.id = ch? r.child2 : r.child1;
+					hc.parent = lc.id;
+					hc.d.off = off; hc.d.n = (uint32_t)st.ndps;
+					hc.d.kOff = kOff; hc.d.K = st.K;
+					hc.d.sOff = sOff; hc.d.ns = st.ns;
+					hc.d.totT = st.totT; hc.d.U = st.ns; hc.d.totLen = st.totLen;
+					hc.d.ss_ok = (st.viol == 0);
+					hc.d.fOff = fOff; hc.d.nf = st.nflip;
+					hc.nassigned = st.nassigned;
+					for(uint32_t w = 0; w < W; w++)
+						hc.never[w] = child_never[((size_t)j * 2 + ch) * W + w];
+					off += st.ndps; kOff += st.K; sOff += st.ns; fOff += st.nflip;
+					nxt[2 * q + ch] = hc;
+				}
+				PartJob pj;
+				pj.off = lc.d.sOff; pj.n = lc.d.ns; pj.n1 = s1.ns;
+				B.part_jobs[0 * (size_t)Pmax + q] = pj;
+				pj.off = lc.d.off; pj.n = lc.d.n; pj.n1 = (uint32_t)s1.ndps;
+				B.part_jobs[1 * (size_t)Pmax + q] = pj;
+				pj.off = lc.d.fOff; pj.n = lc.d.nf; pj.n1 = s1.nflip;
+				B.part_jobs[2 * (size_t)Pmax + q] = pj;
+				pj.off = lc.d.kOff; pj.n = lc.d.K; pj.n1 = s1.K;
+				B.part_jobs[3 * (size_t)Pmax + q] = pj;
+				if(pd1)
+					el += (unsigned long long)lc.d.n * Dlocal;
+			}
+			else {
+				TermJob tj;
+				tj.sOff = lc.d.sOff; tj.ns = lc.d.ns; tj.id = lc.id; tj.rec = nrec0 + c;
+				B.tjobs[Tn + ext] = tj;
+			}
+			if(nrec0 + c < B.rec_cap)
+				B.recs[nrec0 + c] = r;
+		}
+		P += tot_s;
+		Tn += tot_t;
+	}
+	__syncthreads();
+	const uint32_t Cn = 2 * P;
+	// the next level: pass-table offsets, sweep tiles, flip-prefix tiles
+	uint32_t tab_total = 0, TT = 0, FPT = 0;
+	if(build_next) {
+		tab_total = cta_expand(Cn, nullptr, [&](uint32_t i) { return nxt[i].d.K + 1u; }, [&](uint32_t i, uint32_t slot) { nxt[i].d.tabOff = slot; }, sm);
+		TT = cta_expand(Cn, B.tile_tab, [&](uint32_t i) { return (nxt[i].d.n + SW_TILE - 1) / SW_TILE; }, [&](uint32_t i, uint32_t slot) { nxt[i].d.tile0 = slot; }, sm);
+		if(pd2)
+			FPT = cta_expand(Cn, B.fp_tab, [&](uint32_t i) { return (nxt[i].d.nf + FP_TILE - 1) / FP_TILE; }, [](uint32_t, uint32_t) {}, sm);
+	}
+	// partition plans of this level: scaffold list, elements, flip lists, SCG lists
+	const uint32_t pdims[4] = {pd0, pd1, pd2, pd3};
+	uint32_t ptt[4], poff[4];
+	unsigned long long pend[4];
+	uint32_t tab_off = 0;
+	unsigned long long item_end = 0;
+	for(int pl = 0; pl < 4; pl++) {
+		poff[pl] = tab_off;
+		ptt[pl] = 0;
+		if(pdims[pl]) {
+			const PartJob* __restrict__ pj = B.part_jobs + (size_t)pl * Pmax;
+			ptt[pl] = cta_expand(P, B.part_tab + tab_off, [&](uint32_t i) { return (pj[i].n + SW_TILE - 1) / SW_TILE; }, [](uint32_t, uint32_t) {}, sm);
+		}
+		tab_off += ptt[pl];
+		item_end += (unsigned long long)ptt[pl] * pdims[pl];
+		pend[pl] = item_end;
+	}
+	// terminal clusters of this level
+	const uint32_t tm_items = cta_expand(Tn, B.tm_tab, [&](uint32_t i) { return (B.tjobs[i].ns + TM_CHUNK - 1) / TM_CHUNK; }, [](uint32_t, uint32_t) {}, sm);
+	for(uint32_t i = threadIdx.x; i < Tn; i += LV_THREADS) {
+		B.tstats[i].total_size = 0;
+		B.tstats[i].scg_copies = 0;
+	}
+	for(uint32_t i = threadIdx.x; i < Tn * W; i += LV_THREADS)
+		B.tunion[i] = 0;
+	// the one entry of low[] that k_scaf_sides left alone per job
+	for(uint32_t k = threadIdx.x; k < ctl->JM; k += LV_THREADS)
+		B.low[B.jobs[B.jobs_mine[k]].sstar] = 0;
+	atomicAdd(&sm_el, el);
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		ctl->P = P; ctl->Tn = Tn; ctl->TM_items = tm_items; ctl->term_blocks_done = 0;
+		for(int pl = 0; pl < 4; pl++) {
+			ctl->part_TT[pl] = ptt[pl]; ctl->part_tab_off[pl] = poff[pl]; ctl->part_job_off[pl] = (uint32_t)pl * Pmax; ctl->part_item_end[pl] = pend[pl];
+		}
+		ctl->partition_elements += sm_el;
+		ctl->next_id = next_id0 + 2 * P;
+		ctl->nrec = nrec0 + C;
+		if(C > 0)                                           // a level the host enqueued past the end of the search is empty and does not count
+			ctl->level++;
+		ctl->tickets[0] = ctl->tickets[1] = ctl->tickets[2] = 0;
+		// the next level (nothing to do in it when no cluster was split)
+		ctl->C = build_next? Cn : 0;
+		ctl->TT = TT; ctl->FPT = FPT; ctl->tab_total = tab_total;
+		ctl->J = ctl->JM = ctl->CL_items = ctl->SS_items = 0;
+		ctl->done = (Cn == 0 || ctl->done)? 1u : 0u;
+		if(Cn > B.Cmax)
+			ctl->error = 2;
+		B.prog->nrec = ctl->nrec;
+		B.prog->error = ctl->error;
+		B.prog->done = ctl->done;
+		__threadfence_system();
+		B.prog->levels_done = ctl->level;
+		__threadfence_system();
+	}
+}
+
+// pending clusters become bins without being evaluated (abw_search_set_max_levels): the children of the last level that was run
+__global__ void __launch_bounds__(LV_THREADS) k_pending_jobs(const LevelBufs B, int cur, uint32_t Cpend_from_P, uint32_t W)
+{
+	__shared__ uint32_t sm[33];
+	LevelCtl* const ctl = B.ctl;
+	const LevelCluster* __restrict__ cls = B.cl[cur];
+	const uint32_t Tn = Cpend_from_P? 2 * ctl->P : ctl->C;
+	for(uint32_t i = threadIdx.x; i < Tn; i += LV_THREADS) {
+		TermJob tj;
+		tj.sOff = cls[i].d.sOff; tj.ns = cls[i].d.ns; tj.id = cls[i].id; tj.rec = 0xFFFFFFFFu;
+		B.tjobs[i] = tj;
+		B.tstats[i].total_size = 0;
+		B.tstats[i].scg_copies = 0;
+	}
+	for(uint32_t i = threadIdx.x; i < Tn * W; i += LV_THREADS)
+		B.tunion[i] = 0;
+	__syncthreads();
+	const uint32_t tm_items = cta_expand(Tn, B.tm_tab, [&](uint32_t i) { return (B.tjobs[i].ns + TM_CHUNK - 1) / TM_CHUNK; }, [](uint32_t, uint32_t) {}, sm);
+	if(threadIdx.x == 0) {
+		ctl->Tn = Tn; ctl->TM_items = tm_items; ctl->term_blocks_done = 0;
+	}
+}
+
+// terminal cluster: bins of its scaffolds and datapoints (abawaca.cpp:135-138), total size and SCG tallies (ClusterQuality.cpp:44-48,78-87).  The last CTA to
+// finish completes the records: SCGdb::num_unique_scgs / average_num_copies_for_unique_scgs (SCGdb.cpp:6-18,41-55) and, when per-scaffold G+C and coverage were
+// given, the summary statistics of the bin (ClusterQuality::gc / cvg with standard_deviation, ClusterQuality.cpp:6-27,51-75): over the ASSIGNED scaffolds of the
+// bin in scaffold-id order (std::set iteration), mean = sum(len * x) / sum(len), stdev = sqrt(sum(len * (x - mean) * (x - mean)) / (sum(len) - 1)), evaluated
+// with exactly those fp64 operations in that order; (-1, -1) for a bin without assigned scaffolds.  The scaffold list of a cluster stays in ascending id order
+// through the stable partitions, so one thread walks its bin.
+__global__ void __launch_bounds__(128) k_finalize_terminal(const uint32_t* __restrict__ scaf_list, const LevelBufs B, const ScafRow* __restrict__ rows,
+                                    const uint8_t* __restrict__ assigned, const uint64_t* __restrict__ scgmask, uint32_t W, uint32_t* __restrict__ scaf_member,
+                                    uint32_t* __restrict__ scaf_final, const double* __restrict__ x_gc, const double* __restrict__ x_cvg)
+{
+	__shared__ int sm_last;
+	LevelCtl* const ctl = B.ctl;
+	const uint32_t items = ctl->TM_items, Tn = ctl->Tn;
+	for(uint32_t it = blockIdx.x; it < items; it += gridDim.x) {
+		const uint2 te = B.tm_tab[it];
+		const TermJob jb = B.tjobs[te.x];
+		const uint32_t i1 = min(jb.ns, (te.y + 1) * TM_CHUNK);
+		for(uint32_t i = te.y * TM_CHUNK + threadIdx.x; i < i1; i += blockDim.x) {
+			const uint32_t s = scaf_list[jb.sOff + i] & EL_SCAF_MASK;
+			scaf_member[s] = jb.id;
+			if(assigned[s]) {
+				scaf_final[s] = jb.id;
+				atomicAdd(&B.tstats[te.x].total_size, (unsigned long long)rows[s].len);
+				uint32_t copies = 0;
+				for(uint32_t w = 0; w < W; w++) {
+					const uint64_t m = scgmask[(uint64_t)s * W + w];
+					if(m) {
+						copies += __popcll(m);
+						atomicOr((unsigned long long*)&B.tunion[(uint64_t)te.x * W + w], (unsigned long long)m);
+					}
+				}
+				if(copies)
+					atomicAdd(&B.tstats[te.x].scg_copies, (unsigned long long)copies);
+			}
+		}
+	}
+	__threadfence();
+	__syncthreads();
+	if(threadIdx.x == 0)
+		sm_last = (atomicAdd(&ctl->term_blocks_done, 1u) == gridDim.x - 1);
+	__syncthreads();
+	if(!sm_last)
+		return;
+	__threadfence();
+	for(uint32_t q = threadIdx.x; q < Tn; q += blockDim.x) {
+		const TermJob jb = B.tjobs[q];
+		if(jb.rec >= B.rec_cap)
+			continue;
+		uint32_t u = 0;
+		for(uint32_t w = 0; w < W; w++)
+			u += (uint32_t)__popcll(__ldcg((const unsigned long long*)&B.tunion[(uint64_t)q * W + w]));
+		const unsigned long long size = __ldcg(&B.tstats[q].total_size), copies = __ldcg(&B.tstats[q].scg_copies);
+		abw_cluster_rec* r = B.recs + jb.rec;
+		r->total_size = size;
+		r->scg_unique = u;
+		r->scg_avg = (copies == 0)? 0.0 : __ddiv_rn((double)copies, (double)u);   // SCGdb.cpp:54
+	}
+	if(x_gc != nullptr) {
+		for(uint32_t t = threadIdx.x; t < 2 * Tn; t += blockDim.x) {
+			const TermJob jb = B.tjobs[t >> 1];
+			if(jb.rec >= B.rec_cap)
+				continue;
+			const double* __restrict__ x = (t & 1)? x_cvg : x_gc;
+			unsigned long long total = 0;
+			uint32_t count = 0;
+			double mean = 0.0;
+			for(uint32_t i = 0; i < jb.ns; i++) {
+				const uint32_t sc = scaf_list[jb.sOff + i] & EL_SCAF_MASK;
+				if(assigned[sc]) {
+					const unsigned long long l = rows[sc].len;
+					mean = __dadd_rn(mean, __dmul_rn(__ull2double_rn(l), x[sc]));
+					total += l;
+					count++;
+				}
+			}
+			double sd = 0.0;
+			if(count == 0)
+				mean = sd = -1.0;
+			else {
+				mean = __ddiv_rn(mean, __ull2double_rn(total));
+				for(uint32_t i = 0; i < jb.ns; i++) {
+					const uint32_t sc = scaf_list[jb.sOff + i] & EL_SCAF_MASK;
+					if(assigned[sc]) {
+						const double dlt = __dsub_rn(x[sc], mean);
+						sd = __dadd_rn(sd, __dmul_rn(__dmul_rn(__ull2double_rn(rows[sc].len), dlt), dlt));
+					}
+				}
+				sd = __dsqrt_rn(__ddiv_rn(sd, __ull2double_rn(total - 1ull)));
+			}
+			abw_cluster_rec* r = B.recs + jb.rec;
+			if(t & 1) { r->cvg_avg = mean; r->cvg_sd = sd; }
+			else { r->gc_avg = mean; r->gc_sd = sd; }
+		}
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------
-// stable partition of every dimension's elements of a split cluster; the boundary flag of an element becomes
-// "value differs from the previous element OF ITS NEW CLUSTER", i.e. the OR of the flags since that element
-// ---------------------------------------------------------------------------------------------------
-struct PartJob {
-	uint64_t off;        // parent segment (child 1 is written at off, child 2 at off + n1)
-	uint32_t n, n1;
-};
-
-// ---------------------------------------------------------------------------------------------------
-// stable partition of every dimension's elements of a split cluster (same warp-striped rows as k_sweep_ss); the boundary flag of an
+// stable partition of the elements of the split clusters, every dimension (same warp-striped rows as k_sweep_ss); the boundary flag of an
 // element becomes "value differs from the previous element OF ITS NEW CLUSTER", i.e. the OR of the flags since that element.  Lane r owns the masks of row r:
 //   S1 = elements that go to child 1, S2 = to child 2, B = boundary flags.
 // New flag of an element of child X = OR of the old flags since the previous element of child X (itself included).  With the closers
 // P = SX that is a carry chain:  (B & ~P) + ~P  overflows a run of non-closers exactly when the run holds a boundary, and the carry
 // lands on the closer that ends the run.  A run of elements is summarised per child by H ("contains an element of the child") and
 // T ("a boundary is pending after the last such element"); summaries compose associatively, so rows, warps and tiles chain with a
-// scan and the usual look-back.
+// scan and the usual look-back.  The scaffold list, the flip lists and the SCG lists of the level are u32 lists partitioned by the same launch
+// ("plans": work items of all plans share one ticket); the scaffold-list plan also commits the new assignment of every scaffold it moves.
 // ---------------------------------------------------------------------------------------------------
 // bits: 0 = H1, 1 = H2, 2 = T1, 3 = T2
 __device__ __forceinline__ uint32_t ht_compose(uint32_t first, uint32_t then)
@@ -1041,277 +1579,241 @@ __device__ __forceinline__ uint32_t ht_compose(uint32_t first, uint32_t then)
 // pending state (bit 0: child 1, bit 1: child 2) after a run with summary ht entered in `state`
 __device__ __forceinline__ uint32_t ht_apply(uint32_t ht, uint32_t state) { return ((ht >> 2) | (state & ~ht)) & 3u; }
 
-__device__ __forceinline__ unsigned long long lb2_pack(uint32_t cnt, uint32_t ht, uint32_t st) { return (unsigned long long)cnt | ((unsigned long long)ht << 32) | ((unsigned long long)st << 62); }
+// look-back word of the partition: count of child-1 elements, summary bits, the epoch of the level (6 bits), state
+__device__ __forceinline__ unsigned long long lb2_pack(uint32_t cnt, uint32_t ht, uint32_t st, uint32_t epoch)
+{
+	return (unsigned long long)cnt | ((unsigned long long)ht << 32) | ((unsigned long long)(epoch & 63u) << 56) | ((unsigned long long)st << 62);
+}
 
-__global__ void __launch_bounds__(SW_THREADS, 3) k_partition2(const uint32_t* __restrict__ Ein, uint32_t* __restrict__ Eout, uint64_t N, const PartJob* __restrict__ jobs,
-                                                             uint32_t TT, const uint2* __restrict__ tile_tab, const uint8_t* __restrict__ side,
-                                                             unsigned long long* __restrict__ ticket, unsigned long long* __restrict__ lookback, int* __restrict__ error_flag)
+struct PartPlans {
+	const uint32_t* in[4];
+	uint32_t*       out[4];
+	uint64_t        stride[4];
+};
+
+__global__ void __launch_bounds__(SW_THREADS, 3) k_partition2(const PartPlans plans, LevelCtl* __restrict__ ctl, const PartJob* __restrict__ jobs_all,
+                                                             const uint2* __restrict__ tab_all, const uint8_t* __restrict__ side, const uint8_t* __restrict__ new_assigned,
+                                                             uint8_t* __restrict__ assigned, uint32_t epoch, unsigned long long* __restrict__ lookback)
 {
 	__shared__ uint32_t sm_cnt[SW_THREADS / 32];
 	__shared__ uint32_t sm_ht[SW_THREADS / 32];
 	__shared__ unsigned long long sm_w;
-	if(threadIdx.x == 0)
-		sm_w = atomicAdd(ticket, 1ull);
-	__syncthreads();
-	const uint64_t w = sm_w;
-	const uint32_t d = (uint32_t)(w / TT);
-	const uint2 te = __ldg(tile_tab + (uint32_t)(w - (uint64_t)d * TT));
-	const PartJob jb = jobs[te.x];
-	const uint32_t tile = te.y;
-	const uint32_t* __restrict__ src = Ein + (uint64_t)d * N + jb.off;
-	uint32_t* __restrict__ dst1 = Eout + (uint64_t)d * N + jb.off;
-	uint32_t* __restrict__ dst2 = dst1 + jb.n1;
+	const unsigned long long end0 = ctl->part_item_end[0], end1 = ctl->part_item_end[1], end2 = ctl->part_item_end[2], end3 = ctl->part_item_end[3];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t wbase = tile * SW_TILE + warp * SW_WARP_CHUNK;
-	uint32_t el[32];
-	uint32_t my1 = 0;                                      // bit r: my element of row r goes to child 1
-	uint32_t mS1 = 0, mV = 0, mB = 0;                      // masks of row `lane`
-	const bool active = wbase < jb.n;
-	const bool full = wbase + SW_WARP_CHUNK <= jb.n;       // warp uniform: all 1024 elements of the chunk exist, no bounds checks
-	if(full) {
+	while(true) {
+		if(threadIdx.x == 0)
+			sm_w = atomicAdd(&ctl->tickets[2], 1ull);
+		__syncthreads();
+		const uint64_t w = sm_w;
+		if(w >= end3)
+			break;
+		const int pl = (w >= end0) + (w >= end1) + (w >= end2);
+		const uint64_t wl = w - ((pl == 0)? 0ull : (pl == 1)? end0 : (pl == 2)? end1 : end2);
+		const uint32_t TT = ctl->part_TT[pl];
+		const uint32_t d = (uint32_t)(wl / TT);
+		const uint2 te = __ldg(tab_all + ctl->part_tab_off[pl] + (uint32_t)(wl - (uint64_t)d * TT));
+		const PartJob jb = jobs_all[ctl->part_job_off[pl] + te.x];
+		const uint32_t tile = te.y;
+		const uint64_t stride = plans.stride[pl];
+		const uint32_t* __restrict__ src = plans.in[pl] + (uint64_t)d * stride + jb.off;
+		uint32_t* __restrict__ dst1 = plans.out[pl] + (uint64_t)d * stride + jb.off;
+		uint32_t* __restrict__ dst2 = dst1 + jb.n1;
+		const uint32_t wbase = tile * SW_TILE + warp * SW_WARP_CHUNK;
+		uint32_t el[32];
+		uint32_t my1 = 0;                                      // bit r: my element of row r goes to child 1
+		uint32_t mS1 = 0, mV = 0, mB = 0;                      // masks of row `lane`
+		const bool active = wbase < jb.n;
+		const bool full = wbase + SW_WARP_CHUNK <= jb.n;       // warp uniform: all 1024 elements of the chunk exist, no bounds checks
+		if(full) {
 #pragma unroll
-		for(int r = 0; r < 32; r++)
-			el[r] = __ldg(src + wbase + r * 32 + lane);
-		mV = 0xFFFFFFFFu;
+			for(int r = 0; r < 32; r++)
+				el[r] = __ldg(src + wbase + r * 32 + lane);
+			mV = 0xFFFFFFFFu;
 #pragma unroll
-		for(int r = 0; r < 32; r++) {
-			const bool is1 = side[el[r] & EL_SCAF_MASK] == 1;
-			const uint32_t s1 = __ballot_sync(0xffffffffu, is1);
-			const uint32_t b = __ballot_sync(0xffffffffu, el[r] >> 31);
-			my1 |= (is1? 1u : 0u) << r;
-			if(lane == r) { mS1 = s1; mB = b; }
+			for(int r = 0; r < 32; r++) {
+				const bool is1 = side[el[r] & EL_SCAF_MASK] == 1;
+				const uint32_t s1 = __ballot_sync(0xffffffffu, is1);
+				const uint32_t b = __ballot_sync(0xffffffffu, el[r] >> 31);
+				my1 |= (is1? 1u : 0u) << r;
+				if(lane == r) { mS1 = s1; mB = b; }
+			}
 		}
-	}
-	else if(active) {
+		else if(active) {
 #pragma unroll
-		for(int r = 0; r < 32; r++) {
-			const uint32_t idx = wbase + r * 32 + lane;
-			el[r] = (idx < jb.n)? __ldg(src + idx) : 0xFFFFFFFFu;
-		}
+			for(int r = 0; r < 32; r++) {
+				const uint32_t idx = wbase + r * 32 + lane;
+				el[r] = (idx < jb.n)? __ldg(src + idx) : 0xFFFFFFFFu;
+			}
 #pragma unroll
-		for(int r = 0; r < 32; r++) {
-			const uint32_t idx = wbase + r * 32 + lane;
-			const bool valid = idx < jb.n;
-			const bool is1 = valid && side[el[r] & EL_SCAF_MASK] == 1;
-			const uint32_t s1 = __ballot_sync(0xffffffffu, is1);
-			const uint32_t v = __ballot_sync(0xffffffffu, valid);
-			const uint32_t b = __ballot_sync(0xffffffffu, valid && (el[r] >> 31));
-			my1 |= (is1? 1u : 0u) << r;
-			if(lane == r) { mS1 = s1; mV = v; mB = b; }
+			for(int r = 0; r < 32; r++) {
+				const uint32_t idx = wbase + r * 32 + lane;
+				const bool valid = idx < jb.n;
+				const bool is1 = valid && side[el[r] & EL_SCAF_MASK] == 1;
+				const uint32_t s1 = __ballot_sync(0xffffffffu, is1);
+				const uint32_t v = __ballot_sync(0xffffffffu, valid);
+				const uint32_t b = __ballot_sync(0xffffffffu, valid && (el[r] >> 31));
+				my1 |= (is1? 1u : 0u) << r;
+				if(lane == r) { mS1 = s1; mV = v; mB = b; }
+			}
 		}
-	}
-	const uint32_t mS2 = mV & ~mS1;
-	const uint32_t c1 = __popc(mS1);
-	const unsigned long long s1sum = (unsigned long long)(mB & ~mS1) + (unsigned long long)(uint32_t)(~mS1);
-	const unsigned long long s2sum = (unsigned long long)(mB & ~mS2) + (unsigned long long)(uint32_t)(~mS2);
-	uint32_t newflags = (((uint32_t)s1sum | mB) & mS1) | (((uint32_t)s2sum | mB) & mS2);     // assuming nothing is pending when the row starts
-	const uint32_t myht = (mS1? 1u : 0u) | (mS2? 2u : 0u) | ((uint32_t)(s1sum >> 32) << 2) | ((uint32_t)(s2sum >> 32) << 3);
-	// inclusive scans over the rows of the warp
-	uint32_t icnt = c1, iht = myht;
+		const uint32_t mS2 = mV & ~mS1;
+		const uint32_t c1 = __popc(mS1);
+		const unsigned long long s1sum = (unsigned long long)(mB & ~mS1) + (unsigned long long)(uint32_t)(~mS1);
+		const unsigned long long s2sum = (unsigned long long)(mB & ~mS2) + (unsigned long long)(uint32_t)(~mS2);
+		uint32_t newflags = (((uint32_t)s1sum | mB) & mS1) | (((uint32_t)s2sum | mB) & mS2);     // assuming nothing is pending when the row starts
+		const uint32_t myht = (mS1? 1u : 0u) | (mS2? 2u : 0u) | ((uint32_t)(s1sum >> 32) << 2) | ((uint32_t)(s2sum >> 32) << 3);
+		// inclusive scans over the rows of the warp
+		uint32_t icnt = c1, iht = myht;
 #pragma unroll
-	for(int o = 1; o < 32; o <<= 1) {
-		const uint32_t c2 = __shfl_up_sync(0xffffffffu, icnt, o), h2 = __shfl_up_sync(0xffffffffu, iht, o);
-		if(lane >= o) {
-			icnt += c2;
-			iht = ht_compose(h2, iht);
+		for(int o = 1; o < 32; o <<= 1) {
+			const uint32_t c2 = __shfl_up_sync(0xffffffffu, icnt, o), h2 = __shfl_up_sync(0xffffffffu, iht, o);
+			if(lane >= o) {
+				icnt += c2;
+				iht = ht_compose(h2, iht);
+			}
 		}
-	}
-	if(lane == 31) {
-		sm_cnt[warp] = icnt;
-		sm_ht[warp] = iht;
-	}
-	__syncthreads();
-	if(threadIdx.x < 32) {
-		// exclusive over the warps (every lane computes the same), then the look-back over the earlier tiles of this (job, dimension)
-		uint32_t rc = 0, rh = 0;
-		uint32_t wc = 0, wh = 0;
+		if(lane == 31) {
+			sm_cnt[warp] = icnt;
+			sm_ht[warp] = iht;
+		}
+		__syncthreads();
+		if(threadIdx.x < 32) {
+			// exclusive over the warps (every lane computes the same), then the look-back over the earlier tiles of this (job, dimension)
+			uint32_t rc = 0, rh = 0;
+			uint32_t wc = 0, wh = 0;
 #pragma unroll
-		for(int w2 = 0; w2 < SW_THREADS / 32; w2++) {
-			const uint32_t tc = sm_cnt[w2], th = sm_ht[w2];
-			if(w2 == lane) { wc = rc; wh = rh; }
-			rc += tc;
-			rh = ht_compose(rh, th);
-		}
-		uint32_t carry_cnt = 0, carry_state = 3u;          // the first element of each child gets its boundary flag set
-		if(tile > 0) {
-			if(lane == 0)
-				st_volatile_u64(&lookback[w], lb2_pack(rc, rh, LB_AGG));
-			uint32_t acc = 0;                               // summary of the tiles between the probe window and this tile
-			uint64_t base = w - 1;
-			uint32_t remaining = tile;
-			bool done = false, failed = false;
-			while(!done && !failed) {
-				const uint32_t cnt = min(32u, remaining);
-				unsigned long long v;
-				uint32_t first_prefix, spins = 0;
-				while(true) {
-					v = ((uint32_t)lane < cnt)? ld_volatile_u64(&lookback[base - lane]) : lb2_pack(0, 0, LB_AGG);
-					const uint32_t st = (uint32_t)(v >> 62);
-					const uint32_t pm = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == LB_PREFIX);
-					const uint32_t em = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == LB_EMPTY);
-					first_prefix = pm? (uint32_t)(__ffs(pm) - 1) : 32u;
-					const uint32_t need = (first_prefix >= 32u)? 0xFFFFFFFFu : ((2u << first_prefix) - 1u);
-					if((em & need) == 0)
+			for(int w2 = 0; w2 < SW_THREADS / 32; w2++) {
+				const uint32_t tc = sm_cnt[w2], th = sm_ht[w2];
+				if(w2 == lane) { wc = rc; wh = rh; }
+				rc += tc;
+				rh = ht_compose(rh, th);
+			}
+			uint32_t carry_cnt = 0, carry_state = 3u;          // the first element of each child gets its boundary flag set
+			if(tile > 0) {
+				if(lane == 0)
+					st_volatile_u64(&lookback[w], lb2_pack(rc, rh, LB_AGG, epoch));
+				uint32_t acc = 0;                               // summary of the tiles between the probe window and this tile
+				uint64_t base = w - 1;
+				uint32_t remaining = tile;
+				bool done = false, failed = false;
+				while(!done && !failed) {
+					const uint32_t cnt = min(32u, remaining);
+					unsigned long long v;
+					uint32_t first_prefix, spins = 0;
+					while(true) {
+						v = ((uint32_t)lane < cnt)? ld_volatile_u64(&lookback[base - lane]) : lb2_pack(0, 0, LB_AGG, epoch);
+						const uint32_t st = cnt_state(v, epoch);
+						const uint32_t pm = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == LB_PREFIX);
+						const uint32_t em = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == LB_EMPTY);
+						first_prefix = pm? (uint32_t)(__ffs(pm) - 1) : 32u;
+						const uint32_t need = (first_prefix >= 32u)? 0xFFFFFFFFu : ((2u << first_prefix) - 1u);
+						if((em & need) == 0)
+							break;
+						if(++spins >= LB_SPIN_LIMIT) {
+							failed = true;
+							break;
+						}
+					}
+					if(failed)
 						break;
-					if(++spins >= LB_SPIN_LIMIT) {
-						failed = true;
-						break;
+					const bool take = (uint32_t)lane < cnt && (uint32_t)lane <= first_prefix;
+					carry_cnt += __reduce_add_sync(0xffffffffu, take? (uint32_t)v : 0u);
+					// summaries compose in tile order: lane l holds tile base - l, i.e. higher lanes are EARLIER tiles.  Suffix-compose towards lane 0.
+					uint32_t h = (take && (uint32_t)lane != first_prefix)? ((uint32_t)(v >> 32) & 0xFu) : 0u;      // identity for lanes that do not take part
+#pragma unroll
+					for(int o = 1; o < 32; o <<= 1) {
+						const uint32_t hh = __shfl_down_sync(0xffffffffu, h, o);
+						if(lane + o < 32)
+							h = ht_compose(hh, h);
+					}
+					const uint32_t window = __shfl_sync(0xffffffffu, h, 0);            // all aggregates of the window, earliest first
+					if(first_prefix < 32u) {
+						const uint32_t state_at_prefix = (uint32_t)(__shfl_sync(0xffffffffu, v, (int)first_prefix) >> 32) & 3u;
+						carry_state = ht_apply(acc, ht_apply(window, state_at_prefix));
+						done = true;
+					}
+					else {
+						acc = ht_compose(window, acc);
+						base -= 32;
+						remaining -= 32;
 					}
 				}
-				if(failed)
-					break;
-				const bool take = (uint32_t)lane < cnt && (uint32_t)lane <= first_prefix;
-				carry_cnt += __reduce_add_sync(0xffffffffu, take? (uint32_t)v : 0u);
-				// summaries compose in tile order: lane l holds tile base - l, i.e. higher lanes are EARLIER tiles.  Suffix-compose towards lane 0.
-				uint32_t h = (take && (uint32_t)lane != first_prefix)? ((uint32_t)(v >> 32) & 0xFu) : 0u;      // identity for lanes that do not take part
+				if(failed && lane == 0)
+					atomicExch(&ctl->error, 1u);
+			}
+			if(lane == 0)
+				st_volatile_u64(&lookback[w], lb2_pack(carry_cnt + rc, ht_apply(rh, carry_state), LB_PREFIX, epoch));
+			if(lane < SW_THREADS / 32) {
+				sm_cnt[lane] = carry_cnt + wc;                  // child-1 elements before warp `lane`
+				sm_ht[lane] = ht_apply(wh, carry_state);        // pending state when warp `lane` starts
+			}
+		}
+		__syncthreads();
+		if(active) {
+			uint32_t ecnt = __shfl_up_sync(0xffffffffu, icnt, 1), eht = __shfl_up_sync(0xffffffffu, iht, 1);
+			if(lane == 0) {
+				ecnt = 0;
+				eht = 0;
+			}
+			const uint32_t row_before1 = sm_cnt[warp] + ecnt;
+			const uint32_t state = ht_apply(eht, sm_ht[warp]);      // pending when my row starts: lands on the first element of each child in the row
+			if(state & 1u)
+				newflags |= mS1 & (0u - mS1);
+			if(state & 2u)
+				newflags |= mS2 & (0u - mS2);
+			const uint32_t lt = (1u << lane) - 1u;
+			const bool commit = (pl == 0);                      // the scaffold list: every scaffold of a split cluster passes here exactly once
+			if(full) {
 #pragma unroll
-				for(int o = 1; o < 32; o <<= 1) {
-					const uint32_t hh = __shfl_down_sync(0xffffffffu, h, o);
-					if(lane + o < 32)
-						h = ht_compose(hh, h);
-				}
-				const uint32_t window = __shfl_sync(0xffffffffu, h, 0);            // all aggregates of the window, earliest first
-				if(first_prefix < 32u) {
-					const uint32_t state_at_prefix = (uint32_t)(__shfl_sync(0xffffffffu, v, (int)first_prefix) >> 32) & 3u;
-					carry_state = ht_apply(acc, ht_apply(window, state_at_prefix));
-					done = true;
-				}
-				else {
-					acc = ht_compose(window, acc);
-					base -= 32;
-					remaining -= 32;
+				for(int r = 0; r < 32; r++) {
+					const uint32_t S1r = __shfl_sync(0xffffffffu, mS1, r), Fr = __shfl_sync(0xffffffffu, newflags, r), b1 = __shfl_sync(0xffffffffu, row_before1, r);
+					const uint32_t idx = wbase + r * 32 + lane;
+					const uint32_t before1 = b1 + __popc(S1r & lt);
+					const uint32_t e = (el[r] & 0x7FFFFFFFu) | (((Fr >> lane) & 1u) << 31);
+					uint32_t* const dst = ((my1 >> r) & 1u)? dst1 + before1 : dst2 + (idx - before1);
+					*dst = e;
+					if(commit)
+						assigned[el[r] & EL_SCAF_MASK] = new_assigned[el[r] & EL_SCAF_MASK] != 0;
 				}
 			}
-			if(failed && lane == 0)
-				atomicExch(error_flag, 1);
-		}
-		if(lane == 0)
-			st_volatile_u64(&lookback[w], lb2_pack(carry_cnt + rc, ht_apply(rh, carry_state), LB_PREFIX));
-		if(lane < SW_THREADS / 32) {
-			sm_cnt[lane] = carry_cnt + wc;                  // child-1 elements before warp `lane`
-			sm_ht[lane] = ht_apply(wh, carry_state);        // pending state when warp `lane` starts
-		}
-	}
-	__syncthreads();
-	if(!active)
-		return;
-	uint32_t ecnt = __shfl_up_sync(0xffffffffu, icnt, 1), eht = __shfl_up_sync(0xffffffffu, iht, 1);
-	if(lane == 0) {
-		ecnt = 0;
-		eht = 0;
-	}
-	const uint32_t row_before1 = sm_cnt[warp] + ecnt;
-	const uint32_t state = ht_apply(eht, sm_ht[warp]);      // pending when my row starts: lands on the first element of each child in the row
-	if(state & 1u)
-		newflags |= mS1 & (0u - mS1);
-	if(state & 2u)
-		newflags |= mS2 & (0u - mS2);
-	const uint32_t lt = (1u << lane) - 1u;
-	if(full) {
+			else {
 #pragma unroll
-		for(int r = 0; r < 32; r++) {
-			const uint32_t S1r = __shfl_sync(0xffffffffu, mS1, r), Fr = __shfl_sync(0xffffffffu, newflags, r), b1 = __shfl_sync(0xffffffffu, row_before1, r);
-			const uint32_t idx = wbase + r * 32 + lane;
-			const uint32_t before1 = b1 + __popc(S1r & lt);
-			const uint32_t e = (el[r] & 0x7FFFFFFFu) | (((Fr >> lane) & 1u) << 31);
-			uint32_t* const dst = ((my1 >> r) & 1u)? dst1 + before1 : dst2 + (idx - before1);
-			*dst = e;
+				for(int r = 0; r < 32; r++) {
+					const uint32_t S1r = __shfl_sync(0xffffffffu, mS1, r), Fr = __shfl_sync(0xffffffffu, newflags, r), b1 = __shfl_sync(0xffffffffu, row_before1, r);
+					const uint32_t idx = wbase + r * 32 + lane;
+					if(idx < jb.n) {
+						const uint32_t before1 = b1 + __popc(S1r & lt);
+						const uint32_t e = (el[r] & 0x7FFFFFFFu) | (((Fr >> lane) & 1u) << 31);
+						if((my1 >> r) & 1u)
+							dst1[before1] = e;
+						else
+							dst2[idx - before1] = e;
+						if(commit)
+							assigned[el[r] & EL_SCAF_MASK] = new_assigned[el[r] & EL_SCAF_MASK] != 0;
+					}
+				}
+			}
 		}
-		return;
-	}
-#pragma unroll
-	for(int r = 0; r < 32; r++) {
-		const uint32_t S1r = __shfl_sync(0xffffffffu, mS1, r), Fr = __shfl_sync(0xffffffffu, newflags, r), b1 = __shfl_sync(0xffffffffu, row_before1, r);
-		const uint32_t idx = wbase + r * 32 + lane;
-		if(idx < jb.n) {
-			const uint32_t before1 = b1 + __popc(S1r & lt);
-			const uint32_t e = (el[r] & 0x7FFFFFFFu) | (((Fr >> lane) & 1u) << 31);
-			if((my1 >> r) & 1u)
-				dst1[before1] = e;
-			else
-				dst2[idx - before1] = e;
-		}
+		__syncthreads();
 	}
 }
 
-// terminal cluster: bins of its scaffolds and datapoints (abawaca.cpp:135-138), total size and SCG tallies (ClusterQuality.cpp:44-48,78-87)
-struct TermJob { uint32_t sOff, ns, id, slot; };
-struct TermStats { unsigned long long total_size, scg_copies; };
-__global__ void k_finalize_terminal(const uint32_t* __restrict__ scaf_list, const TermJob* __restrict__ jobs, const ScafRow* __restrict__ rows, const uint8_t* __restrict__ assigned,
-                                    const uint64_t* __restrict__ scgmask, uint32_t W, uint32_t* __restrict__ scaf_member, uint32_t* __restrict__ scaf_final,
-                                    TermStats* __restrict__ stats, uint64_t* __restrict__ union_mask)
+// ClusterQuality::scg for an arbitrary scaffold list (abw_cluster_scg): OR and copy count of the SCG sets
+__global__ void k_scg_tally(const uint32_t* __restrict__ list, uint32_t n, const uint64_t* __restrict__ scgmask, uint32_t W, TermStats* __restrict__ stats,
+                            uint64_t* __restrict__ union_mask)
 {
-	const TermJob jb = jobs[blockIdx.y];
-	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.ns; i += gridDim.x * blockDim.x) {
-		const uint32_t s = scaf_list[jb.sOff + i] & EL_SCAF_MASK;
-		scaf_member[s] = jb.id;
-		if(assigned[s]) {
-			scaf_final[s] = jb.id;
-			atomicAdd(&stats[jb.slot].total_size, (unsigned long long)rows[s].len);
-			uint32_t copies = 0;
-			for(uint32_t w = 0; w < W; w++) {
-				const uint64_t m = scgmask[(uint64_t)s * W + w];
-				if(m) {
-					copies += __popcll(m);
-					atomicOr((unsigned long long*)&union_mask[(uint64_t)jb.slot * W + w], (unsigned long long)m);
-				}
-			}
-			if(copies)
-				atomicAdd(&stats[jb.slot].scg_copies, (unsigned long long)copies);
-		}
-	}
-}
-
-// Summary statistics of a terminal bin (ClusterQuality::gc / cvg with standard_deviation, ClusterQuality.cpp:6-27,51-75): over the ASSIGNED scaffolds of
-// the bin in scaffold-id order (std::set iteration), mean = sum(len * x) / sum(len), stdev = sqrt(sum(len * (x - mean) * (x - mean)) / (sum(len) - 1)),
-// evaluated with exactly those fp64 operations in that order; (-1, -1) for a bin without assigned scaffolds.  The scaffold list of a cluster stays in
-// ascending id order through the stable partitions, so one thread walks its bin.  out[job][2 * which + {0, 1}] = mean, stdev (which: 0 gc, 1 coverage).
-__global__ void k_terminal_moments(const uint32_t* __restrict__ scaf_list, const TermJob* __restrict__ jobs, uint32_t njobs, const ScafRow* __restrict__ rows,
-                                   const uint8_t* __restrict__ assigned, const double* __restrict__ x_gc, const double* __restrict__ x_cvg, double* __restrict__ out)
-{
-	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if(t >= njobs * 2)
-		return;
-	const TermJob jb = jobs[t >> 1];
-	const double* __restrict__ x = (t & 1)? x_cvg : x_gc;
-	unsigned long long total = 0;
-	uint32_t count = 0;
-	double mean = 0.0;
-	for(uint32_t i = 0; i < jb.ns; i++) {
-		const uint32_t sc = scaf_list[jb.sOff + i] & EL_SCAF_MASK;
-		if(assigned[sc]) {
-			const unsigned long long l = rows[sc].len;
-			mean = __dadd_rn(mean, __dmul_rn(__ull2double_rn(l), x[sc]));
-			total += l;
-			count++;
-		}
-	}
-	double sd = 0.0;
-	if(count == 0)
-		mean = sd = -1.0;
-	else {
-		mean = __ddiv_rn(mean, __ull2double_rn(total));
-		for(uint32_t i = 0; i < jb.ns; i++) {
-			const uint32_t sc = scaf_list[jb.sOff + i] & EL_SCAF_MASK;
-			if(assigned[sc]) {
-				const double dlt = __dsub_rn(x[sc], mean);
-				sd = __dadd_rn(sd, __dmul_rn(__dmul_rn(__ull2double_rn(rows[sc].len), dlt), dlt));
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t s = list[i];
+		uint32_t copies = 0;
+		for(uint32_t w = 0; w < W; w++) {
+			const uint64_t m = scgmask[(uint64_t)s * W + w];
+			if(m) {
+				copies += __popcll(m);
+				atomicOr((unsigned long long*)&union_mask[w], (unsigned long long)m);
 			}
 		}
-		sd = __dsqrt_rn(__ddiv_rn(sd, __ull2double_rn(total - 1ull)));
-	}
-	out[(size_t)(t >> 1) * 4 + (t & 1) * 2] = mean;
-	out[(size_t)(t >> 1) * 4 + (t & 1) * 2 + 1] = sd;
-}
-
-__global__ void k_commit_assigned(const uint32_t* __restrict__ scaf_list, const ClusterDesc* __restrict__ clusters, const SplitJob* __restrict__ jobs,
-                                  const uint8_t* __restrict__ new_assigned, uint8_t* __restrict__ assigned)
-{
-	const SplitJob jb = jobs[blockIdx.y];
-	const ClusterDesc cl = clusters[jb.cluster];
-	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cl.ns; i += gridDim.x * blockDim.x) {
-		const uint32_t s = scaf_list[cl.sOff + i] & EL_SCAF_MASK;      // the partition kernel leaves its flag bit on list entries
-		assigned[s] = new_assigned[s] != 0;
+		if(copies)
+			atomicAdd(&stats->scg_copies, (unsigned long long)copies);
 	}
 }
 
@@ -1665,13 +2167,6 @@ __global__ void k_iota_pairs(unsigned long long* __restrict__ keys, const uint32
 // ===================================================================================================
 // host side
 // ===================================================================================================
-struct HostCluster {
-	uint32_t id = 0, parent = 0;
-	ClusterDesc desc{};
-	uint32_t nassigned = 0;
-	std::vector<uint64_t> never;     // [W]
-};
-
 struct abw_search {
 	abw_ctx* ctx = nullptr;
 	uint64_t N = 0;
@@ -1972,76 +2467,23 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	return ABW_OK;
 }
 
-// host copy of cand_better (the reference's total order), used to merge the per-rank bests of a sharded search
-bool host_cand_better(int strategy, const CandRec& x, const CandRec& y)
-{
-	if(!x.found) return false;
-	if(!y.found) return true;
-	if(strategy == ABW_SENS_SPEC) {
-		if(x.k1 != y.k1) return x.k1 > y.k1;
-	}
-	else {
-		if(x.k1 != y.k1) return x.k1 < y.k1;
-		if(x.k2 != y.k2) return x.k2 < y.k2;
-	}
-	if(x.dim0 != y.dim0) return x.dim0 < y.dim0;
-	return x.p < y.p;
-}
-
-bool is_legal(const abw_params& p, int strategy, const abw_best& b)
-{
-	if(!b.found)
-		return false;
-	if(strategy == ABW_SENS_SPEC)       // ...Specificity.h:31-35
-		return (b.a >= p.sensitivity_threshold) && (b.b >= p.specificity_threshold) && (b.a + b.b >= p.sum_threshold) && (b.a * b.b >= p.product_threshold);
-	return b.a <= p.split_scaf_ratio_threshold;   // ...SplitScafs.h:38
-}
-
-template <typename T>
-int to_device(abw_ctx* ctx, DevBuf<T>& buf, const std::vector<T>& h)
-{
-	if(buf.n < h.size())
-		ABW_CUDA(ctx, buf.alloc(std::max<size_t>(h.size(), 64)));
-	if(!h.empty())
-		ABW_CUDA(ctx, abw_stage_upload(ctx, buf.p, h.data(), sizeof(T) * h.size()));
-	return ABW_OK;
-}
-
+// Replaces the work-list loop abawaca.cpp:98-197.  The host enqueues level after level on the context stream and never waits for one: work sizes live in the
+// device-resident LevelCtl, every kernel is launched with a grid that does not depend on the data (its CTAs walk the level's work items), look-back words carry
+// the level's epoch instead of being cleared per level, and k_level_decide reports progress through mapped pinned memory, which the host polls between launches.
+// A sharded search (coll != null) adds two collectives per level -- the per-cluster bests of all ranks, then one buffer with the owner's vote -- whose sizes are
+// bounds known to the host (at level l at most 2^l clusters), so they are enqueued blindly as well when the collectives are stream ordered.
 int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_cluster_rec* h_recs, uint32_t cap, uint32_t* nrecs, uint32_t* h_dp2cluster,
                uint32_t* h_scaf2cluster)
 {
-	const int world = coll? coll->world : 1, my_rank = coll? coll->rank : 0;
+	const uint32_t world = coll? (uint32_t)coll->world : 1u;
+	const bool ordered = coll && coll->stream_ordered != 0;
 	if(s->D_total == 0)
 		s->D_total = s->D;
-	// which rank holds which dimensions
-	std::vector<uint32_t> shard_off(world, 0), shard_n(world, s->D);
-	if(coll) {
-		DevBuf<uint32_t> d_mine, d_all;
-		ABW_CUDA(ctx, d_mine.alloc(2));
-		ABW_CUDA(ctx, d_all.alloc(2 * (size_t)world));
-		uint32_t mine[2] = {s->dim_offset, s->D};
-		ABW_CUDA(ctx, cudaMemcpyAsync(d_mine.p, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
-		ABW_CUDA(ctx, abw_sync(ctx));
-		if(coll->allgather(coll->user, d_mine.p, d_all.p, sizeof(mine)) != 0)
-			return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run_sharded: allgather callback failed");
-		std::vector<uint32_t> all(2 * (size_t)world);
-		ABW_CUDA(ctx, abw_fetch(ctx, all.data(), d_all.p, sizeof(uint32_t) * all.size()));
-		ABW_CUDA(ctx, abw_sync(ctx));
-		for(int r = 0; r < world; r++) {
-			shard_off[r] = all[2 * r];
-			shard_n[r] = all[2 * r + 1];
-		}
-	}
-	auto owner_of = [&](uint32_t gdim) {
-		for(int r = 0; r < world; r++)
-			if(gdim >= shard_off[r] && gdim < shard_off[r] + shard_n[r])
-				return r;
-		return -1;
-	};
-	DevBuf<CandRec> d_best_all;
 	const uint64_t N = s->N;
-	const uint32_t D = s->D, S = s->S, W = s->W;
+	const uint32_t D = s->D, S = s->S, W = s->W, K = s->K;
+	const uint64_t Sf = s->Sf;
 	const abw_params& prm = s->prm;
+	const bool ss = s->strategy == ABW_SENS_SPEC;
 	if(s->consumed)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_run: this search object was already run (element arrays are consumed); create a new one");
 	s->consumed = true;
@@ -2054,485 +2496,280 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 	sp.thr = prm.cluster_ndps_threshold;
 	// candidates below min_reported_score are not examined; that must never hide a candidate is_legal would accept, so the cut is never above
 	// the caller's product threshold (a caller who lowers product_threshold and leaves min_reported_score alone still gets every legal split)
-	sp.min_score = (s->strategy == ABW_SENS_SPEC)? std::min(prm.min_reported_score, prm.product_threshold) : prm.min_reported_score;
+	sp.min_score = ss? std::min(prm.min_reported_score, prm.product_threshold) : prm.min_reported_score;
 	sp.prune = (float)(sp.min_score * (1.0 - 1e-5));
 	if(!(sp.prune > 0.0f))
 		sp.prune = 0.0f;
 	sp.scg_min_size = prm.scg_min_size;
 	sp.fraction_in = prm.fraction_dps_in;
 
-	std::vector<HostCluster> level(1);
-	level[0].id = 1;
-	level[0].parent = 0;
-	level[0].desc.off = 0;
-	level[0].desc.n = (uint32_t)N;
-	level[0].desc.kOff = 0;
-	level[0].desc.K = s->K;
-	level[0].desc.sOff = 0;
-	level[0].desc.ns = S;
-	level[0].desc.totT = (uint32_t)s->root_totT;
-	level[0].desc.U = S;
-	level[0].desc.totLen = s->root_totLen;
-	level[0].desc.ss_ok = (s->root_viol == 0);
-	level[0].desc.fOff = 0;
-	level[0].desc.nf = (uint32_t)s->Sf;
-	level[0].nassigned = S;
-	level[0].never = s->root_never;
-	uint32_t next_id = 2, nrec = 0;
-	int cur = 0;
+	// ---- bounds: clusters of one level (every cluster below the root holds at least cluster_ndps_threshold datapoints), tiles, splits
+	const uint64_t thr = std::max<uint32_t>(prm.cluster_ndps_threshold, 1);
+	const uint64_t Cmax64 = 2 * (N / thr) + 2;
+	if(Cmax64 >= (1ull << 31))
+		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_run: too many clusters per level for this build");
+	const uint32_t Cmax = (uint32_t)Cmax64, Pmax = Cmax / 2 + 1;
+	const uint64_t TTmax = N / SW_TILE + Cmax + 1, FPTmax = Sf / FP_TILE + Cmax + 1;
+	const uint64_t items_max = TTmax * D, fp_items_max = ss? FPTmax * D : 0;
+	const uint64_t part_tab_max = (S + N + Sf + K) / SW_TILE + 4ull * Pmax + 8;
+	const uint64_t part_items_max = (S / SW_TILE + Pmax + 1) + (N / SW_TILE + Pmax + 1) * D + (ss? (Sf / SW_TILE + Pmax + 1) * D + (K / SW_TILE + Pmax + 1) * D : 0);
+	if(items_max >= (1ull << 31) || part_items_max >= (1ull << 31))
+		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_run: more than 2^31 tiles in one level");
+	const uint64_t lb_words = std::max(items_max, part_items_max);
+	const uint64_t tab_total_max = (uint64_t)K + Cmax;
 
-	DevBuf<ClusterDesc> d_clusters;
-	DevBuf<CandRec> d_cand, d_best;
-	DevBuf<uint2> d_tile_tab, d_ptile_tab, d_fp_tab;
-	DevBuf<uint32_t> d_status;
-	DevBuf<AggSlot> d_aggs, d_prefixes;
-	DevBuf<unsigned long long> d_ticket, d_lookback;
-	DevBuf<int> d_error;
-	ABW_CUDA(ctx, d_ticket.alloc(1));
-	ABW_CUDA(ctx, d_error.alloc(1));
-	ABW_CUDA(ctx, cudaMemsetAsync(d_error.p, 0, sizeof(int), ctx->stream));
-	DevBuf<uint8_t> d_tab;
-	DevBuf<uint2> d_klohi;
-	DevBuf<uint64_t> d_suffix, d_never, d_union;
-	uint8_t *d_side = nullptr, *d_new_assigned = nullptr;      // slices of s->xchg, set at every level that has a best separation
-	ChildStats* d_stats = nullptr;
-	unsigned long long* d_value_key = nullptr;
-	uint64_t* d_child_never = nullptr;
-	DevBuf<SplitJob> d_jobs, d_jobs_mine;
-	DevBuf<PartJob> d_pjobs;
+	// ---- buffers of the run
+	DevBuf<LevelCtl> d_ctl;
+	DevBuf<LevelCluster> d_cl[2];
+	DevBuf<CandRec> d_cand, d_best, d_best_all;
+	DevBuf<SplitJob> d_jobs;
+	DevBuf<uint32_t> d_jobs_mine, d_job_of, d_status;
+	DevBuf<abw_best> d_bestrec;
+	DevBuf<uint2> d_cl_tab, d_ss_tab, d_tile_tab, d_fp_tab, d_part_tab, d_tm_tab, d_klohi;
+	DevBuf<PartJob> d_part_jobs;
 	DevBuf<TermJob> d_tjobs;
 	DevBuf<TermStats> d_tstats;
-	DevBuf<double> d_moments;
-	if(s->strategy == ABW_SENS_SPEC)
-		ABW_CUDA(ctx, d_suffix.alloc((size_t)D * std::max<uint32_t>(s->K, 1) * W));
+	DevBuf<uint64_t> d_tunion, d_suffix;
+	DevBuf<abw_cluster_rec> d_recs;
+	DevBuf<AggSlot> d_aggs, d_prefixes;
+	DevBuf<unsigned long long> d_lookback;
+	DevBuf<uint8_t> d_tab;
+	ABW_CUDA(ctx, d_ctl.alloc(1));
+	for(int b = 0; b < 2; b++)
+		ABW_CUDA(ctx, d_cl[b].alloc(Cmax));
+	ABW_CUDA(ctx, d_cand.alloc(items_max));
+	ABW_CUDA(ctx, d_best.alloc(Cmax));
+	if(world > 1)
+		ABW_CUDA(ctx, d_best_all.alloc((size_t)Cmax * world));
+	ABW_CUDA(ctx, d_jobs.alloc(Cmax));
+	ABW_CUDA(ctx, d_jobs_mine.alloc(Cmax));
+	ABW_CUDA(ctx, d_job_of.alloc(Cmax));
+	ABW_CUDA(ctx, d_bestrec.alloc(Cmax));
+	ABW_CUDA(ctx, d_cl_tab.alloc(N / CL_CHUNK + Cmax + 1));
+	ABW_CUDA(ctx, d_ss_tab.alloc(S / SS_CHUNK + Cmax + 1));
+	ABW_CUDA(ctx, d_tile_tab.alloc(TTmax));
+	ABW_CUDA(ctx, d_fp_tab.alloc(ss? FPTmax : 1));
+	ABW_CUDA(ctx, d_part_tab.alloc(part_tab_max));
+	ABW_CUDA(ctx, d_tm_tab.alloc(S / TM_CHUNK + Cmax + 1));
+	ABW_CUDA(ctx, d_part_jobs.alloc((size_t)4 * Pmax));
+	ABW_CUDA(ctx, d_tjobs.alloc(Cmax));
+	ABW_CUDA(ctx, d_tstats.alloc(Cmax));
+	ABW_CUDA(ctx, d_tunion.alloc((size_t)Cmax * W));
+	const uint32_t rec_cap = h_recs? cap : 0;
+	ABW_CUDA(ctx, d_recs.alloc(std::max<uint32_t>(rec_cap, 1)));
+	ABW_CUDA(ctx, d_lookback.alloc(lb_words));
+	ABW_CUDA(ctx, cudaMemsetAsync(d_lookback.p, 0, sizeof(unsigned long long) * lb_words, ctx->stream));
+	const uint64_t st_items = ss? fp_items_max : items_max;            // status / aggregate slots: flip-prefix tiles (sens/spec) or sweep tiles (split-scafs)
+	ABW_CUDA(ctx, d_status.alloc(std::max<uint64_t>(st_items, 1)));
+	ABW_CUDA(ctx, d_aggs.alloc(std::max<uint64_t>(st_items, 1)));
+	ABW_CUDA(ctx, d_prefixes.alloc(std::max<uint64_t>(st_items, 1)));
+	ABW_CUDA(ctx, cudaMemsetAsync(d_status.p, 0, sizeof(uint32_t) * std::max<uint64_t>(st_items, 1), ctx->stream));
+	if(ss) {
+		ABW_CUDA(ctx, d_tab.alloc((size_t)D * tab_total_max));
+		ABW_CUDA(ctx, d_klohi.alloc((size_t)D * Cmax));
+		ABW_CUDA(ctx, d_suffix.alloc((size_t)D * std::max<uint32_t>(K, 1) * W));
+	}
+	// what the owner of a winning dimension produces for everybody, in one buffer so that a sharded search needs one sum per level:
+	//   side bytes | assignment bytes | child statistics [J][2] | separating-value keys [J] | masks of scaffolds that can never flip [J][2][W]
+	const size_t s8 = ((size_t)S + 7) / 8, stat_words = sizeof(ChildStats) / 8;
+	auto xwords_for = [&](uint64_t Jb) { return 2 * s8 + (size_t)Jb * (2 * stat_words + 1 + 2 * W); };
+	if(s->xchg.n < xwords_for(Cmax))
+		ABW_CUDA(ctx, s->xchg.alloc(xwords_for(Cmax)));
+	ABW_CUDA(ctx, cudaMemsetAsync(s->xchg.p, 0, sizeof(unsigned long long) * xwords_for(Cmax), ctx->stream));
+	uint8_t* const d_side = reinterpret_cast<uint8_t*>(s->xchg.p);
+	uint8_t* const d_new_assigned = d_side + 8 * s8;
 
-	auto emit = [&](const abw_cluster_rec& r) {
-		if(nrec < cap && h_recs)
-			h_recs[nrec] = r;
-		nrec++;
-	};
+	// progress words in mapped pinned memory (one block per context)
+	if(!ctx->h_prog) {
+		ABW_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_prog, 256, cudaHostAllocMapped));
+	}
+	LevelProgress* const h_prog = reinterpret_cast<LevelProgress*>(ctx->h_prog);
+	h_prog->levels_done = 0; h_prog->done = 0; h_prog->nrec = 0; h_prog->error = 0;
 
-	while(!level.empty()) {
-		abw_stage_flip(ctx);                              // uploads of this level use the other half of the pinned staging area
-		s->prof.levels++;
-		const bool last_level = s->max_levels > 0 && s->prof.levels >= s->max_levels;
-		const uint32_t C = (uint32_t)level.size();
-		// pass-table offsets
-		uint32_t tab_total = 0;
-		std::vector<ClusterDesc> descs(C);
-		std::vector<uint64_t> never((size_t)C * W, 0);
-		for(uint32_t c = 0; c < C; c++) {
-			level[c].desc.tabOff = tab_total;
-			tab_total += level[c].desc.K + 1;
-			descs[c] = level[c].desc;
-			for(uint32_t w = 0; w < W; w++)
-				never[(size_t)c * W + w] = level[c].never.empty()? 0 : level[c].never[w];
+	// ---- root cluster and control block
+	{
+		LevelCluster root;
+		memset(&root, 0, sizeof(root));
+		root.id = 1;
+		root.parent = 0;
+		root.d.off = 0;
+		root.d.n = (uint32_t)N;
+		root.d.kOff = 0; root.d.K = K; root.d.tabOff = 0;
+		root.d.sOff = 0; root.d.ns = S;
+		root.d.totT = (uint32_t)s->root_totT;
+		root.d.U = S;
+		root.d.totLen = s->root_totLen;
+		root.d.ss_ok = (s->root_viol == 0);
+		root.d.tile0 = 0;
+		root.d.fOff = 0; root.d.nf = (uint32_t)Sf;
+		root.nassigned = S;
+		for(uint32_t w = 0; w < W && w < s->root_never.size(); w++)
+			root.never[w] = s->root_never[w];
+		LevelCtl c0;
+		memset(&c0, 0, sizeof(c0));
+		c0.C = 1;
+		c0.TT = abw_div_up(N, SW_TILE);
+		c0.FPT = (ss && Sf > 0)? abw_div_up(Sf, FP_TILE) : 0;
+		c0.tab_total = K + 1;
+		c0.next_id = 2;
+		std::vector<uint2> tt(c0.TT), ft(std::max<uint32_t>(c0.FPT, 1));
+		for(uint32_t t = 0; t < c0.TT; t++) tt[t] = make_uint2(0, t);
+		for(uint32_t t = 0; t < c0.FPT; t++) ft[t] = make_uint2(0, t);
+		abw_stage_flip(ctx);
+		ABW_CUDA(ctx, abw_stage_upload(ctx, d_cl[0].p, &root, sizeof(root)));
+		ABW_CUDA(ctx, abw_stage_upload(ctx, d_ctl.p, &c0, sizeof(c0)));
+		ABW_CUDA(ctx, abw_stage_upload(ctx, d_tile_tab.p, tt.data(), sizeof(uint2) * c0.TT));
+		if(c0.FPT)
+			ABW_CUDA(ctx, abw_stage_upload(ctx, d_fp_tab.p, ft.data(), sizeof(uint2) * c0.FPT));
+	}
+	LevelBufs B;
+	memset(&B, 0, sizeof(B));
+	B.ctl = d_ctl.p;
+	ABW_CUDA(ctx, cudaHostGetDevicePointer((void**)&B.prog, ctx->h_prog, 0));
+	B.cl[0] = d_cl[0].p; B.cl[1] = d_cl[1].p;
+	B.best = d_best.p; B.best_all = d_best_all.p;
+	B.jobs = d_jobs.p; B.jobs_mine = d_jobs_mine.p; B.job_of = d_job_of.p; B.bestrec = d_bestrec.p;
+	B.cl_tab = d_cl_tab.p; B.ss_tab = d_ss_tab.p; B.tile_tab = d_tile_tab.p; B.fp_tab = d_fp_tab.p; B.part_tab = d_part_tab.p; B.tm_tab = d_tm_tab.p;
+	B.part_jobs = d_part_jobs.p; B.tjobs = d_tjobs.p; B.tstats = d_tstats.p; B.tunion = d_tunion.p;
+	B.recs = d_recs.p; B.rec_cap = rec_cap; B.Cmax = Cmax; B.Pmax = Pmax;
+	B.low = s->low.p;
+
+	// grids: CTAs walk the work items of a level, whatever their number turns out to be
+	const unsigned int sms = (unsigned int)ctx->sm_count;
+	const unsigned int g_sweep = (unsigned int)std::min<uint64_t>(items_max, (uint64_t)sms * 4), g_fp = (unsigned int)std::min<uint64_t>(std::max<uint64_t>(fp_items_max, 1), (uint64_t)sms * 4);
+	const unsigned int g_part = (unsigned int)std::min<uint64_t>(part_items_max, (uint64_t)sms * 3), g_small = sms * 4;
+
+	// levels the host may run ahead of the device.  A sharded search must make the same number of collective calls on every rank, so there every
+	// rank waits for the verdict of the level it has just enqueued (a poll of mapped memory, not a stream synchronisation) before it enqueues the next.
+	const uint32_t lead = (world > 1)? 1u : 6u;
+	uint32_t lvl = 0;
+	bool finished = false;
+	int cur = 0;
+	const uint32_t max_levels = s->max_levels;
+	while(!finished) {
+		if(max_levels > 0 && lvl >= max_levels)
+			break;
+		const bool last_level = max_levels > 0 && lvl + 1 >= max_levels;
+		const uint32_t ep_sweep = 2 * lvl + 1, ep_part = 2 * lvl + 2;
+		if(lvl > 0 && lvl % 16 == 0) {
+			// the packed look-back words hold 6 bits of the epoch: clear them before an epoch can repeat
+			ABW_CUDA(ctx, cudaMemsetAsync(d_lookback.p, 0, sizeof(unsigned long long) * lb_words, ctx->stream));
 		}
-		ABW_CHECK(to_device(ctx, d_never, never));
-		// work items of the level: (dimension, tile-table entry); the table lists the tiles of every cluster
-		std::vector<uint2> tile_tab;
-		for(uint32_t c = 0; c < C; c++) {
-			descs[c].tile0 = (uint32_t)tile_tab.size();
-			const uint32_t tiles = (level[c].desc.n + SW_TILE - 1) / SW_TILE;
-			for(uint32_t t = 0; t < tiles; t++)
-				tile_tab.push_back(make_uint2(c, t));
-		}
-		const uint32_t TT = (uint32_t)tile_tab.size();
-		const uint64_t items = (uint64_t)TT * D;
-		if(items >= (1ull << 31))
-			return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_run: more than 2^31 tiles in one level");
-		ABW_CHECK(to_device(ctx, d_tile_tab, tile_tab));
-		ABW_CHECK(to_device(ctx, d_clusters, descs));
-		if(d_cand.n < items) ABW_CUDA(ctx, d_cand.alloc(items));
-		if(s->strategy == ABW_SENS_SPEC) {
-			if(d_lookback.n < items) ABW_CUDA(ctx, d_lookback.alloc(items));
-		}
-		else {
-			if(d_status.n < items) ABW_CUDA(ctx, d_status.alloc(items));
-			if(d_aggs.n < items) ABW_CUDA(ctx, d_aggs.alloc(items));
-			if(d_prefixes.n < items) ABW_CUDA(ctx, d_prefixes.alloc(items));
-		}
-		if(d_best.n < C)
-			ABW_CUDA(ctx, d_best.alloc(C));
-		const uint64_t tab_stride = tab_total;
-		if(s->strategy == ABW_SENS_SPEC) {
-			if(d_tab.n < (size_t)D * tab_stride)
-				ABW_CUDA(ctx, d_tab.alloc((size_t)D * tab_stride));
-			tm.start();
-			if(d_klohi.n < (size_t)D * C)
-				ABW_CUDA(ctx, d_klohi.alloc((size_t)D * C));
-			ABW_LAUNCH(ctx, k_pass_table, dim3(C, D), PT_WARPS * 32, 0, s->scg_list[cur].p, (uint64_t)s->K, d_clusters.p, s->scgmask.p, W, d_never.p,
-			           prm.scg_overlap_threshold, d_suffix.p, d_tab.p, tab_stride, D, d_klohi.p, (unsigned long long)prm.scg_min_size);
+		// at level l there are at most 2^l clusters: the host-known bound for the collectives of a sharded search
+		const uint32_t Cb = (uint32_t)std::min<uint64_t>(Cmax, (lvl < 31)? (1ull << lvl) : Cmax);
+		ChildStats* const d_stats = reinterpret_cast<ChildStats*>(s->xchg.p + 2 * s8);
+		unsigned long long* const d_value_key = s->xchg.p + 2 * s8 + (size_t)Cb * 2 * stat_words;
+		uint64_t* const d_child_never = reinterpret_cast<uint64_t*>(d_value_key + Cb);
+		const size_t xwords = xwords_for(Cb);
+		if(world > 1)          // bytes of earlier levels would otherwise be summed again; without ranks to sum over, every byte that is read was written in this level
+			ABW_CUDA(ctx, cudaMemsetAsync(s->xchg.p, 0, sizeof(unsigned long long) * 2 * s8, ctx->stream));
+		tm.start();
+		if(ss) {
+			ABW_LAUNCH(ctx, k_pass_table, g_small, PT_WARPS * 32, 0, s->scg_list[cur].p, (uint64_t)K, d_cl[cur].p, d_ctl.p, s->scgmask.p, W, prm.scg_overlap_threshold,
+			           d_suffix.p, d_tab.p, D, d_klohi.p, Cmax, (unsigned long long)prm.scg_min_size);
 			s->prof.other_ms += tm.stop();
-		}
-		// sweep
-		tm.start();
-		ABW_CUDA(ctx, cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned long long), ctx->stream));
-		if(s->strategy == ABW_SENS_SPEC) {
-			ABW_CUDA(ctx, cudaMemsetAsync(d_lookback.p, 0, sizeof(unsigned long long) * items, ctx->stream));
-			if(s->Sf > 0) {
-				std::vector<uint2> fp_tab;
-				for(uint32_t c = 0; c < C; c++) {
-					const uint32_t tiles = (level[c].desc.nf + FP_TILE - 1) / FP_TILE;
-					for(uint32_t t = 0; t < tiles; t++)
-						fp_tab.push_back(make_uint2(c, t));
-				}
-				const uint32_t FPT = (uint32_t)fp_tab.size();
-				const uint64_t fp_items = (uint64_t)FPT * D;
-				if(fp_items > 0) {
-					ABW_CHECK(to_device(ctx, d_fp_tab, fp_tab));
-					if(d_status.n < fp_items) ABW_CUDA(ctx, d_status.alloc(fp_items));
-					if(d_aggs.n < fp_items) ABW_CUDA(ctx, d_aggs.alloc(fp_items));
-					if(d_prefixes.n < fp_items) ABW_CUDA(ctx, d_prefixes.alloc(fp_items));
-					ABW_CUDA(ctx, cudaMemsetAsync(d_status.p, 0, sizeof(uint32_t) * fp_items, ctx->stream));
-					ABW_LAUNCH(ctx, k_flip_prefix, (unsigned int)fp_items, SW_THREADS, 0, s->flip_list[cur].p, s->Sf, d_clusters.p, FPT, d_fp_tab.p, s->rows.p, s->has_scg.p,
-					           d_ticket.p, d_status.p, d_aggs.p, d_prefixes.p, s->F8.p, s->FC.p, s->scg_k.p, (uint64_t)s->K, d_klohi.p, C,
-					           (unsigned long long)prm.scg_min_size, d_error.p);
-					ABW_CUDA(ctx, cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned long long), ctx->stream));
-				}
-			}
-			ABW_LAUNCH(ctx, k_sweep_ss, (unsigned int)items, SW_THREADS, 0, s->E[cur].p, N, d_clusters.p, TT, d_tile_tab.p, s->F8.p, s->FC.p, s->scg_k.p, (uint64_t)s->K,
-			           d_klohi.p, C, s->Sf, d_tab.p, tab_stride, sp,
-			           d_ticket.p, d_lookback.p, d_cand.p, d_error.p);
-		}
-		else {
-			ABW_CUDA(ctx, cudaMemsetAsync(d_status.p, 0, sizeof(uint32_t) * items, ctx->stream));
-			ABW_LAUNCH(ctx, k_sweep<ABW_SPLIT_SCAFS>, (unsigned int)items, SW_THREADS, 0, s->E[cur].p, N, d_clusters.p, TT, d_tile_tab.p, s->rows.p, (const uint8_t*)nullptr,
-			           tab_stride, sp, d_ticket.p, d_status.p, d_aggs.p, d_prefixes.p, d_cand.p, d_error.p);
-		}
-		s->prof.sweep_ms += tm.stop();
-		s->prof.sweep_launches++;
-		for(uint32_t c = 0; c < C; c++)
-			s->prof.sweep_elements += (uint64_t)level[c].desc.n * D;
-		tm.start();
-		if(s->strategy == ABW_SENS_SPEC)
-			ABW_LAUNCH(ctx, k_reduce_best<ABW_SENS_SPEC>, C, 256, 0, d_cand.p, TT, D, d_clusters.p, d_best.p);
-		else
-			ABW_LAUNCH(ctx, k_reduce_best<ABW_SPLIT_SCAFS>, C, 256, 0, d_cand.p, TT, D, d_clusters.p, d_best.p);
-		std::vector<CandRec> best(C);
-		ABW_CUDA(ctx, abw_fetch(ctx, best.data(), d_best.p, sizeof(CandRec) * C));
-		ABW_CUDA(ctx, abw_sync(ctx));
-		for(uint32_t c = 0; c < C; c++)
-			best[c].dim0 += s->dim_offset;               // global dimension index from here on
-		if(coll) {
-			// gather the per-shard best of every cluster and apply the same total order on every rank
-			ABW_CUDA(ctx, cudaMemcpyAsync(d_best.p, best.data(), sizeof(CandRec) * C, cudaMemcpyHostToDevice, ctx->stream));
-			if(d_best_all.n < (size_t)C * world) ABW_CUDA(ctx, d_best_all.alloc((size_t)C * world));
-			ABW_CUDA(ctx, abw_sync(ctx));
-			if(coll->allgather(coll->user, d_best.p, d_best_all.p, sizeof(CandRec) * C) != 0)
-				return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run_sharded: allgather callback failed");
-			std::vector<CandRec> all((size_t)C * world);
-			ABW_CUDA(ctx, abw_fetch(ctx, all.data(), d_best_all.p, sizeof(CandRec) * all.size()));
-			ABW_CUDA(ctx, abw_sync(ctx));
-			for(uint32_t c = 0; c < C; c++) {
-				CandRec b = all[c];
-				for(int r = 1; r < world; r++)
-					if(host_cand_better(s->strategy, all[(size_t)r * C + c], b))
-						b = all[(size_t)r * C + c];
-				best[c] = b;
-			}
-		}
-		// host: scores, legality (same IEEE operations as ClusterStats::get_sensitivity/get_specificity, .h:74-75)
-		std::vector<abw_best> hb(C);
-		std::vector<SplitJob> jobs;          // every cluster with a best separation: value recovery; legal ones: children
-		std::vector<uint32_t> job_of(C, UINT32_MAX);
-		for(uint32_t c = 0; c < C; c++) {
-			abw_best b;
-			memset(&b, 0, sizeof(b));
-			b.value = -1;
-			if(s->strategy == ABW_SPLIT_SCAFS) { b.a = 1000000; b.b = 1000000; }
-			if(best[c].found) {
-				b.found = 1;
-				b.dim = best[c].dim0 + 1;
-				if(s->strategy == ABW_SENS_SPEC) {
-					b.a = (double)(int)best[c].i0 / (double)(int)best[c].i1;
-					b.b = (double)(int)best[c].i0 / (double)(int)best[c].i2;
-				}
-				else {
-					b.a = best[c].k1;
-					b.b = best[c].k2;
-				}
-				b.legal = is_legal(prm, s->strategy, b);
-				SplitJob jb;
-				jb.cluster = c;
-				jb.dim0 = best[c].dim0;
-				jb.p = best[c].p;
-				jb.swapped = (level[c].desc.n - best[c].p) < best[c].p;      // ClusterSeparator.cpp:49
-				jb.slot = (uint32_t)jobs.size();
-				jb.pad = 0;
-				job_of[c] = (uint32_t)jobs.size();
-				jobs.push_back(jb);
-			}
-			hb[c] = b;
-		}
-		const uint32_t J = (uint32_t)jobs.size();
-		std::vector<ChildStats> stats((size_t)J * 2);
-		std::vector<unsigned long long> vkeys(J, 0);
-		std::vector<uint64_t> child_never((size_t)J * 2 * W, 0);
-		if(J > 0) {
-			// jobs whose winning dimension lives on this rank (all of them when the search is not sharded), with local dimension indices
-			std::vector<SplitJob> mine;
-			for(const SplitJob& jb : jobs)
-				if(owner_of(jb.dim0) == my_rank) {
-					SplitJob l = jb;
-					l.dim0 = jb.dim0 - s->dim_offset;
-					mine.push_back(l);
-				}
-			const uint32_t JM = (uint32_t)mine.size();
-			ABW_CHECK(to_device(ctx, d_jobs, jobs));
-			ABW_CHECK(to_device(ctx, d_jobs_mine, mine));
-			// Everything the owner of a winning dimension produces for the others lives in ONE buffer, so that a sharded search needs one sum per
-			// level: side bytes | assignment bytes | child statistics | separating-value keys | masks of scaffolds that can never flip
-			const size_t s8 = ((size_t)S + 7) / 8, stat_words = sizeof(ChildStats) / 8;
-			const size_t xwords = 2 * s8 + (size_t)J * (2 * stat_words + 1 + 2 * W);
-			if(s->xchg.n < xwords) ABW_CUDA(ctx, s->xchg.alloc(xwords + xwords / 2));
-			d_side = reinterpret_cast<uint8_t*>(s->xchg.p);
-			d_new_assigned = d_side + 8 * s8;
-			d_stats = reinterpret_cast<ChildStats*>(s->xchg.p + 2 * s8);
-			d_value_key = s->xchg.p + 2 * s8 + (size_t)J * 2 * stat_words;
-			d_child_never = reinterpret_cast<uint64_t*>(d_value_key + J);
-			// whole buffer: stale bytes of earlier levels would otherwise be summed again and carry into their neighbours
-			ABW_CUDA(ctx, cudaMemsetAsync(s->xchg.p, 0, sizeof(unsigned long long) * xwords, ctx->stream));
-			if(JM > 0) {
-				dim3 g1(std::min<uint32_t>(abw_div_up(N, 256), 4u * ctx->sm_count), JM);
-				dim3 g3(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), JM);
-				ABW_LAUNCH(ctx, k_count_low, g1, 256, 0, s->E[cur].p, N, d_clusters.p, d_jobs_mine.p, s->low.p);
-				ABW_LAUNCH(ctx, k_scaf_sides, g3, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs_mine.p, s->rows.p, s->low.p, s->dp_first.p, s->values.p, N, s->scgmask.p, W,
-				           s->strategy, prm.fraction_dps_in, d_side, d_new_assigned, d_stats, d_child_never, d_value_key);
-				ABW_LAUNCH(ctx, k_clear_low, g3, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs_mine.p, s->low.p);
-			}
-			if(coll) {
-				// every quantity is non-zero on exactly one rank (the owner of the winning dimension): a sum is a gather
-				ABW_CUDA(ctx, abw_sync(ctx));
-				if(coll->allreduce_sum_i64(coll->user, s->xchg.p, xwords) != 0)
-					return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run_sharded: allreduce callback failed");
-			}
-			ABW_CUDA(ctx, abw_fetch(ctx, stats.data(), d_stats, sizeof(ChildStats) * J * 2));
-			ABW_CUDA(ctx, abw_fetch(ctx, vkeys.data(), d_value_key, sizeof(unsigned long long) * J));
-			ABW_CUDA(ctx, abw_fetch(ctx, child_never.data(), d_child_never, sizeof(uint64_t) * J * 2 * W));
-			ABW_CUDA(ctx, abw_sync(ctx));
-		}
-		// decide
-		std::vector<HostCluster> next;
-		std::vector<PartJob> pjobs, fjobs, sjobs, kjobs;
-		std::vector<SplitJob> commit_jobs;
-		std::vector<TermJob> tjobs;
-		std::vector<abw_cluster_rec> recs(C);
-		for(uint32_t c = 0; c < C; c++) {
-			abw_cluster_rec r;
-			memset(&r, 0, sizeof(r));
-			r.id = level[c].id;
-			r.parent = level[c].parent;
-			r.ndps = level[c].desc.n;
-			r.nscafs = level[c].nassigned;
-			r.best = hb[c];
-			bool split = false;
-			if(hb[c].found) {
-				const uint32_t j = job_of[c];
-				unsigned long long k = vkeys[j];
-				unsigned long long bits = (k >> 63)? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
-				double v;
-				memcpy(&v, &bits, sizeof(v));
-				r.best.value = v;
-				if(hb[c].legal) {
-					const ChildStats& s1 = stats[(size_t)j * 2], &s2 = stats[(size_t)j * 2 + 1];
-					split = !(s1.ndps < prm.cluster_ndps_threshold || s2.ndps < prm.cluster_ndps_threshold);   // ClusterSeparator.cpp:125
-					if(split) {
-						r.split = 1;
-						r.child1 = next_id++;
-						r.child2 = next_id++;
-						r.child1_ndps = s1.ndps; r.child2_ndps = s2.ndps;
-						r.child1_nscafs = s1.nassigned; r.child2_nscafs = s2.nassigned;
-						r.child1_raw = jobs[j].swapped? level[c].desc.n - jobs[j].p : jobs[j].p;
-						r.child2_raw = level[c].desc.n - r.child1_raw;
-						const ChildStats* st[2] = {&s1, &s2};
-						uint64_t off = level[c].desc.off;
-						uint32_t kOff = level[c].desc.kOff, sOff = level[c].desc.sOff, fOff = level[c].desc.fOff;
-						for(int ch = 0; ch < 2; ch++) {
-							HostCluster hc;
-							hc.id = ch? r.child2 : r.child1;
-							hc.parent = r.id;
-							hc.desc.off = off;
-							hc.desc.n = (uint32_t)st[ch]->ndps;
-							hc.desc.kOff = kOff;
-							hc.desc.K = st[ch]->K;
-							hc.desc.sOff = sOff;
-							hc.desc.ns = st[ch]->ns;
-							hc.desc.totT = st[ch]->totT;
-							hc.desc.U = st[ch]->ns;
-							hc.desc.totLen = st[ch]->totLen;
-							hc.desc.ss_ok = (st[ch]->viol == 0);
-							hc.desc.fOff = fOff;
-							hc.desc.nf = st[ch]->nflip;
-							hc.nassigned = st[ch]->nassigned;
-							hc.never.assign(child_never.begin() + ((size_t)j * 2 + ch) * W, child_never.begin() + ((size_t)j * 2 + ch + 1) * W);
-							off += st[ch]->ndps;
-							kOff += st[ch]->K;
-							sOff += st[ch]->ns;
-							fOff += st[ch]->nflip;
-							next.push_back(hc);
-						}
-						PartJob pj;
-						pj.off = level[c].desc.off; pj.n = level[c].desc.n; pj.n1 = (uint32_t)s1.ndps;
-						pjobs.push_back(pj);
-						PartJob l1; l1.off = level[c].desc.sOff; l1.n = level[c].desc.ns; l1.n1 = s1.ns;
-						sjobs.push_back(l1);
-						PartJob l2; l2.off = level[c].desc.kOff; l2.n = level[c].desc.K; l2.n1 = s1.K;
-						kjobs.push_back(l2);
-						PartJob fj;
-						fj.off = level[c].desc.fOff; fj.n = level[c].desc.nf; fj.n1 = s1.nflip;
-						fjobs.push_back(fj);
-						commit_jobs.push_back(jobs[j]);
-					}
-					else {
-						// children too small: best_separation->reset() (ClusterSeparator.cpp:125-132)
-						memset(&r.best, 0, sizeof(r.best));
-						r.best.value = -1;
-						if(s->strategy == ABW_SPLIT_SCAFS) { r.best.a = 1000000; r.best.b = 1000000; }
-					}
-				}
-			}
-			if(!split) {
-				TermJob tj;
-				tj.sOff = level[c].desc.sOff; tj.ns = level[c].desc.ns; tj.id = level[c].id; tj.slot = (uint32_t)tjobs.size();
-				tjobs.push_back(tj);
-			}
-			recs[c] = r;
-		}
-		s->prof.other_ms += tm.stop();   // includes the host decisions; kernels here are small
-		// terminal clusters
-		tm.start();
-		if(!tjobs.empty()) {
-			const uint32_t Tn = (uint32_t)tjobs.size();
-			ABW_CHECK(to_device(ctx, d_tjobs, tjobs));
-			if(d_tstats.n < Tn) ABW_CUDA(ctx, d_tstats.alloc(Tn));
-			if(d_union.n < (size_t)Tn * W) ABW_CUDA(ctx, d_union.alloc((size_t)Tn * W));
-			ABW_CUDA(ctx, cudaMemsetAsync(d_tstats.p, 0, sizeof(TermStats) * Tn, ctx->stream));
-			ABW_CUDA(ctx, cudaMemsetAsync(d_union.p, 0, sizeof(uint64_t) * Tn * W, ctx->stream));
-			dim3 g(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), Tn);
-			ABW_LAUNCH(ctx, k_finalize_terminal, g, 128, 0, s->scaf_list[cur].p, d_tjobs.p, s->rows.p, s->assigned.p, s->scgmask.p, W, s->scaf_member.p, s->scaf_final.p,
-			           d_tstats.p, d_union.p);
-			std::vector<TermStats> ts(Tn);
-			std::vector<uint64_t> un((size_t)Tn * W);
-			std::vector<double> mom((size_t)Tn * 4, -1.0);
-			if(s->x_gc.p != nullptr) {
-				if(d_moments.n < (size_t)Tn * 4) ABW_CUDA(ctx, d_moments.alloc((size_t)Tn * 4));
-				ABW_LAUNCH(ctx, k_terminal_moments, abw_div_up(2 * Tn, 64), 64, 0, s->scaf_list[cur].p, d_tjobs.p, Tn, s->rows.p, s->assigned.p, s->x_gc.p, s->x_cvg.p, d_moments.p);
-				ABW_CUDA(ctx, abw_fetch(ctx, mom.data(), d_moments.p, sizeof(double) * Tn * 4));
-			}
-			ABW_CUDA(ctx, abw_fetch(ctx, ts.data(), d_tstats.p, sizeof(TermStats) * Tn));
-			ABW_CUDA(ctx, abw_fetch(ctx, un.data(), d_union.p, sizeof(uint64_t) * Tn * W));
-			ABW_CUDA(ctx, abw_sync(ctx));
-			uint32_t t = 0;
-			for(uint32_t c = 0; c < C; c++) {
-				if(recs[c].split)
-					continue;
-				uint32_t u = 0;
-				for(uint32_t w = 0; w < W; w++)
-					u += (uint32_t)__builtin_popcountll(un[(size_t)t * W + w]);
-				recs[c].total_size = ts[t].total_size;
-				recs[c].scg_unique = u;
-				recs[c].scg_avg = (ts[t].scg_copies == 0)? 0 : (double)ts[t].scg_copies / (double)u;   // SCGdb.cpp:54
-				recs[c].gc_avg = mom[(size_t)t * 4]; recs[c].gc_sd = mom[(size_t)t * 4 + 1];
-				recs[c].cvg_avg = mom[(size_t)t * 4 + 2]; recs[c].cvg_sd = mom[(size_t)t * 4 + 3];
-				t++;
-			}
-		}
-		for(uint32_t c = 0; c < C; c++)
-			emit(recs[c]);
-		s->prof.other_ms += tm.stop();
-		// partition the split clusters: elements, flip lists, SCG lists and the scaffold list all go through the same kernel
-		if(!pjobs.empty()) {
-			const uint32_t P = (uint32_t)pjobs.size();
-			ABW_CHECK(to_device(ctx, d_jobs, commit_jobs));
 			tm.start();
-			{
-				dim3 g(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), P);
-				ABW_LAUNCH(ctx, k_commit_assigned, g, 128, 0, s->scaf_list[cur].p, d_clusters.p, d_jobs.p, d_new_assigned, s->assigned.p);
-			}
-			// which arrays take part, in one plan so that the look-back words and tickets are cleared with a single memset
-			struct PartPlan { const uint32_t* in; uint32_t* out; uint64_t stride; uint32_t ndims; const std::vector<PartJob>* jv; uint32_t TT; uint64_t items, lb_off, tab_off, job_off; };
-			std::vector<PartPlan> plans;
-			plans.push_back({s->scaf_list[cur].p, s->scaf_list[cur ^ 1].p, (uint64_t)S, 1u, &sjobs, 0, 0, 0, 0, 0});
-			if(!last_level) {
-				plans.push_back({s->E[cur].p, s->E[cur ^ 1].p, N, D, &pjobs, 0, 0, 0, 0, 0});
-				if(s->strategy == ABW_SENS_SPEC && s->Sf > 0)
-					plans.push_back({s->flip_list[cur].p, s->flip_list[cur ^ 1].p, s->Sf, D, &fjobs, 0, 0, 0, 0, 0});
-				if(s->strategy == ABW_SENS_SPEC && s->K > 0)
-					plans.push_back({s->scg_list[cur].p, s->scg_list[cur ^ 1].p, (uint64_t)s->K, D, &kjobs, 0, 0, 0, 0, 0});
-			}
-			std::vector<uint2> all_tab;
-			std::vector<PartJob> all_jobs;
-			uint64_t lb_total = 8;                              // words 0..7: tickets
-			for(PartPlan& pl : plans) {
-				pl.tab_off = all_tab.size();
-				pl.job_off = all_jobs.size();
-				for(uint32_t i = 0; i < P; i++) {
-					all_jobs.push_back((*pl.jv)[i]);
-					const uint32_t tiles = ((*pl.jv)[i].n + SW_TILE - 1) / SW_TILE;
-					for(uint32_t t = 0; t < tiles; t++)
-						all_tab.push_back(make_uint2(i, t));
-				}
-				pl.TT = (uint32_t)(all_tab.size() - pl.tab_off);
-				pl.items = (uint64_t)pl.TT * pl.ndims;
-				pl.lb_off = lb_total;
-				lb_total += pl.items;
-				if(pl.items >= (1ull << 31))
-					return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_run: more than 2^31 tiles in one level");
-			}
-			ABW_CHECK(to_device(ctx, d_ptile_tab, all_tab));
-			ABW_CHECK(to_device(ctx, d_pjobs, all_jobs));
-			if(d_lookback.n < lb_total) ABW_CUDA(ctx, d_lookback.alloc(lb_total));
-			ABW_CUDA(ctx, cudaMemsetAsync(d_lookback.p, 0, sizeof(unsigned long long) * lb_total, ctx->stream));
-			for(size_t i = 0; i < plans.size(); i++) {
-				const PartPlan& pl = plans[i];
-				if(pl.items == 0)
-					continue;
-				ABW_LAUNCH(ctx, k_partition2, (unsigned int)pl.items, SW_THREADS, 0, pl.in, pl.out, pl.stride, d_pjobs.p + pl.job_off, pl.TT, d_ptile_tab.p + pl.tab_off, d_side,
-				           d_lookback.p + i, d_lookback.p + pl.lb_off, d_error.p);
-			}
-			s->prof.partition_ms += tm.stop();
-			if(!last_level)
-				for(uint32_t i = 0; i < P; i++)
-					s->prof.partition_elements += (uint64_t)pjobs[i].n * D;
-			cur ^= 1;
-			if(last_level) {
-				// the children are not going to be evaluated: only their scaffold lists are needed (for the bins)
-				level.swap(next);
+			if(Sf > 0)
+				ABW_LAUNCH(ctx, k_flip_prefix, g_fp, SW_THREADS, 0, s->flip_list[cur].p, Sf, d_cl[cur].p, D, d_ctl.p, d_fp_tab.p, s->rows.p, s->has_scg.p, ep_sweep, d_status.p,
+				           d_aggs.p, d_prefixes.p, s->F8.p, s->FC.p, s->scg_k.p, (uint64_t)K, d_klohi.p, Cmax, (unsigned long long)prm.scg_min_size);
+			ABW_LAUNCH(ctx, k_sweep_ss, g_sweep, SW_THREADS, 0, s->E[cur].p, N, d_cl[cur].p, D, d_ctl.p, d_tile_tab.p, s->F8.p, s->FC.p, s->scg_k.p, (uint64_t)K, d_klohi.p, Cmax,
+			           Sf, d_tab.p, sp, ep_sweep, d_lookback.p, d_cand.p);
+		}
+		else
+			ABW_LAUNCH(ctx, k_sweep<ABW_SPLIT_SCAFS>, g_sweep, SW_THREADS, 0, s->E[cur].p, N, d_cl[cur].p, D, d_ctl.p, d_tile_tab.p, s->rows.p, (const uint8_t*)nullptr, sp,
+			           ep_sweep, d_status.p, d_aggs.p, d_prefixes.p, d_cand.p);
+		s->prof.sweep_ms += tm.stop();
+		tm.start();
+		if(ss)
+			ABW_LAUNCH(ctx, k_reduce_best<ABW_SENS_SPEC>, g_small, 256, 0, d_cand.p, D, d_ctl.p, d_cl[cur].p, s->dim_offset, d_best.p);
+		else
+			ABW_LAUNCH(ctx, k_reduce_best<ABW_SPLIT_SCAFS>, g_small, 256, 0, d_cand.p, D, d_ctl.p, d_cl[cur].p, s->dim_offset, d_best.p);
+		if(world > 1) {
+			// the per-rank best of every cluster, gathered; k_level_jobs applies the same total order on every rank
+			if(!ordered)
+				ABW_CUDA(ctx, abw_sync(ctx));
+			if(coll->allgather(coll->user, d_best.p, d_best_all.p, sizeof(CandRec) * Cb) != 0)
+				return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run_sharded: allgather callback failed");
+		}
+		ABW_LAUNCH(ctx, k_level_jobs, 1, LV_THREADS, 0, B, cur, world, Cb, s->strategy, prm, s->dim_offset, D, s->E[cur].p, N, d_stats, d_value_key, d_child_never, W);
+		ABW_LAUNCH(ctx, k_count_low, g_small, 256, 0, s->E[cur].p, N, B, cur, s->dim_offset, s->low.p);
+		ABW_LAUNCH(ctx, k_scaf_sides, g_small * 2, SS_CHUNK, 0, s->scaf_list[cur].p, B, cur, s->dim_offset, s->rows.p, s->low.p, s->dp_first.p, s->values.p, N, s->scgmask.p, W,
+		           s->strategy, prm.fraction_dps_in, d_side, d_new_assigned, d_stats, d_child_never, d_value_key);
+		if(world > 1) {
+			// every quantity is non-zero on exactly one rank (the owner of the winning dimension): a sum is a gather
+			if(!ordered)
+				ABW_CUDA(ctx, abw_sync(ctx));
+			if(coll->allreduce_sum_i64(coll->user, s->xchg.p, xwords) != 0)
+				return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run_sharded: allreduce callback failed");
+		}
+		const uint32_t pd0 = 1, pd1 = last_level? 0u : D, pd2 = (!last_level && ss && Sf > 0)? D : 0u, pd3 = (!last_level && ss && K > 0)? D : 0u;
+		ABW_LAUNCH(ctx, k_level_decide, 1, LV_THREADS, 0, B, cur, s->strategy, prm, D, W, s->dim_offset, pd0, pd1, pd2, pd3, last_level? 0 : 1, d_stats, d_value_key,
+		           d_child_never);
+		ABW_LAUNCH(ctx, k_finalize_terminal, g_small, 128, 0, s->scaf_list[cur].p, B, s->rows.p, s->assigned.p, s->scgmask.p, W, s->scaf_member.p, s->scaf_final.p,
+		           (const double*)s->x_gc.p, (const double*)s->x_cvg.p);
+		s->prof.other_ms += tm.stop();
+		tm.start();
+		{
+			PartPlans pp;
+			pp.in[0] = s->scaf_list[cur].p; pp.out[0] = s->scaf_list[cur ^ 1].p; pp.stride[0] = S;
+			pp.in[1] = s->E[cur].p; pp.out[1] = s->E[cur ^ 1].p; pp.stride[1] = N;
+			pp.in[2] = s->flip_list[cur].p; pp.out[2] = s->flip_list[cur ^ 1].p; pp.stride[2] = Sf;
+			pp.in[3] = s->scg_list[cur].p; pp.out[3] = s->scg_list[cur ^ 1].p; pp.stride[3] = K;
+			ABW_LAUNCH(ctx, k_partition2, g_part, SW_THREADS, 0, pp, d_ctl.p, d_part_jobs.p, d_part_tab.p, d_side, d_new_assigned, s->assigned.p, ep_part, d_lookback.p);
+		}
+		s->prof.partition_ms += tm.stop();
+		cur ^= 1;
+		lvl++;
+		// progress: stop as soon as the device has reported the last level; never run more than `lead` levels ahead of it
+		while(true) {
+			const uint32_t ld = h_prog->levels_done;            // written after `done`: a level that is reported has its verdict visible
+			__sync_synchronize();
+			if(h_prog->error) {
+				finished = true;
 				break;
 			}
+			if(ld >= lvl) {                                     // the level just enqueued has been decided
+				finished = h_prog->done != 0;
+				break;
+			}
+			if(lead > 1 && h_prog->done) {                      // an earlier level was the last one: what was enqueued since is empty
+				finished = true;
+				break;
+			}
+			if(lvl - ld < lead)
+				break;
+			if(cudaStreamQuery(ctx->stream) == cudaSuccess) {
+				// the stream is idle although a level has not been reported: a kernel fault surfaces here
+				ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+				__sync_synchronize();
+				if(h_prog->levels_done < lvl && !h_prog->done)
+					return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run: internal error, the device stopped reporting levels");
+			}
 		}
-		level.swap(next);
-		if(last_level)
-			break;
 	}
-	if(!level.empty()) {
-		// level limit reached: the pending clusters are reported as bins (their ids) without being evaluated
-		std::vector<TermJob> tjobs;
-		for(const HostCluster& hc : level) {
-			TermJob tj;
-			tj.sOff = hc.desc.sOff; tj.ns = hc.desc.ns; tj.id = hc.id; tj.slot = (uint32_t)tjobs.size();
-			tjobs.push_back(tj);
-		}
-		const uint32_t Tn = (uint32_t)tjobs.size();
-		ABW_CHECK(to_device(ctx, d_tjobs, tjobs));
-		if(d_tstats.n < Tn) ABW_CUDA(ctx, d_tstats.alloc(Tn));
-		if(d_union.n < (size_t)Tn * W) ABW_CUDA(ctx, d_union.alloc((size_t)Tn * W));
-		ABW_CUDA(ctx, cudaMemsetAsync(d_tstats.p, 0, sizeof(TermStats) * Tn, ctx->stream));
-		ABW_CUDA(ctx, cudaMemsetAsync(d_union.p, 0, sizeof(uint64_t) * Tn * W, ctx->stream));
-		dim3 g(std::min<uint32_t>(abw_div_up(S, 128), 2u * ctx->sm_count), Tn);
-		ABW_LAUNCH(ctx, k_finalize_terminal, g, 128, 0, s->scaf_list[cur].p, d_tjobs.p, s->rows.p, s->assigned.p, s->scgmask.p, W, s->scaf_member.p, s->scaf_final.p,
-		           d_tstats.p, d_union.p);
+	ABW_CUDA(ctx, abw_sync(ctx));
+	LevelCtl h_ctl;
+	ABW_CUDA(ctx, abw_fetch(ctx, &h_ctl, d_ctl.p, sizeof(h_ctl)));
+	ABW_CUDA(ctx, abw_sync(ctx));
+	if(h_ctl.error == 2)
+		return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run: internal error, more clusters in a level than the bound");
+	if(h_ctl.error)
+		return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run: internal error, a look-back wait timed out");
+	if(!h_ctl.done && max_levels > 0 && h_ctl.level >= max_levels && h_ctl.P > 0) {
+		// level limit reached: the pending clusters (the children written by the last level) are reported as bins (their ids) without being evaluated
+		ABW_LAUNCH(ctx, k_pending_jobs, 1, LV_THREADS, 0, B, cur, 1u, W);
+		ABW_LAUNCH(ctx, k_finalize_terminal, g_small, 128, 0, s->scaf_list[cur].p, B, s->rows.p, s->assigned.p, s->scgmask.p, W, s->scaf_member.p, s->scaf_final.p,
+		           (const double*)nullptr, (const double*)nullptr);
 	}
+	s->prof.levels = h_ctl.level;
+	s->prof.sweep_launches = h_ctl.sweep_launches;
+	s->prof.sweep_elements = h_ctl.sweep_elements;
+	s->prof.partition_elements = h_ctl.partition_elements;
+	const uint32_t nrec = h_ctl.nrec;
 	if(nrecs)
 		*nrecs = nrec;
-	{
-		int h_error = 0;
-		ABW_CUDA(ctx, abw_fetch(ctx, &h_error, d_error.p, sizeof(int)));
-		ABW_CUDA(ctx, abw_sync(ctx));
-		if(h_error)
-			return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run: internal error, a look-back wait timed out");
-	}
+	if(h_recs && std::min(nrec, cap) > 0)
+		ABW_CUDA(ctx, abw_fetch(ctx, h_recs, d_recs.p, sizeof(abw_cluster_rec) * std::min(nrec, cap)));
 	if(h_scaf2cluster)
 		ABW_CUDA(ctx, abw_fetch(ctx, h_scaf2cluster, s->scaf_final.p, sizeof(uint32_t) * S));
 	if(h_dp2cluster) {
@@ -2651,32 +2888,22 @@ int abw_cluster_scg(abw_ctx* ctx, const abw_search* s, const uint32_t* h_scafs, 
 	if(!ctx || !s || (!h_scafs && nscafs))
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_cluster_scg: null argument");
 	ABW_ENTER(ctx);
-	// SCGdb::num_unique_scgs / average_num_copies_for_unique_scgs (SCGdb.cpp:6-18,41-55) through the same terminal-cluster kernel
+	// SCGdb::num_unique_scgs / average_num_copies_for_unique_scgs (SCGdb.cpp:6-18,41-55)
 	DevBuf<uint32_t> d_list;
-	DevBuf<TermJob> d_job;
 	DevBuf<TermStats> d_st;
 	DevBuf<uint64_t> d_un;
-	DevBuf<uint32_t> d_member, d_final;
-	DevBuf<uint8_t> d_assigned;
 	for(uint32_t i = 0; i < nscafs; i++)
 		if(h_scafs[i] >= s->S)
 			return abw_fail(ctx, ABW_ERR_ARG, "abw_cluster_scg: scaffold index out of range");
 	ABW_CUDA(ctx, d_list.alloc(nscafs));
-	ABW_CUDA(ctx, d_job.alloc(1));
 	ABW_CUDA(ctx, d_st.alloc(1));
 	ABW_CUDA(ctx, d_un.alloc(s->W));
-	ABW_CUDA(ctx, d_member.alloc(s->S));
-	ABW_CUDA(ctx, d_final.alloc(s->S));
-	ABW_CUDA(ctx, d_assigned.alloc(s->S));
-	TermJob tj; tj.sOff = 0; tj.ns = nscafs; tj.id = 1; tj.slot = 0;
 	if(nscafs)
 		ABW_CUDA(ctx, cudaMemcpyAsync(d_list.p, h_scafs, sizeof(uint32_t) * nscafs, cudaMemcpyHostToDevice, ctx->stream));
-	ABW_CUDA(ctx, cudaMemcpyAsync(d_job.p, &tj, sizeof(tj), cudaMemcpyHostToDevice, ctx->stream));
 	ABW_CUDA(ctx, cudaMemsetAsync(d_st.p, 0, sizeof(TermStats), ctx->stream));
 	ABW_CUDA(ctx, cudaMemsetAsync(d_un.p, 0, sizeof(uint64_t) * s->W, ctx->stream));
-	ABW_CUDA(ctx, cudaMemsetAsync(d_assigned.p, 1, s->S, ctx->stream));
 	if(nscafs)
-		ABW_LAUNCH(ctx, k_finalize_terminal, dim3(abw_div_up(nscafs, 128), 1), 128, 0, d_list.p, d_job.p, s->rows.p, d_assigned.p, s->scgmask.p, s->W, d_member.p, d_final.p, d_st.p, d_un.p);
+		ABW_LAUNCH(ctx, k_scg_tally, std::min<unsigned int>(abw_div_up(nscafs, 128), 1024u), 128, 0, d_list.p, nscafs, s->scgmask.p, s->W, d_st.p, d_un.p);
 	TermStats ts;
 	std::vector<uint64_t> un(s->W);
 	ABW_CUDA(ctx, abw_fetch(ctx, &ts, d_st.p, sizeof(ts)));

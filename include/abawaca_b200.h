@@ -272,6 +272,10 @@ typedef struct {
 	int (*allreduce_sum_i64)(void* user, void* d_buf, size_t count);                         /* in place, 64-bit integer sum */
 	void* user;
 	int rank, world;
+	/* non-zero: the operations are enqueued on the context stream (abw_ctx_stream) and complete in its order, so a whole search is enqueued without a
+	 * host wait (abw_nccl_collectives_create).  Zero: they are host synchronous -- the library waits for its stream before every call and the
+	 * operation has completed when the callback returns. */
+	int stream_ordered;
 } abw_collectives;
 int abw_search_set_shard(abw_search* s, uint32_t dim_offset, uint32_t D_total);
 int abw_search_run_sharded(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_cluster_rec* h_recs, uint32_t cap, uint32_t* nrecs,

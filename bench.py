@@ -7,12 +7,16 @@ One "step" = one pass of the hot path over one synthetic metagenome: pack -> win
 per-sample coverage -> split search down to the final bins.  At N=1 the workload is BASELINE.json configs[1]
 (50k scaffolds, 10 samples).  At N>1 the assembly has N x 50k scaffolds of ONE community (weak scaling): scaffolds are
 sharded across the ranks for the feature build (no exchange), one NCCL all-to-all hands every rank its block of columns of all rows, and the split
-search is sharded by dimension (abw_search_run_sharded: all-gather of per-cluster best records + one sum per level).
+search is sharded by dimension (abw_search_run_sharded: all-gather of per-cluster best records + one sum per level, enqueued on the device stream).
 
   value : whole-job scaffolds/s with the inputs (ASCII assembly, read records) already resident in HBM
-  e2e   : the same through the C ABI with HOST buffers: H2D of assembly + reads and D2H of the .lrn matrix and bins inside the timed region
-  roofline / kernels : per-kernel CUDA-event durations of one extra profiled step (abw_profile_enable), algorithmic bytes from DESIGN.md
-  cpu_baseline : the UNMODIFIED reference binaries (oracle/_ref, -O2 build) on a bounded sample of the same workload, on this box's cores
+  e2e   : the same through the C ABI with HOST buffers: H2D of assembly + compact read records and D2H of the .lrn matrix (integer thousandths),
+          the window table and the bins inside the timed region
+  roofline : algorithmic bytes of SURVEY.md section 8(d) over CUDA-event kernel time (one extra profiled step), for every kernel family the survey
+          gives bytes for; the primary figure is the dominant family -- the split search, ALL its kernels (abw_search_create + abw_search_run)
+  cpu_baseline : the UNMODIFIED reference binaries (oracle/_ref, -O2 build) on a bounded sample of the same workload, on this box's cores:
+          full command lines (text in, text out), compute only (Bio::VectorReader-fed feature stage + work list, no text parsing), and the
+          drop-in command lines of this repo on the same text files (e2e_cli)
 
 `--impl reference` times only that reference arm (rank 0; other ranks exit 0).
 """
@@ -101,7 +105,7 @@ def workload_args(args):
 
 def workload_name(w):
     base = "BASELINE.json configs[1]: 50k scaffolds, 10 samples, feature build + split search" if (w["n_scaffolds"], w["n_samples"]) == (50000, 10) \
-        else "reduced variant of configs[1]"
+        else "variant of configs[1]"
     return f"{base} ({w['n_scaffolds']} scaffolds, {w['n_samples']} samples, {w['n_genomes']} synthetic genomes, seed {w['seed']})"
 
 
@@ -132,57 +136,106 @@ def reference_sample(mg, per_genome=400, genomes=2):
     return synth.Metagenome(names, mg.genome[sel], offsets, seq, reads, mg.scg_names, g2s, mg.read_len, mg.seed)
 
 
-def run_reference_once(paths, workdir, ncpu):
-    ref = os.path.join(ROOT, "oracle", "_ref")
-    build = os.path.join(workdir, "build")
-    out = os.path.join(workdir, "out")
+def run_command_lines(bindir, paths, workdir, ncpu, tag):
+    """abawaca-build + abawaca of `bindir` on the text files of `paths`; returns (build seconds, bin seconds, bins, build directory)."""
+    build = os.path.join(workdir, "build_" + tag)
+    out = os.path.join(workdir, "out_" + tag)
     shutil.rmtree(build, ignore_errors=True)
     shutil.rmtree(out, ignore_errors=True)
     os.makedirs(build)
     t0 = time.perf_counter()
-    subprocess.run([os.path.join(ref, "abawaca-build"), "-f", paths["fasta"], "-o", build, "-s", os.path.join(workdir, "sample*.sam"), "-c", paths["sams"][0]],
+    subprocess.run([os.path.join(bindir, "abawaca-build"), "-f", paths["fasta"], "-o", build, "-s", os.path.join(workdir, "sample*.sam"), "-c", paths["sams"][0]],
                    check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     t1 = time.perf_counter()
     env = dict(os.environ, ABW_SCG_LIST=paths["scg_list"])
-    subprocess.run([os.path.join(ref, "abawaca"), "-u", build, "-o", out, "-c", paths["gene2scg"], "-p", str(ncpu)], check=True, env=env,
+    subprocess.run([os.path.join(bindir, "abawaca"), "-u", build, "-o", out, "-c", paths["gene2scg"], "-p", str(ncpu)], check=True, env=env,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     t2 = time.perf_counter()
     bins = [int(l.split("\t")[1]) for l in open(os.path.join(out, "scaf2cluster.txt"))]
-    return t1 - t0, t2 - t1, bins
+    return t1 - t0, t2 - t1, bins, build
 
 
-def reference_arm(mg, steps, warmup, want_bins=False, extra=None):
+def reference_compute_only(paths, build_dir, ncpu, workdir):
+    """The reference's compute without text parsing: feature stage fed from memory (Bio::VectorReader, oracle/ref_compute_harness.cpp) and the
+    work list alone (oracle/ref_search_harness.cpp prints its wall clock); both run the unmodified reference classes."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not (os.path.exists(os.path.join(ref, "ref_compute")) and os.path.exists(os.path.join(ref, "ref_search"))):
+        return None
+    r = subprocess.run([os.path.join(ref, "ref_compute"), paths["fasta"]] + paths["sams"], check=True, capture_output=True, text=True)
+    feat = json.loads(r.stdout.strip().splitlines()[-1])
+    pre = os.path.join(build_dir, "abawaca")
+    r = subprocess.run([os.path.join(ref, "ref_search"), pre + ".names", paths["fasta"], pre + ".info", pre + ".lrn", paths["gene2scg"], paths["scg_list"], "sensspec",
+                        str(ncpu), os.path.join(workdir, "ref_search_dump.tsv")], check=True, capture_output=True, text=True)
+    search_s = [float(l.split()[1]) for l in r.stderr.splitlines() if l.startswith("SEARCH_SECONDS")][-1]
+    total = feat["scaf_s"] + feat["reads_s"] + search_s
+    return {"windows_and_kmer_s": round(feat["scaf_s"], 3), "coverage_from_memory_s": round(feat["reads_s"], 3), "work_list_s": round(search_s, 3),
+            "scaffolds_per_s": round(feat["scaffolds"] / total, 2),
+            "what": "unmodified reference classes, no text parsing or writing: Scaf/Scaf_segment construction + add_mapped_read fed by Bio::VectorReader "
+                    f"(1 thread, as abawaca-build), ClusterSeparator work list with {ncpu} threads"}
+
+
+def reference_arm(mg, steps, warmup, per_genome, genomes, extra=None, with_compute_only=False, with_cli=False):
     ref = os.path.join(ROOT, "oracle", "_ref")
     if not os.path.exists(os.path.join(ref, "abawaca")):
         raise RuntimeError("oracle/_ref is not built (run __graft_entry__.build() where /root/reference is mounted)")
-    sample = reference_sample(mg)
+    sample = reference_sample(mg, per_genome, genomes)
     ncpu = max(1, min(40, os.cpu_count() or 1))       # abawaca -p is capped at 40 (abawaca.cpp:326-331)
     wd = tempfile.mkdtemp(prefix="abw_ref_")
+    info = {}
     try:
         paths = synth.write_reference_inputs(sample, wd)
-        tb, ts, bins = [], [], None
+        tb, ts, bins, build_dir = [], [], None, None
         for i in range(warmup + steps):
-            b, s, bins = run_reference_once(paths, wd, ncpu)
+            b, s, bins, build_dir = run_command_lines(ref, paths, wd, ncpu, "ref")
             if i >= warmup:
                 tb.append(b); ts.append(s)
+        if with_compute_only:
+            try:
+                info["compute_only"] = reference_compute_only(paths, build_dir, ncpu, wd)
+            except Exception as e:
+                info["compute_only"] = {"failed": repr(e)}
+        if with_cli:
+            # the drop-in command lines of this repo on the same text files: text in -> text out on both sides, CUDA start-up of two processes included
+            try:
+                mine = os.path.join(ROOT, "abawaca_b200", "bin")
+                run_command_lines(mine, paths, wd, ncpu, "b200w")          # first process start on this box pages the library in
+                b2, s2, bins2, _ = run_command_lines(mine, paths, wd, ncpu, "b200")
+                info["e2e_cli"] = {"what": "abawaca-build + abawaca, text files in -> text files out, same sample, same box", "scaffolds": sample.nscaf,
+                                   "reference_s": round(float(np.mean(tb) + np.mean(ts)), 3), "b200_s": round(b2 + s2, 3),
+                                   "b200_build_s": round(b2, 3), "b200_bin_s": round(s2, 3), "ratio": round(float(np.mean(tb) + np.mean(ts)) / (b2 + s2), 2),
+                                   "bins_identical": bool(bins2 == bins)}
+            except Exception as e:
+                info["e2e_cli"] = {"failed": repr(e)}
         extra_out = extra(paths, sample) if extra is not None else None
     finally:
         shutil.rmtree(wd, ignore_errors=True)
     t = float(np.mean(tb) + np.mean(ts))
-    info = dict(value=sample.nscaf / t, unit="scaffolds/s", cores=ncpu, kind="reference",
-                sample=f"{sample.nscaf} scaffolds (first 400 of each of 2 genomes) of the workload, {sum(r.size for r in sample.reads)} reads in {len(sample.reads)} SAM files; "
-                       f"unmodified reference built -O2; abawaca-build (single-threaded by construction) {np.mean(tb):.2f} s + abawaca -p {ncpu} {np.mean(ts):.2f} s",
+    info.update(value=sample.nscaf / t, unit="scaffolds/s", cores=ncpu, kind="reference",
+                sample=f"{sample.nscaf} scaffolds (first {per_genome} of each of {genomes} genomes) of the workload, {sum(r.size for r in sample.reads)} reads in "
+                       f"{len(sample.reads)} SAM files, {len(set(bins)) - (1 if 0 in bins else 0)} bins; unmodified reference built -O2; abawaca-build (single-threaded by construction) "
+                       f"{np.mean(tb):.2f} s + abawaca -p {ncpu} {np.mean(ts):.2f} s; the reference's cost per scaffold grows with the depth of the tree, "
+                       f"so a small sample flatters it",
                 build_s=float(np.mean(tb)), bin_s=float(np.mean(ts)))
     if extra_out is not None:
         info["_extra"] = extra_out
     return info, sample, bins
 
 
+def reference_sample_size(steps, warmup):
+    """Sample of the reference arm: sized so that steps + warmup runs end within a few minutes (about 115 scaffolds/s on this class of host)."""
+    budget = 240.0 / max(1, steps + warmup)             # seconds per run
+    if budget >= 24:
+        return 400, 8                                   # 3200 scaffolds, 7 splits: about 27 s per run
+    if budget >= 8:
+        return 300, 4                                   # 1200 scaffolds, 3 splits: about 8 s per run
+    return 400, 2                                       # 800 scaffolds, 1 split: about 4 s per run
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------------------------------------
 def gpu_bins_for(ctx, mg, pipeline, capi):
-    """One full pass from HOST buffers; returns (scaf2cluster over ALL scaffolds incl. dropped ones = 0, FeatureBuild kept open = None)."""
+    """One full pass from HOST buffers; returns (scaf2cluster over ALL scaffolds incl. dropped ones = 0, kept scaffolds)."""
     fb = pipeline.build_features(ctx, mg.seq, mg.offsets, mg.reads, this_sample=0)
     sg = fb.segments_host()
     keep, dp2scaf, T, kept = pipeline.search_problem_from_features(sg["seg_scaf"], mg.nscaf)
@@ -196,6 +249,12 @@ def gpu_bins_for(ctx, mg, pipeline, capi):
     return bins, kept
 
 
+FEATURE_FAMILIES = {
+    "k_kmer": ("k_kmer",),
+    "coverage": ("k_cov_",),
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -206,6 +265,7 @@ def main():
     ap.add_argument("--samples", type=int, default=0)
     ap.add_argument("--genomes", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the one-off comparison of the sharded search with the single-rank search")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,7 +276,8 @@ def main():
         if rank != 0:
             return 0
         mg = synth.make_metagenome(**w, q6_reads=True)
-        info, sample, _ = reference_arm(mg, args.steps, max(args.warmup, 0))
+        per_genome, genomes = reference_sample_size(args.steps, max(args.warmup, 0))
+        info, sample, _ = reference_arm(mg, args.steps, max(args.warmup, 0), per_genome, genomes)
         line = {"impl": "reference", "metric": "scaffolds/sec binned (feature build + split search)", "value": info["value"], "unit": "scaffolds/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sample.nscaf / info["value"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64/f64", "data": "synthetic",
@@ -261,7 +322,7 @@ def main():
 
     # pinned host copies (e2e) and device-resident copies (value)
     h_seq = torch.from_numpy(mg.seq).pin_memory()
-    h_reads = [torch.from_numpy(r.view(np.uint32).reshape(-1, 4)).pin_memory() for r in mg.reads]
+    h_reads = [torch.from_numpy(r.view(np.uint32).reshape(-1, 4)).pin_memory() for r in mg.reads[:1]]      # one sample, for the link measurement only
     # end-to-end path: what a host-side SAM parser hands over when it applies the read filter itself (abawaca-build.cpp:546-550):
     # 8-byte records {scaffold, position} of the accepted reads in SAM order, one read length per sample (pipeline.compact_reads), in pinned memory
     h_compact = []
@@ -286,11 +347,45 @@ def main():
     result_buffers = {}                                # records and bin arrays of the search, reused by every step
     dev = torch.device("cuda", local_rank)
 
-    def step(resident, timings=None):
+    def exchange(fb, counts, timings=None):
+        """N > 1: the global scaffold table from all ranks' window counts, and this rank's block of columns of ALL datapoints (one NCCL all-to-all)."""
+        t_x0 = time.perf_counter()
+        # 1) windows per scaffold of every rank (the only per-scaffold quantity this step computed; lengths and SCG masks of all ranks were
+        #    exchanged once at set-up): everybody derives the same global scaffold table, scaffold ids rank-major
+        cnt_local = torch.from_numpy(counts.astype(np.int32)).to(dev)
+        cnt_all = torch.empty(world * nscaf, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(cnt_all, cnt_local)
+        cnt_all = cnt_all.cpu().numpy()
+        keep_all = cnt_all >= 2                                            # ScafDpData.cpp:92-93
+        T_all = cnt_all[keep_all].astype(np.uint32)
+        rows_per_rank = np.where(keep_all, cnt_all, 0).reshape(world, nscaf).sum(axis=1).tolist()
+        if timings is not None:
+            timings["exchange_tables_ms"] = 1000.0 * (time.perf_counter() - t_x0)
+            t_x0 = time.perf_counter()
+        # 2) every rank holds the rows of its own scaffolds and will search a block of COLUMNS of all datapoints: one all-to-all (NCCL) in which
+        #    rank q receives from everybody the columns it owns -- 1/world of what an all-gather of whole rows would move
+        keep = np.repeat(counts >= 2, counts) if (counts < 2).any() else None
+        local = torch.as_tensor(distributed._DevArray(fb.d_rows, fb.nseg * fb.ncols * 8, "<f8", 8), device=dev).view(fb.nseg, fb.ncols)
+        if keep is not None:
+            local = local[torch.from_numpy(np.nonzero(keep)[0]).to(dev)]
+        blocks = [distributed.dim_block(fb.ncols, r, world) for r in range(world)]
+        off, cnt = blocks[rank]
+        n_local = int(local.shape[0])
+        send = torch.cat([local[:, o:o + c].reshape(-1) for o, c in blocks])
+        full = torch.empty((sum(rows_per_rank), cnt), dtype=torch.float64, device=dev)
+        dist.all_to_all_single(full.view(-1), send, output_split_sizes=[n * cnt for n in rows_per_rank], input_split_sizes=[n_local * c for _, c in blocks])
+        torch.cuda.synchronize(dev)
+        if timings is not None:
+            timings["exchange_columns_ms"] = 1000.0 * (time.perf_counter() - t_x0)
+        return dict(full=full, off=off, cnt=cnt, T_all=T_all, keep_all=keep_all, rows_per_rank=rows_per_rank, local=local)
+
+    def step(resident, timings=None, on_features=None, keep_exchange=False):
         if resident:
             fb = pipeline.build_features(ctx, d_seq, mg.offsets, d_reads, this_sample=0, seq_on_device=True, reads_on_device=True, nreads=nreads, timings=timings)
         else:
             fb = pipeline.build_features(ctx, h_seq.numpy(), mg.offsets, h_compact, this_sample=0, timings=timings, overlap_h2d=True)
+        if on_features is not None:
+            on_features()
         t_a = time.perf_counter()
         seg_first = fb.seg_first_host()
         t_b = time.perf_counter()
@@ -301,8 +396,6 @@ def main():
             row_of_dp, T, kept, ndps_total = pipeline.search_rows_from_counts(counts)
             if kept is None:
                 kept = slice(None)
-        else:                                          # the global tables are derived from all ranks' window counts further down
-            keep = np.repeat(counts >= 2, counts) if (counts < 2).any() else np.ones(int(counts.sum()), dtype=bool)
         if timings is not None:
             timings["segments_host_ms"] = 1000.0 * (t_b - t_a)
             timings["search_problem_ms"] = 1000.0 * (time.perf_counter() - t_b)
@@ -321,52 +414,31 @@ def main():
         if world == 1:
             res = pipeline.search(ctx, fb.d_rows, None, T, lengths[kept], masks[kept], layout=capi.LAYOUT_ROWMAJOR, values_on_device=True,
                                   nrows=fb.nseg, D=fb.ncols, ld=fb.ncols, row_of_dp=row_of_dp, timings=timings, buffers=result_buffers)
-            nbins = int(np.count_nonzero(np.bincount(res.scaf2cluster)[1:]))
         else:
-            # 1) windows per scaffold of every rank (the only per-scaffold quantity this step computed; lengths and SCG masks of all ranks were
-            #    exchanged once at set-up): everybody derives the same global scaffold table, scaffold ids rank-major
-            t_x0 = time.perf_counter()
-            cnt_local = torch.from_numpy(counts.astype(np.int32)).to(dev)
-            cnt_all = torch.empty(world * nscaf, dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(cnt_all, cnt_local)
-            cnt_all = cnt_all.cpu().numpy()
-            keep_all = cnt_all >= 2                                            # ScafDpData.cpp:92-93
-            T_all = cnt_all[keep_all].astype(np.uint32)
-            rows_per_rank = [int(cnt_all[r * nscaf:(r + 1) * nscaf][keep_all[r * nscaf:(r + 1) * nscaf]].sum()) for r in range(world)]
-            if timings is not None:
-                timings["exchange_tables_ms"] = 1000.0 * (time.perf_counter() - t_x0)
-                t_x0 = time.perf_counter()
-            # 2) every rank holds the rows of its own scaffolds and will search a block of COLUMNS of all datapoints: one all-to-all (NCCL) in which
-            #    rank q receives from everybody the columns it owns -- 1/world of what an all-gather of whole rows would move
-            local = torch.as_tensor(distributed._DevArray(fb.d_rows, fb.nseg * fb.ncols * 8, "<f8", 8), device=dev).view(fb.nseg, fb.ncols)
-            if not keep.all():
-                local = local[torch.from_numpy(np.nonzero(keep)[0]).to(dev)]
-            blocks = [distributed.dim_block(fb.ncols, r, world) for r in range(world)]
-            off, cnt = blocks[rank]
-            n_local = int(local.shape[0])
-            send = torch.cat([local[:, o:o + c].reshape(-1) for o, c in blocks])
-            full = torch.empty((sum(rows_per_rank), cnt), dtype=torch.float64, device=dev)
-            dist.all_to_all_single(full.view(-1), send, output_split_sizes=[n * cnt for n in rows_per_rank], input_split_sizes=[n_local * c for _, c in blocks])
-            torch.cuda.synchronize(dev)
-            if timings is not None:
-                timings["exchange_columns_ms"] = 1000.0 * (time.perf_counter() - t_x0)
-            # 3) dimension-sharded search: this rank sweeps columns [off, off+cnt) of every datapoint
-            res = pipeline.search(ctx, full.data_ptr(), None, T_all, lengths_all[keep_all], masks_all[keep_all],
-                                  layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=int(full.shape[0]), D=cnt, ld=cnt, timings=timings,
-                                  collectives=coll, dim_offset=off, D_total=fb.ncols, buffers=result_buffers)
-            nbins = int(np.count_nonzero(np.bincount(res.scaf2cluster)[1:]))
-            ndps_total = int(full.shape[0])
-            del full
+            x = exchange(fb, counts, timings)
+            # dimension-sharded search: this rank sweeps columns [off, off+cnt) of every datapoint
+            res = pipeline.search(ctx, x["full"].data_ptr(), None, x["T_all"], lengths_all[x["keep_all"]], masks_all[x["keep_all"]],
+                                  layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=int(x["full"].shape[0]), D=x["cnt"], ld=x["cnt"], timings=timings,
+                                  collectives=coll, dim_offset=x["off"], D_total=fb.ncols, buffers=result_buffers)
+            ndps_total = int(x["full"].shape[0])
+            if keep_exchange:
+                state["exchange"] = x
+            else:
+                del x
+        nbins = int(np.count_nonzero(np.bincount(res.scaf2cluster)[1:]))
         if not resident:
             ctx.synchronize()                          # the matrix has arrived on the host (copy stream) before the step counts as done
             if fb.milli_inexact():
                 raise SystemExit("bench.py: a feature value is not a multiple of 0.001")
         state.update(ndps=ndps_total, nseg=fb.nseg, ncols=fb.ncols, prof=res.profile, nclusters=len(res.recs), nbins=nbins,
-                     bins=res.scaf2cluster)
+                     bins=res.scaf2cluster, res=res)
         if timings is not None:                        # window lengths: only needed for the algorithmic byte count of the k-mer kernel
             sg = fb.segments_host()
             state["seg_len"] = sg["seg_end"] - sg["seg_start"] + 1
-        fb.close()
+        if keep_exchange:
+            state["fb"] = fb
+        else:
+            fb.close()
         return res
 
     ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
@@ -403,12 +475,38 @@ def main():
         state["host_ms_and_driver_allocations_" + ("resident" if resident else "e2e")] = host
         return float(t.item()), ctx.launches - l0, per_step
 
+    def verify_sharded():
+        """Once, outside the timed region: the NCCL-sharded search of this run against the single-rank search of the SAME gathered problem on rank 0 --
+        every cluster record and every scaffold's bin must be identical (work list abawaca.cpp:98-197; merge order ClusterSeparator.cpp:11-16)."""
+        res = step(True, keep_exchange=True)
+        x, fb = state.pop("exchange"), state.pop("fb")
+        rows_all = distributed.allgather_rows(torch, dist, x["local"].contiguous(), x["rows_per_rank"])
+        verdict = torch.zeros(1, dtype=torch.int32, device=dev)
+        if rank == 0:
+            single = pipeline.search(ctx, rows_all.data_ptr(), None, x["T_all"], lengths_all[x["keep_all"]], masks_all[x["keep_all"]], layout=capi.LAYOUT_ROWMAJOR,
+                                     values_on_device=True, nrows=int(rows_all.shape[0]), D=fb.ncols, ld=fb.ncols)
+            key = lambda r: (r.id, r.parent, r.ndps, r.nscafs, r.split, r.best.found, r.best.dim, r.best.value, r.best.a, r.best.b, r.child1, r.child2,   # noqa: E731
+                             r.child1_ndps, r.child2_ndps, r.child1_nscafs, r.child2_nscafs, r.child1_raw, r.child2_raw, r.total_size, r.scg_unique, r.scg_avg)
+            same = [key(r) for r in res.recs] == [key(r) for r in single.recs] and np.array_equal(res.scaf2cluster, single.scaf2cluster) and \
+                np.array_equal(res.dp2cluster, single.dp2cluster)
+            verdict[0] = 1 if same else 2
+        dist.all_reduce(verdict, op=dist.ReduceOp.MAX)
+        fb.close()
+        del x, rows_all
+        return {"sharded_equals_single": bool(int(verdict.item()) == 1), "clusters": len(res.recs), "scaffolds": int(res.scaf2cluster.size),
+                "what": "abw_search_run_sharded over NCCL on all ranks against abw_search_run on rank 0, same gathered matrix: records, scaffold bins and datapoint bins"}
+
     # the sampler is started BEFORE the warm-up: nvidia-smi takes driver locks while it starts and would otherwise stall the first timed launches
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("ABW_NO_CLOCK_SAMPLER"):   # one nvidia-smi poller per job: every query takes driver locks that all ranks' launches wait on
         sampler.start()
     for _ in range(args.warmup):
         step(True)
+    verify = None
+    if world > 1 and not args.no_verify:
+        verify = verify_sharded()
+        if not verify["sharded_equals_single"]:
+            raise SystemExit("bench.py: the sharded search differs from the single-rank search")
     n_warm_samples = len(sampler.rows)                 # samples before this index were taken during the warm-up (same load)
     ms_res, launches, steps_res = timed(True, args.steps)
     timed_rows = sampler.rows[n_warm_samples:]
@@ -433,63 +531,82 @@ def main():
         pcie = {"h2d_GBps": round(nb / best / 1e6, 2), "bytes": int(nb)}
         del dst
 
-    # one extra profiled step: per-kernel CUDA-event durations (launches serialised while profiling)
+    # one extra profiled step: per-kernel CUDA-event durations (launches serialised while profiling), feature stage and split search reported apart
     phase_ms = {}
     t0 = time.perf_counter()
     step(True, timings=phase_ms)                       # host wall-clock per ABI phase of one (un-profiled) resident step
     phase_ms["step_total_ms"] = 1000.0 * (time.perf_counter() - t0)
+    reports = {}
+
+    def features_done():
+        reports["features"] = ctx.profile_report()
+        ctx.profile(True)                              # clears: what follows is the split search (create + run)
     ctx.profile(True)
-    step(True)
-    report = ctx.profile_report()
+    step(True, on_features=features_done)
+    reports["search"] = ctx.profile_report()
     ctx.profile(False)
     prof = state["prof"]
     hbm, peak_src = peaks()
     seg_len = state["seg_len"].astype(np.int64)
-    alg = {
-        # algorithmic bytes per step (all launches of the kernel)
-        "k_kmer<ABW_FEAT_TRUNC3>": float(((seg_len + 3) // 4 + (seg_len + 7) // 8).sum() + state["nseg"] * 179 * 8),
-        "k_sweep_ss": 12.0 * prof.sweep_elements,
+    gbps = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0   # noqa: E731
+    traffic_db = {}
+    for f in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            for k, v in json.load(open(os.path.join(ROOT, "profiles", f))).items():
+                traffic_db.setdefault(k, v)
+        except Exception:
+            pass
+    # DESIGN.md section 5 / SURVEY.md section 8(d): algorithmic bytes per step
+    alg_kmer = float(((seg_len + 3) // 4 + (seg_len + 7) // 8).sum() + state["nseg"] * 179 * 8)
+    alg_cov = float(16 * sum(nreads) + 8 * state["nseg"] * len(nreads))
+    alg_search = 12.0 * prof.sweep_elements
+    ms_of = lambda rep, prefixes: sum(ms for k, (c, ms) in rep.items() if any(p in k for p in prefixes))   # noqa: E731
+    ms_kmer = ms_of(reports["features"], FEATURE_FAMILIES["k_kmer"])
+    ms_cov = ms_of(reports["features"], FEATURE_FAMILIES["coverage"]) + ms_of(reports["features"], ("k_rs_", "k_scan_"))   # sort and scans of the feature stage belong to the coverage
+    ms_search = sum(ms for c, ms in reports["search"].values())
+    ms_sweep = ms_of(reports["search"], ("k_sweep_ss", "k_sweep<"))
+    families = {
+        "split_search": {"kernels": "every kernel of abw_search_create + abw_search_run (" + str(len(reports["search"])) + " kernels)", "ms_per_step": round(ms_search, 4),
+                         "algorithmic_bytes_per_step": alg_search, "achieved": round(gbps(alg_search, ms_search), 2), "frac": round(gbps(alg_search, ms_search) / hbm, 4)},
+        "coverage": {"kernels": "every kernel of abw_coverage_batch incl. its sort", "ms_per_step": round(ms_cov, 4), "algorithmic_bytes_per_step": alg_cov,
+                     "achieved": round(gbps(alg_cov, ms_cov), 2), "frac": round(gbps(alg_cov, ms_cov) / hbm, 4)},
+        "k_kmer": {"kernels": "k_kmer", "ms_per_step": round(ms_kmer, 4), "algorithmic_bytes_per_step": alg_kmer, "achieved": round(gbps(alg_kmer, ms_kmer), 2),
+                   "frac": round(gbps(alg_kmer, ms_kmer) / hbm, 4)},
     }
-    # kernels that exist only to feed another one: their time is also reported added to it
-    helpers = {"k_sweep_ss": ["k_flip_prefix"]}
+    # per kernel, beside the family figures: the sweep kernel alone against the same 12 B per (datapoint, dimension), with the DRAM bytes ncu saw it move
+    sweep_traffic = None
+    tj = traffic_db.get("k_sweep_ss")
+    if tj:
+        sweep_traffic = {"dram_bytes_per_step": round(tj["dram_bytes"] / tj["units"] * prof.sweep_elements), "source": tj["source"]}
+    per_kernel = {"k_sweep_ss": {"ms_per_step": round(ms_sweep, 4), "achieved": round(gbps(alg_search, ms_sweep), 2), "frac": round(gbps(alg_search, ms_sweep) / hbm, 4),
+                                 "note": "the sweep streams 4-byte elements; values and scaffold ids (the 12 B) are consumed by sort, packing, flip tables and partition, "
+                                         "whose time the family figure includes", "traffic": sweep_traffic}}
+    dom = max(families, key=lambda k: families[k]["ms_per_step"])
+    launches_dom = sum(c for c, ms in reports["search"].values()) if dom == "split_search" else None
+    fam_traffic = traffic_db.get("family:" + dom)
+    roofline = {"bound": "hbm", "kernel": dom, "kernels": families[dom]["kernels"], "achieved": families[dom]["achieved"], "peak": hbm, "peak_source": peak_src, "unit": "GB/s",
+                "frac": families[dom]["frac"], "traffic": (round(fam_traffic["dram_bytes"] / fam_traffic["units"] * prof.sweep_elements) if fam_traffic and dom == "split_search" else None),
+                "traffic_source": fam_traffic["source"] if fam_traffic else None, "ms_per_step_in_kernels": families[dom]["ms_per_step"],
+                "launches_per_step": launches_dom, "algorithmic_bytes_per_step": families[dom]["algorithmic_bytes_per_step"],
+                "definition": "SURVEY.md 8(d): 12 B per (datapoint, dimension) of every evaluated cluster / CUDA-event time of ALL split-search kernels of a step",
+                "families": families, "per_kernel": per_kernel}
     kernels = {}
-    total_ms = sum(v[1] for v in report.values())
-    for k, (cnt, ms) in sorted(report.items(), key=lambda kv: -kv[1][1]):
-        ent = {"launches": cnt, "ms": round(ms, 4), "share": round(ms / total_ms, 4) if total_ms else None}
-        if k in alg and ms > 0:
-            ent["algorithmic_GBps"] = round(alg[k] / (ms * 1e-3) / 1e9, 2)
-            ent["frac_of_hbm_peak"] = round(alg[k] / (ms * 1e-3) / 1e9 / hbm, 4)
-        kernels[k] = ent
-    # the roofline object: the dominant kernel among those the survey gives algorithmic bytes for
-    dom = max(alg, key=lambda k: report.get(k, (0, 0.0))[1])
-    dcnt, dms = report.get(dom, (1, 0.0))
-    ach = alg[dom] / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
-    # DRAM bytes actually moved, from the committed ncu --set full capture of this kernel (profiles/r01_traffic.json): bytes per unit of that launch
-    # times the units of an average launch of this run
-    traffic, traffic_src = None, None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[dom]
-        units = prof.sweep_elements if dom == "k_sweep_ss" else float(seg_len.sum())
-        traffic = round(tj["dram_bytes"] / tj["units"] * units / max(dcnt, 1))
-        traffic_src = tj["source"]
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 2), "peak": hbm, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / hbm, 4),
-                "traffic": traffic, "traffic_source": traffic_src, "launches_per_step": dcnt, "ms_per_step_in_kernel": round(dms, 4),
-                "algorithmic_bytes_per_step": alg[dom], "algorithmic_bytes_per_launch": round(alg[dom] / max(dcnt, 1))}
-    hms = sum(report.get(h, (0, 0.0))[1] for h in helpers.get(dom, []))
-    if hms > 0:
-        roofline["with_helpers"] = {"kernels": helpers[dom], "ms_per_step": round(dms + hms, 4), "achieved": round(alg[dom] / ((dms + hms) * 1e-3) / 1e9, 2),
-                                    "frac": round(alg[dom] / ((dms + hms) * 1e-3) / 1e9 / hbm, 4)}
+    allrep = {}
+    for rep in reports.values():
+        for k, (c, ms) in rep.items():
+            a = allrep.setdefault(k, [0, 0.0])
+            a[0] += c; a[1] += ms
+    total_ms = sum(v[1] for v in allrep.values())
+    for k, (cnt, ms) in sorted(allrep.items(), key=lambda kv: -kv[1][1]):
+        kernels[k] = {"launches": cnt, "ms": round(ms, 4), "share": round(ms / total_ms, 4) if total_ms else None}
 
     total_scaf = nscaf * world
     value = total_scaf * args.steps / (ms_res * 1e-3)
     e2e_value = total_scaf * args.steps / (ms_e2e * 1e-3)
-    h2d = total_bp + sum(c.nbytes for c in h_compact) + mg.offsets.nbytes + state["nseg"] * 4 + nscaf * (4 + 8 + 8 * masks.shape[1])
-    # .lrn matrix as integer thousandths (2 bytes per k-mer value, 4 per coverage value) + window table + per-scaffold bins + per-datapoint bins
-    d2h = state["nseg"] * (179 * 2 + len(mg.reads) * 4) + state["nseg"] * (4 + 3 * 8) + (nscaf + 1) * 8 + nscaf * 4 + state["nseg"] * 4
-
-    bins_total = state["nbins"]                       # every rank ends with the bins of the whole community
+    nrec_bytes = state["nclusters"] * C.sizeof(capi.ClusterRec)
+    h2d = total_bp + sum(c.nbytes for c in h_compact) + mg.offsets.nbytes + nscaf * (4 + 8 + 8 * masks.shape[1])
+    # .lrn matrix as integer thousandths (2 bytes per k-mer value, 4 per coverage value) + window table + window offsets + cluster records + per-scaffold and per-datapoint bins
+    d2h = state["nseg"] * (179 * 2 + len(mg.reads) * 4) + state["nseg"] * (4 + 3 * 8) + (nscaf + 1) * 8 + nrec_bytes + nscaf * 4 + state["ndps"] * 4
 
     line = {"metric": "scaffolds/sec binned (feature build + split search)", "value": round(value, 2), "unit": "scaffolds/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True, "scaling": "weak",
@@ -498,14 +615,19 @@ def main():
                        "parallelism": (f"one community of {world} x {nscaf} scaffolds: scaffold-sharded feature build, NCCL all-to-all of feature columns, "
                                        f"dimension-sharded split search ({state['ncols']} dimensions over {world} ranks)") if world > 1 else "1 GPU",
                        "l2": "inputs (assembly + read records, > 2 GB) are larger than the 126 MB L2; no explicit flush",
-                       "clusters_evaluated": state["nclusters"], "bins": bins_total, "search_levels": prof.levels, "datapoints": state["ndps"],
+                       "e2e_inputs": "pinned host buffers: ASCII assembly + 8-byte read records of the reads that pass the host-side filter (abw_read8), one length per sample",
+                       "clusters_evaluated": state["nclusters"], "bins": state["nbins"], "search_levels": prof.levels, "datapoints": state["ndps"],
                        "nccl": None if coll is None else {"search_collectives": type(coll).__name__, "callback_collectives_total": coll.calls, "callback_bytes_total": coll.bytes}},
             "e2e": {"value": round(e2e_value, 2), "unit": "scaffolds/s", "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "pcie": pcie, "gpu_launches": int(launches), "step_ms": {"resident": steps_res, "e2e": steps_e2e,
                                                      "host_ms_and_driver_allocations": {"resident": state.get("host_ms_and_driver_allocations_resident"),
                                                                                         "e2e": state.get("host_ms_and_driver_allocations_e2e")}}, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "kernel_time_over_step_time": round(total_ms / (ms_res / args.steps), 3),
             "phase_wall_ms": {k: round(v, 3) for k, v in phase_ms.items()},
             "search_profile_ms": {"build": round(prof.build_ms, 3), "sweep": round(prof.sweep_ms, 3), "partition": round(prof.partition_ms, 3), "other": round(prof.other_ms, 3)}}
+    if verify is not None:
+        line["sharded_equals_single"] = verify["sharded_equals_single"]
+        line["config"]["verification"] = verify
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -535,12 +657,15 @@ def main():
                 ctx.free(d_text); ctx.free(d_rec); sp.close()
                 return {"kernel_path": "abw_parse_sam", "text_bytes": int(text.size), "records": int(n.value), "ms": round(ms, 3),
                         "GBps": round(text.size / (ms * 1e-3) / 1e9, 2), "records_identical_to_generator": ok}
-            info, sample, ref_bins = reference_arm(mg, 1, 0, extra=ingest)
+            # 4 genomes x 300 scaffolds: about 10 s of reference time, and the reference recurses (3 splits)
+            info, sample, ref_bins = reference_arm(mg, 1, 0, 300, 4, extra=ingest, with_compute_only=True, with_cli=True)
             if "_extra" in info:
                 line["ingest"] = info.pop("_extra")
             gbins, kept = gpu_bins_for(ctx, sample, pipeline, capi)
             # the reference lists only scaffolds with >= 2 windows (ScafDpData.cpp:92-93)
             info["gpu_bins_identical_on_sample"] = bool(ref_bins == [int(b) for b in gbins[kept]])
+            if "e2e_cli" in info:
+                line["e2e_cli"] = info.pop("e2e_cli")
             line["cpu_baseline"] = info
         except Exception as e:  # the baseline must never take the bench line down
             line["cpu_baseline"] = {"value": None, "unit": "scaffolds/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e!r}"}

@@ -11,6 +11,7 @@
 // path can be pinned bit-for-bit, for both strategies.
 //
 // usage: ref_search <names> <fasta> <info> <lrn> <gene2scg|-> <scg.list> <sensspec|splitscafs> <nthreads> <out.tsv>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -70,6 +71,8 @@ int main(int argc, char** argv)
 		root->add_assigned_scaf(s);
 	work[next_id++] = root;
 
+	// wall clock of the work list alone (objects are built from the text files above): printed on stderr as SEARCH_SECONDS for bench.py's compute-only baseline
+	const std::chrono::steady_clock::time_point t_search0 = std::chrono::steady_clock::now();
 	while(!work.empty()) {
 		size_t id = work.begin()->first;
 		Cluster* cur = work.begin()->second;
@@ -121,6 +124,7 @@ int main(int argc, char** argv)
 		// the separator leaks its ClusterQuality/ClusteringResult by design (ClusterSeparator.h:38)
 	}
 
+	fprintf(stderr, "SEARCH_SECONDS %.6f\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_search0).count());
 	for(size_t s = 1; s <= scaf_db.nscafs(); s++) {
 		auto it = scaf_bin.find(s);
 		fprintf(out, "S\t%s\t%lu\n", scaf_db.scaf_id2name(s).c_str(), (it == scaf_bin.end())? 0UL : it->second);

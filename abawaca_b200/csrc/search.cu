@@ -14,7 +14,7 @@
 //     instead of re-sorting every cluster (std::sort at ...Specificity.cpp:114) and rebuilding std::map/std::set state.
 //   * the SCG acceptance test (ClusterQuality.cpp:96-136) is evaluated for EVERY candidate through a small per
 //     (cluster, dimension) table indexed by the number of SCG-carrying scaffolds already flipped to side 1.
-#include "common.cuh"
+#include "features.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -1167,6 +1167,19 @@ __global__ void __launch_bounds__(256) k_count_low(const uint32_t* __restrict__ 
 	}
 }
 
+// Where the value of (datapoint, dimension) lives: the caller's matrix, in the caller's layout, read in place (no column-major copy is made).
+struct ValSrc {
+	const double*   p;
+	uint64_t        ld;
+	int             layout;
+	const uint64_t* rowidx;        // matrix row of every datapoint (device), or null: datapoint i is row i
+};
+__device__ __forceinline__ double val_at(const ValSrc& v, uint64_t dp, uint32_t d)
+{
+	const uint64_t r = v.rowidx? v.rowidx[dp] : dp;
+	return (v.layout == ABW_LAYOUT_ROWMAJOR)? v.p[r * v.ld + d] : v.p[(uint64_t)d * v.ld + r];
+}
+
 __device__ __forceinline__ unsigned long long orderable(double v)
 {
 	v = v + 0.0;                                    // -0.0 and +0.0 compare equal in comp_by_value (ClusterSeparator.cpp:8)
@@ -1177,7 +1190,7 @@ __device__ __forceinline__ unsigned long long orderable(double v)
 // recovers the separating value.  The statistics of a warp are combined before they reach the two counters of the job (one atomic per warp and field).
 // low[] is cleared on the way (the entry of the scaffold that carries the separating value by k_level_decide).
 __global__ void __launch_bounds__(SS_CHUNK) k_scaf_sides(const uint32_t* __restrict__ scaf_list, const LevelBufs B, int cur, uint32_t dim_offset,
-                             const ScafRow* __restrict__ rows, uint32_t* __restrict__ low, const uint64_t* __restrict__ dp_first, const double* __restrict__ values, uint64_t N,
+                             const ScafRow* __restrict__ rows, uint32_t* __restrict__ low, const uint64_t* __restrict__ dp_first, const ValSrc vsrc,
                              const uint64_t* __restrict__ scgmask, uint32_t W, int strategy, double fraction_in, uint8_t* __restrict__ side, uint8_t* __restrict__ new_assigned,
                              ChildStats* __restrict__ stats, uint64_t* __restrict__ child_never, unsigned long long* __restrict__ value_key)
 {
@@ -1194,13 +1207,14 @@ __global__ void __launch_bounds__(SS_CHUNK) k_scaf_sides(const uint32_t* __restr
 			const uint32_t s = jb.sstar;
 			const ScafRow r = rows[s];
 			const uint32_t lo = low[s];
-			const double* __restrict__ col = values + (uint64_t)(jb.dim0 - dim_offset) * N + dp_first[s];
+			const uint64_t f = dp_first[s];
+			const uint32_t dl = jb.dim0 - dim_offset;
 			unsigned long long kth = 0;
 			for(uint32_t a = lane; a < r.n; a += 32) {
-				const unsigned long long ka = orderable(col[a]);
+				const unsigned long long ka = orderable(val_at(vsrc, f + a, dl));
 				uint32_t rank = 0;
 				for(uint32_t b = 0; b < r.n; b++) {
-					const unsigned long long kb = orderable(col[b]);
+					const unsigned long long kb = orderable(val_at(vsrc, f + b, dl));
 					rank += (kb < ka) || (kb == ka && b < a);
 				}
 				if(rank + 1 == lo)
@@ -1827,102 +1841,104 @@ __global__ void k_dp_bins(const uint32_t* __restrict__ dp2scaf, const uint32_t* 
 // ---------------------------------------------------------------------------------------------------
 // build: keys, within-scaffold classes, element packing
 // ---------------------------------------------------------------------------------------------------
-// tiled transpose of a row-major [N][ld] matrix (columns [d0, d0+nd)) into column-major [nd][N]
-__global__ void k_transpose_in(const double* __restrict__ rows, uint64_t ld, uint64_t N, uint32_t d0, uint32_t nd, const uint64_t* __restrict__ row_of_dp,
-                               double* __restrict__ cols)
+// Sort keys of the dimensions [d0, d0 + nd) of all datapoints, column major [nd][N], and the datapoint index beside each.
+// MILLI: columns written by abawaca-build hold multiples of 0.001 (int(1000*x)/1000.0, abawaca-build.cpp:603).  When every value v satisfies
+// v == (double)k / 1000.0 for the integer k = rint(1000*v), |k| < 2^31, ordering by k is ordering by v (ties included) and the sort runs on 32-bit keys
+// with few significant bits; any other value sets flag[0] and the chunk is redone with the 64-bit keys (an order-preserving image of the double; -0.0 and
+// +0.0 compare equal in comp_by_value, ClusterSeparator.cpp:8; NaN sets flag[1]).  or_and[2 k], or_and[2 k + 1] (k = blockIdx.x & 63; preset to 0 and ~0):
+// OR and AND of the keys, so that the sort knows which key bits differ at all without another pass over the keys.
+// One CTA transposes a tile of 32 datapoints x 32 dimensions through shared memory: coalesced reads of a row-major matrix, coalesced writes of the keys.
+template <bool MILLI, typename KeyT>
+__global__ void __launch_bounds__(256) k_keys(const ValSrc v, uint64_t N, uint32_t d0, uint32_t nd, KeyT* __restrict__ keys, uint32_t* __restrict__ vals,
+                                              int* __restrict__ flag, uint32_t* __restrict__ or_and)
 {
-	__shared__ double tile[32][33];
+	__shared__ KeyT tile[32][33];
+	__shared__ uint32_t sm_or[8], sm_and[8];
 	const uint64_t r0 = (uint64_t)blockIdx.x * 32;
 	const uint32_t c0 = blockIdx.y * 32;
-	for(int j = threadIdx.y; j < 32; j += blockDim.y) {
-		uint64_t r = r0 + j;
-		uint32_t c = c0 + threadIdx.x;
-		tile[j][threadIdx.x] = (r < N && c < nd)? rows[(row_of_dp? row_of_dp[r] : r) * ld + d0 + c] : 0.0;
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+	uint32_t key_or = 0u, key_and = ~0u;
+	bool bad = false, isnan = false;
+	const bool rowmajor = v.layout == ABW_LAYOUT_ROWMAJOR;
+#pragma unroll
+	for(int j = 0; j < 4; j++) {
+		// row-major: x runs over the dimensions of one datapoint; column-major: x runs over the datapoints of one dimension
+		const uint64_t dp = rowmajor? r0 + ty + 8 * j : r0 + tx;
+		const uint32_t c = rowmajor? c0 + tx : c0 + ty + 8 * j;
+		KeyT key = 0;
+		if(dp < N && c < nd) {
+			const double x = val_at(v, dp, d0 + c);
+			if(MILLI) {
+				const double k = rint(__dmul_rn(x, 1000.0));
+				const bool ok = (k > -2147483000.0) && (k < 2147483000.0) && (__ddiv_rn(k, 1000.0) == x);
+				bad |= !ok;
+				const uint32_t k32 = ok? (uint32_t)((long long)k + 2147483648ll) : 0u;
+				key = (KeyT)k32;
+				key_or |= k32;
+				key_and &= k32;
+			}
+			else {
+				isnan |= x != x;
+				key = (KeyT)orderable(x);
+			}
+		}
+		if(rowmajor)
+			tile[ty + 8 * j][tx] = key;                 // [datapoint][dimension]
+		else
+			tile[tx][ty + 8 * j] = key;
 	}
 	__syncthreads();
-	for(int j = threadIdx.y; j < 32; j += blockDim.y) {
-		uint32_t c = c0 + j;
-		uint64_t r = r0 + threadIdx.x;
-		if(r < N && c < nd)
-			cols[(uint64_t)c * N + r] = tile[threadIdx.x][j];
+#pragma unroll
+	for(int j = 0; j < 4; j++) {
+		const uint32_t c = c0 + ty + 8 * j;
+		const uint64_t dp = r0 + tx;
+		if(dp < N && c < nd) {
+			keys[(uint64_t)c * N + dp] = tile[tx][ty + 8 * j];
+			vals[(uint64_t)c * N + dp] = (uint32_t)dp;
+		}
+	}
+	if(__syncthreads_or(bad || isnan)) {
+		if(bad)
+			atomicExch(&flag[0], 1);
+		if(isnan)
+			atomicExch(&flag[1], 1);
+	}
+	if(MILLI) {
+		key_or = __reduce_or_sync(0xffffffffu, key_or);
+		key_and = __reduce_and_sync(0xffffffffu, key_and);
+		if(tx == 0) {
+			sm_or[ty] = key_or;
+			sm_and[ty] = key_and;
+		}
+		__syncthreads();
+		if(threadIdx.x == 0) {
+#pragma unroll
+			for(int w = 1; w < 8; w++) {
+				key_or |= sm_or[w];
+				key_and &= sm_and[w];
+			}
+			const uint32_t slot = (blockIdx.x + blockIdx.y) & 63u;
+			atomicOr(&or_and[2 * slot], key_or);
+			atomicAnd(&or_and[2 * slot + 1], key_and);
+		}
 	}
 }
 
-__global__ void k_gather_columns(const double* __restrict__ src, uint64_t ld, uint64_t N, const uint64_t* __restrict__ row_of_dp, double* __restrict__ cols)
-{
-	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t d = blockIdx.y;
-	if(i < N)
-		cols[(uint64_t)d * N + i] = src[(uint64_t)d * ld + row_of_dp[i]];
-}
-
-__global__ void k_make_keys(const double* __restrict__ values, uint64_t N, uint32_t nd, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ nan_flag)
-{
-	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t d = blockIdx.y;
-	if(i < N && d < nd) {
-		const double v = values[(uint64_t)d * N + i];
-		if(v != v)
-			atomicExch(nan_flag, 1);
-		keys[(uint64_t)d * N + i] = orderable(v);
-		vals[(uint64_t)d * N + i] = (uint32_t)i;
-	}
-}
-
-__global__ void k_fill_or_and(uint32_t* __restrict__ or_and, uint32_t nd)
+__global__ void k_fill_or_and(uint32_t* __restrict__ or_and, uint32_t n)
 {
 	const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-	if(d < nd) {
+	if(d < n) {
 		or_and[2 * d] = 0u;
 		or_and[2 * d + 1] = ~0u;
 	}
 }
 
-// Columns written by abawaca-build hold multiples of 0.001 (int(1000*x)/1000.0, abawaca-build.cpp:603).  When every value v of the chunk
-// satisfies v == (double)k / 1000.0 for the integer k = rint(1000*v), |k| < 2^31, ordering by k is ordering by v (ties included) and the
-// sort runs on 32-bit keys with few significant bits.  Any other value sets `inexact` and the chunk falls back to the 64-bit keys.
-// or_and[2 d], or_and[2 d + 1] (preset to 0 and ~0): OR and AND of the keys of dimension d, so that the sort knows which key bits differ at all
-// without another pass over the keys.
-__global__ void __launch_bounds__(256) k_make_keys_milli(const double* __restrict__ values, uint64_t N, uint32_t nd, uint32_t* __restrict__ keys,
-                                                         uint32_t* __restrict__ vals, int* __restrict__ inexact, uint32_t* __restrict__ or_and)
-{
-	__shared__ uint32_t sm_or[8], sm_and[8];
-	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t d = blockIdx.y;
-	uint32_t key_or = 0u, key_and = ~0u;
-	if(i < N && d < nd) {
-		const double v = values[(uint64_t)d * N + i];
-		const double k = rint(__dmul_rn(v, 1000.0));
-		bool ok = (k > -2147483000.0) && (k < 2147483000.0) && (__ddiv_rn(k, 1000.0) == v);
-		if(!ok)
-			atomicExch(inexact, 1);
-		const uint32_t key = ok? (uint32_t)((long long)k + 2147483648ll) : 0u;
-		keys[(uint64_t)d * N + i] = key;
-		vals[(uint64_t)d * N + i] = (uint32_t)i;
-		key_or = key_and = key;
-	}
-	key_or = __reduce_or_sync(0xffffffffu, key_or);
-	key_and = __reduce_and_sync(0xffffffffu, key_and);
-	if((threadIdx.x & 31) == 0) {
-		sm_or[threadIdx.x >> 5] = key_or;
-		sm_and[threadIdx.x >> 5] = key_and;
-	}
-	__syncthreads();
-	if(threadIdx.x == 0 && d < nd) {
-#pragma unroll
-		for(int w = 1; w < 8; w++) {
-			key_or |= sm_or[w];
-			key_and &= sm_and[w];
-		}
-		atomicOr(&or_and[2 * d], key_or);
-		atomicAnd(&or_and[2 * d + 1], key_and);
-	}
-}
-
 // class of every datapoint in every dimension of the chunk, from its rank inside its scaffold (ties by datapoint index,
-// the order a stable sort produces).  Thread per (datapoint, dimension).
-__global__ void k_rank_class(const double* __restrict__ values, uint64_t N, uint32_t nd, const uint32_t* __restrict__ dp2scaf, const uint64_t* __restrict__ dp_first,
-                             const ScafRow* __restrict__ rows, const uint8_t* __restrict__ has_scg, int strategy, double fraction_in, uint8_t* __restrict__ cls_out)
+// the order a stable sort produces).  Thread per (datapoint, dimension), on the sort keys (same order as the values, ties included).
+template <typename KeyT>
+__global__ void __launch_bounds__(256) k_rank_class(const KeyT* __restrict__ keys, uint64_t N, uint32_t nd, const uint32_t* __restrict__ dp2scaf,
+                                                    const uint64_t* __restrict__ dp_first, const ScafRow* __restrict__ rows, const uint8_t* __restrict__ has_scg, int strategy,
+                                                    double fraction_in, uint8_t* __restrict__ cls_out)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t d = blockIdx.y;
@@ -1931,11 +1947,11 @@ __global__ void k_rank_class(const double* __restrict__ values, uint64_t N, uint
 	const uint32_t s = dp2scaf[i];
 	const ScafRow r = rows[s];
 	const uint64_t f = dp_first[s];
-	const double* __restrict__ col = values + (uint64_t)d * N;
-	const unsigned long long ki = orderable(col[i]);
+	const KeyT* __restrict__ col = keys + (uint64_t)d * N;
+	const KeyT ki = col[i];
 	uint32_t a = 1;                                              // 1-based rank of this dp among the dps of its scaffold
 	for(uint64_t j = f; j < f + r.n; j++) {
-		const unsigned long long kj = orderable(col[j]);
+		const KeyT kj = __ldg(col + j);
 		a += (kj < ki) || (kj == ki && j < i);
 	}
 	uint32_t cls, aux;
@@ -2173,7 +2189,9 @@ struct abw_search {
 	uint32_t D = 0, S = 0, W = 1, K = 0;
 	int strategy = 0;
 	abw_params prm{};
-	DevBuf<double> values;
+	DevBuf<double> values;                    // device copy of a matrix the caller passed in host memory (a device matrix is read in place)
+	DevBuf<uint64_t> rowidx;                  // matrix row of every datapoint, when the caller gave one
+	ValSrc vsrc{};
 	DevBuf<uint32_t> dp2scaf;
 	DevBuf<uint64_t> dp_first;
 	DevBuf<ScafRow> rows;
@@ -2242,29 +2260,16 @@ int upload(abw_ctx* ctx, DevBuf<T>& buf, const std::vector<T>& h)
 	return ABW_OK;
 }
 
-int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_on_device, int layout, uint64_t ld, uint64_t nrows, const uint64_t* h_row_of_dp,
-                 const uint32_t* h_dp2scaf, const uint32_t* h_T, const uint64_t* h_len, const uint64_t* h_scgmask)
+// The part of abw_search_create that starts from device arrays: s->vsrc (the matrix), d_T, d_len, s->scgmask, s->dp2scaf (when the caller gave one).
+// One host wait for the whole build when all dimensions fit one chunk of sort scratch: per-scaffold tables, their validation, the root statistics, the number
+// of SCG-carrying scaffolds and the key statistics of the first chunk are fetched together.
+int search_build_common(abw_ctx* ctx, abw_search* s, DevBuf<uint32_t>& d_T, DevBuf<uint64_t>& d_len, bool have_dp2scaf, Trace& tr)
 {
 	const uint64_t N = s->N;
 	const uint32_t D = s->D, S = s->S, W = s->W;
-	Trace tr(ctx->stream, "create");
-	// ---- per-scaffold tables, built on the device from the caller's arrays
-	ABW_CUDA(ctx, s->dp2scaf.alloc(N));
-	if(h_dp2scaf)
-		ABW_CUDA(ctx, cudaMemcpyAsync(s->dp2scaf.p, h_dp2scaf, sizeof(uint32_t) * N, cudaMemcpyHostToDevice, ctx->stream));
-	ABW_CUDA(ctx, s->scgmask.alloc((size_t)S * W));
-	if(h_scgmask)
-		ABW_CUDA(ctx, cudaMemcpyAsync(s->scgmask.p, h_scgmask, sizeof(uint64_t) * (size_t)S * W, cudaMemcpyHostToDevice, ctx->stream));
-	else
-		ABW_CUDA(ctx, cudaMemsetAsync(s->scgmask.p, 0, sizeof(uint64_t) * (size_t)S * W, ctx->stream));
-	DevBuf<uint32_t> d_T, d_scg_flag, d_scg_scafs, d_scg_index;
-	DevBuf<uint64_t> d_len, d_scg_before, d_total;
+	DevBuf<uint32_t> d_scg_flag, d_scg_scafs, d_scg_index;
+	DevBuf<uint64_t> d_scg_before, d_total;
 	DevBuf<RootStats> d_rs;
-	ABW_CUDA(ctx, d_T.alloc(S));
-	ABW_CUDA(ctx, d_len.alloc(S));
-	ABW_CUDA(ctx, cudaMemcpyAsync(d_T.p, h_T, sizeof(uint32_t) * S, cudaMemcpyHostToDevice, ctx->stream));
-	ABW_CUDA(ctx, cudaMemcpyAsync(d_len.p, h_len, sizeof(uint64_t) * S, cudaMemcpyHostToDevice, ctx->stream));
-	tr.mark("uploads");
 	ABW_CUDA(ctx, d_rs.alloc(1));
 	ABW_CUDA(ctx, cudaMemsetAsync(d_rs.p, 0, sizeof(RootStats), ctx->stream));
 	ABW_CUDA(ctx, s->rows.alloc(S));
@@ -2277,26 +2282,61 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	ABW_CUDA(ctx, d_total.alloc(1));
 	for(int b = 0; b < 2; b++)
 		ABW_CUDA(ctx, s->scaf_list[b].alloc(S));
-	if(h_dp2scaf)
+	if(have_dp2scaf)
 		ABW_LAUNCH(ctx, k_tab_runs, abw_div_up(N, 256), 256, 0, s->dp2scaf.p, N, S, s->dp_first.p, d_rs.p);
 	else {
-		// no dp2scaf: the matrix holds all T datapoints of every scaffold, in scaffold order
+		// no dp2scaf: the matrix holds all T datapoints of every scaffold, in scaffold order (sum(T) == N is checked with the other results below;
+		// k_tab_fill_dp2scaf never writes past N)
 		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, d_T.p, s->dp_first.p, S, s->dp_first.p + S));
-		uint64_t sumT = 0;
-		ABW_CUDA(ctx, abw_fetch(ctx, &sumT, s->dp_first.p + S, sizeof(uint64_t)));
-		ABW_CUDA(ctx, abw_sync(ctx));
-		if(sumT != N)
-			return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: without dp2scaf the matrix must hold exactly sum(T) datapoints");
 		ABW_LAUNCH(ctx, k_tab_fill_dp2scaf, abw_div_up(S, 256), 256, 0, s->dp_first.p, S, N, s->dp2scaf.p);
 	}
 	ABW_LAUNCH(ctx, k_tab_scaffolds, abw_div_up(S, 256), 256, 0, s->dp_first.p, d_T.p, d_len.p, s->scgmask.p, S, W, s->prm.fraction_dps_in, s->rows.p, s->has_scg.p,
 	           d_scg_flag.p, s->scaf_list[0].p, d_rs.p);
 	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, d_scg_flag.p, d_scg_before.p, S, d_total.p));
+	// ---- per-dimension order, classes, elements; dimensions are processed in chunks to bound scratch memory
+	for(int b = 0; b < 2; b++)
+		ABW_CUDA(ctx, s->E[b].alloc((size_t)D * N));
+	// scratch of the sort is bounded by a fixed budget (the driver is not asked for the free memory: the context caches its blocks, and the query
+	// takes driver-wide locks); ABW_SORT_SCRATCH_GB overrides the 16 GB default
+	const uint64_t per_dim = N * (8 + 8 + 4 + 4 + 1) + 4096;
+	uint64_t budget = 16ull << 30;
+	if(const char* e = getenv("ABW_SORT_SCRATCH_GB"))
+		budget = std::max<uint64_t>(1, strtoull(e, nullptr, 10)) << 30;
+	const uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(D, budget / per_dim));
+	DevBuf<unsigned long long> keys, keys_tmp;
+	DevBuf<uint32_t> vals, vals_tmp, flip_pos, or_and;
+	DevBuf<uint8_t> cls;
+	DevBuf<int> flags;                                     // [0] a value is not an exact multiple of 0.001, [1] NaN
+	ABW_CUDA(ctx, flags.alloc(2));
+	ABW_CUDA(ctx, or_and.alloc(128));
+	ABW_CUDA(ctx, keys.alloc((size_t)chunk * N));
+	ABW_CUDA(ctx, keys_tmp.alloc((size_t)chunk * N));
+	ABW_CUDA(ctx, vals.alloc((size_t)chunk * N));
+	ABW_CUDA(ctx, vals_tmp.alloc((size_t)chunk * N));
+	ABW_CUDA(ctx, cls.alloc((size_t)chunk * N));
+	uint32_t* const keys32 = reinterpret_cast<uint32_t*>(keys.p);
+	uint32_t* const keys32_tmp = reinterpret_cast<uint32_t*>(keys_tmp.p);
+	auto launch_keys32 = [&](uint32_t d0, uint32_t nd) -> int {
+		ABW_CUDA(ctx, cudaMemsetAsync(flags.p, 0, 2 * sizeof(int), ctx->stream));
+		ABW_LAUNCH(ctx, k_fill_or_and, 1, 64, 0, or_and.p, 64u);
+		ABW_LAUNCH(ctx, (k_keys<true, uint32_t>), dim3(abw_div_up(N, 32), abw_div_up(nd, 32)), 256, 0, s->vsrc, N, d0, nd, keys32, vals.p, flags.p, or_and.p);
+		return ABW_OK;
+	};
+	ABW_CHECK(launch_keys32(0, std::min(chunk, D)));
+	// ---- the one host wait: tables, root statistics, SCG count, key statistics of the first chunk
 	RootStats h_rs;
-	uint64_t h_K = 0;
+	uint64_t h_K = 0, sumT = N;
+	int h_flags[2] = {0, 0};
+	uint32_t h_or_and[128];
 	ABW_CUDA(ctx, abw_fetch(ctx, &h_rs, d_rs.p, sizeof(RootStats)));
 	ABW_CUDA(ctx, abw_fetch(ctx, &h_K, d_total.p, sizeof(uint64_t)));
+	if(!have_dp2scaf)
+		ABW_CUDA(ctx, abw_fetch(ctx, &sumT, s->dp_first.p + S, sizeof(uint64_t)));
+	ABW_CUDA(ctx, abw_fetch(ctx, h_flags, flags.p, sizeof(h_flags)));
+	ABW_CUDA(ctx, abw_fetch(ctx, h_or_and, or_and.p, sizeof(h_or_and)));
 	ABW_CUDA(ctx, abw_sync(ctx));
+	if(sumT != N)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: without dp2scaf the matrix must hold exactly sum(T) datapoints");
 	if(h_rs.err & TB_ERR_RANGE)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: dp2scaf entry out of range");
 	if(h_rs.err & TB_ERR_ORDER)
@@ -2315,110 +2355,47 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: sum of T over scaffolds must be below 2^31");
 	s->K = (uint32_t)h_K;
 	const uint64_t K = s->K;
+	tr.mark("tables and first keys");
 	ABW_CUDA(ctx, d_scg_scafs.alloc(std::max<uint64_t>(K, 1)));
 	ABW_LAUNCH(ctx, k_tab_scg, abw_div_up(S, 256), 256, 0, d_scg_flag.p, d_scg_before.p, S, d_scg_index.p, d_scg_scafs.p);
-	tr.mark("tables on the device");
-
-	// ---- values, column major on the device (datapoint i lives in row row_of_dp[i] of the caller's matrix)
-	ABW_CUDA(ctx, s->values.alloc((size_t)D * N));
-	{
-		DevBuf<uint64_t> d_rowidx;
-		if(h_row_of_dp) {
-			for(uint64_t i = 0; i < N; i++)
-				if(h_row_of_dp[i] >= nrows)
-					return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: row_of_dp entry out of range");
-			std::vector<uint64_t> v(h_row_of_dp, h_row_of_dp + N);
-			ABW_CHECK(upload(ctx, d_rowidx, v));
-		}
-		DevBuf<double> tmp;
-		const double* src = values;
-		if(layout == ABW_LAYOUT_COLMAJOR && !h_row_of_dp) {
-			ABW_CUDA(ctx, cudaMemcpy2DAsync(s->values.p, N * sizeof(double), values, ld * sizeof(double), N * sizeof(double), D,
-			                                values_on_device? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-		}
-		else {
-			if(!values_on_device) {
-				const uint64_t count = (layout == ABW_LAYOUT_ROWMAJOR)? nrows * ld : (uint64_t)D * ld;
-				ABW_CUDA(ctx, tmp.alloc(count));
-				ABW_CUDA(ctx, cudaMemcpyAsync(tmp.p, values, sizeof(double) * count, cudaMemcpyHostToDevice, ctx->stream));
-				src = tmp.p;
-			}
-			if(layout == ABW_LAYOUT_ROWMAJOR) {
-				dim3 grid(abw_div_up(N, 32), abw_div_up(D, 32)), block(32, 8);
-				ABW_LAUNCH(ctx, k_transpose_in, grid, block, 0, src, ld, N, 0u, D, (const uint64_t*)(h_row_of_dp? d_rowidx.p : nullptr), s->values.p);
-			}
-			else {
-				dim3 grid(abw_div_up(N, 256), D);
-				ABW_LAUNCH(ctx, k_gather_columns, grid, 256, 0, src, ld, N, (const uint64_t*)d_rowidx.p, s->values.p);
-			}
-		}
-		ABW_CUDA(ctx, abw_sync(ctx));
-	}
-	tr.mark("values to column major");
-	// ---- per-dimension order, classes, elements; dimensions are processed in chunks to bound scratch memory
-	for(int b = 0; b < 2; b++) {
-		ABW_CUDA(ctx, s->E[b].alloc((size_t)D * N));
+	for(int b = 0; b < 2; b++)
 		ABW_CUDA(ctx, s->scg_list[b].alloc((size_t)D * K));
-	}
-	// scratch of the sort is bounded by a fixed budget (the driver is not asked for the free memory: the context caches its blocks, and the query
-	// takes driver-wide locks); ABW_SORT_SCRATCH_GB overrides the 16 GB default
-	const uint64_t per_dim = N * (8 + 8 + 4 + 4 + 1) + 4096;
-	uint64_t budget = 16ull << 30;
-	if(const char* e = getenv("ABW_SORT_SCRATCH_GB"))
-		budget = std::max<uint64_t>(1, strtoull(e, nullptr, 10)) << 30;
-	uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(D, budget / per_dim));
-	DevBuf<unsigned long long> keys, keys_tmp;
-	DevBuf<uint32_t> vals, vals_tmp, flip_pos;
-	DevBuf<uint8_t> cls;
-	DevBuf<int> nan_flag, inexact;
-	ABW_CUDA(ctx, inexact.alloc(1));
-	DevBuf<uint32_t> or_and;
-	std::vector<uint32_t> h_or_and;
-	ABW_CUDA(ctx, or_and.alloc((size_t)2 * chunk));
-	ABW_CUDA(ctx, keys.alloc((size_t)chunk * N));
-	ABW_CUDA(ctx, keys_tmp.alloc((size_t)chunk * N));
-	ABW_CUDA(ctx, vals.alloc((size_t)chunk * N));
-	ABW_CUDA(ctx, vals_tmp.alloc((size_t)chunk * N));
-	ABW_CUDA(ctx, cls.alloc((size_t)chunk * N));
 	ABW_CUDA(ctx, flip_pos.alloc((size_t)D * K));
-	ABW_CUDA(ctx, nan_flag.alloc(1));
-	ABW_CUDA(ctx, cudaMemsetAsync(nan_flag.p, 0, sizeof(int), ctx->stream));
 	for(uint32_t d0 = 0; d0 < D; d0 += chunk) {
 		const uint32_t nd = std::min(chunk, D - d0);
-		dim3 grid(abw_div_up(N, 256), nd);
-		const double* vchunk = s->values.p + (uint64_t)d0 * N;
-		ABW_LAUNCH(ctx, k_rank_class, grid, 256, 0, vchunk, N, nd, s->dp2scaf.p, s->dp_first.p, s->rows.p, s->has_scg.p, s->strategy, s->prm.fraction_dps_in, cls.p);
-		uint32_t* keys32 = reinterpret_cast<uint32_t*>(keys.p);
-		uint32_t* keys32_tmp = reinterpret_cast<uint32_t*>(keys_tmp.p);
-		ABW_CUDA(ctx, cudaMemsetAsync(inexact.p, 0, sizeof(int), ctx->stream));
-		ABW_LAUNCH(ctx, k_fill_or_and, abw_div_up(nd, 256), 256, 0, or_and.p, nd);
-		ABW_LAUNCH(ctx, k_make_keys_milli, grid, 256, 0, vchunk, N, nd, keys32, vals.p, inexact.p, or_and.p);
-		int h_inexact = 0;
-		h_or_and.resize((size_t)2 * nd);
-		ABW_CUDA(ctx, abw_fetch(ctx, &h_inexact, inexact.p, sizeof(int)));
-		ABW_CUDA(ctx, abw_fetch(ctx, h_or_and.data(), or_and.p, sizeof(uint32_t) * 2 * nd));
-		ABW_CUDA(ctx, abw_sync(ctx));
+		const dim3 grid(abw_div_up(N, 256), nd);
+		if(d0 > 0) {
+			ABW_CHECK(launch_keys32(d0, nd));
+			ABW_CUDA(ctx, abw_fetch(ctx, h_flags, flags.p, sizeof(h_flags)));
+			ABW_CUDA(ctx, abw_fetch(ctx, h_or_and, or_and.p, sizeof(h_or_and)));
+			ABW_CUDA(ctx, abw_sync(ctx));
+		}
 		uint32_t all_or = 0u, all_and = ~0u;                  // over all dimensions of the chunk: one digit plan for the batch
-		for(uint32_t d = 0; d < nd; d++) {
-			all_or |= h_or_and[2 * d];
-			all_and &= h_or_and[2 * d + 1];
+		for(int k = 0; k < 64; k++) {
+			all_or |= h_or_and[2 * k];
+			all_and &= h_or_and[2 * k + 1];
 		}
 		uint32_t* fp = (s->strategy == ABW_SENS_SPEC && K > 0)? flip_pos.p + (uint64_t)d0 * K : nullptr;
-		if(!h_inexact) {
+		if(!h_flags[0]) {
+			ABW_LAUNCH(ctx, k_rank_class<uint32_t>, grid, 256, 0, keys32, N, nd, s->dp2scaf.p, s->dp_first.p, s->rows.p, s->has_scg.p, s->strategy, s->prm.fraction_dps_in, cls.p);
 			ABW_CHECK(abw_radix_sort_pairs_u32_varying(ctx, keys32, keys32_tmp, vals.p, vals_tmp.p, N, nd, N, (unsigned long long)(all_or ^ all_and)));
 			ABW_LAUNCH(ctx, k_pack_elements<uint32_t>, grid, 256, 0, keys32, vals.p, N, nd, s->dp2scaf.p, cls.p, s->E[0].p + (uint64_t)d0 * N, d_scg_index.p, fp, K);
 		}
 		else {
-			ABW_LAUNCH(ctx, k_make_keys, grid, 256, 0, vchunk, N, nd, keys.p, vals.p, nan_flag.p);
+			// arbitrary doubles: 64-bit order-preserving keys
+			ABW_LAUNCH(ctx, (k_keys<false, unsigned long long>), dim3(abw_div_up(N, 32), abw_div_up(nd, 32)), 256, 0, s->vsrc, N, d0, nd, keys.p, vals.p, flags.p,
+			           (uint32_t*)nullptr);
+			ABW_LAUNCH(ctx, k_rank_class<unsigned long long>, grid, 256, 0, keys.p, N, nd, s->dp2scaf.p, s->dp_first.p, s->rows.p, s->has_scg.p, s->strategy,
+			           s->prm.fraction_dps_in, cls.p);
 			ABW_CHECK(abw_radix_sort_pairs_u64(ctx, (uint64_t*)keys.p, (uint64_t*)keys_tmp.p, vals.p, vals_tmp.p, N, nd, N, 64));
 			ABW_LAUNCH(ctx, k_pack_elements<unsigned long long>, grid, 256, 0, keys.p, vals.p, N, nd, s->dp2scaf.p, cls.p, s->E[0].p + (uint64_t)d0 * N, d_scg_index.p, fp, K);
+			int h_nan[2] = {0, 0};
+			ABW_CUDA(ctx, abw_fetch(ctx, h_nan, flags.p, sizeof(h_nan)));
+			ABW_CUDA(ctx, abw_sync(ctx));
+			if(h_nan[1])
+				return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: NaN in the feature matrix (comp_by_value is not a strict weak order on NaN)");
 		}
 	}
-	int h_nan = 0;
-	ABW_CUDA(ctx, abw_fetch(ctx, &h_nan, nan_flag.p, sizeof(int)));
-	ABW_CUDA(ctx, abw_sync(ctx));
-	if(h_nan)
-		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: NaN in the feature matrix (comp_by_value is not a strict weak order on NaN)");
 	tr.mark("classes, sort, elements");
 	keys.release(); keys_tmp.release(); vals.release(); vals_tmp.release(); cls.release();
 	// ---- per-dimension flip list: every scaffold that can flip has exactly one class-1 element per dimension
@@ -2462,9 +2439,81 @@ int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_o
 	ABW_CUDA(ctx, cudaMemsetAsync(s->low.p, 0, sizeof(uint32_t) * S, ctx->stream));
 	ABW_CUDA(ctx, cudaMemsetAsync(s->scaf_member.p, 0, sizeof(uint32_t) * S, ctx->stream));
 	ABW_CUDA(ctx, cudaMemsetAsync(s->scaf_final.p, 0, sizeof(uint32_t) * S, ctx->stream));
-	ABW_CUDA(ctx, abw_sync(ctx));
 	tr.mark("root cluster");
+	return ABW_OK;                                         // later entry points work in the order of the context stream: no wait here
+}
+
+// abw_search_create: the caller's host arrays go to the device, the matrix is read where it lies (a host matrix is uploaded once, in its own layout)
+int search_build(abw_ctx* ctx, abw_search* s, const double* values, int values_on_device, int layout, uint64_t ld, uint64_t nrows, const uint64_t* h_row_of_dp,
+                 const uint32_t* h_dp2scaf, const uint32_t* h_T, const uint64_t* h_len, const uint64_t* h_scgmask)
+{
+	const uint64_t N = s->N;
+	const uint32_t D = s->D, S = s->S, W = s->W;
+	Trace tr(ctx->stream, "create");
+	ABW_CUDA(ctx, s->dp2scaf.alloc(N));
+	if(h_dp2scaf)
+		ABW_CUDA(ctx, cudaMemcpyAsync(s->dp2scaf.p, h_dp2scaf, sizeof(uint32_t) * N, cudaMemcpyHostToDevice, ctx->stream));
+	ABW_CUDA(ctx, s->scgmask.alloc((size_t)S * W));
+	if(h_scgmask)
+		ABW_CUDA(ctx, cudaMemcpyAsync(s->scgmask.p, h_scgmask, sizeof(uint64_t) * (size_t)S * W, cudaMemcpyHostToDevice, ctx->stream));
+	else
+		ABW_CUDA(ctx, cudaMemsetAsync(s->scgmask.p, 0, sizeof(uint64_t) * (size_t)S * W, ctx->stream));
+	DevBuf<uint32_t> d_T;
+	DevBuf<uint64_t> d_len;
+	ABW_CUDA(ctx, d_T.alloc(S));
+	ABW_CUDA(ctx, d_len.alloc(S));
+	ABW_CUDA(ctx, cudaMemcpyAsync(d_T.p, h_T, sizeof(uint32_t) * S, cudaMemcpyHostToDevice, ctx->stream));
+	ABW_CUDA(ctx, cudaMemcpyAsync(d_len.p, h_len, sizeof(uint64_t) * S, cudaMemcpyHostToDevice, ctx->stream));
+	s->vsrc.p = values; s->vsrc.ld = ld; s->vsrc.layout = layout; s->vsrc.rowidx = nullptr;
+	if(h_row_of_dp) {
+		for(uint64_t i = 0; i < N; i++)
+			if(h_row_of_dp[i] >= nrows)
+				return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: row_of_dp entry out of range");
+		ABW_CUDA(ctx, s->rowidx.alloc(N));
+		ABW_CUDA(ctx, cudaMemcpyAsync(s->rowidx.p, h_row_of_dp, sizeof(uint64_t) * N, cudaMemcpyHostToDevice, ctx->stream));
+		s->vsrc.rowidx = s->rowidx.p;
+	}
+	if(!values_on_device) {
+		const uint64_t count = (layout == ABW_LAYOUT_ROWMAJOR)? nrows * ld : (uint64_t)D * ld;
+		ABW_CUDA(ctx, s->values.alloc(count));
+		ABW_CUDA(ctx, cudaMemcpyAsync(s->values.p, values, sizeof(double) * count, cudaMemcpyHostToDevice, ctx->stream));
+		s->vsrc.p = s->values.p;
+	}
+	tr.mark("uploads");
+	ABW_CHECK(search_build_common(ctx, s, d_T, d_len, h_dp2scaf != nullptr, tr));
+	// the caller's host arrays (pageable memory: the driver staged them) may be reused as soon as the call returns; the uploads are complete then
+	// because the build waited for the stream after they were enqueued
 	return ABW_OK;
+}
+
+// one thread per scaffold of the assembly: windows per scaffold, and whether ScafDpData keeps it (at least two windows, ScafDpData.cpp:92-93)
+__global__ void k_feat_counts(const uint64_t* __restrict__ seg_first, uint32_t nscaf, uint32_t* __restrict__ keep, uint32_t* __restrict__ cnt)
+{
+	const uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(sidx >= nscaf)
+		return;
+	const uint64_t c = seg_first[sidx + 1] - seg_first[sidx];
+	const bool k = c >= 2;
+	keep[sidx] = k? 1u : 0u;
+	cnt[sidx] = k? (uint32_t)c : 0u;
+}
+__global__ void k_feat_gather(const uint64_t* __restrict__ seg_first, uint32_t nscaf, const uint32_t* __restrict__ keep, const uint64_t* __restrict__ newidx,
+                              const uint64_t* __restrict__ dpfirst, const uint32_t* __restrict__ cnt, const uint64_t* __restrict__ len_in, const uint64_t* __restrict__ mask_in,
+                              uint32_t W, uint32_t* __restrict__ T_out, uint64_t* __restrict__ len_out, uint64_t* __restrict__ mask_out, uint64_t* __restrict__ rowidx,
+                              uint32_t* __restrict__ kept_out)
+{
+	const uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(sidx >= nscaf || !keep[sidx])
+		return;
+	const uint64_t ns = newidx[sidx];
+	T_out[ns] = cnt[sidx];
+	len_out[ns] = len_in[sidx];
+	for(uint32_t w = 0; w < W; w++)
+		mask_out[ns * W + w] = mask_in? mask_in[(uint64_t)sidx * W + w] : 0ull;
+	kept_out[ns] = sidx;
+	const uint64_t f = dpfirst[sidx], r0 = seg_first[sidx];
+	for(uint32_t j = 0; j < cnt[sidx]; j++)
+		rowidx[f + j] = r0 + j;
 }
 
 // Replaces the work-list loop abawaca.cpp:98-197.  The host enqueues level after level on the context stream and never waits for one: work sizes live in the
@@ -2693,7 +2742,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 		}
 		ABW_LAUNCH(ctx, k_level_jobs, 1, LV_THREADS, 0, B, cur, world, Cb, s->strategy, prm, s->dim_offset, D, s->E[cur].p, N, d_stats, d_value_key, d_child_never, W);
 		ABW_LAUNCH(ctx, k_count_low, g_small, 256, 0, s->E[cur].p, N, B, cur, s->dim_offset, s->low.p);
-		ABW_LAUNCH(ctx, k_scaf_sides, g_small * 2, SS_CHUNK, 0, s->scaf_list[cur].p, B, cur, s->dim_offset, s->rows.p, s->low.p, s->dp_first.p, s->values.p, N, s->scgmask.p, W,
+		ABW_LAUNCH(ctx, k_scaf_sides, g_small * 2, SS_CHUNK, 0, s->scaf_list[cur].p, B, cur, s->dim_offset, s->rows.p, s->low.p, s->dp_first.p, s->vsrc, s->scgmask.p, W,
 		           s->strategy, prm.fraction_dps_in, d_side, d_new_assigned, d_stats, d_child_never, d_value_key);
 		if(world > 1) {
 			// every quantity is non-zero on exactly one rank (the owner of the winning dimension): a sum is a gather
@@ -2817,6 +2866,85 @@ int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, 
 	EventTimer tm(ctx->stream, ctx->profiling);
 	tm.start();
 	int rc = search_build(ctx, s, values, values_on_device, layout, ld, nrows, h_row_of_dp, h_dp2scaf, h_T, h_len, (W > 0)? h_scgmask : nullptr);
+	s->prof.build_ms = tm.stop();
+	if(rc != ABW_OK) {
+		delete s;
+		return rc;
+	}
+	*out = s;
+	return ABW_OK;
+}
+
+// The search problem of a feature build without a trip through the host: T = windows per scaffold, scaffolds with fewer than two windows dropped
+// (ScafDpData.cpp:92-93), datapoints = the rows of the kept scaffolds in row order.
+int abw_search_create_from_features(abw_ctx* ctx, const abw_segments* g, const double* d_rows, uint64_t ld, uint32_t D, const uint64_t* h_len, const uint64_t* h_scgmask,
+                                    uint32_t W, const abw_params* params, int strategy, uint32_t* S_out, uint64_t* N_out, uint32_t* h_kept, abw_search** out)
+{
+	if(!ctx || !g || !d_rows || !h_len || !out || (W > 0 && !h_scgmask))
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create_from_features: null argument");
+	if(strategy != ABW_SENS_SPEC && strategy != ABW_SPLIT_SCAFS)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create_from_features: unknown strategy");
+	if(W > SCG_WMAX)
+		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: at most 512 distinct SCG names (W <= 8)");
+	if(D == 0 || ld < D || g->nscaf == 0 || g->nseg == 0)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create_from_features: empty problem or row stride too small");
+	ABW_ENTER(ctx);
+	const uint32_t nscaf = g->nscaf, Wd = (W == 0)? 1 : W;
+	abw_search* s = new abw_search();
+	s->ctx = ctx;
+	s->D = D; s->W = Wd;
+	s->strategy = strategy;
+	if(params)
+		s->prm = *params;
+	else
+		abw_default_params(&s->prm);
+	EventTimer tm(ctx->stream, ctx->profiling);
+	tm.start();
+	int rc = [&]() -> int {
+		Trace tr(ctx->stream, "create");
+		DevBuf<uint32_t> keep, cnt, d_T, d_kept;
+		DevBuf<uint64_t> newidx, dpfirst, totals, len_in, mask_in, d_len;
+		ABW_CUDA(ctx, keep.alloc(nscaf));
+		ABW_CUDA(ctx, cnt.alloc(nscaf));
+		ABW_CUDA(ctx, newidx.alloc(nscaf));
+		ABW_CUDA(ctx, dpfirst.alloc(nscaf));
+		ABW_CUDA(ctx, totals.alloc(2));
+		ABW_CUDA(ctx, len_in.alloc(nscaf));
+		ABW_CUDA(ctx, cudaMemcpyAsync(len_in.p, h_len, sizeof(uint64_t) * nscaf, cudaMemcpyHostToDevice, ctx->stream));
+		if(W > 0) {
+			ABW_CUDA(ctx, mask_in.alloc((size_t)nscaf * W));
+			ABW_CUDA(ctx, cudaMemcpyAsync(mask_in.p, h_scgmask, sizeof(uint64_t) * (size_t)nscaf * W, cudaMemcpyHostToDevice, ctx->stream));
+		}
+		ABW_LAUNCH(ctx, k_feat_counts, abw_div_up(nscaf, 256), 256, 0, g->seg_first.p, nscaf, keep.p, cnt.p);
+		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, keep.p, newidx.p, nscaf, totals.p));
+		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, cnt.p, dpfirst.p, nscaf, totals.p + 1));
+		uint64_t h_tot[2] = {0, 0};
+		ABW_CUDA(ctx, abw_fetch(ctx, h_tot, totals.p, sizeof(h_tot)));
+		ABW_CUDA(ctx, abw_sync(ctx));
+		const uint64_t S = h_tot[0], N = h_tot[1];
+		if(S == 0 || N == 0)
+			return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create_from_features: no scaffold has two windows");
+		if(N >= (1ull << 31) || S >= (1u << EL_SCAF_BITS))
+			return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: at most 2^31-1 datapoints and 2^27-1 scaffolds per device");
+		s->N = N; s->S = (uint32_t)S;
+		ABW_CUDA(ctx, d_T.alloc(S));
+		ABW_CUDA(ctx, d_len.alloc(S));
+		ABW_CUDA(ctx, d_kept.alloc(S));
+		ABW_CUDA(ctx, s->scgmask.alloc((size_t)S * Wd));
+		ABW_CUDA(ctx, s->rowidx.alloc(N));
+		ABW_CUDA(ctx, s->dp2scaf.alloc(N));
+		ABW_LAUNCH(ctx, k_feat_gather, abw_div_up(nscaf, 256), 256, 0, g->seg_first.p, nscaf, keep.p, newidx.p, dpfirst.p, cnt.p, len_in.p, (const uint64_t*)mask_in.p, Wd,
+		           d_T.p, d_len.p, s->scgmask.p, s->rowidx.p, d_kept.p);
+		if(h_kept)
+			ABW_CUDA(ctx, abw_fetch(ctx, h_kept, d_kept.p, sizeof(uint32_t) * S));     // handed over at the wait inside the build
+		s->vsrc.p = d_rows; s->vsrc.ld = ld; s->vsrc.layout = ABW_LAYOUT_ROWMAJOR;
+		s->vsrc.rowidx = (S == nscaf)? nullptr : s->rowidx.p;                          // nothing dropped: datapoint i is row i
+		tr.mark("problem from the feature build");
+		ABW_CHECK(search_build_common(ctx, s, d_T, d_len, false, tr));
+		if(S_out) *S_out = (uint32_t)S;
+		if(N_out) *N_out = N;
+		return ABW_OK;
+	}();
 	s->prof.build_ms = tm.stop();
 	if(rc != ABW_OK) {
 		delete s;

@@ -421,6 +421,36 @@ def search(ctx: capi.Context, values, dp2scaf, T, length, scgmask, params=None, 
     t0 = time.perf_counter()
     ctx.check(L.abw_search_create(ctx.h, vptr, 1 if values_on_device else 0, layout, ld, nrows, capi._p(row_of_dp), N, D, capi._p(dp2scaf), S, capi._p(T), capi._p(length),
                                   capi._p(scgmask), W, C.byref(p), strategy, C.byref(h)))
+    return _run_search(ctx, h, N, S, D, p, t0, want_bins, timings, collectives, dim_offset, D_total, scaf_gc, scaf_cvg, buffers)
+
+
+def search_features(ctx: capi.Context, fb: "FeatureBuild", length, scgmask, params=None, strategy=capi.SENS_SPEC, want_bins=True, timings=None, buffers=None):
+    """The split search straight from a feature build that is still on the device (abw_search_create_from_features): windows per scaffold, the scaffolds
+    ScafDpData would drop and the row index are derived on the device.  length / scgmask: per scaffold of the ASSEMBLY.
+    Returns (SearchResult, kept) -- kept[i] = assembly index of scaffold i of the result."""
+    L = ctx.lib
+    p = params or capi.default_params()
+    length = np.ascontiguousarray(length, dtype=np.uint64)
+    scgmask = np.ascontiguousarray(scgmask, dtype=np.uint64)
+    if scgmask.ndim == 1:
+        scgmask = scgmask.reshape(-1, 1)
+    W = scgmask.shape[1]
+    kept = buffers.get("kept") if buffers is not None else None
+    if kept is None or kept.size < fb.nscaf:
+        kept = np.zeros(fb.nscaf, dtype=np.uint32)
+        if buffers is not None:
+            buffers["kept"] = kept
+    S, N = C.c_uint32(), C.c_uint64()
+    h = C.c_void_p()
+    t0 = time.perf_counter()
+    ctx.check(L.abw_search_create_from_features(ctx.h, fb.segs, C.c_void_p(fb.d_rows), fb.ncols, fb.ncols, capi._p(length), capi._p(scgmask), W, C.byref(p), strategy,
+                                                C.byref(S), C.byref(N), capi._p(kept), C.byref(h)))
+    res = _run_search(ctx, h, int(N.value), int(S.value), fb.ncols, p, t0, want_bins, timings, None, 0, None, None, None, buffers)
+    return res, kept[:S.value]
+
+
+def _run_search(ctx, h, N, S, D, p, t0, want_bins, timings, collectives, dim_offset, D_total, scaf_gc, scaf_cvg, buffers):
+    L = ctx.lib
     t1 = time.perf_counter()
     try:
         if scaf_gc is not None:

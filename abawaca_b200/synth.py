@@ -62,10 +62,13 @@ class Metagenome:
 def make_metagenome(n_scaffolds, n_samples, n_genomes, seed, *, min_len=4000, mean_extra=6000, max_len=200000,
                     read_len=150, cov_lo=0.5, cov_hi=16.0, n_run_frac=0.005, n_scg=51, scg_p=0.9,
                     bad_read_frac=0.03, q6_reads=False, shuffle_reads=False, with_reads=True,
-                    gc_lo=0.25, gc_hi=0.75, tri_sigma=0.6, shard=None) -> Metagenome:
+                    gc_lo=0.25, gc_hi=0.75, tri_sigma=0.6, shard=None, bimodal_frac=0.0, bimodal_factor=4.0) -> Metagenome:
     """shard: when given, the genome models (composition, coverage) still come from `seed` alone, but the scaffolds, reads and gene
     placements are drawn from (seed, shard): several shards are then pieces of ONE community, which is how bench.py builds the
-    N-GPU workload (every rank generates only its own scaffolds)."""
+    N-GPU workload (every rank generates only its own scaffolds).
+    bimodal_frac: that share of the genomes gets two coverage modes (half of their scaffolds are covered bimodal_factor times deeper in every
+    sample) while their single-copy genes stay spread over all their scaffolds: a clean separation INSIDE one genome, which only the SCG test of
+    ClusterQuality::is_split_better (disjoint SCG sets on the two sides) turns down.  Drawn from its own generator: 0 leaves every other set as it was."""
     rng = np.random.default_rng(seed)
     # genome models
     gc = rng.uniform(gc_lo, gc_hi, n_genomes)
@@ -113,11 +116,17 @@ def make_metagenome(n_scaffolds, n_samples, n_genomes, seed, *, min_len=4000, me
             p = int(rng.integers(0, L - run))
             seq[int(offsets[i]) + p:int(offsets[i]) + p + run] = ord("N")
 
+    cov_mult = np.ones(n_scaffolds)
+    if bimodal_frac > 0:
+        rng2 = np.random.default_rng([seed, 424243] + ([int(shard)] if shard is not None else []))
+        bimodal = rng2.random(n_genomes) < bimodal_frac
+        deep = rng2.random(n_scaffolds) < 0.5
+        cov_mult = np.where(bimodal[genome] & deep, bimodal_factor, 1.0)
     # reads, one record stream per sample, scaffold-major with random positions
     reads = []
     if with_reads:
         for j in range(n_samples):
-            lam = cov[genome, j] * lengths / read_len
+            lam = cov[genome, j] * cov_mult * lengths / read_len
             n = np.floor(lam + rng.random(n_scaffolds)).astype(np.int64)
             if q6_reads and j == n_samples - 1:
                 extra = (lengths + 999) // 1000

@@ -386,19 +386,11 @@ def main():
             fb = pipeline.build_features(ctx, h_seq.numpy(), mg.offsets, h_compact, this_sample=0, timings=timings, overlap_h2d=True)
         if on_features is not None:
             on_features()
-        t_a = time.perf_counter()
-        seg_first = fb.seg_first_host()
-        t_b = time.perf_counter()
-        # ScafDpData.cpp:92-93: scaffolds with a single window are dropped
-        counts = np.diff(seg_first.astype(np.int64))
-        if world == 1:
-            # rows that stay (None: all), windows per kept scaffold; dp2scaf is derived on the device from T
-            row_of_dp, T, kept, ndps_total = pipeline.search_rows_from_counts(counts)
-            if kept is None:
-                kept = slice(None)
-        if timings is not None:
-            timings["segments_host_ms"] = 1000.0 * (t_b - t_a)
-            timings["search_problem_ms"] = 1000.0 * (time.perf_counter() - t_b)
+        if world > 1:
+            t_a = time.perf_counter()
+            counts = np.diff(fb.seg_first_host().astype(np.int64))         # windows per scaffold: the ranks exchange them (exchange())
+            if timings is not None:
+                timings["segments_host_ms"] = 1000.0 * (time.perf_counter() - t_a)
         if not resident:
             # the .lrn matrix goes back to the host (pinned buffers) in the end-to-end path, while the split search runs: as integer thousandths
             # (uint16 k-mer columns, uint32 coverage columns; abw_rows_to_milli), which is what the text writer prints anyway
@@ -412,8 +404,10 @@ def main():
             fb.segments_async(state["h_seg"][0].numpy().view(np.uint32), *[t.numpy().view(np.uint64) for t in state["h_seg"][1:]])   # the .names columns
             fb.rows_milli(out16=state["h_k16"].numpy().view(np.uint16), out32=state["h_k32"].numpy().view(np.uint32), wait=False)
         if world == 1:
-            res = pipeline.search(ctx, fb.d_rows, None, T, lengths[kept], masks[kept], layout=capi.LAYOUT_ROWMAJOR, values_on_device=True,
-                                  nrows=fb.nseg, D=fb.ncols, ld=fb.ncols, row_of_dp=row_of_dp, timings=timings, buffers=result_buffers)
+            # the search problem comes straight from the feature build on the device (windows per scaffold, scaffolds with a single window dropped as
+            # ScafDpData.cpp:92-93 does, row index): abw_search_create_from_features
+            res, kept = pipeline.search_features(ctx, fb, lengths, masks, timings=timings, buffers=result_buffers)
+            ndps_total = int(res.dp2cluster.size)
         else:
             x = exchange(fb, counts, timings)
             # dimension-sharded search: this rank sweeps columns [off, off+cnt) of every datapoint

@@ -221,10 +221,19 @@ int abw_d2h_async(abw_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
  * h_dp2scaf may be NULL when the matrix holds all T datapoints of every scaffold in scaffold order (N = sum of T, the reference's own flow).
  * The value matrix has nrows rows; datapoint i is row h_row_of_dp[i] of it (NULL: nrows = N and datapoint i is row i).
  * This is how the rows of scaffolds with a single window, which abawaca-build writes but ScafDpData drops, are skipped
- * without copying the matrix.  The all-inclusive cluster 1 (init_cluster, abawaca.cpp:242-251) is the root. */
+ * without copying the matrix.  The all-inclusive cluster 1 (init_cluster, abawaca.cpp:242-251) is the root.
+ * A matrix in device memory (values_on_device) is read where it lies, also by abw_search_run (the separating value of a split is looked up in it):
+ * it must stay valid and unchanged until the search object is destroyed.  A host matrix is copied to the device once, in its own layout. */
 int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, int layout, uint64_t ld, uint64_t nrows, const uint64_t* h_row_of_dp,
                       uint64_t N, uint32_t D, const uint32_t* h_dp2scaf, uint32_t S, const uint32_t* h_T, const uint64_t* h_len, const uint64_t* h_scgmask, uint32_t W,
                       const abw_params* params, int strategy, abw_search** out);
+/* The same for the matrix of a feature build that is still on the device (abw_kmer_features / abw_coverage* wrote d_rows, one row per window of g):
+ * T = windows per scaffold, scaffolds with fewer than two windows are dropped as ScafDpData does (ScafDpData.cpp:92-93), the datapoints are the rows of
+ * the kept scaffolds -- all derived on the device, no trip through the host.  h_len / h_scgmask are indexed by the scaffolds of the ASSEMBLY [nscaf].
+ * *S_out / *N_out: kept scaffolds and their datapoints; h_kept[0 .. *S_out) (room for nscaf entries, may be NULL): the assembly index of every kept
+ * scaffold, i.e. what scaffold i of the search results refers to. */
+int abw_search_create_from_features(abw_ctx* ctx, const abw_segments* g, const double* d_rows, uint64_t ld, uint32_t D, const uint64_t* h_len, const uint64_t* h_scgmask,
+                                    uint32_t W, const abw_params* params, int strategy, uint32_t* S_out, uint64_t* N_out, uint32_t* h_kept, abw_search** out);
 void abw_search_destroy(abw_search* s);
 
 typedef struct {

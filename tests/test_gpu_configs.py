@@ -3,8 +3,8 @@ unmodified reference, tests/test_oracle_vs_reference.py) finishes in seconds on 
 
   configs[2]  500k scaffolds x 20 samples, 128 genomes   ->  40 000 scaffolds, 20 samples, 128 genomes, reads thinned (deep tree: >= 9 levels)
   configs[3]  1M scaffolds x 50 samples, 256 genomes,
-              deep recursive splitting with SCG checks    ->  30 000 scaffolds, 50 samples, 256 similar genomes: imperfect separations, the SCG test
-                                                              (ClusterQuality::is_split_better) decides which candidates may win
+              deep recursive splitting with SCG checks    ->  20 000 scaffolds, 50 samples, 256 genomes, a third of them with two coverage modes: the SCG
+                                                              test (ClusterQuality::is_split_better) decides which candidates may win; hundreds of clusters
   configs[4]  k-mer feature build over 10 Mbp - 10 Gbp    ->  k-mer rows of a 100 Mbp assembly against the oracle; a 1 Gbp assembly against the oracle on a
                                                               random subsample of its scaffolds plus the sharding invariance (halves == whole)
 
@@ -79,8 +79,8 @@ def test_configs2_shape_500k_x_20_scaled(ctx, oracle):
 
 def test_configs3_shape_1m_x_50_scaled_scg_checks_decide(ctx, oracle):
     from abawaca_b200 import synth
-    mg = synth.make_metagenome(30000, 50, 256, synth.MASTER_SEED + 4, q6_reads=True, cov_lo=0.05, cov_hi=0.5, gc_lo=0.40, gc_hi=0.60, tri_sigma=0.12,
-                               mean_extra=9000)
+    # a third of the genomes carry two coverage modes (synth.make_metagenome: bimodal_frac): clean separations inside one genome that only the SCG test rejects
+    mg = synth.make_metagenome(20000, 50, 256, synth.MASTER_SEED + 4, q6_reads=True, cov_lo=0.05, cov_hi=0.8, mean_extra=9000, bimodal_frac=0.3)
     res, (vals, dp2scaf, T, length, mask), orecs, osc = _features_and_search(ctx, oracle, mg, use_compact=False)
     assert _depth(res.recs) >= 9
     # the SCG test is decisive on this set: without SCG information (every candidate passes on the size rule or fails it) the tree is a different one

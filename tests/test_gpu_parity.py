@@ -336,3 +336,28 @@ def test_cfg1_matches_reference_files(ctx):
     lines = [l.split("\t") for l in g["meta"]["scaf2cluster"].splitlines()]      # the real binary's scaf2cluster.txt (abawaca.cpp:205-210)
     assert [int(x[1]) for x in lines] == res.scaf2cluster.tolist()
     assert len(set(res.scaf2cluster.tolist()) - {0}) == 8
+
+
+def test_search_from_features_equals_the_explicit_problem(ctx):
+    """abw_search_create_from_features derives T, the dropped scaffolds (a single window, ScafDpData.cpp:92-93) and the row index on the device: same records
+    and bins as abw_search_create on the problem the host derives from the window table."""
+    from abawaca_b200 import capi, pipeline, synth
+    for min_len, seed in ((1500, 31), (4000, 32)):          # with and without dropped scaffolds
+        mg = synth.make_metagenome(1500, 3, 4, seed, min_len=min_len, mean_extra=3000)
+        fb = pipeline.build_features(ctx, mg.seq, mg.offsets, mg.reads, this_sample=0)
+        counts = np.diff(fb.seg_first_host().astype(np.int64))
+        assert ((counts < 2).any()) == (min_len == 1500)
+        keep, dp2scaf, T, kept = pipeline.search_problem_from_counts(counts)
+        length = np.diff(mg.offsets.astype(np.int64)).astype(np.uint64)
+        mask = mg.scg_masks()
+        p = capi.default_params()
+        p.min_reported_score = 0.0
+        a = pipeline.search(ctx, fb.d_rows, dp2scaf, T, length[kept], mask[kept], params=p, layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=fb.nseg,
+                            D=fb.ncols, ld=fb.ncols, row_of_dp=None if keep.all() else np.nonzero(keep)[0].astype(np.uint64))
+        b, kept_b = pipeline.search_features(ctx, fb, length, mask, params=p)
+        fb.close()
+        assert kept_b.tolist() == kept.tolist()
+        key = lambda r: (r.id, r.parent, r.ndps, r.nscafs, r.split, r.best.found, r.best.dim, r.best.value, r.best.a, r.best.b, r.child1, r.child2,   # noqa: E731
+                         r.child1_ndps, r.child2_ndps, r.child1_nscafs, r.child2_nscafs, r.child1_raw, r.child2_raw, r.total_size, r.scg_unique, r.scg_avg)
+        assert [key(r) for r in a.recs] == [key(r) for r in b.recs] and len(a.recs) > 1
+        assert a.scaf2cluster.tolist() == b.scaf2cluster.tolist() and a.dp2cluster.tolist() == b.dp2cluster.tolist()

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libabawaca_b200.so")
+LIB_PATH = os.environ.get("ABW_B200_LIB") or os.path.join(_HERE, "libabawaca_b200.so")      # the override is for A/B experiments with two builds
 _LIB = None
 
 NKMER = 180

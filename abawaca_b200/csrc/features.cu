@@ -16,31 +16,74 @@ namespace {
 // ---------------------------------------------------------------------------------------------------
 // pack
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t gather_bits_0_8_16_24(uint32_t v)   // bit0 of each byte -> 4 bits
+// bit 7 of every byte of x that equals the corresponding byte of c4 (exact: the classic zero-byte test on x ^ c4)
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t x, uint32_t c4)
 {
-	uint32_t t = (v | (v >> 7)) & 0x00030003u;
-	return (t | (t >> 14)) & 0xFu;
+	const uint32_t y = x ^ c4;
+	const uint32_t t = (y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+	return ~(t | y) & 0x80808080u;
 }
 
-// 4 ASCII characters -> 8 bits of 2-bit codes + 4 valid bits + 4 N bits (+ GC count, + lower-case-n flag)
+// 4 ASCII characters -> 8 bits of 2-bit codes + 4 valid bits + 4 N bits (+ GC count, + lower-case-n flag), in plain integer arithmetic (the SIMD-in-a-word
+// compare intrinsics are emulated on this architecture and made the kernel instruction bound).  Clearing bit 5 maps a-z onto A-Z (toupper() for letters,
+// String.cpp:44) and maps no other byte onto one of A C G T N; A|C and C|G differ in one bit each, so four byte-wise equality tests decide everything.
 __device__ __forceinline__ void classify4(uint32_t w, uint32_t& code8, uint32_t& valid4, uint32_t& n4, uint32_t& gc, uint32_t& bad)
 {
-	bad |= __vcmpeq4(w, 0x6E6E6E6Eu);                       // 'n' throws in the reference (String.cpp:47-49)
-	// toupper() for letters only (String.cpp:44); bytes outside a-z are left alone
-	uint32_t is_lower = __vcmpgeu4(w, 0x61616161u) & __vcmpleu4(w, 0x7A7A7A7Au);
-	uint32_t u = w & ~(is_lower & 0x20202020u);
-	uint32_t eA = __vcmpeq4(u, 0x41414141u), eC = __vcmpeq4(u, 0x43434343u), eG = __vcmpeq4(u, 0x47474747u), eT = __vcmpeq4(u, 0x54545454u);
-	uint32_t eN = __vcmpeq4(u, 0x4E4E4E4Eu);
-	uint32_t lo = (eC | eT) & 0x01010101u, hi = (eG | eT) & 0x01010101u;
-	uint32_t x = lo | (hi << 1);                            // one 2-bit code per byte
-	uint32_t y = (x | (x >> 6)) & 0x000F000Fu;
-	code8 = (y | (y >> 12)) & 0xFFu;
-	valid4 = gather_bits_0_8_16_24((eA | eC | eG | eT) & 0x01010101u);
-	n4 = gather_bits_0_8_16_24(eN & 0x01010101u);
-	gc += __popc((eC | eG) & 0x01010101u);
+	const uint32_t u = w & 0xDFDFDFDFu;
+	const uint32_t eAC = eq_bytes(u & 0xFDFDFDFDu, 0x41414141u);          // A (0x41) or C (0x43)
+	const uint32_t eCG = eq_bytes(u & 0xFBFBFBFBu, 0x43434343u);          // C (0x43) or G (0x47)
+	const uint32_t eT = eq_bytes(u, 0x54545454u), eN = eq_bytes(u, 0x4E4E4E4Eu);
+	bad |= eN & (w << 2);                                   // bit 5 set: 'n' throws in the reference (String.cpp:47-49)
+	const uint32_t lo = (eAC & eCG) | eT, hi = (eCG & ~eAC) | eT;         // A=0 C=1 G=2 T=3
+	const uint32_t x = (lo >> 7) | (hi >> 6);               // one 2-bit code per byte, 0 for every other character
+	code8 = (x * 0x01041040u) >> 24;                        // the four 2-bit fields side by side (the partial products do not overlap)
+	valid4 = (((eAC | eCG | eT) >> 7) * 0x01020408u) >> 24; // bit 0 of each byte -> 4 bits
+	n4 = ((eN >> 7) * 0x01020408u) >> 24;
+	gc += __popc(eCG);
 }
 
-// one warp per scaffold, one lane per 32-base unit
+// One warp per scaffold; per step a lane takes 16 consecutive bases (one 16-byte window of the text, read as two aligned 16-byte loads and shifted into
+// place -- the offset of a scaffold in the text is arbitrary, its place in the packed arrays is aligned), i.e. one packed word; a warp step is 512 bases
+// with fully coalesced loads and stores, two steps are in flight.  Lane pairs combine their 16 validity / N bits into one word.
+__device__ __forceinline__ void pack16(const unsigned char* __restrict__ ascii, uint64_t ascii_bytes, uint64_t a, uint32_t cnt, uint32_t& code, uint32_t& v16, uint32_t& n16,
+                                       uint32_t& nGC, uint32_t& bad)
+{
+	uint32_t w[4];
+	const uint64_t al = a & ~15ull;
+	if(cnt == 16 && al + 32 <= ascii_bytes) {
+		const uint4 A = __ldg(reinterpret_cast<const uint4*>(ascii + al)), B = __ldg(reinterpret_cast<const uint4*>(ascii + al + 16));
+		const uint32_t sh = (uint32_t)(a & 15), r8 = (sh & 3u) * 8u;
+		switch(sh >> 2) {                                   // uniform over the warp: every lane of a scaffold has the same misalignment
+		case 0: w[0] = __funnelshift_r(A.x, A.y, r8); w[1] = __funnelshift_r(A.y, A.z, r8); w[2] = __funnelshift_r(A.z, A.w, r8); w[3] = __funnelshift_r(A.w, B.x, r8); break;
+		case 1: w[0] = __funnelshift_r(A.y, A.z, r8); w[1] = __funnelshift_r(A.z, A.w, r8); w[2] = __funnelshift_r(A.w, B.x, r8); w[3] = __funnelshift_r(B.x, B.y, r8); break;
+		case 2: w[0] = __funnelshift_r(A.z, A.w, r8); w[1] = __funnelshift_r(A.w, B.x, r8); w[2] = __funnelshift_r(B.x, B.y, r8); w[3] = __funnelshift_r(B.y, B.z, r8); break;
+		default: w[0] = __funnelshift_r(A.w, B.x, r8); w[1] = __funnelshift_r(B.x, B.y, r8); w[2] = __funnelshift_r(B.y, B.z, r8); w[3] = __funnelshift_r(B.z, B.w, r8); break;
+		}
+	}
+	else {
+#pragma unroll
+		for(int i = 0; i < 4; i++) {
+			uint32_t x = 0;
+#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				const uint32_t k = i * 4 + j;
+				const uint32_t c = (k < cnt)? (uint32_t)ascii[a + k] : 0u;
+				x |= c << (8 * j);
+			}
+			w[i] = x;
+		}
+	}
+	code = 0; v16 = 0; n16 = 0;
+#pragma unroll
+	for(int i = 0; i < 4; i++) {
+		uint32_t c8, v4, n4;
+		classify4(w[i], c8, v4, n4, nGC, bad);
+		code |= c8 << (8 * i);
+		v16 |= v4 << (4 * i);
+		n16 |= n4 << (4 * i);
+	}
+}
+
 __global__ void __launch_bounds__(256) k_pack(const unsigned char* __restrict__ ascii, uint64_t ascii_bytes, const uint64_t* __restrict__ offsets,
                                               const uint64_t* __restrict__ base, uint32_t nscaf, uint32_t* __restrict__ packed, uint32_t* __restrict__ valid,
                                               uint32_t* __restrict__ nmask, unsigned long long* __restrict__ countN, unsigned long long* __restrict__ countGC,
@@ -49,54 +92,31 @@ __global__ void __launch_bounds__(256) k_pack(const unsigned char* __restrict__ 
 	const int lane = threadIdx.x & 31;
 	const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
 	for(uint64_t s = warp0; s < nscaf; s += nwarps) {
-		const uint64_t off = offsets[s], len = offsets[s + 1] - off, b0 = base[s], units = (base[s + 1] - b0) >> 5;
+		const uint64_t off = offsets[s], len = offsets[s + 1] - off, b0 = base[s], padded = base[s + 1] - b0;     // padded: a multiple of 128 bases
 		uint32_t nN = 0, nGC = 0, bad = 0;
-		for(uint64_t u = lane; u < units; u += 32) {
-			uint64_t p = u << 5;                            // first base of the unit within the scaffold
-			uint32_t code_lo = 0, code_hi = 0, v = 0, nm = 0;
-			if(p < len) {
-				uint64_t a = off + p;
-				uint32_t cnt = (uint32_t)min((uint64_t)32, len - p);
-				uint32_t w[8];
-				if(cnt == 32 && ((a & ~3ull) + 36 <= ascii_bytes)) {
-					const uint32_t* src = (const uint32_t*)(ascii + (a & ~3ull));
-					uint32_t sh = (uint32_t)(a & 3) * 8;
-					uint32_t t[9];
+		for(uint64_t p0 = 0; p0 < padded; p0 += 1024) {
+			uint32_t code[2], v16[2], n16[2];
 #pragma unroll
-					for(int i = 0; i < 9; i++)
-						t[i] = __ldg(src + i);
+			for(int h = 0; h < 2; h++) {
+				const uint64_t p = p0 + 512 * h + 16 * lane;     // first base of this lane's piece within the scaffold
+				code[h] = 0; v16[h] = 0; n16[h] = 0;
+				if(p < len)
+					pack16(ascii, ascii_bytes, off + p, (uint32_t)min((uint64_t)16, len - p), code[h], v16[h], n16[h], nGC, bad);
+			}
 #pragma unroll
-					for(int i = 0; i < 8; i++)
-						w[i] = __funnelshift_r(t[i], t[i + 1], sh);
-				}
-				else {
-#pragma unroll
-					for(int i = 0; i < 8; i++) {
-						uint32_t x = 0;
-#pragma unroll
-						for(int j = 0; j < 4; j++) {
-							uint32_t k = i * 4 + j;
-							uint32_t c = (k < cnt)? (uint32_t)ascii[a + k] : 0u;
-							x |= c << (8 * j);
-						}
-						w[i] = x;
+			for(int h = 0; h < 2; h++) {
+				const uint64_t p = p0 + 512 * h + 16 * lane;
+				// the neighbour's 16 bits complete the word of 32 positions (every lane takes part in the exchange)
+				const uint32_t v = v16[h] | (__shfl_down_sync(0xffffffffu, v16[h], 1) << 16), nm = n16[h] | (__shfl_down_sync(0xffffffffu, n16[h], 1) << 16);
+				nN += __popc(n16[h]);
+				if(p < padded) {
+					packed[(b0 + p) >> 4] = code[h];
+					if((lane & 1) == 0) {
+						valid[(b0 + p) >> 5] = v;
+						nmask[(b0 + p) >> 5] = nm;
 					}
 				}
-#pragma unroll
-				for(int i = 0; i < 8; i++) {
-					uint32_t c8, v4, n4;
-					classify4(w[i], c8, v4, n4, nGC, bad);
-					if(i < 4) code_lo |= c8 << (8 * i); else code_hi |= c8 << (8 * (i - 4));
-					v |= v4 << (4 * i);
-					nm |= n4 << (4 * i);
-				}
-				nN += __popc(nm);
 			}
-			uint64_t unit = (b0 >> 5) + u;
-			packed[2 * unit] = code_lo;
-			packed[2 * unit + 1] = code_hi;
-			valid[unit] = v;
-			nmask[unit] = nm;
 		}
 #pragma unroll
 		for(int o = 16; o > 0; o >>= 1) {

@@ -36,6 +36,11 @@ struct abw_ctx {
 	std::vector<Fetch> pending;
 	// progress words of a running split search, written by the device (mapped pinned memory, search.cu)
 	void* h_prog = nullptr;
+	// scratch of the one-pass prefix sums (scan_sort.cu): ticket, tile sums, tile prefixes, status words
+	void* scan_scratch = nullptr;
+	size_t scan_cap = 0;
+	uint32_t scan_epoch = 0;
+	uint64_t scan_tickets = 0;
 };
 
 // Small uploads (descriptors, job lists, tile tables) go through pinned memory so that cudaMemcpyAsync really is asynchronous.

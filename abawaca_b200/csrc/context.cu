@@ -257,6 +257,9 @@ void abw_ctx_destroy(abw_ctx* ctx)
 	if(ctx->h_prog)
 		cudaFreeHost(ctx->h_prog);
 	ctx->h_prog = nullptr;
+	if(ctx->scan_scratch)
+		cudaFree(ctx->scan_scratch);
+	ctx->scan_scratch = nullptr;
 	for(cudaEvent_t e : ctx->copy_events)
 		cudaEventDestroy(e);
 	if(ctx->copy_stream)

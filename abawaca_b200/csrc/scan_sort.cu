@@ -46,44 +46,23 @@ __device__ __forceinline__ uint64_t block_excl_scan_u64(uint64_t v, uint64_t* to
 	return r;
 }
 
+// One pass, one launch: tiles of SCAN_TILE values are handed out by ticket (a tile only ever waits for tiles drawn earlier by CTAs that are running);
+// a tile publishes its sum, looks back over its predecessors until it meets a published inclusive prefix, publishes its own and writes its values.
+// The per-context scratch (status words, sums, prefixes, ticket) is never cleared between scans: status words carry the number of the scan that wrote
+// them (epoch), and the ticket counter keeps running -- the host knows how many tickets every scan draws (its number of CTAs = tiles).
+constexpr uint32_t SC_EMPTY = 0, SC_AGG = 1, SC_PREFIX = 2;
 template <typename Tin>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const Tin* __restrict__ in, uint64_t n, uint64_t* __restrict__ block_sums)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(const Tin* __restrict__ in, uint64_t* __restrict__ out, uint64_t n, uint64_t* __restrict__ total_out,
+                                                              unsigned long long* __restrict__ ticket, unsigned long long ticket_base, uint32_t epoch,
+                                                              uint32_t* __restrict__ status, unsigned long long* __restrict__ aggs, unsigned long long* __restrict__ prefixes)
 {
 	__shared__ uint64_t sm[33];
-	uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
-	uint64_t s = 0;
-#pragma unroll
-	for(int i = 0; i < SCAN_ITEMS; i++)
-		if(base + i < n)
-			s += (uint64_t)in[base + i];
-	uint64_t total;
-	block_excl_scan_u64(s, &total, sm);
+	__shared__ unsigned long long sm_tile, sm_carry;
 	if(threadIdx.x == 0)
-		block_sums[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(1024) k_scan_block_sums(uint64_t* __restrict__ block_sums, uint64_t nblocks, uint64_t* __restrict__ total_out)
-{
-	__shared__ uint64_t sm[33];
-	uint64_t carry = 0;
-	for(uint64_t base = 0; base < nblocks; base += blockDim.x) {
-		uint64_t i = base + threadIdx.x;
-		uint64_t v = (i < nblocks)? block_sums[i] : 0;
-		uint64_t total;
-		uint64_t ex = block_excl_scan_u64(v, &total, sm);
-		if(i < nblocks)
-			block_sums[i] = carry + ex;
-		carry += total;
-	}
-	if(threadIdx.x == 0 && total_out != nullptr)
-		*total_out = carry;
-}
-
-template <typename Tin>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const Tin* __restrict__ in, uint64_t* __restrict__ out, uint64_t n, const uint64_t* __restrict__ block_sums)
-{
-	__shared__ uint64_t sm[33];
-	uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+		sm_tile = atomicAdd(ticket, 1ull) - ticket_base;
+	__syncthreads();
+	const uint64_t tile = sm_tile;
+	const uint64_t base = tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
 	uint64_t v[SCAN_ITEMS];
 	uint64_t s = 0;
 #pragma unroll
@@ -92,7 +71,63 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const Tin* __restri
 		s += v[i];
 	}
 	uint64_t total;
-	uint64_t ex = block_excl_scan_u64(s, &total, sm) + block_sums[blockIdx.x];
+	uint64_t ex = block_excl_scan_u64(s, &total, sm);
+	if(threadIdx.x < 32) {
+		const int lane = threadIdx.x;
+		unsigned long long carry = 0;
+		if(tile > 0) {
+			if(lane == 0) {
+				__stcg(&aggs[tile], (unsigned long long)total);
+				__threadfence();
+				*reinterpret_cast<volatile uint32_t*>(&status[tile]) = (epoch << 2) | SC_AGG;
+			}
+			uint64_t probe = tile - 1;
+			uint64_t remaining = tile;
+			bool done = false;
+			while(!done) {
+				const uint32_t cnt = (uint32_t)min((uint64_t)32, remaining);
+				uint32_t st, first_prefix;
+				while(true) {
+					uint32_t raw = ((uint32_t)lane < cnt)? *reinterpret_cast<const volatile uint32_t*>(&status[probe - lane]) : ((epoch << 2) | SC_AGG);
+					st = ((raw >> 2) == epoch)? (raw & 3u) : SC_EMPTY;
+					const uint32_t pm = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == SC_PREFIX);
+					const uint32_t em = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && st == SC_EMPTY);
+					first_prefix = pm? (uint32_t)(__ffs(pm) - 1) : 32u;
+					const uint32_t need = (first_prefix >= 32u)? 0xFFFFFFFFu : ((2u << first_prefix) - 1u);
+					if((em & need) == 0)
+						break;
+				}
+				__threadfence();
+				unsigned long long x = 0;
+				if((uint32_t)lane < cnt) {
+					if((uint32_t)lane < first_prefix)
+						x = __ldcg(&aggs[probe - lane]);
+					else if((uint32_t)lane == first_prefix)
+						x = __ldcg(&prefixes[probe - lane]);
+				}
+#pragma unroll
+				for(int o = 16; o > 0; o >>= 1)
+					x += __shfl_xor_sync(0xffffffffu, x, o);
+				carry += x;
+				if(first_prefix < 32u)
+					done = true;
+				else {
+					probe -= 32;
+					remaining -= 32;
+				}
+			}
+		}
+		if(lane == 0) {
+			__stcg(&prefixes[tile], carry + (unsigned long long)total);
+			__threadfence();
+			*reinterpret_cast<volatile uint32_t*>(&status[tile]) = (epoch << 2) | SC_PREFIX;
+			sm_carry = carry;
+			if(total_out != nullptr && tile == gridDim.x - 1)
+				*total_out = carry + total;
+		}
+	}
+	__syncthreads();
+	ex += sm_carry;
 #pragma unroll
 	for(int i = 0; i < SCAN_ITEMS; i++) {
 		if(base + i < n)
@@ -109,13 +144,35 @@ int scan_impl(abw_ctx* ctx, const Tin* d_in, uint64_t* d_out, uint64_t n, uint64
 			ABW_CUDA(ctx, cudaMemsetAsync(d_total, 0, sizeof(uint64_t), ctx->stream));
 		return ABW_OK;
 	}
-	unsigned int nblocks = abw_div_up(n, SCAN_TILE);
-	DevBuf<uint64_t> sums;
-	ABW_CUDA(ctx, sums.alloc(nblocks));
-	ABW_LAUNCH(ctx, k_scan_reduce<Tin>, nblocks, SCAN_THREADS, 0, d_in, n, sums.p);
-	ABW_LAUNCH(ctx, k_scan_block_sums, 1, 1024, 0, sums.p, (uint64_t)nblocks, d_total);
-	ABW_LAUNCH(ctx, k_scan_apply<Tin>, nblocks, SCAN_THREADS, 0, d_in, d_out, n, sums.p);
-	return ABW_OK;                                       // sums is freed in stream order
+	const unsigned int nblocks = abw_div_up(n, SCAN_TILE);
+	// scratch of the context, grown on demand (scans of one context run one after the other on its stream)
+	if(ctx->scan_cap < nblocks) {
+		size_t cap = 4096;
+		while(cap < nblocks)
+			cap <<= 1;
+		if(ctx->scan_scratch)
+			ABW_CUDA(ctx, cudaFreeAsync(ctx->scan_scratch, ctx->stream));
+		ABW_CUDA(ctx, cudaMallocAsync(&ctx->scan_scratch, cap * 20 + 64, ctx->stream));
+		ABW_CUDA(ctx, cudaMemsetAsync(ctx->scan_scratch, 0, cap * 20 + 64, ctx->stream));
+		ctx->scan_cap = cap;
+		ctx->scan_epoch = 0;
+		ctx->scan_tickets = 0;
+	}
+	unsigned char* base = (unsigned char*)ctx->scan_scratch;
+	unsigned long long* ticket = (unsigned long long*)base;
+	unsigned long long* aggs = (unsigned long long*)(base + 64);
+	unsigned long long* prefixes = aggs + ctx->scan_cap;
+	uint32_t* status = (uint32_t*)(prefixes + ctx->scan_cap);
+	ctx->scan_epoch++;
+	if(ctx->scan_epoch >= (1u << 30)) {                    // the epoch field of the status words would wrap: start over
+		ABW_CUDA(ctx, cudaMemsetAsync(ctx->scan_scratch, 0, ctx->scan_cap * 20 + 64, ctx->stream));
+		ctx->scan_epoch = 1;
+		ctx->scan_tickets = 0;
+	}
+	ABW_LAUNCH(ctx, k_scan_onepass<Tin>, nblocks, SCAN_THREADS, 0, d_in, d_out, n, d_total, ticket, (unsigned long long)ctx->scan_tickets, ctx->scan_epoch, status, aggs,
+	           prefixes);
+	ctx->scan_tickets += nblocks;
+	return ABW_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -786,7 +786,7 @@ __global__ void __launch_bounds__(SW_THREADS, 4) k_sweep_ss(const uint32_t* __re
 // (score, then lowest dimension, then lowest value; ...Specificity.cpp:137-140 under the mutex, ClusterSeparator.cpp:11-16)
 template <int STRATEGY>
 __global__ void __launch_bounds__(256) k_reduce_best(const CandRec* __restrict__ per_item, uint32_t D, const LevelCtl* __restrict__ ctl,
-                                                    const LevelCluster* __restrict__ clusters, uint32_t dim_offset, CandRec* __restrict__ out)
+                                                    const LevelCluster* __restrict__ clusters, uint32_t dim_offset, uint32_t dim_stride, CandRec* __restrict__ out)
 {
 	__shared__ CandRec sm[256];
 	const uint32_t C = ctl->C, TT = ctl->TT;
@@ -811,7 +811,7 @@ __global__ void __launch_bounds__(256) k_reduce_best(const CandRec* __restrict__
 		}
 		if(threadIdx.x == 0) {
 			CandRec b = sm[0];
-			b.dim0 += dim_offset;                               // global dimension index from here on
+			b.dim0 = b.dim0 * dim_stride + dim_offset;          // global dimension index from here on (a sharded search holds every dim_stride-th dimension)
 			out[c] = b;
 		}
 		__syncthreads();
@@ -1045,7 +1045,7 @@ __device__ __forceinline__ void best_reset(abw_best& b, int strategy)
 }
 
 __global__ void __launch_bounds__(LV_THREADS) k_level_jobs(const LevelBufs B, int cur, uint32_t world, uint32_t Cstride, int strategy, const abw_params prm,
-                                                         uint32_t dim_offset, uint32_t Dlocal, const uint32_t* __restrict__ E, uint64_t N,
+                                                         uint32_t dim_offset, uint32_t dim_stride, uint32_t Dlocal, const uint32_t* __restrict__ E, uint64_t N,
                                                          ChildStats* __restrict__ stats, unsigned long long* __restrict__ value_key, uint64_t* __restrict__ child_never, uint32_t W)
 {
 	__shared__ uint32_t sm[33];
@@ -1119,14 +1119,14 @@ __global__ void __launch_bounds__(LV_THREADS) k_level_jobs(const LevelBufs B, in
 		bool mine = false;
 		if(j < J) {
 			const uint32_t d = B.jobs[j].dim0;
-			mine = d >= dim_offset && d < dim_offset + Dlocal;
+			mine = d >= dim_offset && (d - dim_offset) % dim_stride == 0 && (d - dim_offset) / dim_stride < Dlocal;
 		}
 		uint32_t total;
 		const uint32_t ex = cta_excl_scan(mine? 1u : 0u, total, sm);
 		if(mine) {
 			B.jobs_mine[JM + ex] = j;
 			const SplitJob jb = B.jobs[j];
-			B.jobs[j].sstar = E[(uint64_t)(jb.dim0 - dim_offset) * N + cls[jb.cluster].d.off + jb.p - 1] & EL_SCAF_MASK;   // p >= 1: a candidate has datapoints on both sides
+			B.jobs[j].sstar = E[(uint64_t)((jb.dim0 - dim_offset) / dim_stride) * N + cls[jb.cluster].d.off + jb.p - 1] & EL_SCAF_MASK;   // p >= 1: a candidate has datapoints on both sides
 		}
 		JM += total;
 	}
@@ -1153,14 +1153,15 @@ __global__ void __launch_bounds__(LV_THREADS) k_level_jobs(const LevelBufs B, in
 	}
 }
 
-__global__ void __launch_bounds__(256) k_count_low(const uint32_t* __restrict__ E, uint64_t N, const LevelBufs B, int cur, uint32_t dim_offset, uint32_t* __restrict__ low)
+__global__ void __launch_bounds__(256) k_count_low(const uint32_t* __restrict__ E, uint64_t N, const LevelBufs B, int cur, uint32_t dim_offset, uint32_t dim_stride,
+                                                  uint32_t* __restrict__ low)
 {
 	const LevelCluster* __restrict__ cls = B.cl[cur];
 	const uint32_t items = B.ctl->CL_items;
 	for(uint32_t it = blockIdx.x; it < items; it += gridDim.x) {
 		const uint2 te = B.cl_tab[it];
 		const SplitJob jb = B.jobs[B.jobs_mine[te.x]];
-		const uint32_t* __restrict__ seg = E + (uint64_t)(jb.dim0 - dim_offset) * N + cls[jb.cluster].d.off;
+		const uint32_t* __restrict__ seg = E + (uint64_t)((jb.dim0 - dim_offset) / dim_stride) * N + cls[jb.cluster].d.off;
 		const uint32_t i0 = te.y * CL_CHUNK, i1 = min(jb.p, i0 + CL_CHUNK);
 		for(uint32_t i = i0 + threadIdx.x; i < i1; i += blockDim.x)
 			atomicAdd(&low[seg[i] & EL_SCAF_MASK], 1u);
@@ -1189,7 +1190,7 @@ __device__ __forceinline__ unsigned long long orderable(double v)
 // one thread per scaffold of every cluster with a best separation: vote (ClusterSeparator.cpp:94-101), child statistics; the first warp of a job's first item
 // recovers the separating value.  The statistics of a warp are combined before they reach the two counters of the job (one atomic per warp and field).
 // low[] is cleared on the way (the entry of the scaffold that carries the separating value by k_level_decide).
-__global__ void __launch_bounds__(SS_CHUNK) k_scaf_sides(const uint32_t* __restrict__ scaf_list, const LevelBufs B, int cur, uint32_t dim_offset,
+__global__ void __launch_bounds__(SS_CHUNK) k_scaf_sides(const uint32_t* __restrict__ scaf_list, const LevelBufs B, int cur, uint32_t dim_offset, uint32_t dim_stride,
                              const ScafRow* __restrict__ rows, uint32_t* __restrict__ low, const uint64_t* __restrict__ dp_first, const ValSrc vsrc,
                              const uint64_t* __restrict__ scgmask, uint32_t W, int strategy, double fraction_in, uint8_t* __restrict__ side, uint8_t* __restrict__ new_assigned,
                              ChildStats* __restrict__ stats, uint64_t* __restrict__ child_never, unsigned long long* __restrict__ value_key)
@@ -1208,7 +1209,7 @@ __global__ void __launch_bounds__(SS_CHUNK) k_scaf_sides(const uint32_t* __restr
 			const ScafRow r = rows[s];
 			const uint32_t lo = low[s];
 			const uint64_t f = dp_first[s];
-			const uint32_t dl = jb.dim0 - dim_offset;
+			const uint32_t dl = (jb.dim0 - dim_offset) / dim_stride;
 			unsigned long long kth = 0;
 			for(uint32_t a = lane; a < r.n; a += 32) {
 				const unsigned long long ka = orderable(val_at(vsrc, f + a, dl));
@@ -2215,7 +2216,7 @@ struct abw_search {
 	std::vector<uint64_t> root_never;
 	bool consumed = false;
 	uint32_t max_levels = 0;                  // 0: run to the end; k: stop after k levels, the pending children become the bins
-	uint32_t dim_offset = 0, D_total = 0;     // sharded search: this object holds dimensions [dim_offset, dim_offset + D) of D_total
+	uint32_t dim_offset = 0, dim_stride = 1, D_total = 0;     // sharded search: this object holds dimensions dim_offset + k * dim_stride (k < D) of D_total
 	abw_search_profile prof{};
 };
 
@@ -2730,9 +2731,9 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 		s->prof.sweep_ms += tm.stop();
 		tm.start();
 		if(ss)
-			ABW_LAUNCH(ctx, k_reduce_best<ABW_SENS_SPEC>, g_small, 256, 0, d_cand.p, D, d_ctl.p, d_cl[cur].p, s->dim_offset, d_best.p);
+			ABW_LAUNCH(ctx, k_reduce_best<ABW_SENS_SPEC>, g_small, 256, 0, d_cand.p, D, d_ctl.p, d_cl[cur].p, s->dim_offset, s->dim_stride, d_best.p);
 		else
-			ABW_LAUNCH(ctx, k_reduce_best<ABW_SPLIT_SCAFS>, g_small, 256, 0, d_cand.p, D, d_ctl.p, d_cl[cur].p, s->dim_offset, d_best.p);
+			ABW_LAUNCH(ctx, k_reduce_best<ABW_SPLIT_SCAFS>, g_small, 256, 0, d_cand.p, D, d_ctl.p, d_cl[cur].p, s->dim_offset, s->dim_stride, d_best.p);
 		if(world > 1) {
 			// the per-rank best of every cluster, gathered; k_level_jobs applies the same total order on every rank
 			if(!ordered)
@@ -2740,9 +2741,9 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 			if(coll->allgather(coll->user, d_best.p, d_best_all.p, sizeof(CandRec) * Cb) != 0)
 				return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run_sharded: allgather callback failed");
 		}
-		ABW_LAUNCH(ctx, k_level_jobs, 1, LV_THREADS, 0, B, cur, world, Cb, s->strategy, prm, s->dim_offset, D, s->E[cur].p, N, d_stats, d_value_key, d_child_never, W);
-		ABW_LAUNCH(ctx, k_count_low, g_small, 256, 0, s->E[cur].p, N, B, cur, s->dim_offset, s->low.p);
-		ABW_LAUNCH(ctx, k_scaf_sides, g_small * 2, SS_CHUNK, 0, s->scaf_list[cur].p, B, cur, s->dim_offset, s->rows.p, s->low.p, s->dp_first.p, s->vsrc, s->scgmask.p, W,
+		ABW_LAUNCH(ctx, k_level_jobs, 1, LV_THREADS, 0, B, cur, world, Cb, s->strategy, prm, s->dim_offset, s->dim_stride, D, s->E[cur].p, N, d_stats, d_value_key, d_child_never, W);
+		ABW_LAUNCH(ctx, k_count_low, g_small, 256, 0, s->E[cur].p, N, B, cur, s->dim_offset, s->dim_stride, s->low.p);
+		ABW_LAUNCH(ctx, k_scaf_sides, g_small * 2, SS_CHUNK, 0, s->scaf_list[cur].p, B, cur, s->dim_offset, s->dim_stride, s->rows.p, s->low.p, s->dp_first.p, s->vsrc, s->scgmask.p, W,
 		           s->strategy, prm.fraction_dps_in, d_side, d_new_assigned, d_stats, d_child_never, d_value_key);
 		if(world > 1) {
 			// every quantity is non-zero on exactly one rank (the owner of the winning dimension): a sum is a gather
@@ -2987,9 +2988,15 @@ int abw_search_set_max_levels(abw_search* s, uint32_t max_levels)
 
 int abw_search_set_shard(abw_search* s, uint32_t dim_offset, uint32_t D_total)
 {
-	if(!s || (uint64_t)dim_offset + s->D > D_total)
+	return abw_search_set_shard_strided(s, dim_offset, 1, D_total);
+}
+
+int abw_search_set_shard_strided(abw_search* s, uint32_t dim_offset, uint32_t dim_stride, uint32_t D_total)
+{
+	if(!s || dim_stride == 0 || (s->D > 0 && (uint64_t)dim_offset + (uint64_t)(s->D - 1) * dim_stride >= D_total))
 		return ABW_ERR_ARG;
 	s->dim_offset = dim_offset;
+	s->dim_stride = dim_stride;
 	s->D_total = D_total;
 	return ABW_OK;
 }

@@ -386,7 +386,7 @@ class SearchResult:
 
 def search(ctx: capi.Context, values, dp2scaf, T, length, scgmask, params=None, strategy=capi.SENS_SPEC, layout=capi.LAYOUT_COLMAJOR,
            values_on_device=False, N=None, D=None, ld=None, want_bins=True, row_of_dp=None, nrows=None, timings=None,
-           collectives=None, dim_offset=0, D_total=None, scaf_gc=None, scaf_cvg=None, buffers=None) -> SearchResult:
+           collectives=None, dim_offset=0, D_total=None, scaf_gc=None, scaf_cvg=None, buffers=None, dim_stride=1) -> SearchResult:
     """values: numpy [D][nrows] (column major) or [nrows][D] (row major), or a device pointer with nrows, D, ld given.
     row_of_dp (uint64 [N], optional): the matrix row of every datapoint; default: N = nrows, datapoint i = row i."""
     L = ctx.lib
@@ -421,7 +421,7 @@ def search(ctx: capi.Context, values, dp2scaf, T, length, scgmask, params=None, 
     t0 = time.perf_counter()
     ctx.check(L.abw_search_create(ctx.h, vptr, 1 if values_on_device else 0, layout, ld, nrows, capi._p(row_of_dp), N, D, capi._p(dp2scaf), S, capi._p(T), capi._p(length),
                                   capi._p(scgmask), W, C.byref(p), strategy, C.byref(h)))
-    return _run_search(ctx, h, N, S, D, p, t0, want_bins, timings, collectives, dim_offset, D_total, scaf_gc, scaf_cvg, buffers)
+    return _run_search(ctx, h, N, S, D, p, t0, want_bins, timings, collectives, dim_offset, D_total, scaf_gc, scaf_cvg, buffers, dim_stride)
 
 
 def search_features(ctx: capi.Context, fb: "FeatureBuild", length, scgmask, params=None, strategy=capi.SENS_SPEC, want_bins=True, timings=None, buffers=None):
@@ -449,7 +449,7 @@ def search_features(ctx: capi.Context, fb: "FeatureBuild", length, scgmask, para
     return res, kept[:S.value]
 
 
-def _run_search(ctx, h, N, S, D, p, t0, want_bins, timings, collectives, dim_offset, D_total, scaf_gc, scaf_cvg, buffers):
+def _run_search(ctx, h, N, S, D, p, t0, want_bins, timings, collectives, dim_offset, D_total, scaf_gc, scaf_cvg, buffers, dim_stride=1):
     L = ctx.lib
     t1 = time.perf_counter()
     try:
@@ -473,7 +473,7 @@ def _run_search(ctx, h, N, S, D, p, t0, want_bins, timings, collectives, dim_off
             ctx.check(L.abw_search_run(ctx.h, h, recs, cap, C.byref(n), capi._p(dp2c), capi._p(s2c)))
         else:
             # dimension-sharded search: `values` holds dimensions [dim_offset, dim_offset + D) of D_total on this rank
-            ctx.check(L.abw_search_set_shard(h, dim_offset, D_total if D_total is not None else D))
+            ctx.check(L.abw_search_set_shard_strided(h, dim_offset, dim_stride, D_total if D_total is not None else D))
             ctx.check(L.abw_search_run_sharded(ctx.h, h, C.byref(collectives.struct), recs, cap, C.byref(n), capi._p(dp2c), capi._p(s2c)))
         if timings is not None:
             timings["search_create_ms"] = timings.get("search_create_ms", 0.0) + 1000.0 * (t1 - t0)

@@ -356,9 +356,13 @@ def main():
         cnt_all = torch.empty(world * nscaf, dtype=torch.int32, device=dev)
         dist.all_gather_into_tensor(cnt_all, cnt_local)
         cnt_all = cnt_all.cpu().numpy()
-        keep_all = cnt_all >= 2                                            # ScafDpData.cpp:92-93
-        T_all = cnt_all[keep_all].astype(np.uint32)
-        rows_per_rank = np.where(keep_all, cnt_all, 0).reshape(world, nscaf).sum(axis=1).tolist()
+        if int(cnt_all.min()) >= 2:                                        # nothing to drop (every scaffold has two windows): no copies of the tables
+            keep_all, T_all = slice(None), cnt_all.view(np.uint32)
+            rows_per_rank = cnt_all.reshape(world, nscaf).sum(axis=1).tolist()
+        else:
+            keep_all = cnt_all >= 2                                        # ScafDpData.cpp:92-93
+            T_all = cnt_all[keep_all].astype(np.uint32)
+            rows_per_rank = np.where(keep_all, cnt_all, 0).reshape(world, nscaf).sum(axis=1).tolist()
         if timings is not None:
             timings["exchange_tables_ms"] = 1000.0 * (time.perf_counter() - t_x0)
             t_x0 = time.perf_counter()
@@ -368,12 +372,13 @@ def main():
         local = torch.as_tensor(distributed._DevArray(fb.d_rows, fb.nseg * fb.ncols * 8, "<f8", 8), device=dev).view(fb.nseg, fb.ncols)
         if keep is not None:
             local = local[torch.from_numpy(np.nonzero(keep)[0]).to(dev)]
-        blocks = [distributed.dim_block(fb.ncols, r, world) for r in range(world)]
-        off, cnt = blocks[rank]
+        #    (round-robin: rank q owns the dimensions q, q + world, ... so that every rank gets the same mix of k-mer and coverage dimensions)
+        ncol_of = [len(range(r, fb.ncols, world)) for r in range(world)]
+        off, cnt = rank, ncol_of[rank]
         n_local = int(local.shape[0])
-        send = torch.cat([local[:, o:o + c].reshape(-1) for o, c in blocks])
+        send = torch.cat([local[:, r::world].reshape(-1) for r in range(world)])
         full = torch.empty((sum(rows_per_rank), cnt), dtype=torch.float64, device=dev)
-        dist.all_to_all_single(full.view(-1), send, output_split_sizes=[n * cnt for n in rows_per_rank], input_split_sizes=[n_local * c for _, c in blocks])
+        dist.all_to_all_single(full.view(-1), send, output_split_sizes=[n * cnt for n in rows_per_rank], input_split_sizes=[n_local * c for c in ncol_of])
         torch.cuda.synchronize(dev)
         if timings is not None:
             timings["exchange_columns_ms"] = 1000.0 * (time.perf_counter() - t_x0)
@@ -413,7 +418,7 @@ def main():
             # dimension-sharded search: this rank sweeps columns [off, off+cnt) of every datapoint
             res = pipeline.search(ctx, x["full"].data_ptr(), None, x["T_all"], lengths_all[x["keep_all"]], masks_all[x["keep_all"]],
                                   layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=int(x["full"].shape[0]), D=x["cnt"], ld=x["cnt"], timings=timings,
-                                  collectives=coll, dim_offset=x["off"], D_total=fb.ncols, buffers=result_buffers)
+                                  collectives=coll, dim_offset=x["off"], dim_stride=world, D_total=fb.ncols, buffers=result_buffers)
             ndps_total = int(x["full"].shape[0])
             if keep_exchange:
                 state["exchange"] = x

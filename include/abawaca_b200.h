@@ -287,6 +287,9 @@ typedef struct {
 	int stream_ordered;
 } abw_collectives;
 int abw_search_set_shard(abw_search* s, uint32_t dim_offset, uint32_t D_total);
+/* The same with interleaved dimensions: this rank holds the dimensions dim_offset + k * dim_stride (k = 0 .. D-1) of D_total, in that order in its matrix.
+ * Round-robin shards (dim_offset = rank, dim_stride = world) give every rank the same mix of k-mer and coverage dimensions. */
+int abw_search_set_shard_strided(abw_search* s, uint32_t dim_offset, uint32_t dim_stride, uint32_t D_total);
 int abw_search_run_sharded(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_cluster_rec* h_recs, uint32_t cap, uint32_t* nrecs,
                            uint32_t* h_dp2cluster, uint32_t* h_scaf2cluster);
 

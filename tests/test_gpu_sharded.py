@@ -44,8 +44,9 @@ class ThreadCollectives:
             self.structs.append(type("S", (), {"struct": st})())
 
 
-@pytest.mark.parametrize("name,strategy,world", [("tiny_noisy", 0, 2), ("tiny_noisy", 1, 2), ("tiny_clean", 0, 3)])
-def test_sharded_search_equals_single_rank(name, strategy, world):
+@pytest.mark.parametrize("name,strategy,world,strided", [("tiny_noisy", 0, 2, False), ("tiny_noisy", 1, 2, False), ("tiny_clean", 0, 3, False),
+                                                         ("tiny_noisy", 0, 3, True), ("tiny_clean", 1, 2, True)])
+def test_sharded_search_equals_single_rank(name, strategy, world, strided):
     from abawaca_b200 import capi, pipeline, distributed
     prob = search_problem(name)
     vals = prob["values"]
@@ -61,9 +62,13 @@ def test_sharded_search_equals_single_rank(name, strategy, world):
 
     def run(rank):
         try:
-            off, cnt = distributed.dim_block(D, rank, world)
-            results[rank] = pipeline.search(ctxs[rank], np.ascontiguousarray(vals[off:off + cnt]), prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"], params=p,
-                                            strategy=strategy, collectives=coll.structs[rank], dim_offset=off, D_total=D)
+            if strided:                                     # round-robin dimensions: rank r holds r, r + world, ...
+                mine, off, stride = np.ascontiguousarray(vals[rank::world]), rank, world
+            else:
+                off, cnt = distributed.dim_block(D, rank, world)
+                mine, stride = np.ascontiguousarray(vals[off:off + cnt]), 1
+            results[rank] = pipeline.search(ctxs[rank], mine, prob["dp2scaf"], prob["T"], prob["len"], prob["scgmask"], params=p,
+                                            strategy=strategy, collectives=coll.structs[rank], dim_offset=off, dim_stride=stride, D_total=D)
         except Exception as e:
             errors.append(e)
             coll.barrier.abort()

@@ -1,6 +1,7 @@
 // Shared host/device helpers of libabawaca_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>      // header only: ranges cost nothing unless a tool (nsys, ncu --nvtx) is attached
 #include <stdint.h>
 #include <string>
 #include <vector>
@@ -114,7 +115,14 @@ extern thread_local abw_ctx* abw_tls_ctx;
 cudaError_t abw_arena_alloc(abw_ctx* ctx, size_t bytes, void** out);
 void abw_arena_free(abw_ctx* ctx, void* p);
 
+// one NVTX range per ABI entry point (named after the function), closed when the entry point returns
+struct AbwNvtxRange {
+	explicit AbwNvtxRange(const char* name) { nvtxRangePushA(name); }
+	~AbwNvtxRange() { nvtxRangePop(); }
+};
+
 #define ABW_ENTER(ctx)                                                                                               \
+	AbwNvtxRange nvtx_range__(__func__);                                                                             \
 	do {                                                                                                             \
 		ABW_CUDA((ctx), cudaSetDevice((ctx)->device));                                                               \
 		abw_tls_ctx = (ctx);                                                                                         \
@@ -157,7 +165,7 @@ int abw_exclusive_scan_u32_to_u64(abw_ctx* ctx, const uint32_t* d_in, uint64_t* 
 
 // Stable LSD radix sort of `batch` independent arrays of n (key, value) pairs each (array b at offset b*stride).
 // Only key bits [0, nbits) are examined.  Result is left in (keys, vals); (keys_tmp, vals_tmp) are scratch of the same size.
-// Digits are 8 or 9 bits wide, placed only over key bits that actually vary (bits equal in all keys of all arrays are skipped).
+// Digits are 8, 9 or 10 bits wide, placed only over key bits that actually vary (bits equal in all keys of all arrays are skipped).
 int abw_radix_sort_pairs_u64(abw_ctx* ctx, uint64_t* d_keys, uint64_t* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, uint32_t batch,
                              uint64_t stride, int nbits);
 int abw_radix_sort_pairs_u32(abw_ctx* ctx, uint32_t* d_keys, uint32_t* d_keys_tmp, uint32_t* d_vals, uint32_t* d_vals_tmp, uint64_t n, uint32_t batch,

@@ -351,17 +351,23 @@ int radix_sort_impl(abw_ctx* ctx, K* d_keys, K* d_keys_tmp, uint32_t* d_vals, ui
 	Pass plan[16];
 	int npass = 0;
 	{
-		int total9 = 0, total8 = 0;
-		for(int width = 9; width >= 8; width--) {
+		int total[11] = {0};
+		for(int width = 8; width <= 10; width++) {
 			int cnt = 0, bit = 0;
 			while(bit < 64) {
 				if(!((varying >> bit) & 1ull)) { bit++; continue; }
 				cnt++;
 				bit += width;
 			}
-			if(width == 9) total9 = cnt; else total8 = cnt;
+			total[width] = cnt;
 		}
-		const int width = (total9 < total8)? 9 : 8;
+		// the narrowest digit that needs the fewest passes; 10-bit digits measured slower than two 8-bit passes (1024 bins: a third of the CTAs per SM in the
+		// scatter and four times the histogram to scan), so they are only planned when they save two passes
+		int width = 8;
+		if(total[9] < total[width])
+			width = 9;
+		if(total[10] + 1 < total[width])
+			width = 10;
 		int bit = 0;
 		while(bit < 64) {
 			if(!((varying >> bit) & 1ull)) { bit++; continue; }
@@ -373,13 +379,15 @@ int radix_sort_impl(abw_ctx* ctx, K* d_keys, K* d_keys_tmp, uint32_t* d_vals, ui
 	}
 	DevBuf<uint32_t> hist;
 	DevBuf<uint64_t> offs;
-	uint64_t nh = (uint64_t)batch * 512 * nblocks;
+	uint64_t nh = (uint64_t)batch * 1024 * nblocks;
 	ABW_CUDA(ctx, hist.alloc(nh));
 	ABW_CUDA(ctx, offs.alloc(nh));
 	K* src_k = d_keys; K* dst_k = d_keys_tmp;
 	uint32_t* src_v = d_vals; uint32_t* dst_v = d_vals_tmp;
 	for(int ps = 0; ps < npass; ps++) {
-		if(plan[ps].bits == 9)
+		if(plan[ps].bits == 10)
+			ABW_CHECK((radix_pass<K, 10>(ctx, src_k, src_v, dst_k, dst_v, n, batch, stride, plan[ps].shift, nblocks, hist.p, offs.p)));
+		else if(plan[ps].bits == 9)
 			ABW_CHECK((radix_pass<K, 9>(ctx, src_k, src_v, dst_k, dst_v, n, batch, stride, plan[ps].shift, nblocks, hist.p, offs.p)));
 		else
 			ABW_CHECK((radix_pass<K, 8>(ctx, src_k, src_v, dst_k, dst_v, n, batch, stride, plan[ps].shift, nblocks, hist.p, offs.p)));

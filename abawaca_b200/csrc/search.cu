@@ -484,8 +484,8 @@ constexpr int FP_TILE = SW_THREADS * FP_ITEMS;
 // 16-byte slots swizzled so that both the strided stores and the blocked loads are conflict free) instead of living in registers across the
 // scan and the look-back: 40 registers instead of 128, six CTAs per SM instead of two.
 __global__ void __launch_bounds__(SW_THREADS, 4) k_flip_prefix(const uint32_t* __restrict__ flip_list, uint64_t Sf, const LevelCluster* __restrict__ clusters, uint32_t D,
-                                                              LevelCtl* __restrict__ ctl, const uint2* __restrict__ ftile_tab, const ScafRow* __restrict__ rows,
-                                                              const uint8_t* __restrict__ has_scg, uint32_t epoch, uint32_t* __restrict__ status, AggSlot* __restrict__ aggs,
+                                                              LevelCtl* __restrict__ ctl, const uint2* __restrict__ ftile_tab, const uint4* __restrict__ frow,
+                                                              uint32_t epoch, uint32_t* __restrict__ status, AggSlot* __restrict__ aggs,
                                                               AggSlot* __restrict__ prefixes, uint2* __restrict__ F8, uint32_t* __restrict__ FC, uint32_t* __restrict__ scg_k,
                                                               uint64_t Kstride, uint2* __restrict__ klohi, uint32_t Cstride, unsigned long long scg_min_size)
 {
@@ -519,10 +519,8 @@ __global__ void __launch_bounds__(SW_THREADS, 4) k_flip_prefix(const uint32_t* _
 #pragma unroll
 			for(int j = 0; j < FP_ITEMS; j++) {
 				uint4 r = make_uint4(0, 0, 0, 0);
-				if(sc[j] != 0xFFFFFFFFu) {
-					r = __ldg(reinterpret_cast<const uint4*>(rows + sc[j]));
-					r.y |= (uint32_t)(has_scg[sc[j]] != 0) << 31;
-				}
+				if(sc[j] != 0xFFFFFFFFu)
+					r = __ldg(frow + sc[j]);
 				const uint32_t e = j * SW_THREADS + threadIdx.x;
 				sm_r[e ^ ((e >> 3) & 7u)] = r;
 			}
@@ -1846,19 +1844,16 @@ __global__ void k_dp_bins(const uint32_t* __restrict__ dp2scaf, const uint32_t* 
 // MILLI: columns written by abawaca-build hold multiples of 0.001 (int(1000*x)/1000.0, abawaca-build.cpp:603).  When every value v satisfies
 // v == (double)k / 1000.0 for the integer k = rint(1000*v), |k| < 2^31, ordering by k is ordering by v (ties included) and the sort runs on 32-bit keys
 // with few significant bits; any other value sets flag[0] and the chunk is redone with the 64-bit keys (an order-preserving image of the double; -0.0 and
-// +0.0 compare equal in comp_by_value, ClusterSeparator.cpp:8; NaN sets flag[1]).  or_and[2 k], or_and[2 k + 1] (k = blockIdx.x & 63; preset to 0 and ~0):
-// OR and AND of the keys, so that the sort knows which key bits differ at all without another pass over the keys.
+// +0.0 compare equal in comp_by_value, ClusterSeparator.cpp:8; NaN sets flag[1]).
 // One CTA transposes a tile of 32 datapoints x 32 dimensions through shared memory: coalesced reads of a row-major matrix, coalesced writes of the keys.
 template <bool MILLI, typename KeyT>
 __global__ void __launch_bounds__(256) k_keys(const ValSrc v, uint64_t N, uint32_t d0, uint32_t nd, KeyT* __restrict__ keys, uint32_t* __restrict__ vals,
-                                              int* __restrict__ flag, uint32_t* __restrict__ or_and)
+                                              int* __restrict__ flag)
 {
 	__shared__ KeyT tile[32][33];
-	__shared__ uint32_t sm_or[8], sm_and[8];
 	const uint64_t r0 = (uint64_t)blockIdx.x * 32;
 	const uint32_t c0 = blockIdx.y * 32;
 	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-	uint32_t key_or = 0u, key_and = ~0u;
 	bool bad = false, isnan = false;
 	const bool rowmajor = v.layout == ABW_LAYOUT_ROWMAJOR;
 #pragma unroll
@@ -1873,10 +1868,7 @@ __global__ void __launch_bounds__(256) k_keys(const ValSrc v, uint64_t N, uint32
 				const double k = rint(__dmul_rn(x, 1000.0));
 				const bool ok = (k > -2147483000.0) && (k < 2147483000.0) && (__ddiv_rn(k, 1000.0) == x);
 				bad |= !ok;
-				const uint32_t k32 = ok? (uint32_t)((long long)k + 2147483648ll) : 0u;
-				key = (KeyT)k32;
-				key_or |= k32;
-				key_and &= k32;
+				key = (KeyT)(ok? (uint32_t)((long long)k + 2147483648ll) : 0u);
 			}
 			else {
 				isnan |= x != x;
@@ -1884,7 +1876,7 @@ __global__ void __launch_bounds__(256) k_keys(const ValSrc v, uint64_t N, uint32
 			}
 		}
 		if(rowmajor)
-			tile[ty + 8 * j][tx] = key;                 // [datapoint][dimension]
+			tile[ty + 8 * j][tx] = key;                     // [datapoint][dimension]
 		else
 			tile[tx][ty + 8 * j] = key;
 	}
@@ -1904,25 +1896,6 @@ __global__ void __launch_bounds__(256) k_keys(const ValSrc v, uint64_t N, uint32
 		if(isnan)
 			atomicExch(&flag[1], 1);
 	}
-	if(MILLI) {
-		key_or = __reduce_or_sync(0xffffffffu, key_or);
-		key_and = __reduce_and_sync(0xffffffffu, key_and);
-		if(tx == 0) {
-			sm_or[ty] = key_or;
-			sm_and[ty] = key_and;
-		}
-		__syncthreads();
-		if(threadIdx.x == 0) {
-#pragma unroll
-			for(int w = 1; w < 8; w++) {
-				key_or |= sm_or[w];
-				key_and &= sm_and[w];
-			}
-			const uint32_t slot = (blockIdx.x + blockIdx.y) & 63u;
-			atomicOr(&or_and[2 * slot], key_or);
-			atomicAnd(&or_and[2 * slot + 1], key_and);
-		}
-	}
 }
 
 __global__ void k_fill_or_and(uint32_t* __restrict__ or_and, uint32_t n)
@@ -1939,10 +1912,32 @@ __global__ void k_fill_or_and(uint32_t* __restrict__ or_and, uint32_t n)
 template <typename KeyT>
 __global__ void __launch_bounds__(256) k_rank_class(const KeyT* __restrict__ keys, uint64_t N, uint32_t nd, const uint32_t* __restrict__ dp2scaf,
                                                     const uint64_t* __restrict__ dp_first, const ScafRow* __restrict__ rows, const uint8_t* __restrict__ has_scg, int strategy,
-                                                    double fraction_in, uint8_t* __restrict__ cls_out)
+                                                    double fraction_in, uint8_t* __restrict__ cls_out, uint32_t* __restrict__ or_and)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t d = blockIdx.y;
+	if(or_and != nullptr) {
+		// OR and AND of the (32-bit) keys of dimension d (or_and[2 d], or_and[2 d + 1], preset to 0 and ~0): which key bits differ at all, per dimension --
+		// k-mer thousandths fit one radix digit, coverage needs two.  One atomic pair per CTA.
+		__shared__ uint32_t sm_or[8], sm_and[8];
+		const uint32_t k32 = (i < N && d < nd)? (uint32_t)keys[(uint64_t)d * N + i] : 0u;
+		const uint32_t o = __reduce_or_sync(0xffffffffu, k32), a = __reduce_and_sync(0xffffffffu, (i < N && d < nd)? k32 : ~0u);
+		if((threadIdx.x & 31) == 0) {
+			sm_or[threadIdx.x >> 5] = o;
+			sm_and[threadIdx.x >> 5] = a;
+		}
+		__syncthreads();
+		if(threadIdx.x == 0 && d < nd) {
+			uint32_t oo = 0u, aa = ~0u;
+#pragma unroll
+			for(int w = 0; w < 8; w++) {
+				oo |= sm_or[w];
+				aa &= sm_and[w];
+			}
+			atomicOr(&or_and[2 * d], oo);
+			atomicAnd(&or_and[2 * d + 1], aa);
+		}
+	}
 	if(i >= N || d >= nd)
 		return;
 	const uint32_t s = dp2scaf[i];
@@ -2046,7 +2041,7 @@ __global__ void k_tab_fill_dp2scaf(const uint64_t* __restrict__ first, uint32_t 
 // one thread per scaffold: {T, n, len} row, SCG flag, root statistics (warp-aggregated)
 __global__ void __launch_bounds__(256) k_tab_scaffolds(const uint64_t* __restrict__ first, const uint32_t* __restrict__ T, const uint64_t* __restrict__ len,
                                                        const uint64_t* __restrict__ scgmask, uint32_t S, uint32_t W, double fraction_in, ScafRow* __restrict__ rows,
-                                                       uint8_t* __restrict__ has_scg, uint32_t* __restrict__ scg_flag, uint32_t* __restrict__ scaf_iota, RootStats* __restrict__ rs)
+                                                       uint4* __restrict__ frow, uint8_t* __restrict__ has_scg, uint32_t* __restrict__ scg_flag, uint32_t* __restrict__ scaf_iota, RootStats* __restrict__ rs)
 {
 	const uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool active = sidx < S;
@@ -2070,6 +2065,7 @@ __global__ void __launch_bounds__(256) k_tab_scaffolds(const uint64_t* __restric
 		ScafRow r;
 		r.T = t; r.n = n; r.len = l;
 		rows[sidx] = r;
+		frow[sidx] = make_uint4(t, n | ((any? 1u : 0u) << 31), (uint32_t)l, (uint32_t)(l >> 32));     // the same with the SCG flag inside: one gather per flip-list entry
 		has_scg[sidx] = any;
 		scg_flag[sidx] = (any && flippable)? 1u : 0u;
 		scaf_iota[sidx] = sidx;
@@ -2196,6 +2192,7 @@ struct abw_search {
 	DevBuf<uint32_t> dp2scaf;
 	DevBuf<uint64_t> dp_first;
 	DevBuf<ScafRow> rows;
+	DevBuf<uint4> frow;                       // {T, n | SCG flag << 31, length}: what k_flip_prefix gathers per flip-list entry
 	DevBuf<uint64_t> scgmask;
 	DevBuf<uint8_t> has_scg;
 	DevBuf<uint32_t> E[2];
@@ -2274,6 +2271,7 @@ int search_build_common(abw_ctx* ctx, abw_search* s, DevBuf<uint32_t>& d_T, DevB
 	ABW_CUDA(ctx, d_rs.alloc(1));
 	ABW_CUDA(ctx, cudaMemsetAsync(d_rs.p, 0, sizeof(RootStats), ctx->stream));
 	ABW_CUDA(ctx, s->rows.alloc(S));
+	ABW_CUDA(ctx, s->frow.alloc(S));
 	ABW_CUDA(ctx, s->has_scg.alloc(S));
 	ABW_CUDA(ctx, s->dp_first.alloc((size_t)S + 1));
 	ABW_CUDA(ctx, cudaMemsetAsync(s->dp_first.p, 0, sizeof(uint64_t) * ((size_t)S + 1), ctx->stream));
@@ -2291,7 +2289,7 @@ int search_build_common(abw_ctx* ctx, abw_search* s, DevBuf<uint32_t>& d_T, DevB
 		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, d_T.p, s->dp_first.p, S, s->dp_first.p + S));
 		ABW_LAUNCH(ctx, k_tab_fill_dp2scaf, abw_div_up(S, 256), 256, 0, s->dp_first.p, S, N, s->dp2scaf.p);
 	}
-	ABW_LAUNCH(ctx, k_tab_scaffolds, abw_div_up(S, 256), 256, 0, s->dp_first.p, d_T.p, d_len.p, s->scgmask.p, S, W, s->prm.fraction_dps_in, s->rows.p, s->has_scg.p,
+	ABW_LAUNCH(ctx, k_tab_scaffolds, abw_div_up(S, 256), 256, 0, s->dp_first.p, d_T.p, d_len.p, s->scgmask.p, S, W, s->prm.fraction_dps_in, s->rows.p, s->frow.p, s->has_scg.p,
 	           d_scg_flag.p, s->scaf_list[0].p, d_rs.p);
 	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, d_scg_flag.p, d_scg_before.p, S, d_total.p));
 	// ---- per-dimension order, classes, elements; dimensions are processed in chunks to bound scratch memory
@@ -2309,7 +2307,8 @@ int search_build_common(abw_ctx* ctx, abw_search* s, DevBuf<uint32_t>& d_T, DevB
 	DevBuf<uint8_t> cls;
 	DevBuf<int> flags;                                     // [0] a value is not an exact multiple of 0.001, [1] NaN
 	ABW_CUDA(ctx, flags.alloc(2));
-	ABW_CUDA(ctx, or_and.alloc(128));
+	ABW_CUDA(ctx, or_and.alloc((size_t)2 * chunk));
+	std::vector<uint32_t> h_or_and((size_t)2 * chunk);
 	ABW_CUDA(ctx, keys.alloc((size_t)chunk * N));
 	ABW_CUDA(ctx, keys_tmp.alloc((size_t)chunk * N));
 	ABW_CUDA(ctx, vals.alloc((size_t)chunk * N));
@@ -2319,8 +2318,11 @@ int search_build_common(abw_ctx* ctx, abw_search* s, DevBuf<uint32_t>& d_T, DevB
 	uint32_t* const keys32_tmp = reinterpret_cast<uint32_t*>(keys_tmp.p);
 	auto launch_keys32 = [&](uint32_t d0, uint32_t nd) -> int {
 		ABW_CUDA(ctx, cudaMemsetAsync(flags.p, 0, 2 * sizeof(int), ctx->stream));
-		ABW_LAUNCH(ctx, k_fill_or_and, 1, 64, 0, or_and.p, 64u);
-		ABW_LAUNCH(ctx, (k_keys<true, uint32_t>), dim3(abw_div_up(N, 32), abw_div_up(nd, 32)), 256, 0, s->vsrc, N, d0, nd, keys32, vals.p, flags.p, or_and.p);
+		ABW_LAUNCH(ctx, k_fill_or_and, abw_div_up(nd, 256), 256, 0, or_and.p, nd);
+		ABW_LAUNCH(ctx, (k_keys<true, uint32_t>), dim3(abw_div_up(N, 32), abw_div_up(nd, 32)), 256, 0, s->vsrc, N, d0, nd, keys32, vals.p, flags.p);
+		// ranks inside the scaffolds on the 32-bit keys (thrown away if a value turns out not to be a multiple of 0.001), and the key bits that vary per dimension
+		ABW_LAUNCH(ctx, k_rank_class<uint32_t>, dim3(abw_div_up(N, 256), nd), 256, 0, keys32, N, nd, s->dp2scaf.p, s->dp_first.p, s->rows.p, s->has_scg.p, s->strategy,
+		           s->prm.fraction_dps_in, cls.p, or_and.p);
 		return ABW_OK;
 	};
 	ABW_CHECK(launch_keys32(0, std::min(chunk, D)));
@@ -2328,13 +2330,12 @@ int search_build_common(abw_ctx* ctx, abw_search* s, DevBuf<uint32_t>& d_T, DevB
 	RootStats h_rs;
 	uint64_t h_K = 0, sumT = N;
 	int h_flags[2] = {0, 0};
-	uint32_t h_or_and[128];
 	ABW_CUDA(ctx, abw_fetch(ctx, &h_rs, d_rs.p, sizeof(RootStats)));
 	ABW_CUDA(ctx, abw_fetch(ctx, &h_K, d_total.p, sizeof(uint64_t)));
 	if(!have_dp2scaf)
 		ABW_CUDA(ctx, abw_fetch(ctx, &sumT, s->dp_first.p + S, sizeof(uint64_t)));
 	ABW_CUDA(ctx, abw_fetch(ctx, h_flags, flags.p, sizeof(h_flags)));
-	ABW_CUDA(ctx, abw_fetch(ctx, h_or_and, or_and.p, sizeof(h_or_and)));
+	ABW_CUDA(ctx, abw_fetch(ctx, h_or_and.data(), or_and.p, sizeof(uint32_t) * 2 * std::min(chunk, D)));
 	ABW_CUDA(ctx, abw_sync(ctx));
 	if(sumT != N)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: without dp2scaf the matrix must hold exactly sum(T) datapoints");
@@ -2368,26 +2369,35 @@ int search_build_common(abw_ctx* ctx, abw_search* s, DevBuf<uint32_t>& d_T, DevB
 		if(d0 > 0) {
 			ABW_CHECK(launch_keys32(d0, nd));
 			ABW_CUDA(ctx, abw_fetch(ctx, h_flags, flags.p, sizeof(h_flags)));
-			ABW_CUDA(ctx, abw_fetch(ctx, h_or_and, or_and.p, sizeof(h_or_and)));
+			ABW_CUDA(ctx, abw_fetch(ctx, h_or_and.data(), or_and.p, sizeof(uint32_t) * 2 * nd));
 			ABW_CUDA(ctx, abw_sync(ctx));
-		}
-		uint32_t all_or = 0u, all_and = ~0u;                  // over all dimensions of the chunk: one digit plan for the batch
-		for(int k = 0; k < 64; k++) {
-			all_or |= h_or_and[2 * k];
-			all_and &= h_or_and[2 * k + 1];
 		}
 		uint32_t* fp = (s->strategy == ABW_SENS_SPEC && K > 0)? flip_pos.p + (uint64_t)d0 * K : nullptr;
 		if(!h_flags[0]) {
-			ABW_LAUNCH(ctx, k_rank_class<uint32_t>, grid, 256, 0, keys32, N, nd, s->dp2scaf.p, s->dp_first.p, s->rows.p, s->has_scg.p, s->strategy, s->prm.fraction_dps_in, cls.p);
-			ABW_CHECK(abw_radix_sort_pairs_u32_varying(ctx, keys32, keys32_tmp, vals.p, vals_tmp.p, N, nd, N, (unsigned long long)(all_or ^ all_and)));
+			// one digit plan per run of dimensions that need the same number of passes (k-mer thousandths fit one digit, coverage needs two)
+			auto passes = [](uint32_t varying) { int best = 64; for(int wd = 8; wd <= 9; wd++) { int c = 0, bit = 0; while(bit < 32) { if(!((varying >> bit) & 1u)) { bit++; continue; } c++; bit += wd; } best = std::min(best, c); } return best; };
+			for(uint32_t r0 = 0; r0 < nd;) {
+				uint32_t vary = h_or_and[2 * r0] ^ h_or_and[2 * r0 + 1];
+				const int p0 = passes(vary);
+				uint32_t r1 = r0 + 1;
+				while(r1 < nd) {
+					const uint32_t vd = h_or_and[2 * r1] ^ h_or_and[2 * r1 + 1];
+					if(passes(vd) != p0 || passes(vary | vd) != p0)
+						break;
+					vary |= vd;
+					r1++;
+				}
+				ABW_CHECK(abw_radix_sort_pairs_u32_varying(ctx, keys32 + (uint64_t)r0 * N, keys32_tmp + (uint64_t)r0 * N, vals.p + (uint64_t)r0 * N, vals_tmp.p + (uint64_t)r0 * N, N,
+				                                           r1 - r0, N, (unsigned long long)vary));
+				r0 = r1;
+			}
 			ABW_LAUNCH(ctx, k_pack_elements<uint32_t>, grid, 256, 0, keys32, vals.p, N, nd, s->dp2scaf.p, cls.p, s->E[0].p + (uint64_t)d0 * N, d_scg_index.p, fp, K);
 		}
 		else {
 			// arbitrary doubles: 64-bit order-preserving keys
-			ABW_LAUNCH(ctx, (k_keys<false, unsigned long long>), dim3(abw_div_up(N, 32), abw_div_up(nd, 32)), 256, 0, s->vsrc, N, d0, nd, keys.p, vals.p, flags.p,
-			           (uint32_t*)nullptr);
+			ABW_LAUNCH(ctx, (k_keys<false, unsigned long long>), dim3(abw_div_up(N, 32), abw_div_up(nd, 32)), 256, 0, s->vsrc, N, d0, nd, keys.p, vals.p, flags.p);
 			ABW_LAUNCH(ctx, k_rank_class<unsigned long long>, grid, 256, 0, keys.p, N, nd, s->dp2scaf.p, s->dp_first.p, s->rows.p, s->has_scg.p, s->strategy,
-			           s->prm.fraction_dps_in, cls.p);
+			           s->prm.fraction_dps_in, cls.p, (uint32_t*)nullptr);
 			ABW_CHECK(abw_radix_sort_pairs_u64(ctx, (uint64_t*)keys.p, (uint64_t*)keys_tmp.p, vals.p, vals_tmp.p, N, nd, N, 64));
 			ABW_LAUNCH(ctx, k_pack_elements<unsigned long long>, grid, 256, 0, keys.p, vals.p, N, nd, s->dp2scaf.p, cls.p, s->E[0].p + (uint64_t)d0 * N, d_scg_index.p, fp, K);
 			int h_nan[2] = {0, 0};
@@ -2720,7 +2730,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 			s->prof.other_ms += tm.stop();
 			tm.start();
 			if(Sf > 0)
-				ABW_LAUNCH(ctx, k_flip_prefix, g_fp, SW_THREADS, 0, s->flip_list[cur].p, Sf, d_cl[cur].p, D, d_ctl.p, d_fp_tab.p, s->rows.p, s->has_scg.p, ep_sweep, d_status.p,
+				ABW_LAUNCH(ctx, k_flip_prefix, g_fp, SW_THREADS, 0, s->flip_list[cur].p, Sf, d_cl[cur].p, D, d_ctl.p, d_fp_tab.p, s->frow.p, ep_sweep, d_status.p,
 				           d_aggs.p, d_prefixes.p, s->F8.p, s->FC.p, s->scg_k.p, (uint64_t)K, d_klohi.p, Cmax, (unsigned long long)prm.scg_min_size);
 			ABW_LAUNCH(ctx, k_sweep_ss, g_sweep, SW_THREADS, 0, s->E[cur].p, N, d_cl[cur].p, D, d_ctl.p, d_tile_tab.p, s->F8.p, s->FC.p, s->scg_k.p, (uint64_t)K, d_klohi.p, Cmax,
 			           Sf, d_tab.p, sp, ep_sweep, d_lookback.p, d_cand.p);

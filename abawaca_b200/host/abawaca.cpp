@@ -11,6 +11,7 @@
 #include <fstream>
 #include <iostream>
 #include <set>
+#include <chrono>
 
 using namespace abwh;
 
@@ -367,8 +368,21 @@ static void weighted_stats(const std::vector<std::pair<size_t, double>>& data, d
 	stdev = sqrt(stdev / (total - 1));
 }
 
+// ABW_TIMING=1: wall-clock milestones on stderr (where the time of the drop-in program goes: CUDA start-up, text in, search, text out)
+static void milestone(const char* what)
+{
+	static const bool on = getenv("ABW_TIMING") != nullptr;
+	static auto t0 = std::chrono::steady_clock::now();
+	if(!on)
+		return;
+	const auto t1 = std::chrono::steady_clock::now();
+	fprintf(stderr, "[abw timing] %-28s %8.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+	t0 = t1;
+}
+
 int main(int argc, const char** argv)
 {
+	milestone("start");
 	std::cerr << "abawaca " << VERSION << std::endl << std::endl;
 	Params P;
 	if(read_params(P, argc, argv))
@@ -386,8 +400,10 @@ int main(int argc, const char** argv)
 			std::cerr << "Error: no usable CUDA device (abawaca_b200 has no CPU path)" << std::endl;
 			return -1;
 		}
+		milestone("abw_ctx_create");
 		Model M;
 		load_model(P, M, ctx);
+		milestone("load_model");
 		const size_t N = M.N(), S = M.S(), D = M.D();
 		summary << "Cluster\t# scafs\t# dps\t# bps\t%G+C\tStdev\tCvg\tstdev\t#SCG" << '/' << M.total_num_scgs << "\tAvg" << std::endl;
 
@@ -408,6 +424,7 @@ int main(int argc, const char** argv)
 		}
 		recs.resize(nrec);
 		abw_search_destroy(search);
+		milestone("search");
 
 		// membership of every evaluated cluster: terminal bins bubble up to their ancestors
 		std::map<uint32_t, uint32_t> parent_of;
@@ -560,11 +577,13 @@ int main(int argc, const char** argv)
 					    << " copies), %G+C=" << avg_gc << ", coverage=" << avg_cvg << std::endl;
 			}
 		}
+		milestone("logs, fasta and cluster dumps");
 		// dp2cluster.txt has a row for dp 0 as well (abawaca.cpp:199, quirk Q10)
 		ofs_dp << 0 << "\t0" << std::endl;
 		for(size_t i = 0; i < N; i++) ofs_dp << (i + 1) << "\t" << dp2cluster[i] << std::endl;
 		for(size_t s = 0; s < S; s++) ofs_scaf << M.scaf_names[s] << "\t" << scaf2cluster[s] << std::endl;
 		abw_ctx_destroy(ctx);
+		milestone("bin files, teardown");
 	}
 	catch(std::exception& e) {
 		std::cerr << "terminate called after throwing an instance of std::exception: " << e.what() << std::endl;

@@ -67,7 +67,7 @@ class Collectives(C.Structure):
 
 
 EXPORTS = [
-    "abw_ctx_create", "abw_ctx_destroy", "abw_last_error", "abw_version", "abw_default_params", "abw_kernel_launches", "abw_arena_misses", "abw_ctx_stream",
+    "abw_ctx_create", "abw_ctx_destroy", "abw_last_error", "abw_version", "abw_default_params", "abw_kernel_launches", "abw_arena_misses", "abw_redzone_violations", "abw_ctx_stream",
     "abw_ctx_synchronize", "abw_profile_enable", "abw_profile_report", "abw_pack_sequences", "abw_seqset_destroy", "abw_seqset_stats", "abw_segment", "abw_segments_destroy",
     "abw_segments_count", "abw_segments_get", "abw_segments_get_async", "abw_kmer_features", "abw_coverage", "abw_coverage_batch", "abw_rows_to_milli", "abw_device_alloc", "abw_device_free",
     "abw_copy_to_device", "abw_copy_to_host", "abw_memset_device", "abw_h2d_async", "abw_wait_h2d", "abw_d2h_async", "abw_search_create", "abw_search_create_from_features", "abw_search_destroy", "abw_search_run",
@@ -89,6 +89,8 @@ def load():
     L.abw_kernel_launches.restype = C.c_uint64
     L.abw_arena_misses.restype = C.c_uint64
     L.abw_arena_misses.argtypes = [C.c_void_p]
+    L.abw_redzone_violations.restype = C.c_uint64
+    L.abw_redzone_violations.argtypes = []
     L.abw_ctx_stream.restype = C.c_void_p
     L.abw_segments_count.restype = C.c_uint64
     L.abw_segments_count.argtypes = [C.c_void_p]

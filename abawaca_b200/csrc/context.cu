@@ -12,10 +12,82 @@ std::mutex g_live_mutex;
 std::set<abw_ctx*> g_live;                                 // contexts that still exist: a buffer may be released after its context is gone
 }
 
+// ABW_REDZONE=1 (debug; the pool this was developed on refuses compute-sanitizer): every device block gets a 4 KiB canary zone on either side, is
+// filled with 0xFF when handed out (a kernel that relies on memory it never wrote reads NaN / huge integers, and the bit-exact parity tests fail) and
+// with 0xDD when released (use after free), is never reused, and the canaries are verified when the block is released or its context is destroyed.
+// abw_redzone_violations() is the number of damaged canary zones seen so far in this process; ABW_REDZONE=abort also aborts at the first one.
+namespace {
+const size_t RZ = 4096;
+struct RzBlock { unsigned char* base; size_t bytes; abw_ctx* ctx; };
+std::map<void*, RzBlock> g_rz;
+uint64_t g_rz_violations = 0;
+int redzone_mode()
+{
+	static const int m = [] { const char* e = getenv("ABW_REDZONE"); return !e || !*e || strcmp(e, "0") == 0? 0 : strcmp(e, "abort") == 0? 2 : 1; }();
+	return m;
+}
+}
+
+__global__ void k_redzone_check(const unsigned char* __restrict__ front, const unsigned char* __restrict__ back, size_t nback, unsigned long long* bad)
+{
+	// bad[0], bad[1]: damaged bytes before / after the block; bad[2], bad[3]: offset of the first one (atomicMin)
+	for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < RZ + nback; i += (size_t)gridDim.x * blockDim.x) {
+		const bool is_front = i < RZ;
+		const size_t o = is_front? i : i - RZ;
+		if((is_front? front[o] : back[o]) != 0xA5) {
+			atomicAdd(&bad[is_front? 0 : 1], 1ull);
+			atomicMin(&bad[is_front? 2 : 3], (unsigned long long)o);
+		}
+	}
+}
+
+static cudaError_t redzone_alloc(abw_ctx* ctx, size_t bytes, void** out)
+{
+	// the payload ends where the caller's size ends (rounded to 16 bytes only), so that one element past the end already lands on a canary
+	const size_t payload = (bytes + 15) & ~(size_t)15;
+	unsigned char* base = nullptr;
+	cudaError_t e = cudaMallocAsync((void**)&base, RZ + payload + RZ, ctx->stream);
+	if(e != cudaSuccess)
+		return e;
+	cudaMemsetAsync(base, 0xA5, RZ, ctx->stream);
+	cudaMemsetAsync(base + RZ, 0xFF, payload, ctx->stream);
+	cudaMemsetAsync(base + RZ + payload, 0xA5, RZ, ctx->stream);
+	*out = base + RZ;
+	std::lock_guard<std::mutex> lk(g_live_mutex);
+	g_rz[*out] = RzBlock{base, payload, ctx};
+	ctx->arena_misses++;
+	return cudaGetLastError();
+}
+
+// verifies and releases one block (stream: the owning context's if it is still alive, else the default stream)
+static void redzone_release(void* p, const RzBlock& b, cudaStream_t stream)
+{
+	unsigned long long* d_bad = nullptr;
+	unsigned long long h_bad[4] = {0, 0, ~0ull, ~0ull};
+	if(cudaMalloc((void**)&d_bad, sizeof(h_bad)) == cudaSuccess) {
+		cudaMemcpyAsync(d_bad, h_bad, sizeof(h_bad), cudaMemcpyHostToDevice, stream);
+		k_redzone_check<<<8, 256, 0, stream>>>(b.base, b.base + RZ + b.bytes, RZ, d_bad);
+		cudaMemcpyAsync(h_bad, d_bad, sizeof(h_bad), cudaMemcpyDeviceToHost, stream);
+		cudaMemsetAsync(b.base + RZ, 0xDD, b.bytes, stream);
+		cudaStreamSynchronize(stream);
+		cudaFree(d_bad);
+	}
+	if(h_bad[0] || h_bad[1]) {
+		g_rz_violations++;
+		fprintf(stderr, "ABW_REDZONE: block %p of %zu bytes: %llu byte(s) written before it (first at -%llu), %llu after it (first at +%llu)\n", p, b.bytes,
+		        h_bad[0], h_bad[0]? (unsigned long long)RZ - h_bad[2] : 0ull, h_bad[1], h_bad[1]? (unsigned long long)b.bytes + h_bad[3] : 0ull);
+		if(redzone_mode() == 2)
+			abort();
+	}
+	cudaFreeAsync(b.base, stream);
+}
+
 cudaError_t abw_arena_alloc(abw_ctx* ctx, size_t bytes, void** out)
 {
 	if(!ctx)
 		return cudaMalloc(out, bytes);
+	if(redzone_mode())
+		return redzone_alloc(ctx, bytes, out);
 	// best fit among the cached blocks, as long as it does not waste more than a quarter of the block
 	auto it = ctx->free_blocks.lower_bound(bytes);
 	if(it != ctx->free_blocks.end() && it->first <= bytes + bytes / 4 + 65536) {
@@ -161,9 +233,19 @@ void abw_arena_free(abw_ctx* ctx, void* p)
 	if(!p)
 		return;
 	bool alive = false;
-	if(ctx) {
+	RzBlock rz{nullptr, 0, nullptr};
+	{
 		std::lock_guard<std::mutex> lk(g_live_mutex);
-		alive = g_live.count(ctx) != 0;
+		alive = ctx && g_live.count(ctx) != 0;
+		auto it = g_rz.find(p);
+		if(it != g_rz.end()) {
+			rz = it->second;
+			g_rz.erase(it);
+		}
+	}
+	if(rz.base) {
+		redzone_release(p, rz, alive? ctx->stream : (cudaStream_t)0);
+		return;
 	}
 	if(!alive) {
 		cudaFree(p);
@@ -245,6 +327,38 @@ void abw_ctx_destroy(abw_ctx* ctx)
 		g_live.erase(ctx);
 	}
 	cudaStreamSynchronize(ctx->stream);
+	if(redzone_mode()) {
+		// blocks this context handed out that are still held (search handles released later, leaks): verify their canaries now, while the stream exists
+		std::vector<std::pair<void*, RzBlock>> mine;
+		{
+			std::lock_guard<std::mutex> lk(g_live_mutex);
+			for(auto& kv : g_rz)
+				if(kv.second.ctx == ctx)
+					mine.push_back(kv);
+		}
+		for(auto& kv : mine) {
+			RzBlock keep = kv.second;
+			unsigned long long* d_bad = nullptr;
+			unsigned long long h_bad[4] = {0, 0, ~0ull, ~0ull};
+			if(cudaMalloc((void**)&d_bad, sizeof(h_bad)) == cudaSuccess) {
+				cudaMemcpy(d_bad, h_bad, sizeof(h_bad), cudaMemcpyHostToDevice);
+				k_redzone_check<<<8, 256, 0, ctx->stream>>>(keep.base, keep.base + RZ + keep.bytes, RZ, d_bad);
+				cudaStreamSynchronize(ctx->stream);
+				cudaMemcpy(h_bad, d_bad, sizeof(h_bad), cudaMemcpyDeviceToHost);
+				cudaFree(d_bad);
+			}
+			if(h_bad[0] || h_bad[1]) {
+				g_rz_violations++;
+				fprintf(stderr, "ABW_REDZONE: live block %p of %zu bytes damaged at context destruction (%llu before, %llu after)\n", kv.first, keep.bytes, h_bad[0], h_bad[1]);
+				if(redzone_mode() == 2)
+					abort();
+			}
+			std::lock_guard<std::mutex> lk(g_live_mutex);
+			auto it = g_rz.find(kv.first);
+			if(it != g_rz.end())
+				it->second.ctx = nullptr;
+		}
+	}
 	for(auto& kv : ctx->free_blocks)
 		cudaFree(kv.second);
 	ctx->free_blocks.clear();
@@ -278,6 +392,8 @@ const char* abw_last_error(const abw_ctx* ctx) { return ctx? ctx->err.c_str() : 
 uint64_t abw_kernel_launches(const abw_ctx* ctx) { return ctx? ctx->launches : 0; }
 
 uint64_t abw_arena_misses(const abw_ctx* ctx) { return ctx? ctx->arena_misses : 0; }
+
+uint64_t abw_redzone_violations(void) { return g_rz_violations; }
 
 void* abw_ctx_stream(const abw_ctx* ctx) { return ctx? (void*)ctx->stream : nullptr; }
 

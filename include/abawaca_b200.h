@@ -74,6 +74,10 @@ void        abw_default_params(abw_params* p);
 uint64_t    abw_kernel_launches(const abw_ctx* ctx);
 /* number of device blocks this context had to obtain from the driver so far (0 per pass once its block cache is warm) */
 uint64_t    abw_arena_misses(const abw_ctx* ctx);
+/* Debug allocator (environment ABW_REDZONE=1, or =abort): every device block of the library is surrounded by canary zones, handed out filled with 0xFF,
+   never reused, and verified when it is released; this is the number of blocks found damaged so far in this process (always 0 when the mode is off).
+   It stands in for compute-sanitizer memcheck where that tool cannot be run. */
+uint64_t    abw_redzone_violations(void);
 /* the stream every kernel of this context is launched on (a cudaStream_t), for event timing */
 void*       abw_ctx_stream(const abw_ctx* ctx);
 int         abw_ctx_synchronize(abw_ctx* ctx);

@@ -16,7 +16,7 @@ _LIB = None
 
 NKMER = 180
 SENS_SPEC, SPLIT_SCAFS = 0, 1
-LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0, 1
+LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR, LAYOUT_ROWMAJOR_MILLI32 = 0, 1, 2
 FEAT_TRUNC3, FEAT_RAW = 0, 1
 
 READ_DTYPE = np.dtype([("scaf", "<u4"), ("pos0", "<u4"), ("len", "<u4"), ("flag_nsnps", "<u4")])

@@ -78,7 +78,7 @@ struct LevelCtl {
 	uint32_t part_TT[4], part_tab_off[4], part_job_off[4];   // partition plans (scaffold list, elements, flip lists, SCG lists): tile-table entries and offsets
 	unsigned long long part_item_end[4];      // cumulative work items of the plans (item = (dimension, tile-table entry))
 	uint32_t next_id, nrec, level, done;
-	uint32_t error, sweep_launches, pad0, pad1;
+	uint32_t error, sweep_launches, ticks, done_at;   // ticks: levels executed, empty ones included; done_at: value of ticks after the level that ended the search
 	unsigned long long tickets[4];            // flip-prefix, sweep, partition
 	unsigned long long sweep_elements, partition_elements;
 };
@@ -86,6 +86,7 @@ struct LevelCtl {
 // what the host polls (mapped pinned memory): written by k_level_decide at the end of every level
 struct LevelProgress {
 	volatile uint32_t levels_done, done, nrec, error;
+	volatile uint32_t ticks, done_at, pad0, pad1;     // see LevelCtl; done_at is written before ticks
 };
 
 template <int STRATEGY>
@@ -1176,6 +1177,8 @@ struct ValSrc {
 __device__ __forceinline__ double val_at(const ValSrc& v, uint64_t dp, uint32_t d)
 {
 	const uint64_t r = v.rowidx? v.rowidx[dp] : dp;
+	if(v.layout == ABW_LAYOUT_ROWMAJOR_MILLI32)            // integer thousandths: the value is the double abawaca-build printed, int(1000 x) / 1000.0
+		return __ddiv_rn((double)reinterpret_cast<const uint32_t*>(v.p)[r * v.ld + d], 1000.0);
 	return (v.layout == ABW_LAYOUT_ROWMAJOR)? v.p[r * v.ld + d] : v.p[(uint64_t)d * v.ld + r];
 }
 
@@ -1443,11 +1446,16 @@ __global__ void __launch_bounds__(LV_THREADS) k_level_decide(const LevelBufs B, 
 		ctl->done = (Cn == 0 || ctl->done)? 1u : 0u;
 		if(Cn > B.Cmax)
 			ctl->error = 2;
+		ctl->ticks++;
+		if(ctl->done && !ctl->done_at)
+			ctl->done_at = ctl->ticks;
 		B.prog->nrec = ctl->nrec;
 		B.prog->error = ctl->error;
 		B.prog->done = ctl->done;
+		B.prog->done_at = ctl->done_at;
 		__threadfence_system();
 		B.prog->levels_done = ctl->level;
+		B.prog->ticks = ctl->ticks;
 		__threadfence_system();
 	}
 }
@@ -1855,7 +1863,7 @@ __global__ void __launch_bounds__(256) k_keys(const ValSrc v, uint64_t N, uint32
 	const uint32_t c0 = blockIdx.y * 32;
 	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 	bool bad = false, isnan = false;
-	const bool rowmajor = v.layout == ABW_LAYOUT_ROWMAJOR;
+	const bool rowmajor = v.layout != ABW_LAYOUT_COLMAJOR;
 #pragma unroll
 	for(int j = 0; j < 4; j++) {
 		// row-major: x runs over the dimensions of one datapoint; column-major: x runs over the datapoints of one dimension
@@ -1863,16 +1871,24 @@ __global__ void __launch_bounds__(256) k_keys(const ValSrc v, uint64_t N, uint32
 		const uint32_t c = rowmajor? c0 + tx : c0 + ty + 8 * j;
 		KeyT key = 0;
 		if(dp < N && c < nd) {
-			const double x = val_at(v, dp, d0 + c);
-			if(MILLI) {
-				const double k = rint(__dmul_rn(x, 1000.0));
-				const bool ok = (k > -2147483000.0) && (k < 2147483000.0) && (__ddiv_rn(k, 1000.0) == x);
-				bad |= !ok;
-				key = (KeyT)(ok? (uint32_t)((long long)k + 2147483648ll) : 0u);
+			if(MILLI && v.layout == ABW_LAYOUT_ROWMAJOR_MILLI32) {
+				// the matrix already holds the integers
+				const uint32_t u = reinterpret_cast<const uint32_t*>(v.p)[(v.rowidx? v.rowidx[dp] : dp) * v.ld + d0 + c];
+				bad |= u >= 2147483000u;
+				key = (KeyT)(u + 2147483648u);
 			}
 			else {
-				isnan |= x != x;
-				key = (KeyT)orderable(x);
+				const double x = val_at(v, dp, d0 + c);
+				if(MILLI) {
+					const double k = rint(__dmul_rn(x, 1000.0));
+					const bool ok = (k > -2147483000.0) && (k < 2147483000.0) && (__ddiv_rn(k, 1000.0) == x);
+					bad |= !ok;
+					key = (KeyT)(ok? (uint32_t)((long long)k + 2147483648ll) : 0u);
+				}
+				else {
+					isnan |= x != x;
+					key = (KeyT)orderable(x);
+				}
 			}
 		}
 		if(rowmajor)
@@ -2644,7 +2660,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 		ABW_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_prog, 256, cudaHostAllocMapped));
 	}
 	LevelProgress* const h_prog = reinterpret_cast<LevelProgress*>(ctx->h_prog);
-	h_prog->levels_done = 0; h_prog->done = 0; h_prog->nrec = 0; h_prog->error = 0;
+	h_prog->levels_done = 0; h_prog->done = 0; h_prog->nrec = 0; h_prog->error = 0; h_prog->ticks = 0; h_prog->done_at = 0;
 
 	// ---- root cluster and control block
 	{
@@ -2699,9 +2715,13 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 	const unsigned int g_sweep = (unsigned int)std::min<uint64_t>(items_max, (uint64_t)sms * 4), g_fp = (unsigned int)std::min<uint64_t>(std::max<uint64_t>(fp_items_max, 1), (uint64_t)sms * 4);
 	const unsigned int g_part = (unsigned int)std::min<uint64_t>(part_items_max, (uint64_t)sms * 3), g_small = sms * 4;
 
-	// levels the host may run ahead of the device.  A sharded search must make the same number of collective calls on every rank, so there every
-	// rank waits for the verdict of the level it has just enqueued (a poll of mapped memory, not a stream synchronisation) before it enqueues the next.
-	const uint32_t lead = (world > 1)? 1u : 6u;
+	// levels the host may run ahead of the device.  A sharded search must make the same number of collective calls on every rank, so there the decision
+	// to enqueue level l is a function of device state that is final when it is read: level l is enqueued iff the search had not ended by level
+	// l - lead (every rank waits until that level has been reported, then reads done_at, which is written once).  That enqueues lead - 1 empty levels
+	// (kernels that find no work, collectives over zeroes) after the last one, on every rank alike, and hides the host's round trip behind the
+	// kernels of lead - 1 levels.  ABW_SHARD_LEAD overrides (1 = wait for every level's verdict, the first formulation).
+	static const uint32_t shard_lead = [] { const char* e = getenv("ABW_SHARD_LEAD"); const int v = e? atoi(e) : 3; return (uint32_t)std::min(std::max(v, 1), 8); }();
+	const uint32_t lead = (world > 1)? shard_lead : 6u;
 	uint32_t lvl = 0;
 	bool finished = false;
 	int cur = 0;
@@ -2782,27 +2802,41 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 		lvl++;
 		// progress: stop as soon as the device has reported the last level; never run more than `lead` levels ahead of it
 		while(true) {
-			const uint32_t ld = h_prog->levels_done;            // written after `done`: a level that is reported has its verdict visible
-			__sync_synchronize();
-			if(h_prog->error) {
-				finished = true;
-				break;
+			if(world > 1) {
+				// deterministic on every rank: levels 0 .. lvl - lead must have been reported before level lvl is enqueued
+				if(lvl < lead)
+					break;
+				const uint32_t need = lvl - lead + 1, tk = h_prog->ticks;
+				__sync_synchronize();
+				if(tk >= need) {
+					const uint32_t da = h_prog->done_at;
+					finished = h_prog->error != 0 || (da != 0 && da <= need);
+					break;
+				}
 			}
-			if(ld >= lvl) {                                     // the level just enqueued has been decided
-				finished = h_prog->done != 0;
-				break;
+			else {
+				const uint32_t ld = h_prog->levels_done;        // written after `done`: a level that is reported has its verdict visible
+				__sync_synchronize();
+				if(h_prog->error) {
+					finished = true;
+					break;
+				}
+				if(ld >= lvl) {                                 // the level just enqueued has been decided
+					finished = h_prog->done != 0;
+					break;
+				}
+				if(h_prog->done) {                              // an earlier level was the last one: what was enqueued since is empty
+					finished = true;
+					break;
+				}
+				if(lvl - ld < lead)
+					break;
 			}
-			if(lead > 1 && h_prog->done) {                      // an earlier level was the last one: what was enqueued since is empty
-				finished = true;
-				break;
-			}
-			if(lvl - ld < lead)
-				break;
 			if(cudaStreamQuery(ctx->stream) == cudaSuccess) {
 				// the stream is idle although a level has not been reported: a kernel fault surfaces here
 				ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 				__sync_synchronize();
-				if(h_prog->levels_done < lvl && !h_prog->done)
+				if(h_prog->ticks < lvl && !h_prog->done)
 					return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run: internal error, the device stopped reporting levels");
 			}
 		}
@@ -2863,7 +2897,11 @@ int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, 
 		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: at most 2^31-1 datapoints and 2^27-1 scaffolds per device");
 	if(!h_row_of_dp)
 		nrows = N;
-	if(nrows < 1 || (layout == ABW_LAYOUT_COLMAJOR && ld < nrows) || (layout == ABW_LAYOUT_ROWMAJOR && ld < D))
+	if(layout != ABW_LAYOUT_COLMAJOR && layout != ABW_LAYOUT_ROWMAJOR && layout != ABW_LAYOUT_ROWMAJOR_MILLI32)
+		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: unknown layout");
+	if(layout == ABW_LAYOUT_ROWMAJOR_MILLI32 && !values_on_device)
+		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: a matrix of integer thousandths must be in device memory");
+	if(nrows < 1 || (layout == ABW_LAYOUT_COLMAJOR && ld < nrows) || (layout != ABW_LAYOUT_COLMAJOR && ld < D))
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: leading dimension too small");
 	ABW_ENTER(ctx);
 	abw_search* s = new abw_search();

@@ -108,6 +108,7 @@ class FeatureBuild:
         self.ctx, self.seqset, self.segs, self.d_rows, self.nseg, self.ncols, self.nscaf, self.d_nbps = ctx, seqset, segs, d_rows, nseg, ncols, nscaf, d_nbps
         self.nk = ncols if nk is None else nk              # k-mer columns; the remaining ncols - nk are coverage columns
         self._milli = None
+        self._milli32 = None
 
     def rows_milli(self, out16=None, out32=None, wait=True):
         """The .lrn matrix as integer thousandths (abw_rows_to_milli): uint16 [nseg][nk] k-mer columns and uint32 [nseg][ncols - nk] coverage columns,
@@ -134,8 +135,19 @@ class FeatureBuild:
 
     def milli_inexact(self):
         flag = np.zeros(4, dtype=np.int32)
-        self.ctx.to_host(flag, self._milli[2])
+        self.ctx.to_host(flag, (self._milli or self._milli32)[2])
         return int(flag[0])
+
+    def rows_milli32_device(self):
+        """Device pointer of the whole matrix as uint32 thousandths [nseg][ncols] (abw_rows_to_milli, bits = 32): what abw_search_create reads with
+        ABW_LAYOUT_ROWMAJOR_MILLI32, and what the ranks of a dimension-sharded search exchange instead of doubles.  Freed by close()."""
+        L, ctx = self.ctx.lib, self.ctx
+        if self._milli32 is None:
+            self._milli32 = (ctx.alloc(max(self.nseg * self.ncols, 1) * 4), None, ctx.alloc(16))
+        d32, _, dflag = self._milli32
+        ctx.memset(dflag, 0, 16)
+        ctx.check(L.abw_rows_to_milli(ctx.h, C.c_void_p(self.d_rows), self.nseg, self.ncols, 0, self.ncols, 32, C.c_void_p(d32), C.c_void_p(dflag)))
+        return d32
 
     def rows_milli_host(self):
         k16, k32 = self.rows_milli()
@@ -203,6 +215,11 @@ class FeatureBuild:
             for d in self._milli:
                 self.ctx.free(d)
             self._milli = None
+        if self._milli32 is not None:
+            for d in self._milli32:
+                if d:
+                    self.ctx.free(d)
+            self._milli32 = None
         if self.segs:
             L.abw_segments_destroy(self.segs)
             self.segs = None

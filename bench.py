@@ -347,15 +347,20 @@ def main():
     result_buffers = {}                                # records and bin arrays of the search, reused by every step
     dev = torch.device("cuda", local_rank)
 
-    def exchange(fb, counts, timings=None):
+    def exchange(fb, counts, timings=None, keep_doubles=False):
         """N > 1: the global scaffold table from all ranks' window counts, and this rank's block of columns of ALL datapoints (one NCCL all-to-all)."""
         t_x0 = time.perf_counter()
         # 1) windows per scaffold of every rank (the only per-scaffold quantity this step computed; lengths and SCG masks of all ranks were
         #    exchanged once at set-up): everybody derives the same global scaffold table, scaffold ids rank-major
-        cnt_local = torch.from_numpy(counts.astype(np.int32)).to(dev)
-        cnt_all = torch.empty(world * nscaf, dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(cnt_all, cnt_local)
-        cnt_all = cnt_all.cpu().numpy()
+        if state.get("h_cnt") is None:
+            state["h_cnt"] = (torch.empty(nscaf, dtype=torch.int32).pin_memory(), torch.empty(world * nscaf, dtype=torch.int32).pin_memory(),
+                              torch.empty(world * nscaf, dtype=torch.int32, device=dev))
+        h_cnt, h_cnt_all, cnt_all = state["h_cnt"]
+        h_cnt.numpy()[:] = counts
+        dist.all_gather_into_tensor(cnt_all, h_cnt.to(dev, non_blocking=True))
+        h_cnt_all.copy_(cnt_all, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        cnt_all = h_cnt_all.numpy().copy()
         if int(cnt_all.min()) >= 2:                                        # nothing to drop (every scaffold has two windows): no copies of the tables
             keep_all, T_all = slice(None), cnt_all.view(np.uint32)
             rows_per_rank = cnt_all.reshape(world, nscaf).sum(axis=1).tolist()
@@ -368,21 +373,25 @@ def main():
             t_x0 = time.perf_counter()
         # 2) every rank holds the rows of its own scaffolds and will search a block of COLUMNS of all datapoints: one all-to-all (NCCL) in which
         #    rank q receives from everybody the columns it owns -- 1/world of what an all-gather of whole rows would move
+        #    The columns travel as uint32 thousandths (abw_rows_to_milli; every value is int(1000 x) / 1000.0, abawaca-build.cpp:603): half the bytes of the
+        #    doubles, and abw_search_create reads them as they are (ABW_LAYOUT_ROWMAJOR_MILLI32).
         keep = np.repeat(counts >= 2, counts) if (counts < 2).any() else None
-        local = torch.as_tensor(distributed._DevArray(fb.d_rows, fb.nseg * fb.ncols * 8, "<f8", 8), device=dev).view(fb.nseg, fb.ncols)
+        local = torch.as_tensor(distributed._DevArray(state["d_milli32"], fb.nseg * fb.ncols * 4, "<i4", 4), device=dev).view(fb.nseg, fb.ncols)
+        local64 = torch.as_tensor(distributed._DevArray(fb.d_rows, fb.nseg * fb.ncols * 8, "<f8", 8), device=dev).view(fb.nseg, fb.ncols)   # verify_sharded only
         if keep is not None:
-            local = local[torch.from_numpy(np.nonzero(keep)[0]).to(dev)]
+            idx = torch.from_numpy(np.nonzero(keep)[0]).to(dev)
+            local, local64 = local[idx], (local64[idx] if keep_doubles else None)
         #    (round-robin: rank q owns the dimensions q, q + world, ... so that every rank gets the same mix of k-mer and coverage dimensions)
         ncol_of = [len(range(r, fb.ncols, world)) for r in range(world)]
         off, cnt = rank, ncol_of[rank]
         n_local = int(local.shape[0])
         send = torch.cat([local[:, r::world].reshape(-1) for r in range(world)])
-        full = torch.empty((sum(rows_per_rank), cnt), dtype=torch.float64, device=dev)
+        full = torch.empty((sum(rows_per_rank), cnt), dtype=torch.int32, device=dev)
         dist.all_to_all_single(full.view(-1), send, output_split_sizes=[n * cnt for n in rows_per_rank], input_split_sizes=[n_local * c for c in ncol_of])
         torch.cuda.synchronize(dev)
         if timings is not None:
             timings["exchange_columns_ms"] = 1000.0 * (time.perf_counter() - t_x0)
-        return dict(full=full, off=off, cnt=cnt, T_all=T_all, keep_all=keep_all, rows_per_rank=rows_per_rank, local=local)
+        return dict(full=full, off=off, cnt=cnt, T_all=T_all, keep_all=keep_all, rows_per_rank=rows_per_rank, local=local64)
 
     def step(resident, timings=None, on_features=None, keep_exchange=False):
         if resident:
@@ -393,6 +402,7 @@ def main():
             on_features()
         if world > 1:
             t_a = time.perf_counter()
+            state["d_milli32"] = fb.rows_milli32_device()                  # enqueued before the wait below: what the ranks exchange (exchange())
             counts = np.diff(fb.seg_first_host().astype(np.int64))         # windows per scaffold: the ranks exchange them (exchange())
             if timings is not None:
                 timings["segments_host_ms"] = 1000.0 * (time.perf_counter() - t_a)
@@ -414,10 +424,10 @@ def main():
             res, kept = pipeline.search_features(ctx, fb, lengths, masks, timings=timings, buffers=result_buffers)
             ndps_total = int(res.dp2cluster.size)
         else:
-            x = exchange(fb, counts, timings)
+            x = exchange(fb, counts, timings, keep_doubles=keep_exchange)
             # dimension-sharded search: this rank sweeps columns [off, off+cnt) of every datapoint
             res = pipeline.search(ctx, x["full"].data_ptr(), None, x["T_all"], lengths_all[x["keep_all"]], masks_all[x["keep_all"]],
-                                  layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=int(x["full"].shape[0]), D=x["cnt"], ld=x["cnt"], timings=timings,
+                                  layout=capi.LAYOUT_ROWMAJOR_MILLI32, values_on_device=True, nrows=int(x["full"].shape[0]), D=x["cnt"], ld=x["cnt"], timings=timings,
                                   collectives=coll, dim_offset=x["off"], dim_stride=world, D_total=fb.ncols, buffers=result_buffers)
             ndps_total = int(x["full"].shape[0])
             if keep_exchange:
@@ -425,6 +435,8 @@ def main():
             else:
                 del x
         nbins = int(np.count_nonzero(np.bincount(res.scaf2cluster)[1:]))
+        if world > 1 and fb.milli_inexact():
+            raise SystemExit("bench.py: a feature value is not a multiple of 0.001")
         if not resident:
             ctx.synchronize()                          # the matrix has arrived on the host (copy stream) before the step counts as done
             if fb.milli_inexact():

@@ -217,6 +217,9 @@ int abw_d2h_async(abw_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 
 #define ABW_LAYOUT_COLMAJOR 0  /* values[d * ld + dp] */
 #define ABW_LAYOUT_ROWMAJOR 1  /* values[dp * ld + d] (the .lrn layout written by abw_kmer_features/abw_coverage) */
+#define ABW_LAYOUT_ROWMAJOR_MILLI32 2  /* `values` points to uint32_t k[dp * ld + d] in DEVICE memory, the value being (double)k / 1000.0: what abw_rows_to_milli
+                                          (bits = 32) writes.  Every .lrn value is int(1000 x) / 1000.0 (abawaca-build.cpp:603), so nothing is lost; half the bytes
+                                          when ranks exchange feature columns (the dimension-sharded search of bench.py at N > 1) */
 
 /* Replaces ClusterData(lrn, scaf_db) + ScafDpData + SCGdb as the split search sees them (ClusterData.cpp:27,
  * ScafDpData.cpp:91-99, SCGdb.cpp:86-117): N datapoints x D dimensions, dp2scaf[N] (non-decreasing),

@@ -361,3 +361,38 @@ def test_search_from_features_equals_the_explicit_problem(ctx):
                          r.child1_ndps, r.child2_ndps, r.child1_nscafs, r.child2_nscafs, r.child1_raw, r.child2_raw, r.total_size, r.scg_unique, r.scg_avg)
         assert [key(r) for r in a.recs] == [key(r) for r in b.recs] and len(a.recs) > 1
         assert a.scaf2cluster.tolist() == b.scaf2cluster.tolist() and a.dp2cluster.tolist() == b.dp2cluster.tolist()
+
+
+def test_matrix_of_integer_thousandths_gives_the_same_search(ctx):
+    """ABW_LAYOUT_ROWMAJOR_MILLI32: the matrix as uint32 thousandths (abw_rows_to_milli) -- what the ranks of a dimension-sharded search exchange -- gives
+    the records of the search on the doubles, separating values included (value = k / 1000.0, the double abawaca-build prints, abawaca-build.cpp:603)."""
+    from abawaca_b200 import capi, pipeline, synth
+    for min_len, seed in ((1500, 41), (4000, 42)):          # with and without a row index
+        mg = synth.make_metagenome(1200, 3, 4, seed, min_len=min_len, mean_extra=3000)
+        fb = pipeline.build_features(ctx, mg.seq, mg.offsets, mg.reads, this_sample=0)
+        counts = np.diff(fb.seg_first_host().astype(np.int64))
+        keep, dp2scaf, T, kept = pipeline.search_problem_from_counts(counts)
+        length = np.diff(mg.offsets.astype(np.int64)).astype(np.uint64)[kept]
+        mask = mg.scg_masks()[kept]
+        p = capi.default_params()
+        p.min_reported_score = 0.0
+        rod = None if keep.all() else np.nonzero(keep)[0].astype(np.uint64)
+        a = pipeline.search(ctx, fb.d_rows, dp2scaf, T, length, mask, params=p, layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=fb.nseg,
+                            D=fb.ncols, ld=fb.ncols, row_of_dp=rod)
+        d32 = fb.rows_milli32_device()
+        assert fb.milli_inexact() == 0
+        b = pipeline.search(ctx, d32, dp2scaf, T, length, mask, params=p, layout=capi.LAYOUT_ROWMAJOR_MILLI32, values_on_device=True, nrows=fb.nseg,
+                            D=fb.ncols, ld=fb.ncols, row_of_dp=rod)
+        # a block of columns with a stride, as a rank of the sharded search holds them
+        c = pipeline.search(ctx, d32 + 4 * 5, dp2scaf, T, length, mask, params=p, layout=capi.LAYOUT_ROWMAJOR_MILLI32, values_on_device=True, nrows=fb.nseg,
+                            D=40, ld=fb.ncols, row_of_dp=rod)
+        c_ref = pipeline.search(ctx, fb.d_rows + 8 * 5, dp2scaf, T, length, mask, params=p, layout=capi.LAYOUT_ROWMAJOR, values_on_device=True, nrows=fb.nseg,
+                                D=40, ld=fb.ncols, row_of_dp=rod)
+        fb.close()
+        key = lambda r: (r.id, r.parent, r.ndps, r.nscafs, r.split, r.best.found, r.best.dim, r.best.value, r.best.a, r.best.b, r.child1, r.child2,   # noqa: E731
+                         r.child1_ndps, r.child2_ndps, r.child1_nscafs, r.child2_nscafs, r.child1_raw, r.child2_raw, r.total_size, r.scg_unique, r.scg_avg)
+        assert [key(r) for r in a.recs] == [key(r) for r in b.recs] and len(a.recs) > 1
+        assert a.scaf2cluster.tolist() == b.scaf2cluster.tolist() and a.dp2cluster.tolist() == b.dp2cluster.tolist()
+        assert [key(r) for r in c.recs] == [key(r) for r in c_ref.recs]
+    with pytest.raises(Exception):                          # a host matrix of integers is refused, not misread
+        pipeline.search(ctx, np.zeros((4, 2)), np.array([0, 0, 1, 1]), np.array([2, 2]), np.array([10, 10]), np.zeros((2, 1)), layout=capi.LAYOUT_ROWMAJOR_MILLI32)

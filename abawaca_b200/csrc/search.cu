@@ -2893,8 +2893,8 @@ int abw_search_create(abw_ctx* ctx, const double* values, int values_on_device, 
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create: empty problem");
 	if(W > SCG_WMAX)
 		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: at most 512 distinct SCG names (W <= 8)");
-	if(N >= (1ull << 31) || S >= (1u << EL_SCAF_BITS))
-		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: at most 2^31-1 datapoints and 2^27-1 scaffolds per device");
+	if(N >= (1ull << 28) || S >= (1u << EL_SCAF_BITS))       // the look-back words of the sweep carry two 28-bit counts (cnt_pack)
+		return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: at most 2^28-1 datapoints and 2^27-1 scaffolds per device");
 	if(!h_row_of_dp)
 		nrows = N;
 	if(layout != ABW_LAYOUT_COLMAJOR && layout != ABW_LAYOUT_ROWMAJOR && layout != ABW_LAYOUT_ROWMAJOR_MILLI32)
@@ -2973,8 +2973,8 @@ int abw_search_create_from_features(abw_ctx* ctx, const abw_segments* g, const d
 		const uint64_t S = h_tot[0], N = h_tot[1];
 		if(S == 0 || N == 0)
 			return abw_fail(ctx, ABW_ERR_ARG, "abw_search_create_from_features: no scaffold has two windows");
-		if(N >= (1ull << 31) || S >= (1u << EL_SCAF_BITS))
-			return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: at most 2^31-1 datapoints and 2^27-1 scaffolds per device");
+		if(N >= (1ull << 28) || S >= (1u << EL_SCAF_BITS))
+			return abw_fail(ctx, ABW_ERR_UNSUPPORTED, "abw_search_create: at most 2^28-1 datapoints and 2^27-1 scaffolds per device");
 		s->N = N; s->S = (uint32_t)S;
 		ABW_CUDA(ctx, d_T.alloc(S));
 		ABW_CUDA(ctx, d_len.alloc(S));

@@ -202,8 +202,36 @@ __global__ void __launch_bounds__(COV_THREADS, 4) k_cov_sum(const ReadSrc src, u
 			smin = min(smin, rd.scaf[j]);
 		if(!(rd.acc[j] && si[j].y > 0))
 			continue;
+		const uint32_t pos0 = rd.pos0[j], len = rd.len[j];
+		if(si[j].w == COV_REGULAR && pos0 < 0x7FF00000u && len - 1u < CS_MAX_OV - 1u) {
+			// the common case in 32-bit arithmetic and without a loop: a scaffold without N has the windows [q nb + 1, (q + 1) nb] (WinIter::init /
+			// next / overlap for COV_REGULAR, specialised; 1 <= len < 2^20 and pos0 < 2^31 - 2^20 keep every quantity below 2^32)
+			const uint32_t nb = si[j].z, cnt = si[j].y;
+			const uint32_t q = pos0? (pos0 - 1u) / nb : 0u;
+			const uint32_t st = q * nb + 1u, en = st + nb - 1u, e = pos0 + len - 1u;
+			if(q < cnt && e >= st) {
+				const uint32_t g = si[j].x + q;
+				g1[j] = g;
+				ov1[j] = min(e, en) - max(pos0, st) + 1u;
+				gmin = min(gmin, g);
+				gmax = max(gmax, g);
+				if(e > en && q + 1u < cnt) {
+					ov2[j] = min(e - en, nb);
+					gmax = max(gmax, g + 1u);
+					// a read longer than a window reaches further windows (rare)
+					uint32_t gg = g + 2u, stt = en + nb + 1u;
+					while(gg < si[j].x + cnt && e >= stt) {
+						atomicAdd(&sum_ov[gg], (unsigned long long)min(e - stt + 1u, nb));
+						gmax = max(gmax, gg);
+						gg++;
+						stt += nb;
+					}
+				}
+			}
+			continue;
+		}
 		WinIter it;
-		it.init(rd.pos0[j], rd.len[j], si[j], seg_end);
+		it.init(pos0, len, si[j], seg_end);
 		if(!it.valid())
 			continue;
 		g1[j] = it.g;

@@ -529,7 +529,7 @@ int abw_names_create(abw_ctx* ctx, const char* names_blob, const uint64_t* h_nam
 		if(blob_bytes)
 			ABW_CUDA(ctx, cudaMemcpyAsync(nm->blob.p, names_blob, blob_bytes, cudaMemcpyHostToDevice, ctx->stream));
 		ABW_CUDA(ctx, cudaMemcpyAsync(nm->off.p, h_name_off, sizeof(uint64_t) * ((size_t)nscaf + 1), cudaMemcpyHostToDevice, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_sync(ctx));
 		return ABW_OK;
 	}();
 	if(rc != ABW_OK) {
@@ -569,8 +569,8 @@ int abw_parse_sam(abw_ctx* ctx, const abw_names* names, const char* text, uint64
 	ABW_LAUNCH(ctx, k_sam_count_newlines, ntiles, LN_THREADS, 0, src, nbytes, tile_counts.p);
 	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, tile_counts.p, tile_offs.p, ntiles, total.p));
 	uint64_t nnl = 0;
-	ABW_CUDA(ctx, cudaMemcpyAsync(&nnl, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ABW_CUDA(ctx, abw_fetch(ctx, &nnl, total.p, sizeof(uint64_t)));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	const uint64_t nlines = nnl + 1;
 	ABW_CUDA(ctx, line_start.alloc(nlines));
 	ABW_CUDA(ctx, is_record.alloc(nlines));
@@ -579,8 +579,8 @@ int abw_parse_sam(abw_ctx* ctx, const abw_names* names, const char* text, uint64
 	ABW_LAUNCH(ctx, k_sam_is_record, abw_div_up(nlines, 256), 256, 0, src, nbytes, line_start.p, nlines, is_record.p);
 	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, is_record.p, rec_slot.p, nlines, total.p + 1));
 	uint64_t nrec = 0;
-	ABW_CUDA(ctx, cudaMemcpyAsync(&nrec, total.p + 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ABW_CUDA(ctx, abw_fetch(ctx, &nrec, total.p + 1, sizeof(uint64_t)));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	*nreads = nrec;
 	if(nrec > cap)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_parse_sam: the record buffer is too small for this chunk (nreads holds the number needed)");
@@ -589,8 +589,8 @@ int abw_parse_sam(abw_ctx* ctx, const abw_names* names, const char* text, uint64
 		           names->nslots, names->blob.p, names->off.p, d_reads, cap, d_err.p);
 	}
 	int h_err = 0;
-	ABW_CUDA(ctx, cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ABW_CUDA(ctx, abw_fetch(ctx, &h_err, d_err.p, sizeof(int)));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	if(h_err & SAM_ERR_LOWER_N)
 		return abw_fail(ctx, ABW_ERR_ILLEGAL_DNA, "Illegal_DNAString: lower-case 'n' in a read sequence (String.cpp:47-49)");
 	if(h_err & SAM_ERR_FEW_FIELDS)
@@ -629,8 +629,8 @@ int abw_fasta_scan(abw_ctx* ctx, const char* text, uint64_t nbytes, int text_on_
 		ABW_LAUNCH(ctx, k_sam_count_newlines, ntiles, LN_THREADS, 0, f->d_text, nbytes, tile_counts.p);
 		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, tile_counts.p, tile_offs.p, ntiles, total.p));
 		uint64_t nnl = 0;
-		ABW_CUDA(ctx, cudaMemcpyAsync(&nnl, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, &nnl, total.p, sizeof(uint64_t)));
+		ABW_CUDA(ctx, abw_sync(ctx));
 		const uint64_t nlines = nnl + 1;
 		f->nlines = nlines;
 		ABW_CUDA(ctx, line_start.alloc(nlines));
@@ -646,8 +646,8 @@ int abw_fasta_scan(abw_ctx* ctx, const char* text, uint64_t nbytes, int text_on_
 		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, is_header.p, f->hdr_before.p, nlines, total.p + 1));
 		ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, f->line_len.p, f->chars_before.p, nlines, total.p + 2));
 		uint64_t tot[2] = {0, 0};
-		ABW_CUDA(ctx, cudaMemcpyAsync(tot, total.p + 1, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, tot, total.p + 1, 2 * sizeof(uint64_t)));
+		ABW_CUDA(ctx, abw_sync(ctx));
 		const uint64_t nrec = tot[0], nchars = tot[1];
 		f->nrec = nrec;
 		ABW_CUDA(ctx, f->rec_id_off.alloc(nrec));
@@ -657,10 +657,10 @@ int abw_fasta_scan(abw_ctx* ctx, const char* text, uint64_t nbytes, int text_on_
 		           f->rec_id_off.p, f->rec_id_len.p, f->rec_chars0.p, d_err.p);
 		ABW_CUDA(ctx, cudaMemcpyAsync(f->rec_chars0.p + nrec, &nchars, sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
 		int h_err = 0;
-		ABW_CUDA(ctx, cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, &h_err, d_err.p, sizeof(int)));
 		std::vector<uint64_t> c0(nrec + 1);
-		ABW_CUDA(ctx, cudaMemcpyAsync(c0.data(), f->rec_chars0.p, sizeof(uint64_t) * (nrec + 1), cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, c0.data(), f->rec_chars0.p, sizeof(uint64_t) * (nrec + 1)));
+		ABW_CUDA(ctx, abw_sync(ctx));
 		if(h_err)
 			return abw_fail(ctx, ABW_ERR_ARG, "Bad_file: was expecting a header line for the next sequence in a fasta file but got something else (SeqIORead_fasta.h:58-62)");
 		f->h_seq_len.resize(nrec);
@@ -688,10 +688,10 @@ int abw_fasta_get(abw_ctx* ctx, const abw_fasta* f, uint64_t* h_id_off, uint32_t
 	if(f->nrec == 0)
 		return ABW_OK;
 	if(h_id_off)
-		ABW_CUDA(ctx, cudaMemcpyAsync(h_id_off, f->rec_id_off.p, sizeof(uint64_t) * f->nrec, cudaMemcpyDeviceToHost, ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, h_id_off, f->rec_id_off.p, sizeof(uint64_t) * f->nrec));
 	if(h_id_len)
-		ABW_CUDA(ctx, cudaMemcpyAsync(h_id_len, f->rec_id_len.p, sizeof(uint32_t) * f->nrec, cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, h_id_len, f->rec_id_len.p, sizeof(uint32_t) * f->nrec));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	if(h_seq_len)
 		memcpy(h_seq_len, f->h_seq_len.data(), sizeof(uint64_t) * f->nrec);
 	return ABW_OK;
@@ -720,7 +720,7 @@ int abw_fasta_pack(abw_ctx* ctx, const abw_fasta* f, const uint32_t* h_order, ui
 		const unsigned int blocks = (unsigned int)std::min<uint64_t>(abw_div_up(f->nlines * 32, 256), (uint64_t)ctx->sm_count * 16);
 		ABW_LAUNCH(ctx, k_fa_copy, blocks, 256, 0, f->d_text, f->line_a.p, f->line_len.p, f->hdr_before.p, f->chars_before.p, f->nlines, f->rec_chars0.p, d_dst.p, ascii.p);
 	}
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // rec_dst is a local
+	ABW_CUDA(ctx, abw_sync(ctx));      // rec_dst is a local
 	return abw_pack_sequences(ctx, ascii.p, 1, offsets.data(), nout, out);
 }
 
@@ -756,8 +756,8 @@ int abw_parse_lrn(abw_ctx* ctx, const char* text, uint64_t nbytes, int text_on_d
 	ABW_LAUNCH(ctx, k_sam_count_newlines, ntiles, LN_THREADS, 0, src, nbytes, tile_counts.p);
 	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, tile_counts.p, tile_offs.p, ntiles, total.p));
 	uint64_t nnl = 0;
-	ABW_CUDA(ctx, cudaMemcpyAsync(&nnl, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ABW_CUDA(ctx, abw_fetch(ctx, &nnl, total.p, sizeof(uint64_t)));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	const uint64_t nlines = nnl + 1;
 	ABW_CUDA(ctx, line_start.alloc(nlines));
 	ABW_CUDA(ctx, is_row.alloc(nlines));
@@ -766,8 +766,8 @@ int abw_parse_lrn(abw_ctx* ctx, const char* text, uint64_t nbytes, int text_on_d
 	ABW_LAUNCH(ctx, k_lrn_is_row, abw_div_up(nlines, 256), 256, 0, src, nbytes, line_start.p, nlines, is_row.p);
 	ABW_CHECK(abw_exclusive_scan_u32_to_u64(ctx, is_row.p, row_slot.p, nlines, total.p + 1));
 	uint64_t nr = 0;
-	ABW_CUDA(ctx, cudaMemcpyAsync(&nr, total.p + 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ABW_CUDA(ctx, abw_fetch(ctx, &nr, total.p + 1, sizeof(uint64_t)));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	*nrows = nr;
 	if(nr > cap_rows)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_parse_lrn: more data lines than the caller made room for (nrows holds the number found)");
@@ -777,9 +777,9 @@ int abw_parse_lrn(abw_ctx* ctx, const char* text, uint64_t nbytes, int text_on_d
 	           fb_count.p, d_err.p);
 	int h_err = 0;
 	uint32_t h_fb = 0;
-	ABW_CUDA(ctx, cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaMemcpyAsync(&h_fb, fb_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-	ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ABW_CUDA(ctx, abw_fetch(ctx, &h_err, d_err.p, sizeof(int)));
+	ABW_CUDA(ctx, abw_fetch(ctx, &h_fb, fb_count.p, sizeof(uint32_t)));
+	ABW_CUDA(ctx, abw_sync(ctx));
 	if(h_err & LRN_ERR_FIELDS)
 		return abw_fail(ctx, ABW_ERR_ARG, "abw_parse_lrn: a data line does not have the expected number of tab-separated fields (ClusterData.cpp:137-141)");
 	if(h_fb > fb_cap)
@@ -787,8 +787,8 @@ int abw_parse_lrn(abw_ctx* ctx, const char* text, uint64_t nbytes, int text_on_d
 	if(h_fb > 0) {
 		// values that need full strtod (more than 19 digits, exponents beyond +-22, inf/nan, hexadecimal): converted on the host with the C library, as atof does
 		std::vector<LrnFallback> h(h_fb);
-		ABW_CUDA(ctx, cudaMemcpyAsync(h.data(), fb.p, sizeof(LrnFallback) * h_fb, cudaMemcpyDeviceToHost, ctx->stream));
-		ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ABW_CUDA(ctx, abw_fetch(ctx, h.data(), fb.p, sizeof(LrnFallback) * h_fb));
+		ABW_CUDA(ctx, abw_sync(ctx));
 		std::vector<char> tmp;
 		for(const LrnFallback& f : h) {
 			tmp.assign((size_t)f.len + 1, 0);
@@ -798,7 +798,7 @@ int abw_parse_lrn(abw_ctx* ctx, const char* text, uint64_t nbytes, int text_on_d
 				memcpy(tmp.data(), text + f.off, f.len);
 			const double v = atof(tmp.data());
 			ABW_CUDA(ctx, cudaMemcpyAsync(d_values + f.row * D + f.col, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-			ABW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			ABW_CUDA(ctx, abw_sync(ctx));
 		}
 	}
 	return ABW_OK;

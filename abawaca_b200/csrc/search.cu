@@ -87,6 +87,7 @@ struct LevelCtl {
 struct LevelProgress {
 	volatile uint32_t levels_done, done, nrec, error;
 	volatile uint32_t ticks, done_at, pad0, pad1;     // see LevelCtl; done_at is written before ticks
+	volatile uint32_t c_next[16];                     // c_next[t & 15]: clusters of the level that follows the t-th executed level (t = 0, 1, ...)
 };
 
 template <int STRATEGY>
@@ -484,7 +485,10 @@ constexpr int FP_TILE = SW_THREADS * FP_ITEMS;
 // The per-scaffold records of a tile are staged in shared memory (coalesced list reads, the gathers of all eight entries of a thread in flight,
 // 16-byte slots swizzled so that both the strided stores and the blocked loads are conflict free) instead of living in registers across the
 // scan and the look-back: 40 registers instead of 128, six CTAs per SM instead of two.
-__global__ void __launch_bounds__(SW_THREADS, 4) k_flip_prefix(const uint32_t* __restrict__ flip_list, uint64_t Sf, const LevelCluster* __restrict__ clusters, uint32_t D,
+#ifndef ABW_FLIP_CTAS
+#define ABW_FLIP_CTAS 5
+#endif
+__global__ void __launch_bounds__(SW_THREADS, ABW_FLIP_CTAS) k_flip_prefix(const uint32_t* __restrict__ flip_list, uint64_t Sf, const LevelCluster* __restrict__ clusters, uint32_t D,
                                                               LevelCtl* __restrict__ ctl, const uint2* __restrict__ ftile_tab, const uint4* __restrict__ frow,
                                                               uint32_t epoch, uint32_t* __restrict__ status, AggSlot* __restrict__ aggs,
                                                               AggSlot* __restrict__ prefixes, uint2* __restrict__ F8, uint32_t* __restrict__ FC, uint32_t* __restrict__ scg_k,
@@ -597,7 +601,10 @@ __global__ void __launch_bounds__(SW_THREADS, 4) k_flip_prefix(const uint32_t* _
 	}
 }
 
-__global__ void __launch_bounds__(SW_THREADS, 4) k_sweep_ss(const uint32_t* __restrict__ E, uint64_t N, const LevelCluster* __restrict__ clusters, uint32_t D,
+#ifndef ABW_SWEEP_CTAS
+#define ABW_SWEEP_CTAS 6
+#endif
+__global__ void __launch_bounds__(SW_THREADS, ABW_SWEEP_CTAS) k_sweep_ss(const uint32_t* __restrict__ E, uint64_t N, const LevelCluster* __restrict__ clusters, uint32_t D,
                                                            LevelCtl* __restrict__ ctl, const uint2* __restrict__ tile_tab, const uint2* __restrict__ F8,
                                                            const uint32_t* __restrict__ FC, const uint32_t* __restrict__ scg_k, uint64_t Kstride,
                                                            const uint2* __restrict__ klohi, uint32_t Cstride, uint64_t Sf, const uint8_t* __restrict__ pass_tab,
@@ -1446,6 +1453,7 @@ __global__ void __launch_bounds__(LV_THREADS) k_level_decide(const LevelBufs B, 
 		ctl->done = (Cn == 0 || ctl->done)? 1u : 0u;
 		if(Cn > B.Cmax)
 			ctl->error = 2;
+		B.prog->c_next[ctl->ticks & 15u] = ctl->C;
 		ctl->ticks++;
 		if(ctl->done && !ctl->done_at)
 			ctl->done_at = ctl->ticks;
@@ -1612,7 +1620,12 @@ struct PartPlans {
 	uint64_t        stride[4];
 };
 
-__global__ void __launch_bounds__(SW_THREADS, 3) k_partition2(const PartPlans plans, LevelCtl* __restrict__ ctl, const PartJob* __restrict__ jobs_all,
+// resident CTAs per SM of the three look-back kernels, measured on B200 (cfg2, 13 levels; registers are capped accordingly and a few values spill):
+//   k_partition2 3 -> 4: 1625 -> 1500 us;  k_sweep_ss 4 -> 5 -> 6: 1222 -> 1159 -> 1135 us;  k_flip_prefix 4 -> 5 -> 6: 1150 -> 1088 -> 1217 us
+#ifndef ABW_PART_CTAS
+#define ABW_PART_CTAS 4
+#endif
+__global__ void __launch_bounds__(SW_THREADS, ABW_PART_CTAS) k_partition2(const PartPlans plans, LevelCtl* __restrict__ ctl, const PartJob* __restrict__ jobs_all,
                                                              const uint2* __restrict__ tab_all, const uint8_t* __restrict__ side, const uint8_t* __restrict__ new_assigned,
                                                              uint8_t* __restrict__ assigned, uint32_t epoch, unsigned long long* __restrict__ lookback)
 {
@@ -2712,8 +2725,8 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 
 	// grids: CTAs walk the work items of a level, whatever their number turns out to be
 	const unsigned int sms = (unsigned int)ctx->sm_count;
-	const unsigned int g_sweep = (unsigned int)std::min<uint64_t>(items_max, (uint64_t)sms * 4), g_fp = (unsigned int)std::min<uint64_t>(std::max<uint64_t>(fp_items_max, 1), (uint64_t)sms * 4);
-	const unsigned int g_part = (unsigned int)std::min<uint64_t>(part_items_max, (uint64_t)sms * 3), g_small = sms * 4;
+	const unsigned int g_sweep = (unsigned int)std::min<uint64_t>(items_max, (uint64_t)sms * ABW_SWEEP_CTAS), g_fp = (unsigned int)std::min<uint64_t>(std::max<uint64_t>(fp_items_max, 1), (uint64_t)sms * ABW_FLIP_CTAS);
+	const unsigned int g_part = (unsigned int)std::min<uint64_t>(part_items_max, (uint64_t)sms * ABW_PART_CTAS), g_small = sms * 4;
 
 	// levels the host may run ahead of the device.  A sharded search must make the same number of collective calls on every rank, so there the decision
 	// to enqueue level l is a function of device state that is final when it is read: level l is enqueued iff the search had not ended by level
@@ -2723,6 +2736,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 	static const uint32_t shard_lead = [] { const char* e = getenv("ABW_SHARD_LEAD"); const int v = e? atoi(e) : 3; return (uint32_t)std::min(std::max(v, 1), 8); }();
 	const uint32_t lead = (world > 1)? shard_lead : 6u;
 	uint32_t lvl = 0;
+	uint64_t Cb_seen = ~0ull;
 	bool finished = false;
 	int cur = 0;
 	const uint32_t max_levels = s->max_levels;
@@ -2735,8 +2749,9 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 			// the packed look-back words hold 6 bits of the epoch: clear them before an epoch can repeat
 			ABW_CUDA(ctx, cudaMemsetAsync(d_lookback.p, 0, sizeof(unsigned long long) * lb_words, ctx->stream));
 		}
-		// at level l there are at most 2^l clusters: the host-known bound for the collectives of a sharded search
-		const uint32_t Cb = (uint32_t)std::min<uint64_t>(Cmax, (lvl < 31)? (1ull << lvl) : Cmax);
+		// at level l there are at most 2^l clusters, and at most 2^(lead-1) times those of the last level whose verdict every rank has waited for:
+		// the host-known bound for the collectives of a sharded search (the same on every rank)
+		const uint32_t Cb = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(Cmax, Cb_seen), (lvl < 31)? (1ull << lvl) : Cmax);
 		ChildStats* const d_stats = reinterpret_cast<ChildStats*>(s->xchg.p + 2 * s8);
 		unsigned long long* const d_value_key = s->xchg.p + 2 * s8 + (size_t)Cb * 2 * stat_words;
 		uint64_t* const d_child_never = reinterpret_cast<uint64_t*>(d_value_key + Cb);
@@ -2811,6 +2826,8 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 				if(tk >= need) {
 					const uint32_t da = h_prog->done_at;
 					finished = h_prog->error != 0 || (da != 0 && da <= need);
+					// clusters of level `need` (written once, by the level before it), doubled for every level enqueued since
+					Cb_seen = (uint64_t)h_prog->c_next[(need - 1) & 15u] << (lvl - need);
 					break;
 				}
 			}

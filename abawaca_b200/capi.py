@@ -72,7 +72,8 @@ EXPORTS = [
     "abw_segments_count", "abw_segments_get", "abw_segments_get_async", "abw_kmer_features", "abw_coverage", "abw_coverage_batch", "abw_rows_to_milli", "abw_device_alloc", "abw_device_free",
     "abw_copy_to_device", "abw_copy_to_host", "abw_memset_device", "abw_h2d_async", "abw_wait_h2d", "abw_d2h_async", "abw_search_create", "abw_search_create_from_features", "abw_search_destroy", "abw_search_run",
     "abw_search_set_shard", "abw_search_set_shard_strided", "abw_search_set_max_levels", "abw_search_run_sharded", "abw_search_get_profile", "abw_cluster_scg",
-    "abw_names_create", "abw_names_destroy", "abw_parse_sam", "abw_fasta_scan", "abw_fasta_destroy", "abw_fasta_count", "abw_fasta_get", "abw_fasta_pack", "abw_nccl_unique_id", "abw_nccl_collectives_create", "abw_nccl_collectives_destroy", "abw_parse_lrn", "abw_search_set_scaffold_stats",
+    "abw_names_create", "abw_names_destroy", "abw_parse_sam", "abw_fasta_scan", "abw_fasta_destroy", "abw_fasta_count", "abw_fasta_get", "abw_fasta_pack", "abw_nccl_unique_id", "abw_nccl_collectives_create", "abw_nccl_collectives_destroy", "abw_peer_buffer_create", "abw_peer_buffer_destroy", "abw_peer_group_create", "abw_peer_group_destroy",
+    "abw_scatter_columns_milli", "abw_parse_lrn", "abw_search_set_scaffold_stats",
 ]
 
 
@@ -144,6 +145,12 @@ def load():
     L.abw_nccl_unique_id.argtypes = [C.c_void_p, C.c_void_p]
     L.abw_nccl_collectives_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.abw_nccl_collectives_destroy.argtypes = [C.c_void_p]
+    L.abw_peer_buffer_create.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+    L.abw_peer_buffer_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    L.abw_peer_group_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.abw_peer_group_destroy.argtypes = [C.c_void_p]
+    L.abw_peer_group_destroy.restype = None
+    L.abw_scatter_columns_milli.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_size_t, C.c_void_p]
     L.abw_parse_lrn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.abw_search_set_scaffold_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.abw_cluster_scg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_double)]

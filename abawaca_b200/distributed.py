@@ -119,6 +119,67 @@ class NcclCollectives:
             self.ctx.lib.abw_nccl_collectives_destroy(C.byref(self.struct))
 
 
+class PeerExchange:
+    """The column exchange between the feature stage and the dimension-sharded search over NVLink peer memory (csrc/peer.cu): every rank owns one
+    exchange buffer (two halves, used alternately), exported through CUDA IPC and mapped by all other ranks; scatter() converts the local rows to integer
+    thousandths and stores every rank's columns (rank, rank + world, ...) straight into that rank's buffer, and barrier() -- a one-word stream-ordered
+    all-reduce of the search's own collectives -- tells the receivers that everybody's rows have arrived.
+    ok is False when CUDA IPC is not available on some rank (decided collectively): the caller keeps its NCCL all-to-all."""
+
+    def __init__(self, ctx, torch, dist, device_index, half_bytes, coll):
+        self.ctx, self.torch, self.dist, self.coll = ctx, torch, dist, coll
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.dev = torch.device("cuda", device_index)
+        self.half_bytes = (int(half_bytes) + 255) & ~255
+        self.buf = C.c_void_p()
+        self.group = C.c_void_p()
+        self.parity = 0
+        handle = (C.c_ubyte * 64)()
+        rc = ctx.lib.abw_peer_buffer_create(ctx.h, 2 * self.half_bytes, C.byref(self.buf), handle)
+        self.why = "" if rc == 0 else "abw_peer_buffer_create: " + ctx.lib.abw_last_error(ctx.h).decode()
+        mine = torch.tensor(list(bytes(handle)) + [1 if rc == 0 else 0], dtype=torch.uint8, device=self.dev)
+        everybody = torch.empty(self.world * 65, dtype=torch.uint8, device=self.dev)
+        dist.all_gather_into_tensor(everybody, mine)
+        everybody = everybody.cpu().numpy().reshape(self.world, 65)
+        ok = bool(everybody[:, 64].all())
+        if ok:
+            handles = np.ascontiguousarray(everybody[:, :64]).tobytes()
+            ok = ctx.lib.abw_peer_group_create(ctx.h, self.buf, handles, self.rank, self.world, C.byref(self.group)) == 0
+            if not ok:
+                self.why = "abw_peer_group_create: " + ctx.lib.abw_last_error(ctx.h).decode()
+        verdict = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(verdict, op=dist.ReduceOp.MIN)
+        self.ok = bool(int(verdict.item()))
+        self.word = ctx.alloc(64)
+        ctx.memset(self.word, 0, 64)
+        if not self.ok:
+            import sys
+            print(f"PeerExchange (rank {self.rank}): peer memory is not available, {self.why or 'another rank failed'}", file=sys.stderr, flush=True)
+            self.close()
+
+    def scatter(self, d_rows, nrows, ld, ncols, row0, d_inexact=None, segs=None):
+        """enqueue the scatter of this rank's rows into the current half of everybody's buffer; returns the device pointer of MY matrix in that half.
+        segs (the abw_segments the rows belong to): rows of scaffolds with a single window are left out; row0 counts kept rows."""
+        off = self.parity * self.half_bytes
+        self.ctx.check(self.ctx.lib.abw_scatter_columns_milli(self.ctx.h, self.group, segs, C.c_void_p(d_rows), nrows, ld, ncols, row0, off, C.c_void_p(d_inexact or 0)))
+        self.parity ^= 1
+        return self.buf.value + off
+
+    def barrier(self):
+        """stream ordered: what follows on the context stream sees the stores of every rank's scatter that was enqueued before its barrier"""
+        st = self.coll.struct
+        if st.allreduce_sum_i64(st.user, self.word, 1) != 0:
+            raise RuntimeError("PeerExchange.barrier: the collective failed")
+
+    def close(self):
+        if self.group:
+            self.ctx.lib.abw_peer_group_destroy(self.group)
+            self.group = C.c_void_p()
+        if self.buf:
+            self.ctx.lib.abw_peer_buffer_destroy(self.ctx.h, self.buf)
+            self.buf = C.c_void_p()
+
+
 def allgather_rows(torch, dist, local_rows, counts):
     """local_rows: device tensor [n_local][ncols] (float64); counts: rows per rank.  Returns [sum(counts)][ncols] on every rank."""
     world = len(counts)

@@ -373,27 +373,60 @@ def main():
         if timings is not None:
             timings["exchange_tables_ms"] = 1000.0 * (time.perf_counter() - t_x0)
             t_x0 = time.perf_counter()
-        # 2) every rank holds the rows of its own scaffolds and will search a block of COLUMNS of all datapoints: one all-to-all (NCCL) in which
-        #    rank q receives from everybody the columns it owns -- 1/world of what an all-gather of whole rows would move
-        #    The columns travel as uint32 thousandths (abw_rows_to_milli; every value is int(1000 x) / 1000.0, abawaca-build.cpp:603): half the bytes of the
-        #    doubles, and abw_search_create reads them as they are (ABW_LAYOUT_ROWMAJOR_MILLI32).
-        keep = np.repeat(counts >= 2, counts) if (counts < 2).any() else None
-        local = torch.as_tensor(distributed._DevArray(state["d_milli32"], fb.nseg * fb.ncols * 4, "<i4", 4), device=dev).view(fb.nseg, fb.ncols)
-        local64 = torch.as_tensor(distributed._DevArray(fb.d_rows, fb.nseg * fb.ncols * 8, "<f8", 8), device=dev).view(fb.nseg, fb.ncols)   # verify_sharded only
-        if keep is not None:
-            idx = torch.from_numpy(np.nonzero(keep)[0]).to(dev)
-            local, local64 = local[idx], (local64[idx] if keep_doubles else None)
-        #    (round-robin: rank q owns the dimensions q, q + world, ... so that every rank gets the same mix of k-mer and coverage dimensions)
+        # 2) every rank holds the rows of its own scaffolds and will search a block of COLUMNS of all datapoints (round-robin: rank q owns the dimensions
+        #    q, q + world, ... so that every rank gets the same mix of k-mer and coverage dimensions).  The columns travel as uint32
+        #    thousandths (every value is int(1000 x) / 1000.0, abawaca-build.cpp:603): half the bytes of the doubles, and abw_search_create reads them as
+        #    they are (ABW_LAYOUT_ROWMAJOR_MILLI32).
         ncol_of = [len(range(r, fb.ncols, world)) for r in range(world)]
         off, cnt = rank, ncol_of[rank]
-        n_local = int(local.shape[0])
-        send = torch.cat([local[:, r::world].reshape(-1) for r in range(world)])
-        full = torch.empty((sum(rows_per_rank), cnt), dtype=torch.int32, device=dev)
-        dist.all_to_all_single(full.view(-1), send, output_split_sizes=[n * cnt for n in rows_per_rank], input_split_sizes=[n_local * c for c in ncol_of])
-        torch.cuda.synchronize(dev)
+        total_rows = int(sum(rows_per_rank))
+        local64 = torch.as_tensor(distributed._DevArray(fb.d_rows, fb.nseg * fb.ncols * 8, "<f8", 8), device=dev).view(fb.nseg, fb.ncols)   # verify_sharded only
+        keep = np.repeat(counts >= 2, counts) if (counts < 2).any() else None
+        idx = torch.from_numpy(np.nonzero(keep)[0]).to(dev) if keep is not None else None
+        if keep_doubles and idx is not None:
+            local64 = local64[idx]
+        use_peer = not os.environ.get("ABW_NO_PEER") and coll is not None and getattr(coll.struct, "stream_ordered", 0)
+        if os.environ.get("ABW_BENCH_DEBUG") and rank == 0:
+            print("exchange: use_peer", bool(use_peer), "stream_ordered", getattr(coll.struct, "stream_ordered", None), file=sys.stderr, flush=True)
+        if use_peer:
+            # 2a) over NVLink peer memory (csrc/peer.cu): ONE kernel converts the local rows and stores every rank's columns straight into that rank's
+            #     matrix (rows of scaffolds with a single window are left out on the way, ScafDpData.cpp:92-93); a one-word all-reduce on the context
+            #     stream tells the receivers that everybody's rows have arrived.  Decided by global quantities only (buffer size from the global row
+            #     count): every rank takes the same branch.
+            need = total_rows * max(ncol_of) * 4
+            px = state.get("peer")
+            if px is None or (px.ok and px.half_bytes < need):
+                if px is not None:
+                    ctx.synchronize()
+                    px.close()
+                px = state["peer"] = distributed.PeerExchange(ctx, torch, dist, local_rank, int(need * 1.1) + 65536, coll)
+            use_peer = px.ok
+        if use_peer:
+            if state.get("px_flag") is None:
+                state["px_flag"] = ctx.alloc(16)
+                ctx.memset(state["px_flag"], 0, 16)
+            full_ptr = px.scatter(fb.d_rows, fb.nseg, fb.ncols, fb.ncols, int(sum(rows_per_rank[:rank])), d_inexact=state["px_flag"], segs=fb.segs)
+            px.barrier()
+            full = None
+        else:
+            # 2b) one NCCL all-to-all in which rank q receives from everybody the columns it owns -- 1/world of what an all-gather of whole rows would move
+            d32 = fb.rows_milli32_device()
+            ctx.synchronize()
+            local = torch.as_tensor(distributed._DevArray(d32, fb.nseg * fb.ncols * 4, "<i4", 4), device=dev).view(fb.nseg, fb.ncols)
+            if idx is not None:
+                local = local[idx]
+            n_local = int(local.shape[0])
+            send = torch.cat([local[:, r::world].reshape(-1) for r in range(world)])
+            full = torch.empty((total_rows, cnt), dtype=torch.int32, device=dev)
+            dist.all_to_all_single(full.view(-1), send, output_split_sizes=[n * cnt for n in rows_per_rank], input_split_sizes=[n_local * c for c in ncol_of])
+            torch.cuda.synchronize(dev)
+            full_ptr = full.data_ptr()
         if timings is not None:
+            if use_peer:
+                ctx.synchronize()
             timings["exchange_columns_ms"] = 1000.0 * (time.perf_counter() - t_x0)
-        return dict(full=full, off=off, cnt=cnt, T_all=T_all, keep_all=keep_all, rows_per_rank=rows_per_rank, local=local64)
+        state["exchange_path"] = "peer memory (abw_scatter_columns_milli)" if use_peer else "NCCL all-to-all"
+        return dict(full=full, full_ptr=full_ptr, total_rows=total_rows, off=off, cnt=cnt, T_all=T_all, keep_all=keep_all, rows_per_rank=rows_per_rank, local=local64)
 
     def step(resident, timings=None, on_features=None, keep_exchange=False):
         if resident:
@@ -404,7 +437,6 @@ def main():
             on_features()
         if world > 1:
             t_a = time.perf_counter()
-            state["d_milli32"] = fb.rows_milli32_device()                  # enqueued before the wait below: what the ranks exchange (exchange())
             counts = np.diff(fb.seg_first_host().astype(np.int64))         # windows per scaffold: the ranks exchange them (exchange())
             if timings is not None:
                 timings["segments_host_ms"] = 1000.0 * (time.perf_counter() - t_a)
@@ -429,18 +461,22 @@ def main():
             x = exchange(fb, counts, timings, keep_doubles=keep_exchange)
             # dimension-sharded search: this rank sweeps columns [off, off+cnt) of every datapoint
             all_kept = isinstance(x["keep_all"], slice)
-            res = pipeline.search(ctx, x["full"].data_ptr(), None, x["T_all"], lengths_all if all_kept else lengths_all[x["keep_all"]],
+            res = pipeline.search(ctx, x["full_ptr"], None, x["T_all"], lengths_all if all_kept else lengths_all[x["keep_all"]],
                                   masks_all if all_kept else masks_all[x["keep_all"]],
-                                  layout=capi.LAYOUT_ROWMAJOR_MILLI32, values_on_device=True, nrows=int(x["full"].shape[0]), D=x["cnt"], ld=x["cnt"], timings=timings,
+                                  layout=capi.LAYOUT_ROWMAJOR_MILLI32, values_on_device=True, nrows=x["total_rows"], D=x["cnt"], ld=x["cnt"], timings=timings,
                                   collectives=coll, dim_offset=x["off"], dim_stride=world, D_total=fb.ncols, buffers=result_buffers)
-            ndps_total = int(x["full"].shape[0])
+            ndps_total = x["total_rows"]
             if keep_exchange:
                 state["exchange"] = x
             else:
                 del x
         nbins = int(np.count_nonzero(np.bincount(res.scaf2cluster)[1:]))
-        if world > 1 and fb.milli_inexact():
-            raise SystemExit("bench.py: a feature value is not a multiple of 0.001")
+        if world > 1:
+            inexact = np.zeros(4, dtype=np.int32)
+            if state.get("px_flag") is not None:
+                ctx.to_host(inexact, state["px_flag"])
+            if int(inexact[0]) or (fb._milli32 is not None and fb.milli_inexact()):
+                raise SystemExit("bench.py: a feature value is not a multiple of 0.001")
         if not resident:
             ctx.synchronize()                          # the matrix has arrived on the host (copy stream) before the step counts as done
             if fb.milli_inexact():
@@ -635,7 +671,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/int64/f64", "data": "synthetic",
             "config": {"workload": workload_name(w), "per_gpu": f"{nscaf} scaffolds, {total_bp} bp, {state['nseg']} windows x {state['ncols']} dimensions, {sum(nreads)} read records",
-                       "parallelism": (f"one community of {world} x {nscaf} scaffolds: scaffold-sharded feature build, NCCL all-to-all of feature columns, "
+                       "parallelism": (f"one community of {world} x {nscaf} scaffolds: scaffold-sharded feature build, feature columns exchanged as uint32 thousandths over {state.get('exchange_path', 'NCCL all-to-all')}, "
                                        f"dimension-sharded split search ({state['ncols']} dimensions over {world} ranks)") if world > 1 else "1 GPU",
                        "l2": "inputs (assembly + read records, > 2 GB) are larger than the 126 MB L2; no explicit flush",
                        "e2e_inputs": "pinned host buffers: ASCII assembly + 8-byte read records of the reads that pass the host-side filter (abw_read8), one length per sample",
@@ -695,6 +731,10 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     if coll is not None and hasattr(coll, "close"):
+        if state.get("peer") is not None:
+            ctx.synchronize()
+            dist.barrier()                              # nobody unmaps a buffer another rank may still be writing to
+            state["peer"].close()
         coll.close()
     ctx.close()
     if world > 1:

@@ -308,6 +308,29 @@ int  abw_nccl_unique_id(abw_ctx* ctx, void* id128);
 int  abw_nccl_collectives_create(abw_ctx* ctx, const void* id128, int rank, int world, abw_collectives* out);
 void abw_nccl_collectives_destroy(abw_collectives* c);
 
+/* ---- column exchange between the ranks over NVLink peer memory (CUDA IPC; one process per GPU on one node) --------------------------------
+ * Between the scaffold-sharded feature build and the dimension-sharded search every rank needs its columns (rank, rank + world, ...) of
+ * everybody's rows.  Each rank allocates one exchange buffer and exports it; abw_peer_group_create maps the buffers of all ranks; then
+ * abw_scatter_columns_milli reads the local rows once and stores, for every rank q, the integer thousandths (see abw_rows_to_milli) of q's columns
+ * straight into q's buffer: q's matrix is uint32 [total rows][cnt(q)] at byte offset buf_offset_bytes of its buffer, cnt(q) = number of columns
+ * c < ncols with c % world == q, and this rank's rows start at row row0 of it (row0 = rows of the ranks before it).  With `segs` (the windows the
+ * rows belong to, one row per window) the rows of scaffolds with a single window are left out, as ScafDpData drops them (ScafDpData.cpp:92-93) and as
+ * abw_search_create_from_features does; row0 then counts kept rows; NULL: every row is sent.  Conversion, column split and
+ * transfer are one kernel on the context stream.  The receiver may read its buffer (abw_search_create, ABW_LAYOUT_ROWMAJOR_MILLI32, ld = cnt(q)) once
+ * every rank's kernel has completed: order it with any stream-ordered collective of all ranks (a one-word abw_collectives.allreduce_sum_i64 will do),
+ * and alternate between two halves of the buffer so that a rank that is a step ahead does not overwrite what a slower one still reads.
+ * *d_inexact (device int32, may be NULL) is incremented when a value is not an exact multiple of 0.001 in [0, 2^31 / 1000).
+ * ABW_ERR_UNSUPPORTED when CUDA IPC is not available (the caller then exchanges the columns with its own all-to-all). */
+#define ABW_IPC_HANDLE_BYTES 64
+typedef struct abw_peer_group abw_peer_group;
+int  abw_peer_buffer_create(abw_ctx* ctx, size_t bytes, void** d_buf, unsigned char* handle64);
+int  abw_peer_buffer_destroy(abw_ctx* ctx, void* d_buf);
+int  abw_peer_group_create(abw_ctx* ctx, void* d_own, const unsigned char* handles /* [world][ABW_IPC_HANDLE_BYTES], entry `rank` is ignored */, int rank, int world,
+                           abw_peer_group** out);
+void abw_peer_group_destroy(abw_peer_group* g);
+int  abw_scatter_columns_milli(abw_ctx* ctx, const abw_peer_group* g, const abw_segments* segs, const double* d_rows, uint64_t nrows, uint64_t ld, uint32_t ncols,
+                               uint64_t row0, size_t buf_offset_bytes, int32_t* d_inexact);
+
 /* Per-scaffold G+C fraction and coverage (ScafDpData::Seq::get_gc / get_cvg, the .info columns), host arrays [S]: the terminal records then
  * carry the summary.txt statistics ClusterQuality::gc and ClusterQuality::cvg compute.  Call between abw_search_create and abw_search_run. */
 int abw_search_set_scaffold_stats(abw_ctx* ctx, abw_search* s, const double* h_gc, const double* h_cvg);

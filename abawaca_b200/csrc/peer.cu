@@ -49,6 +49,10 @@ __global__ void __launch_bounds__(PX_THREADS) k_scatter_columns(const double* __
 {
 	extern __shared__ uint32_t tile[];         // [PX_ROWS][ncols]
 	__shared__ unsigned long long dst_row[PX_ROWS];
+	__shared__ double milli[1001];             // k / 1000.0 for the k-mer frequencies (k <= 1000): the exactness test without a division per value
+	for(uint32_t k = threadIdx.x; k <= 1000; k += PX_THREADS)
+		milli[k] = __ddiv_rn((double)k, 1000.0);
+	__syncthreads();
 	bool bad = false;
 	for(uint64_t t0 = (uint64_t)blockIdx.x * PX_ROWS; t0 < nrows; t0 += (uint64_t)gridDim.x * PX_ROWS) {
 		const uint32_t nr = (uint32_t)min((uint64_t)PX_ROWS, nrows - t0);
@@ -66,7 +70,9 @@ __global__ void __launch_bounds__(PX_THREADS) k_scatter_columns(const double* __
 			const uint32_t r = i / ncols, c = i - r * ncols;
 			const double v = rows[(t0 + r) * ld + c];
 			const double k = rint(__dmul_rn(v, 1000.0));
-			const bool ok = (k >= 0.0) && (k < 2147483000.0) && (__ddiv_rn(k, 1000.0) == v) && !(v == 0.0 && signbit(v));
+			bool ok = (k >= 0.0) && (k < 2147483000.0) && !(v == 0.0 && signbit(v));
+			if(ok)
+				ok = (k <= 1000.0)? (milli[(uint32_t)k] == v) : (__ddiv_rn(k, 1000.0) == v);
 			tile[i] = ok? (uint32_t)k : 0u;
 			bad |= !ok;
 		}

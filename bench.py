@@ -100,13 +100,16 @@ def workload_args(args):
         w["n_samples"] = args.samples
     if args.genomes:
         w["n_genomes"] = args.genomes
+    if getattr(args, "coverage_scale", 1.0) != 1.0:    # thinned reads for the large shapes (the host generator is the limit, not the GPU)
+        w["cov_lo"], w["cov_hi"] = 0.5 * args.coverage_scale, 16.0 * args.coverage_scale
     return w
 
 
 def workload_name(w):
     base = "BASELINE.json configs[1]: 50k scaffolds, 10 samples, feature build + split search" if (w["n_scaffolds"], w["n_samples"]) == (50000, 10) \
-        else "variant of configs[1]"
-    return f"{base} ({w['n_scaffolds']} scaffolds, {w['n_samples']} samples, {w['n_genomes']} synthetic genomes, seed {w['seed']})"
+        and "cov_lo" not in w else "variant of configs[1]"
+    thin = f", read depth x {w['cov_hi'] / 16.0:g}" if "cov_lo" in w else ""
+    return f"{base} ({w['n_scaffolds']} scaffolds, {w['n_samples']} samples, {w['n_genomes']} synthetic genomes, seed {w['seed']}{thin})"
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -264,6 +267,7 @@ def main():
     ap.add_argument("--scaffolds", type=int, default=0)
     ap.add_argument("--samples", type=int, default=0)
     ap.add_argument("--genomes", type=int, default=0)
+    ap.add_argument("--coverage-scale", type=float, default=1.0, help="multiplies the read depth of the synthetic samples (large shapes: thinned reads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the one-off comparison of the sharded search with the single-rank search")
     args = ap.parse_args()

@@ -385,10 +385,14 @@ def main():
         off, cnt = rank, ncol_of[rank]
         total_rows = int(sum(rows_per_rank))
         local64 = torch.as_tensor(distributed._DevArray(fb.d_rows, fb.nseg * fb.ncols * 8, "<f8", 8), device=dev).view(fb.nseg, fb.ncols)   # verify_sharded only
-        keep = np.repeat(counts >= 2, counts) if (counts < 2).any() else None
-        idx = torch.from_numpy(np.nonzero(keep)[0]).to(dev) if keep is not None else None
-        if keep_doubles and idx is not None:
-            local64 = local64[idx]
+        def kept_rows():                                   # device index of the rows of the scaffolds that keep their windows (None: all); only the
+            if not (counts < 2).any():                     # NCCL path and the one-off verification need it -- the peer kernel drops rows itself
+                return None
+            return torch.from_numpy(np.nonzero(np.repeat(counts >= 2, counts))[0]).to(dev)
+        if keep_doubles:
+            idx = kept_rows()
+            if idx is not None:
+                local64 = local64[idx]
         use_peer = not os.environ.get("ABW_NO_PEER") and coll is not None and getattr(coll.struct, "stream_ordered", 0)
         if os.environ.get("ABW_BENCH_DEBUG") and rank == 0:
             print("exchange: use_peer", bool(use_peer), "stream_ordered", getattr(coll.struct, "stream_ordered", None), file=sys.stderr, flush=True)
@@ -417,6 +421,7 @@ def main():
             d32 = fb.rows_milli32_device()
             ctx.synchronize()
             local = torch.as_tensor(distributed._DevArray(d32, fb.nseg * fb.ncols * 4, "<i4", 4), device=dev).view(fb.nseg, fb.ncols)
+            idx = kept_rows()
             if idx is not None:
                 local = local[idx]
             n_local = int(local.shape[0])
@@ -464,9 +469,15 @@ def main():
         else:
             x = exchange(fb, counts, timings, keep_doubles=keep_exchange)
             # dimension-sharded search: this rank sweeps columns [off, off+cnt) of every datapoint
-            all_kept = isinstance(x["keep_all"], slice)
-            res = pipeline.search(ctx, x["full_ptr"], None, x["T_all"], lengths_all if all_kept else lengths_all[x["keep_all"]],
-                                  masks_all if all_kept else masks_all[x["keep_all"]],
+            if isinstance(x["keep_all"], slice):
+                len_kept, mask_kept = lengths_all, masks_all
+            else:
+                # lengths and SCG masks of the kept scaffolds: inputs, so the (pinned) subsets are reused as long as the step drops the same scaffolds
+                kc = state.get("kept_cache")
+                if kc is None or not np.array_equal(kc[0], x["keep_all"]):
+                    kc = state["kept_cache"] = (x["keep_all"].copy(), pinned_np(lengths_all[x["keep_all"]]), pinned_np(masks_all[x["keep_all"]]))
+                len_kept, mask_kept = kc[1], kc[2]
+            res = pipeline.search(ctx, x["full_ptr"], None, x["T_all"], len_kept, mask_kept,
                                   layout=capi.LAYOUT_ROWMAJOR_MILLI32, values_on_device=True, nrows=x["total_rows"], D=x["cnt"], ld=x["cnt"], timings=timings,
                                   collectives=coll, dim_offset=x["off"], dim_stride=world, D_total=fb.ncols, buffers=result_buffers)
             ndps_total = x["total_rows"]

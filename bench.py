@@ -367,13 +367,18 @@ def main():
         h_cnt_all.copy_(cnt_all, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         cnt_all = h_cnt_all.numpy()                                        # pinned, overwritten by the next step's exchange (the search of this step is over by then)
-        if int(cnt_all.min()) >= 2:                                        # nothing to drop (every scaffold has two windows): no copies of the tables
-            keep_all, T_all = slice(None), cnt_all.view(np.uint32)
-            rows_per_rank = cnt_all.reshape(world, nscaf).sum(axis=1).tolist()
+        memo = state.get("tables_memo")
+        if memo is not None and np.array_equal(memo[0], cnt_all):         # the tables are a pure function of the counts: same counts, same tables
+            keep_all, T_all, rows_per_rank = memo[1], memo[2], memo[3]
         else:
-            keep_all = cnt_all >= 2                                        # ScafDpData.cpp:92-93
-            T_all = cnt_all[keep_all].astype(np.uint32)
-            rows_per_rank = np.where(keep_all, cnt_all, 0).reshape(world, nscaf).sum(axis=1).tolist()
+            if int(cnt_all.min()) >= 2:                                    # nothing to drop (every scaffold has two windows): no copies of the tables
+                keep_all, T_all = slice(None), cnt_all.view(np.uint32).copy()
+                rows_per_rank = cnt_all.reshape(world, nscaf).sum(axis=1).tolist()
+            else:
+                keep_all = cnt_all >= 2                                    # ScafDpData.cpp:92-93
+                T_all = cnt_all[keep_all].astype(np.uint32)
+                rows_per_rank = np.where(keep_all, cnt_all, 0).reshape(world, nscaf).sum(axis=1).tolist()
+            state["tables_memo"] = (cnt_all.copy(), keep_all, T_all, rows_per_rank)
         if timings is not None:
             timings["exchange_tables_ms"] = 1000.0 * (time.perf_counter() - t_x0)
             t_x0 = time.perf_counter()
@@ -474,8 +479,8 @@ def main():
             else:
                 # lengths and SCG masks of the kept scaffolds: inputs, so the (pinned) subsets are reused as long as the step drops the same scaffolds
                 kc = state.get("kept_cache")
-                if kc is None or not np.array_equal(kc[0], x["keep_all"]):
-                    kc = state["kept_cache"] = (x["keep_all"].copy(), pinned_np(lengths_all[x["keep_all"]]), pinned_np(masks_all[x["keep_all"]]))
+                if kc is None or not (kc[0] is x["keep_all"] or np.array_equal(kc[0], x["keep_all"])):
+                    kc = state["kept_cache"] = (x["keep_all"], pinned_np(lengths_all[x["keep_all"]]), pinned_np(masks_all[x["keep_all"]]))
                 len_kept, mask_kept = kc[1], kc[2]
             res = pipeline.search(ctx, x["full_ptr"], None, x["T_all"], len_kept, mask_kept,
                                   layout=capi.LAYOUT_ROWMAJOR_MILLI32, values_on_device=True, nrows=x["total_rows"], D=x["cnt"], ld=x["cnt"], timings=timings,

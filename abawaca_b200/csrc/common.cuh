@@ -13,6 +13,8 @@ struct abw_ctx {
 	int          device = 0;
 	cudaStream_t stream = nullptr;
 	cudaStream_t copy_stream = nullptr;       // host->device staging that overlaps kernels of `stream` (abw_h2d_async)
+	cudaStream_t side_stream = nullptr;       // kernels of a search level that nothing on `stream` waits for until a later level (search.cu: k_finalize_terminal)
+	cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
 	std::vector<cudaEvent_t> copy_events;     // events of the tickets copy_retired + 1 ... (abw_h2d_async)
 	uint64_t     copy_retired = 0;            // tickets retired by abw_ctx_synchronize so far
 	int          sm_count = 148;

@@ -376,6 +376,12 @@ void abw_ctx_destroy(abw_ctx* ctx)
 	ctx->scan_scratch = nullptr;
 	for(cudaEvent_t e : ctx->copy_events)
 		cudaEventDestroy(e);
+	if(ctx->side_stream) {
+		cudaStreamSynchronize(ctx->side_stream);
+		cudaStreamDestroy(ctx->side_stream);
+		cudaEventDestroy(ctx->ev_fork);
+		cudaEventDestroy(ctx->ev_join);
+	}
 	if(ctx->copy_stream)
 		cudaStreamDestroy(ctx->copy_stream);
 	if(ctx->stream)

@@ -2735,6 +2735,28 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 	// kernels of lead - 1 levels.  ABW_SHARD_LEAD overrides (1 = wait for every level's verdict, the first formulation).
 	static const uint32_t shard_lead = [] { const char* e = getenv("ABW_SHARD_LEAD"); const int v = e? atoi(e) : 3; return (uint32_t)std::min(std::max(v, 1), 8); }();
 	const uint32_t lead = (world > 1)? shard_lead : 6u;
+	// side stream for k_finalize_terminal (not while kernels are timed one by one); its destructor makes the main stream wait, so that no buffer of this
+	// call returns to the block cache while a side kernel may still use it
+	struct SideStream {
+		abw_ctx* ctx;
+		bool on = false, pending = false;
+		cudaError_t join()
+		{
+			if(!pending)
+				return cudaSuccess;
+			pending = false;
+			return cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+		}
+		~SideStream() { join(); }
+	} side{ctx};
+	if(!ctx->profiling && !getenv("ABW_NO_SIDE_STREAM")) {
+		if(!ctx->side_stream) {
+			ABW_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+			ABW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+			ABW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+		}
+		side.on = true;
+	}
 	uint32_t lvl = 0;
 	uint64_t Cb_seen = ~0ull;
 	bool finished = false;
@@ -2798,10 +2820,25 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 				return abw_fail(ctx, ABW_ERR_CUDA, "abw_search_run_sharded: allreduce callback failed");
 		}
 		const uint32_t pd0 = 1, pd1 = last_level? 0u : D, pd2 = (!last_level && ss && Sf > 0)? D : 0u, pd3 = (!last_level && ss && K > 0)? D : 0u;
+		ABW_CUDA(ctx, side.join());                            // k_finalize_terminal of the previous level (side stream) has to be through with the job tables
 		ABW_LAUNCH(ctx, k_level_decide, 1, LV_THREADS, 0, B, cur, s->strategy, prm, D, W, s->dim_offset, pd0, pd1, pd2, pd3, last_level? 0 : 1, d_stats, d_value_key,
 		           d_child_never);
-		ABW_LAUNCH(ctx, k_finalize_terminal, g_small, 128, 0, s->scaf_list[cur].p, B, s->rows.p, s->assigned.p, s->scgmask.p, W, s->scaf_member.p, s->scaf_final.p,
-		           (const double*)s->x_gc.p, (const double*)s->x_cvg.p);
+		if(side.on) {
+			// the terminal clusters of this level are finished beside the partition: nothing on the main stream reads what k_finalize_terminal writes
+			// (bins, tallies, fields of the terminal records) or overwrites what it reads (job tables of the level, scaffold list [cur], the `assigned`
+			// bytes of terminal clusters' scaffolds -- the partition commits those of SPLIT clusters) before k_level_decide of the NEXT level, which waits
+			ABW_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+			ABW_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+			k_finalize_terminal<<<g_small, 128, 0, ctx->side_stream>>>(s->scaf_list[cur].p, B, s->rows.p, s->assigned.p, s->scgmask.p, W, s->scaf_member.p, s->scaf_final.p,
+			                                                            (const double*)s->x_gc.p, (const double*)s->x_cvg.p);
+			ctx->launches++;
+			ABW_CUDA(ctx, cudaGetLastError());
+			ABW_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+			side.pending = true;
+		}
+		else
+			ABW_LAUNCH(ctx, k_finalize_terminal, g_small, 128, 0, s->scaf_list[cur].p, B, s->rows.p, s->assigned.p, s->scgmask.p, W, s->scaf_member.p, s->scaf_final.p,
+			           (const double*)s->x_gc.p, (const double*)s->x_cvg.p);
 		s->prof.other_ms += tm.stop();
 		tm.start();
 		{
@@ -2858,6 +2895,7 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 			}
 		}
 	}
+	ABW_CUDA(ctx, side.join());
 	ABW_CUDA(ctx, abw_sync(ctx));
 	LevelCtl h_ctl;
 	ABW_CUDA(ctx, abw_fetch(ctx, &h_ctl, d_ctl.p, sizeof(h_ctl)));

@@ -15,7 +15,6 @@ struct abw_peer_group {
 	abw_ctx* ctx = nullptr;
 	int rank = 0, world = 0;
 	std::vector<void*> base;                   // base[q]: rank q's buffer in this process's address space (own pointer for q == rank)
-	void** d_base = nullptr;                   // the same table in device memory
 };
 
 namespace {

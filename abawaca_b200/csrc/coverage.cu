@@ -143,6 +143,28 @@ struct WinIter {
 	}
 };
 
+// The common case of WinIter in 32-bit arithmetic and without a loop: a read of 1 <= len < 2^20 bases at pos0 < 2^31 - 2^20 on a scaffold without N
+// (windows [q nb + 1, (q + 1) nb]) that reaches at most two windows.  Returns false when the general walk is needed; else ov1 (0: the read counts for
+// no window) belongs to window g and ov2 (0: none) to window g + 1.
+__device__ __forceinline__ bool regular_two(const uint4 si, uint32_t pos0, uint32_t len, uint32_t& g, uint32_t& ov1, uint32_t& ov2)
+{
+	g = 0; ov1 = 0; ov2 = 0;
+	if(!(si.w == COV_REGULAR && pos0 < 0x7FF00000u && len - 1u < (1u << 20) - 1u))
+		return false;
+	const uint32_t nb = si.z, cnt = si.y;
+	const uint32_t q = pos0? (pos0 - 1u) / nb : 0u;
+	const uint32_t st = q * nb + 1u, en = st + nb - 1u, e = pos0 + len - 1u;
+	if(!(q < cnt && e >= st))
+		return true;
+	if(e > en + nb && q + 2u < cnt)
+		return false;                                           // a third window: rare, left to the general walk
+	g = si.x + q;
+	ov1 = min(e, en) - max(pos0, st) + 1u;
+	if(e > en && q + 1u < cnt)
+		ov2 = min(e - en, nb);
+	return true;
+}
+
 // dst[key] += v for the lanes with `valid`, one atomic per distinct key of the warp.  Every lane of the warp calls it.  (Used where it runs once per
 // thread; in the hot loop of k_cov_sum the per-group reduction of a non-uniform mask compiles to a loop over the groups and was the bottleneck.)
 __device__ __forceinline__ void warp_add_by_key(unsigned long long* __restrict__ dst, uint32_t key, uint32_t v, bool valid)
@@ -428,6 +450,14 @@ __global__ void __launch_bounds__(COV_THREADS) k_cov_pairs(const ReadSrc* __rest
 		for(int j = 0; j < COV_ITEMS; j++) {
 			if(!(rd.acc[j] && si[j].y > 0))
 				continue;
+			uint32_t g, o1, o2;
+			if(regular_two(si[j], rd.pos0[j], rd.len[j], g, o1, o2)) {
+				if(o1 && (ALL || ((__ldg(flags + (g >> 5)) >> (g & 31u)) & 1u)))
+					c++;
+				if(o2 && (ALL || ((__ldg(flags + ((g + 1u) >> 5)) >> ((g + 1u) & 31u)) & 1u)))
+					c++;
+				continue;
+			}
 			WinIter it;
 			it.init(rd.pos0[j], rd.len[j], si[j], seg_end);
 			for(; it.valid(); it.next())
@@ -473,6 +503,20 @@ __global__ void __launch_bounds__(COV_THREADS) k_cov_pairs(const ReadSrc* __rest
 		for(int j = 0; j < COV_ITEMS; j++) {
 			if(!(rd.acc[j] && si[j].y > 0))
 				continue;
+			uint32_t g, o1, o2;
+			if(regular_two(si[j], rd.pos0[j], rd.len[j], g, o1, o2)) {
+				if(o1 && (ALL || ((__ldg(flags + (g >> 5)) >> (g & 31u)) & 1u))) {
+					keys[o] = key0 + g;
+					vals[o] = o1;
+					o++;
+				}
+				if(o2 && (ALL || ((__ldg(flags + ((g + 1u) >> 5)) >> ((g + 1u) & 31u)) & 1u))) {
+					keys[o] = key0 + g + 1u;
+					vals[o] = o2;
+					o++;
+				}
+				continue;
+			}
 			WinIter it;
 			it.init(rd.pos0[j], rd.len[j], si[j], seg_end);
 			for(; it.valid(); it.next())

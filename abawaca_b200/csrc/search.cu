@@ -790,19 +790,21 @@ __global__ void __launch_bounds__(SW_THREADS, ABW_SWEEP_CTAS) k_sweep_ss(const u
 
 // best candidate of every cluster over its (dimension, tile) items: the reference's total order
 // (score, then lowest dimension, then lowest value; ...Specificity.cpp:137-140 under the mutex, ClusterSeparator.cpp:11-16)
+constexpr int RB_THREADS = 1024;       // one CTA per cluster: the first levels have few clusters with thousands of candidates each (level 0 of cfg2: 5292), so the
+                                       // time of this kernel is the number of dependent load rounds per thread (256 threads: 22 us at level 0)
 template <int STRATEGY>
-__global__ void __launch_bounds__(256) k_reduce_best(const CandRec* __restrict__ per_item, uint32_t D, const LevelCtl* __restrict__ ctl,
+__global__ void __launch_bounds__(RB_THREADS) k_reduce_best(const CandRec* __restrict__ per_item, uint32_t D, const LevelCtl* __restrict__ ctl,
                                                     const LevelCluster* __restrict__ clusters, uint32_t dim_offset, uint32_t dim_stride, CandRec* __restrict__ out)
 {
-	__shared__ CandRec sm[256];
+	__shared__ CandRec sm[RB_THREADS];
 	const uint32_t C = ctl->C, TT = ctl->TT;
 	for(uint32_t c = blockIdx.x; c < C; c += gridDim.x) {
 		const uint32_t tiles = (clusters[c].d.n + SW_TILE - 1) / SW_TILE, tile0 = clusters[c].d.tile0;
 		CandRec best;
 		best.found = 0; best.k1 = best.k2 = 0; best.p = 0; best.i0 = best.i1 = best.i2 = 0; best.dim0 = 0;
-		const uint64_t total = (uint64_t)D * tiles;
-		for(uint64_t i = threadIdx.x; i < total; i += blockDim.x) {
-			const uint32_t d = (uint32_t)(i / tiles), t = (uint32_t)(i - (uint64_t)d * tiles);
+		const uint32_t total = D * tiles;                     // below 2^31: abw_search_run checks the number of (dimension, tile) items of a level
+		for(uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+			const uint32_t d = i / tiles, t = i - d * tiles;
 			CandRec x = per_item[(uint64_t)d * TT + tile0 + t];
 			x.dim0 = d;
 			if(cand_better<STRATEGY>(x, best))
@@ -2798,9 +2800,9 @@ int search_run(abw_ctx* ctx, abw_search* s, const abw_collectives* coll, abw_clu
 		s->prof.sweep_ms += tm.stop();
 		tm.start();
 		if(ss)
-			ABW_LAUNCH(ctx, k_reduce_best<ABW_SENS_SPEC>, g_small, 256, 0, d_cand.p, D, d_ctl.p, d_cl[cur].p, s->dim_offset, s->dim_stride, d_best.p);
+			ABW_LAUNCH(ctx, k_reduce_best<ABW_SENS_SPEC>, g_small, RB_THREADS, 0, d_cand.p, D, d_ctl.p, d_cl[cur].p, s->dim_offset, s->dim_stride, d_best.p);
 		else
-			ABW_LAUNCH(ctx, k_reduce_best<ABW_SPLIT_SCAFS>, g_small, 256, 0, d_cand.p, D, d_ctl.p, d_cl[cur].p, s->dim_offset, s->dim_stride, d_best.p);
+			ABW_LAUNCH(ctx, k_reduce_best<ABW_SPLIT_SCAFS>, g_small, RB_THREADS, 0, d_cand.p, D, d_ctl.p, d_cl[cur].p, s->dim_offset, s->dim_stride, d_best.p);
 		if(world > 1) {
 			// the per-rank best of every cluster, gathered; k_level_jobs applies the same total order on every rank
 			if(!ordered)

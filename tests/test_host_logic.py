@@ -69,3 +69,27 @@ def test_launch_shares_of_the_committed_launch_list(tmp_path):
     assert "launches," in out.splitlines()[0] and "| k_partition2 | 13 |" in out and "| k_sweep_ss | 13 |" in out
     shares = [float(l.split("|")[4]) for l in out.splitlines() if l.startswith("| k_")]
     assert 0.95 < sum(shares) < 1.02                        # shares are printed with three decimals
+
+
+def test_run_ahead_rule_of_the_sharded_search_enqueues_the_same_levels_on_every_rank():
+    """The rule of abw_search_run_sharded (csrc/search.cu): level l is enqueued iff the search had not ended by level l - lead, decided only after
+    level l - lead has been reported.  Restated here and driven with ranks that observe the device's progress words (ticks, done_at) at arbitrary
+    moments: whatever the timing, every rank enqueues exactly (index of the last level) + lead levels, so the collective counts match."""
+    rng = np.random.default_rng(7)
+
+    def levels_enqueued(last_level, lead, observe):
+        # device: level i completes at time i + 1 (ticks = i + 1); done_at = last_level + 1 from then on
+        lvl = 0
+        while True:
+            lvl += 1                                            # level lvl - 1 has just been enqueued
+            if lvl < lead:
+                continue
+            need = lvl - lead + 1
+            t = max(observe(), need)                            # the host polls until ticks >= need; it may look later than that
+            done_at = last_level + 1 if t >= last_level + 1 else 0
+            if done_at != 0 and done_at <= need:
+                return lvl
+    for lead in (1, 2, 3, 5, 8):
+        for last_level in (0, 1, 2, 7, 12, 30):
+            counts = {levels_enqueued(last_level, lead, lambda: int(rng.integers(0, 50))) for _ in range(200)}
+            assert counts == {last_level + lead}, (lead, last_level, counts)
